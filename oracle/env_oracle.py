@@ -1,0 +1,486 @@
+"""CPU restatement (numpy, fp32) of the *environment half* of the hot path.
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
+leg; never by hcr_genesis_lr_cl_b200.  Pinned against golden vectors recorded from the reference's own
+Python code (tools/make_golden.py -> tests/golden/*.npz, checked in tests/test_env_oracle_golden.py).
+
+Each method cites the reference lines it restates:
+    pre_step            LeggedRobot._pre_sim_step            legged_robot.py:230-252
+                        GenesisSimulator.step (last_* copy)  genesis_simulator.py:21-24
+    pd_torque           _compute_torques                     genesis_simulator.py:630-642
+    post_step           LeggedRobot.post_physics_step        legged_robot.py:55-76
+      _sim_post         GenesisSimulator.post_physics_step   genesis_simulator.py:35-60
+      _heights          _update_surrounding_heights          genesis_simulator.py:552-577
+      _feet_terrain     _calc_terrain_info_around_feet       genesis_simulator.py:579-610
+      _callback         _post_physics_step_callback          legged_robot.py:300-315 (+ push 150-158)
+      _termination      check_termination                    legged_robot.py:78-92
+      _reward           compute_reward + _reward_*           legged_robot.py:150-168,458-608; go2_ts.py:133-176
+      _reset            reset_idx and what it calls          legged_robot.py:94-148,254-298,317-334;
+                                                             go2_ts.py:75-96; genesis_simulator.py:62-148,665-739;
+                                                             legged_robot_ts.py:120-125
+      _observe          compute_observations                 go2.py:40-90, go2_ts.py:5-84
+Random draws come from oracle/philox.py keyed (seed, step, env, site, idx) -- see SURVEY section 8d.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from hcr_genesis_lr_cl_b200 import task_spec as T  # data format (TaskSpec, site ids) only
+from oracle import philox
+
+f32 = np.float32
+
+
+def _rot_inv(q, v):
+    """quat_rotate_inverse, q xyzw (math_utils.py:63-76)."""
+    w = q[:, 3:4]
+    qv = q[:, :3]
+    a = v * (f32(2.0) * w * w - f32(1.0))
+    b = np.cross(qv, v) * (f32(2.0) * w)
+    c = qv * (f32(2.0) * np.sum(qv * v, axis=1, keepdims=True, dtype=f32))
+    return (a - b + c).astype(f32)
+
+
+def _quat_apply(q, v):
+    """quat_apply, q xyzw (math_utils.py:33-40)."""
+    xyz = q[:, :3]
+    t = np.cross(xyz, v) * f32(2.0)
+    return (v + q[:, 3:4] * t + np.cross(xyz, t)).astype(f32)
+
+
+def _euler_xyz(q):
+    """get_euler_xyz (math_utils.py:89-109)."""
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    sinr = f32(2.0) * (w * x + y * z)
+    cosr = w * w - x * x - y * y + z * z
+    roll = np.arctan2(sinr, cosr)
+    sinp = f32(2.0) * (w * y - z * x)
+    pitch = np.where(np.abs(sinp) >= 1, np.abs(f32(np.pi / 2.0)) * np.sign(sinp), np.arcsin(np.clip(sinp, -1, 1)))
+    siny = f32(2.0) * (w * z + x * y)
+    cosy = w * w + x * x - y * y - z * z
+    yaw = np.arctan2(siny, cosy)
+    return np.stack([roll, pitch, yaw], axis=-1).astype(f32)
+
+
+def _norm3(v):
+    """torch.norm(dim=-1) of 3-vectors in fp32."""
+    return np.sqrt(np.sum(v * v, axis=-1, dtype=f32)).astype(f32)
+
+
+class EnvOracle:
+    def __init__(self, spec: T.TaskSpec, num_envs: int, height_samples=None, terrain_origins=None):
+        self.spec = s = spec
+        self.N = N = num_envs
+        self.model = m = spec.load_model()
+        self.A = A = spec.num_actions
+        self.feet, self.pen, self.term, self.cs = spec.link_groups(m)
+        self.F = F = len(self.feet)
+        self.L = m.nlinks
+        self.widths = spec.obs_widths(m)
+        self.sum_names = spec.episode_sum_names()
+        self.hs = None if height_samples is None else np.ascontiguousarray(height_samples, np.int16)
+        self.terrain_origins = None if terrain_origins is None else np.asarray(terrain_origins, f32)
+        self.q0 = np.asarray(spec.default_dof_pos, f32)[None, :]
+        lim = m.dof_limits.astype(f32).copy()                      # soft limits, genesis_simulator.py:373-382
+        for i in range(A):
+            mid = (lim[i, 0] + lim[i, 1]) / f32(2)
+            r = lim[i, 1] - lim[i, 0]
+            lim[i, 0] = mid - f32(0.5) * r * f32(s.soft_dof_pos_limit)
+            lim[i, 1] = mid + f32(0.5) * r * f32(s.soft_dof_pos_limit)
+        self.dof_pos_limits = lim
+        gx, gy = np.meshgrid(np.asarray(s.measured_points_x, f32), np.asarray(s.measured_points_y, f32), indexing="ij")
+        self.height_points = np.stack([gx.ravel(), gy.ravel()], axis=-1).astype(f32)   # [P,2]
+        self.P = self.height_points.shape[0]
+        if s.heightfield:
+            self.x_range = (f32(-s.border_size + 1.0), f32(s.border_size + s.num_rows * s.terrain_length - 1.0))
+            self.y_range = (f32(-s.border_size + 1.0), f32(s.border_size + s.num_cols * s.terrain_width - 1.0))
+        else:
+            self.x_range = self.y_range = (f32(-s.plane_length / 2 + 1), f32(s.plane_length / 2 - 1))
+        self.cmd_range_x = [float(s.cmd_lin_vel_x[0]), float(s.cmd_lin_vel_x[1])]
+        self.common_step_counter = 0
+        self.noise_vec = spec.noise_scale_vec()
+        z = lambda *sh: np.zeros(sh, f32)
+        self.st = dict(
+            base_pos=z(N, 3), base_quat_wxyz=z(N, 4), base_lin_w=z(N, 3), base_ang_w=z(N, 3), q=z(N, A), qd=z(N, A),
+            friction=z(N, 1), added_mass=np.ones((N, 1), f32), com_bias=z(N, 3), kp_scale=np.ones((N, A), f32),
+            kd_scale=np.ones((N, A), f32), joint_armature=z(N, 1), joint_friction=z(N, 1), joint_damping=z(N, 1),
+            rand_push_vels=z(N, 3),
+            actions=z(N, A), last_actions=z(N, A), llast_actions=z(N, A), commands=z(N, 4),
+            episode_length=np.zeros(N, np.int32), fail_buf=np.zeros(N, np.int32), feet_air_time=z(N, F),
+            last_contacts=np.zeros((N, F), np.uint8), episode_sums=z(N, len(self.sum_names)),
+            terrain_levels=np.zeros(N, np.int32), terrain_types=np.zeros(N, np.int32), env_origins=z(N, 3),
+            base_lin_vel=z(N, 3), base_ang_vel=z(N, 3), feet_vel=z(N, F, 3), last_dof_vel=z(N, A),
+            last_feet_vel=z(N, F, 3), last_base_lin_vel=z(N, 3), last_base_ang_vel=z(N, 3),
+            obs_hist=z(N, max(self.widths["hist"], 1)), critic_hist=z(N, max(self.widths["critic"], 1)),
+        )
+        self.st["base_quat_wxyz"][:, 0] = 1
+        self.out = {}
+
+    # ------------------------------------------------------------------ randoms
+    def u(self, site, idx, env=None):
+        env = np.arange(self.N) if env is None else env
+        return philox.uniform(self.spec.seed, self.common_step_counter, np.asarray(env)[:, None], site,
+                              np.atleast_1d(idx)[None, :])
+
+    @staticmethod
+    def _range(lo, hi, u):
+        """torch_rand_float: (upper - lower) * rand + lower in fp32 (math_utils.py:78-81)."""
+        return (f32(hi - lo) * u + f32(lo)).astype(f32)
+
+    # ------------------------------------------------------------------ step halves
+    def pre_step(self, actions):
+        s, st = self.spec, self.st
+        a = np.clip(np.asarray(actions, f32), f32(-s.clip_actions), f32(s.clip_actions))
+        st["llast_actions"][:] = st["last_actions"]
+        st["last_actions"][:] = st["actions"]
+        st["actions"][:] = a
+        st["last_base_lin_vel"][:] = st["base_lin_vel"]
+        st["last_base_ang_vel"][:] = st["base_ang_vel"]
+        st["last_feet_vel"][:] = st["feet_vel"]
+        st["last_dof_vel"][:] = st["qd"]
+        return a
+
+    def pd_torque(self, a, q, qd):
+        s, st = self.spec, self.st
+        scaled = a * f32(s.action_scale)
+        return (st["kp_scale"] * f32(s.kp) * (scaled + self.q0 - q) - st["kd_scale"] * f32(s.kd) * qd).astype(f32)
+
+    def post_step(self, phys):
+        """phys: dict(base_pos, base_quat_wxyz, base_lin_w, base_ang_w, q, qd, torques, link_force[N,L,3],
+        feet_pos[N,F,3], feet_vel[N,F,3]) -- the state right after the decimated physics loop."""
+        st = self.st
+        for k in ("base_pos", "base_quat_wxyz", "base_lin_w", "base_ang_w", "q", "qd"):
+            st[k][:] = np.asarray(phys[k], f32)
+        st["episode_length"] += 1
+        self.common_step_counter += 1
+        o = self.out = {}
+        self._sim_post(phys, o)
+        self._callback(o)
+        self._termination(o)
+        self._reward(o)
+        self._reset(o)
+        self._observe(o)
+        return o
+
+    # ------------------------------------------------------------------ genesis_simulator.py:35-60
+    def _sim_post(self, phys, o):
+        s, st = self.spec, self.st
+        bp = st["base_pos"]
+        feet_pos = np.asarray(phys["feet_pos"], f32).copy()
+        oob = (bp[:, 0] >= self.x_range[1]) | (bp[:, 0] <= self.x_range[0]) | (bp[:, 1] >= self.y_range[1]) | (bp[:, 1] <= self.y_range[0])
+        if oob.any():                                            # genesis_simulator.py:612-628
+            new = (np.asarray(s.init_pos, f32)[None, :] + st["env_origins"][oob]).astype(f32)
+            feet_pos[oob] += (new - bp[oob])[:, None, :]
+            bp[oob] = new
+        o["oob"] = oob
+        qw = st["base_quat_wxyz"]
+        quat = np.concatenate([qw[:, 1:4], qw[:, 0:1]], axis=1).astype(f32)      # wxyz -> xyzw
+        o["base_quat"] = quat
+        o["base_euler"] = _euler_xyz(quat)
+        st["base_lin_vel"][:] = _rot_inv(quat, st["base_lin_w"])
+        st["base_ang_vel"][:] = _rot_inv(quat, st["base_ang_w"])
+        g = np.zeros((self.N, 3), f32)
+        g[:, 2] = -1
+        o["projected_gravity"] = _rot_inv(quat, g)
+        o["dof_pos"], o["dof_vel"] = st["q"].copy(), st["qd"].copy()
+        o["torques"] = np.asarray(phys["torques"], f32).copy()
+        o["link_contact_forces"] = lf = np.asarray(phys["link_force"], f32).copy()
+        o["feet_pos"] = feet_pos
+        st["feet_vel"][:] = np.asarray(phys["feet_vel"], f32)
+        o["feet_vel"] = st["feet_vel"].copy()
+        o["base_pos"] = bp.copy()
+        if s.obtain_link_contact_states:
+            o["link_contact_states"] = (_norm3(lf[:, self.cs, :]) > f32(1.0)).astype(f32)
+        else:
+            o["link_contact_states"] = np.zeros((self.N, 0), f32)
+        if s.measure_heights and s.heightfield:
+            self._heights(o)
+            if s.obtain_terrain_info_around_feet:
+                self._feet_terrain(o)
+        else:                                                     # scan never updated on a plane
+            o["measured_heights"] = np.zeros((self.N, self.P), f32)
+            o["height_cells"] = np.zeros((self.N, self.P, 2), np.int32)
+
+    def _cell(self, p):
+        """trunc((p + border) / hscale) with fp32 IEEE ops (SURVEY a-kernel notes)."""
+        s = self.spec
+        g = ((p + f32(s.border_size)).astype(f32) / f32(s.horizontal_scale)).astype(f32)
+        return np.trunc(g).astype(np.int64)
+
+    def _heights(self, o):
+        s, st = self.spec, self.st
+        quat = o["base_quat"]
+        z, w = quat[:, 2], quat[:, 3]
+        nrm = np.maximum(np.sqrt((z * z + w * w).astype(f32)).astype(f32), f32(1e-9))
+        zn, wn = (z / nrm).astype(f32)[:, None], (w / nrm).astype(f32)[:, None]
+        px, py = self.height_points[None, :, 0], self.height_points[None, :, 1]
+        tx = (-(zn * py) * f32(2.0)).astype(f32)
+        ty = ((zn * px) * f32(2.0)).astype(f32)
+        rx = ((px + wn * tx).astype(f32) + (-(zn * ty)).astype(f32)).astype(f32)
+        ry = ((py + wn * ty).astype(f32) + (zn * tx).astype(f32)).astype(f32)
+        wx = (rx + st["base_pos"][:, 0:1]).astype(f32)
+        wy = (ry + st["base_pos"][:, 1:2]).astype(f32)
+        cx = np.clip(self._cell(wx), 0, self.hs.shape[0] - 2)
+        cy = np.clip(self._cell(wy), 0, self.hs.shape[1] - 2)
+        h = np.minimum(np.minimum(self.hs[cx, cy], self.hs[cx + 1, cy]), self.hs[cx, cy + 1])
+        o["measured_heights"] = (h.astype(f32) * f32(s.vertical_scale)).astype(f32)
+        o["height_cells"] = np.stack([cx, cy], axis=-1).astype(np.int32)
+
+    def _feet_terrain(self, o):
+        s = self.spec
+        fp = o["feet_pos"]
+        cx = np.clip(self._cell(fp[:, :, 0]), 0, self.hs.shape[0] - 2)
+        cy = np.clip(self._cell(fp[:, :, 1]), 0, self.hs.shape[1] - 2)
+        H = lambda dx, dy: self.hs[cx + dx, cy + dy]
+        hh = [H(-1, 0), H(1, 0), H(0, -1), H(0, 1), H(0, 0), H(-1, -1), H(1, 1), H(-1, 1), H(1, -1)]
+        den = f32(s.horizontal_scale * 2)
+        # int16 difference (torch keeps int16) then true division -> fp32
+        dx = ((hh[1] - hh[0]).astype(np.int16).astype(f32) / den).astype(f32)
+        dy = ((hh[3] - hh[2]).astype(np.int16).astype(f32) / den).astype(f32)
+        nv = np.stack([dx, dy, -np.ones_like(dx)], axis=-1).astype(f32)
+        nv = (nv / _norm3(nv)[..., None]).astype(f32)
+        o["normal_vector_around_feet"] = nv.reshape(self.N, -1)
+        o["height_around_feet"] = (np.stack(hh, axis=-1).astype(f32) * f32(s.vertical_scale)).astype(f32)
+        o["feet_cells"] = np.stack([cx, cy], axis=-1).astype(np.int32)
+
+    # ------------------------------------------------------------------ legged_robot.py:300-334
+    def _resample(self, ids, site):
+        s, st = self.spec, self.st
+        if len(ids) == 0:
+            return
+        c = st["commands"]
+        c[ids, 0] = self._range(self.cmd_range_x[0], self.cmd_range_x[1], self.u(site, [0], ids)[:, 0])
+        c[ids, 1] = self._range(s.cmd_lin_vel_y[0], s.cmd_lin_vel_y[1], self.u(site, [1], ids)[:, 0])
+        if s.heading_command:
+            c[ids, 3] = self._range(s.cmd_heading[0], s.cmd_heading[1], self.u(site, [2], ids)[:, 0])
+        else:
+            c[ids, 2] = self._range(s.cmd_ang_vel_yaw[0], s.cmd_ang_vel_yaw[1], self.u(site, [2], ids)[:, 0])
+        keep = (_norm3(c[ids, :3]) > f32(0.2)).astype(f32)
+        c[ids, :3] *= keep[:, None]
+
+    def _callback(self, o):
+        s, st = self.spec, self.st
+        ids = np.nonzero(st["episode_length"] % s.resample_interval == 0)[0]
+        self._resample(ids, T.SITE_CMD_RESAMPLE)
+        if s.heading_command:
+            fwd = _quat_apply(o["base_quat"], np.tile(np.array([[1, 0, 0]], f32), (self.N, 1)))
+            heading = np.arctan2(fwd[:, 1], fwd[:, 0]).astype(f32)
+            ang = (st["commands"][:, 3] - heading).astype(f32)
+            two_pi = f32(2 * np.pi)
+            # wrap_to_pi, math_utils.py:49-53.  TorchScript compiles `angles %= 2*pi` to aten::fmod_ (sign of the
+            # dividend), so negative angles are NOT wrapped: the result lies in (-2*pi, pi]  (quirk R16)
+            ang = np.fmod(ang, two_pi).astype(f32)
+            ang = (ang - two_pi * (ang > f32(np.pi)).astype(f32)).astype(f32)
+            st["commands"][:, 2] = np.clip(f32(0.5) * ang, f32(s.cmd_ang_vel_yaw[0]), f32(s.cmd_ang_vel_yaw[1]))
+        o["pushed"] = False
+        if s.push_robots and self.common_step_counter % s.push_interval == 0:
+            push = self._range(-s.max_push_vel_xy, s.max_push_vel_xy, self.u(T.SITE_PUSH, [0, 1]))
+            st["rand_push_vels"][:, :2] = push
+            st["base_lin_w"][:, :2] += push
+            o["pushed"] = True
+
+    # ------------------------------------------------------------------ legged_robot.py:78-92
+    def _termination(self, o):
+        s, st = self.spec, self.st
+        lf = o["link_contact_forces"]
+        fail = np.zeros(self.N, bool)
+        if len(self.term):
+            fail = np.any(_norm3(lf[:, self.term, :]) > f32(10.0), axis=1)
+        fail |= o["projected_gravity"][:, 2] > f32(s.max_projected_gravity)
+        st["fail_buf"] += fail.astype(np.int32)
+        o["time_out_buf"] = st["episode_length"] > s.max_episode_length
+        o["reset_buf"] = (st["fail_buf"] > s.fail_limit) | o["time_out_buf"]
+
+    # ------------------------------------------------------------------ legged_robot.py:150-168 + _reward_*
+    def _reward(self, o):
+        s, st = self.spec, self.st
+        lf, cmd = o["link_contact_forces"], st["commands"]
+        dt = f32(s.dt)
+        ssum = lambda x: np.sum(x, axis=1, dtype=f32).astype(f32)
+        terms = {}
+
+        def feet_air_time():
+            contact = lf[:, self.feet, 2] > f32(1.0)
+            filt = contact | (st["last_contacts"] > 0)
+            st["last_contacts"][:] = contact
+            first = (st["feet_air_time"] > 0) & filt
+            st["feet_air_time"] += dt
+            r = ssum((st["feet_air_time"] - f32(s.feet_air_time_threshold)) * first)
+            r = r * (_norm3(np.concatenate([cmd[:, :2], np.zeros((self.N, 1), f32)], 1)) > f32(0.1))
+            st["feet_air_time"] *= ~filt
+            return r
+
+        def foot_clearance():
+            vxy = np.sqrt(np.sum(o["feet_vel"][:, :, :2] ** 2, axis=-1, dtype=f32)).astype(f32)
+            z = o["feet_pos"][:, :, 2]
+            if s.foot_clearance_uses_terrain:
+                z = z - np.mean(o["height_around_feet"], axis=-1, dtype=f32).astype(f32)
+            err = ssum(vxy * np.square(z - f32(s.foot_clearance_target) - f32(s.foot_height_offset)))
+            return np.exp(-err / f32(s.foot_clearance_tracking_sigma)).astype(f32)
+
+        def foot_landing_vel():
+            zv = o["feet_vel"][:, :, 2]
+            contacts = lf[:, self.feet, 2] > f32(0.1)
+            about = ((o["feet_pos"][:, :, 2] - f32(s.foot_height_offset)) < f32(s.about_landing_threshold)) & ~contacts & (zv < 0)
+            return ssum(np.square(np.where(about, zv, f32(0))))
+
+        small_cmd = (_norm3(cmd[:, :3]) < f32(0.1)).astype(f32)
+        dq = o["dof_pos"] - self.q0
+        lim = self.dof_pos_limits
+        fn = {
+            "action_rate": lambda: ssum(np.square(st["last_actions"] - st["actions"])),
+            "action_smoothness": lambda: ssum(np.square(st["actions"] - f32(2) * st["last_actions"] + st["llast_actions"])),
+            "ang_vel_xy": lambda: ssum(np.square(st["base_ang_vel"][:, :2])),
+            "base_height": lambda: np.square(np.mean(st["base_pos"][:, 2:3] - o["measured_heights"], axis=1, dtype=f32)
+                                             - f32(s.base_height_target)),
+            "collision": lambda: ssum((_norm3(lf[:, self.pen, :]) > f32(0.1)).astype(f32)),
+            "dof_acc": lambda: ssum(np.square((st["last_dof_vel"] - o["dof_vel"]) / dt)),
+            "dof_close_to_default": lambda: ssum(np.square(dq)),
+            "dof_pos_limits": lambda: ssum(-np.minimum(o["dof_pos"] - lim[None, :, 0], f32(0)) + np.maximum(o["dof_pos"] - lim[None, :, 1], f32(0))),
+            "dof_pos_stand_still": lambda: ssum(np.square(dq)) * small_cmd,
+            "dof_power": lambda: ssum(np.abs(o["torques"] * o["dof_vel"])),
+            "dof_vel": lambda: ssum(np.square(o["dof_vel"])),
+            "dof_vel_stand_still": lambda: ssum(np.abs(o["dof_vel"])) * small_cmd,
+            "feet_air_time": feet_air_time,
+            "feet_contact_stand_still": lambda: (ssum((lf[:, self.feet, 2] > f32(0.1)).astype(f32)) == self.F).astype(f32) * small_cmd,
+            "foot_acc": lambda: np.sum(np.square((o["feet_vel"] - st["last_feet_vel"]) / dt), axis=(1, 2), dtype=f32),
+            "foot_clearance": foot_clearance,
+            "foot_landing_vel": foot_landing_vel,
+            "hip_pos": lambda: ssum(np.square(dq[:, 0::3])),
+            "keep_balance": lambda: np.ones(self.N, f32),
+            "lin_vel_z": lambda: np.square(st["base_lin_vel"][:, 2]),
+            "orientation": lambda: ssum(np.square(o["projected_gravity"][:, :2])),
+            "thigh_pos": lambda: ssum(np.square(dq[:, 1::3])),
+            "torques": lambda: ssum(np.square(o["torques"])),
+            "tracking_ang_vel": lambda: np.exp(-np.square(cmd[:, 2] - st["base_ang_vel"][:, 2]) / f32(s.tracking_sigma)),
+            "tracking_lin_vel": lambda: np.exp(-ssum(np.square(cmd[:, :2] - st["base_lin_vel"][:, :2])) / f32(s.tracking_sigma)),
+        }
+        rew = np.zeros(self.N, f32)
+        for i, name in enumerate(s.active_rewards()):
+            r = (fn[name]().astype(f32) * s.scaled_reward(name)).astype(f32)
+            terms[name] = r
+            rew = (rew + r).astype(f32)
+            st["episode_sums"][:, i] += r
+        if s.only_positive_rewards:
+            rew = np.maximum(rew, f32(0))
+        if s.reward_scales.get("termination", 0) != 0:
+            r = ((o["reset_buf"] & ~o["time_out_buf"]).astype(f32) * s.scaled_reward("termination")).astype(f32)
+            rew = (rew + r).astype(f32)
+            st["episode_sums"][:, len(self.sum_names) - 1] += r
+            terms["termination"] = r
+        o["rew_buf"], o["reward_terms"] = rew, terms
+
+    # ------------------------------------------------------------------ legged_robot.py:94-148
+    def _reset(self, o):
+        s, st = self.spec, self.st
+        ids = np.nonzero(o["reset_buf"])[0]
+        o["env_ids"] = ids
+        o["projected_gravity_obs"] = o["projected_gravity"]
+        o["episode_means"] = None
+        if len(ids) == 0:
+            return
+        if s.terrain_curriculum:                                   # legged_robot.py:254-272; genesis_simulator.py:140-148
+            dist = np.sqrt(np.sum(np.square(st["base_pos"][ids, :2] - st["env_origins"][ids, :2]), axis=1, dtype=f32)).astype(f32)
+            up = dist > f32(s.terrain_length / 2)
+            cn = np.sqrt(np.sum(np.square(st["commands"][ids, :2]), axis=1, dtype=f32)).astype(f32)
+            down = (dist < (cn * f32(s.episode_length_s) * f32(0.5)).astype(f32)) & ~up
+            lv = st["terrain_levels"][ids] + up.astype(np.int32) - down.astype(np.int32)
+            rnd = np.minimum((self.u(T.SITE_LEVEL, [0], ids)[:, 0] * f32(s.num_rows)).astype(np.int32), s.num_rows - 1)
+            lv = np.where(lv >= s.num_rows, rnd, np.maximum(lv, 0))
+            st["terrain_levels"][ids] = lv
+            st["env_origins"][ids] = self.terrain_origins[lv, st["terrain_types"][ids]]
+        # command curriculum (legged_robot.py:336-348) is applied by the host one step later: DESIGN.md "deviations"
+        self._resample(ids, T.SITE_CMD_RESET)
+        A = self.A
+        noise = np.asarray(s.reset_dof_noise, f32)[None, :]        # go2_ts.py:86-91
+        udof = self.u(T.SITE_DOF, np.arange(A), ids)
+        st["q"][ids] = (self.q0 + (f32(2) * noise * udof + (-noise)).astype(f32)).astype(f32)
+        st["qd"][ids] = 0
+        o["dof_pos"][ids], o["dof_vel"][ids] = st["q"][ids], 0
+        uroot = self.u(T.SITE_ROOT, np.arange(8), ids)             # legged_robot.py:283-298
+        pos = (np.asarray(s.init_pos, f32)[None, :] + st["env_origins"][ids]).astype(f32)
+        if s.heightfield:
+            pos[:, :2] += self._range(-s.reset_root_xy, s.reset_root_xy, uroot[:, 0:2])
+        st["base_pos"][ids] = pos
+        qx = np.asarray(s.init_quat_xyzw, f32)
+        st["base_quat_wxyz"][ids] = np.array([qx[3], qx[0], qx[1], qx[2]], f32)
+        lin = self._range(-s.reset_root_vel, s.reset_root_vel, uroot[:, 2:5])
+        ang = self._range(-s.reset_root_vel, s.reset_root_vel, uroot[:, 5:8])
+        st["base_lin_w"][ids], st["base_ang_w"][ids] = lin, ang
+        st["base_lin_vel"][ids], st["base_ang_vel"][ids] = lin, ang
+        quat = o["base_quat"].copy()
+        quat[ids] = qx
+        g = np.zeros((self.N, 3), f32)
+        g[:, 2] = -1
+        o["projected_gravity_obs"] = _rot_inv(quat, g)             # genesis_simulator.py:125
+        o["base_pos"][ids] = pos
+        # domain randomisation, genesis_simulator.py:62-82,665-739
+        if s.randomize_friction:
+            st["friction"][ids, 0] = self._range(s.friction_range[0], s.friction_range[1], self.u(T.SITE_FRICTION, [0], ids)[:, 0])
+        if s.randomize_base_mass:
+            st["added_mass"][ids, 0] = self._range(s.added_mass_range[0], s.added_mass_range[1], self.u(T.SITE_MASS, [0], ids)[:, 0])
+        if s.randomize_com_displacement:
+            uc = self.u(T.SITE_COM, [0, 1, 2], ids)
+            for k, rg in enumerate((s.com_pos_x_range, s.com_pos_y_range, s.com_pos_z_range)):
+                st["com_bias"][ids, k] = self._range(rg[0], rg[1], uc[:, k])
+        for flag, key, rg, site in ((s.randomize_joint_armature, "joint_armature", s.joint_armature_range, T.SITE_ARMATURE),
+                                    (s.randomize_joint_friction, "joint_friction", s.joint_friction_range, T.SITE_JFRICTION),
+                                    (s.randomize_joint_damping, "joint_damping", s.joint_damping_range, T.SITE_JDAMPING)):
+            if flag:
+                st[key][ids, 0] = self._range(rg[0], rg[1], self.u(site, [0], ids)[:, 0])
+        if s.randomize_pd_gain:
+            st["kp_scale"][ids] = self._range(s.kp_range[0], s.kp_range[1], self.u(T.SITE_KP, np.arange(A), ids))
+            st["kd_scale"][ids] = self._range(s.kd_range[0], s.kd_range[1], self.u(T.SITE_KD, np.arange(A), ids))
+        for k in ("last_dof_vel", "last_feet_vel", "last_base_lin_vel", "last_base_ang_vel",
+                  "llast_actions", "last_actions", "actions", "feet_air_time"):
+            st[k][ids] = 0
+        st["episode_length"][ids] = 0
+        st["fail_buf"][ids] = 0
+        o["episode_means"] = {"rew_" + n: np.mean(st["episode_sums"][ids, i], dtype=f32) / f32(s.episode_length_s)
+                              for i, n in enumerate(self.sum_names)}
+        st["episode_sums"][ids] = 0
+        if self.widths["hist"]:
+            st["obs_hist"][ids] = 0
+            st["critic_hist"][ids] = 0
+
+    # ------------------------------------------------------------------ go2.py:40-90 / go2_ts.py:5-84
+    def _observe(self, o):
+        s, st = self.spec, self.st
+        cs = np.array([s.obs_scale_lin_vel, s.obs_scale_lin_vel, s.obs_scale_ang_vel], f32)
+        obs = np.concatenate([
+            st["commands"][:, :3] * cs, o["projected_gravity_obs"], st["base_ang_vel"] * f32(s.obs_scale_ang_vel),
+            (o["dof_pos"] - self.q0) * f32(s.obs_scale_dof_pos), o["dof_vel"] * f32(s.obs_scale_dof_vel), st["actions"]],
+            axis=1).astype(f32)
+        clean = obs.copy()
+        if s.add_noise:
+            un = self.u(T.SITE_OBS_NOISE, np.arange(obs.shape[1]))
+            obs = (obs + ((f32(2) * un - f32(1)).astype(f32) * self.noise_vec[None, :]).astype(f32)).astype(f32)
+        c = f32(s.clip_observations)
+        if s.obs_kind == "go2":
+            o["obs_buf"] = np.clip(obs, -c, c)
+            return
+        dr = np.concatenate([
+            st["friction"] - f32((s.friction_range[0] + s.friction_range[1]) / 2), st["added_mass"], st["com_bias"],
+            st["rand_push_vels"][:, :2], st["kp_scale"] - f32((s.kp_range[0] + s.kp_range[1]) / 2),
+            st["kd_scale"] - f32((s.kd_range[0] + s.kd_range[1]) / 2)], axis=1).astype(f32)
+        lin = (st["base_lin_vel"] * f32(s.obs_scale_lin_vel)).astype(f32)
+        parts = [clean, dr, lin]
+        if s.obtain_link_contact_states:
+            parts.append(o["link_contact_states"])
+        if s.measure_heights:
+            hobs = (np.clip(st["base_pos"][:, 2:3] - f32(s.height_obs_offset) - o["measured_heights"], f32(-1), f32(1))
+                    * f32(s.obs_scale_height)).astype(f32)
+            parts.append(hobs)
+        critic = np.concatenate(parts, axis=1).astype(f32)
+        sc, so = self.widths["single_critic"], self.widths["obs"]
+        st["critic_hist"][:] = np.concatenate([st["critic_hist"][:, sc:], critic], axis=1)
+        st["obs_hist"][:] = np.concatenate([st["obs_hist"][:, so:], obs], axis=1)
+        fz = o["feet_pos"][:, :, 2:3]
+        priv = [dr, np.clip((fz - o["height_around_feet"]).reshape(self.N, -1), f32(-1), f32(1)),
+                o["normal_vector_around_feet"], lin]
+        if s.obtain_link_contact_states:
+            priv.append(o["link_contact_states"])
+        o["obs_buf"] = np.clip(obs, -c, c)
+        o["privileged_obs_buf"] = np.clip(np.concatenate(priv, axis=1).astype(f32), -c, c)
+        o["obs_history"] = st["obs_hist"].copy()
+        o["critic_obs_buf"] = st["critic_hist"].copy()

@@ -1,0 +1,81 @@
+"""ctypes front-end of the CPU physics oracle (oracle/rigid_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs, never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+P_DT, P_GRAV, P_TC, P_DAMPRATIO, P_D0, P_DMAX, P_WIDTH, P_MID, P_POWER, P_TERRAIN_MU, P_GEOM_MU, P_ITERS, \
+    P_HSCALE, P_VSCALE, P_BORDER = range(15)
+
+
+def build(force: bool = False) -> None:
+    src = os.path.join(_HERE, "rigid_oracle.c")
+    for name in ("liboracle_f64.so", "liboracle_f32.so"):
+        out = os.path.join(_HERE, name)
+        if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, name])
+
+
+def default_params(dt=0.005, iters=30, hscale=0.1, vscale=0.005, border=0.0, terrain_mu=1.0, geom_mu=1.0) -> np.ndarray:
+    p = np.zeros(16, np.float32)
+    p[P_DT], p[P_GRAV] = dt, 9.81
+    p[P_TC], p[P_DAMPRATIO] = 2 * dt, 1.0
+    p[P_D0], p[P_DMAX], p[P_WIDTH], p[P_MID], p[P_POWER] = 0.9, 0.95, 0.001, 0.5, 2.0
+    p[P_TERRAIN_MU], p[P_GEOM_MU], p[P_ITERS] = terrain_mu, geom_mu, iters
+    p[P_HSCALE], p[P_VSCALE], p[P_BORDER] = hscale, vscale, border
+    return p
+
+
+class PhysicsOracle:
+    """Batched substep over ``n`` envs; all state arrays are float64 [n, k] numpy arrays."""
+
+    def __init__(self, model, params: np.ndarray, heightfield: np.ndarray | None = None, precision: str = "f64"):
+        build()
+        self.lib = ctypes.CDLL(os.path.join(_HERE, f"liboracle_{precision}.so"))
+        self.model = model
+        self.mi = model.packed_ints()
+        self.mf = model.packed_floats()
+        self.prm = np.ascontiguousarray(params, np.float32)
+        if heightfield is None:
+            self.hf, self.rows, self.cols = np.zeros(1, np.int16), 0, 0
+        else:
+            self.hf = np.ascontiguousarray(heightfield, np.int16)
+            self.rows, self.cols = self.hf.shape
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(ctypes.c_void_p)
+
+    def substep(self, state, q, qd, tau, envp, jparam):
+        """In-place substep. Returns (link_force [n, nlinks, 3], ncontact [n])."""
+        n = state.shape[0]
+        for a in (state, q, qd):
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+        tau = np.ascontiguousarray(tau, np.float64)
+        envp = np.ascontiguousarray(envp, np.float64)
+        jparam = np.ascontiguousarray(jparam, np.float64)
+        lf = np.zeros((n, self.model.nlinks, 3), np.float64)
+        nc = np.zeros(n, np.int32)
+        self.lib.oracle_substep(self._p(self.mi), self._p(self.mf), self._p(self.prm), self._p(self.hf),
+                                ctypes.c_int(self.rows), ctypes.c_int(self.cols), ctypes.c_int(n),
+                                self._p(state), self._p(q), self._p(qd), self._p(tau), self._p(envp), self._p(jparam),
+                                self._p(lf), self._p(nc))
+        return lf, nc
+
+    def link_kinematics(self, state, q, qd):
+        n = state.shape[0]
+        lp = np.zeros((n, self.model.nlinks, 3), np.float64)
+        lv = np.zeros((n, self.model.nlinks, 3), np.float64)
+        self.lib.oracle_link_kinematics(self._p(self.mi), self._p(self.mf), ctypes.c_int(n),
+                                        self._p(np.ascontiguousarray(state, np.float64)),
+                                        self._p(np.ascontiguousarray(q, np.float64)),
+                                        self._p(np.ascontiguousarray(qd, np.float64)), self._p(lp), self._p(lv))
+        return lp, lv

@@ -1,0 +1,1 @@
+"""Import stub for the reference joystick script. Oracle tooling only."""

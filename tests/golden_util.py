@@ -1,0 +1,34 @@
+"""Helpers shared by the golden-vector tests (CPU oracle and CUDA path replay the same recordings)."""
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    g = {k: z[k] for k in z.files}
+    s0 = {k[3:]: v for k, v in g.items() if k.startswith("s0/")}
+    return g, s0
+
+
+def load_terrain():
+    z = np.load(os.path.join(GOLDEN_DIR, "go2_rough_terrain.npz"))
+    return z["height_samples"], z["terrain_origins"]
+
+
+def spec_for(g):
+    from hcr_genesis_lr_cl_b200 import task_spec as T
+    spec = T.PRESETS[str(g["meta/task"])]()
+    spec.seed = int(g["meta/seed"])
+    spec.contact_state_link_names = [str(x) for x in g["meta/contact_links"]]
+    return spec
+
+
+def phys_at(g, t):
+    return {k[5:]: v[t] for k, v in g.items() if k.startswith("phys/")}
+
+
+def out_at(g, t):
+    return {k[4:]: v[t] for k, v in g.items() if k.startswith("out/")}

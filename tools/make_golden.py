@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Record golden vectors from the reference's own environment code.
+
+Runs LeggedGym-Ex's unmodified Python classes (LeggedRobot / GO2 / Go2TS + GenesisSimulator, imported
+from /root/reference) over the CPU physics oracle behind a stand-in `genesis` module
+(oracle/stubs/genesis), with every random draw replaced by the counter-based Philox stream the fused
+kernel uses (oracle/philox.py).  Writes tests/golden/<name>.npz holding
+
+  * the full environment state before the recorded window (``s0/*``),
+  * per step: the actions, the state right after the decimated physics loop (``phys/*`` -- what the
+    engine hands to post_physics_step) and everything the reference computed from it (``out/*``).
+
+Build-container tooling (needs /root/reference); the fixtures it writes travel to the GPU box.
+
+Usage: python tools/make_golden.py [--task go2_ts] [--envs 32] [--steps 10] [--name go2_ts_n32]
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from hcr_genesis_lr_cl_b200 import task_spec as T  # noqa: E402
+from oracle import philox  # noqa: E402
+from oracle.ref_harness import make_env  # noqa: E402
+
+
+class Injector:
+    """Replaces the reference's RNG call sites by philox draws keyed (seed, step, env, site, idx)."""
+
+    def __init__(self, env, seed):
+        import torch
+        self.torch, self.env, self.sim, self.seed = torch, env, env.simulator, seed
+        self.site, self.ids, self.col, self.call, self.in_reset = None, None, 0, 0, False
+        self.N = env.num_envs
+
+    def u(self, site, ids, cols):
+        step = self.env.common_step_counter
+        return philox.uniform(self.seed, step, np.asarray(ids)[:, None], site, np.asarray(cols)[None, :])
+
+    def draw(self, shape):
+        assert self.site is not None, "random draw outside a known site"
+        k = shape[0]
+        ncol = shape[1] if len(shape) > 1 else 1
+        site = self.site
+        if site == T.SITE_DOF and ncol == 4:
+            cols = 3 * np.arange(4) + self.call            # go2_ts.py:86-91: hips, thighs, calves
+        elif site == T.SITE_KP:
+            site, cols = (T.SITE_KP if self.call == 0 else T.SITE_KD), np.arange(ncol)
+        else:
+            cols = self.col + np.arange(ncol)
+            self.col += ncol
+        self.call += 1
+        ids = self.ids
+        assert len(ids) == k, (len(ids), shape, site)
+        return self.torch.from_numpy(self.u(site, ids, cols).reshape(shape).astype(np.float32))
+
+    def ctx(self, fn, site, ids_arg=True, name=None):
+        inj = self
+
+        def wrapped(*a, **kw):
+            prev = (inj.site, inj.ids, inj.col, inj.call)
+            ids = a[0] if ids_arg else np.arange(inj.N)
+            ids = ids.cpu().numpy() if hasattr(ids, "cpu") else np.asarray(ids)
+            s = site
+            if name == "resample":
+                s = T.SITE_CMD_RESET if inj.in_reset else T.SITE_CMD_RESAMPLE
+            inj.site, inj.ids, inj.col, inj.call = s, ids, 0, 0
+            try:
+                return fn(*a, **kw)
+            finally:
+                inj.site, inj.ids, inj.col, inj.call = prev
+        return wrapped
+
+    def install(self):
+        torch, env, sim = self.torch, self.env, self.sim
+        import genesis as gs
+
+        def rand_float(lower, upper, shape, device="cpu"):
+            return (upper - lower) * self.draw(tuple(shape)) + lower
+
+        for mod in list(sys.modules.values()):
+            if mod is not None and getattr(mod, "__name__", "").startswith("legged_gym") and hasattr(mod, "torch_rand_float"):
+                mod.torch_rand_float = rand_float
+        gs._rand_hook = lambda shape: self.draw(shape)
+        torch.rand_like = lambda t, **k: self.draw(tuple(t.shape))
+        torch.rand = lambda *shape, **k: self.draw(tuple(shape[0]) if isinstance(shape[0], (tuple, list)) else tuple(shape))
+
+        def randint_like(t, high, **k):
+            return torch.clamp((self.draw(tuple(t.shape)) * high).to(t.dtype), max=high - 1)
+        torch.randint_like = randint_like
+
+        env._resample_commands = self.ctx(env._resample_commands, None, name="resample")
+        env._reset_dofs = self.ctx(env._reset_dofs, T.SITE_DOF)
+        env._reset_root_states = self.ctx(env._reset_root_states, T.SITE_ROOT)
+        env.compute_observations = self.ctx(env.compute_observations, T.SITE_OBS_NOISE, ids_arg=False)
+        sim.update_terrain_curriculum = self.ctx(sim.update_terrain_curriculum, T.SITE_LEVEL)
+        sim.push_robots = self.ctx(sim.push_robots, T.SITE_PUSH, ids_arg=False)
+        for nm, site in (("_randomize_friction", T.SITE_FRICTION), ("_randomize_base_mass", T.SITE_MASS),
+                         ("_randomize_com_displacement", T.SITE_COM), ("_randomize_pd_gain", T.SITE_KP),
+                         ("_randomize_joint_armature", T.SITE_ARMATURE), ("_randomize_joint_friction", T.SITE_JFRICTION),
+                         ("_randomize_joint_damping", T.SITE_JDAMPING)):
+            setattr(sim, nm, self.ctx(getattr(sim, nm), site))
+        orig_reset = env.reset_idx
+
+        def reset_idx(env_ids):
+            self.in_reset = True
+            try:
+                return orig_reset(env_ids)
+            finally:
+                self.in_reset = False
+        env.reset_idx = reset_idx
+
+
+def snapshot(env, spec, sum_names):
+    """Reference env -> EnvOracle/B200 state dictionary (fp32, dof order = cfg.asset.dof_names)."""
+    sim, rob = env.simulator, env.simulator._robot
+    didx = [d - 6 for d in sim._dof_indices]
+    n = lambda t: t.detach().cpu().numpy().copy()
+    st = dict(
+        base_pos=rob.state[:, 0:3], base_quat_wxyz=rob.state[:, 3:7], base_lin_w=rob.state[:, 7:10],
+        base_ang_w=rob.state[:, 10:13], q=rob.q[:, didx], qd=rob.qd[:, didx],
+        friction=n(sim._friction_values), added_mass=n(sim._added_base_mass), com_bias=n(sim._base_com_bias),
+        kp_scale=n(sim._kp_scale), kd_scale=n(sim._kd_scale), joint_armature=n(sim._joint_armature),
+        joint_friction=n(sim._joint_friction), joint_damping=n(sim._joint_damping), rand_push_vels=n(sim._rand_push_vels),
+        actions=n(env.actions), last_actions=n(env.last_actions), llast_actions=n(env.llast_actions), commands=n(env.commands),
+        episode_length=n(env.episode_length_buf), fail_buf=n(env.fail_buf), feet_air_time=n(env.feet_air_time),
+        last_contacts=n(env.last_contacts).astype(np.uint8),
+        episode_sums=np.stack([n(env.episode_sums[k]) for k in sum_names], axis=1),
+        env_origins=n(sim._env_origins),
+        base_lin_vel=n(sim._base_lin_vel), base_ang_vel=n(sim._base_ang_vel), feet_vel=n(sim._feet_vel),
+        last_dof_vel=n(sim._last_dof_vel), last_feet_vel=n(sim._last_feet_vel),
+        last_base_lin_vel=n(sim._last_base_lin_vel), last_base_ang_vel=n(sim._last_base_ang_vel),
+    )
+    if spec.heightfield:
+        st["terrain_levels"], st["terrain_types"] = n(sim._terrain_levels), n(sim._terrain_types)
+    else:
+        st["terrain_levels"] = st["terrain_types"] = np.zeros(env.num_envs, np.int32)
+    if hasattr(env, "obs_history_deque"):
+        st["obs_hist"] = np.concatenate([n(x) for x in env.obs_history_deque], axis=1)
+        st["critic_hist"] = np.concatenate([n(x) for x in env.critic_obs_deque], axis=1)
+    out = {}
+    for k, v in st.items():
+        v = np.asarray(v)
+        out[k] = v.astype(np.int32) if v.dtype.kind in "iub" and k != "last_contacts" else (v if k == "last_contacts" else v.astype(np.float32))
+    out["common_step_counter"] = np.int64(env.common_step_counter)
+    out["cmd_range_x"] = np.asarray(env.command_ranges["lin_vel_x"], np.float64)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--task", default="go2_ts")
+    ap.add_argument("--envs", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--name", default=None)
+    ap.add_argument("--contact-links", nargs="*", default=None, help="override asset.contact_state_link_names (SURVEY R1)")
+    ap.add_argument("--seed", type=int, default=1)
+    args = ap.parse_args()
+    import torch
+
+    def edit(cfg):
+        if args.contact_links is not None:
+            cfg.asset.contact_state_link_names = list(args.contact_links)
+
+    env, cfg, _ = make_env(args.task, args.envs, cfg_edit=edit)
+    spec = T.TaskSpec.from_reference_cfg(cfg, args.task)
+    spec.seed = args.seed
+    sim = env.simulator
+    sum_names = list(env.episode_sums.keys())
+    assert sum_names == spec.episode_sum_names(), (sum_names, spec.episode_sum_names())
+    N, A = env.num_envs, env.num_actions
+    g = torch.Generator().manual_seed(1234)
+    env.reset()
+    for _ in range(args.warmup):
+        env.step(0.8 * torch.randn(N, A, generator=g))
+    # spread the interesting events over the recorded window
+    L = env.max_episode_length
+    ep = env.episode_length_buf
+    ep[:] = torch.randint(10, 400, (N,), generator=g).to(ep.dtype)
+    ep[0::8] = int(L) - 3 - (torch.arange(len(ep[0::8])) % 3).to(ep.dtype)         # time-outs
+    ep[1::8] = 500 - 2 - (torch.arange(len(ep[1::8])) % 4).to(ep.dtype)            # command resampling
+    env.fail_buf[2::8] = 3                                                         # one more fail -> reset
+    rob = sim._robot
+    flip = np.arange(2, N, 8)
+    rob.state[flip, 3:7] = np.array([0.0, 1.0, 0.0, 0.0])                          # upside down
+    rob.state[flip, 2] += 0.3
+    env.common_step_counter = spec.push_interval * 3 - args.steps // 2             # a push inside the window
+    env.step(torch.zeros(N, A))                                                    # make API buffers consistent
+    inj = Injector(env, spec.seed)
+    inj.install()
+
+    s0 = snapshot(env, spec, sum_names)
+    rec = {f"s0/{k}": v for k, v in s0.items()}
+    feet = sim._feet_indices
+    didx = [d - 6 for d in sim._dof_indices]
+    orig_step = sim.step
+    phys = {}
+
+    def sim_step(actions):
+        orig_step(actions)
+        lp, lv = rob.link_pos, rob.link_vel
+        phys.update(base_pos=rob.state[:, 0:3].copy(), base_quat_wxyz=rob.state[:, 3:7].copy(),
+                    base_lin_w=rob.state[:, 7:10].copy(), base_ang_w=rob.state[:, 10:13].copy(),
+                    q=rob.q[:, didx].copy(), qd=rob.qd[:, didx].copy(), torques=sim._torques.numpy().copy(),
+                    link_force=rob.link_force.copy(), feet_pos=lp[:, feet].copy(), feet_vel=lv[:, feet].copy())
+    sim.step = sim_step
+    n = lambda t: t.detach().cpu().numpy().copy()
+    per = {}
+
+    def put(t, k, v):
+        per.setdefault(k, []).append(np.asarray(v))
+    for t in range(args.steps):
+        a = 0.8 * torch.randn(N, A, generator=g)
+        if t == 1:
+            a[0] = 150.0                                                            # exercise clip_actions
+        ret = env.step(a.clone())
+        put(t, "actions", n(a))
+        for k, v in phys.items():
+            put(t, "phys/" + k, v.astype(np.float32))
+        o = dict(obs_buf=n(ret[0]), rew_buf=n(env.rew_buf), reset_buf=n(env.reset_buf).astype(np.uint8),
+                 time_out_buf=n(env.time_out_buf).astype(np.uint8), commands=n(env.commands),
+                 episode_length=n(env.episode_length_buf), fail_buf=n(env.fail_buf), feet_air_time=n(env.feet_air_time),
+                 last_contacts=n(env.last_contacts).astype(np.uint8),
+                 episode_sums=np.stack([n(env.episode_sums[k]) for k in sum_names], axis=1),
+                 env_origins=n(sim._env_origins), dof_pos=n(sim._dof_pos), dof_vel=n(sim._dof_vel), base_pos=n(sim._base_pos),
+                 base_lin_vel=n(sim._base_lin_vel), base_ang_vel=n(sim._base_ang_vel),
+                 projected_gravity=n(sim._projected_gravity), base_euler=n(sim._base_euler),
+                 friction=n(sim._friction_values), added_mass=n(sim._added_base_mass), com_bias=n(sim._base_com_bias),
+                 kp_scale=n(sim._kp_scale), kd_scale=n(sim._kd_scale), rand_push_vels=n(sim._rand_push_vels),
+                 actions_buf=n(env.actions), last_actions=n(env.last_actions), llast_actions=n(env.llast_actions),
+                 measured_heights=n(sim._measured_heights), link_contact_forces=n(sim._link_contact_forces),
+                 feet_pos=n(sim._feet_pos), feet_vel=n(sim._feet_vel),
+                 end_q=rob.q[:, didx].astype(np.float32), end_qd=rob.qd[:, didx].astype(np.float32),
+                 end_state=rob.state.astype(np.float32))
+        if spec.heightfield:
+            o.update(terrain_levels=n(sim._terrain_levels), height_around_feet=n(sim._height_around_feet),
+                     normal_vector_around_feet=n(sim._normal_vector_around_feet))
+        if spec.obtain_link_contact_states:
+            o["link_contact_states"] = n(sim._link_contact_states)
+        if ret[1] is not None:
+            o["privileged_obs_buf"] = n(ret[1])
+        if args.task == "go2_ts" and t in (args.steps // 2, args.steps - 1):
+            rec[f"hist{t}/obs_history"] = n(env.obs_history)
+            rec[f"hist{t}/critic_obs_buf"] = n(env.critic_obs_buf)
+        for k, v in o.items():
+            put(t, "out/" + k, v)
+    for k, v in per.items():
+        rec[k] = np.stack(v)
+    name = args.name or f"{args.task}_n{N}"
+    if spec.heightfield:
+        # the terrain itself is a fixture of its own (tests/golden/go2_rough_terrain.npz); keep a checksum here
+        rec["terrain_crc"] = np.int64(int(np.asarray(sim._height_samples.numpy(), np.int64).sum()))
+    rec["meta/task"] = np.array(args.task)
+    rec["meta/seed"] = np.int64(spec.seed)
+    rec["meta/contact_links"] = np.array(spec.contact_state_link_names)
+    rec["meta/sum_names"] = np.array(sum_names)
+    out = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(out, **rec)
+    resets = int(rec["out/reset_buf"].sum())
+    print(f"wrote {out}: {os.path.getsize(out)/1e3:.0f} kB, resets={resets}, time_outs={int(rec['out/time_out_buf'].sum())}")
+    if spec.heightfield:
+        tpath = os.path.join(ROOT, "tests", "golden", "go2_rough_terrain.npz")
+        if not os.path.exists(tpath):
+            np.savez_compressed(tpath, height_samples=sim._height_samples.numpy().astype(np.int16),
+                                terrain_origins=sim._terrain_origins.numpy().astype(np.float32))
+            print(f"wrote {tpath}: {os.path.getsize(tpath)/1e3:.0f} kB")
+
+
+if __name__ == "__main__":
+    main()
