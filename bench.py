@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py -- Go2 rough-terrain env-steps/s (physics substeps x envs), 4096 envs per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one policy step of BASELINE config C2 (`go2_ts`, heightfield curriculum, height-scan obs): the decimated
+PD + rigid-body kernel followed by the fused post_physics_step kernel.  Envs shard as contiguous blocks, one process
+per GPU, no collective on the data path (weak scaling).  The line printed by rank 0 carries
+
+  value        whole-job env-substeps/s, inputs resident in HBM, CUDA-event time summed over K steps (max over ranks),
+               L2 flushed between timed steps
+  e2e          the same metric through FusedLeggedEnv.step() with HOST action buffers (pinned H2D each step) and a
+               D2H read of rewards + resets each step
+  roofline     the fused env kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  kernels      per-kernel average duration, share of the step and static resources (the dynamics kernel is latency /
+               issue bound)
+  cpu_baseline the oracle port timed on host cores on a bounded sample (rank 0, N=1 only)
+
+`--impl reference` times the CPU restatement of the reference path (oracle port; the reference's engine cannot be
+installed) with all host threads and prints the same line shape with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (physics substeps x envs), Go2 rough terrain, 4096 envs/GPU"
+UNIT = "env-substeps/s"
+ENVS_PER_GPU = 4096
+TASK = "go2_ts"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port on all host threads (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from hcr_genesis_lr_cl_b200 import task_spec as T
+    from hcr_genesis_lr_cl_b200.terrain_assets import load_go2_rough_terrain
+    from oracle.cpu_baseline import time_cpu_baseline
+    from oracle import physics
+    physics.build()
+    spec = T.PRESETS[TASK]()
+    cores = os.cpu_count() or 1
+    sample_envs = 256 * cores
+    res = time_cpu_baseline(spec, load_go2_rough_terrain(), sample_envs, steps=max(args.steps, 1), threads=cores, warmup=max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{TASK}: Go2 rough-terrain heightfield curriculum with height-scan obs, {ENVS_PER_GPU} envs/GPU "
+                               f"(bounded CPU sample per step: {sample_envs} envs)", "decimation": spec.decimation},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from hcr_genesis_lr_cl_b200 import accounting, build, task_spec as T
+    from hcr_genesis_lr_cl_b200.fused_env import FusedLeggedEnv
+    from hcr_genesis_lr_cl_b200.terrain_assets import load_go2_rough_terrain
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    build.build()
+    spec = T.PRESETS[TASK]()
+    terrain = load_go2_rough_terrain()
+    N = args.envs
+    env = FusedLeggedEnv(spec, N, dev, terrain=terrain, env_offset=rank * N, num_envs_global=world * N)
+    sim = env.simulator
+    env.reset()
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    env.episode_length_buf = torch.randint(0, int(env.max_episode_length), (N,), generator=g).to(dev)  # on_policy_runner.py:169
+    pool = [torch.randn(N, spec.num_actions, generator=g).to(dev) for _ in range(16)]          # policy at init: N(0,1) actions
+    host_pool = [p.cpu().pin_memory() for p in pool]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)                    # > 126 MB L2
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: per-kernel CUDA events on the launching (current) stream, L2 flushed between steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    for i in range(W):
+        env.step(pool[i % 16])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = sim.launch_count
+    for i in range(K):
+        flush.zero_()
+        a = pool[(W + i) % 16]
+        ev[i][0].record()
+        sim.step(a)
+        ev[i][1].record()
+        env.common_step_counter += 1
+        env._apply_pending_curriculum()
+        sim.fused_post_step(env.common_step_counter, env.command_ranges["lin_vel_x"])
+        ev[i][2].record()
+        env._fill_extras()
+    barrier()
+    launches = sim.launch_count - launches0
+    t_dyn = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    t_env = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    total_ms = t_dyn * K + t_env * K
+    # ---- end to end through the public API with host buffers
+    rew_host = torch.empty(N, dtype=torch.float32).pin_memory()
+    rst_host = torch.empty(N, dtype=torch.bool).pin_memory()
+    act_dev = torch.empty(N, spec.num_actions, device=dev)
+    for i in range(W):
+        act_dev.copy_(host_pool[i % 16], non_blocking=True)
+        env.step(act_dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        act_dev.copy_(host_pool[(W + i) % 16], non_blocking=True)
+        out = env.step(act_dev)
+        rew_host.copy_(env.rew_buf, non_blocking=True)
+        rst_host.copy_(env.reset_buf, non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    times = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(times[0]), float(times[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_total = N * world
+    value = n_total * spec.decimation * K / (total_ms * 1e-3)
+    e2e = n_total * spec.decimation * K / (e2e_ms * 1e-3)
+    model = sim._model
+    peak, peak_src = _peaks()
+    env_bytes = accounting.env_kernel_bytes(spec, model) * N
+    dyn_bytes = accounting.dynamics_kernel_bytes(spec, model) * N
+    achieved = env_bytes / (t_env * 1e-3) / 1e9
+    ki_env, ki_dyn = sim.kernel_info("env"), sim.kernel_info("dynamics")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{TASK}: Go2 rough-terrain heightfield curriculum with height-scan obs, {N} envs/GPU",
+                   "envs_per_gpu": N, "decimation": spec.decimation, "pgs_iterations": spec.pgs_iterations,
+                   "actions": "N(0,1) (policy at init)", "l2": "flushed between timed steps (256 MB write)",
+                   "parallelism": f"env-sharded x{world}, no data-path collective"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": N * spec.num_actions * 4 * world, "d2h_bytes_per_step": N * 5 * world,
+                "ms_per_step": e2e_ms / K},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "env_post_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": env_bytes, "avg_launch_ms": t_env},
+        "kernels": {
+            "dynamics_step_kernel": {"avg_ms": t_dyn, "share": t_dyn / (t_dyn + t_env), "bound": "latency/issue", **ki_dyn,
+                                     "algorithmic_bytes_per_launch": dyn_bytes, "hbm_gbs": dyn_bytes / (t_dyn * 1e-3) / 1e9},
+            "env_post_step_kernel": {"avg_ms": t_env, "share": t_env / (t_dyn + t_env), "bound": "hbm", **ki_env},
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import physics
+        from oracle.cpu_baseline import time_cpu_baseline
+        physics.build()
+        cores = os.cpu_count() or 1
+        res = time_cpu_baseline(spec, terrain, 256 * cores, steps=20, threads=cores, warmup=2)
+        line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20          # bounded CPU run
+        args.warmup = min(args.warmup, 2)
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,155 @@
+// b200_step.cu -- C ABI (include/b200_step.h) over the two sm_100a kernels.  Built by nvcc only
+// (hcr_genesis_lr_cl_b200/build.py); there is no CPU implementation behind these symbols.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include "dynamics_kernel.cuh"
+#include "env_kernel.cuh"
+
+static thread_local std::string g_err;
+static int fail(const char *what, cudaError_t e = cudaSuccess) {
+    g_err = what;
+    if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+    return 1;
+}
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(#x, e_); } while (0)
+
+struct B200Handle {
+    TaskDev task;
+    B200Buffers bufs;
+    bool bound = false;
+    ModelDev model{};
+    TerrainDev terrain{};
+    float *d_model_f = nullptr;
+    int *d_model_i = nullptr;
+    long long launches = 0;
+    int dyn_smem = 0, env_smem = 0;
+};
+
+extern "C" {
+
+const char *b200_last_error(void) { return g_err.c_str(); }
+
+int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const int32_t *ti, int n_ti, const float *tf, int n_tf,
+                B200Handle **out) {
+    if (!mi || !mf || !ti || !tf || !out) return fail("b200_create: null argument");
+    if (n_ti != TI_COUNT || n_tf != TF_COUNT) return fail("b200_create: task descriptor size does not match this library (header drift)");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return fail("b200_create: no CUDA device");
+    B200Handle *h = new B200Handle();
+    memcpy(h->task.f, tf, sizeof(float) * TF_COUNT);
+    memcpy(h->task.i, ti, sizeof(int) * TI_COUNT);
+    const int C = ti[TI_C], A = ti[TI_A], L = ti[TI_L], NS = ti[TI_NSPHERES];
+    if (ti[TI_D] != 3 || (C != 2 && C != 4) || A != 3 * C) { delete h; return fail("b200_create: unsupported kinematic tree (need 2 or 4 chains of 3 joints)"); }
+    if (L > B200_MAX_LINKS || NS > B200_MAX_SPHERES || ti[TI_F] > B200_MAX_FEET) { delete h; return fail("b200_create: robot exceeds compiled limits"); }
+    const int nb = 1 + A;
+    if (n_mf != nb * B200_BODY_STRIDE + 3 * L + 4 * NS || n_mi != 8 + L + 2 * NS) { delete h; return fail("b200_create: packed model size mismatch"); }
+    CK(cudaMalloc(&h->d_model_f, sizeof(float) * n_mf));
+    CK(cudaMalloc(&h->d_model_i, sizeof(int) * n_mi));
+    CK(cudaMemcpy(h->d_model_f, mf, sizeof(float) * n_mf, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_model_i, mi, sizeof(int) * n_mi, cudaMemcpyHostToDevice));
+    h->model.body = h->d_model_f; h->model.link_off = h->d_model_f + nb * B200_BODY_STRIDE; h->model.sph = h->model.link_off + 3 * L;
+    h->model.link_body = h->d_model_i + 8; h->model.sph_body = h->model.link_body + L; h->model.sph_link = h->model.sph_body + NS;
+    h->dyn_smem = dyn_smem_bytes(DYN_WARPS_PER_BLOCK);
+    h->env_smem = env_smem_bytes(ENV_WARPS_PER_BLOCK);
+    CK(cudaFuncSetAttribute(dynamics_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
+    CK(cudaFuncSetAttribute(dynamics_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
+    *out = h;
+    return 0;
+}
+
+void b200_destroy(B200Handle *h) {
+    if (!h) return;
+    cudaFree(h->d_model_f); cudaFree(h->d_model_i);
+    delete h;
+}
+
+int b200_set_terrain(B200Handle *h, const int16_t *hf, int rows, int cols, const float *origins, int levels, int types) {
+    if (!h) return fail("b200_set_terrain: null handle");
+    if (h->task.i[TI_HEIGHTFIELD] && (!hf || rows < 3 || cols < 3)) return fail("b200_set_terrain: heightfield task needs height samples");
+    if (h->task.i[TI_TERRAIN_CURRICULUM] && (!origins || levels != h->task.i[TI_NUM_LEVELS] || types != h->task.i[TI_NUM_TYPES]))
+        return fail("b200_set_terrain: terrain origins do not match the task descriptor");
+    h->terrain.hf = h->task.i[TI_HEIGHTFIELD] ? hf : nullptr; h->terrain.rows = rows; h->terrain.cols = cols;
+    h->terrain.origins = origins; h->terrain.levels = levels; h->terrain.types = types;
+    return 0;
+}
+
+int b200_bind_buffers(B200Handle *h, const B200Buffers *b) {
+    if (!h || !b) return fail("b200_bind_buffers: null argument");
+    const void *const *p = (const void *const *)b;
+    const size_t n = sizeof(B200Buffers) / sizeof(void *);
+    for (size_t k = 0; k < n; k++) {
+        const bool optional = (&p[k] == (const void *const *)&b->height_cells);
+        if (!p[k] && !optional) return fail("b200_bind_buffers: null buffer pointer");
+    }
+    h->bufs = *b; h->bound = true;
+    return 0;
+}
+
+static int check_ready(B200Handle *h, const char *who) {
+    if (!h) return fail("null handle");
+    if (!h->bound) { g_err = std::string(who) + ": buffers not bound"; return 1; }
+    if (h->task.i[TI_HEIGHTFIELD] && !h->terrain.hf) { g_err = std::string(who) + ": terrain not set"; return 1; }
+    return 0;
+}
+
+int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
+    if (check_ready(h, "b200_dynamics_step")) return 1;
+    if (!actions) return fail("b200_dynamics_step: null actions");
+    const int N = h->task.i[TI_NUM_ENVS];
+    const dim3 grid((N + DYN_WARPS_PER_BLOCK - 1) / DYN_WARPS_PER_BLOCK), block(DYN_WARPS_PER_BLOCK * 32);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->task.i[TI_C] == 4) dynamics_step_kernel<4><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions);
+    else dynamics_step_kernel<2><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_env(B200Handle *h, long long step, float lo, float span, int parity, int mask, int force, void *stream) {
+    const int N = h->task.i[TI_NUM_ENVS];
+    const int n_sums = h->task.i[TI_N_REWARDS] + (h->task.i[TI_TERMINATION_COL] >= 0 ? 1 : 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mask & PHASE_RESET) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 2), s));
+    EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.parity = parity & 1; call.phase_mask = mask; call.force_reset = force;
+    const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
+    env_post_step_kernel<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200_env_post_step(B200Handle *h, long long step, float lo, float span, int parity, int mask, void *stream) {
+    if (check_ready(h, "b200_env_post_step")) return 1;
+    if ((mask & PHASE_ALL) == 0) return fail("b200_env_post_step: empty phase mask");
+    return launch_env(h, step, lo, span, parity, mask & PHASE_ALL, 0, stream);
+}
+
+int b200_reset_all(B200Handle *h, long long step, float lo, float span, int parity, void *stream) {
+    if (check_ready(h, "b200_reset_all")) return 1;
+    return launch_env(h, step, lo, span, parity, PHASE_RESET, 1, stream);
+}
+
+int b200_kernel_info(B200Handle *h, const char *kernel, int *regs, int *smem, int *blocks_per_sm, int *block_threads) {
+    if (!h || !kernel) return fail("b200_kernel_info: null argument");
+    cudaFuncAttributes fa; int nb = 0, threads = 0, dyn = 0;
+    if (!strcmp(kernel, "dynamics")) {
+        threads = DYN_WARPS_PER_BLOCK * 32; dyn = h->dyn_smem;
+        if (h->task.i[TI_C] == 4) { CK(cudaFuncGetAttributes(&fa, dynamics_step_kernel<4>)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dynamics_step_kernel<4>, threads, dyn)); }
+        else { CK(cudaFuncGetAttributes(&fa, dynamics_step_kernel<2>)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dynamics_step_kernel<2>, threads, dyn)); }
+    } else if (!strcmp(kernel, "env")) {
+        threads = ENV_WARPS_PER_BLOCK * 32; dyn = h->env_smem;
+        CK(cudaFuncGetAttributes(&fa, env_post_step_kernel)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, env_post_step_kernel, threads, dyn));
+    } else return fail("b200_kernel_info: unknown kernel name");
+    if (regs) *regs = fa.numRegs;
+    if (smem) *smem = (int)fa.sharedSizeBytes + dyn;
+    if (blocks_per_sm) *blocks_per_sm = nb;
+    if (block_threads) *block_threads = threads;
+    return 0;
+}
+
+long long b200_launch_count(B200Handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

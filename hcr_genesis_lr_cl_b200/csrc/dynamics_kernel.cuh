@@ -1,0 +1,753 @@
+// dynamics_kernel.cuh -- decimated PD torque loop + articulated rigid-body substeps, one env per warp.
+//
+// Replaces, for one policy step (reference paths relative to the LeggedGym-Ex root):
+//   LeggedRobot._pre_sim_step              legged_gym/envs/base/legged_robot.py:230-252   (clip, action history)
+//   GenesisSimulator.step                  legged_gym/simulator/genesis_simulator.py:20-33 (last_* copy, decimation loop)
+//   GenesisSimulator._compute_torques      legged_gym/simulator/genesis_simulator.py:630-642
+//   scene.step() of the third-party engine legged_gym/simulator/genesis_simulator.py:29    (formulation: DESIGN.md)
+//   get_links_pos/vel/net_contact_force    legged_gym/simulator/genesis_simulator.py:49-51
+//
+// Mapping to the hardware.  A warp owns one env for all `decimation` substeps; state stays in registers between
+// substeps, HBM is touched once on entry and once on exit (~0.5 KB per env).  The robot is a star: a floating
+// base plus C serial chains of 3 revolute joints, so
+//   * lanes 0..C-1 each walk one chain (FK, RNE bias, CRBA) with all spatial quantities expressed about the
+//     base origin in world axes -- composite inertias and forces then add without any frame transforms;
+//   * the mass matrix is an arrowhead [diag(D_c) B; B^T M_bb]: each chain lane inverts its own 3x3 block, the
+//     6x6 Schur complement is reduced with shuffles and factorised redundantly by every lane (no sync needed);
+//   * collision spheres are tested two per lane against the L2-resident int16 heightfield, the active set is
+//     compacted with ballots;
+//   * each of the <=32 constraint rows (3 per contact + joint limits + frictionloss) lives in one lane: the lane
+//     solves M y = J^T for its row, forms its column of A = J M^-1 J^T, and the projected Gauss-Seidel sweep
+//     broadcasts one delta per row with a shuffle (friction-cone projection per contact);
+//   * per-warp scratch (frames, M^-1 factors, J rows, A) is staged in shared memory, the robot model once per CTA.
+// The kernel is latency/issue bound, not HBM bound; tensor cores do not apply.
+#pragma once
+#include "cuda_compat.cuh"
+#include "../../include/b200_step.h"
+
+#define DYN_WARPS_PER_BLOCK 4
+
+struct TaskDev {
+    float f[TF_COUNT];
+    int i[TI_COUNT];
+};
+
+struct ModelDev {          // device pointers to the packed robot model (see robot_model.py)
+    const float *body;     // [nb][20]
+    const float *link_off; // [nlinks][3]
+    const float *sph;      // [nspheres][4]
+    const int *link_body;  // [nlinks]
+    const int *sph_body;   // [nspheres]
+    const int *sph_link;   // [nspheres]
+};
+
+struct TerrainDev {
+    const int16_t *hf;     // [rows][cols] or nullptr (plane)
+    const float *origins;  // [levels][types][3]
+    int rows, cols, levels, types;
+};
+
+// ---- per-warp shared scratch (floats) ----
+#define WS_FR 0                         // frames [13][12]  R(9) o(3)
+#define WS_AX (WS_FR + 13 * 12)         // joint axes [12][3]
+#define WS_VEL (WS_AX + 36)             // body spatial velocity [13][6] (w, v)
+#define WS_MI (WS_VEL + 78)             // per chain: Dinv(6) G(18) ; then Sinv(21)
+#define WS_NU (WS_MI + 4 * 24 + 24)     // generalized velocity [18]
+#define WS_AF (WS_NU + 18)              // smooth acceleration [18]
+#define WS_CT (WS_AF + 18)              // contacts [8][12]
+#define WS_AUX (WS_CT + 96)             // aux rows [8][4]: joint, sign, pos, bound
+#define WS_JR (WS_AUX + 32)             // J rows [32][10]: Jb(6) Jl(3) chain
+#define WS_AM (WS_JR + 320)             // A [32][33]
+#define WS_FV (WS_AM + 32 * 33)         // row force vectors [32][4]
+#define WS_LF (WS_FV + 128)             // link forces [17*3]
+#define WS_Q (WS_LF + 52)               // joint q [12]
+#define WS_TOTAL (WS_Q + 12)
+
+#define MS_BODY 0
+#define MS_LINK (MS_BODY + B200_MAX_BODIES * B200_BODY_STRIDE)
+#define MS_SPH (MS_LINK + B200_MAX_LINKS * 3)
+#define MS_INT (MS_SPH + B200_MAX_SPHERES * 4)      // ints: link_body[17], sph_body[64], sph_link[64]
+#define MS_TOTAL (MS_INT + B200_MAX_LINKS + 2 * B200_MAX_SPHERES)
+
+__host__ __device__ inline int dyn_smem_bytes(int warps) { return (MS_TOTAL + warps * WS_TOTAL) * 4; }
+
+struct SIn { float m; f3 h; float I[6]; };  // spatial inertia about O: I = xx yy zz xy xz yz
+
+__device__ __forceinline__ void si_apply(const SIn &s, f3 w, f3 v, f3 &L, f3 &P) {
+    P = v * s.m + cross3(w, s.h);
+    L = mk3(s.I[0] * w.x + s.I[3] * w.y + s.I[4] * w.z, s.I[3] * w.x + s.I[1] * w.y + s.I[5] * w.z,
+            s.I[4] * w.x + s.I[5] * w.y + s.I[2] * w.z) + cross3(s.h, v);
+}
+__device__ __forceinline__ void si_acc(SIn &a, const SIn &b) {
+    a.m += b.m; a.h = a.h + b.h;
+#pragma unroll
+    for (int k = 0; k < 6; k++) a.I[k] += b.I[k];
+}
+// body inertia (mass m, com c rel. O, local inertia Il rotated by R) about O in world axes
+__device__ __forceinline__ SIn si_body(float m, f3 c, const float *Il, const m33 &R) {
+    SIn s; s.m = m; s.h = c * m;
+    // Iw = R Il R^T
+    float t[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        t[3 * i + 0] = R.m[3 * i] * Il[0] + R.m[3 * i + 1] * Il[3] + R.m[3 * i + 2] * Il[4];
+        t[3 * i + 1] = R.m[3 * i] * Il[3] + R.m[3 * i + 1] * Il[1] + R.m[3 * i + 2] * Il[5];
+        t[3 * i + 2] = R.m[3 * i] * Il[4] + R.m[3 * i + 1] * Il[5] + R.m[3 * i + 2] * Il[2];
+    }
+    const float cc = dot3(c, c);
+    s.I[0] = t[0] * R.m[0] + t[1] * R.m[1] + t[2] * R.m[2] + m * (cc - c.x * c.x);
+    s.I[1] = t[3] * R.m[3] + t[4] * R.m[4] + t[5] * R.m[5] + m * (cc - c.y * c.y);
+    s.I[2] = t[6] * R.m[6] + t[7] * R.m[7] + t[8] * R.m[8] + m * (cc - c.z * c.z);
+    s.I[3] = t[0] * R.m[3] + t[1] * R.m[4] + t[2] * R.m[5] - m * c.x * c.y;
+    s.I[4] = t[0] * R.m[6] + t[1] * R.m[7] + t[2] * R.m[8] - m * c.x * c.z;
+    s.I[5] = t[3] * R.m[6] + t[4] * R.m[7] + t[5] * R.m[8] - m * c.y * c.z;
+    return s;
+}
+
+__device__ __forceinline__ m33 quat_to_mat(float w, float x, float y, float z) {
+    m33 R;
+    R.m[0] = 1 - 2 * (y * y + z * z); R.m[1] = 2 * (x * y - w * z); R.m[2] = 2 * (x * z + w * y);
+    R.m[3] = 2 * (x * y + w * z); R.m[4] = 1 - 2 * (x * x + z * z); R.m[5] = 2 * (y * z - w * x);
+    R.m[6] = 2 * (x * z - w * y); R.m[7] = 2 * (y * z + w * x); R.m[8] = 1 - 2 * (x * x + y * y);
+    return R;
+}
+__device__ __forceinline__ m33 axis_angle(f3 a, float th) {
+    float s, c; sincosf(th, &s, &c);
+    const float t = 1 - c; m33 R;
+    R.m[0] = c + a.x * a.x * t;       R.m[1] = a.x * a.y * t - a.z * s; R.m[2] = a.x * a.z * t + a.y * s;
+    R.m[3] = a.y * a.x * t + a.z * s; R.m[4] = c + a.y * a.y * t;       R.m[5] = a.y * a.z * t - a.x * s;
+    R.m[6] = a.z * a.x * t - a.y * s; R.m[7] = a.z * a.y * t + a.x * s; R.m[8] = c + a.z * a.z * t;
+    return R;
+}
+
+// terrain height and unit normal under world point (x, y): the triangle of the heightfield cell below it
+__device__ __forceinline__ void terrain_query(const TerrainDev &tr, float hs, float vs, float border, float x, float y, float &h, f3 &n) {
+    if (tr.hf == nullptr) { h = 0.f; n = mk3(0.f, 0.f, 1.f); return; }
+    const float gx = (x + border) / hs, gy = (y + border) / hs;
+    int i = (int)floorf(gx), j = (int)floorf(gy);
+    i = max(0, min(i, tr.rows - 2)); j = max(0, min(j, tr.cols - 2));
+    const float u = fminf(fmaxf(gx - (float)i, 0.f), 1.f), w = fminf(fmaxf(gy - (float)j, 0.f), 1.f);
+    const int16_t *p = tr.hf + (size_t)i * tr.cols + j;
+    const float h00 = (float)__ldg(p) * vs, h01 = (float)__ldg(p + 1) * vs;
+    const float h10 = (float)__ldg(p + tr.cols) * vs, h11 = (float)__ldg(p + tr.cols + 1) * vs;
+    float dhx, dhy;
+    if (u + w <= 1.f) { dhx = h10 - h00; dhy = h01 - h00; h = h00 + u * dhx + w * dhy; }
+    else { dhx = h11 - h01; dhy = h11 - h10; h = h11 - (1.f - u) * dhx - (1.f - w) * dhy; }
+    const f3 g = mk3(-dhx / hs, -dhy / hs, 1.f);
+    n = g * (1.f / sqrtf(dot3(g, g)));
+}
+
+__device__ __forceinline__ float impedance(const float *tf, float pos) {
+    const float x = fabsf(pos) / tf[TF_WIDTH];
+    if (x >= 1.f) return tf[TF_DMAX];
+    const float mid = tf[TF_MID], p = tf[TF_POWER];
+    float y;
+    if (x < mid) y = powf(x, p) / powf(mid, p - 1.f);
+    else y = 1.f - powf(1.f - x, p) / powf(1.f - mid, p - 1.f);
+    return tf[TF_D0] + y * (tf[TF_DMAX] - tf[TF_D0]);
+}
+
+// symmetric 6x6 stored as lower triangle, index (i>=j): i*(i+1)/2 + j
+__device__ __forceinline__ constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+// in: S (lower tri, SPD).  out: Sinv (lower tri)
+__device__ __forceinline__ void spd6_inverse(const float *S, float *Sinv) {
+    float L[21], Li[21];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        float d = S[tri(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)];
+        const float r = rsqrtf(d);
+        L[tri(j, j)] = d * r;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            float s = S[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= L[tri(i, k)] * L[tri(j, k)];
+            L[tri(i, j)] = s * r;
+        }
+    }
+    // Li = L^-1 (lower)
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        Li[tri(j, j)] = 1.f / L[tri(j, j)];
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = j; k < i; k++) s += L[tri(i, k)] * Li[tri(k, j)];
+            Li[tri(i, j)] = -s / L[tri(i, i)];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = i; k < 6; k++) s += Li[tri(k, i)] * Li[tri(k, j)];
+            Sinv[tri(i, j)] = s;
+        }
+}
+
+// One env, `decimation` substeps.  C chains of 3 joints.  All 32 lanes execute every collective.
+template <int C>
+__device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const float *ms, float *ws,
+                              const float *actions_in, int env, int lane) {
+    const float *tf = T.f;
+    const int A = 3 * C, NB = 1 + 3 * C, L = T.i[TI_L], NS = T.i[TI_NSPHERES];
+    const int *msi = (const int *)(ms + MS_INT);
+    const float h = tf[TF_SIM_DT];
+    const bool leg = lane < C;
+    const int c = leg ? lane : C - 1;       // chain walked by this lane (lanes >= C shadow the last chain, results masked)
+    const float legm = leg ? 1.f : 0.f;
+
+    // ---------------- load state ----------------
+    f3 p = mk3(B.base_pos[env * 3], B.base_pos[env * 3 + 1], B.base_pos[env * 3 + 2]);
+    float Qw = B.base_quat_wxyz[env * 4], Qx = B.base_quat_wxyz[env * 4 + 1], Qy = B.base_quat_wxyz[env * 4 + 2], Qz = B.base_quat_wxyz[env * 4 + 3];
+    f3 vb = mk3(B.base_lin_w[env * 3], B.base_lin_w[env * 3 + 1], B.base_lin_w[env * 3 + 2]);
+    f3 wb = mk3(B.base_ang_w[env * 3], B.base_ang_w[env * 3 + 1], B.base_ang_w[env * 3 + 2]);
+    float q[3], qd[3], tgt[3], kp[3], kd[3], arm[3], dmp[3], fls[3], tau[3];
+    const float mass_add = B.added_mass[env], fric_ratio = B.friction[env];
+    const f3 com_shift = mk3(B.com_bias[env * 3], B.com_bias[env * 3 + 1], B.com_bias[env * 3 + 2]);
+    const float env_arm = B.joint_armature[env], env_dmp = B.joint_damping[env], env_fls = B.joint_friction[env];
+
+    // ---------------- pre-step: action history, last_* (legged_robot.py:230-252, genesis_simulator.py:21-24) ----------------
+    if (lane < A) {
+        const int o = env * A + lane;
+        const float a = fminf(fmaxf(actions_in[o], -tf[TF_CLIP_ACTIONS]), tf[TF_CLIP_ACTIONS]);
+        B.llast_actions[o] = B.last_actions[o];
+        B.last_actions[o] = B.actions[o];
+        B.actions[o] = a;
+        B.last_dof_vel[o] = B.dof_vel[o];
+        if (lane < 3 * T.i[TI_F]) B.last_feet_vel[env * 3 * T.i[TI_F] + lane] = B.feet_vel[env * 3 * T.i[TI_F] + lane];
+        if (lane < 3) { B.last_base_lin_vel[env * 3 + lane] = B.base_lin_vel[env * 3 + lane]; B.last_base_ang_vel[env * 3 + lane] = B.base_ang_vel[env * 3 + lane]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int j = 3 * c + k, o = env * A + j;
+        q[k] = B.dof_pos[o]; qd[k] = B.dof_vel[o];
+        const float a = fminf(fmaxf(actions_in[o], -tf[TF_CLIP_ACTIONS]), tf[TF_CLIP_ACTIONS]);
+        tgt[k] = a * tf[TF_ACTION_SCALE] + tf[TF_DEFAULT_DOF_POS + j];
+        kp[k] = B.kp_scale[o] * tf[TF_KP]; kd[k] = B.kd_scale[o] * tf[TF_KD];
+        arm[k] = T.i[TI_RAND_ARMATURE] ? env_arm : ms[MS_BODY + (1 + j) * B200_BODY_STRIDE + 19];
+        dmp[k] = T.i[TI_RAND_JDAMPING] ? env_dmp : 0.f;
+        fls[k] = T.i[TI_RAND_JFRICTION] ? env_fls : 0.f;
+        tau[k] = 0.f;
+    }
+    float mu = tf[TF_GEOM_MU] * fric_ratio; mu = fmaxf(mu, tf[TF_TERRAIN_MU]);
+    const float kk = 1.f / (tf[TF_DMAX] * tf[TF_DMAX] * tf[TF_TC] * tf[TF_TC] * tf[TF_DAMPRATIO] * tf[TF_DAMPRATIO]);
+    const float bd = 2.f / (tf[TF_DMAX] * tf[TF_TC]);
+
+    for (int sub = 0; sub <= T.i[TI_DECIMATION]; sub++) {
+        const bool last_pass = sub == T.i[TI_DECIMATION];   // kinematics-only pass for the outputs
+        // ---------------- PD torque (genesis_simulator.py:630-642) ----------------
+        if (!last_pass) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) tau[k] = kp[k] * (tgt[k] - q[k]) - kd[k] * qd[k];
+        }
+        // ---------------- forward kinematics, velocities, RNE, CRBA along this lane's chain ----------------
+        const m33 R0 = quat_to_mat(Qw, Qx, Qy, Qz);
+        f3 a_[3], sv_[3], fn_[3], ff_[3];
+        SIn si_[3];
+        {
+            m33 Rp = R0; f3 op = mk3(0.f, 0.f, 0.f), wp = wb, vp = vb;
+            f3 awp = mk3(0.f, 0.f, 0.f), avp = cross3(vb, wb) + mk3(0.f, 0.f, tf[TF_GRAV]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int b = 1 + 3 * c + k;
+                const float *Bd = ms + MS_BODY + b * B200_BODY_STRIDE;
+                const f3 ax = mk3(Bd[3], Bd[4], Bd[5]);
+                const f3 o = op + mul(Rp, mk3(Bd[0], Bd[1], Bd[2]));
+                const f3 a = mul(Rp, ax);
+                const f3 sv = cross3(o, a);
+                const m33 Rk = mul(Rp, axis_angle(ax, q[k]));
+                const f3 w = wp + a * qd[k], v = vp + sv * qd[k];
+                if (leg) {
+                    float *fr = ws + WS_FR + b * 12;
+#pragma unroll
+                    for (int e = 0; e < 9; e++) fr[e] = Rk.m[e];
+                    fr[9] = o.x; fr[10] = o.y; fr[11] = o.z;
+                    float *axp = ws + WS_AX + (b - 1) * 3; axp[0] = a.x; axp[1] = a.y; axp[2] = a.z;
+                    float *vl = ws + WS_VEL + b * 6; vl[0] = w.x; vl[1] = w.y; vl[2] = w.z; vl[3] = v.x; vl[4] = v.y; vl[5] = v.z;
+                }
+                if (!last_pass) {
+                    const f3 aw = awp + cross3(w, a) * qd[k];
+                    const f3 av = avp + (cross3(w, sv) + cross3(v, a)) * qd[k];
+                    const f3 cm = o + mul(Rk, mk3(Bd[6], Bd[7], Bd[8]));
+                    si_[k] = si_body(Bd[9], cm, Bd + 10, Rk);
+                    f3 LA, PA, LV, PV;
+                    si_apply(si_[k], aw, av, LA, PA);
+                    si_apply(si_[k], w, v, LV, PV);
+                    fn_[k] = LA + cross3(w, LV) + cross3(v, PV);
+                    ff_[k] = PA + cross3(w, PV);
+                    awp = aw; avp = av;
+                }
+                a_[k] = a; sv_[k] = sv; Rp = Rk; op = o; wp = w; vp = v;
+            }
+        }
+        if (lane == 0) {
+            float *fr = ws + WS_FR;
+#pragma unroll
+            for (int e = 0; e < 9; e++) fr[e] = R0.m[e];
+            fr[9] = fr[10] = fr[11] = 0.f;
+            float *vl = ws + WS_VEL; vl[0] = wb.x; vl[1] = wb.y; vl[2] = wb.z; vl[3] = vb.x; vl[4] = vb.y; vl[5] = vb.z;
+        }
+        __syncwarp();
+        if (last_pass) break;
+
+        // backward pass along the chain: composite inertias, bias forces, CRBA columns
+        float Dm[6];           // chain block, lower tri (00,10,11,20,21,22)
+        f3 BP[3], BL[3];       // base coupling: column k of B^T = (P_k (lin rows), L_k (ang rows))
+        float biasl[3];
+        SIn comp = si_[2];
+        f3 fns = fn_[2], ffs = ff_[2];
+#pragma unroll
+        for (int k = 2; k >= 0; k--) {
+            if (k < 2) { si_acc(comp, si_[k]); fns = fns + fn_[k]; ffs = ffs + ff_[k]; }
+            biasl[k] = dot3(a_[k], fns) + dot3(sv_[k], ffs);
+            f3 Lk, Pk; si_apply(comp, a_[k], sv_[k], Lk, Pk);
+            BP[k] = Pk; BL[k] = Lk;
+#pragma unroll
+            for (int i2 = 0; i2 <= k; i2++) Dm[tri(k, i2)] = dot3(a_[i2], Lk) + dot3(sv_[i2], Pk);
+            Dm[tri(k, k)] += arm[k] + h * dmp[k];
+        }
+        // base body + reduction of chain roots
+        SIn cb;
+        f3 fnb, ffb;
+        {
+            const float *Bd = ms + MS_BODY;
+            const f3 cm = mul(R0, mk3(Bd[6], Bd[7], Bd[8]) + com_shift);
+            SIn sb = si_body(Bd[9] + mass_add, cm, Bd + 10, R0);
+            const f3 aw = mk3(0.f, 0.f, 0.f), av = cross3(vb, wb) + mk3(0.f, 0.f, tf[TF_GRAV]);
+            f3 LA, PA, LV, PV;
+            si_apply(sb, aw, av, LA, PA);
+            si_apply(sb, wb, vb, LV, PV);
+            fnb = LA + cross3(wb, LV) + cross3(vb, PV);
+            ffb = PA + cross3(wb, PV);
+            cb = sb;
+            cb.m += warp_sum(comp.m * legm);
+            cb.h.x += warp_sum(comp.h.x * legm); cb.h.y += warp_sum(comp.h.y * legm); cb.h.z += warp_sum(comp.h.z * legm);
+#pragma unroll
+            for (int e = 0; e < 6; e++) cb.I[e] += warp_sum(comp.I[e] * legm);
+            fnb.x += warp_sum(fns.x * legm); fnb.y += warp_sum(fns.y * legm); fnb.z += warp_sum(fns.z * legm);
+            ffb.x += warp_sum(ffs.x * legm); ffb.y += warp_sum(ffs.y * legm); ffb.z += warp_sum(ffs.z * legm);
+        }
+        // chain block inverse (3x3 SPD), G = Dinv B^T, Schur complement
+        float Di[6], G[3][6];
+        {
+            const float l00 = sqrtf(Dm[0]), l10 = Dm[1] / l00, l20 = Dm[3] / l00;
+            const float l11 = sqrtf(Dm[2] - l10 * l10), l21 = (Dm[4] - l20 * l10) / l11;
+            const float l22 = sqrtf(Dm[5] - l20 * l20 - l21 * l21);
+            const float i00 = 1.f / l00, i11 = 1.f / l11, i22 = 1.f / l22;
+            const float i10 = -l10 * i00 * i11, i21 = -l21 * i11 * i22, i20 = -(l20 * i00 + l21 * i10) * i22;
+            Di[0] = i00 * i00 + i10 * i10 + i20 * i20; Di[1] = i10 * i11 + i20 * i21; Di[2] = i11 * i11 + i21 * i21;
+            Di[3] = i20 * i22; Di[4] = i21 * i22; Di[5] = i22 * i22;
+        }
+        float Bt[3][6];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { Bt[k][0] = BP[k].x; Bt[k][1] = BP[k].y; Bt[k][2] = BP[k].z; Bt[k][3] = BL[k].x; Bt[k][4] = BL[k].y; Bt[k][5] = BL[k].z; }
+#pragma unroll
+        for (int a2 = 0; a2 < 3; a2++)
+#pragma unroll
+            for (int e = 0; e < 6; e++) G[a2][e] = Di[tri(a2, 0)] * Bt[0][e] + Di[tri(a2, 1)] * Bt[1][e] + Di[tri(a2, 2)] * Bt[2][e];
+        float S[21];
+        {
+            // base block: [m 1, [h]x^T ; [h]x, I]  ordering lin(0..2), ang(3..5)
+#pragma unroll
+            for (int e = 0; e < 21; e++) S[e] = 0.f;
+            S[tri(0, 0)] = S[tri(1, 1)] = S[tri(2, 2)] = cb.m;
+            S[tri(3, 1)] = -cb.h.z; S[tri(3, 2)] = cb.h.y; S[tri(4, 0)] = cb.h.z; S[tri(4, 2)] = -cb.h.x; S[tri(5, 0)] = -cb.h.y; S[tri(5, 1)] = cb.h.x;
+            S[tri(3, 3)] = cb.I[0]; S[tri(4, 4)] = cb.I[1]; S[tri(5, 5)] = cb.I[2]; S[tri(4, 3)] = cb.I[3]; S[tri(5, 3)] = cb.I[4]; S[tri(5, 4)] = cb.I[5];
+#pragma unroll
+            for (int i2 = 0; i2 < 6; i2++)
+#pragma unroll
+                for (int j2 = 0; j2 <= i2; j2++) {
+                    const float t = Bt[0][i2] * G[0][j2] + Bt[1][i2] * G[1][j2] + Bt[2][i2] * G[2][j2];
+                    S[tri(i2, j2)] -= warp_sum(t * legm);
+                }
+        }
+        float Sinv[21];
+        spd6_inverse(S, Sinv);
+        if (leg) {
+            float *mi = ws + WS_MI + c * 24;
+#pragma unroll
+            for (int e = 0; e < 6; e++) mi[e] = Di[e];
+#pragma unroll
+            for (int a2 = 0; a2 < 3; a2++)
+#pragma unroll
+                for (int e = 0; e < 6; e++) mi[6 + a2 * 6 + e] = G[a2][e];
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int e = 0; e < 21; e++) ws[WS_MI + 4 * 24 + e] = Sinv[e];
+        }
+        // smooth acceleration: a = M^-1 (tau_applied - damping qd - bias)
+        float ab[6], al[3];
+        {
+            float rl[3], tl[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float eff = ms[MS_BODY + (1 + 3 * c + k) * B200_BODY_STRIDE + 18];
+                rl[k] = fminf(fmaxf(tau[k], -eff), eff) - dmp[k] * qd[k] - biasl[k];
+            }
+#pragma unroll
+            for (int a2 = 0; a2 < 3; a2++) tl[a2] = Di[tri(a2, 0)] * rl[0] + Di[tri(a2, 1)] * rl[1] + Di[tri(a2, 2)] * rl[2];
+            float rb[6] = {-ffb.x, -ffb.y, -ffb.z, -fnb.x, -fnb.y, -fnb.z};
+#pragma unroll
+            for (int e = 0; e < 6; e++) rb[e] -= warp_sum((Bt[0][e] * tl[0] + Bt[1][e] * tl[1] + Bt[2][e] * tl[2]) * legm);
+#pragma unroll
+            for (int i2 = 0; i2 < 6; i2++) {
+                float s = 0.f;
+#pragma unroll
+                for (int j2 = 0; j2 < 6; j2++) s += Sinv[tri(i2, j2)] * rb[j2];
+                ab[i2] = s;
+            }
+#pragma unroll
+            for (int a2 = 0; a2 < 3; a2++) {
+                float s = tl[a2];
+#pragma unroll
+                for (int e = 0; e < 6; e++) s -= G[a2][e] * ab[e];
+                al[a2] = s;
+            }
+        }
+        if (leg) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { ws[WS_NU + 6 + 3 * c + k] = qd[k]; ws[WS_AF + 6 + 3 * c + k] = al[k]; ws[WS_Q + 3 * c + k] = q[k]; }
+        }
+        if (lane == 0) {
+            ws[WS_NU + 0] = vb.x; ws[WS_NU + 1] = vb.y; ws[WS_NU + 2] = vb.z; ws[WS_NU + 3] = wb.x; ws[WS_NU + 4] = wb.y; ws[WS_NU + 5] = wb.z;
+#pragma unroll
+            for (int e = 0; e < 6; e++) ws[WS_AF + e] = ab[e];
+        }
+
+        // ---------------- collision detection: two spheres per lane ----------------
+        float sdist[2]; f3 sn[2], sx[2]; bool act[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const int s = lane + 32 * t;
+            act[t] = false; sdist[t] = 0.f; sn[t] = mk3(0.f, 0.f, 1.f); sx[t] = mk3(0.f, 0.f, 0.f);
+            if (s < NS) {
+                const float *Sp = ms + MS_SPH + 4 * s;
+                const float *fr = ws + WS_FR + msi[B200_MAX_LINKS + s] * 12;
+                m33 Rb;
+#pragma unroll
+                for (int e = 0; e < 9; e++) Rb.m[e] = fr[e];
+                sx[t] = mk3(fr[9], fr[10], fr[11]) + mul(Rb, mk3(Sp[0], Sp[1], Sp[2]));
+                float hh;
+                terrain_query(tr, tf[TF_HSCALE], tf[TF_VSCALE], tf[TF_BORDER], p.x + sx[t].x, p.y + sx[t].y, hh, sn[t]);
+                sdist[t] = (p.z + sx[t].z - hh) * sn[t].z - Sp[3];
+                act[t] = sdist[t] < 0.f;
+            }
+        }
+        unsigned m0 = __ballot_sync(B200_FULL_MASK, act[0]), m1 = __ballot_sync(B200_FULL_MASK, act[1]);
+        int nact = __popc(m0) + __popc(m1);
+        while (nact > B200_KMAX) {   // drop the shallowest contact (ties: highest sphere index)
+            float best = act[1] ? sdist[1] : (act[0] ? sdist[0] : -1e30f);
+            int bidx = act[1] ? lane + 32 : (act[0] ? lane : -1);
+            if (act[0] && act[1] && sdist[0] > sdist[1]) { best = sdist[0]; bidx = lane; }
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                const float ob = __shfl_xor_sync(B200_FULL_MASK, best, o2);
+                const int oi = __shfl_xor_sync(B200_FULL_MASK, bidx, o2);
+                if (ob > best || (ob == best && oi > bidx)) { best = ob; bidx = oi; }
+            }
+            if (bidx == lane) act[0] = false;
+            if (bidx == lane + 32) act[1] = false;
+            m0 = __ballot_sync(B200_FULL_MASK, act[0]); m1 = __ballot_sync(B200_FULL_MASK, act[1]);
+            nact--;
+        }
+        const int nc = nact;
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            if (act[t]) {
+                const int s = lane + 32 * t;
+                const int slot = t == 0 ? __popc(m0 & lt) : __popc(m0) + __popc(m1 & lt);
+                float *ct = ws + WS_CT + slot * 12;
+                const float rad = ms[MS_SPH + 4 * s + 3];
+                const f3 xc = sx[t] - sn[t] * (rad + 0.5f * sdist[t]);
+                ct[0] = xc.x; ct[1] = xc.y; ct[2] = xc.z; ct[3] = sn[t].x; ct[4] = sn[t].y; ct[5] = sn[t].z; ct[6] = sdist[t];
+                ct[7] = __int_as_float(msi[B200_MAX_LINKS + s]);                        // body
+                ct[8] = __int_as_float(msi[B200_MAX_LINKS + B200_MAX_SPHERES + s]);     // reporting link
+            }
+        }
+        // ---------------- aux rows: joint limits first, then frictionloss, joint order ----------------
+        unsigned limmask = 0, flsmask = 0;
+        float limpos[3], limsign[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float *Bd = ms + MS_BODY + (1 + 3 * c + k) * B200_BODY_STRIDE;
+            const bool lo_v = q[k] < Bd[16], hi_v = q[k] > Bd[17];
+            limsign[k] = lo_v ? 1.f : -1.f;
+            limpos[k] = lo_v ? q[k] - Bd[16] : Bd[17] - q[k];
+            const unsigned bl = __ballot_sync(B200_FULL_MASK, leg && (lo_v || hi_v));
+            const unsigned bf = __ballot_sync(B200_FULL_MASK, leg && fls[k] > 0.f);
+#pragma unroll
+            for (int cc = 0; cc < C; cc++) { limmask |= ((bl >> cc) & 1u) << (3 * cc + k); flsmask |= ((bf >> cc) & 1u) << (3 * cc + k); }
+        }
+        const int nlim = min(__popc(limmask), B200_AUXMAX);
+        const int nfls = min(__popc(flsmask), B200_AUXMAX - nlim);
+        if (leg) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int j = 3 * c + k;
+                const unsigned below = (1u << j) - 1u;
+                if ((limmask >> j) & 1u) {
+                    const int slot = __popc(limmask & below);
+                    if (slot < nlim) { float *ax = ws + WS_AUX + 4 * slot; ax[0] = __int_as_float(j); ax[1] = limsign[k]; ax[2] = limpos[k]; ax[3] = -1.f; }
+                }
+                if ((flsmask >> j) & 1u) {
+                    const int slot = nlim + __popc(flsmask & below);
+                    if (slot < nlim + nfls) { float *ax = ws + WS_AUX + 4 * slot; ax[0] = __int_as_float(j); ax[1] = 1.f; ax[2] = 0.f; ax[3] = fls[k]; }
+                }
+            }
+        }
+        __syncwarp();
+        const int R = 3 * nc + nlim + nfls;
+
+        // ---------------- constraint rows: one per lane ----------------
+        float Jb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Jl[3] = {0.f, 0.f, 0.f};
+        int cl = -1, kind = 5;          // 0 normal, 1/2 tangents, 3 limit, 4 frictionloss, 5 unused
+        float rpos = 0.f, bound = 0.f;
+        f3 dir = mk3(0.f, 0.f, 0.f);
+        int rlink = 0;
+        if (lane < 3 * nc) {
+            const float *ct = ws + WS_CT + (lane / 3) * 12;
+            const int d = lane - 3 * (lane / 3);
+            const f3 xc = mk3(ct[0], ct[1], ct[2]), n = mk3(ct[3], ct[4], ct[5]);
+            const f3 e = fabsf(n.x) < 0.9f ? mk3(1.f, 0.f, 0.f) : mk3(0.f, 1.f, 0.f);
+            f3 t1 = e - n * dot3(e, n); t1 = t1 * (1.f / sqrtf(dot3(t1, t1)));
+            const f3 t2 = cross3(n, t1);
+            dir = d == 0 ? n : (d == 1 ? t1 : t2);
+            kind = d; rpos = d == 0 ? ct[6] : 0.f;
+            const int b = __float_as_int(ct[7]); rlink = __float_as_int(ct[8]);
+            Jb[0] = dir.x; Jb[1] = dir.y; Jb[2] = dir.z;
+            const f3 xd = cross3(xc, dir); Jb[3] = xd.x; Jb[4] = xd.y; Jb[5] = xd.z;
+            if (b > 0) {
+                cl = (b - 1) / 3;
+                const int kd2 = (b - 1) - 3 * cl;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (k <= kd2) {
+                        const int bj = 1 + 3 * cl + k;
+                        const float *fr = ws + WS_FR + bj * 12; const float *axp = ws + WS_AX + (bj - 1) * 3;
+                        Jl[k] = dot3(dir, cross3(mk3(axp[0], axp[1], axp[2]), xc - mk3(fr[9], fr[10], fr[11])));
+                    }
+                }
+            }
+        } else if (lane < R) {
+            const float *ax = ws + WS_AUX + 4 * (lane - 3 * nc);
+            const int j = __float_as_int(ax[0]);
+            cl = j / 3;
+            const int k2 = j - 3 * cl;
+#pragma unroll
+            for (int k = 0; k < 3; k++) Jl[k] = (k == k2) ? ax[1] : 0.f;
+            rpos = ax[2]; bound = ax[3];
+            kind = ax[3] < 0.f ? 3 : 4;
+        }
+        // y = M^-1 J^T for this lane's row
+        float Yb[6], Yl[C][3];
+        float vel = 0.f, ja = 0.f;
+        {
+            float tl[3] = {0.f, 0.f, 0.f}, rb[6];
+#pragma unroll
+            for (int e = 0; e < 6; e++) rb[e] = Jb[e];
+            if (cl >= 0) {
+                const float *mi = ws + WS_MI + cl * 24;
+#pragma unroll
+                for (int a2 = 0; a2 < 3; a2++) tl[a2] = mi[tri(a2, 0)] * Jl[0] + mi[tri(a2, 1)] * Jl[1] + mi[tri(a2, 2)] * Jl[2];
+#pragma unroll
+                for (int e = 0; e < 6; e++) rb[e] -= mi[6 + e] * Jl[0] + mi[12 + e] * Jl[1] + mi[18 + e] * Jl[2];
+            }
+#pragma unroll
+            for (int i2 = 0; i2 < 6; i2++) {
+                float s = 0.f;
+#pragma unroll
+                for (int j2 = 0; j2 < 6; j2++) s += Sinv[tri(i2, j2)] * rb[j2];
+                Yb[i2] = s;
+            }
+#pragma unroll
+            for (int l2 = 0; l2 < C; l2++) {
+                const float *mi = ws + WS_MI + l2 * 24;
+#pragma unroll
+                for (int a2 = 0; a2 < 3; a2++) {
+                    float s = (l2 == cl) ? tl[a2] : 0.f;
+#pragma unroll
+                    for (int e = 0; e < 6; e++) s -= mi[6 + a2 * 6 + e] * Yb[e];
+                    Yl[l2][a2] = s;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 6; e++) { vel += Jb[e] * ws[WS_NU + e]; ja += Jb[e] * ws[WS_AF + e]; }
+            if (cl >= 0) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) { vel += Jl[k] * ws[WS_NU + 6 + 3 * cl + k]; ja += Jl[k] * ws[WS_AF + 6 + 3 * cl + k]; }
+            }
+            float *jr = ws + WS_JR + lane * 10;
+#pragma unroll
+            for (int e = 0; e < 6; e++) jr[e] = Jb[e];
+            jr[6] = Jl[0]; jr[7] = Jl[1]; jr[8] = Jl[2]; jr[9] = __int_as_float(cl);
+        }
+        __syncwarp();
+        // this lane's column of A = J M^-1 J^T
+        float Arr = 1.f;
+        for (int r = 0; r < R; r++) {
+            const float *jr = ws + WS_JR + r * 10;
+            float a2 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 6; e++) a2 += jr[e] * Yb[e];
+            const int clr = __float_as_int(jr[9]);
+#pragma unroll
+            for (int l2 = 0; l2 < C; l2++)
+                if (clr == l2) a2 += jr[6] * Yl[l2][0] + jr[7] * Yl[l2][1] + jr[8] * Yl[l2][2];
+            ws[WS_AM + r * 33 + lane] = a2;
+            if (r == lane) Arr = a2;
+        }
+        float imp = (kind == 0 || kind == 3 || kind == 4) ? impedance(tf, rpos) : 0.f;
+        {
+            const int src = (kind == 1) ? lane - 1 : ((kind == 2) ? lane - 2 : lane);
+            imp = __shfl_sync(B200_FULL_MASK, imp, src);
+        }
+        float f = 0.f, Rr = 0.f, dd = 1.f, wres = 0.f;
+        if (lane < R) {
+            const float aref = -bd * vel - kk * imp * rpos;
+            Rr = (1.f - imp) / imp * Arr;
+            dd = Arr + Rr;
+            wres = ja - aref;
+        }
+        __syncwarp();
+        // ---------------- projected Gauss-Seidel with friction-cone projection ----------------
+        const int iters = T.i[TI_PGS_ITERS];
+        for (int it = 0; it < iters; it++) {
+            for (int r = 0; r < R; r++) {
+                float delta = 0.f;
+                if (lane == r) {
+                    float fnew = f - (wres + Rr * f) / dd;
+                    if (kind == 0 || kind == 3) fnew = fmaxf(fnew, 0.f);
+                    else if (kind == 4) fnew = fminf(fmaxf(fnew, -bound), bound);
+                    delta = fnew - f; f = fnew;
+                }
+                delta = __shfl_sync(B200_FULL_MASK, delta, r);
+                wres += ws[WS_AM + r * 33 + lane] * delta;
+                if (r < 3 * nc && (r % 3) == 2) {
+                    const float fnn = __shfl_sync(B200_FULL_MASK, f, r - 2);
+                    const float f1 = __shfl_sync(B200_FULL_MASK, f, r - 1);
+                    const float f2 = __shfl_sync(B200_FULL_MASK, f, r);
+                    const float lim = mu * fnn, tt = sqrtf(f1 * f1 + f2 * f2);
+                    if (tt > lim) {
+                        const float sc = tt > 0.f ? lim / tt : 0.f;
+                        const float n1 = f1 * sc, n2 = f2 * sc;
+                        if (lane == r - 1) f = n1;
+                        if (lane == r) f = n2;
+                        wres += ws[WS_AM + (r - 1) * 33 + lane] * (n1 - f1) + ws[WS_AM + r * 33 + lane] * (n2 - f2);
+                    }
+                }
+            }
+        }
+        // ---------------- total acceleration, contact forces, integration ----------------
+        float accb[6], accl[3] = {al[0], al[1], al[2]};
+        {
+            const float fz = lane < R ? f : 0.f;
+#pragma unroll
+            for (int e = 0; e < 6; e++) accb[e] = ab[e] + warp_sum(Yb[e] * fz);
+#pragma unroll
+            for (int l2 = 0; l2 < C; l2++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const float s = warp_sum(Yl[l2][k] * fz);
+                    if (l2 == c) accl[k] += s;
+                }
+        }
+        {
+            float *fv = ws + WS_FV + lane * 4;
+            const float fz = lane < 3 * nc ? f : 0.f;
+            fv[0] = fz * dir.x; fv[1] = fz * dir.y; fv[2] = fz * dir.z; fv[3] = __int_as_float(lane < 3 * nc ? rlink : -1);
+        }
+        __syncwarp();
+        for (int e = lane; e < 3 * L; e += 32) {
+            const int l2 = e / 3, k = e - 3 * l2;
+            float s = 0.f;
+            for (int r = 0; r < 3 * nc; r++) {
+                const float *fv = ws + WS_FV + r * 4;
+                if (__float_as_int(fv[3]) == l2) s += fv[k];
+            }
+            ws[WS_LF + e] = s;
+        }
+        // semi-implicit Euler
+        vb = vb + mk3(accb[0], accb[1], accb[2]) * h;
+        wb = wb + mk3(accb[3], accb[4], accb[5]) * h;
+        p = p + vb * h;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { qd[k] += h * accl[k]; q[k] += h * qd[k]; }
+        {
+            const float wn = sqrtf(dot3(wb, wb));
+            float dw = 1.f, dx = 0.f, dy = 0.f, dz = 0.f;
+            if (wn > 1e-12f) {
+                float sn2, cs2; sincosf(0.5f * wn * h, &sn2, &cs2);
+                const float s = sn2 / wn; dw = cs2; dx = wb.x * s; dy = wb.y * s; dz = wb.z * s;
+            }
+            const float nw = dw * Qw - dx * Qx - dy * Qy - dz * Qz;
+            const float nx = dw * Qx + dx * Qw + dy * Qz - dz * Qy;
+            const float ny = dw * Qy - dx * Qz + dy * Qw + dz * Qx;
+            const float nz = dw * Qz + dx * Qy - dy * Qx + dz * Qw;
+            const float inv = 1.f / sqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
+            Qw = nw * inv; Qx = nx * inv; Qy = ny * inv; Qz = nz * inv;
+        }
+        __syncwarp();
+    }
+
+    // ---------------- write back (frames/velocities of the final state are in shared memory) ----------------
+    if (lane < 3) {
+        B.base_pos[env * 3 + lane] = comp3(p, lane);
+        B.base_lin_w[env * 3 + lane] = comp3(vb, lane);
+        B.base_ang_w[env * 3 + lane] = comp3(wb, lane);
+    }
+    if (lane < 4) B.base_quat_wxyz[env * 4 + lane] = lane == 0 ? Qw : (lane == 1 ? Qx : (lane == 2 ? Qy : Qz));
+    if (leg) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int o = env * A + 3 * c + k;
+            B.dof_pos[o] = q[k]; B.dof_vel[o] = qd[k]; B.torques[o] = tau[k];
+        }
+    }
+    for (int e = lane; e < 3 * L; e += 32) B.link_contact_forces[env * 3 * L + e] = ws[WS_LF + e];
+    const int F = T.i[TI_F];
+    if (lane < F) {
+        const int l2 = T.i[TI_FEET_LINKS + lane];
+        const int b = msi[l2];
+        const float *fr = ws + WS_FR + b * 12, *vl = ws + WS_VEL + b * 6, *off = ms + MS_LINK + 3 * l2;
+        m33 Rb;
+#pragma unroll
+        for (int e = 0; e < 9; e++) Rb.m[e] = fr[e];
+        const f3 x = mk3(fr[9], fr[10], fr[11]) + mul(Rb, mk3(off[0], off[1], off[2]));
+        const f3 v = mk3(vl[3], vl[4], vl[5]) + cross3(mk3(vl[0], vl[1], vl[2]), x);
+        float *fp = B.feet_pos + (env * F + lane) * 3, *fv = B.feet_vel + (env * F + lane) * 3;
+        fp[0] = p.x + x.x; fp[1] = p.y + x.y; fp[2] = p.z + x.z; fv[0] = v.x; fv[1] = v.y; fv[2] = v.z;
+    }
+}
+
+// stage the packed robot model into shared memory (once per CTA)
+__device__ __forceinline__ void stage_model(const ModelDev &M, const TaskDev &T, float *ms) {
+    const int NB = 1 + T.i[TI_A], L = T.i[TI_L], NS = T.i[TI_NSPHERES];
+    int *msi = (int *)(ms + MS_INT);
+    for (int e = threadIdx.x; e < NB * B200_BODY_STRIDE; e += blockDim.x) ms[MS_BODY + e] = M.body[e];
+    for (int e = threadIdx.x; e < L * 3; e += blockDim.x) ms[MS_LINK + e] = M.link_off[e];
+    for (int e = threadIdx.x; e < NS * 4; e += blockDim.x) ms[MS_SPH + e] = M.sph[e];
+    for (int e = threadIdx.x; e < L; e += blockDim.x) msi[e] = M.link_body[e];
+    for (int e = threadIdx.x; e < NS; e += blockDim.x) { msi[B200_MAX_LINKS + e] = M.sph_body[e]; msi[B200_MAX_LINKS + B200_MAX_SPHERES + e] = M.sph_link[e]; }
+}
+
+template <int C>
+__global__ void B200_LAUNCH_BOUNDS(DYN_WARPS_PER_BLOCK * 32, 1)
+dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, const TerrainDev tr, const float *actions) {
+    extern __shared__ float smem[];
+    float *ms = smem;
+    stage_model(M, T, ms);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (env >= T.i[TI_NUM_ENVS]) return;
+    dynamics_warp<C>(T, B, tr, ms, smem + MS_TOTAL + warp * WS_TOTAL, actions, env, lane);
+}

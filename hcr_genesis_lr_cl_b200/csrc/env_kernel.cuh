@@ -1,0 +1,513 @@
+// env_kernel.cuh -- the fused post_physics_step: one launch, one pass over the per-env state in HBM.
+//
+// Replaces (reference paths relative to the LeggedGym-Ex root) for the `go2` and `go2_ts` observation layouts:
+//   LeggedRobot.post_physics_step            legged_gym/envs/base/legged_robot.py:55-76
+//   GenesisSimulator.post_physics_step       legged_gym/simulator/genesis_simulator.py:35-60
+//     _check_base_pos_out_of_bound           :612-628      _update_surrounding_heights   :552-577
+//     _calc_terrain_info_around_feet         :579-610
+//   _post_physics_step_callback / _resample_commands / push_robots   legged_robot.py:300-334, genesis_simulator.py:150-158
+//   check_termination                        legged_robot.py:78-92
+//   compute_reward + _reward_*               legged_robot.py:150-168,458-608; go2_ts.py:133-176
+//   reset_idx (+ curriculum, _reset_dofs, _reset_root_states, simulator.reset_idx DR, history clearing)
+//                                            legged_robot.py:94-148,254-298; go2_ts.py:75-96; genesis_simulator.py:62-148,665-739;
+//                                            legged_robot_ts.py:120-125
+//   compute_observations (+ noise, history deques, clip)   go2.py:40-90; go2_ts.py:5-84; legged_robot_ts.py:59-76
+//
+// HBM-bound (~16.7 KB per env per policy step for go2_ts, dominated by the 900-float obs history and
+// the 885-float critic stack).  One warp owns one env: every [N,k] row-major tensor row is read/written by
+// consecutive lanes (coalesced), per-env scalars are computed redundantly by all lanes (no divergence), per-joint /
+// per-foot / per-link quantities live one per lane and are reduced with shuffles.  Integer-valued outputs (cell
+// indices, reset flags) follow the reference's fp32 operation order with explicit _rn intrinsics (no FMA
+// contraction, true division by horizontal_scale; SURVEY "a-kernel notes").
+#pragma once
+#include "cuda_compat.cuh"
+#include "philox.cuh"
+#include "dynamics_kernel.cuh"   // TaskDev, TerrainDev
+
+#define ENV_WARPS_PER_BLOCK 4
+#define ES_OBS 0                   // clean obs [48]
+#define ES_NOISY 48                // noisy obs [48]
+#define ES_CRIT 96                 // single critic frame [<=256]
+#define ES_PRIV 352                // privileged obs [<=128]
+#define ES_TOTAL 480
+
+struct EnvCall {
+    uint32_t step;       // LeggedRobot.common_step_counter after its increment
+    float vx_lo, vx_span;
+    int parity;          // history buffers: read [parity], write [parity ^ 1]
+    int phase_mask;
+    int force_reset;     // b200_reset_all: run only the reset phase, for every env
+};
+
+__host__ __device__ inline int env_smem_bytes(int warps) { return warps * ES_TOTAL * 4; }
+
+// quat_rotate_inverse (math_utils.py:63-76), q = xyzw
+__device__ __forceinline__ f3 rot_inv(float qx, float qy, float qz, float qw, f3 v) {
+    const f3 qv = mk3(qx, qy, qz);
+    const float s = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, qw), qw), 1.0f);
+    const f3 a = mk3(__fmul_rn(v.x, s), __fmul_rn(v.y, s), __fmul_rn(v.z, s));
+    const float w2 = __fmul_rn(2.0f, qw);
+    const f3 cr = mk3(__fsub_rn(__fmul_rn(qv.y, v.z), __fmul_rn(qv.z, v.y)), __fsub_rn(__fmul_rn(qv.z, v.x), __fmul_rn(qv.x, v.z)),
+                      __fsub_rn(__fmul_rn(qv.x, v.y), __fmul_rn(qv.y, v.x)));
+    const f3 b = mk3(__fmul_rn(cr.x, w2), __fmul_rn(cr.y, w2), __fmul_rn(cr.z, w2));
+    const float d = __fadd_rn(__fadd_rn(__fmul_rn(qv.x, v.x), __fmul_rn(qv.y, v.y)), __fmul_rn(qv.z, v.z));
+    const float d2 = __fmul_rn(2.0f, d);
+    const f3 c = mk3(__fmul_rn(qv.x, d2), __fmul_rn(qv.y, d2), __fmul_rn(qv.z, d2));
+    return mk3(__fadd_rn(__fsub_rn(a.x, b.x), c.x), __fadd_rn(__fsub_rn(a.y, b.y), c.y), __fadd_rn(__fsub_rn(a.z, b.z), c.z));
+}
+
+__device__ __forceinline__ float norm3_rn(float x, float y, float z) {
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+
+// trunc((p + border) / hscale) as torch evaluates it in fp32 (genesis_simulator.py:564-565,582-583)
+__device__ __forceinline__ int cell_of(float p, float border, float hscale) {
+    return (int)truncf(__fdiv_rn(__fadd_rn(p, border), hscale));
+}
+
+__device__ __forceinline__ int wrap_idx(int i, int n) { return i < 0 ? i + n : i; }   // torch negative-index wrap
+
+__device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const EnvCall &call,
+                                   float *es, int env, int lane) {
+    const float *tf = T.f;
+    const int *ti = T.i;
+    const int A = ti[TI_A], F = ti[TI_F], L = ti[TI_L], P = ti[TI_PX] * ti[TI_PY];
+    const int n_sums = ti[TI_N_REWARDS] + (ti[TI_TERMINATION_COL] >= 0 ? 1 : 0);
+    const int pm = call.force_reset ? PHASE_RESET : call.phase_mask;
+    EnvRng rng; rng.k0 = (uint32_t)ti[TI_SEED_LO]; rng.k1 = (uint32_t)ti[TI_SEED_HI]; rng.env = (uint32_t)(env + ti[TI_ENV_OFFSET]); rng.step = call.step;
+    const float dt = tf[TF_POLICY_DT];
+
+    // ------------------------------------------------------------------ per-env scalars (replicated in all lanes)
+    f3 bp = mk3(B.base_pos[env * 3], B.base_pos[env * 3 + 1], B.base_pos[env * 3 + 2]);
+    const float Qw = B.base_quat_wxyz[env * 4], Qx = B.base_quat_wxyz[env * 4 + 1], Qy = B.base_quat_wxyz[env * 4 + 2], Qz = B.base_quat_wxyz[env * 4 + 3];
+    f3 vw = mk3(B.base_lin_w[env * 3], B.base_lin_w[env * 3 + 1], B.base_lin_w[env * 3 + 2]);
+    f3 ww = mk3(B.base_ang_w[env * 3], B.base_ang_w[env * 3 + 1], B.base_ang_w[env * 3 + 2]);
+    f3 origin = mk3(B.env_origins[env * 3], B.env_origins[env * 3 + 1], B.env_origins[env * 3 + 2]);
+    float cmd0 = B.commands[env * 4], cmd1 = B.commands[env * 4 + 1], cmd2 = B.commands[env * 4 + 2], cmd3 = B.commands[env * 4 + 3];
+    int ep_len = B.episode_length[env];
+    int fail_cnt = B.fail_buf[env];
+    // read before any lane may overwrite them below (lanes are not in lock-step between collectives)
+    const int level0 = ti[TI_TERRAIN_CURRICULUM] ? (int)B.terrain_levels[env] : 0;
+    const int ttype = ti[TI_TERRAIN_CURRICULUM] ? (int)B.terrain_types[env] : 0;
+    f3 push_vel = mk3(B.rand_push_vels[env * 3], B.rand_push_vels[env * 3 + 1], 0.f);
+    f3 lin_b, ang_b, grav;           // body-frame velocities, projected gravity
+    // ------------------------------------------------------------------ per-lane values
+    const bool jl = lane < A, fl = lane < F;
+    float qj = jl ? B.dof_pos[env * A + lane] : 0.f, qdj = jl ? B.dof_vel[env * A + lane] : 0.f;
+    float actj = jl ? B.actions[env * A + lane] : 0.f;
+    const float q0j = jl ? tf[TF_DEFAULT_DOF_POS + lane] : 0.f;
+    f3 fpos = mk3(0.f, 0.f, 0.f), fvel = mk3(0.f, 0.f, 0.f);
+    if (fl) {
+        const float *a = B.feet_pos + (env * F + lane) * 3, *b = B.feet_vel + (env * F + lane) * 3;
+        fpos = mk3(a[0], a[1], a[2]); fvel = mk3(b[0], b[1], b[2]);
+    }
+    float ffz = fl ? B.link_contact_forces[(env * L + ti[TI_FEET_LINKS + lane]) * 3 + 2] : 0.f;   // foot contact force z
+    float hmean = 0.f;               // mean of the 9 terrain heights around this lane's foot
+
+    if (pm & PHASE_CALLBACK) ep_len += 1;                       // legged_robot.py:60
+
+    // ================================================================== GenesisSimulator.post_physics_step
+    if (pm & PHASE_SIM_POST) {
+        const bool oob = (bp.x >= tf[TF_X_HI]) || (bp.x <= tf[TF_X_LO]) || (bp.y >= tf[TF_Y_HI]) || (bp.y <= tf[TF_Y_LO]);
+        if (oob) {                                               // genesis_simulator.py:612-628
+            const f3 nb = mk3(__fadd_rn(tf[TF_INIT_POS], origin.x), __fadd_rn(tf[TF_INIT_POS + 1], origin.y), __fadd_rn(tf[TF_INIT_POS + 2], origin.z));
+            fpos = fpos + (nb - bp);
+            if (fl) { float *a = B.feet_pos + (env * F + lane) * 3; a[0] = fpos.x; a[1] = fpos.y; a[2] = fpos.z; }
+            bp = nb;
+            if (lane < 3) B.base_pos[env * 3 + lane] = comp3(bp, lane);
+        }
+        lin_b = rot_inv(Qx, Qy, Qz, Qw, vw);
+        ang_b = rot_inv(Qx, Qy, Qz, Qw, ww);
+        grav = rot_inv(Qx, Qy, Qz, Qw, mk3(0.f, 0.f, -1.f));
+        if (lane < 3) {
+            B.base_lin_vel[env * 3 + lane] = comp3(lin_b, lane);
+            B.base_ang_vel[env * 3 + lane] = comp3(ang_b, lane);
+            B.projected_gravity[env * 3 + lane] = comp3(grav, lane);
+        }
+        if (lane < 4) B.base_quat[env * 4 + lane] = lane == 0 ? Qx : (lane == 1 ? Qy : (lane == 2 ? Qz : Qw));
+        if (lane == 0) {                                         // get_euler_xyz, math_utils.py:89-109
+            const float sinr = 2.0f * (Qw * Qx + Qy * Qz), cosr = Qw * Qw - Qx * Qx - Qy * Qy + Qz * Qz;
+            const float sinp = 2.0f * (Qw * Qy - Qz * Qx);
+            const float siny = 2.0f * (Qw * Qz + Qx * Qy), cosy = Qw * Qw + Qx * Qx - Qy * Qy - Qz * Qz;
+            B.base_euler[env * 3 + 0] = atan2f(sinr, cosr);
+            B.base_euler[env * 3 + 1] = fabsf(sinp) >= 1.f ? copysignf(1.5707963267948966f, sinp) : asinf(sinp);
+            B.base_euler[env * 3 + 2] = atan2f(siny, cosy);
+        }
+        if (ti[TI_CONTACT_STATES] && lane < ti[TI_N_CS]) {
+            const float *f = B.link_contact_forces + (env * L + ti[TI_CS_LINKS + lane]) * 3;
+            B.link_contact_states[env * ti[TI_N_CS] + lane] = norm3_rn(f[0], f[1], f[2]) > 1.0f ? 1.f : 0.f;
+        }
+        if (ti[TI_MEASURE_HEIGHTS]) {
+            // quat_apply_yaw (math_utils.py:42-47) of the scan grid, then min of 3 int16 samples
+            const float nrm = fmaxf(__fsqrt_rn(__fadd_rn(__fmul_rn(Qz, Qz), __fmul_rn(Qw, Qw))), 1e-9f);
+            const float zn = __fdiv_rn(Qz, nrm), wn = __fdiv_rn(Qw, nrm);
+            for (int pt = lane; pt < P; pt += 32) {
+                const float px = tf[TF_POINTS_X + pt / ti[TI_PY]], py = tf[TF_POINTS_Y + pt % ti[TI_PY]];
+                const float tx = __fmul_rn(-__fmul_rn(zn, py), 2.0f), ty = __fmul_rn(__fmul_rn(zn, px), 2.0f);
+                const float rx = __fadd_rn(__fadd_rn(px, __fmul_rn(wn, tx)), -__fmul_rn(zn, ty));
+                const float ry = __fadd_rn(__fadd_rn(py, __fmul_rn(wn, ty)), __fmul_rn(zn, tx));
+                int cx = cell_of(__fadd_rn(rx, bp.x), tf[TF_BORDER], tf[TF_HSCALE]);
+                int cy = cell_of(__fadd_rn(ry, bp.y), tf[TF_BORDER], tf[TF_HSCALE]);
+                cx = max(0, min(cx, tr.rows - 2)); cy = max(0, min(cy, tr.cols - 2));
+                const int16_t *hp = tr.hf + (size_t)cx * tr.cols + cy;
+                const int16_t h = min(min(__ldg(hp), __ldg(hp + tr.cols)), __ldg(hp + 1));
+                B.measured_heights[env * P + pt] = __fmul_rn((float)h, tf[TF_VSCALE]);
+                if (B.height_cells) { B.height_cells[(env * P + pt) * 2] = cx; B.height_cells[(env * P + pt) * 2 + 1] = cy; }
+            }
+            if (ti[TI_FEET_INFO]) {
+                int cx = cell_of(fpos.x, tf[TF_BORDER], tf[TF_HSCALE]), cy = cell_of(fpos.y, tf[TF_BORDER], tf[TF_HSCALE]);
+                cx = max(0, min(cx, tr.rows - 2)); cy = max(0, min(cy, tr.cols - 2));
+                if (fl) {
+                    const int DX[9] = {-1, 1, 0, 0, 0, -1, 1, -1, 1}, DY[9] = {0, 0, -1, 1, 0, -1, 1, 1, -1};
+                    int16_t hv[9];
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 9; k++) {
+                        hv[k] = __ldg(tr.hf + (size_t)wrap_idx(cx + DX[k], tr.rows) * tr.cols + wrap_idx(cy + DY[k], tr.cols));
+                        const float hk = __fmul_rn((float)hv[k], tf[TF_VSCALE]);
+                        B.height_around_feet[(env * F + lane) * 9 + k] = hk;
+                        s = __fadd_rn(s, hk);
+                    }
+                    hmean = __fdiv_rn(s, 9.0f);
+                    const float den = __fmul_rn(tf[TF_HSCALE], 2.0f);
+                    const float dx = __fdiv_rn((float)(int16_t)(hv[1] - hv[0]), den), dy = __fdiv_rn((float)(int16_t)(hv[3] - hv[2]), den);
+                    const float nn = norm3_rn(dx, dy, -1.0f);
+                    float *nv = B.normal_vector_around_feet + env * 3 * F + lane * 3;
+                    nv[0] = __fdiv_rn(dx, nn); nv[1] = __fdiv_rn(dy, nn); nv[2] = __fdiv_rn(-1.0f, nn);
+                }
+            }
+        }
+    } else {
+        lin_b = mk3(B.base_lin_vel[env * 3], B.base_lin_vel[env * 3 + 1], B.base_lin_vel[env * 3 + 2]);
+        ang_b = mk3(B.base_ang_vel[env * 3], B.base_ang_vel[env * 3 + 1], B.base_ang_vel[env * 3 + 2]);
+        grav = mk3(B.projected_gravity[env * 3], B.projected_gravity[env * 3 + 1], B.projected_gravity[env * 3 + 2]);
+        if (fl && ti[TI_FEET_INFO]) {
+            float s = 0.f;
+            for (int k = 0; k < 9; k++) s = __fadd_rn(s, B.height_around_feet[(env * F + lane) * 9 + k]);
+            hmean = __fdiv_rn(s, 9.0f);
+        }
+    }
+    __syncwarp();
+
+    // ================================================================== _post_physics_step_callback
+    if (pm & PHASE_CALLBACK) {
+        if (ep_len % ti[TI_RESAMPLE_INTERVAL] == 0) {            // legged_robot.py:305-306, 317-334
+            cmd0 = rand_range(call.vx_lo, call.vx_span, rng.u(SITE_CMD_RESAMPLE, 0));
+            cmd1 = rand_range(tf[TF_CMD_VY_LO], tf[TF_CMD_VY_SPAN], rng.u(SITE_CMD_RESAMPLE, 1));
+            if (ti[TI_HEADING_COMMAND]) cmd3 = rand_range(tf[TF_CMD_HEADING_LO], tf[TF_CMD_HEADING_SPAN], rng.u(SITE_CMD_RESAMPLE, 2));
+            else cmd2 = rand_range(tf[TF_CMD_YAW_LO], tf[TF_CMD_YAW_SPAN], rng.u(SITE_CMD_RESAMPLE, 2));
+            const float keep = norm3_rn(cmd0, cmd1, cmd2) > 0.2f ? 1.f : 0.f;
+            cmd0 *= keep; cmd1 *= keep; cmd2 *= keep;
+        }
+        if (ti[TI_HEADING_COMMAND]) {                            // legged_robot.py:307-312
+            // forward = quat_apply(base_quat, (1,0,0)); only x,y are needed
+            const float t_y = __fmul_rn(Qz, 2.0f), t_z = __fmul_rn(-Qy, 2.0f);   // t = cross(q_xyz, e_x) * 2 = (0, 2 qz, -2 qy)
+            const float fx = __fadd_rn(__fadd_rn(1.0f, __fmul_rn(Qw, 0.0f)), __fsub_rn(__fmul_rn(Qy, t_z), __fmul_rn(Qz, t_y)));
+            const float fy = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(Qw, t_y)), __fsub_rn(__fmul_rn(Qz, 0.0f), __fmul_rn(Qx, t_z)));
+            const float heading = atan2f(fy, fx);
+            // wrap_to_pi as compiled by TorchScript: fmod (sign of the dividend), then -2pi where > pi  (quirk R16)
+            float ang = fmodf(__fsub_rn(cmd3, heading), 6.2831853071795862f);
+            ang = __fsub_rn(ang, ang > 3.1415926535897931f ? 6.2831853071795862f : 0.0f);
+            cmd2 = fminf(fmaxf(__fmul_rn(0.5f, ang), tf[TF_CMD_YAW_LO]), tf[TF_CMD_YAW_HI]);
+        }
+        if (ti[TI_PUSH_ROBOTS] && (call.step % (uint32_t)ti[TI_PUSH_INTERVAL]) == 0) {   // genesis_simulator.py:150-158
+            const float span = __fmul_rn(2.0f, tf[TF_MAX_PUSH]);
+            push_vel.x = rand_range(-tf[TF_MAX_PUSH], span, rng.u(SITE_PUSH, 0));
+            push_vel.y = rand_range(-tf[TF_MAX_PUSH], span, rng.u(SITE_PUSH, 1));
+            vw.x = __fadd_rn(vw.x, push_vel.x); vw.y = __fadd_rn(vw.y, push_vel.y);
+            if (lane < 2) { B.rand_push_vels[env * 3 + lane] = lane == 0 ? push_vel.x : push_vel.y; B.base_lin_w[env * 3 + lane] = lane == 0 ? vw.x : vw.y; }
+        }
+    }
+
+    // ================================================================== check_termination
+    bool time_out = false, reset = false;
+    if (pm & PHASE_TERMINATION) {
+        bool hit = false;
+        if (lane < ti[TI_N_TERM]) {
+            const float *f = B.link_contact_forces + (env * L + ti[TI_TERM_LINKS + lane]) * 3;
+            hit = norm3_rn(f[0], f[1], f[2]) > 10.0f;
+        }
+        const bool fail = (__ballot_sync(B200_FULL_MASK, hit) != 0u) || (grav.z > tf[TF_MAX_PROJ_GRAV]);
+        fail_cnt += fail ? 1 : 0;
+        time_out = ep_len > ti[TI_MAX_EPISODE_LENGTH];
+        reset = ((float)fail_cnt > tf[TF_FAIL_LIMIT]) || time_out;
+    }
+    if (call.force_reset) reset = true;
+
+    // ================================================================== compute_reward
+    float my_sum = (lane < n_sums) ? B.episode_sums[env * n_sums + lane] : 0.f;
+    float fat = fl ? B.feet_air_time[env * F + lane] : 0.f;
+    if (pm & PHASE_REWARD) {
+        const float lastj = jl ? B.last_actions[env * A + lane] : 0.f, llastj = jl ? B.llast_actions[env * A + lane] : 0.f;
+        const float tauj = jl ? B.torques[env * A + lane] : 0.f, lqdj = jl ? B.last_dof_vel[env * A + lane] : 0.f;
+        const float small_cmd = norm3_rn(cmd0, cmd1, cmd2) < 0.1f ? 1.f : 0.f;
+        const float dqj = qj - q0j;
+        float rew = 0.f;
+        const int nr = ti[TI_N_REWARDS];
+        for (int i = 0; i < nr; i++) {
+            const int id = ti[TI_REWARD_IDS + i];
+            float r = 0.f;
+            switch (id) {
+            case RW_ACTION_RATE: { const float d = lastj - actj; r = warp_sum(d * d); break; }
+            case RW_ACTION_SMOOTHNESS: { const float d = actj - 2.0f * lastj + llastj; r = warp_sum(d * d); break; }
+            case RW_ANG_VEL_XY: r = ang_b.x * ang_b.x + ang_b.y * ang_b.y; break;
+            case RW_BASE_HEIGHT: {
+                float s = 0.f;
+                for (int pt = lane; pt < P; pt += 32) s += bp.z - (ti[TI_MEASURE_HEIGHTS] ? B.measured_heights[env * P + pt] : 0.f);
+                const float m = warp_sum(s) / (float)P - tf[TF_BASE_HEIGHT_TARGET];
+                r = m * m; break; }
+            case RW_COLLISION: {
+                float hitf = 0.f;
+                if (lane < ti[TI_N_PEN]) { const float *f = B.link_contact_forces + (env * L + ti[TI_PEN_LINKS + lane]) * 3; hitf = norm3_rn(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f; }
+                r = warp_sum(hitf); break; }
+            case RW_DOF_ACC: { const float d = (lqdj - qdj) / dt; r = warp_sum(d * d); break; }
+            case RW_DOF_CLOSE_TO_DEFAULT: r = warp_sum(dqj * dqj); break;
+            case RW_DOF_POS_LIMITS: {
+                float o = 0.f;
+                if (jl) o = -fminf(qj - tf[TF_DOF_LIM_LO + lane], 0.f) + fmaxf(qj - tf[TF_DOF_LIM_HI + lane], 0.f);
+                r = warp_sum(o); break; }
+            case RW_DOF_POS_STAND_STILL: r = warp_sum(dqj * dqj) * small_cmd; break;
+            case RW_DOF_POWER: r = warp_sum(fabsf(tauj * qdj)); break;
+            case RW_DOF_VEL: r = warp_sum(qdj * qdj); break;
+            case RW_DOF_VEL_STAND_STILL: r = warp_sum(fabsf(qdj)) * small_cmd; break;
+            case RW_FEET_AIR_TIME: {                              // stateful; go2_ts.py:133-145
+                const bool contact = ffz > 1.0f;
+                const bool lastc = fl ? (B.last_contacts[env * F + lane] != 0) : false;
+                const bool filt = contact || lastc;
+                if (fl) B.last_contacts[env * F + lane] = contact ? 1 : 0;
+                const bool first = (fat > 0.f) && filt;
+                fat = __fadd_rn(fat, dt);
+                float s = warp_sum((fl && first) ? __fsub_rn(fat, tf[TF_AIR_TIME_THRESHOLD]) : 0.f);
+                s *= norm3_rn(cmd0, cmd1, 0.f) > 0.1f ? 1.f : 0.f;
+                if (filt) fat = 0.f;
+                r = s; break; }
+            case RW_FEET_CONTACT_STAND_STILL: {
+                const float cnt = warp_sum((fl && ffz > 0.1f) ? 1.f : 0.f);
+                r = (cnt == (float)F ? 1.f : 0.f) * small_cmd; break; }
+            case RW_FOOT_ACC: {
+                float s = 0.f;
+                if (fl) { const float *lv = B.last_feet_vel + (env * F + lane) * 3;
+                    const float ax = (fvel.x - lv[0]) / dt, ay = (fvel.y - lv[1]) / dt, az = (fvel.z - lv[2]) / dt; s = ax * ax + ay * ay + az * az; }
+                r = warp_sum(s); break; }
+            case RW_FOOT_CLEARANCE: {                             // legged_robot.py:575-588; go2_ts.py:147-161
+                float s = 0.f;
+                if (fl) {
+                    const float vxy = sqrtf(fvel.x * fvel.x + fvel.y * fvel.y);
+                    float z = fpos.z;
+                    if (ti[TI_CLEARANCE_USES_TERRAIN]) z -= hmean;
+                    const float e = z - tf[TF_FOOT_CLEARANCE_TARGET] - tf[TF_FOOT_HEIGHT_OFFSET];
+                    s = vxy * e * e;
+                }
+                r = expf(-warp_sum(s) / tf[TF_FOOT_CLEARANCE_SIGMA]); break; }
+            case RW_FOOT_LANDING_VEL: {
+                float s = 0.f;
+                if (fl) { const bool about = ((fpos.z - tf[TF_FOOT_HEIGHT_OFFSET]) < tf[TF_ABOUT_LANDING]) && !(ffz > 0.1f) && (fvel.z < 0.f); s = about ? fvel.z * fvel.z : 0.f; }
+                r = warp_sum(s); break; }
+            case RW_HIP_POS: r = warp_sum((jl && (lane % 3) == 0) ? dqj * dqj : 0.f); break;
+            case RW_KEEP_BALANCE: r = 1.f; break;
+            case RW_LIN_VEL_Z: r = lin_b.z * lin_b.z; break;
+            case RW_ORIENTATION: r = grav.x * grav.x + grav.y * grav.y; break;
+            case RW_THIGH_POS: r = warp_sum((jl && (lane % 3) == 1) ? dqj * dqj : 0.f); break;
+            case RW_TORQUES: r = warp_sum(tauj * tauj); break;
+            case RW_TRACKING_ANG_VEL: { const float e = cmd2 - ang_b.z; r = expf(-(e * e) / tf[TF_TRACKING_SIGMA]); break; }
+            case RW_TRACKING_LIN_VEL: { const float ex = cmd0 - lin_b.x, ey = cmd1 - lin_b.y; r = expf(-(ex * ex + ey * ey) / tf[TF_TRACKING_SIGMA]); break; }
+            default: break;
+            }
+            const float sr = __fmul_rn(r, tf[TF_REWARD_SCALE + id]);
+            rew = __fadd_rn(rew, sr);
+            if (lane == i) my_sum = __fadd_rn(my_sum, sr);
+        }
+        if (ti[TI_ONLY_POSITIVE]) rew = fmaxf(rew, 0.f);
+        if (ti[TI_TERMINATION_COL] >= 0) {
+            const float sr = __fmul_rn((reset && !time_out) ? 1.f : 0.f, tf[TF_REWARD_SCALE + RW_TERMINATION]);
+            rew = __fadd_rn(rew, sr);
+            if (lane == ti[TI_TERMINATION_COL]) my_sum = __fadd_rn(my_sum, sr);
+        }
+        if (lane == 0) B.rew_buf[env] = rew;
+    }
+    if ((pm & PHASE_TERMINATION) && lane == 0) { B.reset_buf[env] = reset ? 1 : 0; B.time_out_buf[env] = time_out ? 1 : 0; }
+
+    // ================================================================== reset_idx
+    f3 grav_obs = grav;
+    if ((pm & PHASE_RESET) && reset) {
+        if (lane < n_sums) atomicAdd(B.stats + lane, my_sum);                    // extras["episode"] numerators
+        if (lane == 0) atomicAdd(B.stats + n_sums, 1.0f);
+        my_sum = 0.f;
+        if (ti[TI_TERRAIN_CURRICULUM]) {                                          // legged_robot.py:254-272; genesis_simulator.py:140-148
+            const float ddx = __fsub_rn(bp.x, origin.x), ddy = __fsub_rn(bp.y, origin.y);
+            const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+            const bool up = dist > tf[TF_TERRAIN_HALF_LENGTH];
+            const float cn = __fsqrt_rn(__fadd_rn(__fmul_rn(cmd0, cmd0), __fmul_rn(cmd1, cmd1)));
+            const bool down = (dist < __fmul_rn(__fmul_rn(cn, tf[TF_EPISODE_LENGTH_S]), 0.5f)) && !up;
+            int lv = level0 + (up ? 1 : 0) - (down ? 1 : 0);
+            if (call.force_reset) lv = level0;               // init_done == False: no curriculum move
+            const int nl = ti[TI_NUM_LEVELS];
+            const int rnd = min((int)__fmul_rn(rng.u(SITE_LEVEL, 0), (float)nl), nl - 1);
+            lv = lv >= nl ? rnd : max(lv, 0);
+            const int ty = ttype;
+            const float *og = tr.origins + ((size_t)lv * tr.types + ty) * 3;
+            origin = mk3(og[0], og[1], og[2]);
+            if (lane == 0) B.terrain_levels[env] = lv;
+            if (lane < 3) B.env_origins[env * 3 + lane] = comp3(origin, lane);
+        }
+        {   // _resample_commands(env_ids)
+            cmd0 = rand_range(call.vx_lo, call.vx_span, rng.u(SITE_CMD_RESET, 0));
+            cmd1 = rand_range(tf[TF_CMD_VY_LO], tf[TF_CMD_VY_SPAN], rng.u(SITE_CMD_RESET, 1));
+            if (ti[TI_HEADING_COMMAND]) cmd3 = rand_range(tf[TF_CMD_HEADING_LO], tf[TF_CMD_HEADING_SPAN], rng.u(SITE_CMD_RESET, 2));
+            else cmd2 = rand_range(tf[TF_CMD_YAW_LO], tf[TF_CMD_YAW_SPAN], rng.u(SITE_CMD_RESET, 2));
+            const float keep = norm3_rn(cmd0, cmd1, cmd2) > 0.2f ? 1.f : 0.f;
+            cmd0 *= keep; cmd1 *= keep; cmd2 *= keep;
+        }
+        if (jl) {                                                                 // _reset_dofs: q0 + U(-r, r), qd = 0
+            const float rr = tf[TF_RESET_DOF_NOISE + lane];
+            qj = __fadd_rn(q0j, rand_range(-rr, __fmul_rn(2.0f, rr), rng.u(SITE_DOF, lane)));
+            qdj = 0.f; actj = 0.f;
+            B.dof_pos[env * A + lane] = qj; B.dof_vel[env * A + lane] = 0.f;
+            B.actions[env * A + lane] = 0.f; B.last_actions[env * A + lane] = 0.f; B.llast_actions[env * A + lane] = 0.f;
+            B.last_dof_vel[env * A + lane] = 0.f;
+        }
+        {   // _reset_root_states
+            bp = mk3(__fadd_rn(tf[TF_INIT_POS], origin.x), __fadd_rn(tf[TF_INIT_POS + 1], origin.y), __fadd_rn(tf[TF_INIT_POS + 2], origin.z));
+            if (ti[TI_HEIGHTFIELD]) {
+                const float sp = __fmul_rn(2.0f, tf[TF_RESET_ROOT_XY]);
+                bp.x = __fadd_rn(bp.x, rand_range(-tf[TF_RESET_ROOT_XY], sp, rng.u(SITE_ROOT, 0)));
+                bp.y = __fadd_rn(bp.y, rand_range(-tf[TF_RESET_ROOT_XY], sp, rng.u(SITE_ROOT, 1)));
+            }
+            const float sv = __fmul_rn(2.0f, tf[TF_RESET_ROOT_VEL]), lo = -tf[TF_RESET_ROOT_VEL];
+            lin_b = mk3(rand_range(lo, sv, rng.u(SITE_ROOT, 2)), rand_range(lo, sv, rng.u(SITE_ROOT, 3)), rand_range(lo, sv, rng.u(SITE_ROOT, 4)));
+            ang_b = mk3(rand_range(lo, sv, rng.u(SITE_ROOT, 5)), rand_range(lo, sv, rng.u(SITE_ROOT, 6)), rand_range(lo, sv, rng.u(SITE_ROOT, 7)));
+            const float ix = tf[TF_INIT_QUAT], iy = tf[TF_INIT_QUAT + 1], iz = tf[TF_INIT_QUAT + 2], iw = tf[TF_INIT_QUAT + 3];
+            grav_obs = rot_inv(ix, iy, iz, iw, mk3(0.f, 0.f, -1.f));
+            if (lane < 3) {
+                B.base_pos[env * 3 + lane] = comp3(bp, lane);
+                B.base_lin_w[env * 3 + lane] = comp3(lin_b, lane); B.base_ang_w[env * 3 + lane] = comp3(ang_b, lane);
+                B.base_lin_vel[env * 3 + lane] = comp3(lin_b, lane); B.base_ang_vel[env * 3 + lane] = comp3(ang_b, lane);
+                B.projected_gravity[env * 3 + lane] = comp3(grav_obs, lane);
+                B.last_base_lin_vel[env * 3 + lane] = 0.f; B.last_base_ang_vel[env * 3 + lane] = 0.f;
+            }
+            if (lane < 4) {
+                B.base_quat_wxyz[env * 4 + lane] = lane == 0 ? iw : (lane == 1 ? ix : (lane == 2 ? iy : iz));
+                B.base_quat[env * 4 + lane] = lane == 0 ? ix : (lane == 1 ? iy : (lane == 2 ? iz : iw));
+            }
+        }
+        // domain randomisation (genesis_simulator.py:62-82,665-739)
+        if (lane == 0) {
+            if (ti[TI_RAND_FRICTION]) B.friction[env] = rand_range(tf[TF_FRICTION_LO], tf[TF_FRICTION_SPAN], rng.u(SITE_FRICTION, 0));
+            if (ti[TI_RAND_MASS]) B.added_mass[env] = rand_range(tf[TF_MASS_LO], tf[TF_MASS_SPAN], rng.u(SITE_MASS, 0));
+            if (ti[TI_RAND_ARMATURE]) B.joint_armature[env] = rand_range(tf[TF_ARM_LO], tf[TF_ARM_SPAN], rng.u(SITE_ARMATURE, 0));
+            if (ti[TI_RAND_JFRICTION]) B.joint_friction[env] = rand_range(tf[TF_JFR_LO], tf[TF_JFR_SPAN], rng.u(SITE_JFRICTION, 0));
+            if (ti[TI_RAND_JDAMPING]) B.joint_damping[env] = rand_range(tf[TF_JDA_LO], tf[TF_JDA_SPAN], rng.u(SITE_JDAMPING, 0));
+        }
+        if (ti[TI_RAND_COM] && lane < 3)
+            B.com_bias[env * 3 + lane] = rand_range(tf[TF_COMX_LO + 2 * lane], tf[TF_COMX_SPAN + 2 * lane], rng.u(SITE_COM, lane));
+        if (ti[TI_RAND_PD] && jl) {
+            B.kp_scale[env * A + lane] = rand_range(tf[TF_KPS_LO], tf[TF_KPS_SPAN], rng.u(SITE_KP, lane));
+            B.kd_scale[env * A + lane] = rand_range(tf[TF_KDS_LO], tf[TF_KDS_SPAN], rng.u(SITE_KD, lane));
+        }
+        if (lane < 3 * F) B.last_feet_vel[env * 3 * F + lane] = 0.f;
+        fat = 0.f;
+        ep_len = 0; fail_cnt = 0;
+    }
+    // ---- write back the small per-env state
+    if (pm & (PHASE_CALLBACK | PHASE_RESET)) {
+        if (lane < 4) B.commands[env * 4 + lane] = lane == 0 ? cmd0 : (lane == 1 ? cmd1 : (lane == 2 ? cmd2 : cmd3));
+        if (lane == 0) B.episode_length[env] = ep_len;
+    }
+    if ((pm & (PHASE_TERMINATION | PHASE_RESET)) && lane == 0) B.fail_buf[env] = fail_cnt;
+    if (pm & (PHASE_REWARD | PHASE_RESET)) {
+        if (lane < n_sums) B.episode_sums[env * n_sums + lane] = my_sum;
+        if (fl) B.feet_air_time[env * F + lane] = fat;
+    }
+    __syncwarp();   // DR parameters written above are re-read below by other lanes
+
+    // ================================================================== compute_observations
+    if (pm & PHASE_OBSERVE) {
+        const int NO = ti[TI_NUM_OBS];
+        float *ob = es + ES_OBS, *nz = es + ES_NOISY;
+        if (lane < 3) {
+            const float cs = lane < 2 ? tf[TF_OS_LIN_VEL] : tf[TF_OS_ANG_VEL];
+            ob[lane] = __fmul_rn(lane == 0 ? cmd0 : (lane == 1 ? cmd1 : cmd2), cs);
+            ob[3 + lane] = comp3(grav_obs, lane);
+            ob[6 + lane] = __fmul_rn(comp3(ang_b, lane), tf[TF_OS_ANG_VEL]);
+        }
+        if (jl) {
+            ob[9 + lane] = __fmul_rn(__fsub_rn(qj, q0j), tf[TF_OS_DOF_POS]);
+            ob[9 + A + lane] = __fmul_rn(qdj, tf[TF_OS_DOF_VEL]);
+            ob[9 + 2 * A + lane] = actj;
+        }
+        __syncwarp();
+        const float clipo = tf[TF_CLIP_OBS];
+        for (int e = lane; e < NO; e += 32) {
+            float v = ob[e];
+            if (ti[TI_ADD_NOISE]) {
+                const float u = rng.u(SITE_OBS_NOISE, e);
+                v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(2.0f, u), 1.0f), tf[TF_NOISE_VEC + e]));
+            }
+            nz[e] = v;
+            B.obs_buf[env * NO + e] = fminf(fmaxf(v, -clipo), clipo);
+        }
+        if (ti[TI_OBS_KIND] == 1) {   // go2_ts: critic frame, privileged obs, history stacks
+            const int SC = ti[TI_SINGLE_CRITIC], NP = ti[TI_NUM_PRIV], NCS = ti[TI_CONTACT_STATES] ? ti[TI_N_CS] : 0;
+            float *cr = es + ES_CRIT, *pv = es + ES_PRIV;
+            const int DRN = 7 + 2 * A;
+            for (int e = lane; e < NO; e += 32) cr[e] = ob[e];
+            // domain_randomization_info (go2_ts.py:16-28)
+            for (int e = lane; e < DRN; e += 32) {
+                float v;
+                if (e == 0) v = __fsub_rn(B.friction[env], tf[TF_FRICTION_OFFSET]);
+                else if (e == 1) v = B.added_mass[env];
+                else if (e < 5) v = B.com_bias[env * 3 + e - 2];
+                else if (e < 7) v = e == 5 ? push_vel.x : push_vel.y;
+                else if (e < 7 + A) v = __fsub_rn(B.kp_scale[env * A + e - 7], tf[TF_KPS_OFFSET]);
+                else v = __fsub_rn(B.kd_scale[env * A + e - 7 - A], tf[TF_KDS_OFFSET]);
+                cr[NO + e] = v; pv[e] = v;
+            }
+            if (lane < 3) {
+                const float v = __fmul_rn(comp3(lin_b, lane), tf[TF_OS_LIN_VEL]);
+                cr[NO + DRN + lane] = v; pv[DRN + 12 * F + lane] = v;
+            }
+            for (int e = lane; e < NCS; e += 32) {
+                const float v = B.link_contact_states[env * NCS + e];
+                cr[NO + DRN + 3 + e] = v; pv[DRN + 12 * F + 3 + e] = v;
+            }
+            if (ti[TI_MEASURE_HEIGHTS]) {
+                for (int pt = lane; pt < P; pt += 32) {
+                    const float d = __fsub_rn(__fsub_rn(bp.z, tf[TF_HEIGHT_OBS_OFFSET]), B.measured_heights[env * P + pt]);
+                    cr[NO + DRN + 3 + NCS + pt] = __fmul_rn(fminf(fmaxf(d, -1.0f), 1.0f), tf[TF_OS_HEIGHT]);
+                }
+            }
+            for (int e = lane; e < 9 * F; e += 32) {
+                const float fz = B.feet_pos[(env * F + e / 9) * 3 + 2];
+                pv[DRN + e] = fminf(fmaxf(__fsub_rn(fz, B.height_around_feet[env * F * 9 + e]), -1.0f), 1.0f);
+            }
+            for (int e = lane; e < 3 * F; e += 32) pv[DRN + 9 * F + e] = B.normal_vector_around_feet[env * 3 * F + e];
+            __syncwarp();
+            for (int e = lane; e < NP; e += 32) B.privileged_obs_buf[env * NP + e] = fminf(fmaxf(pv[e], -clipo), clipo);
+            // history stacks: shift one frame out, append the new one (legged_robot_ts.py:29-47); cleared on reset (:120-125)
+            const bool cleared = (pm & PHASE_RESET) && reset;
+            {
+                const int W = ti[TI_FRAME_STACK] * NO, keepw = W - NO;
+                const float *src = B.obs_history[call.parity] + (size_t)env * W + NO;
+                float *dst = B.obs_history[call.parity ^ 1] + (size_t)env * W;
+                for (int e = lane; e < keepw; e += 32) dst[e] = cleared ? 0.f : src[e];
+                for (int e = lane; e < NO; e += 32) dst[keepw + e] = nz[e];
+            }
+            {
+                const int W = ti[TI_C_FRAME_STACK] * SC, keepw = W - SC;
+                const float *src = B.critic_obs[call.parity] + (size_t)env * W + SC;
+                float *dst = B.critic_obs[call.parity ^ 1] + (size_t)env * W;
+                for (int e = lane; e < keepw; e += 32) dst[e] = cleared ? 0.f : src[e];
+                for (int e = lane; e < SC; e += 32) dst[keepw + e] = cr[e];
+            }
+        }
+    }
+}
+
+__global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, 4)
+env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (env >= T.i[TI_NUM_ENVS]) return;
+    env_post_step_warp(T, B, tr, call, smem + warp * ES_TOTAL, env, lane);
+}

@@ -1,0 +1,151 @@
+"""``FusedLeggedEnv`` -- the VecEnv the rsl_rl runners drive, with the whole ``env.step`` on two CUDA kernels.
+
+Mirrors the call contract of ``LeggedRobot.step`` / ``LeggedRobotTS.step`` (legged_gym/envs/base/legged_robot.py:37-53,
+legged_robot_ts.py:59-76): same return tuples, same attribute names the runners read (``num_envs``, ``num_obs``,
+``num_privileged_obs``, ``num_actions``, ``max_episode_length``, ``episode_length_buf``, ``extras``, ``device``,
+``get_observations``, ``reset``).  Per policy step it issues
+
+    b200_dynamics_step   (clip/shift actions, 4 x [PD torque + rigid-body substep])
+    b200_env_post_step   (fused post_physics_step)
+
+and nothing else on the GPU; there is no host synchronisation inside ``step`` (SURVEY 8b "Threading").
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import task_spec as T
+from .simulator import B200Simulator
+
+
+class FusedLeggedEnv:
+    def __init__(self, spec: T.TaskSpec, num_envs: int, device: str = "cuda:0", terrain=None, env_offset: int = 0,
+                 num_envs_global: Optional[int] = None, cfg=None, debug_cells: bool = False):
+        self.spec = spec
+        self.cfg = cfg
+        self.device = device
+        self.headless = True
+        self.num_envs = int(num_envs)
+        self.simulator = B200Simulator(spec, None, device, True, num_envs=num_envs, terrain=terrain, env_offset=env_offset,
+                                       num_envs_global=num_envs_global, debug_cells=debug_cells)
+        sim = self.simulator
+        self._b = sim._buf
+        self.widths = spec.obs_widths(sim._model)
+        self.num_obs = self.widths["obs"]
+        self.num_privileged_obs = self.widths["priv"] if spec.obs_kind == "go2_ts" else None
+        self.num_actions = spec.num_actions
+        self.num_history_obs = self.widths["hist"]
+        self.num_critic_obs = self.widths["critic"]
+        self.dt = spec.dt
+        self.max_episode_length_s = spec.episode_length_s
+        self.max_episode_length = float(spec.max_episode_length)
+        self.common_step_counter = 0
+        self.command_ranges = dict(lin_vel_x=list(spec.cmd_lin_vel_x), lin_vel_y=list(spec.cmd_lin_vel_y),
+                                   ang_vel_yaw=list(spec.cmd_ang_vel_yaw), heading=list(spec.cmd_heading))
+        self.sum_names = spec.episode_sum_names()
+        self.reward_scales = {n: float(spec.reward_scales[n] * spec.dt) for n in self.sum_names}
+        self.extras = {}
+        self._pending_curriculum = None
+        self.init_done = True
+        # live views (same storage the kernels write)
+        b = self._b
+        self.obs_buf, self.rew_buf = b["obs_buf"], b["rew_buf"]
+        self.privileged_obs_buf = b["privileged_obs_buf"] if self.num_privileged_obs is not None else None
+        self.reset_buf = b["reset_buf"].view(torch.bool)
+        self.time_out_buf = b["time_out_buf"].view(torch.bool)
+        self.commands, self.actions = b["commands"], b["actions"]
+        self.last_actions, self.llast_actions = b["last_actions"], b["llast_actions"]
+        self.feet_air_time, self.fail_buf = b["feet_air_time"], b["fail_buf"]
+        self.episode_sums = {n: b["episode_sums"][:, i] for i, n in enumerate(self.sum_names)}
+
+    # runners assign a fresh tensor to env.episode_length_buf (on_policy_runner.py:169); keep the bound storage
+    @property
+    def episode_length_buf(self):
+        return self._b["episode_length"]
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value):
+        self._b["episode_length"].copy_(value.to(self._b["episode_length"].dtype))
+
+    @property
+    def obs_history(self):
+        return self._b[f"obs_history{self.simulator._parity}"]
+
+    @property
+    def critic_obs_buf(self):
+        return self._b[f"critic_obs{self.simulator._parity}"]
+
+    # ------------------------------------------------------------------ VecEnv API
+    def step(self, actions: torch.Tensor):
+        sim = self.simulator
+        sim.step(actions)                                      # _pre_sim_step + simulator.step
+        self.common_step_counter += 1
+        self._apply_pending_curriculum()
+        sim.fused_post_step(self.common_step_counter, self.command_ranges["lin_vel_x"])
+        self._fill_extras()
+        return self._returns()
+
+    def _returns(self):
+        if self.spec.obs_kind == "go2_ts":
+            return (self.obs_buf, self.privileged_obs_buf, self.obs_history, self.critic_obs_buf, self.rew_buf,
+                    self.reset_buf, self.extras)
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def reset(self):
+        """BaseTask.reset (base_task.py:60-64): reset_idx(all) then one zero-action step."""
+        self.simulator.fused_reset_all(self.common_step_counter, self.command_ranges["lin_vel_x"])
+        out = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
+        return out[:4] if self.spec.obs_kind == "go2_ts" else out[:2]
+
+    def get_observations(self):
+        if self.spec.obs_kind == "go2_ts":
+            return self.obs_buf, self.privileged_obs_buf, self.obs_history, self.critic_obs_buf
+        return self.obs_buf
+
+    def get_privileged_observations(self):
+        return self.privileged_obs_buf
+
+    # ------------------------------------------------------------------ extras / curricula (device side, no sync)
+    def _fill_extras(self):
+        """extras["episode"]["rew_*"] = mean over resetting envs of episode_sums / episode_length_s
+        (legged_robot.py:127-141), from the per-step reductions the kernel leaves in `stats`."""
+        n = len(self.sum_names)
+        stats = self._b["stats"]
+        cnt = stats[n].clamp(min=1.0)
+        means = stats[:n] / (cnt * self.max_episode_length_s)
+        ep = {"rew_" + name: means[i] for i, name in enumerate(self.sum_names)}
+        if self.spec.terrain_curriculum:
+            ep["terrain_level"] = self._b["terrain_levels"].float().mean()
+        if self.spec.cmd_curriculum:
+            ep["max_command_x"] = self.command_ranges["lin_vel_x"][1]
+        self.extras["episode"] = ep
+        if self.spec.send_timeouts:
+            self.extras["time_outs"] = self.time_out_buf
+        # command curriculum (legged_robot.py:110-111,336-348): evaluated on the reductions of this step and applied
+        # before the next one (one-step delay, DESIGN.md "deviations"); the only host read, once per max_episode_length.
+        if self.spec.cmd_curriculum and self.common_step_counter % int(self.max_episode_length) == 0 \
+                and "tracking_lin_vel" in self.sum_names:
+            i = self.sum_names.index("tracking_lin_vel")
+            self._pending_curriculum = (stats[i] / cnt / self.max_episode_length, stats[n].clone())
+
+    def _apply_pending_curriculum(self):
+        if self._pending_curriculum is None:
+            return
+        mean_track, cnt = self._pending_curriculum
+        self._pending_curriculum = None
+        if float(cnt) > 0 and float(mean_track) > self.spec.curriculum_threshold * self.reward_scales["tracking_lin_vel"]:
+            r = self.command_ranges["lin_vel_x"]
+            r[0] = float(np.clip(r[0] - 0.5, -self.spec.max_curriculum, 0.0))
+            r[1] = float(np.clip(r[1] + 0.5, 0.0, self.spec.max_curriculum))
+
+
+def make_env(task: str, num_envs: int, device: str = "cuda:0", terrain=None, env_offset: int = 0,
+             num_envs_global: Optional[int] = None, **spec_overrides) -> FusedLeggedEnv:
+    """Build a fused env from a built-in task preset (`go2`, `go2_ts`)."""
+    if task not in T.PRESETS:
+        raise ValueError(f"no fused descriptor for task {task!r} (available: {sorted(T.PRESETS)})")
+    spec = T.PRESETS[task](**spec_overrides)
+    return FusedLeggedEnv(spec, num_envs, device, terrain=terrain, env_offset=env_offset, num_envs_global=num_envs_global)

@@ -1,0 +1,221 @@
+/*
+ * b200_step.h -- C ABI of the B200-native "physics + environment step" backend.
+ *
+ * One shared library (hcr_genesis_lr_cl_b200/libb200step.so), plain pointers and sizes, no torch types.
+ * Every entry point replaces a piece of the reference's Python hot path (LeggedGym-Ex, paths relative
+ * to the reference root):
+ *
+ *   b200_dynamics_step   LeggedRobot._pre_sim_step            legged_gym/envs/base/legged_robot.py:230-252
+ *                        GenesisSimulator.step                legged_gym/simulator/genesis_simulator.py:20-33
+ *                        GenesisSimulator._compute_torques    legged_gym/simulator/genesis_simulator.py:630-642
+ *                        scene.step() (third-party engine)    legged_gym/simulator/genesis_simulator.py:29
+ *   b200_env_post_step   LeggedRobot.post_physics_step        legged_gym/envs/base/legged_robot.py:55-76
+ *                        GenesisSimulator.post_physics_step   legged_gym/simulator/genesis_simulator.py:35-60
+ *                        (+ everything those call: height scan :552-610, OOB :612-628, callbacks,
+ *                        check_termination, compute_reward, reset_idx, compute_observations)
+ *   b200_reset_all       BaseTask.reset -> reset_idx(all)     legged_gym/envs/base/base_task.py:60-64
+ *
+ * All state lives in caller-owned device buffers (torch CUDA tensors in the Python host layer) that are
+ * bound once with b200_bind_buffers(); the Simulator plugin properties (simulator.py:243-613) are
+ * zero-copy views of the same memory.  Functions return 0 on success, non-zero on failure with a
+ * message in b200_last_error() (the Python wrapper raises RuntimeError).  No host synchronisation
+ * happens inside the step functions; they enqueue on the stream they are given.
+ *
+ * The enums below index the flat task descriptor (float[] / int[]); hcr_genesis_lr_cl_b200/_cabi.py parses
+ * this header, so the names here are the single source of truth for the host layer too.
+ */
+#ifndef B200_STEP_H
+#define B200_STEP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_MAX_JOINTS 12
+#define B200_MAX_CHAINS 4
+#define B200_MAX_BODIES 13
+#define B200_MAX_LINKS 17
+#define B200_MAX_SPHERES 64
+#define B200_MAX_FEET 4
+#define B200_KMAX 8        /* contacts kept per env                        */
+#define B200_AUXMAX 8      /* joint-limit + frictionloss constraint rows   */
+#define B200_RMAX 32       /* constraint rows = 3*KMAX + AUXMAX = one warp */
+#define B200_MAX_REWARDS 26
+#define B200_MAX_OBS 48
+#define B200_MAX_PTS_AXIS 17
+#define B200_BODY_STRIDE 20
+
+/* ---- task descriptor: float section ---- */
+enum B200TaskF {
+    TF_SIM_DT, TF_POLICY_DT, TF_ACTION_SCALE, TF_KP, TF_KD, TF_CLIP_ACTIONS, TF_CLIP_OBS,
+    TF_INIT_POS, TF_INIT_POS_1, TF_INIT_POS_2, TF_INIT_QUAT, TF_INIT_QUAT_1, TF_INIT_QUAT_2, TF_INIT_QUAT_3, /* xyzw */
+    TF_RESET_ROOT_XY, TF_RESET_ROOT_VEL, TF_FAIL_LIMIT, TF_MAX_PROJ_GRAV,
+    TF_HSCALE, TF_VSCALE, TF_BORDER, TF_X_LO, TF_X_HI, TF_Y_LO, TF_Y_HI, TF_TERRAIN_HALF_LENGTH, TF_EPISODE_LENGTH_S,
+    /* uniform ranges are stored as (lower, span) with span = fp32(upper - lower) evaluated in double, which is
+       what torch_rand_float does with its python-float arguments (math_utils.py:78-81) */
+    TF_CMD_VY_LO, TF_CMD_VY_SPAN, TF_CMD_YAW_LO, TF_CMD_YAW_HI, TF_CMD_YAW_SPAN, TF_CMD_HEADING_LO, TF_CMD_HEADING_SPAN,
+    TF_FRICTION_LO, TF_FRICTION_SPAN, TF_MASS_LO, TF_MASS_SPAN, TF_COMX_LO, TF_COMX_SPAN, TF_COMY_LO, TF_COMY_SPAN,
+    TF_COMZ_LO, TF_COMZ_SPAN, TF_KPS_LO, TF_KPS_SPAN, TF_KDS_LO, TF_KDS_SPAN, TF_ARM_LO, TF_ARM_SPAN, TF_JFR_LO, TF_JFR_SPAN,
+    TF_JDA_LO, TF_JDA_SPAN, TF_MAX_PUSH, TF_FRICTION_OFFSET, TF_KPS_OFFSET, TF_KDS_OFFSET,
+    TF_OS_LIN_VEL, TF_OS_ANG_VEL, TF_OS_DOF_POS, TF_OS_DOF_VEL, TF_OS_HEIGHT, TF_HEIGHT_OBS_OFFSET,
+    TF_TRACKING_SIGMA, TF_BASE_HEIGHT_TARGET, TF_FOOT_CLEARANCE_TARGET, TF_FOOT_HEIGHT_OFFSET, TF_FOOT_CLEARANCE_SIGMA,
+    TF_ABOUT_LANDING, TF_AIR_TIME_THRESHOLD,
+    TF_GRAV, TF_TC, TF_DAMPRATIO, TF_D0, TF_DMAX, TF_WIDTH, TF_MID, TF_POWER, TF_TERRAIN_MU, TF_GEOM_MU,
+    TF_DEFAULT_DOF_POS,                                         /* [B200_MAX_JOINTS] */
+    TF_RESET_DOF_NOISE = TF_DEFAULT_DOF_POS + B200_MAX_JOINTS,  /* [B200_MAX_JOINTS] */
+    TF_DOF_LIM_LO = TF_RESET_DOF_NOISE + B200_MAX_JOINTS,       /* [B200_MAX_JOINTS] soft limits */
+    TF_DOF_LIM_HI = TF_DOF_LIM_LO + B200_MAX_JOINTS,            /* [B200_MAX_JOINTS] */
+    TF_REWARD_SCALE = TF_DOF_LIM_HI + B200_MAX_JOINTS,          /* [B200_MAX_REWARDS] scale*dt, by term id */
+    TF_NOISE_VEC = TF_REWARD_SCALE + B200_MAX_REWARDS,          /* [B200_MAX_OBS] */
+    TF_POINTS_X = TF_NOISE_VEC + B200_MAX_OBS,                  /* [B200_MAX_PTS_AXIS] */
+    TF_POINTS_Y = TF_POINTS_X + B200_MAX_PTS_AXIS,              /* [B200_MAX_PTS_AXIS] */
+    TF_COUNT = TF_POINTS_Y + B200_MAX_PTS_AXIS
+};
+
+/* ---- task descriptor: int section ---- */
+enum B200TaskI {
+    TI_NUM_ENVS, TI_A, TI_C, TI_D, TI_L, TI_F, TI_PX, TI_PY, TI_NSPHERES, TI_DECIMATION, TI_PGS_ITERS,
+    TI_OBS_KIND, TI_NUM_OBS, TI_NUM_PRIV, TI_SINGLE_CRITIC, TI_FRAME_STACK, TI_C_FRAME_STACK,
+    TI_MAX_EPISODE_LENGTH, TI_RESAMPLE_INTERVAL, TI_PUSH_INTERVAL,
+    TI_HEIGHTFIELD, TI_MEASURE_HEIGHTS, TI_FEET_INFO, TI_TERRAIN_CURRICULUM, TI_HEADING_COMMAND, TI_PUSH_ROBOTS,
+    TI_ADD_NOISE, TI_ONLY_POSITIVE, TI_RAND_FRICTION, TI_RAND_MASS, TI_RAND_COM, TI_RAND_PD, TI_RAND_ARMATURE,
+    TI_RAND_JFRICTION, TI_RAND_JDAMPING, TI_CONTACT_STATES, TI_CLEARANCE_USES_TERRAIN,
+    TI_NUM_LEVELS, TI_NUM_TYPES, TI_HF_ROWS, TI_HF_COLS, TI_SEED_LO, TI_SEED_HI,
+    TI_N_REWARDS, TI_TERMINATION_COL,                            /* column of "termination" in episode_sums or -1 */
+    TI_N_PEN, TI_N_TERM, TI_N_CS,
+    TI_ENV_OFFSET,                                               /* global id of local env 0 (multi-GPU sharding; keys the RNG) */
+    TI_REWARD_IDS,                                               /* [B200_MAX_REWARDS] active term ids, evaluation order */
+    TI_FEET_LINKS = TI_REWARD_IDS + B200_MAX_REWARDS,            /* [B200_MAX_FEET]  */
+    TI_PEN_LINKS = TI_FEET_LINKS + B200_MAX_FEET,                /* [B200_MAX_LINKS] */
+    TI_TERM_LINKS = TI_PEN_LINKS + B200_MAX_LINKS,               /* [B200_MAX_LINKS] */
+    TI_CS_LINKS = TI_TERM_LINKS + B200_MAX_LINKS,                /* [B200_MAX_LINKS] */
+    TI_COUNT = TI_CS_LINKS + B200_MAX_LINKS
+};
+
+/* reward term ids (alphabetical == the reference's evaluation order, legged_robot.py:411-434) */
+enum B200Reward {
+    RW_ACTION_RATE, RW_ACTION_SMOOTHNESS, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_COLLISION, RW_DOF_ACC,
+    RW_DOF_CLOSE_TO_DEFAULT, RW_DOF_POS_LIMITS, RW_DOF_POS_STAND_STILL, RW_DOF_POWER, RW_DOF_VEL,
+    RW_DOF_VEL_STAND_STILL, RW_FEET_AIR_TIME, RW_FEET_CONTACT_STAND_STILL, RW_FOOT_ACC, RW_FOOT_CLEARANCE,
+    RW_FOOT_LANDING_VEL, RW_HIP_POS, RW_KEEP_BALANCE, RW_LIN_VEL_Z, RW_ORIENTATION, RW_THIGH_POS, RW_TORQUES,
+    RW_TRACKING_ANG_VEL, RW_TRACKING_LIN_VEL, RW_TERMINATION, RW_COUNT
+};
+
+/* random-draw sites: u = philox4x32-10(key = seed, counter = (env, step, site, idx >> 2))[idx & 3] */
+enum B200Site {
+    SITE_CMD_RESAMPLE, SITE_PUSH, SITE_LEVEL, SITE_CMD_RESET, SITE_DOF, SITE_ROOT, SITE_FRICTION, SITE_MASS, SITE_COM,
+    SITE_KP, SITE_KD, SITE_ARMATURE, SITE_JFRICTION, SITE_JDAMPING, SITE_OBS_NOISE
+};
+
+/* phases of b200_env_post_step (bit mask) */
+enum B200Phase {
+    PHASE_SIM_POST = 1,      /* GenesisSimulator.post_physics_step: derived base state, contacts, height scan */
+    PHASE_CALLBACK = 2,      /* command resampling, heading command, pushes */
+    PHASE_TERMINATION = 4,
+    PHASE_REWARD = 8,
+    PHASE_RESET = 16,
+    PHASE_OBSERVE = 32,
+    PHASE_ALL = 63
+};
+
+/*
+ * Device buffers, row-major [num_envs, k] float32 unless noted.  The field order below is the ABI
+ * (the host layer fills a ctypes array of pointers in this order).
+ */
+typedef struct B200Buffers {
+    /* physics state */
+    float *base_pos;            /* [N,3]  world; also the API `base_pos`                              */
+    float *base_quat_wxyz;      /* [N,4]  engine convention (genesis_simulator.py:40)                 */
+    float *base_lin_w;          /* [N,3]  world-frame linear velocity (dofs 0..2)                     */
+    float *base_ang_w;          /* [N,3]  world-frame angular velocity (dofs 3..5)                    */
+    float *dof_pos;             /* [N,A]  joint positions, cfg.asset.dof_names order                  */
+    float *dof_vel;             /* [N,A]                                                              */
+    /* domain randomisation (private attrs the tasks read) */
+    float *friction;            /* [N,1]  _friction_values     */
+    float *added_mass;          /* [N,1]  _added_base_mass     */
+    float *com_bias;            /* [N,3]  _base_com_bias       */
+    float *kp_scale;            /* [N,A]  _kp_scale            */
+    float *kd_scale;            /* [N,A]  _kd_scale            */
+    float *joint_armature;      /* [N,1]  _joint_armature      */
+    float *joint_friction;      /* [N,1]  _joint_friction      */
+    float *joint_damping;       /* [N,1]  _joint_damping       */
+    float *rand_push_vels;      /* [N,3]  _rand_push_vels      */
+    /* task state */
+    float *actions;             /* [N,A] */
+    float *last_actions;        /* [N,A] */
+    float *llast_actions;       /* [N,A] */
+    float *commands;            /* [N,4] */
+    int32_t *episode_length;    /* [N] int32 (episode_length_buf) */
+    int32_t *fail_buf;          /* [N] int32 */
+    float *feet_air_time;       /* [N,F] */
+    uint8_t *last_contacts;     /* [N,F] uint8 */
+    float *episode_sums;        /* [N,n_sums] columns = active reward terms (+ termination) */
+    int64_t *terrain_levels;    /* [N] int64 */
+    int64_t *terrain_types;     /* [N] int64 */
+    float *env_origins;         /* [N,3] */
+    /* derived, API visible */
+    float *base_quat;           /* [N,4] xyzw */
+    float *base_euler;          /* [N,3] */
+    float *base_lin_vel;        /* [N,3] body frame */
+    float *base_ang_vel;        /* [N,3] body frame */
+    float *projected_gravity;   /* [N,3] */
+    float *torques;             /* [N,A] unclipped PD torque of the last substep */
+    float *link_contact_forces; /* [N,L,3] */
+    float *feet_pos;            /* [N,F,3] */
+    float *feet_vel;            /* [N,F,3] */
+    float *link_contact_states; /* [N,n_cs] */
+    float *measured_heights;    /* [N,P] */
+    float *height_around_feet;  /* [N,F,9] */
+    float *normal_vector_around_feet; /* [N,3F] */
+    float *last_dof_vel;        /* [N,A] */
+    float *last_feet_vel;       /* [N,F,3] */
+    float *last_base_lin_vel;   /* [N,3] */
+    float *last_base_ang_vel;   /* [N,3] */
+    /* outputs */
+    float *obs_buf;             /* [N,num_obs]   */
+    float *privileged_obs_buf;  /* [N,num_priv]  */
+    float *obs_history[2];      /* [N,frame_stack*num_obs]      ping-pong, see b200_env_post_step */
+    float *critic_obs[2];       /* [N,c_frame_stack*single]     ping-pong */
+    float *rew_buf;             /* [N] */
+    uint8_t *reset_buf;         /* [N] uint8 (torch.bool storage) */
+    uint8_t *time_out_buf;      /* [N] uint8 */
+    int32_t *height_cells;      /* [N,P,2] int32 cell indices of the scan (diagnostic, may be NULL) */
+    float *stats;               /* [2*n_sums+4] per-step reductions: sum over resetting envs of episode_sums,
+                                   then [n_sums]=count of resets, [n_sums+1]=sum of terrain levels (all envs) */
+} B200Buffers;
+
+typedef struct B200Handle B200Handle;
+
+int b200_create(const int32_t *model_i, int n_model_i, const float *model_f, int n_model_f,
+                const int32_t *task_i, int n_task_i, const float *task_f, int n_task_f, B200Handle **out);
+void b200_destroy(B200Handle *h);
+int b200_set_terrain(B200Handle *h, const int16_t *dev_height_samples, int rows, int cols,
+                     const float *dev_terrain_origins, int num_levels, int num_types);
+int b200_bind_buffers(B200Handle *h, const B200Buffers *bufs);
+
+/* clip + shift action history, save last_*, then `decimation` x (PD torque, rigid-body substep). */
+int b200_dynamics_step(B200Handle *h, const float *dev_actions, void *cuda_stream);
+
+/* Fused post_physics_step. `step_counter` is LeggedRobot.common_step_counter *after* its increment;
+ * `cmd_vx_lo/span` is the (curriculum-mutable) lin_vel_x command range as (lower, fp32(upper-lower)); `parity` (0/1) selects which of the
+ * ping-pong history buffers is read (parity) and written (parity^1). */
+int b200_env_post_step(B200Handle *h, long long step_counter, float cmd_vx_lo, float cmd_vx_span, int parity,
+                       int phase_mask, void *cuda_stream);
+
+/* reset_idx(all envs) without a preceding step (BaseTask.reset). */
+int b200_reset_all(B200Handle *h, long long step_counter, float cmd_vx_lo, float cmd_vx_span, int parity, void *cuda_stream);
+
+/* static resource usage of a kernel ("dynamics" | "env"): registers/thread, static+dynamic smem/block, max blocks/SM */
+int b200_kernel_info(B200Handle *h, const char *kernel, int *regs, int *smem_bytes, int *blocks_per_sm, int *block_threads);
+
+/* number of kernel launches issued through this handle since creation */
+long long b200_launch_count(B200Handle *h);
+
+const char *b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_STEP_H */

@@ -1,0 +1,125 @@
+"""TEST-ONLY helpers: run the CUDA kernel sources on the host warp emulator (tests/warp_emu) with numpy buffers,
+and drive the CPU oracle through the same policy step for comparison."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from hcr_genesis_lr_cl_b200 import _cabi
+from oracle import physics as ophys
+
+_EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "warp_emu")
+_CSRC = os.path.join(os.path.dirname(_EMU_DIR), "..", "hcr_genesis_lr_cl_b200", "csrc")
+
+
+def build_emu(with_env=True):
+    out = os.path.join(_EMU_DIR, "libwarpemu.so")
+    srcs = [os.path.join(_EMU_DIR, f) for f in ("emu.cpp", "emu_main.cpp", "emu.h")]
+    srcs += [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
+    srcs.append(os.path.join(os.path.dirname(_EMU_DIR), "..", "include", "b200_step.h"))
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        cmd = ["g++", "-O1", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-I", _EMU_DIR, "-o", out,
+               os.path.join(_EMU_DIR, "emu.cpp"), os.path.join(_EMU_DIR, "emu_main.cpp")]
+        if with_env:
+            cmd.insert(1, "-DEMU_WITH_ENV")
+        subprocess.check_call(cmd)
+    return ctypes.CDLL(out)
+
+
+class EmuSim:
+    """numpy-buffer twin of the device-side state; the emulated kernels read/write it in place."""
+
+    def __init__(self, spec, num_envs, height_samples=None, terrain_origins=None, with_env=True):
+        self.lib = build_emu(with_env)
+        self.spec, self.N = spec, num_envs
+        self.model = spec.load_model()
+        self.hs = None if height_samples is None else np.ascontiguousarray(height_samples, np.int16)
+        self.origins = None if terrain_origins is None else np.ascontiguousarray(terrain_origins, np.float32)
+        shape = self.hs.shape if self.hs is not None else (0, 0)
+        self.tf, self.ti = _cabi.pack_task(spec, self.model, num_envs, shape)
+        self.mi, self.mf = self.model.packed_ints(), self.model.packed_floats()
+        self.buf = {k: np.zeros(s, d) for k, (s, d) in _cabi.buffer_shapes(spec, self.model, num_envs).items()}
+        self.buf["base_quat_wxyz"][:, 0] = 1
+        self.buf["added_mass"][:] = 1
+        self.buf["kp_scale"][:] = 1
+        self.buf["kd_scale"][:] = 1
+        self.cbuf = _cabi.fill_buffers(lambda n: self.buf[n].ctypes.data)
+        self.parity = 0
+        self.step_counter = 0
+        self.cmd_range_x = [float(spec.cmd_lin_vel_x[0]), float(spec.cmd_lin_vel_x[1])]
+
+    @staticmethod
+    def _p(a):
+        return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+    def load_state(self, st):
+        alias = {"q": "dof_pos", "qd": "dof_vel", "obs_hist": f"obs_history{self.parity}", "critic_hist": f"critic_obs{self.parity}"}
+        for k, v in st.items():
+            name = alias.get(k, k)
+            if name in self.buf and np.asarray(v).size == self.buf[name].size:
+                self.buf[name][...] = np.asarray(v).reshape(self.buf[name].shape)
+        if "common_step_counter" in st:
+            self.step_counter = int(st["common_step_counter"])
+        if "cmd_range_x" in st:
+            self.cmd_range_x = [float(x) for x in st["cmd_range_x"]]
+
+    def dynamics_step(self, actions):
+        a = np.ascontiguousarray(actions, np.float32)
+        rows, cols = (self.hs.shape if self.hs is not None else (0, 0))
+        self.lib.emu_dynamics_step(self._p(self.tf), self._p(self.ti), self._p(self.mi), self._p(self.mf), self._p(self.hs),
+                                   ctypes.c_int(rows), ctypes.c_int(cols), ctypes.byref(self.cbuf), self._p(a))
+
+    def env_post_step(self, phase_mask=63, force_reset=0):
+        rows, cols = (self.hs.shape if self.hs is not None else (0, 0))
+        lv, ty = (self.origins.shape[:2] if self.origins is not None else (0, 0))
+        self.step_counter += 1
+        lo, hi = self.cmd_range_x
+        self.lib.emu_env_post_step(self._p(self.tf), self._p(self.ti), self._p(self.hs), ctypes.c_int(rows), ctypes.c_int(cols),
+                                   self._p(self.origins), ctypes.c_int(lv), ctypes.c_int(ty), ctypes.byref(self.cbuf),
+                                   ctypes.c_longlong(self.step_counter), ctypes.c_float(lo), ctypes.c_float(np.float32(hi - lo)),
+                                   ctypes.c_int(self.parity), ctypes.c_int(phase_mask), ctypes.c_int(force_reset))
+        self.parity ^= 1
+
+    @property
+    def obs_history(self):
+        return self.buf[f"obs_history{self.parity}"]
+
+    @property
+    def critic_obs(self):
+        return self.buf[f"critic_obs{self.parity}"]
+
+
+def oracle_params(spec, model, hf=None):
+    return ophys.default_params(dt=spec.sim_dt, iters=spec.pgs_iterations, hscale=spec.horizontal_scale,
+                                vscale=spec.vertical_scale, border=spec.border_size if spec.heightfield else 0.0,
+                                terrain_mu=spec.static_friction, geom_mu=1.0)
+
+
+def oracle_policy_step(spec, model, oracle, st, actions):
+    """Reference statement of one decimated physics step (genesis_simulator.py:20-33) on a state dict `st` of fp32
+    arrays (keys as B200Buffers).  Returns the post-physics dict the env half consumes (float64 internally)."""
+    f32 = np.float32
+    N, A = actions.shape
+    a = np.clip(actions.astype(f32), f32(-spec.clip_actions), f32(spec.clip_actions))
+    state = np.concatenate([st["base_pos"], st["base_quat_wxyz"], st["base_lin_w"], st["base_ang_w"]], axis=1).astype(np.float64)
+    q, qd = st["dof_pos"].astype(np.float64).copy(), st["dof_vel"].astype(np.float64).copy()
+    envp = np.concatenate([st["added_mass"], st["com_bias"], st["friction"]], axis=1).astype(np.float64)
+    arm = np.tile(model.body[1:, 19][None, :], (N, 1)).astype(np.float64)
+    if spec.randomize_joint_armature:
+        arm = np.tile(st["joint_armature"], (1, A)).astype(np.float64)
+    dmp = np.tile(st["joint_damping"], (1, A)).astype(np.float64) if spec.randomize_joint_damping else np.zeros((N, A))
+    fls = np.tile(st["joint_friction"], (1, A)).astype(np.float64) if spec.randomize_joint_friction else np.zeros((N, A))
+    jp = np.concatenate([arm, dmp, fls], axis=1)
+    q0 = np.asarray(spec.default_dof_pos, f32)[None, :]
+    kp, kd = (st["kp_scale"] * f32(spec.kp)).astype(f32), (st["kd_scale"] * f32(spec.kd)).astype(f32)
+    tgt = (a * f32(spec.action_scale) + q0).astype(f32)
+    tau = np.zeros((N, A), f32)
+    lf = nc = None
+    for _ in range(spec.decimation):
+        tau = (kp * (tgt - q.astype(f32)) - kd * qd.astype(f32)).astype(f32)
+        lf, nc = oracle.substep(state, q, qd, tau, envp, jp)
+    lp, lv = oracle.link_kinematics(state, q, qd)
+    feet = spec.link_groups(model)[0]
+    return dict(base_pos=state[:, 0:3], base_quat_wxyz=state[:, 3:7], base_lin_w=state[:, 7:10], base_ang_w=state[:, 10:13],
+                q=q, qd=qd, torques=tau, link_force=lf, feet_pos=lp[:, feet], feet_vel=lv[:, feet], ncontact=nc)

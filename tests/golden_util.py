@@ -14,8 +14,8 @@ def load_golden(name):
 
 
 def load_terrain():
-    z = np.load(os.path.join(GOLDEN_DIR, "go2_rough_terrain.npz"))
-    return z["height_samples"], z["terrain_origins"]
+    from hcr_genesis_lr_cl_b200.terrain_assets import load_go2_rough_terrain
+    return load_go2_rough_terrain()
 
 
 def spec_for(g):

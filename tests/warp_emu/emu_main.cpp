@@ -1,0 +1,52 @@
+// tests/warp_emu/emu_main.cpp -- TEST-ONLY (see emu.h): C entry points that run the kernels of
+// hcr_genesis_lr_cl_b200/csrc on the single-warp emulator with host (numpy) buffers.
+#define B200_WARP_EMU 1
+#include "emu.h"
+#include "../../hcr_genesis_lr_cl_b200/csrc/dynamics_kernel.cuh"
+#ifdef EMU_WITH_ENV
+#include "../../hcr_genesis_lr_cl_b200/csrc/env_kernel.cuh"
+#endif
+
+struct DynArgs { TaskDev T; B200Buffers B; ModelDev M; TerrainDev tr; const float *actions; };
+
+static void dyn_body(void *p) {
+    DynArgs *a = (DynArgs *)p;
+    if (a->T.i[TI_C] == 4) dynamics_step_kernel<4>(a->T, a->B, a->M, a->tr, a->actions);
+    else dynamics_step_kernel<2>(a->T, a->B, a->M, a->tr, a->actions);
+}
+
+static ModelDev mk_model(const TaskDev &T, const int *mi, const float *mf) {
+    ModelDev M; const int nb = 1 + T.i[TI_A], nl = T.i[TI_L], ns = T.i[TI_NSPHERES];
+    M.body = mf; M.link_off = mf + nb * B200_BODY_STRIDE; M.sph = M.link_off + 3 * nl;
+    M.link_body = mi + 8; M.sph_body = M.link_body + nl; M.sph_link = M.sph_body + ns;
+    return M;
+}
+
+extern "C" {
+int emu_dynamics_step(const float *tf, const int *ti, const int *mi, const float *mf, const int16_t *hf, int rows, int cols,
+                      const B200Buffers *bufs, const float *actions) {
+    static DynArgs a;
+    memcpy(a.T.f, tf, sizeof a.T.f); memcpy(a.T.i, ti, sizeof a.T.i);
+    a.B = *bufs; a.M = mk_model(a.T, mi, mf);
+    a.tr.hf = rows > 0 ? hf : nullptr; a.tr.origins = nullptr; a.tr.rows = rows; a.tr.cols = cols; a.tr.levels = a.tr.types = 0;
+    a.actions = actions;
+    emu_launch(dyn_body, &a, a.T.i[TI_NUM_ENVS]);
+    return 0;
+}
+
+#ifdef EMU_WITH_ENV
+struct EnvArgs { TaskDev T; B200Buffers B; TerrainDev tr; EnvCall call; };
+static void env_body(void *p) { EnvArgs *a = (EnvArgs *)p; env_post_step_kernel(a->T, a->B, a->tr, a->call); }
+int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int rows, int cols, const float *origins, int levels, int types,
+                      const B200Buffers *bufs, long long step, float vx_lo, float vx_span, int parity, int phase_mask, int force_reset) {
+    static EnvArgs a;
+    memcpy(a.T.f, tf, sizeof a.T.f); memcpy(a.T.i, ti, sizeof a.T.i);
+    a.B = *bufs;
+    a.tr.hf = rows > 0 ? hf : nullptr; a.tr.origins = origins; a.tr.rows = rows; a.tr.cols = cols; a.tr.levels = levels; a.tr.types = types;
+    a.call.step = (uint32_t)step; a.call.vx_lo = vx_lo; a.call.vx_span = vx_span; a.call.parity = parity; a.call.phase_mask = phase_mask;
+    a.call.force_reset = force_reset;
+    emu_launch(env_body, &a, a.T.i[TI_NUM_ENVS]);
+    return 0;
+}
+#endif
+}

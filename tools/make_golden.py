@@ -255,7 +255,7 @@ def main():
         rec[k] = np.stack(v)
     name = args.name or f"{args.task}_n{N}"
     if spec.heightfield:
-        # the terrain itself is a fixture of its own (tests/golden/go2_rough_terrain.npz); keep a checksum here
+        # the terrain itself is a fixture of its own (hcr_genesis_lr_cl_b200/assets/go2_rough_terrain.npz); keep a checksum here
         rec["terrain_crc"] = np.int64(int(np.asarray(sim._height_samples.numpy(), np.int64).sum()))
     rec["meta/task"] = np.array(args.task)
     rec["meta/seed"] = np.int64(spec.seed)
@@ -266,7 +266,7 @@ def main():
     resets = int(rec["out/reset_buf"].sum())
     print(f"wrote {out}: {os.path.getsize(out)/1e3:.0f} kB, resets={resets}, time_outs={int(rec['out/time_out_buf'].sum())}")
     if spec.heightfield:
-        tpath = os.path.join(ROOT, "tests", "golden", "go2_rough_terrain.npz")
+        tpath = os.path.join(ROOT, "hcr_genesis_lr_cl_b200", "assets", "go2_rough_terrain.npz")
         if not os.path.exists(tpath):
             np.savez_compressed(tpath, height_samples=sim._height_samples.numpy().astype(np.int16),
                                 terrain_origins=sim._terrain_origins.numpy().astype(np.float32))
