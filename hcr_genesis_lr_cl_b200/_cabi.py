@@ -121,7 +121,7 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     # physics formulation constants: MuJoCo-style soft constraints
     sf("TF_GRAV", 9.81); sf("TF_TC", 2 * spec.sim_dt); sf("TF_DAMPRATIO", 1.0)
     sf("TF_D0", 0.9); sf("TF_DMAX", 0.95); sf("TF_WIDTH", 0.001); sf("TF_MID", 0.5); sf("TF_POWER", 2.0)
-    sf("TF_TERRAIN_MU", spec.static_friction); sf("TF_GEOM_MU", 1.0)
+    sf("TF_TERRAIN_MU", spec.static_friction); sf("TF_GEOM_MU", 1.0); sf("TF_PGS_TOL", spec.pgs_tolerance)
     lim = soft_dof_limits(spec, model)
     for j in range(A):
         sf("TF_DEFAULT_DOF_POS", spec.default_dof_pos[j], j); sf("TF_RESET_DOF_NOISE", spec.reset_dof_noise[j], j)

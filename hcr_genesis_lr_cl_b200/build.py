@@ -23,7 +23,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: the CUDA extension cannot be built (and there is no fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", out, os.path.join(_CSRC, "b200_step.cu")]
+    extra = os.environ.get("B200_NVCC_EXTRA", "").split()      # tuning experiments, e.g. -DDYN_MIN_BLOCKS=5
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", out, os.path.join(_CSRC, "b200_step.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(_PKG, "build.log"), "w") as f:

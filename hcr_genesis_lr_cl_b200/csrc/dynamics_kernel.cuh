@@ -25,7 +25,22 @@
 #include "cuda_compat.cuh"
 #include "../../include/b200_step.h"
 
+#ifndef DYN_WARPS_PER_BLOCK
 #define DYN_WARPS_PER_BLOCK 4
+#endif
+// The substep body is ~7k SASS instructions of mostly straight-line code (~110 KB), larger than the 32 KB L1.5
+// instruction cache: warps that drift apart each stream it from L2 and the kernel becomes instruction-fetch bound
+// (ncu: stall_no_instruction on top, profiles/r1b).  A CTA barrier at each phase boundary keeps the 4 warps of a CTA
+// in the same code region so one fetch serves all of them: 0.545 -> 0.414 ms per launch at 4096 envs.
+#ifndef DYN_NO_PHASE_SYNC
+#define PHASE_SYNC() __syncthreads()
+#define DYN_PHASE_SYNCS_PER_SUBSTEP 5
+#else
+#define PHASE_SYNC()
+#endif
+#ifndef DYN_MIN_BLOCKS
+#define DYN_MIN_BLOCKS 6      // resident CTAs per SM the register allocator must allow (80 regs/thread, 24 warps/SM)
+#endif
 
 struct TaskDev {
     float f[TF_COUNT];
@@ -242,6 +257,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 
     for (int sub = 0; sub <= T.i[TI_DECIMATION]; sub++) {
         const bool last_pass = sub == T.i[TI_DECIMATION];   // kinematics-only pass for the outputs
+        PHASE_SYNC();
         // ---------------- PD torque (genesis_simulator.py:630-642) ----------------
         if (!last_pass) {
 #pragma unroll
@@ -297,6 +313,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         __syncwarp();
         if (last_pass) break;
 
+        PHASE_SYNC();
         // backward pass along the chain: composite inertias, bias forces, CRBA columns
         float Dm[6];           // chain block, lower tri (00,10,11,20,21,22)
         f3 BP[3], BL[3];       // base coupling: column k of B^T = (P_k (lin rows), L_k (ang rows))
@@ -422,6 +439,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             for (int e = 0; e < 6; e++) ws[WS_AF + e] = ab[e];
         }
 
+        PHASE_SYNC();
         // ---------------- collision detection: two spheres per lane ----------------
         float sdist[2]; f3 sn[2], sx[2]; bool act[2];
 #pragma unroll
@@ -507,6 +525,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         __syncwarp();
         const int R = 3 * nc + nlim + nfls;
 
+        PHASE_SYNC();
         // ---------------- constraint rows: one per lane ----------------
         float Jb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Jl[3] = {0.f, 0.f, 0.f};
         int cl = -1, kind = 5;          // 0 normal, 1/2 tangents, 3 limit, 4 frictionloss, 5 unused
@@ -610,42 +629,62 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             const int src = (kind == 1) ? lane - 1 : ((kind == 2) ? lane - 2 : lane);
             imp = __shfl_sync(B200_FULL_MASK, imp, src);
         }
-        float f = 0.f, Rr = 0.f, dd = 1.f, wres = 0.f;
+        float f = 0.f, Rr = 0.f, idd = 1.f, wres = 0.f;
         if (lane < R) {
             const float aref = -bd * vel - kk * imp * rpos;
             Rr = (1.f - imp) / imp * Arr;
-            dd = Arr + Rr;
+            idd = 1.f / (Arr + Rr);
             wres = ja - aref;
         }
         __syncwarp();
         // ---------------- projected Gauss-Seidel with friction-cone projection ----------------
+        // One row per lane; a sweep visits the rows in order, the owner lane updates its force and broadcasts the
+        // change, every lane folds it into its residual with its entry of the (symmetric) row of A.
         const int iters = T.i[TI_PGS_ITERS];
+        const float *Arow = ws + WS_AM + lane;            // A[r][lane] at Arow[33 * r]
+        const bool clamp0 = (kind == 0 || kind == 3);
+        const float fhi = kind == 4 ? bound : 3.0e38f, flo = clamp0 ? 0.f : -fhi;
         for (int it = 0; it < iters; it++) {
-            for (int r = 0; r < R; r++) {
-                float delta = 0.f;
-                if (lane == r) {
-                    float fnew = f - (wres + Rr * f) / dd;
-                    if (kind == 0 || kind == 3) fnew = fmaxf(fnew, 0.f);
-                    else if (kind == 4) fnew = fminf(fmaxf(fnew, -bound), bound);
-                    delta = fnew - f; f = fnew;
+            const float fprev = f;
+            // contacts: normal, tangent 1, tangent 2, then projection of the tangential pair onto the friction disc
+            for (int c2 = 0; c2 < nc; c2++) {
+                const int r0 = 3 * c2;
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const float fnew = fminf(fmaxf(f - (wres + Rr * f) * idd, flo), fhi);   // every lane: candidate for its own row
+                    const float delta = __shfl_sync(B200_FULL_MASK, fnew - f, r0 + d);
+                    if (lane == r0 + d) f = fnew;
+                    wres += Arow[33 * (r0 + d)] * delta;
                 }
-                delta = __shfl_sync(B200_FULL_MASK, delta, r);
-                wres += ws[WS_AM + r * 33 + lane] * delta;
-                if (r < 3 * nc && (r % 3) == 2) {
-                    const float fnn = __shfl_sync(B200_FULL_MASK, f, r - 2);
-                    const float f1 = __shfl_sync(B200_FULL_MASK, f, r - 1);
-                    const float f2 = __shfl_sync(B200_FULL_MASK, f, r);
-                    const float lim = mu * fnn, tt = sqrtf(f1 * f1 + f2 * f2);
-                    if (tt > lim) {
-                        const float sc = tt > 0.f ? lim / tt : 0.f;
-                        const float n1 = f1 * sc, n2 = f2 * sc;
-                        if (lane == r - 1) f = n1;
-                        if (lane == r) f = n2;
-                        wres += ws[WS_AM + (r - 1) * 33 + lane] * (n1 - f1) + ws[WS_AM + r * 33 + lane] * (n2 - f2);
-                    }
+                const float fnn = __shfl_sync(B200_FULL_MASK, f, r0);
+                const float f1 = __shfl_sync(B200_FULL_MASK, f, r0 + 1);
+                const float f2 = __shfl_sync(B200_FULL_MASK, f, r0 + 2);
+                const float lim = mu * fnn, t2 = f1 * f1 + f2 * f2;
+                if (t2 > lim * lim) {                                 // warp-uniform
+                    const float sc = lim * rsqrtf(t2);
+                    const float n1 = f1 * sc, n2 = f2 * sc;
+                    if (lane == r0 + 1) f = n1;
+                    if (lane == r0 + 2) f = n2;
+                    wres += Arow[33 * (r0 + 1)] * (n1 - f1) + Arow[33 * (r0 + 2)] * (n2 - f2);
                 }
             }
+            // joint-limit (f >= 0) and frictionloss (|f| <= bound) rows
+            for (int r = 3 * nc; r < R; r++) {
+                const float fnew = fminf(fmaxf(f - (wres + Rr * f) * idd, flo), fhi);
+                const float delta = __shfl_sync(B200_FULL_MASK, fnew - f, r);
+                if (lane == r) f = fnew;
+                wres += Arow[33 * r] * delta;
+            }
+            // convergence: largest change of any row over the sweep relative to the largest force (warp-uniform exit)
+            float dmax = fabsf(f - fprev), fmx = fabsf(f);
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                dmax = fmaxf(dmax, __shfl_xor_sync(B200_FULL_MASK, dmax, o2));
+                fmx = fmaxf(fmx, __shfl_xor_sync(B200_FULL_MASK, fmx, o2));
+            }
+            if (dmax <= tf[TF_PGS_TOL] * (1.f + fmx)) break;
         }
+        PHASE_SYNC();
         // ---------------- total acceleration, contact forces, integration ----------------
         float accb[6], accl[3] = {al[0], al[1], al[2]};
         {
@@ -740,7 +779,7 @@ __device__ __forceinline__ void stage_model(const ModelDev &M, const TaskDev &T,
 }
 
 template <int C>
-__global__ void B200_LAUNCH_BOUNDS(DYN_WARPS_PER_BLOCK * 32, 1)
+__global__ void B200_LAUNCH_BOUNDS(DYN_WARPS_PER_BLOCK * 32, DYN_MIN_BLOCKS)
 dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, const TerrainDev tr, const float *actions) {
     extern __shared__ float smem[];
     float *ms = smem;
@@ -748,6 +787,16 @@ dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, con
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (env >= T.i[TI_NUM_ENVS]) return;
+    if (env >= T.i[TI_NUM_ENVS]) {
+#ifndef DYN_NO_PHASE_SYNC
+        // ragged last CTA: idle warps still take part in the phase barriers of dynamics_warp (1 + 4 per substep, 1 in the last pass)
+        for (int sub = 0; sub <= T.i[TI_DECIMATION]; sub++) {
+            __syncthreads();
+            if (sub == T.i[TI_DECIMATION]) break;
+            __syncthreads(); __syncthreads(); __syncthreads(); __syncthreads();
+        }
+#endif
+        return;
+    }
     dynamics_warp<C>(T, B, tr, ms, smem + MS_TOTAL + warp * WS_TOTAL, actions, env, lane);
 }

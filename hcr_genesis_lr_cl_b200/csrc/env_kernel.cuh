@@ -67,6 +67,19 @@ __device__ __forceinline__ int cell_of(float p, float border, float hscale) {
 
 __device__ __forceinline__ int wrap_idx(int i, int n) { return i < 0 ? i + n : i; }   // torch negative-index wrap
 
+// dst[0..n) = cleared ? 0 : src[0..n): coalesced, 8 independent 128-byte requests in flight per warp
+__device__ __forceinline__ void shift_copy(float *__restrict__ dst, const float *__restrict__ src, int n, bool cleared, int lane) {
+    int e = lane;
+    for (; e + 7 * 32 < n; e += 8 * 32) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = cleared ? 0.f : __ldcs(src + e + 32 * k);
+#pragma unroll
+        for (int k = 0; k < 8; k++) dst[e + 32 * k] = v[k];
+    }
+    for (; e < n; e += 32) dst[e] = cleared ? 0.f : __ldcs(src + e);
+}
+
 __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const EnvCall &call,
                                    float *es, int env, int lane) {
     const float *tf = T.f;
@@ -487,16 +500,14 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             const bool cleared = (pm & PHASE_RESET) && reset;
             {
                 const int W = ti[TI_FRAME_STACK] * NO, keepw = W - NO;
-                const float *src = B.obs_history[call.parity] + (size_t)env * W + NO;
+                shift_copy(B.obs_history[call.parity ^ 1] + (size_t)env * W, B.obs_history[call.parity] + (size_t)env * W + NO, keepw, cleared, lane);
                 float *dst = B.obs_history[call.parity ^ 1] + (size_t)env * W;
-                for (int e = lane; e < keepw; e += 32) dst[e] = cleared ? 0.f : src[e];
                 for (int e = lane; e < NO; e += 32) dst[keepw + e] = nz[e];
             }
             {
                 const int W = ti[TI_C_FRAME_STACK] * SC, keepw = W - SC;
-                const float *src = B.critic_obs[call.parity] + (size_t)env * W + SC;
+                shift_copy(B.critic_obs[call.parity ^ 1] + (size_t)env * W, B.critic_obs[call.parity] + (size_t)env * W + SC, keepw, cleared, lane);
                 float *dst = B.critic_obs[call.parity ^ 1] + (size_t)env * W;
-                for (int e = lane; e < keepw; e += 32) dst[e] = cleared ? 0.f : src[e];
                 for (int e = lane; e < SC; e += 32) dst[keepw + e] = cr[e];
             }
         }

@@ -161,7 +161,8 @@ class TaskSpec:
     obtain_link_contact_states: bool = False
     contact_state_link_names: List[str] = field(default_factory=lambda: ["thigh", "calf", "foot"])
     # engine knobs (no reference counterpart; DESIGN.md "physics formulation")
-    pgs_iterations: int = 30
+    pgs_iterations: int = 30          # sweep cap of the projected Gauss-Seidel contact solver
+    pgs_tolerance: float = 1e-4       # stop when max|df| over a sweep <= tol * (1 + max|f|)
     seed: int = 1
 
     # ------------------------------------------------------------------ derived

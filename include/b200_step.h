@@ -62,7 +62,7 @@ enum B200TaskF {
     TF_OS_LIN_VEL, TF_OS_ANG_VEL, TF_OS_DOF_POS, TF_OS_DOF_VEL, TF_OS_HEIGHT, TF_HEIGHT_OBS_OFFSET,
     TF_TRACKING_SIGMA, TF_BASE_HEIGHT_TARGET, TF_FOOT_CLEARANCE_TARGET, TF_FOOT_HEIGHT_OFFSET, TF_FOOT_CLEARANCE_SIGMA,
     TF_ABOUT_LANDING, TF_AIR_TIME_THRESHOLD,
-    TF_GRAV, TF_TC, TF_DAMPRATIO, TF_D0, TF_DMAX, TF_WIDTH, TF_MID, TF_POWER, TF_TERRAIN_MU, TF_GEOM_MU,
+    TF_GRAV, TF_TC, TF_DAMPRATIO, TF_D0, TF_DMAX, TF_WIDTH, TF_MID, TF_POWER, TF_TERRAIN_MU, TF_GEOM_MU, TF_PGS_TOL,
     TF_DEFAULT_DOF_POS,                                         /* [B200_MAX_JOINTS] */
     TF_RESET_DOF_NOISE = TF_DEFAULT_DOF_POS + B200_MAX_JOINTS,  /* [B200_MAX_JOINTS] */
     TF_DOF_LIM_LO = TF_RESET_DOF_NOISE + B200_MAX_JOINTS,       /* [B200_MAX_JOINTS] soft limits */

@@ -28,7 +28,7 @@ class OracleEnv:
         self.eo = EnvOracle(spec, num_envs, hs, origins)
         self.model = self.eo.model
         prm = default_params(dt=spec.sim_dt, iters=spec.pgs_iterations, hscale=spec.horizontal_scale, vscale=spec.vertical_scale,
-                             border=spec.border_size if spec.heightfield else 0.0, terrain_mu=spec.static_friction)
+                             border=spec.border_size if spec.heightfield else 0.0, terrain_mu=spec.static_friction, tol=spec.pgs_tolerance)
         self.phys = PhysicsOracle(self.model, prm, hs, precision=precision)
         self.env_offset = env_offset
         st = self.eo.st

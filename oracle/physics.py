@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 P_DT, P_GRAV, P_TC, P_DAMPRATIO, P_D0, P_DMAX, P_WIDTH, P_MID, P_POWER, P_TERRAIN_MU, P_GEOM_MU, P_ITERS, \
-    P_HSCALE, P_VSCALE, P_BORDER = range(15)
+    P_HSCALE, P_VSCALE, P_BORDER, P_TOL = range(16)
 
 
 def build(force: bool = False) -> None:
@@ -24,13 +24,14 @@ def build(force: bool = False) -> None:
             subprocess.check_call(["make", "-C", _HERE, name])
 
 
-def default_params(dt=0.005, iters=30, hscale=0.1, vscale=0.005, border=0.0, terrain_mu=1.0, geom_mu=1.0) -> np.ndarray:
-    p = np.zeros(16, np.float32)
+def default_params(dt=0.005, iters=30, hscale=0.1, vscale=0.005, border=0.0, terrain_mu=1.0, geom_mu=1.0, tol=1e-4) -> np.ndarray:
+    p = np.zeros(20, np.float32)
     p[P_DT], p[P_GRAV] = dt, 9.81
     p[P_TC], p[P_DAMPRATIO] = 2 * dt, 1.0
     p[P_D0], p[P_DMAX], p[P_WIDTH], p[P_MID], p[P_POWER] = 0.9, 0.95, 0.001, 0.5, 2.0
     p[P_TERRAIN_MU], p[P_GEOM_MU], p[P_ITERS] = terrain_mu, geom_mu, iters
     p[P_HSCALE], p[P_VSCALE], p[P_BORDER] = hscale, vscale, border
+    p[P_TOL] = tol
     return p
 
 

@@ -60,7 +60,7 @@ typedef struct {
 
 /* physics parameters, float[16] */
 enum { P_DT, P_GRAV, P_TC, P_DAMPRATIO, P_D0, P_DMAX, P_WIDTH, P_MID, P_POWER,
-       P_TERRAIN_MU, P_GEOM_MU, P_ITERS, P_HSCALE, P_VSCALE, P_BORDER, P_NPARAM };
+       P_TERRAIN_MU, P_GEOM_MU, P_ITERS, P_HSCALE, P_VSCALE, P_BORDER, P_TOL, P_NPARAM };
 
 typedef struct { real x, y, z; } v3;
 static v3 V(real x, real y, real z) { v3 r = {x, y, z}; return r; }
@@ -342,6 +342,7 @@ static void substep_one(const Model *M, const float *prm, const int16_t *hf, int
         }
         int iters = (int)prm[P_ITERS];
         for (int it = 0; it < iters; it++) {
+            real fprev[RMAX]; memcpy(fprev, f, sizeof f);
             for (int r = 0; r < R; r++) {
                 real res = bb[r] + Rr[r] * f[r];
                 for (int s = 0; s < R; s++) res += A[r][s] * f[s];
@@ -354,6 +355,10 @@ static void substep_one(const Model *M, const float *prm, const int16_t *hf, int
                     if (t > lim) { real sc = (t > 0) ? lim / t : 0; f[r - 1] *= sc; f[r] *= sc; }
                 }
             }
+            /* convergence: largest change of any row over this sweep, relative to the largest force */
+            real dmax = 0, fmax = 0;
+            for (int r = 0; r < R; r++) { real d = fabs(f[r] - fprev[r]); if (d > dmax) dmax = d; if (fabs(f[r]) > fmax) fmax = fabs(f[r]); }
+            if (dmax <= prm[P_TOL] * (1 + fmax)) break;
         }
         for (int r = 0; r < R; r++) for (int k = 0; k < nv; k++) acc[k] += Y[r][k] * f[r];
     }

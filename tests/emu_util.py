@@ -93,7 +93,7 @@ class EmuSim:
 def oracle_params(spec, model, hf=None):
     return ophys.default_params(dt=spec.sim_dt, iters=spec.pgs_iterations, hscale=spec.horizontal_scale,
                                 vscale=spec.vertical_scale, border=spec.border_size if spec.heightfield else 0.0,
-                                terrain_mu=spec.static_friction, geom_mu=1.0)
+                                terrain_mu=spec.static_friction, geom_mu=1.0, tol=spec.pgs_tolerance)
 
 
 def oracle_policy_step(spec, model, oracle, st, actions):
