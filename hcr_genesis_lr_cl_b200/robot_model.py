@@ -93,7 +93,9 @@ def load_robot_model(robot: str, dof_names: Sequence[str], armature: float = DEF
         first = dof_names[c * D]
         if first not in by_joint:
             raise ValueError(f"{robot}: unknown joint {first!r}")
-        ch = next(ch for ch in chains if ch[0] == by_joint[first])
+        ch = next((ch for ch in chains if ch[0] == by_joint[first]), None)
+        if ch is None:
+            raise ValueError(f"{robot}: dof_names must list each leg root-to-tip ({first!r} is not a chain root)")
         for k in range(D):
             if bodies[ch[k]]["joint_name"] != dof_names[c * D + k]:
                 raise ValueError(f"{robot}: dof_names must list each leg root-to-tip ({dof_names[c*D+k]!r})")

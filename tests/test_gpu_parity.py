@@ -45,9 +45,12 @@ def test_library_is_the_cuda_path(built_library):
     assert all(hasattr(lib, s) for s in _cabi.EXPORTED_SYMBOLS)
 
 
-def test_env_kernel_matches_reference_golden(golden):
+@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32"])
+def test_env_kernel_matches_reference_golden(name):
     """Injected post-physics states from the reference run -> every output of the fused kernel."""
-    g, s0, spec, terrain = golden
+    g, s0 = load_golden(name)
+    spec = spec_for(g)
+    terrain = load_terrain() if spec.heightfield else None
     N, T_ = g["actions"].shape[1], g["actions"].shape[0]
     env = _env(spec, N, terrain)
     sim = env.simulator

@@ -1,0 +1,75 @@
+"""CPU checks of the CUDA kernel *sources* on the single-warp emulator (tests/warp_emu): the same .cuh files that
+nvcc compiles for sm_100a are compiled by g++ with lock-step coroutine lanes, so kernel logic (and missing
+__syncwarp() hazards) is caught here before GPU time is spent.  This is test infrastructure only: the product
+library is built by nvcc and has no CPU path."""
+import numpy as np
+import pytest
+
+from emu_util import EmuSim, oracle_params, oracle_policy_step
+from golden_util import load_golden, load_terrain, out_at, phys_at, spec_for
+from oracle.physics import PhysicsOracle
+
+PH = dict(base_pos="base_pos", base_quat_wxyz="base_quat_wxyz", base_lin_w="base_lin_w", base_ang_w="base_ang_w",
+          q="dof_pos", qd="dof_vel", torques="torques", link_force="link_contact_forces", feet_pos="feet_pos", feet_vel="feet_vel")
+INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels")
+
+
+@pytest.mark.parametrize("name,steps", [("go2_ts_n32", 5), ("go2_n32", 4)])
+def test_emulated_env_kernel_matches_reference_golden(name, steps):
+    g, s0 = load_golden(name)
+    spec = spec_for(g)
+    hs, origins = load_terrain() if spec.heightfield else (None, None)
+    N = g["actions"].shape[1]
+    sim = EmuSim(spec, N, hs, origins)
+    sim.load_state(s0)
+    B = sim.buf
+    for t in range(steps):
+        # pre-step bookkeeping of the dynamics kernel, then the recorded post-physics state
+        a = np.clip(g["actions"][t], -spec.clip_actions, spec.clip_actions)
+        B["llast_actions"][:] = B["last_actions"]; B["last_actions"][:] = B["actions"]; B["actions"][:] = a
+        B["last_dof_vel"][:] = B["dof_vel"]; B["last_feet_vel"][:] = B["feet_vel"]
+        for k, b in PH.items():
+            B[b][...] = phys_at(g, t)[k].reshape(B[b].shape)
+        B["stats"][:] = 0
+        sim.env_post_step()
+        ref = out_at(g, t)
+        mine = dict(B, actions_buf=B["actions"], end_q=B["dof_pos"], end_qd=B["dof_vel"])
+        for k, r in ref.items():
+            if k not in mine or k == "end_state":
+                continue
+            m = np.asarray(mine[k]).reshape(r.shape)
+            if k in INTS:
+                assert np.array_equal(m.astype(np.int64), r.astype(np.int64)), f"step {t}: {k}"
+            else:
+                assert np.allclose(m, r, rtol=1e-4, atol=1e-5), f"step {t}: {k} max err {np.abs(m - r).max():.3e}"
+        if f"hist{t}/obs_history" in g:
+            assert np.allclose(sim.obs_history, g[f"hist{t}/obs_history"], rtol=1e-4, atol=1e-5)
+            assert np.allclose(sim.critic_obs, g[f"hist{t}/critic_obs_buf"], rtol=1e-4, atol=1e-5)
+        n = len(spec.episode_sum_names())
+        assert B["stats"][n] == ref["reset_buf"].sum()            # reset counter of the per-step reductions
+
+
+def test_emulated_dynamics_kernel_matches_oracle():
+    g, s0 = load_golden("go2_ts_n32")
+    spec = spec_for(g)
+    hs, origins = load_terrain()
+    N = 6
+    sub = {k: (v[:N] if getattr(v, "ndim", 0) > 0 and v.shape[0] == 32 else v) for k, v in s0.items()}
+    sim = EmuSim(spec, N, hs, origins)
+    sim.load_state(sub)
+    before = {k: v.copy() for k, v in sim.buf.items()}
+    a = g["actions"][0][:N]
+    sim.dynamics_step(a)
+    orc = PhysicsOracle(sim.model, oracle_params(spec, sim.model), hs, precision="f32")
+    ref = oracle_policy_step(spec, sim.model, orc, before, a)
+    assert ref["ncontact"].max() >= 3
+    for k, name in PH.items():
+        r = np.asarray(ref[k], np.float64)
+        err = np.abs(sim.buf[name].reshape(r.shape) - r).max()
+        tol = (2e-3 if k == "link_force" else 1e-4) * max(1.0, np.abs(r).max())
+        assert err < tol, f"{k}: {err:.3e} >= {tol:.1e}"
+    # pre-step bookkeeping (legged_robot.py:230-252, genesis_simulator.py:21-24)
+    assert np.array_equal(sim.buf["actions"], np.clip(a, -100, 100))
+    assert np.array_equal(sim.buf["last_actions"], before["actions"])
+    assert np.array_equal(sim.buf["llast_actions"], before["last_actions"])
+    assert np.array_equal(sim.buf["last_dof_vel"], before["dof_vel"])
