@@ -30,6 +30,10 @@
 #define ES_CRIT 96                 // single critic frame [<=256]
 #define ES_PRIV 352                // privileged obs [<=128]
 #define ES_TOTAL 480
+// CTA-level staging of the two history stacks (TMA bulk copies): the rows of a CTA's ENV_WARPS_PER_BLOCK consecutive
+// envs form one contiguous, 16-byte aligned slab in HBM even though a single 885-float critic row is not.
+#define ENV_MAX_HIST_ROW 960       // >= frame_stack * num_obs floats (900)
+#define ENV_MAX_CRIT_ROW 960       // >= c_frame_stack * single_critic floats (885)
 
 struct EnvCall {
     uint32_t step;       // LeggedRobot.common_step_counter after its increment
@@ -39,7 +43,7 @@ struct EnvCall {
     int force_reset;     // b200_reset_all: run only the reset phase, for every env
 };
 
-__host__ __device__ inline int env_smem_bytes(int warps) { return warps * ES_TOTAL * 4; }
+__host__ __device__ inline int env_smem_bytes(int warps) { return 16 + warps * (ES_TOTAL + ENV_MAX_HIST_ROW + ENV_MAX_CRIT_ROW) * 4; }
 
 // quat_rotate_inverse (math_utils.py:63-76), q = xyzw
 __device__ __forceinline__ f3 rot_inv(float qx, float qy, float qz, float qw, f3 v) {
@@ -80,8 +84,25 @@ __device__ __forceinline__ void shift_copy(float *__restrict__ dst, const float 
     for (; e < n; e += 32) dst[e] = cleared ? 0.f : __ldcs(src + e);
 }
 
+// in-place shift of a staged row by `frame` floats (drop the oldest frame), then append `newf`; writes trail reads
+__device__ __forceinline__ void smem_shift_append(float *row, int W, int frame, const float *newf, bool cleared, int lane) {
+    const int keepw = W - frame;
+    for (int i0 = 0; i0 < keepw; i0 += 256) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int e = i0 + 32 * k + lane; v[k] = (e < keepw && !cleared) ? row[e + frame] : 0.f; }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int e = i0 + 32 * k + lane; if (e < keepw) row[e] = v[k]; }
+        __syncwarp();
+    }
+    for (int e = lane; e < frame; e += 32) row[keepw + e] = newf[e];
+}
+
+// `hrow` / `crow`: this env's rows of the CTA's staged history slabs (nullptr -> direct global copies), `bar`: the
+// mbarrier the TMA loads complete on.
 __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const EnvCall &call,
-                                   float *es, int env, int lane) {
+                                   float *es, int env, int lane, float *hrow, float *crow, uint64_t *bar) {
     const float *tf = T.f;
     const int *ti = T.i;
     const int A = ti[TI_A], F = ti[TI_F], L = ti[TI_L], P = ti[TI_PX] * ti[TI_PY];
@@ -498,27 +519,61 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             for (int e = lane; e < NP; e += 32) B.privileged_obs_buf[env * NP + e] = fminf(fmaxf(pv[e], -clipo), clipo);
             // history stacks: shift one frame out, append the new one (legged_robot_ts.py:29-47); cleared on reset (:120-125)
             const bool cleared = (pm & PHASE_RESET) && reset;
-            {
-                const int W = ti[TI_FRAME_STACK] * NO, keepw = W - NO;
-                shift_copy(B.obs_history[call.parity ^ 1] + (size_t)env * W, B.obs_history[call.parity] + (size_t)env * W + NO, keepw, cleared, lane);
-                float *dst = B.obs_history[call.parity ^ 1] + (size_t)env * W;
-                for (int e = lane; e < NO; e += 32) dst[keepw + e] = nz[e];
-            }
-            {
-                const int W = ti[TI_C_FRAME_STACK] * SC, keepw = W - SC;
-                shift_copy(B.critic_obs[call.parity ^ 1] + (size_t)env * W, B.critic_obs[call.parity] + (size_t)env * W + SC, keepw, cleared, lane);
-                float *dst = B.critic_obs[call.parity ^ 1] + (size_t)env * W;
-                for (int e = lane; e < SC; e += 32) dst[keepw + e] = cr[e];
+            if (hrow != nullptr) {
+                mbar_wait(bar, 0);                          // the CTA's TMA loads of both slabs have landed
+                smem_shift_append(hrow, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, lane);
+                smem_shift_append(crow, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, lane);
+            } else {
+                {
+                    const int W = ti[TI_FRAME_STACK] * NO, keepw = W - NO;
+                    shift_copy(B.obs_history[call.parity ^ 1] + (size_t)env * W, B.obs_history[call.parity] + (size_t)env * W + NO, keepw, cleared, lane);
+                    float *dst = B.obs_history[call.parity ^ 1] + (size_t)env * W;
+                    for (int e = lane; e < NO; e += 32) dst[keepw + e] = nz[e];
+                }
+                {
+                    const int W = ti[TI_C_FRAME_STACK] * SC, keepw = W - SC;
+                    shift_copy(B.critic_obs[call.parity ^ 1] + (size_t)env * W, B.critic_obs[call.parity] + (size_t)env * W + SC, keepw, cleared, lane);
+                    float *dst = B.critic_obs[call.parity ^ 1] + (size_t)env * W;
+                    for (int e = lane; e < SC; e += 32) dst[keepw + e] = cr[e];
+                }
             }
         }
     }
 }
 
-__global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, 4)
+__global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, 5)
 env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call) {
     extern __shared__ float smem[];
+    const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (env >= T.i[TI_NUM_ENVS]) return;
-    env_post_step_warp(T, B, tr, call, smem + warp * ES_TOTAL, env, lane);
+    const int env0 = blockIdx.x * nwarps, env = env0 + warp;
+    const int N = T.i[TI_NUM_ENVS];
+    uint64_t *bar = (uint64_t *)smem;
+    float *hslab = smem + 4, *cslab = hslab + nwarps * ENV_MAX_HIST_ROW, *es = cslab + nwarps * ENV_MAX_CRIT_ROW;
+    const int HW = T.i[TI_FRAME_STACK] * T.i[TI_NUM_OBS], CW = T.i[TI_C_FRAME_STACK] * T.i[TI_SINGLE_CRITIC];
+    const uint32_t hbytes = (uint32_t)(nwarps * HW * 4), cbytes = (uint32_t)(nwarps * CW * 4);
+    const bool observe = !call.force_reset && (call.phase_mask & PHASE_OBSERVE);
+    // CTA-uniform: full CTA, history task, slabs fit and are 16-byte multiples -> stage the history through shared memory with TMA
+    const bool staged = observe && T.i[TI_OBS_KIND] == 1 && env0 + nwarps <= N && HW <= ENV_MAX_HIST_ROW && CW <= ENV_MAX_CRIT_ROW &&
+                        B200_TMA_SIZE_OK(hbytes) && B200_TMA_SIZE_OK(cbytes);
+    if (staged) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, hbytes + cbytes);
+            tma_load_1d(hslab, B.obs_history[call.parity] + (size_t)env0 * HW, hbytes, bar);
+            tma_load_1d(cslab, B.critic_obs[call.parity] + (size_t)env0 * CW, cbytes, bar);
+        }
+        __syncthreads();                                   // barrier initialised before anyone waits on it
+        env_post_step_warp(T, B, tr, call, es + warp * ES_TOTAL, env, lane, hslab + warp * HW, cslab + warp * CW, bar);
+        fence_proxy_async();                               // generic-proxy smem writes -> visible to the bulk store
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tma_store_1d(B.obs_history[call.parity ^ 1] + (size_t)env0 * HW, hslab, hbytes);
+            tma_store_1d(B.critic_obs[call.parity ^ 1] + (size_t)env0 * CW, cslab, cbytes);
+            tma_store_commit_wait();
+        }
+        return;
+    }
+    if (env >= N) return;
+    env_post_step_warp(T, B, tr, call, es + warp * ES_TOTAL, env, lane, nullptr, nullptr, bar);
 }
