@@ -50,7 +50,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { (void)bar; (void)count; }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { (void)bar; (void)bytes; }
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) { (void)bar; memcpy(dst_smem, src_gmem, bytes); }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) { (void)bar; (void)phase; }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) { (void)bar; (void)phase; emu_sync(); }   // all lanes' copies are issued before the wait
 __device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) { memcpy(dst_gmem, src_smem, bytes); }
 __device__ __forceinline__ void tma_store_commit_wait() {}
 __device__ __forceinline__ void fence_proxy_async() {}

@@ -27,13 +27,18 @@
 #define ENV_WARPS_PER_BLOCK 4
 #define ES_OBS 0                   // clean obs [48]
 #define ES_NOISY 48                // noisy obs [48]
-#define ES_CRIT 96                 // single critic frame [<=256]
-#define ES_PRIV 352                // privileged obs [<=128]
-#define ES_TOTAL 480
+#define ES_CRIT 96                 // single critic frame [<=192]
+#define ES_PRIV 288                // privileged obs [<=112]
+#define ES_MH 400                  // measured heights of this env [<=96]   (outputs that later phases re-read:
+#define ES_LCS 496                 // link contact states [<=32]             kept on chip instead of a global round trip)
+#define ES_HAF 528                 // height around feet [4*9]
+#define ES_NV 564                  // terrain normals around feet [4*3]
+#define ES_TOTAL 576
+#define ENV_IN_WORDS 288           // staged per-env input rows (all small state tensors), words per env
 // CTA-level staging of the two history stacks (TMA bulk copies): the rows of a CTA's ENV_WARPS_PER_BLOCK consecutive
 // envs form one contiguous, 16-byte aligned slab in HBM even though a single 885-float critic row is not.
-#define ENV_MAX_HIST_ROW 960       // >= frame_stack * num_obs floats (900)
-#define ENV_MAX_CRIT_ROW 960       // >= c_frame_stack * single_critic floats (885)
+#define ENV_MAX_HIST_ROW 912       // >= frame_stack * num_obs floats (900)
+#define ENV_MAX_CRIT_ROW 896       // >= c_frame_stack * single_critic floats (885)
 
 struct EnvCall {
     uint32_t step;       // LeggedRobot.common_step_counter after its increment
@@ -43,7 +48,7 @@ struct EnvCall {
     int force_reset;     // b200_reset_all: run only the reset phase, for every env
 };
 
-__host__ __device__ inline int env_smem_bytes(int warps) { return 16 + warps * (ES_TOTAL + ENV_MAX_HIST_ROW + ENV_MAX_CRIT_ROW) * 4; }
+__host__ __device__ inline int env_smem_bytes(int warps) { return 16 + warps * (ES_TOTAL + ENV_MAX_HIST_ROW + ENV_MAX_CRIT_ROW + ENV_IN_WORDS) * 4; }
 
 // quat_rotate_inverse (math_utils.py:63-76), q = xyzw
 __device__ __forceinline__ f3 rot_inv(float qx, float qy, float qz, float qw, f3 v) {
@@ -101,7 +106,10 @@ __device__ __forceinline__ void smem_shift_append(float *row, int W, int frame, 
 
 // `hrow` / `crow`: this env's rows of the CTA's staged history slabs (nullptr -> direct global copies), `bar`: the
 // mbarrier the TMA loads complete on.
-__device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const EnvCall &call,
+// `R` is the view all per-env *inputs* are read through: B itself, or (staged CTAs) a copy whose pointers are biased so
+// that R.x[env * k + i] lands in the CTA's shared-memory slab that TMA filled -- one exposed DRAM latency per CTA
+// instead of one per dependent load.  All stores go to B (global memory).
+__device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const B200Buffers &R, const TerrainDev &tr, const EnvCall &call,
                                    float *es, int env, int lane, float *hrow, float *crow, uint64_t *bar) {
     const float *tf = T.f;
     const int *ti = T.i;
@@ -110,32 +118,33 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     const int pm = call.force_reset ? PHASE_RESET : call.phase_mask;
     EnvRng rng; rng.k0 = (uint32_t)ti[TI_SEED_LO]; rng.k1 = (uint32_t)ti[TI_SEED_HI]; rng.env = (uint32_t)(env + ti[TI_ENV_OFFSET]); rng.step = call.step;
     const float dt = tf[TF_POLICY_DT];
+    if (hrow != nullptr) mbar_wait(bar, 0);                     // staged CTA: every input slab (state + history) has landed
 
     // ------------------------------------------------------------------ per-env scalars (replicated in all lanes)
-    f3 bp = mk3(B.base_pos[env * 3], B.base_pos[env * 3 + 1], B.base_pos[env * 3 + 2]);
-    const float Qw = B.base_quat_wxyz[env * 4], Qx = B.base_quat_wxyz[env * 4 + 1], Qy = B.base_quat_wxyz[env * 4 + 2], Qz = B.base_quat_wxyz[env * 4 + 3];
-    f3 vw = mk3(B.base_lin_w[env * 3], B.base_lin_w[env * 3 + 1], B.base_lin_w[env * 3 + 2]);
-    f3 ww = mk3(B.base_ang_w[env * 3], B.base_ang_w[env * 3 + 1], B.base_ang_w[env * 3 + 2]);
-    f3 origin = mk3(B.env_origins[env * 3], B.env_origins[env * 3 + 1], B.env_origins[env * 3 + 2]);
-    float cmd0 = B.commands[env * 4], cmd1 = B.commands[env * 4 + 1], cmd2 = B.commands[env * 4 + 2], cmd3 = B.commands[env * 4 + 3];
-    int ep_len = B.episode_length[env];
-    int fail_cnt = B.fail_buf[env];
+    f3 bp = mk3(R.base_pos[env * 3], R.base_pos[env * 3 + 1], R.base_pos[env * 3 + 2]);
+    const float Qw = R.base_quat_wxyz[env * 4], Qx = R.base_quat_wxyz[env * 4 + 1], Qy = R.base_quat_wxyz[env * 4 + 2], Qz = R.base_quat_wxyz[env * 4 + 3];
+    f3 vw = mk3(R.base_lin_w[env * 3], R.base_lin_w[env * 3 + 1], R.base_lin_w[env * 3 + 2]);
+    f3 ww = mk3(R.base_ang_w[env * 3], R.base_ang_w[env * 3 + 1], R.base_ang_w[env * 3 + 2]);
+    f3 origin = mk3(R.env_origins[env * 3], R.env_origins[env * 3 + 1], R.env_origins[env * 3 + 2]);
+    float cmd0 = R.commands[env * 4], cmd1 = R.commands[env * 4 + 1], cmd2 = R.commands[env * 4 + 2], cmd3 = R.commands[env * 4 + 3];
+    int ep_len = R.episode_length[env];
+    int fail_cnt = R.fail_buf[env];
     // read before any lane may overwrite them below (lanes are not in lock-step between collectives)
-    const int level0 = ti[TI_TERRAIN_CURRICULUM] ? (int)B.terrain_levels[env] : 0;
-    const int ttype = ti[TI_TERRAIN_CURRICULUM] ? (int)B.terrain_types[env] : 0;
-    f3 push_vel = mk3(B.rand_push_vels[env * 3], B.rand_push_vels[env * 3 + 1], 0.f);
+    const int level0 = ti[TI_TERRAIN_CURRICULUM] ? (int)R.terrain_levels[env] : 0;
+    const int ttype = ti[TI_TERRAIN_CURRICULUM] ? (int)R.terrain_types[env] : 0;
+    f3 push_vel = mk3(R.rand_push_vels[env * 3], R.rand_push_vels[env * 3 + 1], 0.f);
     f3 lin_b, ang_b, grav;           // body-frame velocities, projected gravity
     // ------------------------------------------------------------------ per-lane values
     const bool jl = lane < A, fl = lane < F;
-    float qj = jl ? B.dof_pos[env * A + lane] : 0.f, qdj = jl ? B.dof_vel[env * A + lane] : 0.f;
-    float actj = jl ? B.actions[env * A + lane] : 0.f;
+    float qj = jl ? R.dof_pos[env * A + lane] : 0.f, qdj = jl ? R.dof_vel[env * A + lane] : 0.f;
+    float actj = jl ? R.actions[env * A + lane] : 0.f;
     const float q0j = jl ? tf[TF_DEFAULT_DOF_POS + lane] : 0.f;
     f3 fpos = mk3(0.f, 0.f, 0.f), fvel = mk3(0.f, 0.f, 0.f);
     if (fl) {
-        const float *a = B.feet_pos + (env * F + lane) * 3, *b = B.feet_vel + (env * F + lane) * 3;
+        const float *a = R.feet_pos + (env * F + lane) * 3, *b = R.feet_vel + (env * F + lane) * 3;
         fpos = mk3(a[0], a[1], a[2]); fvel = mk3(b[0], b[1], b[2]);
     }
-    float ffz = fl ? B.link_contact_forces[(env * L + ti[TI_FEET_LINKS + lane]) * 3 + 2] : 0.f;   // foot contact force z
+    float ffz = fl ? R.link_contact_forces[(env * L + ti[TI_FEET_LINKS + lane]) * 3 + 2] : 0.f;   // foot contact force z
     float hmean = 0.f;               // mean of the 9 terrain heights around this lane's foot
 
     if (pm & PHASE_CALLBACK) ep_len += 1;                       // legged_robot.py:60
@@ -146,7 +155,10 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         if (oob) {                                               // genesis_simulator.py:612-628
             const f3 nb = mk3(__fadd_rn(tf[TF_INIT_POS], origin.x), __fadd_rn(tf[TF_INIT_POS + 1], origin.y), __fadd_rn(tf[TF_INIT_POS + 2], origin.z));
             fpos = fpos + (nb - bp);
-            if (fl) { float *a = B.feet_pos + (env * F + lane) * 3; a[0] = fpos.x; a[1] = fpos.y; a[2] = fpos.z; }
+            if (fl) {
+                float *a = B.feet_pos + (env * F + lane) * 3, *b = const_cast<float *>(R.feet_pos) + (env * F + lane) * 3;
+                a[0] = fpos.x; a[1] = fpos.y; a[2] = fpos.z; b[0] = fpos.x; b[1] = fpos.y; b[2] = fpos.z;
+            }
             bp = nb;
             if (lane < 3) B.base_pos[env * 3 + lane] = comp3(bp, lane);
         }
@@ -168,8 +180,9 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             B.base_euler[env * 3 + 2] = atan2f(siny, cosy);
         }
         if (ti[TI_CONTACT_STATES] && lane < ti[TI_N_CS]) {
-            const float *f = B.link_contact_forces + (env * L + ti[TI_CS_LINKS + lane]) * 3;
-            B.link_contact_states[env * ti[TI_N_CS] + lane] = norm3_rn(f[0], f[1], f[2]) > 1.0f ? 1.f : 0.f;
+            const float *f = R.link_contact_forces + (env * L + ti[TI_CS_LINKS + lane]) * 3;
+            const float cs = norm3_rn(f[0], f[1], f[2]) > 1.0f ? 1.f : 0.f;
+            B.link_contact_states[env * ti[TI_N_CS] + lane] = cs; es[ES_LCS + lane] = cs;
         }
         if (ti[TI_MEASURE_HEIGHTS]) {
             // quat_apply_yaw (math_utils.py:42-47) of the scan grid, then min of 3 int16 samples
@@ -185,7 +198,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 cx = max(0, min(cx, tr.rows - 2)); cy = max(0, min(cy, tr.cols - 2));
                 const int16_t *hp = tr.hf + (size_t)cx * tr.cols + cy;
                 const int16_t h = min(min(__ldg(hp), __ldg(hp + tr.cols)), __ldg(hp + 1));
-                B.measured_heights[env * P + pt] = __fmul_rn((float)h, tf[TF_VSCALE]);
+                const float mh = __fmul_rn((float)h, tf[TF_VSCALE]);
+                B.measured_heights[env * P + pt] = mh; es[ES_MH + pt] = mh;
                 if (B.height_cells) { B.height_cells[(env * P + pt) * 2] = cx; B.height_cells[(env * P + pt) * 2 + 1] = cy; }
             }
             if (ti[TI_FEET_INFO]) {
@@ -199,7 +213,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                     for (int k = 0; k < 9; k++) {
                         hv[k] = __ldg(tr.hf + (size_t)wrap_idx(cx + DX[k], tr.rows) * tr.cols + wrap_idx(cy + DY[k], tr.cols));
                         const float hk = __fmul_rn((float)hv[k], tf[TF_VSCALE]);
-                        B.height_around_feet[(env * F + lane) * 9 + k] = hk;
+                        B.height_around_feet[(env * F + lane) * 9 + k] = hk; es[ES_HAF + lane * 9 + k] = hk;
                         s = __fadd_rn(s, hk);
                     }
                     hmean = __fdiv_rn(s, 9.0f);
@@ -208,6 +222,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                     const float nn = norm3_rn(dx, dy, -1.0f);
                     float *nv = B.normal_vector_around_feet + env * 3 * F + lane * 3;
                     nv[0] = __fdiv_rn(dx, nn); nv[1] = __fdiv_rn(dy, nn); nv[2] = __fdiv_rn(-1.0f, nn);
+                    es[ES_NV + lane * 3] = nv[0]; es[ES_NV + lane * 3 + 1] = nv[1]; es[ES_NV + lane * 3 + 2] = nv[2];
                 }
             }
         }
@@ -217,9 +232,12 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         grav = mk3(B.projected_gravity[env * 3], B.projected_gravity[env * 3 + 1], B.projected_gravity[env * 3 + 2]);
         if (fl && ti[TI_FEET_INFO]) {
             float s = 0.f;
-            for (int k = 0; k < 9; k++) s = __fadd_rn(s, B.height_around_feet[(env * F + lane) * 9 + k]);
+            for (int k = 0; k < 9; k++) { const float hk = B.height_around_feet[(env * F + lane) * 9 + k]; es[ES_HAF + lane * 9 + k] = hk; s = __fadd_rn(s, hk); }
             hmean = __fdiv_rn(s, 9.0f);
+            for (int k = 0; k < 3; k++) es[ES_NV + lane * 3 + k] = B.normal_vector_around_feet[env * 3 * F + lane * 3 + k];
         }
+        if (ti[TI_MEASURE_HEIGHTS]) for (int pt = lane; pt < P; pt += 32) es[ES_MH + pt] = B.measured_heights[env * P + pt];
+        if (ti[TI_CONTACT_STATES] && lane < ti[TI_N_CS]) es[ES_LCS + lane] = B.link_contact_states[env * ti[TI_N_CS] + lane];
     }
     __syncwarp();
 
@@ -258,7 +276,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     if (pm & PHASE_TERMINATION) {
         bool hit = false;
         if (lane < ti[TI_N_TERM]) {
-            const float *f = B.link_contact_forces + (env * L + ti[TI_TERM_LINKS + lane]) * 3;
+            const float *f = R.link_contact_forces + (env * L + ti[TI_TERM_LINKS + lane]) * 3;
             hit = norm3_rn(f[0], f[1], f[2]) > 10.0f;
         }
         const bool fail = (__ballot_sync(B200_FULL_MASK, hit) != 0u) || (grav.z > tf[TF_MAX_PROJ_GRAV]);
@@ -269,11 +287,11 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     if (call.force_reset) reset = true;
 
     // ================================================================== compute_reward
-    float my_sum = (lane < n_sums) ? B.episode_sums[env * n_sums + lane] : 0.f;
-    float fat = fl ? B.feet_air_time[env * F + lane] : 0.f;
+    float my_sum = (lane < n_sums) ? R.episode_sums[env * n_sums + lane] : 0.f;
+    float fat = fl ? R.feet_air_time[env * F + lane] : 0.f;
     if (pm & PHASE_REWARD) {
-        const float lastj = jl ? B.last_actions[env * A + lane] : 0.f, llastj = jl ? B.llast_actions[env * A + lane] : 0.f;
-        const float tauj = jl ? B.torques[env * A + lane] : 0.f, lqdj = jl ? B.last_dof_vel[env * A + lane] : 0.f;
+        const float lastj = jl ? R.last_actions[env * A + lane] : 0.f, llastj = jl ? R.llast_actions[env * A + lane] : 0.f;
+        const float tauj = jl ? R.torques[env * A + lane] : 0.f, lqdj = jl ? R.last_dof_vel[env * A + lane] : 0.f;
         const float small_cmd = norm3_rn(cmd0, cmd1, cmd2) < 0.1f ? 1.f : 0.f;
         const float dqj = qj - q0j;
         float rew = 0.f;
@@ -287,12 +305,12 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             case RW_ANG_VEL_XY: r = ang_b.x * ang_b.x + ang_b.y * ang_b.y; break;
             case RW_BASE_HEIGHT: {
                 float s = 0.f;
-                for (int pt = lane; pt < P; pt += 32) s += bp.z - (ti[TI_MEASURE_HEIGHTS] ? B.measured_heights[env * P + pt] : 0.f);
+                for (int pt = lane; pt < P; pt += 32) s += bp.z - (ti[TI_MEASURE_HEIGHTS] ? es[ES_MH + pt] : 0.f);
                 const float m = warp_sum(s) / (float)P - tf[TF_BASE_HEIGHT_TARGET];
                 r = m * m; break; }
             case RW_COLLISION: {
                 float hitf = 0.f;
-                if (lane < ti[TI_N_PEN]) { const float *f = B.link_contact_forces + (env * L + ti[TI_PEN_LINKS + lane]) * 3; hitf = norm3_rn(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f; }
+                if (lane < ti[TI_N_PEN]) { const float *f = R.link_contact_forces + (env * L + ti[TI_PEN_LINKS + lane]) * 3; hitf = norm3_rn(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f; }
                 r = warp_sum(hitf); break; }
             case RW_DOF_ACC: { const float d = (lqdj - qdj) / dt; r = warp_sum(d * d); break; }
             case RW_DOF_CLOSE_TO_DEFAULT: r = warp_sum(dqj * dqj); break;
@@ -306,7 +324,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             case RW_DOF_VEL_STAND_STILL: r = warp_sum(fabsf(qdj)) * small_cmd; break;
             case RW_FEET_AIR_TIME: {                              // stateful; go2_ts.py:133-145
                 const bool contact = ffz > 1.0f;
-                const bool lastc = fl ? (B.last_contacts[env * F + lane] != 0) : false;
+                const bool lastc = fl ? (R.last_contacts[env * F + lane] != 0) : false;
                 const bool filt = contact || lastc;
                 if (fl) B.last_contacts[env * F + lane] = contact ? 1 : 0;
                 const bool first = (fat > 0.f) && filt;
@@ -320,7 +338,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 r = (cnt == (float)F ? 1.f : 0.f) * small_cmd; break; }
             case RW_FOOT_ACC: {
                 float s = 0.f;
-                if (fl) { const float *lv = B.last_feet_vel + (env * F + lane) * 3;
+                if (fl) { const float *lv = R.last_feet_vel + (env * F + lane) * 3;
                     const float ax = (fvel.x - lv[0]) / dt, ay = (fvel.y - lv[1]) / dt, az = (fvel.z - lv[2]) / dt; s = ax * ax + ay * ay + az * az; }
                 r = warp_sum(s); break; }
             case RW_FOOT_CLEARANCE: {                             // legged_robot.py:575-588; go2_ts.py:147-161
@@ -425,19 +443,22 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             }
         }
         // domain randomisation (genesis_simulator.py:62-82,665-739)
+        // (stored to global memory and to the view the observation phase reads them back through)
+#define DR_PUT(field, idx, val) do { const float v_ = (val); B.field[idx] = v_; const_cast<float *>(R.field)[idx] = v_; } while (0)
         if (lane == 0) {
-            if (ti[TI_RAND_FRICTION]) B.friction[env] = rand_range(tf[TF_FRICTION_LO], tf[TF_FRICTION_SPAN], rng.u(SITE_FRICTION, 0));
-            if (ti[TI_RAND_MASS]) B.added_mass[env] = rand_range(tf[TF_MASS_LO], tf[TF_MASS_SPAN], rng.u(SITE_MASS, 0));
+            if (ti[TI_RAND_FRICTION]) DR_PUT(friction, env, rand_range(tf[TF_FRICTION_LO], tf[TF_FRICTION_SPAN], rng.u(SITE_FRICTION, 0)));
+            if (ti[TI_RAND_MASS]) DR_PUT(added_mass, env, rand_range(tf[TF_MASS_LO], tf[TF_MASS_SPAN], rng.u(SITE_MASS, 0)));
             if (ti[TI_RAND_ARMATURE]) B.joint_armature[env] = rand_range(tf[TF_ARM_LO], tf[TF_ARM_SPAN], rng.u(SITE_ARMATURE, 0));
             if (ti[TI_RAND_JFRICTION]) B.joint_friction[env] = rand_range(tf[TF_JFR_LO], tf[TF_JFR_SPAN], rng.u(SITE_JFRICTION, 0));
             if (ti[TI_RAND_JDAMPING]) B.joint_damping[env] = rand_range(tf[TF_JDA_LO], tf[TF_JDA_SPAN], rng.u(SITE_JDAMPING, 0));
         }
         if (ti[TI_RAND_COM] && lane < 3)
-            B.com_bias[env * 3 + lane] = rand_range(tf[TF_COMX_LO + 2 * lane], tf[TF_COMX_SPAN + 2 * lane], rng.u(SITE_COM, lane));
+            DR_PUT(com_bias, env * 3 + lane, rand_range(tf[TF_COMX_LO + 2 * lane], tf[TF_COMX_SPAN + 2 * lane], rng.u(SITE_COM, lane)));
         if (ti[TI_RAND_PD] && jl) {
-            B.kp_scale[env * A + lane] = rand_range(tf[TF_KPS_LO], tf[TF_KPS_SPAN], rng.u(SITE_KP, lane));
-            B.kd_scale[env * A + lane] = rand_range(tf[TF_KDS_LO], tf[TF_KDS_SPAN], rng.u(SITE_KD, lane));
+            DR_PUT(kp_scale, env * A + lane, rand_range(tf[TF_KPS_LO], tf[TF_KPS_SPAN], rng.u(SITE_KP, lane)));
+            DR_PUT(kd_scale, env * A + lane, rand_range(tf[TF_KDS_LO], tf[TF_KDS_SPAN], rng.u(SITE_KD, lane)));
         }
+#undef DR_PUT
         if (lane < 3 * F) B.last_feet_vel[env * 3 * F + lane] = 0.f;
         fat = 0.f;
         ep_len = 0; fail_cnt = 0;
@@ -488,12 +509,12 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             // domain_randomization_info (go2_ts.py:16-28)
             for (int e = lane; e < DRN; e += 32) {
                 float v;
-                if (e == 0) v = __fsub_rn(B.friction[env], tf[TF_FRICTION_OFFSET]);
-                else if (e == 1) v = B.added_mass[env];
-                else if (e < 5) v = B.com_bias[env * 3 + e - 2];
+                if (e == 0) v = __fsub_rn(R.friction[env], tf[TF_FRICTION_OFFSET]);
+                else if (e == 1) v = R.added_mass[env];
+                else if (e < 5) v = R.com_bias[env * 3 + e - 2];
                 else if (e < 7) v = e == 5 ? push_vel.x : push_vel.y;
-                else if (e < 7 + A) v = __fsub_rn(B.kp_scale[env * A + e - 7], tf[TF_KPS_OFFSET]);
-                else v = __fsub_rn(B.kd_scale[env * A + e - 7 - A], tf[TF_KDS_OFFSET]);
+                else if (e < 7 + A) v = __fsub_rn(R.kp_scale[env * A + e - 7], tf[TF_KPS_OFFSET]);
+                else v = __fsub_rn(R.kd_scale[env * A + e - 7 - A], tf[TF_KDS_OFFSET]);
                 cr[NO + e] = v; pv[e] = v;
             }
             if (lane < 3) {
@@ -501,26 +522,25 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 cr[NO + DRN + lane] = v; pv[DRN + 12 * F + lane] = v;
             }
             for (int e = lane; e < NCS; e += 32) {
-                const float v = B.link_contact_states[env * NCS + e];
+                const float v = es[ES_LCS + e];
                 cr[NO + DRN + 3 + e] = v; pv[DRN + 12 * F + 3 + e] = v;
             }
             if (ti[TI_MEASURE_HEIGHTS]) {
                 for (int pt = lane; pt < P; pt += 32) {
-                    const float d = __fsub_rn(__fsub_rn(bp.z, tf[TF_HEIGHT_OBS_OFFSET]), B.measured_heights[env * P + pt]);
+                    const float d = __fsub_rn(__fsub_rn(bp.z, tf[TF_HEIGHT_OBS_OFFSET]), es[ES_MH + pt]);
                     cr[NO + DRN + 3 + NCS + pt] = __fmul_rn(fminf(fmaxf(d, -1.0f), 1.0f), tf[TF_OS_HEIGHT]);
                 }
             }
             for (int e = lane; e < 9 * F; e += 32) {
-                const float fz = B.feet_pos[(env * F + e / 9) * 3 + 2];
-                pv[DRN + e] = fminf(fmaxf(__fsub_rn(fz, B.height_around_feet[env * F * 9 + e]), -1.0f), 1.0f);
+                const float fz = R.feet_pos[(env * F + e / 9) * 3 + 2];
+                pv[DRN + e] = fminf(fmaxf(__fsub_rn(fz, es[ES_HAF + e]), -1.0f), 1.0f);
             }
-            for (int e = lane; e < 3 * F; e += 32) pv[DRN + 9 * F + e] = B.normal_vector_around_feet[env * 3 * F + e];
+            for (int e = lane; e < 3 * F; e += 32) pv[DRN + 9 * F + e] = es[ES_NV + e];
             __syncwarp();
             for (int e = lane; e < NP; e += 32) B.privileged_obs_buf[env * NP + e] = fminf(fmaxf(pv[e], -clipo), clipo);
             // history stacks: shift one frame out, append the new one (legged_robot_ts.py:29-47); cleared on reset (:120-125)
             const bool cleared = (pm & PHASE_RESET) && reset;
             if (hrow != nullptr) {
-                mbar_wait(bar, 0);                          // the CTA's TMA loads of both slabs have landed
                 smem_shift_append(hrow, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, lane);
                 smem_shift_append(crow, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, lane);
             } else {
@@ -541,6 +561,17 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     }
 }
 
+// per-env input tensors staged per CTA: X(field, element type, elements per env)
+#define ENV_STAGED_INPUTS(X, A_, F_, L_, NS_)                                                                          \
+    X(base_pos, float, 3) X(base_quat_wxyz, float, 4) X(base_lin_w, float, 3) X(base_ang_w, float, 3) X(env_origins, float, 3) \
+    X(commands, float, 4) X(episode_length, int32_t, 1) X(fail_buf, int32_t, 1) X(terrain_levels, int64_t, 1)          \
+    X(terrain_types, int64_t, 1) X(rand_push_vels, float, 3) X(dof_pos, float, A_) X(dof_vel, float, A_)               \
+    X(actions, float, A_) X(last_actions, float, A_) X(llast_actions, float, A_) X(torques, float, A_)                 \
+    X(last_dof_vel, float, A_) X(feet_pos, float, 3 * F_) X(feet_vel, float, 3 * F_) X(last_feet_vel, float, 3 * F_)   \
+    X(link_contact_forces, float, 3 * L_) X(episode_sums, float, NS_) X(feet_air_time, float, F_)                      \
+    X(last_contacts, uint8_t, F_) X(friction, float, 1) X(added_mass, float, 1) X(com_bias, float, 3)                  \
+    X(kp_scale, float, A_) X(kd_scale, float, A_)
+
 __global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, 5)
 env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call) {
     extern __shared__ float smem[];
@@ -550,21 +581,34 @@ env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, 
     const int N = T.i[TI_NUM_ENVS];
     uint64_t *bar = (uint64_t *)smem;
     float *hslab = smem + 4, *cslab = hslab + nwarps * ENV_MAX_HIST_ROW, *es = cslab + nwarps * ENV_MAX_CRIT_ROW;
+    char *inslab = (char *)(es + nwarps * ES_TOTAL);
     const int HW = T.i[TI_FRAME_STACK] * T.i[TI_NUM_OBS], CW = T.i[TI_C_FRAME_STACK] * T.i[TI_SINGLE_CRITIC];
     const uint32_t hbytes = (uint32_t)(nwarps * HW * 4), cbytes = (uint32_t)(nwarps * CW * 4);
-    const bool observe = !call.force_reset && (call.phase_mask & PHASE_OBSERVE);
-    // CTA-uniform: full CTA, history task, slabs fit and are 16-byte multiples -> stage the history through shared memory with TMA
-    const bool staged = observe && T.i[TI_OBS_KIND] == 1 && env0 + nwarps <= N && HW <= ENV_MAX_HIST_ROW && CW <= ENV_MAX_CRIT_ROW &&
-                        B200_TMA_SIZE_OK(hbytes) && B200_TMA_SIZE_OK(cbytes);
+    const int A = T.i[TI_A], F = T.i[TI_F], L = T.i[TI_L];
+    const int NSUM = T.i[TI_N_REWARDS] + (T.i[TI_TERMINATION_COL] >= 0 ? 1 : 0);
+    const bool full = !call.force_reset && (call.phase_mask & PHASE_ALL) == PHASE_ALL;
+    // pass 1 (all threads, uniform): byte counts of every slab -> is the CTA stageable, how many bytes will arrive
+    uint32_t total = hbytes + cbytes, off = 0;
+    bool ok = full && T.i[TI_OBS_KIND] == 1 && env0 + nwarps <= N && HW <= ENV_MAX_HIST_ROW && CW <= ENV_MAX_CRIT_ROW &&
+              B200_TMA_SIZE_OK(hbytes) && B200_TMA_SIZE_OK(cbytes);
+#define X_COUNT(field, type, k) { const uint32_t b_ = (uint32_t)(nwarps * (k) * sizeof(type)); ok = ok && B200_TMA_SIZE_OK(b_); total += b_; off += (b_ + 15u) & ~15u; }
+    ENV_STAGED_INPUTS(X_COUNT, A, F, L, NSUM)
+#undef X_COUNT
+    const bool staged = ok && off <= (uint32_t)(nwarps * ENV_IN_WORDS * 4);
     if (staged) {
-        if (threadIdx.x == 0) {
-            mbar_init(bar, 1);
-            mbar_expect_tx(bar, hbytes + cbytes);
-            tma_load_1d(hslab, B.obs_history[call.parity] + (size_t)env0 * HW, hbytes, bar);
-            tma_load_1d(cslab, B.critic_obs[call.parity] + (size_t)env0 * CW, cbytes, bar);
-        }
-        __syncthreads();                                   // barrier initialised before anyone waits on it
-        env_post_step_warp(T, B, tr, call, es + warp * ES_TOTAL, env, lane, hslab + warp * HW, cslab + warp * CW, bar);
+        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_expect_tx(bar, total); }
+        __syncthreads();                                   // barrier armed before any copy can complete on it
+        // pass 2: thread t issues the bulk copy of tensor t; every thread builds the same biased read view R
+        B200Buffers R = B;
+        int t = 2; off = 0;
+        if (threadIdx.x == 0) tma_load_1d(hslab, B.obs_history[call.parity] + (size_t)env0 * HW, hbytes, bar);
+        if (threadIdx.x == 1) tma_load_1d(cslab, B.critic_obs[call.parity] + (size_t)env0 * CW, cbytes, bar);
+#define X_LOAD(field, type, k) { const uint32_t b_ = (uint32_t)(nwarps * (k) * sizeof(type));                              \
+        if ((int)threadIdx.x == t) tma_load_1d(inslab + off, B.field + (size_t)env0 * (k), b_, bar);                      \
+        R.field = (type *)(inslab + off) - (size_t)env0 * (k); off += (b_ + 15u) & ~15u; t++; }
+        ENV_STAGED_INPUTS(X_LOAD, A, F, L, NSUM)
+#undef X_LOAD
+        env_post_step_warp(T, B, R, tr, call, es + warp * ES_TOTAL, env, lane, hslab + warp * HW, cslab + warp * CW, bar);
         fence_proxy_async();                               // generic-proxy smem writes -> visible to the bulk store
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -575,5 +619,5 @@ env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, 
         return;
     }
     if (env >= N) return;
-    env_post_step_warp(T, B, tr, call, es + warp * ES_TOTAL, env, lane, nullptr, nullptr, bar);
+    env_post_step_warp(T, B, B, tr, call, es + warp * ES_TOTAL, env, lane, nullptr, nullptr, bar);
 }
