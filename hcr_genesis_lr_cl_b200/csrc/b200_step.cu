@@ -118,6 +118,11 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     env_post_step_kernel<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call);
     h->launches++;
     CK(cudaGetLastError());
+    if ((mask & PHASE_RESET) && !force) {
+        stats_finalize_kernel<<<1, 64, 0, s>>>(h->bufs.stats, n_sums, 1.0f / h->task.f[TF_EPISODE_LENGTH_S], 1.0f / (float)N, (int)(step % ENV_STATS_RING));
+        h->launches++;
+        CK(cudaGetLastError());
+    }
     return 0;
 }
 

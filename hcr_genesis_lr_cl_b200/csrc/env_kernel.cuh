@@ -40,6 +40,8 @@
 #define ENV_MAX_HIST_ROW 912       // >= frame_stack * num_obs floats (900)
 #define ENV_MAX_CRIT_ROW 896       // >= c_frame_stack * single_critic floats (885)
 
+#define ENV_STATS_RING 32           // per-step episode statistics are kept for this many policy steps
+
 struct EnvCall {
     uint32_t step;       // LeggedRobot.common_step_counter after its increment
     float vx_lo, vx_span;
@@ -381,6 +383,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
 
     // ================================================================== reset_idx
     f3 grav_obs = grav;
+    int new_level = level0;
     if ((pm & PHASE_RESET) && reset) {
         if (lane < n_sums) atomicAdd(B.stats + lane, my_sum);                    // extras["episode"] numerators
         if (lane == 0) atomicAdd(B.stats + n_sums, 1.0f);
@@ -400,6 +403,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             const float *og = tr.origins + ((size_t)lv * tr.types + ty) * 3;
             origin = mk3(og[0], og[1], og[2]);
             if (lane == 0) B.terrain_levels[env] = lv;
+            new_level = lv;
             if (lane < 3) B.env_origins[env * 3 + lane] = comp3(origin, lane);
         }
         {   // _resample_commands(env_ids)
@@ -463,6 +467,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         fat = 0.f;
         ep_len = 0; fail_cnt = 0;
     }
+    if ((pm & PHASE_RESET) && ti[TI_TERRAIN_CURRICULUM] && !call.force_reset && lane == 0)
+        atomicAdd(B.stats + n_sums + 1, (float)new_level);          // terrain_level mean of extras["episode"]
     // ---- write back the small per-env state
     if (pm & (PHASE_CALLBACK | PHASE_RESET)) {
         if (lane < 4) B.commands[env * 4 + lane] = lane == 0 ? cmd0 : (lane == 1 ? cmd1 : (lane == 2 ? cmd2 : cmd3));
@@ -620,4 +626,15 @@ env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, 
     }
     if (env >= N) return;
     env_post_step_warp(T, B, B, tr, call, es + warp * ES_TOTAL, env, lane, nullptr, nullptr, bar);
+}
+
+// extras["episode"] (legged_robot.py:127-141): means over the envs that reset this step, from the reductions the env
+// kernel left in stats[0..n_sums] (+ reset count, + sum of terrain levels); written to slot (step % ENV_STATS_RING) of
+// the ring that follows the work area so that the host can hand out per-step values without any further launch.
+__global__ void stats_finalize_kernel(float *stats, int n_sums, float inv_episode_length_s, float inv_num_envs, int slot) {
+    const int i = threadIdx.x;
+    float *ring = stats + (2 * n_sums + 4) + slot * (n_sums + 1);
+    const float cnt = fmaxf(stats[n_sums], 1.0f);
+    if (i < n_sums) ring[i] = stats[i] / cnt * inv_episode_length_s;
+    if (i == n_sums) ring[i] = stats[n_sums + 1] * inv_num_envs;
 }

@@ -60,6 +60,7 @@ class FusedLeggedEnv:
         self.last_actions, self.llast_actions = b["last_actions"], b["llast_actions"]
         self.feet_air_time, self.fail_buf = b["feet_air_time"], b["fail_buf"]
         self.episode_sums = {n: b["episode_sums"][:, i] for i, n in enumerate(self.sum_names)}
+        self._extras_ring = self._build_extras_ring()
 
     # runners assign a fresh tensor to env.episode_length_buf (on_policy_runner.py:169); keep the bound storage
     @property
@@ -109,16 +110,28 @@ class FusedLeggedEnv:
         return self.privileged_obs_buf
 
     # ------------------------------------------------------------------ extras / curricula (device side, no sync)
-    def _fill_extras(self):
-        """extras["episode"]["rew_*"] = mean over resetting envs of episode_sums / episode_length_s
-        (legged_robot.py:127-141), from the per-step reductions the kernel leaves in `stats`."""
+    def _build_extras_ring(self):
+        """Per-slot dicts of 0-dim views into the statistics ring the finalize kernel fills (no launch per step)."""
+        from ._cabi import STATS_RING
         n = len(self.sum_names)
         stats = self._b["stats"]
-        cnt = stats[n].clamp(min=1.0)
-        means = stats[:n] / (cnt * self.max_episode_length_s)
-        ep = {"rew_" + name: means[i] for i, name in enumerate(self.sum_names)}
-        if self.spec.terrain_curriculum:
-            ep["terrain_level"] = self._b["terrain_levels"].float().mean()
+        base = 2 * max(n, 1) + 4
+        ring = []
+        for slot in range(STATS_RING):
+            row = stats[base + slot * (n + 1): base + (slot + 1) * (n + 1)]
+            ep = {"rew_" + name: row[i] for i, name in enumerate(self.sum_names)}
+            if self.spec.terrain_curriculum:
+                ep["terrain_level"] = row[n]
+            ring.append(ep)
+        return ring
+
+    def _fill_extras(self):
+        """extras["episode"]["rew_*"] = mean over resetting envs of episode_sums / episode_length_s
+        (legged_robot.py:127-141): computed on the device by stats_finalize_kernel into slot step % 32."""
+        from ._cabi import STATS_RING
+        n = len(self.sum_names)
+        stats = self._b["stats"]
+        ep = dict(self._extras_ring[self.common_step_counter % STATS_RING])
         if self.spec.cmd_curriculum:
             ep["max_command_x"] = self.command_ranges["lin_vel_x"][1]
         self.extras["episode"] = ep
@@ -129,6 +142,7 @@ class FusedLeggedEnv:
         if self.spec.cmd_curriculum and self.common_step_counter % int(self.max_episode_length) == 0 \
                 and "tracking_lin_vel" in self.sum_names:
             i = self.sum_names.index("tracking_lin_vel")
+            cnt = stats[n].clamp(min=1.0)
             self._pending_curriculum = (stats[i] / cnt / self.max_episode_length, stats[n].clone())
 
     def _apply_pending_curriculum(self):

@@ -182,8 +182,10 @@ typedef struct B200Buffers {
     uint8_t *reset_buf;         /* [N] uint8 (torch.bool storage) */
     uint8_t *time_out_buf;      /* [N] uint8 */
     int32_t *height_cells;      /* [N,P,2] int32 cell indices of the scan (diagnostic, may be NULL) */
-    float *stats;               /* [2*n_sums+4] per-step reductions: sum over resetting envs of episode_sums,
-                                   then [n_sums]=count of resets, [n_sums+1]=sum of terrain levels (all envs) */
+    float *stats;               /* [2*n_sums+4 + 32*(n_sums+1)] per-step reductions: [0,n_sums) sum over resetting envs of
+                                   episode_sums, [n_sums] count of resets, [n_sums+1] sum of terrain levels (all envs);
+                                   then a ring of 32 slots [n_sums+1]: the extras["episode"] means of step % 32
+                                   (rew_* in episode-sum order, then the mean terrain level) */
 } B200Buffers;
 
 typedef struct B200Handle B200Handle;

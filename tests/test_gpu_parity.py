@@ -204,6 +204,13 @@ def test_env_kernel_matches_numpy_oracle_seeded(golden):
         _close(out["base_pos"], eo.st["base_pos"], what=f"step {t}: reset base_pos")
         for k in ("friction", "added_mass", "com_bias", "kp_scale", "kd_scale"):
             _close(out[k], eo.st[k], what=f"step {t}: {k}")
+        if o["episode_means"] is not None:                                   # extras["episode"] of this step (device ring)
+            n = len(eo.sum_names)
+            base = 2 * n + 4 + (env.common_step_counter % 32) * (n + 1)
+            ring = out["stats"][base:base + n + 1]
+            for i, name in enumerate(eo.sum_names):
+                assert abs(ring[i] - o["episode_means"]["rew_" + name]) <= 1e-4 * abs(o["episode_means"]["rew_" + name]) + 1e-6, name
+            assert abs(ring[n] - eo.st["terrain_levels"].mean()) < 1e-3
     assert total_resets > 0
 
 
@@ -244,7 +251,7 @@ def test_full_size_properties():
         assert torch.equal(sa[k][half:], sc[k]), f"shard != full job for {k}"
     assert torch.isfinite(sa["obs_buf"]).all() and torch.isfinite(sa["rew_buf"]).all()
     assert sa["height_cells"].min() >= 0 and sa["height_cells"].max() <= 1198
-    assert env_a.simulator.launch_count == 1 + 2 * (len(acts) + 1)     # reset_all + (dynamics, env) per step
+    assert env_a.simulator.launch_count == 1 + 3 * (len(acts) + 1)     # reset_all + (dynamics, env, stats finalize) per step
 
 
 def test_short_rollout_against_oracle(golden):
