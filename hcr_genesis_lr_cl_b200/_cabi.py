@@ -210,7 +210,7 @@ def buffer_shapes(spec: T.TaskSpec, model: RobotModel, N: int) -> "OrderedDict[s
         obs_buf=(N, w["obs"]), privileged_obs_buf=(N, max(w["priv"], 1)),
         obs_history0=(N, max(w["hist"], 1)), obs_history1=(N, max(w["hist"], 1)),
         critic_obs0=(N, max(w["critic"], 1)), critic_obs1=(N, max(w["critic"], 1)),
-        rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), height_cells=(N, P, 2), stats=(2 * max(nsum, 1) + 4 + STATS_RING * (max(nsum, 1) + 1),),
+        rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), height_cells=(N, P, 2), stats=(2 * max(nsum, 1) + 4 + STATS_RING * (max(nsum, 1) + 1),),
     )
     return OrderedDict((name, (shp[name], _NP[ct])) for name, ct in BUFFER_FIELDS)
 

@@ -76,7 +76,8 @@ struct TerrainDev {
 #define WS_FV (WS_AM + 32 * 33)         // row force vectors [32][4]
 #define WS_LF (WS_FV + 128)             // link forces [17*3]
 #define WS_Q (WS_LF + 52)               // joint q [12]
-#define WS_TOTAL (WS_Q + 12)
+#define WS_WARM (WS_Q + 12)             // PGS warm start [48]: 8 x (sphere id + 1, f_n, f_t1, f_t2), 8 x (aux code + 1, f)
+#define WS_TOTAL (WS_WARM + 48)
 
 #define MS_BODY 0
 #define MS_LINK (MS_BODY + B200_MAX_BODIES * B200_BODY_STRIDE)
@@ -228,6 +229,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     const f3 com_shift = mk3(B.com_bias[env * 3], B.com_bias[env * 3 + 1], B.com_bias[env * 3 + 2]);
     const float env_arm = B.joint_armature[env], env_dmp = B.joint_damping[env], env_fls = B.joint_friction[env];
 
+    for (int e = lane; e < 48; e += 32) ws[WS_WARM + e] = B.contact_warm[env * 48 + e];
     // ---------------- pre-step: action history, last_* (legged_robot.py:230-252, genesis_simulator.py:21-24) ----------------
     if (lane < A) {
         const int o = env * A + lane;
@@ -489,6 +491,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                 ct[0] = xc.x; ct[1] = xc.y; ct[2] = xc.z; ct[3] = sn[t].x; ct[4] = sn[t].y; ct[5] = sn[t].z; ct[6] = sdist[t];
                 ct[7] = __int_as_float(msi[B200_MAX_LINKS + s]);                        // body
                 ct[8] = __int_as_float(msi[B200_MAX_LINKS + B200_MAX_SPHERES + s]);     // reporting link
+                ct[9] = (float)(s + 1);                                                 // warm-start key
             }
         }
         // ---------------- aux rows: joint limits first, then frictionloss, joint order ----------------
@@ -532,6 +535,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         float rpos = 0.f, bound = 0.f;
         f3 dir = mk3(0.f, 0.f, 0.f);
         int rlink = 0;
+        float wkey = 0.f;               // warm-start key of this row (contact: sphere id + 1, aux: code + 1)
         if (lane < 3 * nc) {
             const float *ct = ws + WS_CT + (lane / 3) * 12;
             const int d = lane - 3 * (lane / 3);
@@ -540,7 +544,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             f3 t1 = e - n * dot3(e, n); t1 = t1 * (1.f / sqrtf(dot3(t1, t1)));
             const f3 t2 = cross3(n, t1);
             dir = d == 0 ? n : (d == 1 ? t1 : t2);
-            kind = d; rpos = d == 0 ? ct[6] : 0.f;
+            kind = d; rpos = d == 0 ? ct[6] : 0.f; wkey = ct[9];
             const int b = __float_as_int(ct[7]); rlink = __float_as_int(ct[8]);
             Jb[0] = dir.x; Jb[1] = dir.y; Jb[2] = dir.z;
             const f3 xd = cross3(xc, dir); Jb[3] = xd.x; Jb[4] = xd.y; Jb[5] = xd.z;
@@ -565,6 +569,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             for (int k = 0; k < 3; k++) Jl[k] = (k == k2) ? ax[1] : 0.f;
             rpos = ax[2]; bound = ax[3];
             kind = ax[3] < 0.f ? 3 : 4;
+            wkey = (float)(8 * j + (kind == 3 ? (ax[1] > 0.f ? 7 : 6) : 4) + 1);
         }
         // y = M^-1 J^T for this lane's row
         float Yb[6], Yl[C][3];
@@ -630,11 +635,22 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             imp = __shfl_sync(B200_FULL_MASK, imp, src);
         }
         float f = 0.f, Rr = 0.f, idd = 1.f, wres = 0.f;
+        if (lane < 3 * nc) {                  // warm start: same sphere as in the previous substep keeps its force
+            const int d = lane - 3 * (lane / 3);
+#pragma unroll
+            for (int k = 0; k < B200_KMAX; k++) if (ws[WS_WARM + 4 * k] == wkey) f = ws[WS_WARM + 4 * k + 1 + d];
+        } else if (lane < R) {
+#pragma unroll
+            for (int k = 0; k < B200_AUXMAX; k++) if (ws[WS_WARM + 32 + 2 * k] == wkey) f = ws[WS_WARM + 32 + 2 * k + 1];
+        }
+        ws[WS_FV + lane * 4] = lane < R ? f : 0.f;
+        __syncwarp();
         if (lane < R) {
             const float aref = -bd * vel - kk * imp * rpos;
             Rr = (1.f - imp) / imp * Arr;
             idd = 1.f / (Arr + Rr);
             wres = ja - aref;
+            for (int s2 = 0; s2 < R; s2++) wres += ws[WS_AM + s2 * 33 + lane] * ws[WS_FV + s2 * 4];
         }
         __syncwarp();
         // ---------------- projected Gauss-Seidel with friction-cone projection ----------------
@@ -683,6 +699,17 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                 fmx = fmaxf(fmx, __shfl_xor_sync(B200_FULL_MASK, fmx, o2));
             }
             if (dmax <= tf[TF_PGS_TOL] * (1.f + fmx)) break;
+        }
+        __syncwarp();
+        for (int e = lane; e < 48; e += 32) ws[WS_WARM + e] = 0.f;
+        __syncwarp();
+        if (lane < 3 * nc) {
+            const int c2 = lane / 3, d = lane - 3 * c2;
+            if (d == 0) ws[WS_WARM + 4 * c2] = wkey;
+            ws[WS_WARM + 4 * c2 + 1 + d] = f;
+        } else if (lane < R) {
+            const int a2 = lane - 3 * nc;
+            ws[WS_WARM + 32 + 2 * a2] = wkey; ws[WS_WARM + 32 + 2 * a2 + 1] = f;
         }
         PHASE_SYNC();
         // ---------------- total acceleration, contact forces, integration ----------------
@@ -752,6 +779,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         }
     }
     for (int e = lane; e < 3 * L; e += 32) B.link_contact_forces[env * 3 * L + e] = ws[WS_LF + e];
+    for (int e = lane; e < 48; e += 32) B.contact_warm[env * 48 + e] = ws[WS_WARM + e];
     const int F = T.i[TI_F];
     if (lane < F) {
         const int l2 = T.i[TI_FEET_LINKS + lane];

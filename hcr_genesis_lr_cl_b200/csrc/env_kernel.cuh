@@ -464,6 +464,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         }
 #undef DR_PUT
         if (lane < 3 * F) B.last_feet_vel[env * 3 * F + lane] = 0.f;
+        for (int e = lane; e < 48; e += 32) B.contact_warm[env * 48 + e] = 0.f;    // teleported: the contact warm start is stale
         fat = 0.f;
         ep_len = 0; fail_cnt = 0;
     }

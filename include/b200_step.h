@@ -186,6 +186,8 @@ typedef struct B200Buffers {
                                    episode_sums, [n_sums] count of resets, [n_sums+1] sum of terrain levels (all envs);
                                    then a ring of 32 slots [n_sums+1]: the extras["episode"] means of step % 32
                                    (rew_* in episode-sum order, then the mean terrain level) */
+    float *contact_warm;        /* [N,48] contact-solver warm start carried between substeps and policy steps: 8 x (sphere id + 1,
+                                   f_n, f_t1, f_t2) then 8 x (aux-row code + 1, f); zero = empty */
 } B200Buffers;
 
 typedef struct B200Handle B200Handle;

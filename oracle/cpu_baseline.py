@@ -42,6 +42,7 @@ class OracleEnv:
         st["friction"][:] = 1.0
         st["episode_length"][:] = rng.integers(0, spec.max_episode_length, num_envs)
         self._feet = spec.link_groups(self.model)[0]
+        self.warm = np.zeros((num_envs, 48), np.float64)
 
     def step(self, actions):
         spec, st, N, A = self.spec, self.eo.st, self.N, self.spec.num_actions
@@ -58,11 +59,13 @@ class OracleEnv:
         tau, lf = None, None
         for _ in range(spec.decimation):
             tau = (kp * (tgt - q.astype(f32)) - kd * qd.astype(f32)).astype(f32)
-            lf, _ = self.phys.substep(state, q, qd, tau, envp, jp)
+            lf, _ = self.phys.substep(state, q, qd, tau, envp, jp, self.warm)
         lp, lv = self.phys.link_kinematics(state, q, qd)
         phys = dict(base_pos=state[:, 0:3], base_quat_wxyz=state[:, 3:7], base_lin_w=state[:, 7:10], base_ang_w=state[:, 10:13],
                     q=q, qd=qd, torques=tau, link_force=lf, feet_pos=lp[:, self._feet], feet_vel=lv[:, self._feet])
-        return self.eo.post_step(phys)
+        o = self.eo.post_step(phys)
+        self.warm[o["env_ids"]] = 0
+        return o
 
 
 def _worker(args):

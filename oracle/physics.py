@@ -55,8 +55,9 @@ class PhysicsOracle:
     def _p(a):
         return a.ctypes.data_as(ctypes.c_void_p)
 
-    def substep(self, state, q, qd, tau, envp, jparam):
-        """In-place substep. Returns (link_force [n, nlinks, 3], ncontact [n])."""
+    def substep(self, state, q, qd, tau, envp, jparam, warm=None):
+        """In-place substep. Returns (link_force [n, nlinks, 3], ncontact [n]).  `warm` [n, 48] float64 (in/out) carries the
+        contact-solver warm start between substeps; None = cold start."""
         n = state.shape[0]
         for a in (state, q, qd):
             assert a.dtype == np.float64 and a.flags.c_contiguous
@@ -65,10 +66,13 @@ class PhysicsOracle:
         jparam = np.ascontiguousarray(jparam, np.float64)
         lf = np.zeros((n, self.model.nlinks, 3), np.float64)
         nc = np.zeros(n, np.int32)
+        if warm is None:
+            warm = np.zeros((n, 48), np.float64)
+        assert warm.dtype == np.float64 and warm.flags.c_contiguous and warm.shape == (n, 48)
         self.lib.oracle_substep(self._p(self.mi), self._p(self.mf), self._p(self.prm), self._p(self.hf),
                                 ctypes.c_int(self.rows), ctypes.c_int(self.cols), ctypes.c_int(n),
                                 self._p(state), self._p(q), self._p(qd), self._p(tau), self._p(envp), self._p(jparam),
-                                self._p(lf), self._p(nc))
+                                self._p(lf), self._p(nc), self._p(warm))
         return lf, nc
 
     def link_kinematics(self, state, q, qd):

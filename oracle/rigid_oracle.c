@@ -62,6 +62,7 @@ typedef struct {
 enum { P_DT, P_GRAV, P_TC, P_DAMPRATIO, P_D0, P_DMAX, P_WIDTH, P_MID, P_POWER,
        P_TERRAIN_MU, P_GEOM_MU, P_ITERS, P_HSCALE, P_VSCALE, P_BORDER, P_TOL, P_NPARAM };
 
+static long long g_sweeps, g_substeps, g_rows, g_contacts;
 typedef struct { real x, y, z; } v3;
 static v3 V(real x, real y, real z) { v3 r = {x, y, z}; return r; }
 static v3 add(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -193,7 +194,7 @@ static void forward_kinematics(const Model *M, const real quat[4], const real *q
  */
 static void substep_one(const Model *M, const float *prm, const int16_t *hf, int rows, int cols,
                         real *st, real *q, real *qd, const real *tau_cmd, const real *envp, const real *jp,
-                        real *link_force, int *ncontact) {
+                        real *link_force, int *ncontact, real *warm /* [48] in/out: PGS warm start, see DESIGN.md */) {
     const int nb = M->nb, nj = M->nj, nv = 6 + nj, D = M->D;
     const real h = prm[P_DT];
     Kin K;
@@ -290,7 +291,7 @@ static void substep_one(const Model *M, const float *prm, const int16_t *hf, int
 
     /* --- constraint rows --- */
     real J[RMAX][MAXV], pos[RMAX], lo[RMAX], hi[RMAX]; int kind[RMAX]; /* 0 normal,1/2 tangent,3 limit,4 frictionloss */
-    v3 cdir[RMAX]; int clink[RMAX]; real cmu[KMAX];
+    v3 cdir[RMAX]; int clink[RMAX]; real cmu[KMAX]; int csph[KMAX], auxcode[AUXMAX];
     int R = 0, nc = 0;
     memset(J, 0, sizeof J);
     real mu = prm[P_GEOM_MU] * envp[4]; if (prm[P_TERRAIN_MU] > mu) mu = prm[P_TERRAIN_MU];
@@ -310,19 +311,23 @@ static void substep_one(const Model *M, const float *prm, const int16_t *hf, int
             kind[R] = d; pos[R] = (d == 0) ? sd[s] : 0; cdir[R] = dd; clink[R] = M->sph_link[s];
             lo[R] = 0; hi[R] = 0; R++;
         }
-        cmu[nc++] = mu;
+        csph[nc] = s; cmu[nc++] = mu;
     }
     int naux = 0;
     for (int j = 0; j < nj && naux < AUXMAX; j++) {
         real l = M->body[(j + 1) * BODY_STRIDE + 16], u = M->body[(j + 1) * BODY_STRIDE + 17];
-        if (q[j] < l) { J[R][6 + j] = 1; pos[R] = q[j] - l; kind[R] = 3; R++; naux++; }
-        else if (q[j] > u) { J[R][6 + j] = -1; pos[R] = u - q[j]; kind[R] = 3; R++; naux++; }
+        if (q[j] < l) { J[R][6 + j] = 1; pos[R] = q[j] - l; kind[R] = 3; auxcode[naux] = 8 * j + 7; R++; naux++; }
+        else if (q[j] > u) { J[R][6 + j] = -1; pos[R] = u - q[j]; kind[R] = 3; auxcode[naux] = 8 * j + 6; R++; naux++; }
     }
     for (int j = 0; j < nj && naux < AUXMAX; j++) if (jp[2 * nj + j] > 0) {
-        J[R][6 + j] = 1; pos[R] = 0; kind[R] = 4; lo[R] = -jp[2 * nj + j]; hi[R] = jp[2 * nj + j]; R++; naux++;
+        J[R][6 + j] = 1; pos[R] = 0; kind[R] = 4; lo[R] = -jp[2 * nj + j]; hi[R] = jp[2 * nj + j]; auxcode[naux] = 8 * j + 4; R++; naux++;
     }
 
     real f[RMAX]; memset(f, 0, sizeof f);
+    /* warm start: a contact keeps the force of the same sphere from the previous substep, an aux row that of the same
+       (joint, kind, side); anything new starts from zero */
+    for (int c = 0; c < nc; c++) for (int k = 0; k < KMAX; k++) if ((int)warm[4 * k] == csph[c] + 1) { f[3 * c] = warm[4 * k + 1]; f[3 * c + 1] = warm[4 * k + 2]; f[3 * c + 2] = warm[4 * k + 3]; }
+    for (int a = 0; a < naux; a++) for (int k = 0; k < AUXMAX; k++) if ((int)warm[32 + 2 * k] == auxcode[a] + 1) f[3 * nc + a] = warm[32 + 2 * k + 1];
     real Y[RMAX][MAXV];
     real acc[MAXV]; memcpy(acc, afree, sizeof afree);
     if (R > 0) {
@@ -358,11 +363,15 @@ static void substep_one(const Model *M, const float *prm, const int16_t *hf, int
             /* convergence: largest change of any row over this sweep, relative to the largest force */
             real dmax = 0, fmax = 0;
             for (int r = 0; r < R; r++) { real d = fabs(f[r] - fprev[r]); if (d > dmax) dmax = d; if (fabs(f[r]) > fmax) fmax = fabs(f[r]); }
+            g_sweeps++;
             if (dmax <= prm[P_TOL] * (1 + fmax)) break;
         }
         for (int r = 0; r < R; r++) for (int k = 0; k < nv; k++) acc[k] += Y[r][k] * f[r];
     }
 
+    for (int k = 0; k < 48; k++) warm[k] = 0;   /* ids are stored +1 so that 0 means empty */
+    for (int c = 0; c < nc; c++) { warm[4 * c] = csph[c] + 1; warm[4 * c + 1] = f[3 * c]; warm[4 * c + 2] = f[3 * c + 1]; warm[4 * c + 3] = f[3 * c + 2]; }
+    for (int a = 0; a < naux; a++) { warm[32 + 2 * a] = auxcode[a] + 1; warm[32 + 2 * a + 1] = f[3 * nc + a]; }
     /* --- contact forces per reporting link (world frame) --- */
     for (int i = 0; i < 3 * M->nlinks; i++) link_force[i] = 0;
     for (int r = 0; r < 3 * nc; r++) {
@@ -371,6 +380,7 @@ static void substep_one(const Model *M, const float *prm, const int16_t *hf, int
         link_force[3 * clink[r] + 2] += f[r] * cdir[r].z;
     }
     *ncontact = nc;
+    g_substeps++; g_rows += R; g_contacts += nc;
 
     /* --- semi-implicit Euler --- */
     for (int k = 0; k < nv; k++) nu[k] += h * acc[k];
@@ -410,6 +420,9 @@ static void link_kinematics(const Model *M, const real *st, const real *q, const
 }
 
 /* ------------------------------ exported (ctypes) ------------------------------ */
+/* diagnostics (single-threaded use): totals since the last oracle_counters() call */
+void oracle_counters(long long *out) { out[0] = g_sweeps; out[1] = g_substeps; out[2] = g_rows; out[3] = g_contacts; g_sweeps = g_substeps = g_rows = g_contacts = 0; }
+
 static Model mk_model(const int *mi, const float *mf) {
     Model M; M.C = mi[0]; M.D = mi[1]; M.nb = mi[2]; M.nj = mi[3]; M.nlinks = mi[4]; M.nspheres = mi[5];
     M.link_body = mi + 8; M.sph_body = M.link_body + M.nlinks; M.sph_link = M.sph_body + M.nspheres;
@@ -421,15 +434,17 @@ static Model mk_model(const int *mi, const float *mf) {
 void oracle_substep(const int *mi, const float *mf, const float *prm, const int16_t *hf, int rows, int cols, int n_envs,
                     double *state /*[n][13]*/, double *q, double *qd, const double *tau /*[n][nj]*/,
                     const double *envp /*[n][5]*/, const double *jparam /*[n][3*nj]*/,
-                    double *link_force /*[n][nlinks][3]*/, int *ncontact /*[n]*/) {
+                    double *link_force /*[n][nlinks][3]*/, int *ncontact /*[n]*/, double *warm /*[n][48]*/) {
     Model M = mk_model(mi, mf); int nj = M.nj;
     for (int e = 0; e < n_envs; e++) {
-        real st[13], qq[MAXJ], qv[MAXJ], tt[MAXJ], ep[5], jp[3 * MAXJ], lf[3 * MAXB + 12];
+        real st[13], qq[MAXJ], qv[MAXJ], tt[MAXJ], ep[5], jp[3 * MAXJ], lf[3 * MAXB + 12], wm[48];
         for (int k = 0; k < 13; k++) st[k] = (real)state[e * 13 + k];
+        for (int k = 0; k < 48; k++) wm[k] = (real)warm[e * 48 + k];
         for (int k = 0; k < nj; k++) { qq[k] = (real)q[e * nj + k]; qv[k] = (real)qd[e * nj + k]; tt[k] = (real)tau[e * nj + k]; }
         for (int k = 0; k < 5; k++) ep[k] = (real)envp[e * 5 + k];
         for (int k = 0; k < 3 * nj; k++) jp[k] = (real)jparam[e * 3 * nj + k];
-        substep_one(&M, prm, hf, rows, cols, st, qq, qv, tt, ep, jp, lf, ncontact + e);
+        substep_one(&M, prm, hf, rows, cols, st, qq, qv, tt, ep, jp, lf, ncontact + e, wm);
+        for (int k = 0; k < 48; k++) warm[e * 48 + k] = wm[k];
         for (int k = 0; k < 13; k++) state[e * 13 + k] = st[k];
         for (int k = 0; k < nj; k++) { q[e * nj + k] = qq[k]; qd[e * nj + k] = qv[k]; }
         for (int k = 0; k < 3 * M.nlinks; k++) link_force[e * 3 * M.nlinks + k] = lf[k];

@@ -122,13 +122,14 @@ class RobotEntity:
         self.jparam[:, :nj] = self.model.body[1:, 19]
         self.link_force = np.zeros((n, self.model.nlinks, 3))
         self.ncontact = np.zeros(n, np.int32)
+        self.warm = np.zeros((n, 48))
         self._refresh()
 
     def _refresh(self):
         self.link_pos, self.link_vel = self.scene.oracle.link_kinematics(self.state, self.q, self.qd)
 
     def _step(self):
-        self.link_force, self.ncontact = self.scene.oracle.substep(self.state, self.q, self.qd, self.tau, self.envp, self.jparam)
+        self.link_force, self.ncontact = self.scene.oracle.substep(self.state, self.q, self.qd, self.tau, self.envp, self.jparam, self.warm)
         self._refresh()
 
     # ---- helpers ----

@@ -114,10 +114,11 @@ def oracle_policy_step(spec, model, oracle, st, actions):
     tgt = (a * f32(spec.action_scale) + q0).astype(f32)
     tau = np.zeros((N, A), f32)
     lf = nc = None
+    warm = np.ascontiguousarray(st.get("contact_warm", np.zeros((N, 48))), np.float64).copy()
     for _ in range(spec.decimation):
         tau = (kp * (tgt - q.astype(f32)) - kd * qd.astype(f32)).astype(f32)
-        lf, nc = oracle.substep(state, q, qd, tau, envp, jp)
+        lf, nc = oracle.substep(state, q, qd, tau, envp, jp, warm)
     lp, lv = oracle.link_kinematics(state, q, qd)
     feet = spec.link_groups(model)[0]
     return dict(base_pos=state[:, 0:3], base_quat_wxyz=state[:, 3:7], base_lin_w=state[:, 7:10], base_ang_w=state[:, 10:13],
-                q=q, qd=qd, torques=tau, link_force=lf, feet_pos=lp[:, feet], feet_vel=lv[:, feet], ncontact=nc)
+                q=q, qd=qd, torques=tau, link_force=lf, feet_pos=lp[:, feet], feet_vel=lv[:, feet], ncontact=nc, contact_warm=warm)

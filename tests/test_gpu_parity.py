@@ -274,15 +274,19 @@ def test_short_rollout_against_oracle(golden):
             eo.st[k][...] = v
     eo.common_step_counter = env.common_step_counter
     worst = 0.0
+    warm = np.zeros((N, 48))
     for t in range(5):
         a = g["actions"][t]
         cur = {k: eo.st[k2] for k, k2 in (("base_pos", "base_pos"), ("base_quat_wxyz", "base_quat_wxyz"), ("base_lin_w", "base_lin_w"),
                                          ("base_ang_w", "base_ang_w"), ("dof_pos", "q"), ("dof_vel", "qd"), ("added_mass", "added_mass"),
                                          ("com_bias", "com_bias"), ("friction", "friction"), ("kp_scale", "kp_scale"), ("kd_scale", "kd_scale"),
                                          ("joint_armature", "joint_armature"), ("joint_damping", "joint_damping"), ("joint_friction", "joint_friction"))}
+        cur["contact_warm"] = warm
         eo.pre_step(a)
         ref = oracle_policy_step(spec, model, orc, cur, a)
-        o = eo.post_step({k: np.asarray(v, np.float32) for k, v in ref.items() if k != "ncontact"})
+        o = eo.post_step({k: np.asarray(v, np.float32) for k, v in ref.items() if k not in ("ncontact", "contact_warm")})
+        warm = ref["contact_warm"]
+        warm[o["env_ids"]] = 0
         out = env.step(torch.from_numpy(a).cuda())
         same = ~o["reset_buf"]
         worst = max(worst, float(np.abs(out[0].cpu().numpy() - o["obs_buf"])[same].max()))
