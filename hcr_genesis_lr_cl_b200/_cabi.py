@@ -56,6 +56,11 @@ def _parse_header():
 
 H, BUFFER_FIELDS = _parse_header()
 STATS_RING = 32      # ENV_STATS_RING in csrc/env_kernel.cuh
+
+
+def stats_base(nsum: int) -> int:
+    """Offset of the statistics ring inside `stats` (work area: sums, reset count, level sum, cstr_prob sum + padding)."""
+    return 2 * max(nsum, 1) + 4
 _NP = {"float": np.float32, "int32_t": np.int32, "uint8_t": np.uint8, "int64_t": np.int64}
 
 
@@ -73,6 +78,8 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     A = spec.num_actions
     if model.chain_len != 3:
         raise ValueError("only chains of 3 revolute joints are supported")
+    if len(spec.episode_sum_names()) > 32:
+        raise ValueError("more than 32 episode-sum columns")
     if len(feet) > H["B200_MAX_FEET"] or model.nlinks > H["B200_MAX_LINKS"] or w["obs"] > H["B200_MAX_OBS"]:
         raise ValueError("robot exceeds the compiled limits in b200_step.h")
 
@@ -123,10 +130,14 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     sf("TF_GRAV", 9.81); sf("TF_TC", 2 * spec.sim_dt); sf("TF_DAMPRATIO", 1.0)
     sf("TF_D0", 0.9); sf("TF_DMAX", 0.95); sf("TF_WIDTH", 0.001); sf("TF_MID", 0.5); sf("TF_POWER", 2.0)
     sf("TF_TERRAIN_MU", spec.static_friction); sf("TF_GEOM_MU", 1.0); sf("TF_PGS_TOL", spec.pgs_tolerance)
+    sf("TF_CAT_SOFT_P", spec.cat_soft_p); sf("TF_CAT_ACTION_RATE", spec.cat_action_rate)
+    sf("TF_CAT_MIN_BASE_HEIGHT", spec.cat_min_base_height); sf("TF_CAT_MAX_PROJ_GRAV", spec.cat_max_projected_gravity)
     lim = soft_dof_limits(spec, model)
     for j in range(A):
         sf("TF_DEFAULT_DOF_POS", spec.default_dof_pos[j], j); sf("TF_RESET_DOF_NOISE", spec.reset_dof_noise[j], j)
         sf("TF_DOF_LIM_LO", lim[j, 0], j); sf("TF_DOF_LIM_HI", lim[j, 1], j)
+        sf("TF_TORQUE_LIMIT", model.effort[j], j)
+        sf("TF_DOF_VEL_LIMIT", spec.dof_vel_limits[j] if spec.dof_vel_limits else model.velocity[j], j)
     for name in T.REWARD_TERMS:
         sf("TF_REWARD_SCALE", spec.scaled_reward(name), T.REWARD_ID[name])
     nv = spec.noise_scale_vec()
@@ -165,6 +176,8 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     sums = spec.episode_sum_names()
     si("TI_TERMINATION_COL", sums.index("termination") if "termination" in sums else -1)
     si("TI_N_PEN", len(pen)); si("TI_N_TERM", len(term)); si("TI_N_CS", len(cs)); si("TI_ENV_OFFSET", env_offset)
+    si("TI_CAT", spec.cat_enabled); si("TI_CAT_GLOBAL_STANDSTILL", spec.cat_stand_still_global)
+    si("TI_DOUBLE_SHIFT", spec.double_shift_actions); si("TI_N_SUMS", len(spec.episode_sum_names()))
     for k, v in enumerate(feet):
         si("TI_FEET_LINKS", v, k)
     for k, v in enumerate(pen):
@@ -210,7 +223,7 @@ def buffer_shapes(spec: T.TaskSpec, model: RobotModel, N: int) -> "OrderedDict[s
         obs_buf=(N, w["obs"]), privileged_obs_buf=(N, max(w["priv"], 1)),
         obs_history0=(N, max(w["hist"], 1)), obs_history1=(N, max(w["hist"], 1)),
         critic_obs0=(N, max(w["critic"], 1)), critic_obs1=(N, max(w["critic"], 1)),
-        rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), height_cells=(N, P, 2), stats=(2 * max(nsum, 1) + 4 + STATS_RING * (max(nsum, 1) + 1),),
+        rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), height_cells=(N, P, 2), stats=(stats_base(nsum) + STATS_RING * (max(nsum, 1) + 2),), cstr_prob=(N,), global_flags=(4,),
     )
     return OrderedDict((name, (shp[name], _NP[ct])) for name, ct in BUFFER_FIELDS)
 

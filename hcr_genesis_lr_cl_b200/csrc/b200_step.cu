@@ -101,6 +101,7 @@ int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
     const int N = h->task.i[TI_NUM_ENVS];
     const dim3 grid((N + DYN_WARPS_PER_BLOCK - 1) / DYN_WARPS_PER_BLOCK), block(DYN_WARPS_PER_BLOCK * 32);
     cudaStream_t s = (cudaStream_t)stream;
+    if (h->task.i[TI_CAT]) CK(cudaMemsetAsync(h->bufs.global_flags, 0, 4 * sizeof(int32_t), s));
     if (h->task.i[TI_C] == 4) dynamics_step_kernel<4><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions);
     else dynamics_step_kernel<2><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions);
     h->launches++;
@@ -110,9 +111,9 @@ int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
 
 static int launch_env(B200Handle *h, long long step, float lo, float span, int parity, int mask, int force, void *stream) {
     const int N = h->task.i[TI_NUM_ENVS];
-    const int n_sums = h->task.i[TI_N_REWARDS] + (h->task.i[TI_TERMINATION_COL] >= 0 ? 1 : 0);
+    const int n_sums = h->task.i[TI_N_SUMS];
     cudaStream_t s = (cudaStream_t)stream;
-    if (mask & PHASE_RESET) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 2), s));
+    if (mask & PHASE_RESET) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 3), s));
     EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.parity = parity & 1; call.phase_mask = mask; call.force_reset = force;
     const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
     env_post_step_kernel<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call);

@@ -778,6 +778,10 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             B.dof_pos[o] = q[k]; B.dof_vel[o] = qd[k]; B.torques[o] = tau[k];
         }
     }
+    if (T.i[TI_CAT]) {   // CaT stand-still constraint couples all envs as shipped (go2_cat.py:177-178)
+        const bool fast = leg && (fabsf(qd[0]) > 4.0f || fabsf(qd[1]) > 4.0f || fabsf(qd[2]) > 4.0f);
+        if (__ballot_sync(B200_FULL_MASK, fast) != 0u && lane == 0) atomicOr(B.global_flags, 1);
+    }
     for (int e = lane; e < 3 * L; e += 32) B.link_contact_forces[env * 3 * L + e] = ws[WS_LF + e];
     for (int e = lane; e < 48; e += 32) B.contact_warm[env * 48 + e] = ws[WS_WARM + e];
     const int F = T.i[TI_F];

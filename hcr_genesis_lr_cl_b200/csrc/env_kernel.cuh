@@ -116,7 +116,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     const float *tf = T.f;
     const int *ti = T.i;
     const int A = ti[TI_A], F = ti[TI_F], L = ti[TI_L], P = ti[TI_PX] * ti[TI_PY];
-    const int n_sums = ti[TI_N_REWARDS] + (ti[TI_TERMINATION_COL] >= 0 ? 1 : 0);
+    const int n_sums = ti[TI_N_SUMS];
     const int pm = call.force_reset ? PHASE_RESET : call.phase_mask;
     EnvRng rng; rng.k0 = (uint32_t)ti[TI_SEED_LO]; rng.k1 = (uint32_t)ti[TI_SEED_HI]; rng.env = (uint32_t)(env + ti[TI_ENV_OFFSET]); rng.step = call.step;
     const float dt = tf[TF_POLICY_DT];
@@ -288,12 +288,51 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     }
     if (call.force_reset) reset = true;
 
+    // per-joint / per-foot history values used by the constraints and the rewards
+    float lastj = 0.f, llastj = 0.f, tauj = 0.f, lqdj = 0.f;
+    if ((pm & PHASE_REWARD) && jl) {
+        lastj = R.last_actions[env * A + lane]; llastj = R.llast_actions[env * A + lane];
+        tauj = R.torques[env * A + lane]; lqdj = R.last_dof_vel[env * A + lane];
+    }
     // ================================================================== compute_reward
     float my_sum = (lane < n_sums) ? R.episode_sums[env * n_sums + lane] : 0.f;
     float fat = fl ? R.feet_air_time[env * F + lane] : 0.f;
+    float cprob = 0.f;
+    if ((pm & PHASE_REWARD) && ti[TI_CAT]) {
+        // ============================================================== compute_constraints_cat (go2_cat.py:135-215)
+        // violations are 0/1 and ConstraintManager's running maximum never exceeds 1 (constraint_manager.py:43-64), so
+        // each constraint contributes max_p where violated; cstr_prob = max over the nine constraints.
+        const bool c_torque = __ballot_sync(B200_FULL_MASK, jl && fabsf(tauj) > tf[TF_TORQUE_LIMIT + lane]) != 0u;
+        const bool c_dofvel = __ballot_sync(B200_FULL_MASK, jl && fabsf(qdj) > tf[TF_DOF_VEL_LIMIT + lane]) != 0u;
+        const bool c_arate = __ballot_sync(B200_FULL_MASK, jl && __fdiv_rn(fabsf(__fsub_rn(actj, lastj)), dt) > tf[TF_CAT_ACTION_RATE]) != 0u;
+        float hs = 0.f;
+        for (int pt = lane; pt < P; pt += 32) hs += bp.z - (ti[TI_MEASURE_HEIGHTS] ? es[ES_MH + pt] : 0.f);
+        const bool c_height = warp_sum(hs) / (float)P < tf[TF_CAT_MIN_BASE_HEIGHT];
+        bool hit = false;
+        if (lane < ti[TI_N_PEN]) { const float *f = R.link_contact_forces + (env * L + ti[TI_PEN_LINKS + lane]) * 3; hit = norm3_rn(f[0], f[1], f[2]) > 10.0f; }
+        const bool c_coll = __ballot_sync(B200_FULL_MASK, hit) != 0u;
+        bool stumble = false;
+        if (fl) { const float *f = R.link_contact_forces + (env * L + ti[TI_FEET_LINKS + lane]) * 3; stumble = norm3_rn(f[0], f[1], f[2]) > __fmul_rn(4.0f, fabsf(f[2])); }
+        const bool c_stumble = __ballot_sync(B200_FULL_MASK, stumble) != 0u;
+        const bool below = __ballot_sync(B200_FULL_MASK, jl && qj < tf[TF_DOF_LIM_LO + lane]) != 0u;
+        const bool above = __ballot_sync(B200_FULL_MASK, jl && qj > tf[TF_DOF_LIM_HI + lane]) != 0u;
+        const bool c_dofpos = below && above;                                 // product of two any() as written (go2_cat.py:168-169)
+        const bool c_orient = grav.z > tf[TF_CAT_MAX_PROJ_GRAV];
+        const bool fast_here = __ballot_sync(B200_FULL_MASK, jl && fabsf(qdj) > 4.0f) != 0u;
+        const bool fast = ti[TI_CAT_GLOBAL_STANDSTILL] ? (R.global_flags[0] != 0) : fast_here;
+        const bool c_still = (norm3_rn(cmd0, cmd1, cmd2) < 0.1f) && fast;
+        const float sp = tf[TF_CAT_SOFT_P];
+        const bool cv[9] = {c_torque, c_dofvel, c_arate, c_height, c_coll, c_stumble, c_dofpos, c_orient, c_still};
+        const float cp[9] = {sp, sp, sp, sp, 1.f, 1.f, 1.f, 1.f, sp};
+        const int cbase = n_sums - 9;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            if (cv[k]) cprob = fmaxf(cprob, cp[k]);
+            if (lane == cbase + k && cv[k]) my_sum = __fadd_rn(my_sum, 1.0f);
+        }
+        if (lane == 0) { B.cstr_prob[env] = cprob; atomicAdd(B.stats + n_sums + 2, cprob); }
+    }
     if (pm & PHASE_REWARD) {
-        const float lastj = jl ? R.last_actions[env * A + lane] : 0.f, llastj = jl ? R.llast_actions[env * A + lane] : 0.f;
-        const float tauj = jl ? R.torques[env * A + lane] : 0.f, lqdj = jl ? R.last_dof_vel[env * A + lane] : 0.f;
         const float small_cmd = norm3_rn(cmd0, cmd1, cmd2) < 0.1f ? 1.f : 0.f;
         const float dqj = qj - q0j;
         float rew = 0.f;
@@ -371,7 +410,10 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             rew = __fadd_rn(rew, sr);
             if (lane == i) my_sum = __fadd_rn(my_sum, sr);
         }
-        if (ti[TI_ONLY_POSITIVE]) rew = fmaxf(rew, 0.f);
+        if (ti[TI_ONLY_POSITIVE]) {
+            if (ti[TI_CAT]) rew = __fmul_rn(rew, __fsub_rn(1.0f, cprob));      // go2_cat.py:229-231
+            rew = fmaxf(rew, 0.f);
+        }
         if (ti[TI_TERMINATION_COL] >= 0) {
             const float sr = __fmul_rn((reset && !time_out) ? 1.f : 0.f, tf[TF_REWARD_SCALE + RW_TERMINATION]);
             rew = __fadd_rn(rew, sr);
@@ -508,10 +550,11 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             nz[e] = v;
             B.obs_buf[env * NO + e] = fminf(fmaxf(v, -clipo), clipo);
         }
-        if (ti[TI_OBS_KIND] == 1) {   // go2_ts: critic frame, privileged obs, history stacks
+        if (ti[TI_OBS_KIND] >= 1) {   // go2_ts (1) / go2_cat (2): critic frame, privileged obs, history stacks
+            const bool cat = ti[TI_OBS_KIND] == 2;      // go2_cat.py:19-99: 3 more DR entries, no base_lin_vel, raw feet heights
             const int SC = ti[TI_SINGLE_CRITIC], NP = ti[TI_NUM_PRIV], NCS = ti[TI_CONTACT_STATES] ? ti[TI_N_CS] : 0;
             float *cr = es + ES_CRIT, *pv = es + ES_PRIV;
-            const int DRN = 7 + 2 * A;
+            const int DRN = (cat ? 10 : 7) + 2 * A, LIN = cat ? 0 : 3;
             for (int e = lane; e < NO; e += 32) cr[e] = ob[e];
             // domain_randomization_info (go2_ts.py:16-28)
             for (int e = lane; e < DRN; e += 32) {
@@ -521,26 +564,27 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 else if (e < 5) v = R.com_bias[env * 3 + e - 2];
                 else if (e < 7) v = e == 5 ? push_vel.x : push_vel.y;
                 else if (e < 7 + A) v = __fsub_rn(R.kp_scale[env * A + e - 7], tf[TF_KPS_OFFSET]);
-                else v = __fsub_rn(R.kd_scale[env * A + e - 7 - A], tf[TF_KDS_OFFSET]);
+                else if (e < 7 + 2 * A) v = __fsub_rn(R.kd_scale[env * A + e - 7 - A], tf[TF_KDS_OFFSET]);
+                else v = e == 7 + 2 * A ? B.joint_armature[env] : (e == 8 + 2 * A ? B.joint_friction[env] : B.joint_damping[env]);
                 cr[NO + e] = v; pv[e] = v;
             }
-            if (lane < 3) {
+            if (lane < LIN) {
                 const float v = __fmul_rn(comp3(lin_b, lane), tf[TF_OS_LIN_VEL]);
                 cr[NO + DRN + lane] = v; pv[DRN + 12 * F + lane] = v;
             }
             for (int e = lane; e < NCS; e += 32) {
                 const float v = es[ES_LCS + e];
-                cr[NO + DRN + 3 + e] = v; pv[DRN + 12 * F + 3 + e] = v;
+                cr[NO + DRN + LIN + e] = v; pv[DRN + 12 * F + LIN + e] = v;
             }
             if (ti[TI_MEASURE_HEIGHTS]) {
                 for (int pt = lane; pt < P; pt += 32) {
                     const float d = __fsub_rn(__fsub_rn(bp.z, tf[TF_HEIGHT_OBS_OFFSET]), es[ES_MH + pt]);
-                    cr[NO + DRN + 3 + NCS + pt] = __fmul_rn(fminf(fmaxf(d, -1.0f), 1.0f), tf[TF_OS_HEIGHT]);
+                    cr[NO + DRN + LIN + NCS + pt] = __fmul_rn(fminf(fmaxf(d, -1.0f), 1.0f), tf[TF_OS_HEIGHT]);
                 }
             }
             for (int e = lane; e < 9 * F; e += 32) {
                 const float fz = R.feet_pos[(env * F + e / 9) * 3 + 2];
-                pv[DRN + e] = fminf(fmaxf(__fsub_rn(fz, es[ES_HAF + e]), -1.0f), 1.0f);
+                pv[DRN + e] = cat ? es[ES_HAF + e] : fminf(fmaxf(__fsub_rn(fz, es[ES_HAF + e]), -1.0f), 1.0f);
             }
             for (int e = lane; e < 3 * F; e += 32) pv[DRN + 9 * F + e] = es[ES_NV + e];
             __syncwarp();
@@ -565,6 +609,17 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 }
             }
         }
+    }
+    // Tasks that shift the history again at the end of post_physics_step (go2_cat.py:127-130): the dynamics
+    // kernel shifts once more at the start of the next step, so llast == last at reward time.
+    if (ti[TI_DOUBLE_SHIFT] && (pm & PHASE_OBSERVE)) {
+        const bool was_reset = (pm & PHASE_RESET) && reset;
+        if (jl) {
+            B.llast_actions[env * A + lane] = was_reset ? 0.f : lastj;
+            B.last_actions[env * A + lane] = actj;
+            B.last_dof_vel[env * A + lane] = qdj;
+        }
+        if (fl) { float *lv = B.last_feet_vel + (env * F + lane) * 3; lv[0] = fvel.x; lv[1] = fvel.y; lv[2] = fvel.z; }
     }
 }
 
@@ -592,11 +647,11 @@ env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, 
     const int HW = T.i[TI_FRAME_STACK] * T.i[TI_NUM_OBS], CW = T.i[TI_C_FRAME_STACK] * T.i[TI_SINGLE_CRITIC];
     const uint32_t hbytes = (uint32_t)(nwarps * HW * 4), cbytes = (uint32_t)(nwarps * CW * 4);
     const int A = T.i[TI_A], F = T.i[TI_F], L = T.i[TI_L];
-    const int NSUM = T.i[TI_N_REWARDS] + (T.i[TI_TERMINATION_COL] >= 0 ? 1 : 0);
+    const int NSUM = T.i[TI_N_SUMS];
     const bool full = !call.force_reset && (call.phase_mask & PHASE_ALL) == PHASE_ALL;
     // pass 1 (all threads, uniform): byte counts of every slab -> is the CTA stageable, how many bytes will arrive
     uint32_t total = hbytes + cbytes, off = 0;
-    bool ok = full && T.i[TI_OBS_KIND] == 1 && env0 + nwarps <= N && HW <= ENV_MAX_HIST_ROW && CW <= ENV_MAX_CRIT_ROW &&
+    bool ok = full && T.i[TI_OBS_KIND] >= 1 && env0 + nwarps <= N && HW <= ENV_MAX_HIST_ROW && CW <= ENV_MAX_CRIT_ROW &&
               B200_TMA_SIZE_OK(hbytes) && B200_TMA_SIZE_OK(cbytes);
 #define X_COUNT(field, type, k) { const uint32_t b_ = (uint32_t)(nwarps * (k) * sizeof(type)); ok = ok && B200_TMA_SIZE_OK(b_); total += b_; off += (b_ + 15u) & ~15u; }
     ENV_STAGED_INPUTS(X_COUNT, A, F, L, NSUM)
@@ -634,8 +689,9 @@ env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, 
 // the ring that follows the work area so that the host can hand out per-step values without any further launch.
 __global__ void stats_finalize_kernel(float *stats, int n_sums, float inv_episode_length_s, float inv_num_envs, int slot) {
     const int i = threadIdx.x;
-    float *ring = stats + (2 * n_sums + 4) + slot * (n_sums + 1);
+    float *ring = stats + (2 * n_sums + 4) + slot * (n_sums + 2);
     const float cnt = fmaxf(stats[n_sums], 1.0f);
     if (i < n_sums) ring[i] = stats[i] / cnt * inv_episode_length_s;
-    if (i == n_sums) ring[i] = stats[n_sums + 1] * inv_num_envs;
+    if (i == n_sums) ring[i] = stats[n_sums + 1] * inv_num_envs;            // mean terrain level
+    if (i == n_sums + 1) ring[i] = stats[n_sums + 2] * inv_num_envs;        // mean CaT termination probability
 }

@@ -35,7 +35,7 @@ class FusedLeggedEnv:
         self._b = sim._buf
         self.widths = spec.obs_widths(sim._model)
         self.num_obs = self.widths["obs"]
-        self.num_privileged_obs = self.widths["priv"] if spec.obs_kind == "go2_ts" else None
+        self.num_privileged_obs = self.widths["priv"] if spec.obs_kind in ("go2_ts", "go2_cat") else None
         self.num_actions = spec.num_actions
         self.num_history_obs = self.widths["hist"]
         self.num_critic_obs = self.widths["critic"]
@@ -46,7 +46,7 @@ class FusedLeggedEnv:
         self.command_ranges = dict(lin_vel_x=list(spec.cmd_lin_vel_x), lin_vel_y=list(spec.cmd_lin_vel_y),
                                    ang_vel_yaw=list(spec.cmd_ang_vel_yaw), heading=list(spec.cmd_heading))
         self.sum_names = spec.episode_sum_names()
-        self.reward_scales = {n: float(spec.reward_scales[n] * spec.dt) for n in self.sum_names}
+        self.reward_scales = {n: float(spec.reward_scales[n] * spec.dt) for n in self.sum_names if n in spec.reward_scales}
         self.extras = {}
         self._pending_curriculum = None
         self.init_done = True
@@ -60,6 +60,7 @@ class FusedLeggedEnv:
         self.last_actions, self.llast_actions = b["last_actions"], b["llast_actions"]
         self.feet_air_time, self.fail_buf = b["feet_air_time"], b["fail_buf"]
         self.episode_sums = {n: b["episode_sums"][:, i] for i, n in enumerate(self.sum_names)}
+        self.cstr_prob = b["cstr_prob"]
         self._extras_ring = self._build_extras_ring()
 
     # runners assign a fresh tensor to env.episode_length_buf (on_policy_runner.py:169); keep the bound storage
@@ -90,7 +91,7 @@ class FusedLeggedEnv:
         return self._returns()
 
     def _returns(self):
-        if self.spec.obs_kind == "go2_ts":
+        if self.spec.obs_kind in ("go2_ts", "go2_cat"):
             return (self.obs_buf, self.privileged_obs_buf, self.obs_history, self.critic_obs_buf, self.rew_buf,
                     self.reset_buf, self.extras)
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
@@ -99,10 +100,10 @@ class FusedLeggedEnv:
         """BaseTask.reset (base_task.py:60-64): reset_idx(all) then one zero-action step."""
         self.simulator.fused_reset_all(self.common_step_counter, self.command_ranges["lin_vel_x"])
         out = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
-        return out[:4] if self.spec.obs_kind == "go2_ts" else out[:2]
+        return out[:4] if self.spec.obs_kind in ("go2_ts", "go2_cat") else out[:2]
 
     def get_observations(self):
-        if self.spec.obs_kind == "go2_ts":
+        if self.spec.obs_kind in ("go2_ts", "go2_cat"):
             return self.obs_buf, self.privileged_obs_buf, self.obs_history, self.critic_obs_buf
         return self.obs_buf
 
@@ -118,10 +119,12 @@ class FusedLeggedEnv:
         base = 2 * max(n, 1) + 4
         ring = []
         for slot in range(STATS_RING):
-            row = stats[base + slot * (n + 1): base + (slot + 1) * (n + 1)]
+            row = stats[base + slot * (n + 2): base + (slot + 1) * (n + 2)]
             ep = {"rew_" + name: row[i] for i, name in enumerate(self.sum_names)}
             if self.spec.terrain_curriculum:
                 ep["terrain_level"] = row[n]
+            if self.spec.cat_enabled:
+                ep["cstr_probs"] = row[n + 1]               # go2_cat.py:101-104
             ring.append(ep)
         return ring
 

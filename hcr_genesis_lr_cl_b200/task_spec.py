@@ -39,7 +39,10 @@ REWARD_ID: Dict[str, int] = {n: i for i, n in enumerate(REWARD_TERMS)}
 NUM_REWARD_TERMS = len(REWARD_TERMS)
 
 #: observation layouts the fused kernel knows (per-task ``compute_observations``)
-OBS_KINDS = {"go2": 0, "go2_ts": 1}
+OBS_KINDS = {"go2": 0, "go2_ts": 1, "go2_cat": 2}
+
+CAT_CONSTRAINTS = ["torque", "dof_vel", "action_rate", "base_height", "collision", "feet_stumble", "dof_pos",
+                   "base_orientation", "stand_still"]      # order of ConstraintManager.add calls, go2_cat.py:197-208
 
 # Philox draw sites (see oracle/philox.py and csrc/philox.cuh)
 SITE_CMD_RESAMPLE, SITE_PUSH, SITE_LEVEL, SITE_CMD_RESET, SITE_DOF, SITE_ROOT, SITE_FRICTION, SITE_MASS, SITE_COM, \
@@ -160,6 +163,15 @@ class TaskSpec:
     terminate_after_contacts_on: List[str] = field(default_factory=list)
     obtain_link_contact_states: bool = False
     contact_state_link_names: List[str] = field(default_factory=lambda: ["thigh", "calf", "foot"])
+    # Constraints as Terminations (go2_cat_config.py:28-36, go2_cat.py:135-215)
+    cat_enabled: bool = False
+    cat_soft_p: float = 0.25
+    cat_action_rate: float = 100.0
+    cat_min_base_height: float = 0.25
+    cat_max_projected_gravity: float = -0.1
+    cat_stand_still_global: bool = True     # as shipped: [N]*[N,1] broadcast couples all envs; False = per env
+    double_shift_actions: bool = False      # go2_cat.py:127-130 shifts the action history a second time (R6)
+    dof_vel_limits: List[float] = field(default_factory=list)
     # engine knobs (no reference counterpart; DESIGN.md "physics formulation")
     pgs_iterations: int = 30          # sweep cap of the projected Gauss-Seidel contact solver
     pgs_tolerance: float = 1e-4       # stop when max|df| over a sweep <= tol * (1 + max|f|)
@@ -206,6 +218,8 @@ class TaskSpec:
         names = self.active_rewards()
         if self.reward_scales.get("termination", 0) != 0:
             names.append("termination")
+        if self.cat_enabled:                       # ConstraintManager.log_all appends these keys (constraint_manager.py:84-91)
+            names += ["cstr_" + c for c in CAT_CONSTRAINTS]
         return names
 
     def scaled_reward(self, name: str) -> np.float32:
@@ -228,6 +242,12 @@ class TaskSpec:
         feet, _, _, cs = self.link_groups(model)
         if self.obs_kind == "go2":
             return dict(obs=9 + 3 * A, priv=0, single_critic=0, hist=0, critic=0)
+        if self.obs_kind == "go2_cat":                      # go2_cat.py:19-99: DR info has 3 more entries, no base_lin_vel
+            single = 9 + 3 * A
+            dr = 10 + 2 * A
+            sc = single + dr + len(cs) + (self.num_height_points if self.measure_heights else 0)
+            priv = dr + 9 * len(feet) + 3 * len(feet) + len(cs)
+            return dict(obs=single, priv=priv, single_critic=sc, hist=self.frame_stack * single, critic=self.c_frame_stack * sc)
         if self.obs_kind == "go2_ts":
             single = 9 + 3 * A
             dr = 7 + 2 * A
@@ -252,7 +272,7 @@ class TaskSpec:
     @classmethod
     def from_reference_cfg(cls, cfg, task: str) -> "TaskSpec":
         """Read a LeggedGym-Ex config object (nested classes/instances) into a TaskSpec."""
-        kinds = {"go2": "go2", "go2_ts": "go2_ts"}
+        kinds = {"go2": "go2", "go2_ts": "go2_ts", "go2_cat": "go2_cat"}
         if task not in kinds:
             raise ValueError(f"task {task!r} has no fused descriptor yet (supported: {sorted(kinds)})")
 
@@ -315,14 +335,21 @@ class TaskSpec:
             foot_clearance_target=r.foot_clearance_target, foot_height_offset=r.foot_height_offset,
             foot_clearance_tracking_sigma=r.foot_clearance_tracking_sigma,
             about_landing_threshold=getattr(r, "about_landing_threshold", 0.03),
-            feet_air_time_threshold=0.25 if task == "go2_ts" else 0.3,
-            foot_clearance_uses_terrain=(task == "go2_ts"),
+            feet_air_time_threshold=0.25 if task in ("go2_ts", "go2_cat") else 0.3,
+            foot_clearance_uses_terrain=task in ("go2_ts", "go2_cat"),
+            dof_vel_limits=list(getattr(a, "dof_vel_limits", [])),
             foot_name=a.foot_name, penalize_contacts_on=list(a.penalize_contacts_on),
             terminate_after_contacts_on=list(a.terminate_after_contacts_on),
             obtain_link_contact_states=a.obtain_link_contact_states,
             contact_state_link_names=list(a.contact_state_link_names),
             seed=getattr(cfg, "seed", 1),
         )
+        if task == "go2_cat":
+            cc = cfg.constraints
+            spec.cat_enabled = cc.enable == "cat"
+            spec.cat_soft_p, spec.cat_action_rate = cc.soft_p, cc.limits.action_rate
+            spec.cat_min_base_height, spec.cat_max_projected_gravity = cc.limits.min_base_height, cc.limits.max_projected_gravity
+            spec.double_shift_actions = True
         unknown = [k for k, v in spec.reward_scales.items() if v != 0 and k not in REWARD_ID]
         if unknown:
             raise ValueError(f"reward terms without a fused implementation: {unknown}")
@@ -337,7 +364,7 @@ def go2_spec(**over) -> TaskSpec:
     s = TaskSpec(
         task="go2", obs_kind="go2", robot="go2", dof_names=list(GO2_DOF_NAMES), num_obs=45, num_privileged_obs=None,
         default_dof_pos=list(_GO2_Q0), reset_dof_noise=[0.2, 0.4, 0.4] * 4, reset_root_vel=0.0,
-        mesh_type="plane", border_size=5.0, env_spacing=1.0,
+        dof_vel_limits=[30.1, 30.1, 15.7] * 4, mesh_type="plane", border_size=5.0, env_spacing=1.0,
         measured_points_x=[round(-0.8 + 0.1 * i, 1) for i in range(17)],
         measured_points_y=[round(-0.5 + 0.1 * i, 1) for i in range(11)],
         cmd_curriculum=True, max_curriculum=1.0, cmd_lin_vel_x=[-0.5, 0.5], cmd_lin_vel_y=[-1.0, 1.0],
@@ -363,7 +390,7 @@ def go2_ts_spec(**over) -> TaskSpec:
         task="go2_ts", obs_kind="go2_ts", robot="go2", dof_names=list(GO2_DOF_NAMES), num_obs=45, num_privileged_obs=94,
         frame_stack=20, c_frame_stack=5,
         default_dof_pos=list(_GO2_Q0), reset_dof_noise=[0.2, 0.4, 0.4] * 4, reset_root_vel=0.5,
-        env_spacing=0.5,
+        dof_vel_limits=[30.1, 30.1, 15.7] * 4, env_spacing=0.5,
         mesh_type="heightfield", border_size=20.0, terrain_length=8.0, terrain_width=8.0, num_rows=10, num_cols=10,
         terrain_curriculum=True, max_init_terrain_level=1, measure_heights=True,
         measured_points_x=list(pts), measured_points_y=list(pts), obtain_terrain_info_around_feet=True,
@@ -387,4 +414,19 @@ def go2_ts_spec(**over) -> TaskSpec:
     return s
 
 
-PRESETS = {"go2": go2_spec, "go2_ts": go2_ts_spec}
+def go2_cat_spec(**over) -> TaskSpec:
+    """`go2_cat` constraints-as-terminations task (BASELINE config C5; go2_cat_config.py:4-45 on top of Go2TSCfg)."""
+    s = go2_ts_spec()
+    s.task, s.obs_kind = "go2_cat", "go2_cat"
+    s.clip_actions = 10.0
+    s.base_height_target = 0.34
+    s.reward_scales.update(dof_pos_limits=0.0, collision=0.0, dof_pos_stand_still=0.0, lin_vel_z=-1.0, orientation=-0.5,
+                           hip_pos=-0.2, dof_close_to_default=-0.05, foot_clearance=0.2)
+    s.cat_enabled, s.double_shift_actions = True, True
+    s.dof_vel_limits = [30.1, 30.1, 15.7] * 4
+    for k, v in over.items():
+        setattr(s, k, v)
+    return s
+
+
+PRESETS = {"go2": go2_spec, "go2_ts": go2_ts_spec, "go2_cat": go2_cat_spec}

@@ -63,6 +63,8 @@ enum B200TaskF {
     TF_TRACKING_SIGMA, TF_BASE_HEIGHT_TARGET, TF_FOOT_CLEARANCE_TARGET, TF_FOOT_HEIGHT_OFFSET, TF_FOOT_CLEARANCE_SIGMA,
     TF_ABOUT_LANDING, TF_AIR_TIME_THRESHOLD,
     TF_GRAV, TF_TC, TF_DAMPRATIO, TF_D0, TF_DMAX, TF_WIDTH, TF_MID, TF_POWER, TF_TERRAIN_MU, TF_GEOM_MU, TF_PGS_TOL,
+    /* Constraints-as-Terminations (go2_cat.py:135-215, go2_cat_config.py:28-36) */
+    TF_CAT_SOFT_P, TF_CAT_ACTION_RATE, TF_CAT_MIN_BASE_HEIGHT, TF_CAT_MAX_PROJ_GRAV,
     TF_DEFAULT_DOF_POS,                                         /* [B200_MAX_JOINTS] */
     TF_RESET_DOF_NOISE = TF_DEFAULT_DOF_POS + B200_MAX_JOINTS,  /* [B200_MAX_JOINTS] */
     TF_DOF_LIM_LO = TF_RESET_DOF_NOISE + B200_MAX_JOINTS,       /* [B200_MAX_JOINTS] soft limits */
@@ -71,7 +73,9 @@ enum B200TaskF {
     TF_NOISE_VEC = TF_REWARD_SCALE + B200_MAX_REWARDS,          /* [B200_MAX_OBS] */
     TF_POINTS_X = TF_NOISE_VEC + B200_MAX_OBS,                  /* [B200_MAX_PTS_AXIS] */
     TF_POINTS_Y = TF_POINTS_X + B200_MAX_PTS_AXIS,              /* [B200_MAX_PTS_AXIS] */
-    TF_COUNT = TF_POINTS_Y + B200_MAX_PTS_AXIS
+    TF_TORQUE_LIMIT = TF_POINTS_Y + B200_MAX_PTS_AXIS,          /* [B200_MAX_JOINTS] URDF effort (simulator.torque_limits) */
+    TF_DOF_VEL_LIMIT = TF_TORQUE_LIMIT + B200_MAX_JOINTS,       /* [B200_MAX_JOINTS] cfg.asset.dof_vel_limits */
+    TF_COUNT = TF_DOF_VEL_LIMIT + B200_MAX_JOINTS
 };
 
 /* ---- task descriptor: int section ---- */
@@ -85,7 +89,11 @@ enum B200TaskI {
     TI_NUM_LEVELS, TI_NUM_TYPES, TI_HF_ROWS, TI_HF_COLS, TI_SEED_LO, TI_SEED_HI,
     TI_N_REWARDS, TI_TERMINATION_COL,                            /* column of "termination" in episode_sums or -1 */
     TI_N_PEN, TI_N_TERM, TI_N_CS,
-    TI_ENV_OFFSET,                                               /* global id of local env 0 (multi-GPU sharding; keys the RNG) */
+    TI_ENV_OFFSET,
+    TI_CAT,                                                      /* 1: compute CaT constraint probabilities (9 constraints) */
+    TI_CAT_GLOBAL_STANDSTILL,                                    /* 1: reproduce the [N,N] broadcast of go2_cat.py:177-178 */
+    TI_DOUBLE_SHIFT,                                             /* 1: tasks that shift the action history again after the step (R6) */
+    TI_N_SUMS,                                                   /* columns of episode_sums: rewards (+termination) (+9 cstr_*) */                                               /* global id of local env 0 (multi-GPU sharding; keys the RNG) */
     TI_REWARD_IDS,                                               /* [B200_MAX_REWARDS] active term ids, evaluation order */
     TI_FEET_LINKS = TI_REWARD_IDS + B200_MAX_REWARDS,            /* [B200_MAX_FEET]  */
     TI_PEN_LINKS = TI_FEET_LINKS + B200_MAX_FEET,                /* [B200_MAX_LINKS] */
@@ -184,8 +192,11 @@ typedef struct B200Buffers {
     int32_t *height_cells;      /* [N,P,2] int32 cell indices of the scan (diagnostic, may be NULL) */
     float *stats;               /* [2*n_sums+4 + 32*(n_sums+1)] per-step reductions: [0,n_sums) sum over resetting envs of
                                    episode_sums, [n_sums] count of resets, [n_sums+1] sum of terrain levels (all envs);
-                                   then a ring of 32 slots [n_sums+1]: the extras["episode"] means of step % 32
-                                   (rew_* in episode-sum order, then the mean terrain level) */
+                                   [n_sums+2] sum of cstr_prob (all envs); then a ring of 32 slots [n_sums+2]: the
+                                   extras["episode"] means of step % 32 (rew_* in episode-sum order, mean terrain level,
+                                   mean cstr_prob) */
+    float *cstr_prob;           /* [N] CaT termination probability (Go2CaT.cstr_prob); unused (but bound) for other tasks */
+    int32_t *global_flags;      /* [4] int32: [0] any env with |dof_vel| > 4 after the physics step (CaT stand-still, R4) */
     float *contact_warm;        /* [N,48] contact-solver warm start carried between substeps and policy steps: 8 x (sphere id + 1,
                                    f_n, f_t1, f_t2) then 8 x (aux-row code + 1, f); zero = empty */
 } B200Buffers;

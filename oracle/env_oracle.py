@@ -157,9 +157,16 @@ class EnvOracle:
         self._sim_post(phys, o)
         self._callback(o)
         self._termination(o)
+        if self.spec.cat_enabled:
+            self._constraints_cat(o)
         self._reward(o)
         self._reset(o)
         self._observe(o)
+        if self.spec.double_shift_actions:               # go2_cat.py:127-130
+            st["llast_actions"][:] = st["last_actions"]
+            st["last_actions"][:] = st["actions"]
+            st["last_dof_vel"][:] = st["qd"]
+            st["last_feet_vel"][:] = st["feet_vel"]
         return o
 
     # ------------------------------------------------------------------ genesis_simulator.py:35-60
@@ -291,6 +298,39 @@ class EnvOracle:
         o["time_out_buf"] = st["episode_length"] > s.max_episode_length
         o["reset_buf"] = (st["fail_buf"] > s.fail_limit) | o["time_out_buf"]
 
+    # ------------------------------------------------------------------ go2_cat.py:135-215 + constraint_manager.py:23-71
+    def _constraints_cat(self, o):
+        s, st = self.spec, self.st
+        lf = o["link_contact_forces"]
+        tl = self.model.effort.astype(f32)[None, :]
+        vl = np.asarray(s.dof_vel_limits, f32)[None, :]
+        lim = self.dof_pos_limits
+        c = {}
+        c["torque"] = np.any(np.abs(o["torques"]) > tl, axis=1)
+        c["dof_vel"] = np.any(np.abs(o["dof_vel"]) > vl, axis=1)
+        c["action_rate"] = np.any((np.abs(st["actions"] - st["last_actions"]) / f32(s.dt)).astype(f32) > f32(s.cat_action_rate), axis=1)
+        c["base_height"] = np.mean(st["base_pos"][:, 2:3] - o["measured_heights"], axis=1, dtype=f32) < f32(s.cat_min_base_height)
+        c["collision"] = np.any(_norm3(lf[:, self.pen, :]) > f32(10.0), axis=1)
+        ff = lf[:, self.feet, :]
+        c["feet_stumble"] = np.any(_norm3(ff) > (f32(4) * np.abs(ff[:, :, 2])).astype(f32), axis=1)
+        c["dof_pos"] = np.any(o["dof_pos"] < lim[None, :, 0], axis=1) & np.any(o["dof_pos"] > lim[None, :, 1], axis=1)
+        c["base_orientation"] = o["projected_gravity"][:, 2] > f32(s.cat_max_projected_gravity)
+        fast = np.any(np.abs(o["dof_vel"]) > f32(4.0), axis=1)
+        still = _norm3(st["commands"][:, :3]) < f32(0.1)
+        # as shipped the product is an [N,N] broadcast: env i is flagged when it stands still and ANY env moves fast (R4)
+        c["stand_still"] = (still & fast.any()) if s.cat_stand_still_global else (still & fast)
+        soft = f32(s.cat_soft_p)
+        pmax = dict(torque=soft, dof_vel=soft, action_rate=soft, base_height=soft, collision=f32(1), feet_stumble=f32(1),
+                    dof_pos=f32(1), base_orientation=f32(1), stand_still=soft)
+        # violations are 0/1 and the running maximum never exceeds 1, so the probability is max_p wherever violated
+        prob = np.zeros(self.N, f32)
+        base = len(self.sum_names) - len(T.CAT_CONSTRAINTS)
+        for k, name in enumerate(T.CAT_CONSTRAINTS):
+            prob = np.maximum(prob, np.where(c[name], pmax[name], f32(0)))
+            st["episode_sums"][:, base + k] += c[name].astype(f32)
+        o["cstr"] = c
+        o["cstr_prob"] = prob
+
     # ------------------------------------------------------------------ legged_robot.py:150-168 + _reward_*
     def _reward(self, o):
         s, st = self.spec, self.st
@@ -362,11 +402,13 @@ class EnvOracle:
             rew = (rew + r).astype(f32)
             st["episode_sums"][:, i] += r
         if s.only_positive_rewards:
+            if s.cat_enabled:                                      # go2_cat.py:229-231
+                rew = (rew * (f32(1.0) - o["cstr_prob"])).astype(f32)
             rew = np.maximum(rew, f32(0))
         if s.reward_scales.get("termination", 0) != 0:
             r = ((o["reset_buf"] & ~o["time_out_buf"]).astype(f32) * s.scaled_reward("termination")).astype(f32)
             rew = (rew + r).astype(f32)
-            st["episode_sums"][:, len(self.sum_names) - 1] += r
+            st["episode_sums"][:, self.sum_names.index("termination")] += r
             terms["termination"] = r
         o["rew_buf"], o["reward_terms"] = rew, terms
 
@@ -459,12 +501,15 @@ class EnvOracle:
         if s.obs_kind == "go2":
             o["obs_buf"] = np.clip(obs, -c, c)
             return
-        dr = np.concatenate([
-            st["friction"] - f32((s.friction_range[0] + s.friction_range[1]) / 2), st["added_mass"], st["com_bias"],
-            st["rand_push_vels"][:, :2], st["kp_scale"] - f32((s.kp_range[0] + s.kp_range[1]) / 2),
-            st["kd_scale"] - f32((s.kd_range[0] + s.kd_range[1]) / 2)], axis=1).astype(f32)
+        dr = [st["friction"] - f32((s.friction_range[0] + s.friction_range[1]) / 2), st["added_mass"], st["com_bias"],
+              st["rand_push_vels"][:, :2], st["kp_scale"] - f32((s.kp_range[0] + s.kp_range[1]) / 2),
+              st["kd_scale"] - f32((s.kd_range[0] + s.kd_range[1]) / 2)]
+        cat = s.obs_kind == "go2_cat"
+        if cat:                                                    # go2_cat.py:40-42
+            dr += [st["joint_armature"], st["joint_friction"], st["joint_damping"]]
+        dr = np.concatenate(dr, axis=1).astype(f32)
         lin = (st["base_lin_vel"] * f32(s.obs_scale_lin_vel)).astype(f32)
-        parts = [clean, dr, lin]
+        parts = [clean, dr] if cat else [clean, dr, lin]
         if s.obtain_link_contact_states:
             parts.append(o["link_contact_states"])
         if s.measure_heights:
@@ -476,8 +521,11 @@ class EnvOracle:
         st["critic_hist"][:] = np.concatenate([st["critic_hist"][:, sc:], critic], axis=1)
         st["obs_hist"][:] = np.concatenate([st["obs_hist"][:, so:], obs], axis=1)
         fz = o["feet_pos"][:, :, 2:3]
-        priv = [dr, np.clip((fz - o["height_around_feet"]).reshape(self.N, -1), f32(-1), f32(1)),
-                o["normal_vector_around_feet"], lin]
+        if cat:                                                    # go2_cat.py:82-99: raw heights, no base_lin_vel
+            priv = [dr, o["height_around_feet"].reshape(self.N, -1), o["normal_vector_around_feet"]]
+        else:
+            priv = [dr, np.clip((fz - o["height_around_feet"]).reshape(self.N, -1), f32(-1), f32(1)),
+                    o["normal_vector_around_feet"], lin]
         if s.obtain_link_contact_states:
             priv.append(o["link_contact_states"])
         o["obs_buf"] = np.clip(obs, -c, c)

@@ -45,7 +45,7 @@ def test_library_is_the_cuda_path(built_library):
     assert all(hasattr(lib, s) for s in _cabi.EXPORTED_SYMBOLS)
 
 
-@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32"])
+@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32"])
 def test_env_kernel_matches_reference_golden(name):
     """Injected post-physics states from the reference run -> every output of the fused kernel."""
     g, s0 = load_golden(name)
@@ -62,6 +62,7 @@ def test_env_kernel_matches_reference_golden(name):
         a = torch.from_numpy(g["actions"][t]).cuda()
         sim.step(a)                                   # pre-step bookkeeping (+ our own physics, overwritten below)
         sim.load_state({PH[k]: v for k, v in phys_at(g, t).items()})
+        sim._buf["global_flags"][0] = int((np.abs(phys_at(g, t)["qd"]) > 4).any())   # what the dynamics kernel would leave (CaT R4)
         env.common_step_counter += 1
         sim.fused_post_step(env.common_step_counter, env.command_ranges["lin_vel_x"])
         st = sim.get_state()
@@ -147,10 +148,12 @@ def test_dynamics_kernel_matches_oracle(task):
             assert err.max() < tol * scale(r), f"{k}: abs err {err.max():.3e} (scale {scale(r):.2f})"
 
 
-def test_env_kernel_matches_numpy_oracle_seeded(golden):
+@pytest.mark.parametrize("task", ["go2_ts", "go2_cat"])
+def test_env_kernel_matches_numpy_oracle_seeded(task):
     """Seeded random states at N=512 through several fused steps vs the numpy restatement (all phases, with resets)."""
+    from hcr_genesis_lr_cl_b200 import task_spec as T
     from oracle.env_oracle import EnvOracle
-    _, _, spec, terrain = golden
+    spec, terrain = T.PRESETS[task](), load_terrain()
     N = 512
     st, model = _random_state(spec, N, terrain, seed=11)
     rng = np.random.default_rng(5)
@@ -194,6 +197,8 @@ def test_env_kernel_matches_numpy_oracle_seeded(golden):
         assert np.array_equal(out["episode_length"], eo.st["episode_length"])
         assert np.array_equal(out["fail_buf"], eo.st["fail_buf"])
         _close(out["rew_buf"], o["rew_buf"], what=f"step {t}: rew")
+        if spec.cat_enabled:
+            assert np.array_equal(out["cstr_prob"], o["cstr_prob"]), f"step {t}: cstr_prob"
         _close(out["obs_buf"], o["obs_buf"], what=f"step {t}: obs")
         _close(out["privileged_obs_buf"], o["privileged_obs_buf"], what=f"step {t}: priv")
         _close(out[f"obs_history{sim._parity}"], o["obs_history"], what=f"step {t}: obs_history")
@@ -206,8 +211,8 @@ def test_env_kernel_matches_numpy_oracle_seeded(golden):
             _close(out[k], eo.st[k], what=f"step {t}: {k}")
         if o["episode_means"] is not None:                                   # extras["episode"] of this step (device ring)
             n = len(eo.sum_names)
-            base = 2 * n + 4 + (env.common_step_counter % 32) * (n + 1)
-            ring = out["stats"][base:base + n + 1]
+            base = 2 * n + 4 + (env.common_step_counter % 32) * (n + 2)
+            ring = out["stats"][base:base + n + 2]
             for i, name in enumerate(eo.sum_names):
                 assert abs(ring[i] - o["episode_means"]["rew_" + name]) <= 1e-4 * abs(o["episode_means"]["rew_" + name]) + 1e-6, name
             assert abs(ring[n] - eo.st["terrain_levels"].mean()) < 1e-3

@@ -59,6 +59,7 @@ static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 static inline float atomicAdd(float *p, float v) { float o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
+static inline int atomicOr(int *p, int v) { int o = *p; *p = o | v; return o; }
 using std::max;
 using std::min;
 

@@ -173,8 +173,6 @@ def main():
     spec = T.TaskSpec.from_reference_cfg(cfg, args.task)
     spec.seed = args.seed
     sim = env.simulator
-    sum_names = list(env.episode_sums.keys())
-    assert sum_names == spec.episode_sum_names(), (sum_names, spec.episode_sum_names())
     N, A = env.num_envs, env.num_actions
     g = torch.Generator().manual_seed(1234)
     env.reset()
@@ -192,7 +190,15 @@ def main():
     rob.state[flip, 3:7] = np.array([0.0, 1.0, 0.0, 0.0])                          # upside down
     rob.state[flip, 2] += 0.3
     env.common_step_counter = spec.push_interval * 3 - args.steps // 2             # a push inside the window
+    # a few envs with a (near-)zero command: stand-still rewards / CaT stand-still constraint
+    from legged_gym.utils.math_utils import quat_apply
+    q_xyzw = torch.from_numpy(np.concatenate([rob.state[:, 4:7], rob.state[:, 3:4]], axis=1)).float()
+    fwd = quat_apply(q_xyzw, torch.tensor([[1.0, 0.0, 0.0]]).repeat(N, 1))
+    env.commands[3::8, :3] = 0.0
+    env.commands[3::8, 3] = torch.atan2(fwd[3::8, 1], fwd[3::8, 0])
     env.step(torch.zeros(N, A))                                                    # make API buffers consistent
+    sum_names = list(env.episode_sums.keys())                                      # CaT adds its cstr_* keys lazily
+    assert sum_names == spec.episode_sum_names(), (sum_names, spec.episode_sum_names())
     inj = Injector(env, spec.seed)
     inj.install()
 
@@ -244,9 +250,11 @@ def main():
                      normal_vector_around_feet=n(sim._normal_vector_around_feet))
         if spec.obtain_link_contact_states:
             o["link_contact_states"] = n(sim._link_contact_states)
+        if hasattr(env, "cstr_prob"):
+            o["cstr_prob"] = n(env.cstr_prob)
         if ret[1] is not None:
             o["privileged_obs_buf"] = n(ret[1])
-        if args.task == "go2_ts" and t in (args.steps // 2, args.steps - 1):
+        if hasattr(env, "obs_history") and t in (args.steps // 2, args.steps - 1):
             rec[f"hist{t}/obs_history"] = n(env.obs_history)
             rec[f"hist{t}/critic_obs_buf"] = n(env.critic_obs_buf)
         for k, v in o.items():
