@@ -125,7 +125,7 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     sf("TF_TRACKING_SIGMA", spec.tracking_sigma); sf("TF_BASE_HEIGHT_TARGET", spec.base_height_target)
     sf("TF_FOOT_CLEARANCE_TARGET", spec.foot_clearance_target); sf("TF_FOOT_HEIGHT_OFFSET", spec.foot_height_offset)
     sf("TF_FOOT_CLEARANCE_SIGMA", spec.foot_clearance_tracking_sigma); sf("TF_ABOUT_LANDING", spec.about_landing_threshold)
-    sf("TF_AIR_TIME_THRESHOLD", spec.feet_air_time_threshold)
+    sf("TF_AIR_TIME_THRESHOLD", spec.feet_air_time_threshold); sf("TF_FOOT_DISTANCE_THRESHOLD", spec.foot_distance_threshold)
     # physics formulation constants: MuJoCo-style soft constraints
     sf("TF_GRAV", 9.81); sf("TF_TC", 2 * spec.sim_dt); sf("TF_DAMPRATIO", 1.0)
     sf("TF_D0", 0.9); sf("TF_DMAX", 0.95); sf("TF_WIDTH", 0.001); sf("TF_MID", 0.5); sf("TF_POWER", 2.0)

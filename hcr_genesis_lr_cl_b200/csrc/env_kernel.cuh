@@ -377,6 +377,14 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             case RW_FEET_CONTACT_STAND_STILL: {
                 const float cnt = warp_sum((fl && ffz > 0.1f) ? 1.f : 0.f);
                 r = (cnt == (float)F ? 1.f : 0.f) * small_cmd; break; }
+            case RW_FEET_DISTANCE: {                              // tron1_pf.py:146-151 (feet 0 and 1)
+                const float x0 = __shfl_sync(B200_FULL_MASK, fpos.x, 0), y0 = __shfl_sync(B200_FULL_MASK, fpos.y, 0);
+                const float x1 = __shfl_sync(B200_FULL_MASK, fpos.x, 1), y1 = __shfl_sync(B200_FULL_MASK, fpos.y, 1);
+                const float dx = x0 - x1, dy = y0 - y1;
+                r = fmaxf(0.f, tf[TF_FOOT_DISTANCE_THRESHOLD] - sqrtf(dx * dx + dy * dy)); break; }
+            case RW_NO_FLY: {                                     // tron1_pf.py:153-156
+                const float cnt = warp_sum((fl && ffz > 0.1f) ? 1.f : 0.f);
+                r = cnt == 1.f ? 1.f : 0.f; break; }
             case RW_FOOT_ACC: {
                 float s = 0.f;
                 if (fl) { const float *lv = R.last_feet_vel + (env * F + lane) * 3;
@@ -550,7 +558,39 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             nz[e] = v;
             B.obs_buf[env * NO + e] = fminf(fmaxf(v, -clipo), clipo);
         }
-        if (ti[TI_OBS_KIND] >= 1) {   // go2_ts (1) / go2_cat (2): critic frame, privileged obs, history stacks
+        if (ti[TI_OBS_KIND] == 3) {   // tron1_pf.py:15-70: obs_buf = stack of noisy frames, privileged_obs_buf = stack of critic frames
+            const int SC = ti[TI_SINGLE_CRITIC];
+            float *cr = es + ES_CRIT;
+            const bool cleared = (pm & PHASE_RESET) && reset;
+            if (lane < 3) cr[lane] = fminf(fmaxf(__fmul_rn(comp3(lin_b, lane), tf[TF_OS_LIN_VEL]), -clipo), clipo);
+            for (int e = lane; e < NO; e += 32) { cr[3 + e] = fminf(fmaxf(ob[e], -clipo), clipo); nz[e] = fminf(fmaxf(nz[e], -clipo), clipo); }
+            if (jl) cr[3 + NO + lane] = cleared ? 0.f : lastj;
+            if (lane == 0) {
+                float *d = cr + 3 + NO + A;
+                d[0] = __fsub_rn(R.friction[env], tf[TF_FRICTION_OFFSET]); d[1] = R.added_mass[env];
+                d[2] = R.com_bias[env * 3]; d[3] = R.com_bias[env * 3 + 1]; d[4] = R.com_bias[env * 3 + 2];
+                d[5] = push_vel.x; d[6] = push_vel.y;
+            }
+            if (fl) cr[3 + NO + A + 7 + lane] = fat;
+            __syncwarp();
+            if (hrow != nullptr) {
+                smem_shift_append(hrow, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, lane);
+                smem_shift_append(crow, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, lane);
+            } else {
+                {
+                    const int W = ti[TI_FRAME_STACK] * NO, keepw = W - NO;
+                    shift_copy(B.obs_history[call.parity ^ 1] + (size_t)env * W, B.obs_history[call.parity] + (size_t)env * W + NO, keepw, cleared, lane);
+                    float *dst = B.obs_history[call.parity ^ 1] + (size_t)env * W;
+                    for (int e = lane; e < NO; e += 32) dst[keepw + e] = nz[e];
+                }
+                {
+                    const int W = ti[TI_C_FRAME_STACK] * SC, keepw = W - SC;
+                    shift_copy(B.critic_obs[call.parity ^ 1] + (size_t)env * W, B.critic_obs[call.parity] + (size_t)env * W + SC, keepw, cleared, lane);
+                    float *dst = B.critic_obs[call.parity ^ 1] + (size_t)env * W;
+                    for (int e = lane; e < SC; e += 32) dst[keepw + e] = cr[e];
+                }
+            }
+        } else if (ti[TI_OBS_KIND] >= 1) {   // go2_ts (1) / go2_cat (2): critic frame, privileged obs, history stacks
             const bool cat = ti[TI_OBS_KIND] == 2;      // go2_cat.py:19-99: 3 more DR entries, no base_lin_vel, raw feet heights
             const int SC = ti[TI_SINGLE_CRITIC], NP = ti[TI_NUM_PRIV], NCS = ti[TI_CONTACT_STATES] ? ti[TI_N_CS] : 0;
             float *cr = es + ES_CRIT, *pv = es + ES_PRIV;

@@ -34,8 +34,10 @@ class FusedLeggedEnv:
         sim = self.simulator
         self._b = sim._buf
         self.widths = spec.obs_widths(sim._model)
-        self.num_obs = self.widths["obs"]
-        self.num_privileged_obs = self.widths["priv"] if spec.obs_kind in ("go2_ts", "go2_cat") else None
+        self.stacked = spec.obs_kind == "tron1_pf"          # obs / privileged obs are the frame stacks themselves
+        self.num_obs = self.widths["hist"] if self.stacked else self.widths["obs"]
+        self.num_privileged_obs = self.widths["critic"] if self.stacked else (
+            self.widths["priv"] if spec.obs_kind in ("go2_ts", "go2_cat") else None)
         self.num_actions = spec.num_actions
         self.num_history_obs = self.widths["hist"]
         self.num_critic_obs = self.widths["critic"]
@@ -52,8 +54,10 @@ class FusedLeggedEnv:
         self.init_done = True
         # live views (same storage the kernels write)
         b = self._b
-        self.obs_buf, self.rew_buf = b["obs_buf"], b["rew_buf"]
-        self.privileged_obs_buf = b["privileged_obs_buf"] if self.num_privileged_obs is not None else None
+        self.rew_buf = b["rew_buf"]
+        if not self.stacked:
+            self.obs_buf = b["obs_buf"]
+            self.privileged_obs_buf = b["privileged_obs_buf"] if self.num_privileged_obs is not None else None
         self.reset_buf = b["reset_buf"].view(torch.bool)
         self.time_out_buf = b["time_out_buf"].view(torch.bool)
         self.commands, self.actions = b["commands"], b["actions"]
@@ -71,6 +75,14 @@ class FusedLeggedEnv:
     @episode_length_buf.setter
     def episode_length_buf(self, value):
         self._b["episode_length"].copy_(value.to(self._b["episode_length"].dtype))
+
+    # tron1_pf: LeggedRobot.step returns the stacks as obs_buf / privileged_obs_buf (tron1_pf.py:57-70)
+    def __getattr__(self, name):
+        if name == "obs_buf" and self.__dict__.get("stacked"):
+            return self.obs_history
+        if name == "privileged_obs_buf" and self.__dict__.get("stacked"):
+            return self.critic_obs_buf
+        raise AttributeError(name)
 
     @property
     def obs_history(self):

@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from .robot_model import GO2_DOF_NAMES, RobotModel, load_robot_model
+from .robot_model import GO2_DOF_NAMES, TRON1_PF_DOF_NAMES, RobotModel, load_robot_model
 
 # Reward terms, alphabetical: the reference evaluates `_reward_<name>` in the order of
 # class_to_dict(cfg.rewards.scales) == dir() order (legged_gym/utils/helpers.py:10-25,
@@ -31,15 +31,15 @@ from .robot_model import GO2_DOF_NAMES, RobotModel, load_robot_model
 REWARD_TERMS: List[str] = [
     "action_rate", "action_smoothness", "ang_vel_xy", "base_height", "collision", "dof_acc",
     "dof_close_to_default", "dof_pos_limits", "dof_pos_stand_still", "dof_power", "dof_vel",
-    "dof_vel_stand_still", "feet_air_time", "feet_contact_stand_still", "foot_acc", "foot_clearance",
-    "foot_landing_vel", "hip_pos", "keep_balance", "lin_vel_z", "orientation", "thigh_pos", "torques",
+    "dof_vel_stand_still", "feet_air_time", "feet_contact_stand_still", "feet_distance", "foot_acc", "foot_clearance",
+    "foot_landing_vel", "hip_pos", "keep_balance", "lin_vel_z", "no_fly", "orientation", "thigh_pos", "torques",
     "tracking_ang_vel", "tracking_lin_vel", "termination",
 ]
 REWARD_ID: Dict[str, int] = {n: i for i, n in enumerate(REWARD_TERMS)}
 NUM_REWARD_TERMS = len(REWARD_TERMS)
 
 #: observation layouts the fused kernel knows (per-task ``compute_observations``)
-OBS_KINDS = {"go2": 0, "go2_ts": 1, "go2_cat": 2}
+OBS_KINDS = {"go2": 0, "go2_ts": 1, "go2_cat": 2, "tron1_pf": 3}
 
 CAT_CONSTRAINTS = ["torque", "dof_vel", "action_rate", "base_height", "collision", "feet_stumble", "dof_pos",
                    "base_orientation", "stand_still"]      # order of ConstraintManager.add calls, go2_cat.py:197-208
@@ -155,6 +155,7 @@ class TaskSpec:
     foot_height_offset: float = 0.0
     foot_clearance_tracking_sigma: float = 0.01
     about_landing_threshold: float = 0.03
+    foot_distance_threshold: float = 0.115  # tron1_pf_config.py:64
     feet_air_time_threshold: float = 0.3   # legged_robot.py:552; 0.25 in go2_ts.py:142
     foot_clearance_uses_terrain: bool = False  # go2_ts.py:147-161 subtracts mean(height_around_feet)
     # link name groups (substring rules, genesis_simulator.py:333-363)
@@ -242,6 +243,10 @@ class TaskSpec:
         feet, _, _, cs = self.link_groups(model)
         if self.obs_kind == "go2":
             return dict(obs=9 + 3 * A, priv=0, single_critic=0, hist=0, critic=0)
+        if self.obs_kind == "tron1_pf":                     # tron1_pf.py:15-70: both outputs are frame stacks
+            single = 9 + 3 * A
+            sc = 3 + single + A + 7 + len(feet)
+            return dict(obs=single, priv=0, single_critic=sc, hist=self.frame_stack * single, critic=self.c_frame_stack * sc)
         if self.obs_kind == "go2_cat":                      # go2_cat.py:19-99: DR info has 3 more entries, no base_lin_vel
             single = 9 + 3 * A
             dr = 10 + 2 * A
@@ -272,7 +277,7 @@ class TaskSpec:
     @classmethod
     def from_reference_cfg(cls, cfg, task: str) -> "TaskSpec":
         """Read a LeggedGym-Ex config object (nested classes/instances) into a TaskSpec."""
-        kinds = {"go2": "go2", "go2_ts": "go2_ts", "go2_cat": "go2_cat"}
+        kinds = {"go2": "go2", "go2_ts": "go2_ts", "go2_cat": "go2_cat", "tron1_pf": "tron1_pf"}
         if task not in kinds:
             raise ValueError(f"task {task!r} has no fused descriptor yet (supported: {sorted(kinds)})")
 
@@ -288,6 +293,8 @@ class TaskSpec:
             raise ValueError("per-joint PD gains are not supported by the fused descriptor yet")
         robot = {"go2": "go2", "PF_TRON1A": "tron1_pf"}[next(k for k in ("go2", "PF_TRON1A") if k in a.file)]
         hip_thigh_calf = [0.2, 0.4, 0.4] * (len(a.dof_names) // 3)   # go2.py:30-35 / go2_ts.py:86-91
+        if task == "tron1_pf":
+            hip_thigh_calf = [0.2] * len(a.dof_names)                  # base class, legged_robot.py:279-280
         spec = cls(
             task=task, obs_kind=kinds[task], robot=robot, dof_names=list(a.dof_names),
             num_obs=e.num_observations, num_privileged_obs=e.num_privileged_obs,
@@ -335,7 +342,8 @@ class TaskSpec:
             foot_clearance_target=r.foot_clearance_target, foot_height_offset=r.foot_height_offset,
             foot_clearance_tracking_sigma=r.foot_clearance_tracking_sigma,
             about_landing_threshold=getattr(r, "about_landing_threshold", 0.03),
-            feet_air_time_threshold=0.25 if task in ("go2_ts", "go2_cat") else 0.3,
+            feet_air_time_threshold=0.25 if task in ("go2_ts", "go2_cat", "tron1_pf") else 0.3,
+            foot_distance_threshold=getattr(r, "foot_distance_threshold", 0.115),
             foot_clearance_uses_terrain=task in ("go2_ts", "go2_cat"),
             dof_vel_limits=list(getattr(a, "dof_vel_limits", [])),
             foot_name=a.foot_name, penalize_contacts_on=list(a.penalize_contacts_on),
@@ -429,4 +437,31 @@ def go2_cat_spec(**over) -> TaskSpec:
     return s
 
 
-PRESETS = {"go2": go2_spec, "go2_ts": go2_ts_spec, "go2_cat": go2_cat_spec}
+def tron1_pf_spec(**over) -> TaskSpec:
+    """`tron1_pf` point-foot biped, flat terrain (tron1_pf_config.py:4-117): 2 chains x 3 joints, frame-stacked obs."""
+    s = TaskSpec(
+        task="tron1_pf", obs_kind="tron1_pf", robot="tron1_pf", dof_names=list(TRON1_PF_DOF_NAMES), num_obs=135,
+        num_privileged_obs=225, frame_stack=5, c_frame_stack=5, kp=42.0, kd=2.5, action_scale=0.25,
+        default_dof_pos=[0.0] * 6, reset_dof_noise=[0.2] * 6, reset_root_vel=0.5, init_pos=[0.0, 0.0, 0.8],
+        mesh_type="plane", border_size=5.0, env_spacing=2.0,
+        measured_points_x=[round(-0.8 + 0.1 * i, 1) for i in range(17)],
+        measured_points_y=[round(-0.5 + 0.1 * i, 1) for i in range(11)],
+        cmd_curriculum=True, max_curriculum=1.0, cmd_lin_vel_x=[-0.5, 0.5], cmd_lin_vel_y=[-0.6, 0.6],
+        friction_range=[0.5, 1.25], push_interval_s=10.0,
+        com_pos_x_range=[-0.03, 0.03], com_pos_y_range=[-0.03, 0.03], com_pos_z_range=[-0.03, 0.03],
+        reward_scales=dict(termination=-0.0, tracking_lin_vel=1.0, tracking_ang_vel=0.5, lin_vel_z=-0.5, ang_vel_xy=-0.05,
+                           orientation=-3.0, torques=-2.0e-5, dof_vel=-5.0e-4, dof_acc=-2.0e-7, base_height=-2.0,
+                           feet_air_time=1.0, collision=-1.0, feet_stumble=-0.0, action_rate=-0.01, dof_pos_stand_still=-0.0,
+                           keep_balance=1.0, dof_pos_limits=-2.0, feet_distance=-100.0, action_smoothness=-0.01,
+                           foot_clearance=0.5, no_fly=0.5, foot_landing_vel=-0.15),
+        only_positive_rewards=False, soft_dof_pos_limit=0.9, base_height_target=0.68, foot_clearance_target=0.07,
+        foot_height_offset=0.032, about_landing_threshold=0.1, foot_distance_threshold=0.115,
+        penalize_contacts_on=["knee", "hip"], terminate_after_contacts_on=["base", "abad"],
+        feet_air_time_threshold=0.25, foot_clearance_uses_terrain=False,
+    )
+    for k, v in over.items():
+        setattr(s, k, v)
+    return s
+
+
+PRESETS = {"go2": go2_spec, "go2_ts": go2_ts_spec, "go2_cat": go2_cat_spec, "tron1_pf": tron1_pf_spec}

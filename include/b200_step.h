@@ -42,7 +42,7 @@ extern "C" {
 #define B200_KMAX 8        /* contacts kept per env                        */
 #define B200_AUXMAX 8      /* joint-limit + frictionloss constraint rows   */
 #define B200_RMAX 32       /* constraint rows = 3*KMAX + AUXMAX = one warp */
-#define B200_MAX_REWARDS 26
+#define B200_MAX_REWARDS 28
 #define B200_MAX_OBS 48
 #define B200_MAX_PTS_AXIS 17
 #define B200_BODY_STRIDE 20
@@ -61,7 +61,7 @@ enum B200TaskF {
     TF_JDA_LO, TF_JDA_SPAN, TF_MAX_PUSH, TF_FRICTION_OFFSET, TF_KPS_OFFSET, TF_KDS_OFFSET,
     TF_OS_LIN_VEL, TF_OS_ANG_VEL, TF_OS_DOF_POS, TF_OS_DOF_VEL, TF_OS_HEIGHT, TF_HEIGHT_OBS_OFFSET,
     TF_TRACKING_SIGMA, TF_BASE_HEIGHT_TARGET, TF_FOOT_CLEARANCE_TARGET, TF_FOOT_HEIGHT_OFFSET, TF_FOOT_CLEARANCE_SIGMA,
-    TF_ABOUT_LANDING, TF_AIR_TIME_THRESHOLD,
+    TF_ABOUT_LANDING, TF_AIR_TIME_THRESHOLD, TF_FOOT_DISTANCE_THRESHOLD,
     TF_GRAV, TF_TC, TF_DAMPRATIO, TF_D0, TF_DMAX, TF_WIDTH, TF_MID, TF_POWER, TF_TERRAIN_MU, TF_GEOM_MU, TF_PGS_TOL,
     /* Constraints-as-Terminations (go2_cat.py:135-215, go2_cat_config.py:28-36) */
     TF_CAT_SOFT_P, TF_CAT_ACTION_RATE, TF_CAT_MIN_BASE_HEIGHT, TF_CAT_MAX_PROJ_GRAV,
@@ -106,8 +106,8 @@ enum B200TaskI {
 enum B200Reward {
     RW_ACTION_RATE, RW_ACTION_SMOOTHNESS, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_COLLISION, RW_DOF_ACC,
     RW_DOF_CLOSE_TO_DEFAULT, RW_DOF_POS_LIMITS, RW_DOF_POS_STAND_STILL, RW_DOF_POWER, RW_DOF_VEL,
-    RW_DOF_VEL_STAND_STILL, RW_FEET_AIR_TIME, RW_FEET_CONTACT_STAND_STILL, RW_FOOT_ACC, RW_FOOT_CLEARANCE,
-    RW_FOOT_LANDING_VEL, RW_HIP_POS, RW_KEEP_BALANCE, RW_LIN_VEL_Z, RW_ORIENTATION, RW_THIGH_POS, RW_TORQUES,
+    RW_DOF_VEL_STAND_STILL, RW_FEET_AIR_TIME, RW_FEET_CONTACT_STAND_STILL, RW_FEET_DISTANCE, RW_FOOT_ACC, RW_FOOT_CLEARANCE,
+    RW_FOOT_LANDING_VEL, RW_HIP_POS, RW_KEEP_BALANCE, RW_LIN_VEL_Z, RW_NO_FLY, RW_ORIENTATION, RW_THIGH_POS, RW_TORQUES,
     RW_TRACKING_ANG_VEL, RW_TRACKING_LIN_VEL, RW_TERMINATION, RW_COUNT
 };
 

@@ -383,6 +383,9 @@ class EnvOracle:
             "dof_vel_stand_still": lambda: ssum(np.abs(o["dof_vel"])) * small_cmd,
             "feet_air_time": feet_air_time,
             "feet_contact_stand_still": lambda: (ssum((lf[:, self.feet, 2] > f32(0.1)).astype(f32)) == self.F).astype(f32) * small_cmd,
+            "feet_distance": lambda: np.maximum(f32(0), f32(s.foot_distance_threshold) - np.sqrt(np.sum(np.square(
+                o["feet_pos"][:, 0, :2] - o["feet_pos"][:, 1, :2]), axis=-1, dtype=f32)).astype(f32)),      # tron1_pf.py:146-151
+            "no_fly": lambda: (ssum((lf[:, self.feet, 2] > f32(0.1)).astype(f32)) == 1).astype(f32),       # tron1_pf.py:153-156
             "foot_acc": lambda: np.sum(np.square((o["feet_vel"] - st["last_feet_vel"]) / dt), axis=(1, 2), dtype=f32),
             "foot_clearance": foot_clearance,
             "foot_landing_vel": foot_landing_vel,
@@ -498,6 +501,17 @@ class EnvOracle:
             un = self.u(T.SITE_OBS_NOISE, np.arange(obs.shape[1]))
             obs = (obs + ((f32(2) * un - f32(1)).astype(f32) * self.noise_vec[None, :]).astype(f32)).astype(f32)
         c = f32(s.clip_observations)
+        if s.obs_kind == "tron1_pf":                               # tron1_pf.py:15-70
+            lin = (st["base_lin_vel"] * f32(s.obs_scale_lin_vel)).astype(f32)
+            priv = np.concatenate([lin, clean, st["last_actions"], st["friction"] - f32((s.friction_range[0] + s.friction_range[1]) / 2),
+                                   st["added_mass"], st["com_bias"], st["rand_push_vels"][:, :2], st["feet_air_time"]], axis=1).astype(f32)
+            sc, so = self.widths["single_critic"], self.widths["obs"]
+            st["critic_hist"][:] = np.concatenate([st["critic_hist"][:, sc:], priv], axis=1)
+            st["obs_hist"][:] = np.concatenate([st["obs_hist"][:, so:], obs], axis=1)
+            o["obs_buf"] = np.clip(st["obs_hist"], -c, c)
+            o["privileged_obs_buf"] = np.clip(st["critic_hist"], -c, c)
+            o["obs_history"], o["critic_obs_buf"] = o["obs_buf"], o["privileged_obs_buf"]
+            return
         if s.obs_kind == "go2":
             o["obs_buf"] = np.clip(obs, -c, c)
             return

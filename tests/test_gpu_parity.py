@@ -45,7 +45,7 @@ def test_library_is_the_cuda_path(built_library):
     assert all(hasattr(lib, s) for s in _cabi.EXPORTED_SYMBOLS)
 
 
-@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32"])
+@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32"])
 def test_env_kernel_matches_reference_golden(name):
     """Injected post-physics states from the reference run -> every output of the fused kernel."""
     g, s0 = load_golden(name)
@@ -68,6 +68,8 @@ def test_env_kernel_matches_reference_golden(name):
         st = sim.get_state()
         ref = out_at(g, t)
         mine = dict(st, actions_buf=st["actions"], end_q=st["dof_pos"], end_qd=st["dof_vel"])
+        if spec.obs_kind == "tron1_pf":                      # the returned obs / privileged obs are the frame stacks
+            mine["obs_buf"], mine["privileged_obs_buf"] = st[f"obs_history{sim._parity}"], st[f"critic_obs{sim._parity}"]
         for k, r in ref.items():
             if k not in mine or k in ("end_state",):
                 continue
@@ -116,7 +118,7 @@ def _random_state(spec, N, terrain, seed):
     return st, model
 
 
-@pytest.mark.parametrize("task", ["go2_ts", "go2"])
+@pytest.mark.parametrize("task", ["go2_ts", "go2", "tron1_pf"])
 def test_dynamics_kernel_matches_oracle(task):
     """One policy step (4 substeps) of the warp-per-env kernel vs the fp32 C oracle on seeded states."""
     from emu_util import oracle_params, oracle_policy_step

@@ -14,7 +14,7 @@ PH = dict(base_pos="base_pos", base_quat_wxyz="base_quat_wxyz", base_lin_w="base
 INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels")
 
 
-@pytest.mark.parametrize("name,steps", [("go2_ts_n32", 5), ("go2_n32", 4), ("go2_cat_n32", 5)])
+@pytest.mark.parametrize("name,steps", [("go2_ts_n32", 5), ("go2_n32", 4), ("go2_cat_n32", 5), ("tron1_pf_n32", 5)])
 def test_emulated_env_kernel_matches_reference_golden(name, steps):
     g, s0 = load_golden(name)
     spec = spec_for(g)
@@ -35,6 +35,8 @@ def test_emulated_env_kernel_matches_reference_golden(name, steps):
         sim.env_post_step()
         ref = out_at(g, t)
         mine = dict(B, actions_buf=B["actions"], end_q=B["dof_pos"], end_qd=B["dof_vel"])
+        if spec.obs_kind == "tron1_pf":                      # the returned obs / privileged obs are the frame stacks
+            mine["obs_buf"], mine["privileged_obs_buf"] = sim.obs_history, sim.critic_obs
         for k, r in ref.items():
             if k not in mine or k == "end_state":
                 continue

@@ -73,7 +73,7 @@ def test_presets_match_reference_configs():
     if not reference_available():
         pytest.skip("reference tree not present (GPU box)")
     reg = import_reference()
-    for task in ("go2", "go2_ts", "go2_cat"):
+    for task in ("go2", "go2_ts", "go2_cat", "tron1_pf"):
         cfg, _ = reg.get_cfgs(task)
         a, b = dataclasses.asdict(T.TaskSpec.from_reference_cfg(cfg, task)), dataclasses.asdict(T.PRESETS[task]())
         ra, rb = a.pop("reward_scales"), b.pop("reward_scales")

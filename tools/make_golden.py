@@ -52,6 +52,12 @@ class Injector:
             cols = 3 * np.arange(4) + self.call            # go2_ts.py:86-91: hips, thighs, calves
         elif site == T.SITE_KP:
             site, cols = (T.SITE_KP if self.call == 0 else T.SITE_KD), np.arange(ncol)
+        elif site == T.SITE_ROOT:                      # fixed slots: xy -> 0,1; lin vel -> 2..4; ang vel -> 5..7 (legged_robot.py:283-298)
+            if ncol == 2:
+                cols = np.arange(2)
+            else:
+                cols = 2 + 3 * self.col + np.arange(3)
+                self.col += 1
         else:
             cols = self.col + np.arange(ncol)
             self.col += ncol
@@ -188,7 +194,7 @@ def main():
     rob = sim._robot
     flip = np.arange(2, N, 8)
     rob.state[flip, 3:7] = np.array([0.0, 1.0, 0.0, 0.0])                          # upside down
-    rob.state[flip, 2] += 0.3
+    rob.state[flip, 2] += 0.3 if A == 12 else 0.8
     env.common_step_counter = spec.push_interval * 3 - args.steps // 2             # a push inside the window
     # a few envs with a (near-)zero command: stand-still rewards / CaT stand-still constraint
     from legged_gym.utils.math_utils import quat_apply
