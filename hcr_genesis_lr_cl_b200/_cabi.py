@@ -130,6 +130,17 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     sf("TF_GRAV", 9.81); sf("TF_TC", 2 * spec.sim_dt); sf("TF_DAMPRATIO", 1.0)
     sf("TF_D0", 0.9); sf("TF_DMAX", 0.95); sf("TF_WIDTH", 0.001); sf("TF_MID", 0.5); sf("TF_POWER", 2.0)
     sf("TF_TERRAIN_MU", spec.static_friction); sf("TF_GEOM_MU", 1.0); sf("TF_PGS_TOL", spec.pgs_tolerance)
+    sf("TF_GAIT_PERIOD", spec.gait_period); sf("TF_GAIT_THETA_LEFT", spec.gait_theta_left)
+    sf("TF_GAIT_THETA_RIGHT", np.float32(spec.gait_theta_right - spec.gait_theta_left))      # stored as the offset right - left
+    sf("TF_GAIT_B_SWING", np.float32(spec.gait_b_swing * 2) * np.float32(np.pi))            # b_swing * 2 * torch.pi in fp32
+    sf("TF_BASE_HEIGHT_SIGMA", spec.base_height_tracking_sigma); sf("TF_SIT_PERCENT", spec.sit_init_percent)
+    for k in range(3):
+        sf("TF_SIT_POS", spec.sit_pos[k], k)
+    half = np.float32(spec.sit_pitch_angle) * np.float32(0.5)
+    for k, v in enumerate((0.0, np.sin(half), 0.0, np.cos(half))):                          # quat_from_euler_xyz(0, pitch, 0), xyzw
+        sf("TF_SIT_QUAT", v, k)
+    for j, v in enumerate(spec.sit_joint_angles):
+        sf("TF_SIT_DOF_POS", v, j)
     sf("TF_CAT_SOFT_P", spec.cat_soft_p); sf("TF_CAT_ACTION_RATE", spec.cat_action_rate)
     sf("TF_CAT_MIN_BASE_HEIGHT", spec.cat_min_base_height); sf("TF_CAT_MAX_PROJ_GRAV", spec.cat_max_projected_gravity)
     lim = soft_dof_limits(spec, model)
@@ -178,6 +189,7 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     si("TI_N_PEN", len(pen)); si("TI_N_TERM", len(term)); si("TI_N_CS", len(cs)); si("TI_ENV_OFFSET", env_offset)
     si("TI_CAT", spec.cat_enabled); si("TI_CAT_GLOBAL_STANDSTILL", spec.cat_stand_still_global)
     si("TI_DOUBLE_SHIFT", spec.double_shift_actions); si("TI_N_SUMS", len(spec.episode_sum_names()))
+    si("TI_GAIT", spec.gait_enabled); si("TI_CLEARANCE_MODE", spec.foot_clearance_mode)
     for k, v in enumerate(feet):
         si("TI_FEET_LINKS", v, k)
     for k, v in enumerate(pen):
@@ -223,7 +235,7 @@ def buffer_shapes(spec: T.TaskSpec, model: RobotModel, N: int) -> "OrderedDict[s
         obs_buf=(N, w["obs"]), privileged_obs_buf=(N, max(w["priv"], 1)),
         obs_history0=(N, max(w["hist"], 1)), obs_history1=(N, max(w["hist"], 1)),
         critic_obs0=(N, max(w["critic"], 1)), critic_obs1=(N, max(w["critic"], 1)),
-        rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), height_cells=(N, P, 2), stats=(stats_base(nsum) + STATS_RING * (max(nsum, 1) + 2),), cstr_prob=(N,), global_flags=(4,),
+        rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), gait_state=(N, 8), height_cells=(N, P, 2), stats=(stats_base(nsum) + STATS_RING * (max(nsum, 1) + 2),), cstr_prob=(N,), global_flags=(4,),
     )
     return OrderedDict((name, (shp[name], _NP[ct])) for name, ct in BUFFER_FIELDS)
 
@@ -266,6 +278,8 @@ def load_library() -> ctypes.CDLL:
     lib.b200_dynamics_step.restype = ctypes.c_int
     lib.b200_env_post_step.argtypes = [vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, vp]
     lib.b200_env_post_step.restype = ctypes.c_int
+    lib.b200_set_step_flags.argtypes = [vp, ctypes.c_int]
+    lib.b200_set_step_flags.restype = ctypes.c_int
     lib.b200_reset_all.argtypes = [vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, vp]
     lib.b200_reset_all.restype = ctypes.c_int
     lib.b200_kernel_info.argtypes = [vp, ctypes.c_char_p, ip, ip, ip, ip]
@@ -279,4 +293,4 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = ["b200_create", "b200_destroy", "b200_set_terrain", "b200_bind_buffers", "b200_dynamics_step",
-                    "b200_env_post_step", "b200_reset_all", "b200_kernel_info", "b200_launch_count", "b200_last_error"]
+                    "b200_env_post_step", "b200_set_step_flags", "b200_reset_all", "b200_kernel_info", "b200_launch_count", "b200_last_error"]

@@ -25,6 +25,7 @@ struct B200Handle {
     int *d_model_i = nullptr;
     long long launches = 0;
     int dyn_smem = 0, env_smem = 0;
+    int sit_pose = 0;
 };
 
 extern "C" {
@@ -53,7 +54,9 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
     h->model.body = h->d_model_f; h->model.link_off = h->d_model_f + nb * B200_BODY_STRIDE; h->model.sph = h->model.link_off + 3 * L;
     h->model.link_body = h->d_model_i + 8; h->model.sph_body = h->model.link_body + L; h->model.sph_link = h->model.sph_body + NS;
     h->dyn_smem = dyn_smem_bytes(DYN_WARPS_PER_BLOCK);
-    h->env_smem = env_smem_bytes(ENV_WARPS_PER_BLOCK);
+    h->env_smem = env_smem_bytes(ENV_WARPS_PER_BLOCK, ti[TI_OBS_KIND] >= 1 ? ti[TI_FRAME_STACK] * ti[TI_NUM_OBS] : 0,
+                                 ti[TI_OBS_KIND] >= 1 ? ti[TI_C_FRAME_STACK] * ti[TI_SINGLE_CRITIC] : 0);
+    if (h->env_smem > 48 * 1024) CK(cudaFuncSetAttribute(env_post_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->env_smem));
     CK(cudaFuncSetAttribute(dynamics_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
     CK(cudaFuncSetAttribute(dynamics_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
     *out = h;
@@ -114,7 +117,7 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     const int n_sums = h->task.i[TI_N_SUMS];
     cudaStream_t s = (cudaStream_t)stream;
     if (mask & PHASE_RESET) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 3), s));
-    EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.parity = parity & 1; call.phase_mask = mask; call.force_reset = force;
+    EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.parity = parity & 1; call.phase_mask = mask; call.force_reset = force; call.sit_pose = h->sit_pose;
     const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
     env_post_step_kernel<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call);
     h->launches++;
@@ -131,6 +134,12 @@ int b200_env_post_step(B200Handle *h, long long step, float lo, float span, int 
     if (check_ready(h, "b200_env_post_step")) return 1;
     if ((mask & PHASE_ALL) == 0) return fail("b200_env_post_step: empty phase mask");
     return launch_env(h, step, lo, span, parity, mask & PHASE_ALL, 0, stream);
+}
+
+int b200_set_step_flags(B200Handle *h, int sit_pose) {
+    if (!h) return fail("b200_set_step_flags: null handle");
+    h->sit_pose = sit_pose ? 1 : 0;
+    return 0;
 }
 
 int b200_reset_all(B200Handle *h, long long step, float lo, float span, int parity, void *stream) {

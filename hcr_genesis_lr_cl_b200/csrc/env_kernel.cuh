@@ -37,8 +37,6 @@
 #define ENV_IN_WORDS 288           // staged per-env input rows (all small state tensors), words per env
 // CTA-level staging of the two history stacks (TMA bulk copies): the rows of a CTA's ENV_WARPS_PER_BLOCK consecutive
 // envs form one contiguous, 16-byte aligned slab in HBM even though a single 885-float critic row is not.
-#define ENV_MAX_HIST_ROW 912       // >= frame_stack * num_obs floats (900)
-#define ENV_MAX_CRIT_ROW 896       // >= c_frame_stack * single_critic floats (885)
 
 #define ENV_STATS_RING 32           // per-step episode statistics are kept for this many policy steps
 
@@ -48,9 +46,14 @@ struct EnvCall {
     int parity;          // history buffers: read [parity], write [parity ^ 1]
     int phase_mask;
     int force_reset;     // b200_reset_all: run only the reset phase, for every env
+    int sit_pose;        // envs resetting in this call start in the sit pose (one host coin per step, tron1_pf_ee.py:204-210)
 };
 
-__host__ __device__ inline int env_smem_bytes(int warps) { return 16 + warps * (ES_TOTAL + ENV_MAX_HIST_ROW + ENV_MAX_CRIT_ROW + ENV_IN_WORDS) * 4; }
+// shared memory per CTA: mbarrier + per warp (scratch, staged history row, staged critic row, staged input rows)
+__host__ __device__ inline int env_row_words(int w) { return (w + 3) & ~3; }
+__host__ __device__ inline int env_smem_bytes(int warps, int hist_words, int crit_words) {
+    return 16 + warps * (ES_TOTAL + env_row_words(hist_words) + env_row_words(crit_words) + ENV_IN_WORDS) * 4;
+}
 
 // quat_rotate_inverse (math_utils.py:63-76), q = xyzw
 __device__ __forceinline__ f3 rot_inv(float qx, float qy, float qz, float qw, f3 v) {
@@ -136,6 +139,9 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     const int ttype = ti[TI_TERRAIN_CURRICULUM] ? (int)R.terrain_types[env] : 0;
     f3 push_vel = mk3(R.rand_push_vels[env * 3], R.rand_push_vels[env * 3 + 1], 0.f);
     f3 lin_b, ang_b, grav;           // body-frame velocities, projected gravity
+    // periodic-gait state (tron1_pf_ee.py:186-197): theta_left/right, gait time, phase
+    float th0 = 0.f, th1 = 0.f, gtime = 0.f, gphi = 0.f, expc_frc = 0.f;
+    if (ti[TI_GAIT]) { th0 = R.gait_state[env * 8]; th1 = R.gait_state[env * 8 + 1]; gtime = R.gait_state[env * 8 + 2]; gphi = R.gait_state[env * 8 + 3]; }
     // ------------------------------------------------------------------ per-lane values
     const bool jl = lane < A, fl = lane < F;
     float qj = jl ? R.dof_pos[env * A + lane] : 0.f, qdj = jl ? R.dof_vel[env * A + lane] : 0.f;
@@ -147,7 +153,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         fpos = mk3(a[0], a[1], a[2]); fvel = mk3(b[0], b[1], b[2]);
     }
     float ffz = fl ? R.link_contact_forces[(env * L + ti[TI_FEET_LINKS + lane]) * 3 + 2] : 0.f;   // foot contact force z
-    float hmean = 0.f;               // mean of the 9 terrain heights around this lane's foot
+    float hmean = 0.f, hmax = 0.f;   // mean / max of the 9 terrain heights around this lane's foot
 
     if (pm & PHASE_CALLBACK) ep_len += 1;                       // legged_robot.py:60
 
@@ -211,12 +217,13 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                     const int DX[9] = {-1, 1, 0, 0, 0, -1, 1, -1, 1}, DY[9] = {0, 0, -1, 1, 0, -1, 1, 1, -1};
                     int16_t hv[9];
                     float s = 0.f;
+                    hmax = -3.0e38f;
 #pragma unroll
                     for (int k = 0; k < 9; k++) {
                         hv[k] = __ldg(tr.hf + (size_t)wrap_idx(cx + DX[k], tr.rows) * tr.cols + wrap_idx(cy + DY[k], tr.cols));
                         const float hk = __fmul_rn((float)hv[k], tf[TF_VSCALE]);
                         B.height_around_feet[(env * F + lane) * 9 + k] = hk; es[ES_HAF + lane * 9 + k] = hk;
-                        s = __fadd_rn(s, hk);
+                        s = __fadd_rn(s, hk); hmax = fmaxf(hmax, hk);
                     }
                     hmean = __fdiv_rn(s, 9.0f);
                     const float den = __fmul_rn(tf[TF_HSCALE], 2.0f);
@@ -234,7 +241,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         grav = mk3(B.projected_gravity[env * 3], B.projected_gravity[env * 3 + 1], B.projected_gravity[env * 3 + 2]);
         if (fl && ti[TI_FEET_INFO]) {
             float s = 0.f;
-            for (int k = 0; k < 9; k++) { const float hk = B.height_around_feet[(env * F + lane) * 9 + k]; es[ES_HAF + lane * 9 + k] = hk; s = __fadd_rn(s, hk); }
+            hmax = -3.0e38f;
+            for (int k = 0; k < 9; k++) { const float hk = B.height_around_feet[(env * F + lane) * 9 + k]; es[ES_HAF + lane * 9 + k] = hk; s = __fadd_rn(s, hk); hmax = fmaxf(hmax, hk); }
             hmean = __fdiv_rn(s, 9.0f);
             for (int k = 0; k < 3; k++) es[ES_NV + lane * 3 + k] = B.normal_vector_around_feet[env * 3 * F + lane * 3 + k];
         }
@@ -349,6 +357,17 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 for (int pt = lane; pt < P; pt += 32) s += bp.z - (ti[TI_MEASURE_HEIGHTS] ? es[ES_MH + pt] : 0.f);
                 const float m = warp_sum(s) / (float)P - tf[TF_BASE_HEIGHT_TARGET];
                 r = m * m; break; }
+            case RW_BIPED_PERIODIC_GAIT: {                        // tron1_pf_ee.py:335-437, "step" indicator; feet 0 (left), 1 (right)
+                float term = 0.f;
+                if (lane < 2) {
+                    const float *f = R.link_contact_forces + (env * L + ti[TI_FEET_LINKS + lane]) * 3;
+                    const float q_frc = norm3_rn(f[0], f[1], f[2]), q_spd = norm3_rn(fvel.x, fvel.y, fvel.z);
+                    const float ph = __fmul_rn(fmodf(__fadd_rn(gphi, lane == 0 ? th0 : th1), 1.0f), 6.2831853071795862f);
+                    const bool swing = ph >= 0.f && ph < tf[TF_GAIT_B_SWING], stance = ph >= tf[TF_GAIT_B_SWING] && ph < 6.2831853071795862f;
+                    expc_frc = swing ? -1.f : 0.f;
+                    term = __fadd_rn(__fmul_rn(stance ? -1.f : 0.f, q_spd), __fmul_rn(expc_frc, q_frc));
+                }
+                r = expf(warp_sum(term)); break; }
             case RW_COLLISION: {
                 float hitf = 0.f;
                 if (lane < ti[TI_N_PEN]) { const float *f = R.link_contact_forces + (env * L + ti[TI_PEN_LINKS + lane]) * 3; hitf = norm3_rn(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f; }
@@ -395,7 +414,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 if (fl) {
                     const float vxy = sqrtf(fvel.x * fvel.x + fvel.y * fvel.y);
                     float z = fpos.z;
-                    if (ti[TI_CLEARANCE_USES_TERRAIN]) z -= hmean;
+                    if (ti[TI_CLEARANCE_MODE] == 1) z -= hmean; else if (ti[TI_CLEARANCE_MODE] == 2) z -= hmax;
                     const float e = z - tf[TF_FOOT_CLEARANCE_TARGET] - tf[TF_FOOT_HEIGHT_OFFSET];
                     s = vxy * e * e;
                 }
@@ -411,6 +430,11 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             case RW_THIGH_POS: r = warp_sum((jl && (lane % 3) == 1) ? dqj * dqj : 0.f); break;
             case RW_TORQUES: r = warp_sum(tauj * tauj); break;
             case RW_TRACKING_ANG_VEL: { const float e = cmd2 - ang_b.z; r = expf(-(e * e) / tf[TF_TRACKING_SIGMA]); break; }
+            case RW_TRACKING_BASE_HEIGHT: {                       // tron1_pf_ee.py:439-444
+                float s = 0.f;
+                for (int pt = lane; pt < P; pt += 32) s += bp.z - (ti[TI_MEASURE_HEIGHTS] ? es[ES_MH + pt] : 0.f);
+                const float m = warp_sum(s) / (float)P - tf[TF_BASE_HEIGHT_TARGET];
+                r = expf(-(m * m) / tf[TF_BASE_HEIGHT_SIGMA]); break; }
             case RW_TRACKING_LIN_VEL: { const float ex = cmd0 - lin_b.x, ey = cmd1 - lin_b.y; r = expf(-(ex * ex + ey * ey) / tf[TF_TRACKING_SIGMA]); break; }
             default: break;
             }
@@ -431,6 +455,11 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     }
     if ((pm & PHASE_TERMINATION) && lane == 0) { B.reset_buf[env] = reset ? 1 : 0; B.time_out_buf[env] = time_out ? 1 : 0; }
 
+    if (ti[TI_GAIT] && (pm & PHASE_REWARD)) {                    // tron1_pf_ee.py:27-35: advance the gait clock after the reward
+        gtime = __fadd_rn(gtime, dt);
+        if (gtime >= __fsub_rn(tf[TF_GAIT_PERIOD], __fmul_rn(dt, 0.5f))) gtime = 0.f;
+        gphi = __fdiv_rn(gtime, tf[TF_GAIT_PERIOD]);
+    }
     // ================================================================== reset_idx
     f3 grav_obs = grav;
     int new_level = level0;
@@ -466,14 +495,15 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         }
         if (jl) {                                                                 // _reset_dofs: q0 + U(-r, r), qd = 0
             const float rr = tf[TF_RESET_DOF_NOISE + lane];
-            qj = __fadd_rn(q0j, rand_range(-rr, __fmul_rn(2.0f, rr), rng.u(SITE_DOF, lane)));
+            qj = call.sit_pose ? tf[TF_SIT_DOF_POS + lane] : __fadd_rn(q0j, rand_range(-rr, __fmul_rn(2.0f, rr), rng.u(SITE_DOF, lane)));
             qdj = 0.f; actj = 0.f;
             B.dof_pos[env * A + lane] = qj; B.dof_vel[env * A + lane] = 0.f;
             B.actions[env * A + lane] = 0.f; B.last_actions[env * A + lane] = 0.f; B.llast_actions[env * A + lane] = 0.f;
             B.last_dof_vel[env * A + lane] = 0.f;
         }
         {   // _reset_root_states
-            bp = mk3(__fadd_rn(tf[TF_INIT_POS], origin.x), __fadd_rn(tf[TF_INIT_POS + 1], origin.y), __fadd_rn(tf[TF_INIT_POS + 2], origin.z));
+            const int ip = call.sit_pose ? TF_SIT_POS : TF_INIT_POS;     // tron1_pf_ee.py:204-210,287-305
+            bp = mk3(__fadd_rn(tf[ip], origin.x), __fadd_rn(tf[ip + 1], origin.y), __fadd_rn(tf[ip + 2], origin.z));
             if (ti[TI_HEIGHTFIELD]) {
                 const float sp = __fmul_rn(2.0f, tf[TF_RESET_ROOT_XY]);
                 bp.x = __fadd_rn(bp.x, rand_range(-tf[TF_RESET_ROOT_XY], sp, rng.u(SITE_ROOT, 0)));
@@ -482,7 +512,9 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             const float sv = __fmul_rn(2.0f, tf[TF_RESET_ROOT_VEL]), lo = -tf[TF_RESET_ROOT_VEL];
             lin_b = mk3(rand_range(lo, sv, rng.u(SITE_ROOT, 2)), rand_range(lo, sv, rng.u(SITE_ROOT, 3)), rand_range(lo, sv, rng.u(SITE_ROOT, 4)));
             ang_b = mk3(rand_range(lo, sv, rng.u(SITE_ROOT, 5)), rand_range(lo, sv, rng.u(SITE_ROOT, 6)), rand_range(lo, sv, rng.u(SITE_ROOT, 7)));
-            const float ix = tf[TF_INIT_QUAT], iy = tf[TF_INIT_QUAT + 1], iz = tf[TF_INIT_QUAT + 2], iw = tf[TF_INIT_QUAT + 3];
+            if (call.sit_pose) { lin_b = mk3(0.f, 0.f, 0.f); ang_b = mk3(0.f, 0.f, 0.f); }
+            const int iq = call.sit_pose ? TF_SIT_QUAT : TF_INIT_QUAT;
+            const float ix = tf[iq], iy = tf[iq + 1], iz = tf[iq + 2], iw = tf[iq + 3];
             grav_obs = rot_inv(ix, iy, iz, iw, mk3(0.f, 0.f, -1.f));
             if (lane < 3) {
                 B.base_pos[env * 3 + lane] = comp3(bp, lane);
@@ -515,6 +547,12 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
 #undef DR_PUT
         if (lane < 3 * F) B.last_feet_vel[env * 3 * F + lane] = 0.f;
         for (int e = lane; e < 48; e += 32) B.contact_warm[env * 48 + e] = 0.f;    // teleported: the contact warm start is stale
+        if (ti[TI_GAIT]) {                                                          // tron1_pf_ee.py:221-228
+            th0 = __fadd_rn(tf[TF_GAIT_THETA_LEFT], rng.u(SITE_GAIT, 0));
+            th1 = __fadd_rn(th0, tf[TF_GAIT_THETA_RIGHT]);                              // TF_GAIT_THETA_RIGHT holds right - left
+            gtime = __fmul_rn(rng.u(SITE_GAIT, 1), tf[TF_GAIT_PERIOD]);
+            gphi = __fdiv_rn(gtime, tf[TF_GAIT_PERIOD]);
+        }
         fat = 0.f;
         ep_len = 0; fail_cnt = 0;
     }
@@ -529,6 +567,13 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     if (pm & (PHASE_REWARD | PHASE_RESET)) {
         if (lane < n_sums) B.episode_sums[env * n_sums + lane] = my_sum;
         if (fl) B.feet_air_time[env * F + lane] = fat;
+    }
+    float clk = 0.f;                 // clock_input[lane], lanes 0..3 (tron1_pf_ee.py:258-263)
+    if (ti[TI_GAIT] && (pm & PHASE_OBSERVE)) {
+        const float arg = __fmul_rn(6.2831853071795862f, __fadd_rn(gphi, (lane & 1) == 0 ? th0 : th1));
+        clk = lane < 2 ? sinf(arg) : cosf(arg);
+        const float clk_lo = __shfl_sync(B200_FULL_MASK, clk, (lane + 28) & 31);    // lanes 4..7 <- clock of lanes 0..3
+        if (lane < 8) B.gait_state[env * 8 + lane] = lane == 0 ? th0 : (lane == 1 ? th1 : (lane == 2 ? gtime : (lane == 3 ? gphi : clk_lo)));
     }
     __syncwarp();   // DR parameters written above are re-read below by other lanes
 
@@ -549,7 +594,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         }
         __syncwarp();
         const float clipo = tf[TF_CLIP_OBS];
-        for (int e = lane; e < NO; e += 32) {
+        for (int e = lane; e < (ti[TI_OBS_KIND] == 4 ? 0 : NO); e += 32) {
             float v = ob[e];
             if (ti[TI_ADD_NOISE]) {
                 const float u = rng.u(SITE_OBS_NOISE, e);
@@ -558,7 +603,74 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             nz[e] = v;
             B.obs_buf[env * NO + e] = fminf(fmaxf(v, -clipo), clipo);
         }
-        if (ti[TI_OBS_KIND] == 3) {   // tron1_pf.py:15-70: obs_buf = stack of noisy frames, privileged_obs_buf = stack of critic frames
+        if (ti[TI_OBS_KIND] == 4) {   // tron1_pf_ee.py:53-141: features = 10 x 31 noisy frames, labels 17, critic = 10 x 134
+            const int SC = ti[TI_SINGLE_CRITIC], NP = ti[TI_NUM_PRIV], NCS = ti[TI_N_CS], NB = NO - 4;   // NB = 9 + 3A
+            float *cr = es + ES_CRIT, *pv = es + ES_PRIV;
+            const bool cleared = (pm & PHASE_RESET) && reset;
+            const int DRN = 10 + 2 * A;
+            if (lane < 4) ob[NB + lane] = clk;
+            __syncwarp();
+            // the generic loop above already produced nz[0..NB) / obs_buf; redo it over the full 31-wide frame (clock included)
+            for (int e = lane; e < NO; e += 32) {
+                float v = ob[e];
+                if (ti[TI_ADD_NOISE]) v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(2.0f, rng.u(SITE_OBS_NOISE, e)), 1.0f), tf[TF_NOISE_VEC + e]));
+                nz[e] = fminf(fmaxf(v, -clipo), clipo);
+                B.obs_buf[env * NO + e] = nz[e];
+                cr[e] = fminf(fmaxf(ob[e], -clipo), clipo);
+            }
+            for (int e = lane; e < DRN; e += 32) {
+                float v;
+                if (e == 0) v = __fsub_rn(R.friction[env], tf[TF_FRICTION_OFFSET]);
+                else if (e == 1) v = R.added_mass[env];
+                else if (e < 5) v = R.com_bias[env * 3 + e - 2];
+                else if (e < 7) v = e == 5 ? push_vel.x : push_vel.y;
+                else if (e < 7 + A) v = __fsub_rn(R.kp_scale[env * A + e - 7], tf[TF_KPS_OFFSET]);
+                else if (e < 7 + 2 * A) v = __fsub_rn(R.kd_scale[env * A + e - 7 - A], tf[TF_KDS_OFFSET]);
+                else v = e == 7 + 2 * A ? B.joint_armature[env] : (e == 8 + 2 * A ? B.joint_friction[env] : B.joint_damping[env]);
+                cr[NO + e] = v;
+            }
+            {   // gait_info: exp_C_frc of the left / right foot as left by the reward (R13)
+                const float e0 = __shfl_sync(B200_FULL_MASK, expc_frc, 0), e1 = __shfl_sync(B200_FULL_MASK, expc_frc, 1);
+                if (lane == 0) { cr[NO + DRN] = e0; cr[NO + DRN + 1] = e1; }
+            }
+            int off = NO + DRN + 2;
+            for (int e = lane; e < NCS; e += 32) { cr[off + e] = es[ES_LCS + e]; pv[3 + e] = es[ES_LCS + e]; }
+            off += NCS;
+            for (int pt = lane; pt < P; pt += 32) {
+                const float d = __fsub_rn(__fsub_rn(bp.z, tf[TF_HEIGHT_OBS_OFFSET]), es[ES_MH + pt]);
+                cr[off + pt] = __fmul_rn(fminf(fmaxf(d, -1.0f), 1.0f), tf[TF_OS_HEIGHT]);
+            }
+            off += P;
+            for (int e = lane; e < 3 * F; e += 32) { cr[off + e] = es[ES_NV + e]; pv[3 + NCS + F + e] = es[ES_NV + e]; }
+            off += 3 * F;
+            for (int e = lane; e < 9 * F; e += 32) {
+                const float fz = R.feet_pos[(env * F + e / 9) * 3 + 2];
+                cr[off + e] = fminf(fmaxf(__fsub_rn(fz, es[ES_HAF + e]), -1.0f), 1.0f);
+            }
+            if (lane < 3) pv[lane] = __fmul_rn(comp3(lin_b, lane), tf[TF_OS_LIN_VEL]);
+            if (fl) pv[3 + NCS + lane] = fminf(fmaxf(__fsub_rn(__fsub_rn(fpos.z, hmax), tf[TF_FOOT_HEIGHT_OFFSET]), -1.0f), 1.0f);
+            __syncwarp();
+            for (int e = lane; e < NP; e += 32) B.privileged_obs_buf[env * NP + e] = pv[e];          // estimator labels (unclipped)
+            for (int e = lane; e < SC; e += 32) cr[e] = fminf(fmaxf(cr[e], -clipo), clipo);
+            __syncwarp();
+            if (hrow != nullptr) {
+                smem_shift_append(hrow, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, lane);
+                smem_shift_append(crow, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, lane);
+            } else {
+                {
+                    const int W = ti[TI_FRAME_STACK] * NO, keepw = W - NO;
+                    shift_copy(B.obs_history[call.parity ^ 1] + (size_t)env * W, B.obs_history[call.parity] + (size_t)env * W + NO, keepw, cleared, lane);
+                    float *dst = B.obs_history[call.parity ^ 1] + (size_t)env * W;
+                    for (int e = lane; e < NO; e += 32) dst[keepw + e] = nz[e];
+                }
+                {
+                    const int W = ti[TI_C_FRAME_STACK] * SC, keepw = W - SC;
+                    shift_copy(B.critic_obs[call.parity ^ 1] + (size_t)env * W, B.critic_obs[call.parity] + (size_t)env * W + SC, keepw, cleared, lane);
+                    float *dst = B.critic_obs[call.parity ^ 1] + (size_t)env * W;
+                    for (int e = lane; e < SC; e += 32) dst[keepw + e] = cr[e];
+                }
+            }
+        } else if (ti[TI_OBS_KIND] == 3) {   // tron1_pf.py:15-70: obs_buf = stack of noisy frames, privileged_obs_buf = stack of critic frames
             const int SC = ti[TI_SINGLE_CRITIC];
             float *cr = es + ES_CRIT;
             const bool cleared = (pm & PHASE_RESET) && reset;
@@ -672,7 +784,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     X(last_dof_vel, float, A_) X(feet_pos, float, 3 * F_) X(feet_vel, float, 3 * F_) X(last_feet_vel, float, 3 * F_)   \
     X(link_contact_forces, float, 3 * L_) X(episode_sums, float, NS_) X(feet_air_time, float, F_)                      \
     X(last_contacts, uint8_t, F_) X(friction, float, 1) X(added_mass, float, 1) X(com_bias, float, 3)                  \
-    X(kp_scale, float, A_) X(kd_scale, float, A_)
+    X(kp_scale, float, A_) X(kd_scale, float, A_) X(gait_state, float, 8)
 
 __global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, 5)
 env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call) {
@@ -682,17 +794,16 @@ env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, 
     const int env0 = blockIdx.x * nwarps, env = env0 + warp;
     const int N = T.i[TI_NUM_ENVS];
     uint64_t *bar = (uint64_t *)smem;
-    float *hslab = smem + 4, *cslab = hslab + nwarps * ENV_MAX_HIST_ROW, *es = cslab + nwarps * ENV_MAX_CRIT_ROW;
-    char *inslab = (char *)(es + nwarps * ES_TOTAL);
     const int HW = T.i[TI_FRAME_STACK] * T.i[TI_NUM_OBS], CW = T.i[TI_C_FRAME_STACK] * T.i[TI_SINGLE_CRITIC];
+    float *hslab = smem + 4, *cslab = hslab + nwarps * env_row_words(HW), *es = cslab + nwarps * env_row_words(CW);
+    char *inslab = (char *)(es + nwarps * ES_TOTAL);
     const uint32_t hbytes = (uint32_t)(nwarps * HW * 4), cbytes = (uint32_t)(nwarps * CW * 4);
     const int A = T.i[TI_A], F = T.i[TI_F], L = T.i[TI_L];
     const int NSUM = T.i[TI_N_SUMS];
     const bool full = !call.force_reset && (call.phase_mask & PHASE_ALL) == PHASE_ALL;
     // pass 1 (all threads, uniform): byte counts of every slab -> is the CTA stageable, how many bytes will arrive
     uint32_t total = hbytes + cbytes, off = 0;
-    bool ok = full && T.i[TI_OBS_KIND] >= 1 && env0 + nwarps <= N && HW <= ENV_MAX_HIST_ROW && CW <= ENV_MAX_CRIT_ROW &&
-              B200_TMA_SIZE_OK(hbytes) && B200_TMA_SIZE_OK(cbytes);
+    bool ok = full && T.i[TI_OBS_KIND] >= 1 && env0 + nwarps <= N && B200_TMA_SIZE_OK(hbytes) && B200_TMA_SIZE_OK(cbytes);
 #define X_COUNT(field, type, k) { const uint32_t b_ = (uint32_t)(nwarps * (k) * sizeof(type)); ok = ok && B200_TMA_SIZE_OK(b_); total += b_; off += (b_ + 15u) & ~15u; }
     ENV_STAGED_INPUTS(X_COUNT, A, F, L, NSUM)
 #undef X_COUNT
@@ -706,7 +817,7 @@ env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, 
         if (threadIdx.x == 0) tma_load_1d(hslab, B.obs_history[call.parity] + (size_t)env0 * HW, hbytes, bar);
         if (threadIdx.x == 1) tma_load_1d(cslab, B.critic_obs[call.parity] + (size_t)env0 * CW, cbytes, bar);
 #define X_LOAD(field, type, k) { const uint32_t b_ = (uint32_t)(nwarps * (k) * sizeof(type));                              \
-        if ((int)threadIdx.x == t) tma_load_1d(inslab + off, B.field + (size_t)env0 * (k), b_, bar);                      \
+        if ((int)threadIdx.x == t % (int)blockDim.x) tma_load_1d(inslab + off, B.field + (size_t)env0 * (k), b_, bar);                      \
         R.field = (type *)(inslab + off) - (size_t)env0 * (k); off += (b_ + 15u) & ~15u; t++; }
         ENV_STAGED_INPUTS(X_LOAD, A, F, L, NSUM)
 #undef X_LOAD

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import task_spec as T
+from .host_rng import host_uniform
 from .simulator import B200Simulator
 
 
@@ -34,8 +35,9 @@ class FusedLeggedEnv:
         sim = self.simulator
         self._b = sim._buf
         self.widths = spec.obs_widths(sim._model)
-        self.stacked = spec.obs_kind == "tron1_pf"          # obs / privileged obs are the frame stacks themselves
+        self.stacked = spec.obs_kind in ("tron1_pf", "tron1_pf_ee")   # obs / privileged obs are the frame stacks themselves
         self.num_obs = self.widths["hist"] if self.stacked else self.widths["obs"]
+        self.num_estimator_features, self.num_estimator_labels = self.widths["hist"], self.widths["priv"]
         self.num_privileged_obs = self.widths["critic"] if self.stacked else (
             self.widths["priv"] if spec.obs_kind in ("go2_ts", "go2_cat") else None)
         self.num_actions = spec.num_actions
@@ -98,11 +100,28 @@ class FusedLeggedEnv:
         sim.step(actions)                                      # _pre_sim_step + simulator.step
         self.common_step_counter += 1
         self._apply_pending_curriculum()
+        self._set_step_flags()
         sim.fused_post_step(self.common_step_counter, self.command_ranges["lin_vel_x"])
         self._fill_extras()
         return self._returns()
 
+    def _set_step_flags(self):
+        """Host scalars of the step: the sit-pose coin (one per reset batch, tron1_pf_ee.py:204-210)."""
+        if self.spec.sit_init_percent > 0:
+            coin = host_uniform(self.spec.seed, self.common_step_counter, T.SITE_HOST, 0)
+            self.simulator.set_step_flags(coin < self.spec.sit_init_percent)
+
+    @property
+    def estimator_features_buf(self):
+        return self.obs_history
+
+    @property
+    def estimator_labels_buf(self):
+        return self._b["privileged_obs_buf"]
+
     def _returns(self):
+        if self.spec.obs_kind == "tron1_pf_ee":          # LeggedRobotEE.step, legged_robot_ee.py:56-73
+            return (self.obs_history, self.estimator_labels_buf, self.critic_obs_buf, self.rew_buf, self.reset_buf, self.extras)
         if self.spec.obs_kind in ("go2_ts", "go2_cat"):
             return (self.obs_buf, self.privileged_obs_buf, self.obs_history, self.critic_obs_buf, self.rew_buf,
                     self.reset_buf, self.extras)
@@ -110,11 +129,16 @@ class FusedLeggedEnv:
 
     def reset(self):
         """BaseTask.reset (base_task.py:60-64): reset_idx(all) then one zero-action step."""
+        self._set_step_flags()
         self.simulator.fused_reset_all(self.common_step_counter, self.command_ranges["lin_vel_x"])
         out = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
+        if self.spec.obs_kind == "tron1_pf_ee":
+            return out[:3]
         return out[:4] if self.spec.obs_kind in ("go2_ts", "go2_cat") else out[:2]
 
     def get_observations(self):
+        if self.spec.obs_kind == "tron1_pf_ee":
+            return self.obs_history, self.estimator_labels_buf, self.critic_obs_buf
         if self.spec.obs_kind in ("go2_ts", "go2_cat"):
             return self.obs_buf, self.privileged_obs_buf, self.obs_history, self.critic_obs_buf
         return self.obs_buf

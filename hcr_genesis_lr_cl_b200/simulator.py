@@ -257,6 +257,9 @@ class B200Simulator:
         if mask & H["PHASE_OBSERVE"]:
             self._parity ^= 1
 
+    def set_step_flags(self, sit_pose: bool) -> None:
+        self._ck(self._lib.b200_set_step_flags(self._handle, int(bool(sit_pose))))
+
     def fused_reset_all(self, step_counter: int, cmd_range_x: Sequence[float]):
         lo, hi = float(cmd_range_x[0]), float(cmd_range_x[1])
         self._ck(self._lib.b200_reset_all(self._handle, int(step_counter), lo, float(np.float32(hi - lo)), self._parity, self._stream()))

@@ -29,24 +29,24 @@ from .robot_model import GO2_DOF_NAMES, TRON1_PF_DOF_NAMES, RobotModel, load_rob
 # class_to_dict(cfg.rewards.scales) == dir() order (legged_gym/utils/helpers.py:10-25,
 # legged_robot.py:411-434); "termination" is always added last (legged_robot.py:163-168).
 REWARD_TERMS: List[str] = [
-    "action_rate", "action_smoothness", "ang_vel_xy", "base_height", "collision", "dof_acc",
+    "action_rate", "action_smoothness", "ang_vel_xy", "base_height", "biped_periodic_gait", "collision", "dof_acc",
     "dof_close_to_default", "dof_pos_limits", "dof_pos_stand_still", "dof_power", "dof_vel",
     "dof_vel_stand_still", "feet_air_time", "feet_contact_stand_still", "feet_distance", "foot_acc", "foot_clearance",
     "foot_landing_vel", "hip_pos", "keep_balance", "lin_vel_z", "no_fly", "orientation", "thigh_pos", "torques",
-    "tracking_ang_vel", "tracking_lin_vel", "termination",
+    "tracking_ang_vel", "tracking_base_height", "tracking_lin_vel", "termination",
 ]
 REWARD_ID: Dict[str, int] = {n: i for i, n in enumerate(REWARD_TERMS)}
 NUM_REWARD_TERMS = len(REWARD_TERMS)
 
 #: observation layouts the fused kernel knows (per-task ``compute_observations``)
-OBS_KINDS = {"go2": 0, "go2_ts": 1, "go2_cat": 2, "tron1_pf": 3}
+OBS_KINDS = {"go2": 0, "go2_ts": 1, "go2_cat": 2, "tron1_pf": 3, "tron1_pf_ee": 4}
 
 CAT_CONSTRAINTS = ["torque", "dof_vel", "action_rate", "base_height", "collision", "feet_stumble", "dof_pos",
                    "base_orientation", "stand_still"]      # order of ConstraintManager.add calls, go2_cat.py:197-208
 
 # Philox draw sites (see oracle/philox.py and csrc/philox.cuh)
 SITE_CMD_RESAMPLE, SITE_PUSH, SITE_LEVEL, SITE_CMD_RESET, SITE_DOF, SITE_ROOT, SITE_FRICTION, SITE_MASS, SITE_COM, \
-    SITE_KP, SITE_KD, SITE_ARMATURE, SITE_JFRICTION, SITE_JDAMPING, SITE_OBS_NOISE = range(15)
+    SITE_KP, SITE_KD, SITE_ARMATURE, SITE_JFRICTION, SITE_JDAMPING, SITE_OBS_NOISE, SITE_GAIT, SITE_HOST = range(17)
 
 
 @dataclass
@@ -164,6 +164,18 @@ class TaskSpec:
     terminate_after_contacts_on: List[str] = field(default_factory=list)
     obtain_link_contact_states: bool = False
     contact_state_link_names: List[str] = field(default_factory=lambda: ["thigh", "calf", "foot"])
+    # periodic-gait framework + sit-pose resets (tron1_pf_ee_config.py:51-63,128-137)
+    gait_enabled: bool = False
+    gait_period: float = 0.5
+    gait_theta_left: float = 0.0
+    gait_theta_right: float = 0.5
+    gait_b_swing: float = 0.5
+    base_height_tracking_sigma: float = 0.01
+    foot_clearance_mode: int = 0            # height under the foot: 0 none, 1 mean of the 9 samples, 2 max
+    sit_init_percent: float = 0.0
+    sit_pos: List[float] = field(default_factory=lambda: [0.0, 0.0, 0.55])
+    sit_pitch_angle: float = 0.0
+    sit_joint_angles: List[float] = field(default_factory=list)
     # Constraints as Terminations (go2_cat_config.py:28-36, go2_cat.py:135-215)
     cat_enabled: bool = False
     cat_soft_p: float = 0.25
@@ -177,6 +189,10 @@ class TaskSpec:
     pgs_iterations: int = 30          # sweep cap of the projected Gauss-Seidel contact solver
     pgs_tolerance: float = 1e-4       # stop when max|df| over a sweep <= tol * (1 + max|f|)
     seed: int = 1
+
+    def __post_init__(self):
+        if self.foot_clearance_uses_terrain and self.foot_clearance_mode == 0:
+            self.foot_clearance_mode = 1
 
     # ------------------------------------------------------------------ derived
     @property
@@ -243,6 +259,13 @@ class TaskSpec:
         feet, _, _, cs = self.link_groups(model)
         if self.obs_kind == "go2":
             return dict(obs=9 + 3 * A, priv=0, single_critic=0, hist=0, critic=0)
+        if self.obs_kind == "tron1_pf_ee":                  # tron1_pf_ee.py:53-141
+            single = 9 + 3 * A + 4
+            dr = 10 + 2 * A
+            P_ = self.num_height_points if self.measure_heights else 0
+            sc = single + dr + 2 + len(cs) + P_ + 3 * len(feet) + 9 * len(feet)
+            labels = 3 + len(cs) + len(feet) + 3 * len(feet)
+            return dict(obs=single, priv=labels, single_critic=sc, hist=self.frame_stack * single, critic=self.c_frame_stack * sc)
         if self.obs_kind == "tron1_pf":                     # tron1_pf.py:15-70: both outputs are frame stacks
             single = 9 + 3 * A
             sc = 3 + single + A + 7 + len(feet)
@@ -264,6 +287,16 @@ class TaskSpec:
     def noise_scale_vec(self) -> np.ndarray:
         """go2.py:92-117 / go2_ts.py:98-123 (same 45-wide layout)."""
         A = self.num_actions
+        if self.obs_kind == "tron1_pf_ee":
+            # tron1_pf_ee.py:309-333 keeps the 12-dof slice bounds on a 31-wide vector: entries 15..20 (dof_vel) get the
+            # dof_pos scale and 21..30 (actions, clock) the dof_vel scale -- reproduced as shipped (quirk R17)
+            v = np.zeros(9 + 3 * A + 4, np.float32)
+            if self.add_noise:
+                v[3:6] = self.noise_gravity * self.noise_level
+                v[6:9] = self.noise_ang_vel * self.noise_level * self.obs_scale_ang_vel
+                v[9:21] = self.noise_dof_pos * self.noise_level * self.obs_scale_dof_pos
+                v[21:33] = self.noise_dof_vel * self.noise_level * self.obs_scale_dof_vel
+            return v
         v = np.zeros(9 + 3 * A, np.float32)
         if not self.add_noise:
             return v
@@ -277,7 +310,7 @@ class TaskSpec:
     @classmethod
     def from_reference_cfg(cls, cfg, task: str) -> "TaskSpec":
         """Read a LeggedGym-Ex config object (nested classes/instances) into a TaskSpec."""
-        kinds = {"go2": "go2", "go2_ts": "go2_ts", "go2_cat": "go2_cat", "tron1_pf": "tron1_pf"}
+        kinds = {"go2": "go2", "go2_ts": "go2_ts", "go2_cat": "go2_cat", "tron1_pf": "tron1_pf", "tron1_pf_ee": "tron1_pf_ee"}
         if task not in kinds:
             raise ValueError(f"task {task!r} has no fused descriptor yet (supported: {sorted(kinds)})")
 
@@ -342,7 +375,7 @@ class TaskSpec:
             foot_clearance_target=r.foot_clearance_target, foot_height_offset=r.foot_height_offset,
             foot_clearance_tracking_sigma=r.foot_clearance_tracking_sigma,
             about_landing_threshold=getattr(r, "about_landing_threshold", 0.03),
-            feet_air_time_threshold=0.25 if task in ("go2_ts", "go2_cat", "tron1_pf") else 0.3,
+            feet_air_time_threshold=0.25 if task in ("go2_ts", "go2_cat", "tron1_pf", "tron1_pf_ee") else 0.3,
             foot_distance_threshold=getattr(r, "foot_distance_threshold", 0.115),
             foot_clearance_uses_terrain=task in ("go2_ts", "go2_cat"),
             dof_vel_limits=list(getattr(a, "dof_vel_limits", [])),
@@ -352,6 +385,19 @@ class TaskSpec:
             contact_state_link_names=list(a.contact_state_link_names),
             seed=getattr(cfg, "seed", 1),
         )
+        if task == "tron1_pf_ee":
+            g = r.periodic_reward_framework
+            if g.gait_function_type != "step":
+                raise ValueError("only the 'step' gait indicator is fused (the 'smooth' variant calls scipy on the host)")
+            spec.gait_enabled = True
+            spec.gait_period, spec.gait_theta_left, spec.gait_theta_right, spec.gait_b_swing = g.gait_period, g.theta_left, g.theta_right, g.b_swing
+            spec.base_height_tracking_sigma = r.base_height_tracking_sigma
+            spec.foot_clearance_mode, spec.foot_clearance_uses_terrain = 2, True
+            spec.sit_init_percent, spec.sit_pos = cfg.init_state.sit_init_percent, list(cfg.init_state.sit_pos)
+            spec.sit_pitch_angle = cfg.init_state.sit_pitch_angle
+            spec.sit_joint_angles = [float(cfg.init_state.sit_joint_angles[n_]) for n_ in a.dof_names]
+            spec.double_shift_actions = True
+            spec.height_obs_offset = 0.6
         if task == "go2_cat":
             cc = cfg.constraints
             spec.cat_enabled = cc.enable == "cat"
@@ -464,4 +510,41 @@ def tron1_pf_spec(**over) -> TaskSpec:
     return s
 
 
-PRESETS = {"go2": go2_spec, "go2_ts": go2_ts_spec, "go2_cat": go2_cat_spec, "tron1_pf": tron1_pf_spec}
+def tron1_pf_ee_spec(**over) -> TaskSpec:
+    """`tron1_pf_ee` point-foot biped on rough terrain with full DR, periodic gait and sit-pose resets (BASELINE config
+    C4; tron1_pf_ee_config.py:4-170)."""
+    pts = [-0.3, -0.2, -0.1, 0.0, 0.1, 0.2, 0.3]
+    s = TaskSpec(
+        task="tron1_pf_ee", obs_kind="tron1_pf_ee", robot="tron1_pf", dof_names=list(TRON1_PF_DOF_NAMES), num_obs=48,
+        num_privileged_obs=1340, frame_stack=10, c_frame_stack=10, kp=42.0, kd=2.5, action_scale=0.25, clip_actions=20.0,
+        default_dof_pos=[0.0] * 6, reset_dof_noise=[0.2, 0.4, 0.4] * 2, reset_root_vel=0.5, init_pos=[0.0, 0.0, 0.83],
+        env_spacing=3.0, mesh_type="heightfield", border_size=15.0, terrain_length=8.0, terrain_width=8.0, num_rows=10,
+        num_cols=10, terrain_curriculum=True, max_init_terrain_level=1, measure_heights=True,
+        measured_points_x=list(pts), measured_points_y=list(pts), obtain_terrain_info_around_feet=True,
+        cmd_curriculum=True, max_curriculum=0.8, cmd_lin_vel_x=[-0.5, 0.5], cmd_lin_vel_y=[-0.6, 0.6],
+        friction_range=[0.0, 1.7], added_mass_range=[-1.0, 2.0], push_interval_s=10.0,
+        com_pos_x_range=[-0.03, 0.03], com_pos_y_range=[-0.03, 0.03], com_pos_z_range=[-0.03, 0.03],
+        randomize_pd_gain=True, randomize_joint_armature=True, joint_armature_range=[0.11, 0.13],
+        randomize_joint_friction=True, joint_friction_range=[0.0, 0.01], randomize_joint_damping=True,
+        joint_damping_range=[1.4, 1.45],
+        reward_scales=dict(termination=-0.0, tracking_lin_vel=1.0, tracking_ang_vel=0.5, lin_vel_z=-0.5, ang_vel_xy=-0.05,
+                           orientation=-4.0, torques=0.0, dof_vel=-0.0, dof_acc=-2.0e-7, base_height=-0.0, feet_air_time=0.0,
+                           collision=-1.0, feet_stumble=-0.0, action_rate=-0.01, dof_pos_stand_still=-0.0, keep_balance=1.0,
+                           dof_pos_limits=-2.0, feet_distance=-100.0, tracking_base_height=0.3, dof_power=-2.0e-4,
+                           foot_acc=-1.0e-5, action_smoothness=-0.01, biped_periodic_gait=1.0, foot_clearance=0.5),
+        only_positive_rewards=False, soft_dof_pos_limit=0.95, base_height_target=0.75, foot_clearance_target=0.06,
+        foot_height_offset=0.032, foot_distance_threshold=0.115, max_projected_gravity=-0.2,
+        penalize_contacts_on=["knee", "hip"], terminate_after_contacts_on=["base", "abad"],
+        obtain_link_contact_states=True, contact_state_link_names=["hip", "knee", "foot"],
+        feet_air_time_threshold=0.25, foot_clearance_uses_terrain=True, foot_clearance_mode=2, height_obs_offset=0.6,
+        gait_enabled=True, gait_period=0.5, gait_theta_left=0.0, gait_theta_right=0.5, gait_b_swing=0.5,
+        base_height_tracking_sigma=0.01, sit_init_percent=0.7, sit_pos=[0.0, 0.0, 0.55], sit_pitch_angle=-0.2,
+        sit_joint_angles=[0.0, 0.6, 1.36, 0.0, -0.6, -1.36], double_shift_actions=True,
+    )
+    for k, v in over.items():
+        setattr(s, k, v)
+    return s
+
+
+PRESETS = {"go2": go2_spec, "go2_ts": go2_ts_spec, "go2_cat": go2_cat_spec, "tron1_pf": tron1_pf_spec,
+           "tron1_pf_ee": tron1_pf_ee_spec}

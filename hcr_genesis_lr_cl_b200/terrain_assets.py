@@ -14,6 +14,18 @@ import numpy as np
 _ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
 
 
-def load_go2_rough_terrain():
-    z = np.load(os.path.join(_ASSETS, "go2_rough_terrain.npz"))
+def load_terrain(name: str):
+    """`go2_rough` (Go2RoughCommonCfg.terrain) or `tron1_rough` (TRON1PF_EECfg.terrain: 15 m border, 1100 x 1100)."""
+    z = np.load(os.path.join(_ASSETS, f"{name}_terrain.npz"))
     return z["height_samples"].astype(np.int16), z["terrain_origins"].astype(np.float32)
+
+
+def load_go2_rough_terrain():
+    return load_terrain("go2_rough")
+
+
+def terrain_for(spec):
+    """Packaged terrain matching a task preset (None for plane tasks)."""
+    if not spec.heightfield:
+        return None
+    return load_terrain("tron1_rough" if spec.robot == "tron1_pf" else "go2_rough")

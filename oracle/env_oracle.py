@@ -112,7 +112,14 @@ class EnvOracle:
             base_lin_vel=z(N, 3), base_ang_vel=z(N, 3), feet_vel=z(N, F, 3), last_dof_vel=z(N, A),
             last_feet_vel=z(N, F, 3), last_base_lin_vel=z(N, 3), last_base_ang_vel=z(N, 3),
             obs_hist=z(N, max(self.widths["hist"], 1)), critic_hist=z(N, max(self.widths["critic"], 1)),
+            gait_state=z(N, 8),      # theta_left, theta_right, gait_time, phi, clock_input[4]
         )
+        # R18 (reference defect, found here): tron1_pf_ee.py:32-34,414-421 flatten `nonzero()` of [N,1] masks, so the column
+        # index 0 joins the row indices: env 0's gait time is zeroed whenever ANY env wraps and its swing/stance indicator
+        # is overwritten whenever any env is in swing/stance.  The product does not reproduce this coupling;
+        # the oracle can, so that it is pinned on every env of the reference goldens.
+        self.reproduce_r18 = False
+        self.sit_coin = None         # host coin of the step (tron1_pf_ee.py:204); None -> drawn from the SITE_HOST stream
         self.st["base_quat_wxyz"][:, 0] = 1
         self.out = {}
 
@@ -160,7 +167,21 @@ class EnvOracle:
         if self.spec.cat_enabled:
             self._constraints_cat(o)
         self._reward(o)
+        if self.spec.gait_enabled:                        # tron1_pf_ee.py:27-35
+            g = st["gait_state"]
+            g[:, 2] = (g[:, 2] + f32(self.spec.dt)).astype(f32)
+            over = g[:, 2] >= f32(self.spec.gait_period - self.spec.dt / 2)
+            g[over, 2] = 0
+            if self.reproduce_r18 and over.any():
+                g[0, 2] = 0
+            g[:, 3] = (g[:, 2] / f32(self.spec.gait_period)).astype(f32)
         self._reset(o)
+        if self.spec.gait_enabled:                        # _calc_periodic_reward_obs, tron1_pf_ee.py:258-263
+            g = st["gait_state"]
+            for i in range(2):
+                arg = (f32(2 * np.pi) * (g[:, 3] + g[:, i]).astype(f32)).astype(f32)
+                g[:, 4 + i] = np.sin(arg)
+                g[:, 6 + i] = np.cos(arg)
         self._observe(o)
         if self.spec.double_shift_actions:               # go2_cat.py:127-130
             st["llast_actions"][:] = st["last_actions"]
@@ -353,8 +374,10 @@ class EnvOracle:
         def foot_clearance():
             vxy = np.sqrt(np.sum(o["feet_vel"][:, :, :2] ** 2, axis=-1, dtype=f32)).astype(f32)
             z = o["feet_pos"][:, :, 2]
-            if s.foot_clearance_uses_terrain:
+            if s.foot_clearance_mode == 1:
                 z = z - np.mean(o["height_around_feet"], axis=-1, dtype=f32).astype(f32)
+            elif s.foot_clearance_mode == 2:                         # tron1_pf_ee.py:446-456
+                z = z - np.max(o["height_around_feet"], axis=-1)
             err = ssum(vxy * np.square(z - f32(s.foot_clearance_target) - f32(s.foot_height_offset)))
             return np.exp(-err / f32(s.foot_clearance_tracking_sigma)).astype(f32)
 
@@ -386,6 +409,9 @@ class EnvOracle:
             "feet_distance": lambda: np.maximum(f32(0), f32(s.foot_distance_threshold) - np.sqrt(np.sum(np.square(
                 o["feet_pos"][:, 0, :2] - o["feet_pos"][:, 1, :2]), axis=-1, dtype=f32)).astype(f32)),      # tron1_pf.py:146-151
             "no_fly": lambda: (ssum((lf[:, self.feet, 2] > f32(0.1)).astype(f32)) == 1).astype(f32),       # tron1_pf.py:153-156
+            "biped_periodic_gait": lambda: self._biped_gait(o),
+            "tracking_base_height": lambda: np.exp(-np.square(np.mean(st["base_pos"][:, 2:3] - o["measured_heights"], axis=1, dtype=f32)
+                                                              - f32(s.base_height_target)) / f32(s.base_height_tracking_sigma)).astype(f32),
             "foot_acc": lambda: np.sum(np.square((o["feet_vel"] - st["last_feet_vel"]) / dt), axis=(1, 2), dtype=f32),
             "foot_clearance": foot_clearance,
             "foot_landing_vel": foot_landing_vel,
@@ -415,6 +441,31 @@ class EnvOracle:
             terms["termination"] = r
         o["rew_buf"], o["reward_terms"] = rew, terms
 
+    # ------------------------------------------------------------------ tron1_pf_ee.py:335-437 ("step" indicator)
+    def _biped_gait(self, o):
+        s, st = self.spec, self.st
+        g = st["gait_state"]
+        lf = o["link_contact_forces"]
+        total = np.zeros(self.N, f32)
+        o["exp_C_frc"] = np.zeros((self.N, 2), f32)
+        for i in range(2):
+            q_frc = _norm3(lf[:, self.feet[i], :])
+            q_spd = _norm3(o["feet_vel"][:, i, :])
+            phi = (np.mod((g[:, 3] + g[:, i]).astype(f32), f32(1.0)) * f32(2 * np.pi)).astype(f32)
+            b_swing = f32(s.gait_b_swing * 2 * np.pi)
+            swing = (phi >= 0) & (phi < b_swing)
+            stance = (phi >= b_swing) & (phi < f32(2 * np.pi))
+            c_frc = np.where(swing, f32(-1), f32(0))
+            c_spd = np.where(stance, f32(-1), f32(0))
+            if self.reproduce_r18:
+                if swing.any():
+                    c_frc[0], c_spd[0] = -1, 0
+                if stance.any():
+                    c_frc[0], c_spd[0] = 0, -1
+            o["exp_C_frc"][:, i] = c_frc
+            total = (total + (c_spd * q_spd + c_frc * q_frc).astype(f32)).astype(f32)
+        return np.exp(total).astype(f32)
+
     # ------------------------------------------------------------------ legged_robot.py:94-148
     def _reset(self, o):
         s, st = self.spec, self.st
@@ -437,20 +488,33 @@ class EnvOracle:
         # command curriculum (legged_robot.py:336-348) is applied by the host one step later: DESIGN.md "deviations"
         self._resample(ids, T.SITE_CMD_RESET)
         A = self.A
+        sit = False
+        if s.sit_init_percent > 0:                                 # tron1_pf_ee.py:204-210: ONE coin per reset batch (R8)
+            coin = self.sit_coin if self.sit_coin is not None else float(philox.uniform(s.seed, self.common_step_counter, 0xFFFFFFFF, T.SITE_HOST, 0))
+            sit = coin < s.sit_init_percent
+        o["sit"] = sit
         noise = np.asarray(s.reset_dof_noise, f32)[None, :]        # go2_ts.py:86-91
         udof = self.u(T.SITE_DOF, np.arange(A), ids)
-        st["q"][ids] = (self.q0 + (f32(2) * noise * udof + (-noise)).astype(f32)).astype(f32)
+        if sit:
+            st["q"][ids] = np.asarray(s.sit_joint_angles, f32)[None, :]
+        else:
+            st["q"][ids] = (self.q0 + (f32(2) * noise * udof + (-noise)).astype(f32)).astype(f32)
         st["qd"][ids] = 0
         o["dof_pos"][ids], o["dof_vel"][ids] = st["q"][ids], 0
         uroot = self.u(T.SITE_ROOT, np.arange(8), ids)             # legged_robot.py:283-298
-        pos = (np.asarray(s.init_pos, f32)[None, :] + st["env_origins"][ids]).astype(f32)
+        pos = (np.asarray(s.sit_pos if sit else s.init_pos, f32)[None, :] + st["env_origins"][ids]).astype(f32)
         if s.heightfield:
             pos[:, :2] += self._range(-s.reset_root_xy, s.reset_root_xy, uroot[:, 0:2])
         st["base_pos"][ids] = pos
         qx = np.asarray(s.init_quat_xyzw, f32)
+        if sit:                                                    # quat_from_euler_xyz(0, pitch, 0), tron1_pf_ee.py:294-300
+            half = f32(s.sit_pitch_angle) * f32(0.5)
+            qx = np.array([0, np.sin(half), 0, np.cos(half)], f32)
         st["base_quat_wxyz"][ids] = np.array([qx[3], qx[0], qx[1], qx[2]], f32)
         lin = self._range(-s.reset_root_vel, s.reset_root_vel, uroot[:, 2:5])
         ang = self._range(-s.reset_root_vel, s.reset_root_vel, uroot[:, 5:8])
+        if sit:
+            lin, ang = np.zeros_like(lin), np.zeros_like(ang)
         st["base_lin_w"][ids], st["base_ang_w"][ids] = lin, ang
         st["base_lin_vel"][ids], st["base_ang_vel"][ids] = lin, ang
         quat = o["base_quat"].copy()
@@ -481,6 +545,14 @@ class EnvOracle:
             st[k][ids] = 0
         st["episode_length"][ids] = 0
         st["fail_buf"][ids] = 0
+        if s.gait_enabled:                                         # tron1_pf_ee.py:221-228
+            ug = self.u(T.SITE_GAIT, [0, 1], ids)
+            g = st["gait_state"]
+            g[ids, 0] = (f32(s.gait_theta_left) + ug[:, 0]).astype(f32)
+            g[ids, 1] = (g[ids, 0] + f32(s.gait_theta_right - s.gait_theta_left)).astype(f32)
+            g[ids, 2] = (ug[:, 1] * f32(s.gait_period)).astype(f32)
+            g[ids, 3] = (g[ids, 2] / f32(s.gait_period)).astype(f32)
+            g[ids, 4:8] = 0
         o["episode_means"] = {"rew_" + n: np.mean(st["episode_sums"][ids, i], dtype=f32) / f32(s.episode_length_s)
                               for i, n in enumerate(self.sum_names)}
         st["episode_sums"][ids] = 0
@@ -497,10 +569,38 @@ class EnvOracle:
             (o["dof_pos"] - self.q0) * f32(s.obs_scale_dof_pos), o["dof_vel"] * f32(s.obs_scale_dof_vel), st["actions"]],
             axis=1).astype(f32)
         clean = obs.copy()
-        if s.add_noise:
+        if s.add_noise and s.obs_kind != "tron1_pf_ee":
             un = self.u(T.SITE_OBS_NOISE, np.arange(obs.shape[1]))
             obs = (obs + ((f32(2) * un - f32(1)).astype(f32) * self.noise_vec[None, :]).astype(f32)).astype(f32)
         c = f32(s.clip_observations)
+        if s.obs_kind == "tron1_pf_ee":                            # tron1_pf_ee.py:53-141
+            g = st["gait_state"]
+            obs31 = np.concatenate([clean, g[:, 4:8]], axis=1).astype(f32)
+            noisy = obs31.copy()
+            if s.add_noise:
+                un = self.u(T.SITE_OBS_NOISE, np.arange(obs31.shape[1]))
+                noisy = (obs31 + ((f32(2) * un - f32(1)).astype(f32) * self.noise_vec[None, :]).astype(f32)).astype(f32)
+            dr = np.concatenate([st["friction"] - f32((s.friction_range[0] + s.friction_range[1]) / 2), st["added_mass"], st["com_bias"],
+                                 st["rand_push_vels"][:, :2], st["kp_scale"] - f32((s.kp_range[0] + s.kp_range[1]) / 2),
+                                 st["kd_scale"] - f32((s.kd_range[0] + s.kd_range[1]) / 2), st["joint_armature"], st["joint_friction"],
+                                 st["joint_damping"]], axis=1).astype(f32)
+            hobs = (np.clip(st["base_pos"][:, 2:3] - f32(s.height_obs_offset) - o["measured_heights"], f32(-1), f32(1))
+                    * f32(s.obs_scale_height)).astype(f32)
+            fz = o["feet_pos"][:, :, 2:3]
+            crit = np.concatenate([obs31, dr, o.get("exp_C_frc", np.zeros((self.N, 2), f32)), o["link_contact_states"], hobs,
+                                   o["normal_vector_around_feet"],
+                                   np.clip((fz - o["height_around_feet"]).reshape(self.N, -1), f32(-1), f32(1))], axis=1).astype(f32)
+            sc, so = self.widths["single_critic"], self.widths["obs"]
+            st["critic_hist"][:] = np.concatenate([st["critic_hist"][:, sc:], crit], axis=1)
+            st["obs_hist"][:] = np.concatenate([st["obs_hist"][:, so:], noisy], axis=1)
+            lin = (st["base_lin_vel"] * f32(s.obs_scale_lin_vel)).astype(f32)
+            clr = np.clip(o["feet_pos"][:, :, 2] - np.max(o["height_around_feet"], axis=-1) - f32(s.foot_height_offset), f32(-1), f32(1))
+            o["estimator_labels_buf"] = np.concatenate([lin, o["link_contact_states"], clr, o["normal_vector_around_feet"]], axis=1).astype(f32)
+            o["estimator_features_buf"] = np.clip(st["obs_hist"], -c, c)
+            o["privileged_obs_buf"] = np.clip(st["critic_hist"], -c, c)
+            o["obs_history"], o["critic_obs_buf"] = o["estimator_features_buf"], o["privileged_obs_buf"]
+            o["obs_buf"] = o["estimator_features_buf"]
+            return
         if s.obs_kind == "tron1_pf":                               # tron1_pf.py:15-70
             lin = (st["base_lin_vel"] * f32(s.obs_scale_lin_vel)).astype(f32)
             priv = np.concatenate([lin, clean, st["last_actions"], st["friction"] - f32((s.friction_range[0] + s.friction_range[1]) / 2),

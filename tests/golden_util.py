@@ -13,9 +13,9 @@ def load_golden(name):
     return g, s0
 
 
-def load_terrain():
-    from hcr_genesis_lr_cl_b200.terrain_assets import load_go2_rough_terrain
-    return load_go2_rough_terrain()
+def load_terrain(spec=None):
+    from hcr_genesis_lr_cl_b200.terrain_assets import load_go2_rough_terrain, terrain_for
+    return load_go2_rough_terrain() if spec is None else terrain_for(spec)
 
 
 def spec_for(g):

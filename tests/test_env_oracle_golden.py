@@ -9,13 +9,14 @@ from oracle.env_oracle import EnvOracle
 INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels")
 
 
-@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32"])
+@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32"])
 def test_env_oracle_reproduces_reference(name):
     g, s0 = load_golden(name)
     spec = spec_for(g)
-    hs, origins = load_terrain() if spec.heightfield else (None, None)
+    hs, origins = (load_terrain(spec) if spec.heightfield else (None, None))
     N, T_ = g["actions"].shape[1], g["actions"].shape[0]
     eo = EnvOracle(spec, N, hs, origins)
+    eo.reproduce_r18 = True            # pin the oracle on every env of the reference run, env 0 included (R18)
     for k, v in s0.items():
         if k in eo.st:
             eo.st[k][...] = v
@@ -33,7 +34,7 @@ def test_env_oracle_reproduces_reference(name):
                     projected_gravity=o["projected_gravity_obs"], friction=st["friction"], added_mass=st["added_mass"],
                     com_bias=st["com_bias"], kp_scale=st["kp_scale"], kd_scale=st["kd_scale"], rand_push_vels=st["rand_push_vels"],
                     actions_buf=st["actions"], last_actions=st["last_actions"], llast_actions=st["llast_actions"],
-                    terrain_levels=st["terrain_levels"], end_q=st["q"], end_qd=st["qd"])
+                    terrain_levels=st["terrain_levels"], end_q=st["q"], end_qd=st["qd"], gait_state=st["gait_state"])
         for k, r in ref.items():
             if k not in mine:
                 continue

@@ -45,12 +45,12 @@ def test_library_is_the_cuda_path(built_library):
     assert all(hasattr(lib, s) for s in _cabi.EXPORTED_SYMBOLS)
 
 
-@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32"])
+@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32"])
 def test_env_kernel_matches_reference_golden(name):
     """Injected post-physics states from the reference run -> every output of the fused kernel."""
     g, s0 = load_golden(name)
     spec = spec_for(g)
-    terrain = load_terrain() if spec.heightfield else None
+    terrain = load_terrain(spec) if spec.heightfield else None
     N, T_ = g["actions"].shape[1], g["actions"].shape[0]
     env = _env(spec, N, terrain)
     sim = env.simulator
@@ -64,19 +64,25 @@ def test_env_kernel_matches_reference_golden(name):
         sim.load_state({PH[k]: v for k, v in phys_at(g, t).items()})
         sim._buf["global_flags"][0] = int((np.abs(phys_at(g, t)["qd"]) > 4).any())   # what the dynamics kernel would leave (CaT R4)
         env.common_step_counter += 1
+        env._set_step_flags()
         sim.fused_post_step(env.common_step_counter, env.command_ranges["lin_vel_x"])
         st = sim.get_state()
         ref = out_at(g, t)
         mine = dict(st, actions_buf=st["actions"], end_q=st["dof_pos"], end_qd=st["dof_vel"])
-        if spec.obs_kind == "tron1_pf":                      # the returned obs / privileged obs are the frame stacks
+        if spec.obs_kind in ("tron1_pf", "tron1_pf_ee"):     # the returned obs / privileged obs are the frame stacks
+            mine["estimator_labels_buf"] = st["privileged_obs_buf"]
             mine["obs_buf"], mine["privileged_obs_buf"] = st[f"obs_history{sim._parity}"], st[f"critic_obs{sim._parity}"]
+        skip0 = spec.obs_kind == "tron1_pf_ee"               # R18: env 0 is coupled to all envs in the reference; not reproduced
         for k, r in ref.items():
             if k not in mine or k in ("end_state",):
                 continue
+            m = np.asarray(mine[k]).reshape(r.shape)
+            if skip0 and m.ndim >= 1 and m.shape[0] == N:
+                m, r = m[1:], r[1:]
             if k in ints:
-                assert np.array_equal(mine[k].astype(np.int64).reshape(r.shape), r.astype(np.int64)), f"step {t}: {k} not bit-exact"
+                assert np.array_equal(m.astype(np.int64), r.astype(np.int64)), f"step {t}: {k} not bit-exact"
             else:
-                _close(mine[k], r, what=f"step {t}: {k}")
+                _close(m, r, what=f"step {t}: {k}")
         for hk, name in (("obs_history", f"obs_history{sim._parity}"), ("critic_obs_buf", f"critic_obs{sim._parity}")):
             if f"hist{t}/{hk}" in g:
                 _close(st[name], g[f"hist{t}/{hk}"], what=f"step {t}: {hk}")
@@ -115,17 +121,20 @@ def _random_state(spec, N, terrain, seed):
     st["com_bias"] = rng.uniform(-0.03, 0.03, (N, 3)).astype(np.float32)
     st["kp_scale"] = rng.uniform(0.8, 1.2, (N, A)).astype(np.float32)
     st["kd_scale"] = rng.uniform(0.8, 1.2, (N, A)).astype(np.float32)
+    st["joint_armature"] = rng.uniform(0.11, 0.13, (N, 1)).astype(np.float32)     # consumed only when the task randomises them
+    st["joint_friction"] = rng.uniform(0.0, 0.01, (N, 1)).astype(np.float32)
+    st["joint_damping"] = rng.uniform(1.4, 1.45, (N, 1)).astype(np.float32)
     return st, model
 
 
-@pytest.mark.parametrize("task", ["go2_ts", "go2", "tron1_pf"])
+@pytest.mark.parametrize("task", ["go2_ts", "go2", "tron1_pf", "tron1_pf_ee"])
 def test_dynamics_kernel_matches_oracle(task):
     """One policy step (4 substeps) of the warp-per-env kernel vs the fp32 C oracle on seeded states."""
     from emu_util import oracle_params, oracle_policy_step
     from hcr_genesis_lr_cl_b200 import task_spec as T
     from oracle.physics import PhysicsOracle
     spec = T.PRESETS[task]()
-    terrain = load_terrain() if spec.heightfield else None
+    terrain = load_terrain(spec) if spec.heightfield else None
     N = 256
     st, model = _random_state(spec, N, terrain, seed=7)
     env = _env(spec, N, terrain)
@@ -150,12 +159,14 @@ def test_dynamics_kernel_matches_oracle(task):
             assert err.max() < tol * scale(r), f"{k}: abs err {err.max():.3e} (scale {scale(r):.2f})"
 
 
-@pytest.mark.parametrize("task", ["go2_ts", "go2_cat"])
+@pytest.mark.parametrize("task", ["go2_ts", "go2_cat", "tron1_pf_ee"])
 def test_env_kernel_matches_numpy_oracle_seeded(task):
     """Seeded random states at N=512 through several fused steps vs the numpy restatement (all phases, with resets)."""
     from hcr_genesis_lr_cl_b200 import task_spec as T
     from oracle.env_oracle import EnvOracle
-    spec, terrain = T.PRESETS[task](), load_terrain()
+    spec = T.PRESETS[task]()
+    terrain = load_terrain(spec)
+    F = len(spec.link_groups(spec.load_model())[0])
     N = 512
     st, model = _random_state(spec, N, terrain, seed=11)
     rng = np.random.default_rng(5)
@@ -163,8 +174,11 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
     st["episode_length"][::7] = 499
     st["fail_buf"] = rng.integers(0, 6, N).astype(np.int32)
     st["commands"] = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
-    st["feet_air_time"] = rng.uniform(0, 0.4, (N, 4)).astype(np.float32)
-    st["last_contacts"] = rng.integers(0, 2, (N, 4)).astype(np.uint8)
+    st["feet_air_time"] = rng.uniform(0, 0.4, (N, F)).astype(np.float32)
+    st["last_contacts"] = rng.integers(0, 2, (N, F)).astype(np.uint8)
+    st["gait_state"] = np.concatenate([rng.uniform(0, 1, (N, 1)), rng.uniform(0, 1, (N, 1)) + 0.5, rng.integers(0, 25, (N, 1)) * 0.02,
+                                       np.zeros((N, 5))], axis=1).astype(np.float32)
+    st["gait_state"][:, 3] = st["gait_state"][:, 2] / np.float32(0.5)
     env = _env(spec, N, terrain)
     sim = env.simulator
     sim.load_state(st)
@@ -189,6 +203,7 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
         eo.pre_step(a)
         o = eo.post_step(phys)
         env.common_step_counter += 1
+        env._set_step_flags()
         sim.fused_post_step(env.common_step_counter, env.command_ranges["lin_vel_x"])
         out = sim.get_state()
         total_resets += int(o["reset_buf"].sum())
@@ -201,8 +216,12 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
         _close(out["rew_buf"], o["rew_buf"], what=f"step {t}: rew")
         if spec.cat_enabled:
             assert np.array_equal(out["cstr_prob"], o["cstr_prob"]), f"step {t}: cstr_prob"
-        _close(out["obs_buf"], o["obs_buf"], what=f"step {t}: obs")
-        _close(out["privileged_obs_buf"], o["privileged_obs_buf"], what=f"step {t}: priv")
+        if spec.obs_kind == "tron1_pf_ee":
+            _close(out["privileged_obs_buf"], o["estimator_labels_buf"], what=f"step {t}: labels")
+            _close(out["gait_state"], eo.st["gait_state"], what=f"step {t}: gait_state")
+        else:
+            _close(out["obs_buf"], o["obs_buf"], what=f"step {t}: obs")
+            _close(out["privileged_obs_buf"], o["privileged_obs_buf"], what=f"step {t}: priv")
         _close(out[f"obs_history{sim._parity}"], o["obs_history"], what=f"step {t}: obs_history")
         _close(out[f"critic_obs{sim._parity}"], o["critic_obs_buf"], what=f"step {t}: critic")
         _close(out["episode_sums"], eo.st["episode_sums"], what=f"step {t}: episode_sums")

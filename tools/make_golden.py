@@ -48,13 +48,15 @@ class Injector:
         k = shape[0]
         ncol = shape[1] if len(shape) > 1 else 1
         site = self.site
-        if site == T.SITE_DOF and ncol == 4:
-            cols = 3 * np.arange(4) + self.call            # go2_ts.py:86-91: hips, thighs, calves
+        if site == T.SITE_DOF and ncol * 3 == self.env.num_actions:
+            cols = 3 * np.arange(ncol) + self.call         # go2_ts.py:86-91 / tron1_pf_ee.py:276-281: hips, thighs, calves
         elif site == T.SITE_KP:
             site, cols = (T.SITE_KP if self.call == 0 else T.SITE_KD), np.arange(ncol)
         elif site == T.SITE_ROOT:                      # fixed slots: xy -> 0,1; lin vel -> 2..4; ang vel -> 5..7 (legged_robot.py:283-298)
             if ncol == 2:
                 cols = np.arange(2)
+            elif ncol == 1:                                # torch_rand_float(c, c, ...) constants of the sit pose (tron1_pf_ee.py:294-300)
+                cols = np.arange(1) + 8
             else:
                 cols = 2 + 3 * self.col + np.arange(3)
                 self.col += 1
@@ -100,10 +102,15 @@ class Injector:
         def randint_like(t, high, **k):
             return torch.clamp((self.draw(tuple(t.shape)) * high).to(t.dtype), max=high - 1)
         torch.randint_like = randint_like
+        # tron1_pf_ee.py:204: one host coin per reset batch (R8)
+        np.random.random = lambda *a, **k: float(philox.uniform(self.seed, self.env.common_step_counter, 0xFFFFFFFF, T.SITE_HOST, 0))
 
         env._resample_commands = self.ctx(env._resample_commands, None, name="resample")
         env._reset_dofs = self.ctx(env._reset_dofs, T.SITE_DOF)
         env._reset_root_states = self.ctx(env._reset_root_states, T.SITE_ROOT)
+        if hasattr(env, "_reset_root_states_sit_pose"):
+            env._reset_root_states_sit_pose = self.ctx(env._reset_root_states_sit_pose, T.SITE_ROOT)
+            env._reset_dofs_sit_pose = self.ctx(env._reset_dofs_sit_pose, T.SITE_DOF)
         env.compute_observations = self.ctx(env.compute_observations, T.SITE_OBS_NOISE, ids_arg=False)
         sim.update_terrain_curriculum = self.ctx(sim.update_terrain_curriculum, T.SITE_LEVEL)
         sim.push_robots = self.ctx(sim.push_robots, T.SITE_PUSH, ids_arg=False)
@@ -116,10 +123,14 @@ class Injector:
 
         def reset_idx(env_ids):
             self.in_reset = True
+            prev = (self.site, self.ids, self.col, self.call)
+            ids = env_ids.cpu().numpy() if hasattr(env_ids, "cpu") else np.asarray(env_ids)
+            self.site, self.ids, self.col, self.call = T.SITE_GAIT, ids, 0, 0     # direct torch.rand calls (gait phase)
             try:
                 return orig_reset(env_ids)
             finally:
                 self.in_reset = False
+                self.site, self.ids, self.col, self.call = prev
         env.reset_idx = reset_idx
 
 
@@ -147,6 +158,8 @@ def snapshot(env, spec, sum_names):
         st["terrain_levels"], st["terrain_types"] = n(sim._terrain_levels), n(sim._terrain_types)
     else:
         st["terrain_levels"] = st["terrain_types"] = np.zeros(env.num_envs, np.int32)
+    if hasattr(env, "gait_time"):
+        st["gait_state"] = np.concatenate([n(env.theta), n(env.gait_time), n(env.phi), n(env.clock_input)], axis=1)
     if hasattr(env, "obs_history_deque"):
         st["obs_hist"] = np.concatenate([n(x) for x in env.obs_history_deque], axis=1)
         st["critic_hist"] = np.concatenate([n(x) for x in env.critic_obs_deque], axis=1)
@@ -258,9 +271,13 @@ def main():
             o["link_contact_states"] = n(sim._link_contact_states)
         if hasattr(env, "cstr_prob"):
             o["cstr_prob"] = n(env.cstr_prob)
-        if ret[1] is not None:
+        if args.task == "tron1_pf_ee":
+            o["estimator_labels_buf"] = n(ret[1])
+            o["privileged_obs_buf"] = n(ret[2])
+            o["gait_state"] = np.concatenate([n(env.theta), n(env.gait_time), n(env.phi), n(env.clock_input)], axis=1)
+        elif ret[1] is not None:
             o["privileged_obs_buf"] = n(ret[1])
-        if hasattr(env, "obs_history") and t in (args.steps // 2, args.steps - 1):
+        if hasattr(env, "obs_history") and args.task != "tron1_pf_ee" and t in (args.steps // 2, args.steps - 1):
             rec[f"hist{t}/obs_history"] = n(env.obs_history)
             rec[f"hist{t}/critic_obs_buf"] = n(env.critic_obs_buf)
         for k, v in o.items():
@@ -280,7 +297,8 @@ def main():
     resets = int(rec["out/reset_buf"].sum())
     print(f"wrote {out}: {os.path.getsize(out)/1e3:.0f} kB, resets={resets}, time_outs={int(rec['out/time_out_buf'].sum())}")
     if spec.heightfield:
-        tpath = os.path.join(ROOT, "hcr_genesis_lr_cl_b200", "assets", "go2_rough_terrain.npz")
+        tname = "tron1_rough" if spec.robot == "tron1_pf" else "go2_rough"
+        tpath = os.path.join(ROOT, "hcr_genesis_lr_cl_b200", "assets", tname + "_terrain.npz")
         if not os.path.exists(tpath):
             np.savez_compressed(tpath, height_samples=sim._height_samples.numpy().astype(np.int16),
                                 terrain_origins=sim._terrain_origins.numpy().astype(np.float32))
