@@ -141,6 +141,10 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
         sf("TF_SIT_QUAT", v, k)
     for j, v in enumerate(spec.sit_joint_angles):
         sf("TF_SIT_DOF_POS", v, j)
+    sf("TF_EULER_SIGMA", spec.euler_tracking_sigma)
+    for gi, th in enumerate(spec.gait_theta_lists[:H["B200_MAX_GAITS"]]):
+        for fi, v in enumerate(th):
+            sf("TF_GAIT_THETA", v, gi * H["B200_MAX_FEET"] + fi)
     sf("TF_CAT_SOFT_P", spec.cat_soft_p); sf("TF_CAT_ACTION_RATE", spec.cat_action_rate)
     sf("TF_CAT_MIN_BASE_HEIGHT", spec.cat_min_base_height); sf("TF_CAT_MAX_PROJ_GRAV", spec.cat_max_projected_gravity)
     lim = soft_dof_limits(spec, model)
@@ -190,6 +194,7 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     si("TI_CAT", spec.cat_enabled); si("TI_CAT_GLOBAL_STANDSTILL", spec.cat_stand_still_global)
     si("TI_DOUBLE_SHIFT", spec.double_shift_actions); si("TI_N_SUMS", len(spec.episode_sum_names()))
     si("TI_GAIT", spec.gait_enabled); si("TI_CLEARANCE_MODE", spec.foot_clearance_mode)
+    si("TI_BEHAVIOR", spec.behavior_enabled); si("TI_BEHAVIOR_INTERVAL", max(int(spec.behavior_resampling_time / spec.dt), 1))
     for k, v in enumerate(feet):
         si("TI_FEET_LINKS", v, k)
     for k, v in enumerate(pen):
@@ -235,7 +240,7 @@ def buffer_shapes(spec: T.TaskSpec, model: RobotModel, N: int) -> "OrderedDict[s
         obs_buf=(N, w["obs"]), privileged_obs_buf=(N, max(w["priv"], 1)),
         obs_history0=(N, max(w["hist"], 1)), obs_history1=(N, max(w["hist"], 1)),
         critic_obs0=(N, max(w["critic"], 1)), critic_obs1=(N, max(w["critic"], 1)),
-        rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), gait_state=(N, 8), height_cells=(N, P, 2), stats=(stats_base(nsum) + STATS_RING * (max(nsum, 1) + 2),), cstr_prob=(N,), global_flags=(4,),
+        rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), gait_state=(N, H["B200_GAIT_STATE"]), height_cells=(N, P, 2), stats=(stats_base(nsum) + STATS_RING * (max(nsum, 1) + 2),), cstr_prob=(N,), global_flags=(4,),
     )
     return OrderedDict((name, (shp[name], _NP[ct])) for name, ct in BUFFER_FIELDS)
 
@@ -280,6 +285,8 @@ def load_library() -> ctypes.CDLL:
     lib.b200_env_post_step.restype = ctypes.c_int
     lib.b200_set_step_flags.argtypes = [vp, ctypes.c_int]
     lib.b200_set_step_flags.restype = ctypes.c_int
+    lib.b200_set_behavior.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+    lib.b200_set_behavior.restype = ctypes.c_int
     lib.b200_reset_all.argtypes = [vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, vp]
     lib.b200_reset_all.restype = ctypes.c_int
     lib.b200_kernel_info.argtypes = [vp, ctypes.c_char_p, ip, ip, ip, ip]
@@ -293,4 +300,4 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = ["b200_create", "b200_destroy", "b200_set_terrain", "b200_bind_buffers", "b200_dynamics_step",
-                    "b200_env_post_step", "b200_set_step_flags", "b200_reset_all", "b200_kernel_info", "b200_launch_count", "b200_last_error"]
+                    "b200_env_post_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_launch_count", "b200_last_error"]

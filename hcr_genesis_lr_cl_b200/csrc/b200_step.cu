@@ -26,6 +26,8 @@ struct B200Handle {
     long long launches = 0;
     int dyn_smem = 0, env_smem = 0;
     int sit_pose = 0;
+    float beh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int gait_cb = 0, gait_reset = 0;
 };
 
 extern "C" {
@@ -118,6 +120,8 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     cudaStream_t s = (cudaStream_t)stream;
     if (mask & PHASE_RESET) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 3), s));
     EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.parity = parity & 1; call.phase_mask = mask; call.force_reset = force; call.sit_pose = h->sit_pose;
+    for (int k = 0; k < 8; k++) call.beh[k] = h->beh[k];
+    call.gait_cb = h->gait_cb; call.gait_reset = h->gait_reset;
     const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
     env_post_step_kernel<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call);
     h->launches++;
@@ -139,6 +143,15 @@ int b200_env_post_step(B200Handle *h, long long step, float lo, float span, int 
 int b200_set_step_flags(B200Handle *h, int sit_pose) {
     if (!h) return fail("b200_set_step_flags: null handle");
     h->sit_pose = sit_pose ? 1 : 0;
+    return 0;
+}
+
+int b200_set_behavior(B200Handle *h, const float *ranges8, int gait_callback, int gait_reset) {
+    if (!h || !ranges8) return fail("b200_set_behavior: null argument");
+    if (gait_callback < 0 || gait_callback >= B200_MAX_GAITS || gait_reset < 0 || gait_reset >= B200_MAX_GAITS) return fail("b200_set_behavior: gait index out of range");
+    // stored as (lower, span) with span rounded like torch_rand_float's python-float subtraction
+    for (int k = 0; k < 4; k++) { h->beh[2 * k] = ranges8[2 * k]; h->beh[2 * k + 1] = (float)((double)ranges8[2 * k + 1] - (double)ranges8[2 * k]); }
+    h->gait_cb = gait_callback; h->gait_reset = gait_reset;
     return 0;
 }
 

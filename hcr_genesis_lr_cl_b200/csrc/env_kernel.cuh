@@ -25,15 +25,15 @@
 #include "dynamics_kernel.cuh"   // TaskDev, TerrainDev
 
 #define ENV_WARPS_PER_BLOCK 4
-#define ES_OBS 0                   // clean obs [48]
-#define ES_NOISY 48                // noisy obs [48]
-#define ES_CRIT 96                 // single critic frame [<=192]
-#define ES_PRIV 288                // privileged obs [<=112]
-#define ES_MH 400                  // measured heights of this env [<=96]   (outputs that later phases re-read:
-#define ES_LCS 496                 // link contact states [<=32]             kept on chip instead of a global round trip)
-#define ES_HAF 528                 // height around feet [4*9]
-#define ES_NV 564                  // terrain normals around feet [4*3]
-#define ES_TOTAL 576
+#define ES_OBS 0                   // clean obs [B200_MAX_OBS = 64]
+#define ES_NOISY 64                // noisy obs [64]
+#define ES_CRIT 128                 // single critic frame [<=192]
+#define ES_PRIV 320                // privileged obs [<=112]
+#define ES_MH 432                  // measured heights of this env [<=96]   (outputs that later phases re-read:
+#define ES_LCS 528                 // link contact states [<=32]             kept on chip instead of a global round trip)
+#define ES_HAF 560                 // height around feet [4*9]
+#define ES_NV 596                  // terrain normals around feet [4*3]
+#define ES_TOTAL 608
 #define ENV_IN_WORDS 288           // staged per-env input rows (all small state tensors), words per env
 // CTA-level staging of the two history stacks (TMA bulk copies): the rows of a CTA's ENV_WARPS_PER_BLOCK consecutive
 // envs form one contiguous, 16-byte aligned slab in HBM even though a single 885-float critic row is not.
@@ -47,6 +47,8 @@ struct EnvCall {
     int phase_mask;
     int force_reset;     // b200_reset_all: run only the reset phase, for every env
     int sit_pose;        // envs resetting in this call start in the sit pose (one host coin per step, tron1_pf_ee.py:204-210)
+    float beh[8];        // go2_wtw behaviour ranges {gait period, base height, foot clearance, pitch} x {lo, span}
+    int gait_cb, gait_reset;   // gait index the host drew for the callback / reset resampling of this step
 };
 
 // shared memory per CTA: mbarrier + per warp (scratch, staged history row, staged critic row, staged input rows)
@@ -139,9 +141,29 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     const int ttype = ti[TI_TERRAIN_CURRICULUM] ? (int)R.terrain_types[env] : 0;
     f3 push_vel = mk3(R.rand_push_vels[env * 3], R.rand_push_vels[env * 3 + 1], 0.f);
     f3 lin_b, ang_b, grav;           // body-frame velocities, projected gravity
+    float e_roll = 0.f, e_pitch = 0.f;   // base_euler (get_euler_xyz) for tracking_orientation
+    if (ti[TI_BEHAVIOR]) {
+        e_roll = atan2f(2.0f * (Qw * Qx + Qy * Qz), Qw * Qw - Qx * Qx - Qy * Qy + Qz * Qz);
+        const float sinp = 2.0f * (Qw * Qy - Qz * Qx);
+        e_pitch = fabsf(sinp) >= 1.f ? copysignf(1.5707963267948966f, sinp) : asinf(sinp);
+    }
     // periodic-gait state (tron1_pf_ee.py:186-197): theta_left/right, gait time, phase
-    float th0 = 0.f, th1 = 0.f, gtime = 0.f, gphi = 0.f, expc_frc = 0.f;
-    if (ti[TI_GAIT]) { th0 = R.gait_state[env * 8]; th1 = R.gait_state[env * 8 + 1]; gtime = R.gait_state[env * 8 + 2]; gphi = R.gait_state[env * 8 + 3]; }
+    float th0 = 0.f, th1 = 0.f, th2 = 0.f, th3 = 0.f, gtime = 0.f, gphi = 0.f, gper = tf[TF_GAIT_PERIOD], bh_t = 0.f, fc_t = 0.f, pt_t = 0.f, expc_frc = 0.f;
+    if (ti[TI_GAIT]) {
+        const float *gs = R.gait_state + env * B200_GAIT_STATE;
+        th0 = gs[B200_GS_TH]; th1 = gs[B200_GS_TH + 1]; th2 = gs[B200_GS_TH + 2]; th3 = gs[B200_GS_TH + 3]; gtime = gs[B200_GS_GT]; gphi = gs[B200_GS_PHI];
+        if (ti[TI_BEHAVIOR]) { gper = gs[B200_GS_PER]; bh_t = gs[B200_GS_BH]; fc_t = gs[B200_GS_FC]; pt_t = gs[B200_GS_PT]; }
+    }
+    // go2_wtw.py:180-217: behaviour parameters of one env (the pronk/bound clearance clamp is applied per resampled env)
+    auto resample_behavior = [&](int site, int gait) {
+        gper = rand_range(call.beh[0], call.beh[1], rng.u(site, 0));
+        bh_t = rand_range(call.beh[2], call.beh[3], rng.u(site, 1));
+        fc_t = rand_range(call.beh[4], call.beh[5], rng.u(site, 2));
+        pt_t = rand_range(call.beh[6], call.beh[7], rng.u(site, 3));
+        const float *tl = tf + TF_GAIT_THETA + gait * B200_MAX_FEET;
+        th0 = tl[0]; th1 = tl[1]; th2 = tl[2]; th3 = tl[3];
+        if (th0 == 0.f && th1 == 0.f && ((th2 == 0.f && th3 == 0.f) || (th2 == 0.5f && th3 == 0.5f))) fc_t = call.beh[4];
+    };
     // ------------------------------------------------------------------ per-lane values
     const bool jl = lane < A, fl = lane < F;
     float qj = jl ? R.dof_pos[env * A + lane] : 0.f, qdj = jl ? R.dof_vel[env * A + lane] : 0.f;
@@ -281,6 +303,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         }
     }
 
+    if ((pm & PHASE_CALLBACK) && ti[TI_BEHAVIOR] && ep_len % ti[TI_BEHAVIOR_INTERVAL] == 0) resample_behavior(SITE_BEHAVIOR, call.gait_cb);   // go2_wtw.py:258-263
     // ================================================================== check_termination
     bool time_out = false, reset = false;
     if (pm & PHASE_TERMINATION) {
@@ -357,12 +380,15 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 for (int pt = lane; pt < P; pt += 32) s += bp.z - (ti[TI_MEASURE_HEIGHTS] ? es[ES_MH + pt] : 0.f);
                 const float m = warp_sum(s) / (float)P - tf[TF_BASE_HEIGHT_TARGET];
                 r = m * m; break; }
-            case RW_BIPED_PERIODIC_GAIT: {                        // tron1_pf_ee.py:335-437, "step" indicator; feet 0 (left), 1 (right)
+            case RW_BIPED_PERIODIC_GAIT:                          // tron1_pf_ee.py:335-437 / go2_wtw.py:374-478, "step" indicator
+            case RW_QUAD_PERIODIC_GAIT: {
+                const int nf = id == RW_BIPED_PERIODIC_GAIT ? 2 : 4;
                 float term = 0.f;
-                if (lane < 2) {
+                if (lane < nf) {
                     const float *f = R.link_contact_forces + (env * L + ti[TI_FEET_LINKS + lane]) * 3;
                     const float q_frc = norm3_rn(f[0], f[1], f[2]), q_spd = norm3_rn(fvel.x, fvel.y, fvel.z);
-                    const float ph = __fmul_rn(fmodf(__fadd_rn(gphi, lane == 0 ? th0 : th1), 1.0f), 6.2831853071795862f);
+                    const float thl = lane == 0 ? th0 : (lane == 1 ? th1 : (lane == 2 ? th2 : th3));
+                    const float ph = __fmul_rn(fmodf(__fadd_rn(gphi, thl), 1.0f), 6.2831853071795862f);
                     const bool swing = ph >= 0.f && ph < tf[TF_GAIT_B_SWING], stance = ph >= tf[TF_GAIT_B_SWING] && ph < 6.2831853071795862f;
                     expc_frc = swing ? -1.f : 0.f;
                     term = __fadd_rn(__fmul_rn(stance ? -1.f : 0.f, q_spd), __fmul_rn(expc_frc, q_frc));
@@ -433,8 +459,13 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             case RW_TRACKING_BASE_HEIGHT: {                       // tron1_pf_ee.py:439-444
                 float s = 0.f;
                 for (int pt = lane; pt < P; pt += 32) s += bp.z - (ti[TI_MEASURE_HEIGHTS] ? es[ES_MH + pt] : 0.f);
-                const float m = warp_sum(s) / (float)P - tf[TF_BASE_HEIGHT_TARGET];
+                const float m = warp_sum(s) / (float)P - (ti[TI_BEHAVIOR] ? bh_t : tf[TF_BASE_HEIGHT_TARGET]);
                 r = expf(-(m * m) / tf[TF_BASE_HEIGHT_SIGMA]); break; }
+            case RW_TRACKING_FOOT_CLEARANCE: {                    // go2_wtw.py:502-518
+                float s = 0.f;
+                if (fl) { const float e = fpos.z - fc_t - tf[TF_FOOT_HEIGHT_OFFSET]; s = sqrtf(fvel.x * fvel.x + fvel.y * fvel.y) * e * e; }
+                r = expf(-warp_sum(s) / tf[TF_FOOT_CLEARANCE_SIGMA]); break; }
+            case RW_TRACKING_ORIENTATION: { const float ep = e_pitch - pt_t; r = expf(-(e_roll * e_roll + ep * ep) / tf[TF_EULER_SIGMA]); break; }   // go2_wtw.py:497-500
             case RW_TRACKING_LIN_VEL: { const float ex = cmd0 - lin_b.x, ey = cmd1 - lin_b.y; r = expf(-(ex * ex + ey * ey) / tf[TF_TRACKING_SIGMA]); break; }
             default: break;
             }
@@ -457,8 +488,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
 
     if (ti[TI_GAIT] && (pm & PHASE_REWARD)) {                    // tron1_pf_ee.py:27-35: advance the gait clock after the reward
         gtime = __fadd_rn(gtime, dt);
-        if (gtime >= __fsub_rn(tf[TF_GAIT_PERIOD], __fmul_rn(dt, 0.5f))) gtime = 0.f;
-        gphi = __fdiv_rn(gtime, tf[TF_GAIT_PERIOD]);
+        if (gtime >= __fsub_rn(gper, __fmul_rn(dt, 0.5f))) gtime = 0.f;
+        gphi = __fdiv_rn(gtime, gper);
     }
     // ================================================================== reset_idx
     f3 grav_obs = grav;
@@ -485,6 +516,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             new_level = lv;
             if (lane < 3) B.env_origins[env * 3 + lane] = comp3(origin, lane);
         }
+        if (ti[TI_BEHAVIOR]) resample_behavior(SITE_BEHAVIOR_RESET, call.gait_reset);   // go2_wtw.py:124-126, before the commands
         {   // _resample_commands(env_ids)
             cmd0 = rand_range(call.vx_lo, call.vx_span, rng.u(SITE_CMD_RESET, 0));
             cmd1 = rand_range(tf[TF_CMD_VY_LO], tf[TF_CMD_VY_SPAN], rng.u(SITE_CMD_RESET, 1));
@@ -547,11 +579,12 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
 #undef DR_PUT
         if (lane < 3 * F) B.last_feet_vel[env * 3 * F + lane] = 0.f;
         for (int e = lane; e < 48; e += 32) B.contact_warm[env * 48 + e] = 0.f;    // teleported: the contact warm start is stale
-        if (ti[TI_GAIT]) {                                                          // tron1_pf_ee.py:221-228
+        if (ti[TI_BEHAVIOR]) { gtime = 0.f; gphi = 0.f; }                               // go2_wtw.py:139-142
+        else if (ti[TI_GAIT]) {                                                     // tron1_pf_ee.py:221-228
             th0 = __fadd_rn(tf[TF_GAIT_THETA_LEFT], rng.u(SITE_GAIT, 0));
             th1 = __fadd_rn(th0, tf[TF_GAIT_THETA_RIGHT]);                              // TF_GAIT_THETA_RIGHT holds right - left
-            gtime = __fmul_rn(rng.u(SITE_GAIT, 1), tf[TF_GAIT_PERIOD]);
-            gphi = __fdiv_rn(gtime, tf[TF_GAIT_PERIOD]);
+            gtime = __fmul_rn(rng.u(SITE_GAIT, 1), gper);
+            gphi = __fdiv_rn(gtime, gper);
         }
         fat = 0.f;
         ep_len = 0; fail_cnt = 0;
@@ -568,12 +601,21 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         if (lane < n_sums) B.episode_sums[env * n_sums + lane] = my_sum;
         if (fl) B.feet_air_time[env * F + lane] = fat;
     }
-    float clk = 0.f;                 // clock_input[lane], lanes 0..3 (tron1_pf_ee.py:258-263)
+    float clk = 0.f;                 // clock_input[lane]: sin for lanes 0..F-1, cos for lanes F..2F-1 (tron1_pf_ee.py:258-263, go2_wtw.py:251-256)
     if (ti[TI_GAIT] && (pm & PHASE_OBSERVE)) {
-        const float arg = __fmul_rn(6.2831853071795862f, __fadd_rn(gphi, (lane & 1) == 0 ? th0 : th1));
-        clk = lane < 2 ? sinf(arg) : cosf(arg);
-        const float clk_lo = __shfl_sync(B200_FULL_MASK, clk, (lane + 28) & 31);    // lanes 4..7 <- clock of lanes 0..3
-        if (lane < 8) B.gait_state[env * 8 + lane] = lane == 0 ? th0 : (lane == 1 ? th1 : (lane == 2 ? gtime : (lane == 3 ? gphi : clk_lo)));
+        const int fi = lane < F ? lane : lane - F;
+        const float thl = fi == 0 ? th0 : (fi == 1 ? th1 : (fi == 2 ? th2 : th3));
+        const float arg = __fmul_rn(6.2831853071795862f, __fadd_rn(gphi, thl));
+        clk = lane < F ? sinf(arg) : cosf(arg);
+        const float clk_sh = __shfl_sync(B200_FULL_MASK, clk, (lane + 32 - B200_GS_CLK) & 31);    // lane B200_GS_CLK + i <- clock of lane i
+        if (lane < B200_GAIT_STATE) {
+            float v = 0.f;
+            if (lane < 4) v = lane == 0 ? th0 : (lane == 1 ? th1 : (lane == 2 ? th2 : th3));
+            else if (lane == B200_GS_GT) v = gtime; else if (lane == B200_GS_PHI) v = gphi; else if (lane == B200_GS_PER) v = gper;
+            else if (lane == B200_GS_BH) v = bh_t; else if (lane == B200_GS_FC) v = fc_t; else if (lane == B200_GS_PT) v = pt_t;
+            else if (lane < B200_GS_CLK + 2 * F) v = clk_sh;
+            B.gait_state[env * B200_GAIT_STATE + lane] = v;
+        }
     }
     __syncwarp();   // DR parameters written above are re-read below by other lanes
 
@@ -594,7 +636,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         }
         __syncwarp();
         const float clipo = tf[TF_CLIP_OBS];
-        for (int e = lane; e < (ti[TI_OBS_KIND] == 4 ? 0 : NO); e += 32) {
+        for (int e = lane; e < (ti[TI_OBS_KIND] >= 4 ? 0 : NO); e += 32) {
             float v = ob[e];
             if (ti[TI_ADD_NOISE]) {
                 const float u = rng.u(SITE_OBS_NOISE, e);
@@ -603,12 +645,54 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             nz[e] = v;
             B.obs_buf[env * NO + e] = fminf(fmaxf(v, -clipo), clipo);
         }
-        if (ti[TI_OBS_KIND] == 4) {   // tron1_pf_ee.py:53-141: features = 10 x 31 noisy frames, labels 17, critic = 10 x 134
+        if (ti[TI_OBS_KIND] == 5) {   // go2_wtw.py:53-111: obs_buf = 5 x 61 noisy frames, privileged_obs_buf = 5 x 99 critic frames
+            const int SC = ti[TI_SINGLE_CRITIC], NB = 9 + 3 * A;
+            float *cr = es + ES_CRIT;
+            const bool cleared = (pm & PHASE_RESET) && reset;
+            if (lane < 2 * F) ob[NB + lane] = clk;
+            if (lane == 0) { float *d = ob + NB + 2 * F; d[0] = gper; d[1] = bh_t; d[2] = fc_t; d[3] = pt_t; d[4] = th0; d[5] = th1; d[6] = th2; d[7] = th3; }
+            __syncwarp();
+            for (int e = lane; e < NO; e += 32) {
+                float v = ob[e];
+                if (ti[TI_ADD_NOISE]) v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(2.0f, rng.u(SITE_OBS_NOISE, e)), 1.0f), tf[TF_NOISE_VEC + e]));
+                nz[e] = fminf(fmaxf(v, -clipo), clipo);
+                B.obs_buf[env * NO + e] = nz[e];
+                cr[e] = fminf(fmaxf(ob[e], -clipo), clipo);
+            }
+            if (lane < 3) cr[NO + lane] = __fmul_rn(comp3(lin_b, lane), tf[TF_OS_LIN_VEL]);
+            if (lane == 0) {
+                float *d = cr + NO + 3;
+                d[0] = push_vel.x; d[1] = push_vel.y; d[2] = R.added_mass[env]; d[3] = R.friction[env];
+                d[4] = R.com_bias[env * 3]; d[5] = R.com_bias[env * 3 + 1]; d[6] = R.com_bias[env * 3 + 2];
+            }
+            if (jl) { cr[NO + 10 + lane] = R.kp_scale[env * A + lane]; cr[NO + 10 + A + lane] = R.kd_scale[env * A + lane]; }
+            if (fl) cr[NO + 10 + 2 * A + lane] = expc_frc;      // exp_C_frc of FL, FR, RL, RR as left by the reward (R13)
+            __syncwarp();
+            for (int e = lane; e < SC; e += 32) cr[e] = fminf(fmaxf(cr[e], -clipo), clipo);
+            __syncwarp();
+            if (hrow != nullptr) {
+                smem_shift_append(hrow, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, lane);
+                smem_shift_append(crow, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, lane);
+            } else {
+                {
+                    const int W = ti[TI_FRAME_STACK] * NO, keepw = W - NO;
+                    shift_copy(B.obs_history[call.parity ^ 1] + (size_t)env * W, B.obs_history[call.parity] + (size_t)env * W + NO, keepw, cleared, lane);
+                    float *dst = B.obs_history[call.parity ^ 1] + (size_t)env * W;
+                    for (int e = lane; e < NO; e += 32) dst[keepw + e] = nz[e];
+                }
+                {
+                    const int W = ti[TI_C_FRAME_STACK] * SC, keepw = W - SC;
+                    shift_copy(B.critic_obs[call.parity ^ 1] + (size_t)env * W, B.critic_obs[call.parity] + (size_t)env * W + SC, keepw, cleared, lane);
+                    float *dst = B.critic_obs[call.parity ^ 1] + (size_t)env * W;
+                    for (int e = lane; e < SC; e += 32) dst[keepw + e] = cr[e];
+                }
+            }
+        } else if (ti[TI_OBS_KIND] == 4) {   // tron1_pf_ee.py:53-141: features = 10 x 31 noisy frames, labels 17, critic = 10 x 134
             const int SC = ti[TI_SINGLE_CRITIC], NP = ti[TI_NUM_PRIV], NCS = ti[TI_N_CS], NB = NO - 4;   // NB = 9 + 3A
             float *cr = es + ES_CRIT, *pv = es + ES_PRIV;
             const bool cleared = (pm & PHASE_RESET) && reset;
             const int DRN = 10 + 2 * A;
-            if (lane < 4) ob[NB + lane] = clk;
+            if (lane < 2 * F) ob[NB + lane] = clk;
             __syncwarp();
             // the generic loop above already produced nz[0..NB) / obs_buf; redo it over the full 31-wide frame (clock included)
             for (int e = lane; e < NO; e += 32) {
@@ -784,7 +868,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     X(last_dof_vel, float, A_) X(feet_pos, float, 3 * F_) X(feet_vel, float, 3 * F_) X(last_feet_vel, float, 3 * F_)   \
     X(link_contact_forces, float, 3 * L_) X(episode_sums, float, NS_) X(feet_air_time, float, F_)                      \
     X(last_contacts, uint8_t, F_) X(friction, float, 1) X(added_mass, float, 1) X(com_bias, float, 3)                  \
-    X(kp_scale, float, A_) X(kd_scale, float, A_) X(gait_state, float, 8)
+    X(kp_scale, float, A_) X(kd_scale, float, A_) X(gait_state, float, B200_GAIT_STATE)
 
 __global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, 5)
 env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call) {

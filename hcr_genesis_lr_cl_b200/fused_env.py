@@ -35,7 +35,7 @@ class FusedLeggedEnv:
         sim = self.simulator
         self._b = sim._buf
         self.widths = spec.obs_widths(sim._model)
-        self.stacked = spec.obs_kind in ("tron1_pf", "tron1_pf_ee")   # obs / privileged obs are the frame stacks themselves
+        self.stacked = spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw")   # obs / privileged obs are the frame stacks themselves
         self.num_obs = self.widths["hist"] if self.stacked else self.widths["obs"]
         self.num_estimator_features, self.num_estimator_labels = self.widths["hist"], self.widths["priv"]
         self.num_privileged_obs = self.widths["critic"] if self.stacked else (
@@ -67,6 +67,18 @@ class FusedLeggedEnv:
         self.feet_air_time, self.fail_buf = b["feet_air_time"], b["fail_buf"]
         self.episode_sums = {n: b["episode_sums"][:, i] for i, n in enumerate(self.sum_names)}
         self.cstr_prob = b["cstr_prob"]
+        if spec.behavior_enabled:                             # go2_wtw.py:354-375 + 320-352: ranges start at mid / min
+            def mid(r):
+                return [(r[0] + r[1]) / 2] * 2
+            self.gait_period_range, self.base_height_target_range = mid(spec.gait_period_range), mid(spec.base_height_target_range)
+            self.foot_clearance_target_range, self.pitch_target_range = [spec.foot_clearance_target_range[0]] * 2, mid(spec.pitch_target_range)
+            self.num_gaits, self.num_gait_max = 1, len(spec.gait_theta_lists)
+            from ._cabi import H
+            g = b["gait_state"]
+            g.zero_()
+            g[:, H["B200_GS_TH"]:H["B200_GS_TH"] + 4] = torch.tensor(spec.gait_theta_lists[0], device=g.device)
+            g[:, H["B200_GS_PER"]], g[:, H["B200_GS_BH"]] = self.gait_period_range[0], self.base_height_target_range[0]
+            g[:, H["B200_GS_FC"]], g[:, H["B200_GS_PT"]] = self.foot_clearance_target_range[0], self.pitch_target_range[0]
         self._extras_ring = self._build_extras_ring()
 
     # runners assign a fresh tensor to env.episode_length_buf (on_policy_runner.py:169); keep the bound storage
@@ -110,6 +122,13 @@ class FusedLeggedEnv:
         if self.spec.sit_init_percent > 0:
             coin = host_uniform(self.spec.seed, self.common_step_counter, T.SITE_HOST, 0)
             self.simulator.set_step_flags(coin < self.spec.sit_init_percent)
+        if self.spec.behavior_enabled:
+            # ONE gait index per resampling call, shared by all its envs (go2_wtw.py:205-206): host draws
+            # 1 (callback) and 2 (reset) of the step
+            gaits = [min(int(host_uniform(self.spec.seed, self.common_step_counter, T.SITE_HOST, 1 + w) * self.num_gaits),
+                         self.num_gaits - 1) for w in (0, 1)]
+            self.simulator.set_behavior([self.gait_period_range, self.base_height_target_range, self.foot_clearance_target_range,
+                                         self.pitch_target_range], gaits[0], gaits[1])
 
     @property
     def estimator_features_buf(self):
@@ -173,6 +192,10 @@ class FusedLeggedEnv:
         ep = dict(self._extras_ring[self.common_step_counter % STATS_RING])
         if self.spec.cmd_curriculum:
             ep["max_command_x"] = self.command_ranges["lin_vel_x"][1]
+        if self.spec.behavior_enabled:                      # go2_wtw.py:161-165
+            ep["gait_period_max"], ep["base_height_target_max"] = self.gait_period_range[1], self.base_height_target_range[1]
+            ep["foot_clearance_target_max"], ep["pitch_target_max"] = self.foot_clearance_target_range[1], self.pitch_target_range[1]
+            ep["num_gaits"] = self.num_gaits
         self.extras["episode"] = ep
         if self.spec.send_timeouts:
             self.extras["time_outs"] = self.time_out_buf
@@ -182,22 +205,44 @@ class FusedLeggedEnv:
                 and "tracking_lin_vel" in self.sum_names:
             i = self.sum_names.index("tracking_lin_vel")
             cnt = stats[n].clamp(min=1.0)
-            self._pending_curriculum = (stats[i] / cnt / self.max_episode_length, stats[n].clone())
+            self._pending_curriculum = (stats[i] / cnt / self.max_episode_length, stats[n].clone(),
+                                        (stats[:n] / cnt / self.max_episode_length) if self.spec.behavior_enabled else None)
 
     def _apply_pending_curriculum(self):
         if self._pending_curriculum is None:
             return
-        mean_track, cnt = self._pending_curriculum
+        mean_track, cnt, means = self._pending_curriculum
         self._pending_curriculum = None
-        if float(cnt) > 0 and float(mean_track) > self.spec.curriculum_threshold * self.reward_scales["tracking_lin_vel"]:
+        if float(cnt) <= 0:
+            return
+        if float(mean_track) > self.spec.curriculum_threshold * self.reward_scales["tracking_lin_vel"]:
             r = self.command_ranges["lin_vel_x"]
             r[0] = float(np.clip(r[0] - 0.5, -self.spec.max_curriculum, 0.0))
             r[1] = float(np.clip(r[1] + 0.5, 0.0, self.spec.max_curriculum))
+        if means is not None:                                 # go2_wtw.py:220-249
+            self._update_behavior_param_curriculum(dict(zip(self.sum_names, means.tolist())))
+
+    def _update_behavior_param_curriculum(self, mean_sums):
+        """Widen the behaviour ranges from the mean per-step episode sums of the resetting envs (go2_wtw.py:220-249)."""
+        s, sc = self.spec, self.reward_scales
+
+        def widen(rng, step, lim):
+            rng[0], rng[1] = max(rng[0] - step, lim[0]), min(rng[1] + step, lim[1])
+
+        if mean_sums.get("quad_periodic_gait", -np.inf) > 0.8 * sc.get("quad_periodic_gait", np.inf):
+            widen(self.gait_period_range, 0.05, s.gait_period_range)
+            self.num_gaits = min(self.num_gaits + 1, self.num_gait_max)
+        if mean_sums.get("tracking_base_height", -np.inf) > 0.9 * sc.get("tracking_base_height", np.inf):
+            widen(self.base_height_target_range, 0.02, s.base_height_target_range)
+        if mean_sums.get("tracking_foot_clearance", -np.inf) > 0.8 * sc.get("tracking_foot_clearance", np.inf):
+            widen(self.foot_clearance_target_range, 0.01, s.foot_clearance_target_range)
+        if mean_sums.get("tracking_orientation", -np.inf) > 0.9 * sc.get("tracking_orientation", np.inf):
+            widen(self.pitch_target_range, 0.05, s.pitch_target_range)
 
 
 def make_env(task: str, num_envs: int, device: str = "cuda:0", terrain=None, env_offset: int = 0,
              num_envs_global: Optional[int] = None, **spec_overrides) -> FusedLeggedEnv:
-    """Build a fused env from a built-in task preset (`go2`, `go2_ts`)."""
+    """Build a fused env from a built-in task preset (`task_spec.PRESETS`)."""
     if task not in T.PRESETS:
         raise ValueError(f"no fused descriptor for task {task!r} (available: {sorted(T.PRESETS)})")
     spec = T.PRESETS[task](**spec_overrides)

@@ -260,6 +260,13 @@ class B200Simulator:
     def set_step_flags(self, sit_pose: bool) -> None:
         self._ck(self._lib.b200_set_step_flags(self._handle, int(bool(sit_pose))))
 
+    def set_behavior(self, ranges, gait_callback: int, gait_reset: int) -> None:
+        """go2_wtw host scalars of the step: the four behaviour ranges [(lo, hi)] x {gait period, base height, foot
+        clearance, pitch} and the gait index drawn for the callback / reset resampling (go2_wtw.py:180-217)."""
+        import ctypes
+        arr = (ctypes.c_float * 8)(*[float(v) for pair in ranges for v in pair])
+        self._ck(self._lib.b200_set_behavior(self._handle, arr, int(gait_callback), int(gait_reset)))
+
     def fused_reset_all(self, step_counter: int, cmd_range_x: Sequence[float]):
         lo, hi = float(cmd_range_x[0]), float(cmd_range_x[1])
         self._ck(self._lib.b200_reset_all(self._handle, int(step_counter), lo, float(np.float32(hi - lo)), self._parity, self._stream()))

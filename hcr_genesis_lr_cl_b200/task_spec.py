@@ -32,21 +32,21 @@ REWARD_TERMS: List[str] = [
     "action_rate", "action_smoothness", "ang_vel_xy", "base_height", "biped_periodic_gait", "collision", "dof_acc",
     "dof_close_to_default", "dof_pos_limits", "dof_pos_stand_still", "dof_power", "dof_vel",
     "dof_vel_stand_still", "feet_air_time", "feet_contact_stand_still", "feet_distance", "foot_acc", "foot_clearance",
-    "foot_landing_vel", "hip_pos", "keep_balance", "lin_vel_z", "no_fly", "orientation", "thigh_pos", "torques",
-    "tracking_ang_vel", "tracking_base_height", "tracking_lin_vel", "termination",
+    "foot_landing_vel", "hip_pos", "keep_balance", "lin_vel_z", "no_fly", "orientation", "quad_periodic_gait", "thigh_pos", "torques",
+    "tracking_ang_vel", "tracking_base_height", "tracking_foot_clearance", "tracking_lin_vel", "tracking_orientation", "termination",
 ]
 REWARD_ID: Dict[str, int] = {n: i for i, n in enumerate(REWARD_TERMS)}
 NUM_REWARD_TERMS = len(REWARD_TERMS)
 
 #: observation layouts the fused kernel knows (per-task ``compute_observations``)
-OBS_KINDS = {"go2": 0, "go2_ts": 1, "go2_cat": 2, "tron1_pf": 3, "tron1_pf_ee": 4}
+OBS_KINDS = {"go2": 0, "go2_ts": 1, "go2_cat": 2, "tron1_pf": 3, "tron1_pf_ee": 4, "go2_wtw": 5}
 
 CAT_CONSTRAINTS = ["torque", "dof_vel", "action_rate", "base_height", "collision", "feet_stumble", "dof_pos",
                    "base_orientation", "stand_still"]      # order of ConstraintManager.add calls, go2_cat.py:197-208
 
 # Philox draw sites (see oracle/philox.py and csrc/philox.cuh)
 SITE_CMD_RESAMPLE, SITE_PUSH, SITE_LEVEL, SITE_CMD_RESET, SITE_DOF, SITE_ROOT, SITE_FRICTION, SITE_MASS, SITE_COM, \
-    SITE_KP, SITE_KD, SITE_ARMATURE, SITE_JFRICTION, SITE_JDAMPING, SITE_OBS_NOISE, SITE_GAIT, SITE_HOST = range(17)
+    SITE_KP, SITE_KD, SITE_ARMATURE, SITE_JFRICTION, SITE_JDAMPING, SITE_OBS_NOISE, SITE_GAIT, SITE_HOST, SITE_BEHAVIOR, SITE_BEHAVIOR_RESET = range(19)
 
 
 @dataclass
@@ -176,6 +176,15 @@ class TaskSpec:
     sit_pos: List[float] = field(default_factory=lambda: [0.0, 0.0, 0.55])
     sit_pitch_angle: float = 0.0
     sit_joint_angles: List[float] = field(default_factory=list)
+    # go2_wtw behaviour parameters (go2_wtw_config.py:56-73)
+    behavior_enabled: bool = False
+    behavior_resampling_time: float = 5.0
+    gait_period_range: List[float] = field(default_factory=lambda: [0.3, 0.6])
+    foot_clearance_target_range: List[float] = field(default_factory=lambda: [0.04, 0.12])
+    base_height_target_range: List[float] = field(default_factory=lambda: [0.2, 0.34])
+    pitch_target_range: List[float] = field(default_factory=lambda: [-0.3, 0.3])
+    gait_theta_lists: List[List[float]] = field(default_factory=list)   # [gait][foot FL,FR,RL,RR]
+    euler_tracking_sigma: float = 0.1
     # Constraints as Terminations (go2_cat_config.py:28-36, go2_cat.py:135-215)
     cat_enabled: bool = False
     cat_soft_p: float = 0.25
@@ -259,6 +268,10 @@ class TaskSpec:
         feet, _, _, cs = self.link_groups(model)
         if self.obs_kind == "go2":
             return dict(obs=9 + 3 * A, priv=0, single_critic=0, hist=0, critic=0)
+        if self.obs_kind == "go2_wtw":                      # go2_wtw.py:53-111
+            single = 9 + 3 * A + 2 * len(feet) + 4 + len(feet)
+            sc = single + 3 + 7 + 2 * A + len(feet)
+            return dict(obs=single, priv=0, single_critic=sc, hist=self.frame_stack * single, critic=self.c_frame_stack * sc)
         if self.obs_kind == "tron1_pf_ee":                  # tron1_pf_ee.py:53-141
             single = 9 + 3 * A + 4
             dr = 10 + 2 * A
@@ -287,6 +300,14 @@ class TaskSpec:
     def noise_scale_vec(self) -> np.ndarray:
         """go2.py:92-117 / go2_ts.py:98-123 (same 45-wide layout)."""
         A = self.num_actions
+        if self.obs_kind == "go2_wtw":                     # go2_wtw.py:265-295: zeros beyond the first 9 + 3A entries
+            v = np.zeros(9 + 3 * A + 16, np.float32)
+            if self.add_noise:
+                v[3:6] = self.noise_gravity * self.noise_level
+                v[6:9] = self.noise_ang_vel * self.noise_level * self.obs_scale_ang_vel
+                v[9:9 + A] = self.noise_dof_pos * self.noise_level * self.obs_scale_dof_pos
+                v[9 + A:9 + 2 * A] = self.noise_dof_vel * self.noise_level * self.obs_scale_dof_vel
+            return v
         if self.obs_kind == "tron1_pf_ee":
             # tron1_pf_ee.py:309-333 keeps the 12-dof slice bounds on a 31-wide vector: entries 15..20 (dof_vel) get the
             # dof_pos scale and 21..30 (actions, clock) the dof_vel scale -- reproduced as shipped (quirk R17)
@@ -310,7 +331,7 @@ class TaskSpec:
     @classmethod
     def from_reference_cfg(cls, cfg, task: str) -> "TaskSpec":
         """Read a LeggedGym-Ex config object (nested classes/instances) into a TaskSpec."""
-        kinds = {"go2": "go2", "go2_ts": "go2_ts", "go2_cat": "go2_cat", "tron1_pf": "tron1_pf", "tron1_pf_ee": "tron1_pf_ee"}
+        kinds = {"go2": "go2", "go2_ts": "go2_ts", "go2_cat": "go2_cat", "tron1_pf": "tron1_pf", "tron1_pf_ee": "tron1_pf_ee", "go2_wtw": "go2_wtw"}
         if task not in kinds:
             raise ValueError(f"task {task!r} has no fused descriptor yet (supported: {sorted(kinds)})")
 
@@ -385,6 +406,19 @@ class TaskSpec:
             contact_state_link_names=list(a.contact_state_link_names),
             seed=getattr(cfg, "seed", 1),
         )
+        if task == "go2_wtw":
+            g, bp = r.periodic_reward_framework, r.behavior_params_range
+            if g.gait_function_type != "step":
+                raise ValueError("only the 'step' gait indicator is fused (the 'smooth' variant calls scipy on the host)")
+            spec.gait_enabled, spec.behavior_enabled, spec.double_shift_actions = True, True, True
+            spec.gait_b_swing = g.b_swing
+            spec.gait_theta_lists = [[g.theta_fl_list[k], g.theta_fr_list[k], g.theta_rl_list[k], g.theta_rr_list[k]]
+                                     for k in range(len(g.theta_fl_list))]
+            spec.behavior_resampling_time = bp.resampling_time
+            spec.gait_period_range, spec.foot_clearance_target_range = list(bp.gait_period_range), list(bp.foot_clearance_target_range)
+            spec.base_height_target_range, spec.pitch_target_range = list(bp.base_height_target_range), list(bp.pitch_target_range)
+            spec.base_height_tracking_sigma, spec.euler_tracking_sigma = r.base_height_tracking_sigma, r.euler_tracking_sigma
+            spec.reset_dof_noise = [0.2] * len(a.dof_names)           # base class _reset_dofs, legged_robot.py:279-280
         if task == "tron1_pf_ee":
             g = r.periodic_reward_framework
             if g.gait_function_type != "step":
@@ -546,5 +580,34 @@ def tron1_pf_ee_spec(**over) -> TaskSpec:
     return s
 
 
+def go2_wtw_spec(**over) -> TaskSpec:
+    """`go2_wtw` Walk-These-Ways on flat ground with periodic-gait rewards and behaviour parameters (BASELINE config C3;
+    go2_wtw_config.py:5-103)."""
+    s = TaskSpec(
+        task="go2_wtw", obs_kind="go2_wtw", robot="go2", dof_names=list(GO2_DOF_NAMES), num_obs=305, num_privileged_obs=495,
+        frame_stack=5, c_frame_stack=5, default_dof_pos=list(_GO2_Q0), reset_dof_noise=[0.2] * 12, reset_root_vel=0.5,
+        dof_vel_limits=[30.1, 30.1, 15.7] * 4, mesh_type="plane", border_size=5.0, env_spacing=1.0,
+        measured_points_x=[round(-0.8 + 0.1 * i, 1) for i in range(17)],
+        measured_points_y=[round(-0.5 + 0.1 * i, 1) for i in range(11)],
+        cmd_curriculum=True, max_curriculum=1.0, resampling_time=8.0, cmd_lin_vel_x=[-0.5, 0.5], cmd_lin_vel_y=[-1.0, 1.0],
+        friction_range=[0.2, 1.7], push_interval_s=15.0, randomize_pd_gain=True,
+        com_pos_x_range=[-0.03, 0.03], com_pos_y_range=[-0.03, 0.03], com_pos_z_range=[-0.03, 0.03],
+        reward_scales=dict(termination=-0.0, tracking_lin_vel=1.0, tracking_ang_vel=0.5, lin_vel_z=-0.5, ang_vel_xy=-0.05,
+                           orientation=-0.0, torques=-2.0e-4, dof_vel=-5.0e-4, dof_acc=-2.0e-7, base_height=-0.0, feet_air_time=0.0,
+                           collision=-1.0, feet_stumble=-0.0, action_rate=-0.01, dof_pos_stand_still=-0.0, dof_pos_limits=-10.0,
+                           tracking_base_height=0.6, tracking_orientation=0.6, tracking_foot_clearance=0.9,
+                           quad_periodic_gait=1.5, action_smoothness=-0.01, foot_landing_vel=-0.1, hip_pos=-1.0),
+        only_positive_rewards=True, soft_dof_pos_limit=0.9, foot_height_offset=0.022, about_landing_threshold=0.03,
+        base_height_tracking_sigma=0.01, euler_tracking_sigma=0.1,
+        penalize_contacts_on=["thigh", "calf"], terminate_after_contacts_on=["base", "Head"],
+        gait_enabled=True, behavior_enabled=True, double_shift_actions=True, gait_b_swing=0.5,
+        gait_theta_lists=[[0.0, 0.5, 0.5, 0.0], [0.0, 0.0, 0.0, 0.0], [0.5, 0.0, 0.5, 0.0], [0.0, 0.0, 0.5, 0.5]],
+        behavior_resampling_time=5.0,
+    )
+    for k, v in over.items():
+        setattr(s, k, v)
+    return s
+
+
 PRESETS = {"go2": go2_spec, "go2_ts": go2_ts_spec, "go2_cat": go2_cat_spec, "tron1_pf": tron1_pf_spec,
-           "tron1_pf_ee": tron1_pf_ee_spec}
+           "tron1_pf_ee": tron1_pf_ee_spec, "go2_wtw": go2_wtw_spec}

@@ -42,8 +42,20 @@ extern "C" {
 #define B200_KMAX 8        /* contacts kept per env                        */
 #define B200_AUXMAX 8      /* joint-limit + frictionloss constraint rows   */
 #define B200_RMAX 32       /* constraint rows = 3*KMAX + AUXMAX = one warp */
-#define B200_MAX_REWARDS 30
-#define B200_MAX_OBS 48
+#define B200_MAX_REWARDS 33
+#define B200_MAX_GAITS 4
+#define B200_GAIT_STATE 20   /* floats per env in gait_state */
+/* columns of one gait_state row: theta[4] (FL,FR,RL,RR or L,R), gait time, phase, gait period, base-height /
+ * foot-clearance / pitch targets (go2_wtw behaviour parameters), clock[8] = sin[feet], cos[feet] */
+#define B200_GS_TH 0
+#define B200_GS_GT 4
+#define B200_GS_PHI 5
+#define B200_GS_PER 6
+#define B200_GS_BH 7
+#define B200_GS_FC 8
+#define B200_GS_PT 9
+#define B200_GS_CLK 10
+#define B200_MAX_OBS 64
 #define B200_MAX_PTS_AXIS 17
 #define B200_BODY_STRIDE 20
 
@@ -68,6 +80,7 @@ enum B200TaskF {
     /* periodic-gait framework and sit-pose resets (tron1_pf_ee.py:186-256,347-437; tron1_pf_ee_config.py:51-63,128-137) */
     TF_GAIT_PERIOD, TF_GAIT_THETA_LEFT, TF_GAIT_THETA_RIGHT, TF_GAIT_B_SWING, TF_BASE_HEIGHT_SIGMA, TF_SIT_PERCENT,
     TF_SIT_POS, TF_SIT_POS_1, TF_SIT_POS_2, TF_SIT_QUAT, TF_SIT_QUAT_1, TF_SIT_QUAT_2, TF_SIT_QUAT_3, /* xyzw */
+    TF_EULER_SIGMA,                                             /* go2_wtw tracking_orientation */
     TF_DEFAULT_DOF_POS,                                         /* [B200_MAX_JOINTS] */
     TF_RESET_DOF_NOISE = TF_DEFAULT_DOF_POS + B200_MAX_JOINTS,  /* [B200_MAX_JOINTS] */
     TF_DOF_LIM_LO = TF_RESET_DOF_NOISE + B200_MAX_JOINTS,       /* [B200_MAX_JOINTS] soft limits */
@@ -79,7 +92,8 @@ enum B200TaskF {
     TF_TORQUE_LIMIT = TF_POINTS_Y + B200_MAX_PTS_AXIS,          /* [B200_MAX_JOINTS] URDF effort (simulator.torque_limits) */
     TF_DOF_VEL_LIMIT = TF_TORQUE_LIMIT + B200_MAX_JOINTS,       /* [B200_MAX_JOINTS] cfg.asset.dof_vel_limits */
     TF_SIT_DOF_POS = TF_DOF_VEL_LIMIT + B200_MAX_JOINTS,        /* [B200_MAX_JOINTS] sit-pose joint angles */
-    TF_COUNT = TF_SIT_DOF_POS + B200_MAX_JOINTS
+    TF_GAIT_THETA = TF_SIT_DOF_POS + B200_MAX_JOINTS,           /* [B200_MAX_GAITS][B200_MAX_FEET] phase offsets per gait (go2_wtw) */
+    TF_COUNT = TF_GAIT_THETA + B200_MAX_GAITS * B200_MAX_FEET
 };
 
 /* ---- task descriptor: int section ---- */
@@ -98,6 +112,8 @@ enum B200TaskI {
     TI_CAT_GLOBAL_STANDSTILL,                                    /* 1: reproduce the [N,N] broadcast of go2_cat.py:177-178 */
     TI_DOUBLE_SHIFT,                                             /* 1: tasks that shift the action history again after the step (R6) */
     TI_GAIT,                                                     /* 1: biped periodic-gait state (theta, gait time, phi, clock) */
+    TI_BEHAVIOR,                                                 /* 1: per-env behaviour params (gait period, targets) resampled (go2_wtw) */
+    TI_BEHAVIOR_INTERVAL,                                        /* int(behavior resampling_time / dt) */
     TI_CLEARANCE_MODE,                                           /* foot clearance / labels relative to: 0 nothing, 1 mean, 2 max of the 9 heights */
     TI_N_SUMS,                                                   /* columns of episode_sums: rewards (+termination) (+9 cstr_*) */                                               /* global id of local env 0 (multi-GPU sharding; keys the RNG) */
     TI_REWARD_IDS,                                               /* [B200_MAX_REWARDS] active term ids, evaluation order */
@@ -113,8 +129,9 @@ enum B200Reward {
     RW_ACTION_RATE, RW_ACTION_SMOOTHNESS, RW_ANG_VEL_XY, RW_BASE_HEIGHT, RW_BIPED_PERIODIC_GAIT, RW_COLLISION, RW_DOF_ACC,
     RW_DOF_CLOSE_TO_DEFAULT, RW_DOF_POS_LIMITS, RW_DOF_POS_STAND_STILL, RW_DOF_POWER, RW_DOF_VEL,
     RW_DOF_VEL_STAND_STILL, RW_FEET_AIR_TIME, RW_FEET_CONTACT_STAND_STILL, RW_FEET_DISTANCE, RW_FOOT_ACC, RW_FOOT_CLEARANCE,
-    RW_FOOT_LANDING_VEL, RW_HIP_POS, RW_KEEP_BALANCE, RW_LIN_VEL_Z, RW_NO_FLY, RW_ORIENTATION, RW_THIGH_POS, RW_TORQUES,
-    RW_TRACKING_ANG_VEL, RW_TRACKING_BASE_HEIGHT, RW_TRACKING_LIN_VEL, RW_TERMINATION, RW_COUNT
+    RW_FOOT_LANDING_VEL, RW_HIP_POS, RW_KEEP_BALANCE, RW_LIN_VEL_Z, RW_NO_FLY, RW_ORIENTATION, RW_QUAD_PERIODIC_GAIT, RW_THIGH_POS, RW_TORQUES,
+    RW_TRACKING_ANG_VEL, RW_TRACKING_BASE_HEIGHT, RW_TRACKING_FOOT_CLEARANCE, RW_TRACKING_LIN_VEL, RW_TRACKING_ORIENTATION,
+    RW_TERMINATION, RW_COUNT
 };
 
 /* random-draw sites: u = philox4x32-10(key = seed, counter = (env, step, site, idx >> 2))[idx & 3] */
@@ -122,7 +139,10 @@ enum B200Site {
     SITE_CMD_RESAMPLE, SITE_PUSH, SITE_LEVEL, SITE_CMD_RESET, SITE_DOF, SITE_ROOT, SITE_FRICTION, SITE_MASS, SITE_COM,
     SITE_KP, SITE_KD, SITE_ARMATURE, SITE_JFRICTION, SITE_JDAMPING, SITE_OBS_NOISE,
     SITE_GAIT,        /* idx 0: theta offset, 1: gait time (tron1_pf_ee.py:222-226) */
-    SITE_HOST         /* host-side scalar draws keyed env = 0xffffffff: idx 0 = sit-pose coin of the step (R8) */
+    SITE_HOST,        /* host-side scalar draws keyed env = 0xffffffff: idx 0 = sit-pose coin (R8), 1 / 2 = gait choice of the
+                         callback / reset resampling of the step (R7) */
+    SITE_BEHAVIOR,    /* idx 0..3: gait period, base height, foot clearance, pitch targets (callback resampling) */
+    SITE_BEHAVIOR_RESET
 };
 
 /* phases of b200_env_post_step (bit mask) */
@@ -203,7 +223,8 @@ typedef struct B200Buffers {
                                    [n_sums+2] sum of cstr_prob (all envs); then a ring of 32 slots [n_sums+2]: the
                                    extras["episode"] means of step % 32 (rew_* in episode-sum order, mean terrain level,
                                    mean cstr_prob) */
-    float *gait_state;          /* [N,8] theta_left, theta_right, gait_time, phi, clock_input[4] (periodic-gait tasks) */
+    float *gait_state;          /* [N,20] theta[4], gait_time, phi, gait_period, base_height_target, foot_clearance_target,
+                                   pitch_target, clock_input[8] = sin[F], cos[F] (periodic-gait tasks) */
     float *cstr_prob;           /* [N] CaT termination probability (Go2CaT.cstr_prob); unused (but bound) for other tasks */
     int32_t *global_flags;      /* [4] int32: [0] any env with |dof_vel| > 4 after the physics step (CaT stand-still, R4) */
     float *contact_warm;        /* [N,48] contact-solver warm start carried between substeps and policy steps: 8 x (sphere id + 1,
@@ -231,6 +252,11 @@ int b200_env_post_step(B200Handle *h, long long step_counter, float cmd_vx_lo, f
 /* Per-step host scalars for the next b200_env_post_step / b200_reset_all: `sit_pose` != 0 -> envs that reset in that
  * call start in the sit pose (tron1_pf_ee.py:204-210 draws ONE coin per reset batch). */
 int b200_set_step_flags(B200Handle *h, int sit_pose);
+
+/* go2_wtw behaviour parameters (go2_wtw.py:180-217): the curriculum-mutable sampling ranges
+ * {gait period, base height, foot clearance, pitch} x {lo, hi} and the gait index the host drew for the callback
+ * resampling and for the reset resampling of the next step (ONE randint per call for all envs). */
+int b200_set_behavior(B200Handle *h, const float *ranges8, int gait_callback, int gait_reset);
 
 /* reset_idx(all envs) without a preceding step (BaseTask.reset). */
 int b200_reset_all(B200Handle *h, long long step_counter, float cmd_vx_lo, float cmd_vx_span, int parity, void *cuda_stream);

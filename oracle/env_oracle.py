@@ -29,6 +29,7 @@ from hcr_genesis_lr_cl_b200 import task_spec as T  # data format (TaskSpec, site
 from oracle import philox
 
 f32 = np.float32
+G_TH, G_GT, G_PHI, G_PER, G_BH, G_FC, G_PT, G_CLK = 0, 4, 5, 6, 7, 8, 9, 10      # columns of gait_state
 
 
 def _rot_inv(q, v):
@@ -112,8 +113,15 @@ class EnvOracle:
             base_lin_vel=z(N, 3), base_ang_vel=z(N, 3), feet_vel=z(N, F, 3), last_dof_vel=z(N, A),
             last_feet_vel=z(N, F, 3), last_base_lin_vel=z(N, 3), last_base_ang_vel=z(N, 3),
             obs_hist=z(N, max(self.widths["hist"], 1)), critic_hist=z(N, max(self.widths["critic"], 1)),
-            gait_state=z(N, 8),      # theta_left, theta_right, gait_time, phi, clock_input[4]
+            gait_state=z(N, 20),     # theta[4], gait_time, phi, gait_period, base_height_t, foot_clearance_t, pitch_t, clock[8]
         )
+        self.st["gait_state"][:, G_PER] = spec.gait_period
+        # go2_wtw host-side behaviour state (go2_wtw.py:352-372): curriculum-mutable ranges and the number of unlocked gaits
+        mid = lambda r: [(r[0] + r[1]) / 2] * 2
+        self.beh_ranges = dict(gait_period=mid(spec.gait_period_range), base_height=mid(spec.base_height_target_range),
+                               foot_clearance=[spec.foot_clearance_target_range[0]] * 2, pitch=mid(spec.pitch_target_range))
+        self.num_gaits = 1
+        self.gait_choice = None      # (callback, reset) gait indices of the step; None -> drawn from the SITE_HOST stream
         # R18 (reference defect, found here): tron1_pf_ee.py:32-34,414-421 flatten `nonzero()` of [N,1] masks, so the column
         # index 0 joins the row indices: env 0's gait time is zeroed whenever ANY env wraps and its swing/stance indicator
         # is overwritten whenever any env is in swing/stance.  The product does not reproduce this coupling;
@@ -169,19 +177,19 @@ class EnvOracle:
         self._reward(o)
         if self.spec.gait_enabled:                        # tron1_pf_ee.py:27-35
             g = st["gait_state"]
-            g[:, 2] = (g[:, 2] + f32(self.spec.dt)).astype(f32)
-            over = g[:, 2] >= f32(self.spec.gait_period - self.spec.dt / 2)
-            g[over, 2] = 0
+            g[:, G_GT] = (g[:, G_GT] + f32(self.spec.dt)).astype(f32)
+            over = g[:, G_GT] >= (g[:, G_PER] - f32(self.spec.dt / 2)).astype(f32)
+            g[over, G_GT] = 0
             if self.reproduce_r18 and over.any():
-                g[0, 2] = 0
-            g[:, 3] = (g[:, 2] / f32(self.spec.gait_period)).astype(f32)
+                g[0, G_GT] = 0
+            g[:, G_PHI] = (g[:, G_GT] / g[:, G_PER]).astype(f32)
         self._reset(o)
         if self.spec.gait_enabled:                        # _calc_periodic_reward_obs, tron1_pf_ee.py:258-263
             g = st["gait_state"]
-            for i in range(2):
-                arg = (f32(2 * np.pi) * (g[:, 3] + g[:, i]).astype(f32)).astype(f32)
-                g[:, 4 + i] = np.sin(arg)
-                g[:, 6 + i] = np.cos(arg)
+            for i in range(self.F):
+                arg = (f32(2 * np.pi) * (g[:, G_PHI] + g[:, G_TH + i]).astype(f32)).astype(f32)
+                g[:, G_CLK + i] = np.sin(arg)
+                g[:, G_CLK + self.F + i] = np.cos(arg)
         self._observe(o)
         if self.spec.double_shift_actions:               # go2_cat.py:127-130
             st["llast_actions"][:] = st["last_actions"]
@@ -306,6 +314,32 @@ class EnvOracle:
             st["rand_push_vels"][:, :2] = push
             st["base_lin_w"][:, :2] += push
             o["pushed"] = True
+        if s.behavior_enabled:                                     # go2_wtw.py:258-263
+            ids = np.nonzero(st["episode_length"] % int(s.behavior_resampling_time / s.dt) == 0)[0]
+            self._resample_behavior(ids, T.SITE_BEHAVIOR, self._gait_choice(0))
+
+    def _gait_choice(self, which):
+        """ONE randint per resampling call for all envs (go2_wtw.py:205-206); host draw idx 1 (callback) / 2 (reset)."""
+        if self.gait_choice is not None:
+            return self.gait_choice[which]
+        u = float(philox.uniform(self.spec.seed, self.common_step_counter, 0xFFFFFFFF, T.SITE_HOST, 1 + which))
+        return min(int(u * self.num_gaits), self.num_gaits - 1)
+
+    def _resample_behavior(self, ids, site, gait):
+        """go2_wtw.py:180-217 (the pronk/bound clearance clamp is applied per resampled env; DESIGN.md deviation D4)."""
+        s, g = self.spec, self.st["gait_state"]
+        if len(ids) == 0:
+            return
+        u = self.u(site, [0, 1, 2, 3], ids)
+        r = self.beh_ranges
+        g[ids, G_PER] = self._range(r["gait_period"][0], r["gait_period"][1], u[:, 0])
+        g[ids, G_BH] = self._range(r["base_height"][0], r["base_height"][1], u[:, 1])
+        g[ids, G_FC] = self._range(r["foot_clearance"][0], r["foot_clearance"][1], u[:, 2])
+        g[ids, G_PT] = self._range(r["pitch"][0], r["pitch"][1], u[:, 3])
+        th = np.asarray(s.gait_theta_lists[gait], f32)
+        g[ids, G_TH:G_TH + 4] = th[None, :]
+        if (th[0] == 0 and th[1] == 0) and ((th[2] == 0 and th[3] == 0) or (th[2] == 0.5 and th[3] == 0.5)):
+            g[ids, G_FC] = f32(r["foot_clearance"][0])
 
     # ------------------------------------------------------------------ legged_robot.py:78-92
     def _termination(self, o):
@@ -409,9 +443,15 @@ class EnvOracle:
             "feet_distance": lambda: np.maximum(f32(0), f32(s.foot_distance_threshold) - np.sqrt(np.sum(np.square(
                 o["feet_pos"][:, 0, :2] - o["feet_pos"][:, 1, :2]), axis=-1, dtype=f32)).astype(f32)),      # tron1_pf.py:146-151
             "no_fly": lambda: (ssum((lf[:, self.feet, 2] > f32(0.1)).astype(f32)) == 1).astype(f32),       # tron1_pf.py:153-156
-            "biped_periodic_gait": lambda: self._biped_gait(o),
+            "biped_periodic_gait": lambda: self._periodic_gait(o, 2),
+            "quad_periodic_gait": lambda: self._periodic_gait(o, 4),
             "tracking_base_height": lambda: np.exp(-np.square(np.mean(st["base_pos"][:, 2:3] - o["measured_heights"], axis=1, dtype=f32)
-                                                              - f32(s.base_height_target)) / f32(s.base_height_tracking_sigma)).astype(f32),
+                                                              - (st["gait_state"][:, G_BH] if s.behavior_enabled else f32(s.base_height_target)))
+                                                   / f32(s.base_height_tracking_sigma)).astype(f32),
+            "tracking_orientation": lambda: np.exp(-(np.square(o["base_euler"][:, 0]) + np.square(o["base_euler"][:, 1] - st["gait_state"][:, G_PT]))
+                                                   / f32(s.euler_tracking_sigma)).astype(f32),                      # go2_wtw.py:497-500
+            "tracking_foot_clearance": lambda: np.exp(-ssum(np.sqrt(np.sum(o["feet_vel"][:, :, :2] ** 2, axis=-1, dtype=f32)).astype(f32) * np.square(
+                o["feet_pos"][:, :, 2] - st["gait_state"][:, G_FC:G_FC + 1] - f32(s.foot_height_offset))) / f32(s.foot_clearance_tracking_sigma)).astype(f32),
             "foot_acc": lambda: np.sum(np.square((o["feet_vel"] - st["last_feet_vel"]) / dt), axis=(1, 2), dtype=f32),
             "foot_clearance": foot_clearance,
             "foot_landing_vel": foot_landing_vel,
@@ -442,16 +482,16 @@ class EnvOracle:
         o["rew_buf"], o["reward_terms"] = rew, terms
 
     # ------------------------------------------------------------------ tron1_pf_ee.py:335-437 ("step" indicator)
-    def _biped_gait(self, o):
+    def _periodic_gait(self, o, nfeet):
         s, st = self.spec, self.st
         g = st["gait_state"]
         lf = o["link_contact_forces"]
         total = np.zeros(self.N, f32)
-        o["exp_C_frc"] = np.zeros((self.N, 2), f32)
-        for i in range(2):
+        o["exp_C_frc"] = np.zeros((self.N, nfeet), f32)
+        for i in range(nfeet):
             q_frc = _norm3(lf[:, self.feet[i], :])
             q_spd = _norm3(o["feet_vel"][:, i, :])
-            phi = (np.mod((g[:, 3] + g[:, i]).astype(f32), f32(1.0)) * f32(2 * np.pi)).astype(f32)
+            phi = (np.mod((g[:, G_PHI] + g[:, G_TH + i]).astype(f32), f32(1.0)) * f32(2 * np.pi)).astype(f32)
             b_swing = f32(s.gait_b_swing * 2 * np.pi)
             swing = (phi >= 0) & (phi < b_swing)
             stance = (phi >= b_swing) & (phi < f32(2 * np.pi))
@@ -486,6 +526,8 @@ class EnvOracle:
             st["terrain_levels"][ids] = lv
             st["env_origins"][ids] = self.terrain_origins[lv, st["terrain_types"][ids]]
         # command curriculum (legged_robot.py:336-348) is applied by the host one step later: DESIGN.md "deviations"
+        if s.behavior_enabled:                                     # go2_wtw.py:124-126: behaviour params before commands
+            self._resample_behavior(ids, T.SITE_BEHAVIOR_RESET, self._gait_choice(1))
         self._resample(ids, T.SITE_CMD_RESET)
         A = self.A
         sit = False
@@ -546,13 +588,17 @@ class EnvOracle:
         st["episode_length"][ids] = 0
         st["fail_buf"][ids] = 0
         if s.gait_enabled:                                         # tron1_pf_ee.py:221-228
-            ug = self.u(T.SITE_GAIT, [0, 1], ids)
             g = st["gait_state"]
-            g[ids, 0] = (f32(s.gait_theta_left) + ug[:, 0]).astype(f32)
-            g[ids, 1] = (g[ids, 0] + f32(s.gait_theta_right - s.gait_theta_left)).astype(f32)
-            g[ids, 2] = (ug[:, 1] * f32(s.gait_period)).astype(f32)
-            g[ids, 3] = (g[ids, 2] / f32(s.gait_period)).astype(f32)
-            g[ids, 4:8] = 0
+            if s.behavior_enabled:                                 # go2_wtw.py:139-142
+                g[ids, G_GT] = 0
+                g[ids, G_PHI] = 0
+            else:
+                ug = self.u(T.SITE_GAIT, [0, 1], ids)
+                g[ids, G_TH] = (f32(s.gait_theta_left) + ug[:, 0]).astype(f32)
+                g[ids, G_TH + 1] = (g[ids, G_TH] + f32(s.gait_theta_right - s.gait_theta_left)).astype(f32)
+                g[ids, G_GT] = (ug[:, 1] * g[ids, G_PER]).astype(f32)
+                g[ids, G_PHI] = (g[ids, G_GT] / g[ids, G_PER]).astype(f32)
+            g[ids, G_CLK:G_CLK + 8] = 0
         o["episode_means"] = {"rew_" + n: np.mean(st["episode_sums"][ids, i], dtype=f32) / f32(s.episode_length_s)
                               for i, n in enumerate(self.sum_names)}
         st["episode_sums"][ids] = 0
@@ -569,13 +615,30 @@ class EnvOracle:
             (o["dof_pos"] - self.q0) * f32(s.obs_scale_dof_pos), o["dof_vel"] * f32(s.obs_scale_dof_vel), st["actions"]],
             axis=1).astype(f32)
         clean = obs.copy()
-        if s.add_noise and s.obs_kind != "tron1_pf_ee":
+        if s.add_noise and s.obs_kind not in ("tron1_pf_ee", "go2_wtw"):
             un = self.u(T.SITE_OBS_NOISE, np.arange(obs.shape[1]))
             obs = (obs + ((f32(2) * un - f32(1)).astype(f32) * self.noise_vec[None, :]).astype(f32)).astype(f32)
         c = f32(s.clip_observations)
+        if s.obs_kind == "go2_wtw":                                # go2_wtw.py:53-111
+            g = st["gait_state"]
+            obs61 = np.concatenate([clean, g[:, G_CLK:G_CLK + 8], g[:, G_PER:G_PT + 1], g[:, G_TH:G_TH + 4]], axis=1).astype(f32)
+            lin = (st["base_lin_vel"] * f32(s.obs_scale_lin_vel)).astype(f32)
+            crit = np.concatenate([obs61, lin, st["rand_push_vels"][:, :2], st["added_mass"], st["friction"], st["com_bias"],
+                                   st["kp_scale"], st["kd_scale"], o.get("exp_C_frc", np.zeros((self.N, 4), f32))], axis=1).astype(f32)
+            noisy = obs61.copy()
+            if s.add_noise:
+                un = self.u(T.SITE_OBS_NOISE, np.arange(obs61.shape[1]))
+                noisy = (obs61 + ((f32(2) * un - f32(1)).astype(f32) * self.noise_vec[None, :]).astype(f32)).astype(f32)
+            sc, so = self.widths["single_critic"], self.widths["obs"]
+            st["critic_hist"][:] = np.concatenate([st["critic_hist"][:, sc:], crit], axis=1)
+            st["obs_hist"][:] = np.concatenate([st["obs_hist"][:, so:], noisy], axis=1)
+            o["obs_buf"] = np.clip(st["obs_hist"], -c, c)
+            o["privileged_obs_buf"] = np.clip(st["critic_hist"], -c, c)
+            o["obs_history"], o["critic_obs_buf"] = o["obs_buf"], o["privileged_obs_buf"]
+            return
         if s.obs_kind == "tron1_pf_ee":                            # tron1_pf_ee.py:53-141
             g = st["gait_state"]
-            obs31 = np.concatenate([clean, g[:, 4:8]], axis=1).astype(f32)
+            obs31 = np.concatenate([clean, g[:, G_CLK:G_CLK + 4]], axis=1).astype(f32)
             noisy = obs31.copy()
             if s.add_noise:
                 un = self.u(T.SITE_OBS_NOISE, np.arange(obs31.shape[1]))

@@ -46,6 +46,8 @@ class EmuSim:
         self.parity = 0
         self.step_counter = 0
         self.cmd_range_x = [float(spec.cmd_lin_vel_x[0]), float(spec.cmd_lin_vel_x[1])]
+        self.beh_ranges = np.zeros((4, 2), np.float64)      # go2_wtw behaviour ranges (period, height, clearance, pitch)
+        self.num_gaits = 1
 
     @staticmethod
     def _p(a):
@@ -61,6 +63,9 @@ class EmuSim:
             self.step_counter = int(st["common_step_counter"])
         if "cmd_range_x" in st:
             self.cmd_range_x = [float(x) for x in st["cmd_range_x"]]
+        if "beh_ranges" in st:
+            self.beh_ranges = np.asarray(st["beh_ranges"], np.float64).reshape(4, 2)
+            self.num_gaits = int(st["num_gaits"])
 
     def dynamics_step(self, actions):
         a = np.ascontiguousarray(actions, np.float32)
@@ -77,10 +82,17 @@ class EmuSim:
             from hcr_genesis_lr_cl_b200.host_rng import host_uniform
             from hcr_genesis_lr_cl_b200 import task_spec as T
             sit_pose = self.spec.sit_init_percent > 0 and host_uniform(self.spec.seed, self.step_counter, T.SITE_HOST, 0) < self.spec.sit_init_percent
+        from hcr_genesis_lr_cl_b200.host_rng import host_uniform as _hu
+        from hcr_genesis_lr_cl_b200 import task_spec as _T
+        gaits = [min(int(_hu(self.spec.seed, self.step_counter, _T.SITE_HOST, 1 + w) * self.num_gaits), self.num_gaits - 1) for w in (0, 1)]
+        beh = np.zeros(8, np.float32)
+        beh[0::2] = self.beh_ranges[:, 0]
+        beh[1::2] = self.beh_ranges[:, 1] - self.beh_ranges[:, 0]
         self.lib.emu_env_post_step(self._p(self.tf), self._p(self.ti), self._p(self.hs), ctypes.c_int(rows), ctypes.c_int(cols),
                                    self._p(self.origins), ctypes.c_int(lv), ctypes.c_int(ty), ctypes.byref(self.cbuf),
                                    ctypes.c_longlong(self.step_counter), ctypes.c_float(lo), ctypes.c_float(np.float32(hi - lo)),
-                                   ctypes.c_int(self.parity), ctypes.c_int(phase_mask), ctypes.c_int(force_reset), ctypes.c_int(int(bool(sit_pose))))
+                                   ctypes.c_int(self.parity), ctypes.c_int(phase_mask), ctypes.c_int(force_reset), ctypes.c_int(int(bool(sit_pose))),
+                                   self._p(beh), ctypes.c_int(gaits[0]), ctypes.c_int(gaits[1]))
         self.parity ^= 1
 
     @property

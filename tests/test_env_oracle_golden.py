@@ -9,7 +9,7 @@ from oracle.env_oracle import EnvOracle
 INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels")
 
 
-@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32"])
+@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32", "go2_wtw_n32"])
 def test_env_oracle_reproduces_reference(name):
     g, s0 = load_golden(name)
     spec = spec_for(g)
@@ -22,6 +22,9 @@ def test_env_oracle_reproduces_reference(name):
             eo.st[k][...] = v
     eo.common_step_counter = int(s0["common_step_counter"])
     eo.cmd_range_x = [float(x) for x in s0["cmd_range_x"]]
+    if "beh_ranges" in s0:             # go2_wtw curriculum state of the recorded window
+        eo.beh_ranges = dict(zip(("gait_period", "base_height", "foot_clearance", "pitch"), np.asarray(s0["beh_ranges"], np.float64).tolist()))
+        eo.num_gaits = int(s0["num_gaits"])
     resets = 0
     for t in range(T_):
         eo.pre_step(g["actions"][t])

@@ -45,7 +45,7 @@ def test_library_is_the_cuda_path(built_library):
     assert all(hasattr(lib, s) for s in _cabi.EXPORTED_SYMBOLS)
 
 
-@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32"])
+@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32", "go2_wtw_n32"])
 def test_env_kernel_matches_reference_golden(name):
     """Injected post-physics states from the reference run -> every output of the fused kernel."""
     g, s0 = load_golden(name)
@@ -57,6 +57,7 @@ def test_env_kernel_matches_reference_golden(name):
     sim.load_state(s0)
     env.common_step_counter = int(s0["common_step_counter"])
     env.command_ranges["lin_vel_x"] = [float(x) for x in s0["cmd_range_x"]]
+    _load_behavior(env, s0)
     ints = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels")
     for t in range(T_):
         a = torch.from_numpy(g["actions"][t]).cuda()
@@ -69,10 +70,10 @@ def test_env_kernel_matches_reference_golden(name):
         st = sim.get_state()
         ref = out_at(g, t)
         mine = dict(st, actions_buf=st["actions"], end_q=st["dof_pos"], end_qd=st["dof_vel"])
-        if spec.obs_kind in ("tron1_pf", "tron1_pf_ee"):     # the returned obs / privileged obs are the frame stacks
+        if spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw"):     # the returned obs / privileged obs are the frame stacks
             mine["estimator_labels_buf"] = st["privileged_obs_buf"]
             mine["obs_buf"], mine["privileged_obs_buf"] = st[f"obs_history{sim._parity}"], st[f"critic_obs{sim._parity}"]
-        skip0 = spec.obs_kind == "tron1_pf_ee"               # R18: env 0 is coupled to all envs in the reference; not reproduced
+        skip0 = spec.obs_kind in ("tron1_pf_ee", "go2_wtw")  # R18: env 0 is coupled to all envs in the reference; not reproduced
         for k, r in ref.items():
             if k not in mine or k in ("end_state",):
                 continue
@@ -87,6 +88,14 @@ def test_env_kernel_matches_reference_golden(name):
             if f"hist{t}/{hk}" in g:
                 _close(st[name], g[f"hist{t}/{hk}"], what=f"step {t}: {hk}")
     assert int(g["out/reset_buf"].sum()) > 0          # the window did contain resets
+
+
+def _load_behavior(env, s0):
+    """go2_wtw curriculum state (behaviour ranges, unlocked gaits) of a recorded window."""
+    if "beh_ranges" in s0:
+        r = np.asarray(s0["beh_ranges"], np.float64).tolist()
+        env.gait_period_range, env.base_height_target_range, env.foot_clearance_target_range, env.pitch_target_range = r
+        env.num_gaits = int(s0["num_gaits"])
 
 
 def _random_state(spec, N, terrain, seed):
@@ -127,7 +136,7 @@ def _random_state(spec, N, terrain, seed):
     return st, model
 
 
-@pytest.mark.parametrize("task", ["go2_ts", "go2", "tron1_pf", "tron1_pf_ee"])
+@pytest.mark.parametrize("task", ["go2_ts", "go2", "tron1_pf", "tron1_pf_ee", "go2_wtw"])
 def test_dynamics_kernel_matches_oracle(task):
     """One policy step (4 substeps) of the warp-per-env kernel vs the fp32 C oracle on seeded states."""
     from emu_util import oracle_params, oracle_policy_step
@@ -159,13 +168,13 @@ def test_dynamics_kernel_matches_oracle(task):
             assert err.max() < tol * scale(r), f"{k}: abs err {err.max():.3e} (scale {scale(r):.2f})"
 
 
-@pytest.mark.parametrize("task", ["go2_ts", "go2_cat", "tron1_pf_ee"])
+@pytest.mark.parametrize("task", ["go2_ts", "go2_cat", "tron1_pf_ee", "go2_wtw"])
 def test_env_kernel_matches_numpy_oracle_seeded(task):
     """Seeded random states at N=512 through several fused steps vs the numpy restatement (all phases, with resets)."""
     from hcr_genesis_lr_cl_b200 import task_spec as T
     from oracle.env_oracle import EnvOracle
     spec = T.PRESETS[task]()
-    terrain = load_terrain(spec)
+    terrain = load_terrain(spec) if spec.heightfield else None
     F = len(spec.link_groups(spec.load_model())[0])
     N = 512
     st, model = _random_state(spec, N, terrain, seed=11)
@@ -176,14 +185,30 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
     st["commands"] = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
     st["feet_air_time"] = rng.uniform(0, 0.4, (N, F)).astype(np.float32)
     st["last_contacts"] = rng.integers(0, 2, (N, F)).astype(np.uint8)
-    st["gait_state"] = np.concatenate([rng.uniform(0, 1, (N, 1)), rng.uniform(0, 1, (N, 1)) + 0.5, rng.integers(0, 25, (N, 1)) * 0.02,
-                                       np.zeros((N, 5))], axis=1).astype(np.float32)
-    st["gait_state"][:, 3] = st["gait_state"][:, 2] / np.float32(0.5)
+    from hcr_genesis_lr_cl_b200._cabi import H
+    gs = np.zeros((N, H["B200_GAIT_STATE"]), np.float32)
+    gs[:, H["B200_GS_GT"]] = rng.integers(0, 15, N) * np.float32(spec.dt)
+    if spec.behavior_enabled:                                # go2_wtw: per-env behaviour parameters, one of the four gaits
+        st["episode_length"][3::7] = 249                     # behaviour resampling interval (250 steps) hit in the callback
+        gs[:, H["B200_GS_TH"]:H["B200_GS_TH"] + 4] = np.asarray(spec.gait_theta_lists, np.float32)[rng.integers(0, 4, N)]
+        for col, r in ((H["B200_GS_PER"], spec.gait_period_range), (H["B200_GS_BH"], spec.base_height_target_range),
+                       (H["B200_GS_FC"], spec.foot_clearance_target_range), (H["B200_GS_PT"], spec.pitch_target_range)):
+            gs[:, col] = rng.uniform(r[0], r[1], N)
+        gs[:, H["B200_GS_PHI"]] = gs[:, H["B200_GS_GT"]] / gs[:, H["B200_GS_PER"]]
+    else:
+        gs[:, 0], gs[:, 1] = rng.uniform(0, 1, N), rng.uniform(0, 1, N) + 0.5
+        gs[:, H["B200_GS_PHI"]] = gs[:, H["B200_GS_GT"]] / np.float32(spec.gait_period)
+    st["gait_state"] = gs
     env = _env(spec, N, terrain)
     sim = env.simulator
     sim.load_state(st)
     env.common_step_counter = spec.push_interval - 2
-    eo = EnvOracle(spec, N, terrain[0], terrain[1])
+    eo = EnvOracle(spec, N, *(terrain if terrain is not None else (None, None)))
+    if spec.behavior_enabled:                                # a mid-curriculum state: wide ranges, all gaits unlocked
+        rr = [[0.35, 0.55], [0.24, 0.32], [0.05, 0.1], [-0.2, 0.2]]
+        _load_behavior(env, dict(beh_ranges=rr, num_gaits=4))
+        eo.beh_ranges = dict(zip(("gait_period", "base_height", "foot_clearance", "pitch"), rr))
+        eo.num_gaits = 4
     alias = {"dof_pos": "q", "dof_vel": "qd"}
     # explicit phases: the oracle is fed exactly the kernel's post-physics state (this test isolates the env half)
     s_now = sim.get_state()
@@ -209,8 +234,9 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
         total_resets += int(o["reset_buf"].sum())
         assert np.array_equal(out["reset_buf"].astype(bool), o["reset_buf"]), f"step {t}: reset_buf"
         assert np.array_equal(out["time_out_buf"].astype(bool), o["time_out_buf"]), f"step {t}: time_out_buf"
-        assert np.array_equal(out["height_cells"], o["height_cells"]), f"step {t}: height-scan cell indices"
-        assert np.array_equal(out["terrain_levels"], eo.st["terrain_levels"]), f"step {t}: terrain levels"
+        if spec.heightfield:
+            assert np.array_equal(out["height_cells"], o["height_cells"]), f"step {t}: height-scan cell indices"
+            assert np.array_equal(out["terrain_levels"], eo.st["terrain_levels"]), f"step {t}: terrain levels"
         assert np.array_equal(out["episode_length"], eo.st["episode_length"])
         assert np.array_equal(out["fail_buf"], eo.st["fail_buf"])
         _close(out["rew_buf"], o["rew_buf"], what=f"step {t}: rew")
@@ -218,6 +244,8 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
             assert np.array_equal(out["cstr_prob"], o["cstr_prob"]), f"step {t}: cstr_prob"
         if spec.obs_kind == "tron1_pf_ee":
             _close(out["privileged_obs_buf"], o["estimator_labels_buf"], what=f"step {t}: labels")
+            _close(out["gait_state"], eo.st["gait_state"], what=f"step {t}: gait_state")
+        elif spec.obs_kind == "go2_wtw":
             _close(out["gait_state"], eo.st["gait_state"], what=f"step {t}: gait_state")
         else:
             _close(out["obs_buf"], o["obs_buf"], what=f"step {t}: obs")
@@ -236,7 +264,8 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
             ring = out["stats"][base:base + n + 2]
             for i, name in enumerate(eo.sum_names):
                 assert abs(ring[i] - o["episode_means"]["rew_" + name]) <= 1e-4 * abs(o["episode_means"]["rew_" + name]) + 1e-6, name
-            assert abs(ring[n] - eo.st["terrain_levels"].mean()) < 1e-3
+            if spec.terrain_curriculum:
+                assert abs(ring[n] - eo.st["terrain_levels"].mean()) < 1e-3
     assert total_resets > 0
 
 

@@ -14,7 +14,7 @@ PH = dict(base_pos="base_pos", base_quat_wxyz="base_quat_wxyz", base_lin_w="base
 INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels")
 
 
-@pytest.mark.parametrize("name,steps", [("go2_ts_n32", 5), ("go2_n32", 4), ("go2_cat_n32", 5), ("tron1_pf_n32", 5), ("tron1_pf_ee_n32", 5)])
+@pytest.mark.parametrize("name,steps", [("go2_ts_n32", 5), ("go2_n32", 4), ("go2_cat_n32", 5), ("tron1_pf_n32", 5), ("tron1_pf_ee_n32", 5), ("go2_wtw_n32", 5)])
 def test_emulated_env_kernel_matches_reference_golden(name, steps):
     g, s0 = load_golden(name)
     spec = spec_for(g)
@@ -35,10 +35,10 @@ def test_emulated_env_kernel_matches_reference_golden(name, steps):
         sim.env_post_step()
         ref = out_at(g, t)
         mine = dict(B, actions_buf=B["actions"], end_q=B["dof_pos"], end_qd=B["dof_vel"])
-        if spec.obs_kind in ("tron1_pf", "tron1_pf_ee"):     # the returned obs / privileged obs are the frame stacks
+        if spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw"):     # the returned obs / privileged obs are the frame stacks
             mine["estimator_labels_buf"] = B["privileged_obs_buf"]
             mine["obs_buf"], mine["privileged_obs_buf"] = sim.obs_history, sim.critic_obs
-        skip0 = spec.obs_kind == "tron1_pf_ee"               # R18: the reference couples env 0 to all envs; not reproduced
+        skip0 = spec.obs_kind in ("tron1_pf_ee", "go2_wtw")  # R18: the reference couples env 0 to all envs; not reproduced
         for k, r in ref.items():
             if k not in mine or k == "end_state":
                 continue

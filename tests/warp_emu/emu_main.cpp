@@ -38,13 +38,15 @@ int emu_dynamics_step(const float *tf, const int *ti, const int *mi, const float
 struct EnvArgs { TaskDev T; B200Buffers B; TerrainDev tr; EnvCall call; };
 static void env_body(void *p) { EnvArgs *a = (EnvArgs *)p; env_post_step_kernel(a->T, a->B, a->tr, a->call); }
 int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int rows, int cols, const float *origins, int levels, int types,
-                      const B200Buffers *bufs, long long step, float vx_lo, float vx_span, int parity, int phase_mask, int force_reset, int sit_pose) {
+                      const B200Buffers *bufs, long long step, float vx_lo, float vx_span, int parity, int phase_mask, int force_reset, int sit_pose, const float *beh8, int gait_cb, int gait_reset) {
     static EnvArgs a;
     memcpy(a.T.f, tf, sizeof a.T.f); memcpy(a.T.i, ti, sizeof a.T.i);
     a.B = *bufs;
     a.tr.hf = rows > 0 ? hf : nullptr; a.tr.origins = origins; a.tr.rows = rows; a.tr.cols = cols; a.tr.levels = levels; a.tr.types = types;
     a.call.step = (uint32_t)step; a.call.vx_lo = vx_lo; a.call.vx_span = vx_span; a.call.parity = parity; a.call.phase_mask = phase_mask;
     a.call.force_reset = force_reset; a.call.sit_pose = sit_pose;
+    for (int k = 0; k < 8; k++) a.call.beh[k] = beh8 ? beh8[k] : 0.f;
+    a.call.gait_cb = gait_cb; a.call.gait_reset = gait_reset;
     emu_launch(env_body, &a, a.T.i[TI_NUM_ENVS]);
     return 0;
 }

@@ -78,6 +78,8 @@ class Injector:
             s = site
             if name == "resample":
                 s = T.SITE_CMD_RESET if inj.in_reset else T.SITE_CMD_RESAMPLE
+            if name == "behavior":
+                s = T.SITE_BEHAVIOR_RESET if inj.in_reset else T.SITE_BEHAVIOR
             inj.site, inj.ids, inj.col, inj.call = s, ids, 0, 0
             try:
                 return fn(*a, **kw)
@@ -106,6 +108,13 @@ class Injector:
         np.random.random = lambda *a, **k: float(philox.uniform(self.seed, self.env.common_step_counter, 0xFFFFFFFF, T.SITE_HOST, 0))
 
         env._resample_commands = self.ctx(env._resample_commands, None, name="resample")
+        if hasattr(env, "_resample_behavior_params"):
+            env._resample_behavior_params = self.ctx(env._resample_behavior_params, None, name="behavior")
+
+            def randint(low, high, size, **k):              # go2_wtw.py:205-206: one gait index per call (R7)
+                u = float(philox.uniform(self.seed, self.env.common_step_counter, 0xFFFFFFFF, T.SITE_HOST, 2 if self.in_reset else 1))
+                return torch.tensor([min(int(u * high), high - 1)])
+            torch.randint = randint
         env._reset_dofs = self.ctx(env._reset_dofs, T.SITE_DOF)
         env._reset_root_states = self.ctx(env._reset_root_states, T.SITE_ROOT)
         if hasattr(env, "_reset_root_states_sit_pose"):
@@ -134,6 +143,21 @@ class Injector:
         env.reset_idx = reset_idx
 
 
+def pack_gait(env):
+    """theta[4], gait_time, phi, gait_period, base_height_t, foot_clearance_t, pitch_t, clock[8] (B200Buffers.gait_state)."""
+    n = lambda t: t.detach().cpu().numpy().astype(np.float32)
+    N = env.num_envs
+    g = np.zeros((N, 20), np.float32)
+    th, clk = n(env.theta), n(env.clock_input)
+    g[:, 0:th.shape[1]] = th
+    g[:, 4:5], g[:, 5:6], g[:, 6:7] = n(env.gait_time), n(env.phi), n(env.gait_period)
+    for k, name in ((7, "base_height_target"), (8, "foot_clearance_target"), (9, "pitch_target")):
+        if hasattr(env, name):
+            g[:, k:k + 1] = n(getattr(env, name))
+    g[:, 10:10 + clk.shape[1]] = clk
+    return g
+
+
 def snapshot(env, spec, sum_names):
     """Reference env -> EnvOracle/B200 state dictionary (fp32, dof order = cfg.asset.dof_names)."""
     sim, rob = env.simulator, env.simulator._robot
@@ -159,7 +183,10 @@ def snapshot(env, spec, sum_names):
     else:
         st["terrain_levels"] = st["terrain_types"] = np.zeros(env.num_envs, np.int32)
     if hasattr(env, "gait_time"):
-        st["gait_state"] = np.concatenate([n(env.theta), n(env.gait_time), n(env.phi), n(env.clock_input)], axis=1)
+        st["gait_state"] = pack_gait(env)
+    if hasattr(env, "critic_history"):                       # go2_wtw names its deques obs_history / critic_history
+        st["obs_hist"] = np.concatenate([n(x) for x in env.obs_history], axis=1)
+        st["critic_hist"] = np.concatenate([n(x) for x in env.critic_history], axis=1)
     if hasattr(env, "obs_history_deque"):
         st["obs_hist"] = np.concatenate([n(x) for x in env.obs_history_deque], axis=1)
         st["critic_hist"] = np.concatenate([n(x) for x in env.critic_obs_deque], axis=1)
@@ -168,6 +195,10 @@ def snapshot(env, spec, sum_names):
         v = np.asarray(v)
         out[k] = v.astype(np.int32) if v.dtype.kind in "iub" and k != "last_contacts" else (v if k == "last_contacts" else v.astype(np.float32))
     out["common_step_counter"] = np.int64(env.common_step_counter)
+    if hasattr(env, "gait_period_range"):                     # go2_wtw host-side behaviour state
+        out["beh_ranges"] = np.asarray([env.gait_period_range, env.base_height_target_range, env.foot_clearance_target_range,
+                                        env.pitch_target_range], np.float64)
+        out["num_gaits"] = np.int64(env.num_gaits)
     out["cmd_range_x"] = np.asarray(env.command_ranges["lin_vel_x"], np.float64)
     return out
 
@@ -215,6 +246,11 @@ def main():
     fwd = quat_apply(q_xyzw, torch.tensor([[1.0, 0.0, 0.0]]).repeat(N, 1))
     env.commands[3::8, :3] = 0.0
     env.commands[3::8, 3] = torch.atan2(fwd[3::8, 1], fwd[3::8, 0])
+    if hasattr(env, "num_gaits"):                                                  # exercise every gait and real ranges
+        env.num_gaits = env.num_gait_max
+        env.gait_period_range, env.base_height_target_range = [0.35, 0.55], [0.24, 0.32]
+        env.foot_clearance_target_range, env.pitch_target_range = [0.05, 0.10], [-0.2, 0.2]
+        ep[4::8] = 250 - 2 - (torch.arange(len(ep[4::8])) % 4).to(ep.dtype)        # behaviour resampling inside the window
     env.step(torch.zeros(N, A))                                                    # make API buffers consistent
     sum_names = list(env.episode_sums.keys())                                      # CaT adds its cstr_* keys lazily
     assert sum_names == spec.episode_sum_names(), (sum_names, spec.episode_sum_names())
@@ -271,13 +307,16 @@ def main():
             o["link_contact_states"] = n(sim._link_contact_states)
         if hasattr(env, "cstr_prob"):
             o["cstr_prob"] = n(env.cstr_prob)
-        if args.task == "tron1_pf_ee":
+        if args.task == "go2_wtw":
+            o["privileged_obs_buf"] = n(ret[1])
+            o["gait_state"] = pack_gait(env)
+        elif args.task == "tron1_pf_ee":
             o["estimator_labels_buf"] = n(ret[1])
             o["privileged_obs_buf"] = n(ret[2])
-            o["gait_state"] = np.concatenate([n(env.theta), n(env.gait_time), n(env.phi), n(env.clock_input)], axis=1)
+            o["gait_state"] = pack_gait(env)
         elif ret[1] is not None:
             o["privileged_obs_buf"] = n(ret[1])
-        if hasattr(env, "obs_history") and args.task != "tron1_pf_ee" and t in (args.steps // 2, args.steps - 1):
+        if hasattr(env, "obs_history") and args.task not in ("tron1_pf_ee", "go2_wtw") and t in (args.steps // 2, args.steps - 1):
             rec[f"hist{t}/obs_history"] = n(env.obs_history)
             rec[f"hist{t}/critic_obs_buf"] = n(env.critic_obs_buf)
         for k, v in o.items():
