@@ -28,6 +28,7 @@ struct B200Handle {
     int sit_pose = 0;
     float beh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int gait_cb = 0, gait_reset = 0;
+    EnvStageTab stage{};
 };
 
 extern "C" {
@@ -90,6 +91,7 @@ int b200_bind_buffers(B200Handle *h, const B200Buffers *b) {
         if (!p[k] && !optional) return fail("b200_bind_buffers: null buffer pointer");
     }
     h->bufs = *b; h->bound = true;
+    h->stage = env_stage_table(h->task, h->bufs, ENV_WARPS_PER_BLOCK);
     return 0;
 }
 
@@ -123,7 +125,7 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     for (int k = 0; k < 8; k++) call.beh[k] = h->beh[k];
     call.gait_cb = h->gait_cb; call.gait_reset = h->gait_reset;
     const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
-    env_post_step_kernel<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call);
+    env_post_step_kernel<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call, h->stage);
     h->launches++;
     CK(cudaGetLastError());
     if ((mask & PHASE_RESET) && !force) {

@@ -70,10 +70,12 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
     uint32_t ok;
-    do {
+    for (;;) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
-    } while (!ok);
+        if (ok) break;
+        __nanosleep(200);                                  // leave the issue slots to the CTAs that already have their data
+    }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {

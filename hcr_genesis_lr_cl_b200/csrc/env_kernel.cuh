@@ -24,7 +24,12 @@
 #include "philox.cuh"
 #include "dynamics_kernel.cuh"   // TaskDev, TerrainDev
 
+#ifndef ENV_WARPS_PER_BLOCK
 #define ENV_WARPS_PER_BLOCK 4
+#endif
+#ifndef ENV_MIN_BLOCKS
+#define ENV_MIN_BLOCKS 5
+#endif
 #define ES_OBS 0                   // clean obs [B200_MAX_OBS = 64]
 #define ES_NOISY 64                // noisy obs [64]
 #define ES_CRIT 128                 // single critic frame [<=192]
@@ -126,6 +131,14 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     EnvRng rng; rng.k0 = (uint32_t)ti[TI_SEED_LO]; rng.k1 = (uint32_t)ti[TI_SEED_HI]; rng.env = (uint32_t)(env + ti[TI_ENV_OFFSET]); rng.step = call.step;
     const float dt = tf[TF_POLICY_DT];
     if (hrow != nullptr) mbar_wait(bar, 0);                     // staged CTA: every input slab (state + history) has landed
+    // Staged CTAs hold only live envs, so their warps can meet at CTA barriers between the sections below: the warps of
+    // an SM then walk the (several hundred KB of) straight-line code together and share instruction-cache lines instead
+    // of each missing on its own (ncu: `no_instruction` was the second-largest stall).  Uniform per CTA by construction.
+#ifndef ENV_NO_SECTION_SYNC
+#define ENV_SECTION_SYNC() do { if (hrow != nullptr) __syncthreads(); } while (0)
+#else
+#define ENV_SECTION_SYNC()
+#endif
 
     // ------------------------------------------------------------------ per-env scalars (replicated in all lanes)
     f3 bp = mk3(R.base_pos[env * 3], R.base_pos[env * 3 + 1], R.base_pos[env * 3 + 2]);
@@ -272,6 +285,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         if (ti[TI_CONTACT_STATES] && lane < ti[TI_N_CS]) es[ES_LCS + lane] = B.link_contact_states[env * ti[TI_N_CS] + lane];
     }
     __syncwarp();
+    ENV_SECTION_SYNC();
 
     // ================================================================== _post_physics_step_callback
     if (pm & PHASE_CALLBACK) {
@@ -371,6 +385,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         for (int i = 0; i < nr; i++) {
             const int id = ti[TI_REWARD_IDS + i];
             float r = 0.f;
+            ENV_SECTION_SYNC();
             switch (id) {
             case RW_ACTION_RATE: { const float d = lastj - actj; r = warp_sum(d * d); break; }
             case RW_ACTION_SMOOTHNESS: { const float d = actj - 2.0f * lastj + llastj; r = warp_sum(d * d); break; }
@@ -491,6 +506,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         if (gtime >= __fsub_rn(gper, __fmul_rn(dt, 0.5f))) gtime = 0.f;
         gphi = __fdiv_rn(gtime, gper);
     }
+    ENV_SECTION_SYNC();
     // ================================================================== reset_idx
     f3 grav_obs = grav;
     int new_level = level0;
@@ -619,6 +635,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     }
     __syncwarp();   // DR parameters written above are re-read below by other lanes
 
+    ENV_SECTION_SYNC();
     // ================================================================== compute_observations
     if (pm & PHASE_OBSERVE) {
         const int NO = ti[TI_NUM_OBS];
@@ -870,8 +887,41 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     X(last_contacts, uint8_t, F_) X(friction, float, 1) X(added_mass, float, 1) X(com_bias, float, 3)                  \
     X(kp_scale, float, A_) X(kd_scale, float, A_) X(gait_state, float, B200_GAIT_STATE)
 
-__global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, 5)
-env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call) {
+// Staging table, built once on the host when the buffers are bound: for every per-env input tensor its base pointer,
+// bytes per env and byte offset inside a CTA's input slab (ENV_NOT_STAGED when a CTA's slice is not a multiple of 16
+// bytes -- that tensor is then read straight from global memory).  Thread t of a CTA issues the bulk copy of entry t,
+// so the per-thread set-up is a handful of instructions instead of the address arithmetic of all tensors.
+#define ENV_MAX_STAGED 40
+#define ENV_NOT_STAGED 0xFFFFFFFFu
+struct EnvStageTab {
+    const char *src[ENV_MAX_STAGED];
+    uint32_t row_bytes[ENV_MAX_STAGED];
+    uint32_t off[ENV_MAX_STAGED];
+    int n;                 // entries
+    uint32_t in_bytes;     // bytes the staged entries of one CTA bring in
+    int ok;                // the task's CTAs can be staged at all (history slabs satisfy the bulk-copy size rule)
+};
+
+inline EnvStageTab env_stage_table(const TaskDev &T, const B200Buffers &B, int nwarps) {
+    EnvStageTab tab;
+    const int A = T.i[TI_A], F = T.i[TI_F], L = T.i[TI_L], NSUM = T.i[TI_N_SUMS];
+    const uint32_t hbytes = (uint32_t)(nwarps * T.i[TI_FRAME_STACK] * T.i[TI_NUM_OBS] * 4), cbytes = (uint32_t)(nwarps * T.i[TI_C_FRAME_STACK] * T.i[TI_SINGLE_CRITIC] * 4);
+    tab.n = 0; tab.in_bytes = 0;
+    tab.ok = T.i[TI_OBS_KIND] >= 1 && B200_TMA_SIZE_OK(hbytes) && B200_TMA_SIZE_OK(cbytes);
+    uint32_t off = 0;
+#define X_TAB(field, type, k) { const uint32_t row_ = (uint32_t)((k) * sizeof(type)), b_ = (uint32_t)nwarps * row_;                \
+        const bool st_ = B.field != nullptr && B200_TMA_SIZE_OK(b_) && off + b_ <= (uint32_t)(nwarps * ENV_IN_WORDS * 4);           \
+        tab.src[tab.n] = (const char *)B.field; tab.row_bytes[tab.n] = row_; tab.off[tab.n] = st_ ? off : ENV_NOT_STAGED;           \
+        if (st_) { tab.in_bytes += b_; off += (b_ + 15u) & ~15u; }                                                                  \
+        tab.n++; }
+    ENV_STAGED_INPUTS(X_TAB, A, F, L, NSUM)
+#undef X_TAB
+    for (int k = tab.n; k < ENV_MAX_STAGED; k++) { tab.src[k] = nullptr; tab.row_bytes[k] = 0; tab.off[k] = ENV_NOT_STAGED; }
+    return tab;
+}
+
+__global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, ENV_MIN_BLOCKS)
+env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call, const EnvStageTab tab) {
     extern __shared__ float smem[];
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -882,29 +932,23 @@ env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, 
     float *hslab = smem + 4, *cslab = hslab + nwarps * env_row_words(HW), *es = cslab + nwarps * env_row_words(CW);
     char *inslab = (char *)(es + nwarps * ES_TOTAL);
     const uint32_t hbytes = (uint32_t)(nwarps * HW * 4), cbytes = (uint32_t)(nwarps * CW * 4);
-    const int A = T.i[TI_A], F = T.i[TI_F], L = T.i[TI_L];
-    const int NSUM = T.i[TI_N_SUMS];
     const bool full = !call.force_reset && (call.phase_mask & PHASE_ALL) == PHASE_ALL;
-    // pass 1 (all threads, uniform): byte counts of every slab -> is the CTA stageable, how many bytes will arrive
-    uint32_t total = hbytes + cbytes, off = 0;
-    bool ok = full && T.i[TI_OBS_KIND] >= 1 && env0 + nwarps <= N && B200_TMA_SIZE_OK(hbytes) && B200_TMA_SIZE_OK(cbytes);
-#define X_COUNT(field, type, k) { const uint32_t b_ = (uint32_t)(nwarps * (k) * sizeof(type)); ok = ok && B200_TMA_SIZE_OK(b_); total += b_; off += (b_ + 15u) & ~15u; }
-    ENV_STAGED_INPUTS(X_COUNT, A, F, L, NSUM)
-#undef X_COUNT
-    const bool staged = ok && off <= (uint32_t)(nwarps * ENV_IN_WORDS * 4);
+    const bool staged = full && tab.ok && env0 + nwarps <= N;
     if (staged) {
-        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_expect_tx(bar, total); }
+        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_expect_tx(bar, tab.in_bytes + hbytes + cbytes); }
         __syncthreads();                                   // barrier armed before any copy can complete on it
-        // pass 2: thread t issues the bulk copy of tensor t; every thread builds the same biased read view R
+        // thread t issues the bulk copy of table entry t; the last two threads bring in the history slabs
+        for (int t = (int)threadIdx.x; t < tab.n; t += (int)blockDim.x)
+            if (tab.off[t] != ENV_NOT_STAGED)
+                tma_load_1d(inslab + tab.off[t], tab.src[t] + (size_t)env0 * tab.row_bytes[t], (uint32_t)nwarps * tab.row_bytes[t], bar);
+        if (threadIdx.x == blockDim.x - 1) tma_load_1d(hslab, B.obs_history[call.parity] + (size_t)env0 * HW, hbytes, bar);
+        if (threadIdx.x == blockDim.x - 2) tma_load_1d(cslab, B.critic_obs[call.parity] + (size_t)env0 * CW, cbytes, bar);
+        // every thread builds the same read view R: staged tensors point into the slab, biased so that R.x[env * k + i] works
         B200Buffers R = B;
-        int t = 2; off = 0;
-        if (threadIdx.x == 0) tma_load_1d(hslab, B.obs_history[call.parity] + (size_t)env0 * HW, hbytes, bar);
-        if (threadIdx.x == 1) tma_load_1d(cslab, B.critic_obs[call.parity] + (size_t)env0 * CW, cbytes, bar);
-#define X_LOAD(field, type, k) { const uint32_t b_ = (uint32_t)(nwarps * (k) * sizeof(type));                              \
-        if ((int)threadIdx.x == t % (int)blockDim.x) tma_load_1d(inslab + off, B.field + (size_t)env0 * (k), b_, bar);                      \
-        R.field = (type *)(inslab + off) - (size_t)env0 * (k); off += (b_ + 15u) & ~15u; t++; }
-        ENV_STAGED_INPUTS(X_LOAD, A, F, L, NSUM)
-#undef X_LOAD
+        int t = 0;
+#define X_VIEW(field, type, k) { if (tab.off[t] != ENV_NOT_STAGED) R.field = (type *)(inslab + tab.off[t]) - (size_t)env0 * (k); t++; }
+        ENV_STAGED_INPUTS(X_VIEW, T.i[TI_A], T.i[TI_F], T.i[TI_L], T.i[TI_N_SUMS])
+#undef X_VIEW
         env_post_step_warp(T, B, R, tr, call, es + warp * ES_TOTAL, env, lane, hslab + warp * HW, cslab + warp * CW, bar);
         fence_proxy_async();                               // generic-proxy smem writes -> visible to the bulk store
         __syncthreads();

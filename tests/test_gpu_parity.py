@@ -197,6 +197,7 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
         gs[:, H["B200_GS_PHI"]] = gs[:, H["B200_GS_GT"]] / gs[:, H["B200_GS_PER"]]
     else:
         gs[:, 0], gs[:, 1] = rng.uniform(0, 1, N), rng.uniform(0, 1, N) + 0.5
+        gs[:, H["B200_GS_PER"]] = spec.gait_period
         gs[:, H["B200_GS_PHI"]] = gs[:, H["B200_GS_GT"]] / np.float32(spec.gait_period)
     st["gait_state"] = gs
     env = _env(spec, N, terrain)

@@ -35,8 +35,8 @@ int emu_dynamics_step(const float *tf, const int *ti, const int *mi, const float
 }
 
 #ifdef EMU_WITH_ENV
-struct EnvArgs { TaskDev T; B200Buffers B; TerrainDev tr; EnvCall call; };
-static void env_body(void *p) { EnvArgs *a = (EnvArgs *)p; env_post_step_kernel(a->T, a->B, a->tr, a->call); }
+struct EnvArgs { TaskDev T; B200Buffers B; TerrainDev tr; EnvCall call; EnvStageTab tab; };
+static void env_body(void *p) { EnvArgs *a = (EnvArgs *)p; env_post_step_kernel(a->T, a->B, a->tr, a->call, a->tab); }
 int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int rows, int cols, const float *origins, int levels, int types,
                       const B200Buffers *bufs, long long step, float vx_lo, float vx_span, int parity, int phase_mask, int force_reset, int sit_pose, const float *beh8, int gait_cb, int gait_reset) {
     static EnvArgs a;
@@ -47,6 +47,7 @@ int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int row
     a.call.force_reset = force_reset; a.call.sit_pose = sit_pose;
     for (int k = 0; k < 8; k++) a.call.beh[k] = beh8 ? beh8[k] : 0.f;
     a.call.gait_cb = gait_cb; a.call.gait_reset = gait_reset;
+    a.tab = env_stage_table(a.T, a.B, 1);          // the emulator runs one warp per block
     emu_launch(env_body, &a, a.T.i[TI_NUM_ENVS]);
     return 0;
 }
