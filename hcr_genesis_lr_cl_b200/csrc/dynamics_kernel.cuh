@@ -39,7 +39,7 @@
 #define PHASE_SYNC()
 #endif
 #ifndef DYN_MIN_BLOCKS
-#define DYN_MIN_BLOCKS 6      // resident CTAs per SM the register allocator must allow (80 regs/thread, 24 warps/SM)
+#define DYN_MIN_BLOCKS 7      // resident CTAs per SM the register allocator must allow (72 regs/thread, 28 warps/SM)
 #endif
 
 struct TaskDev {
@@ -63,21 +63,25 @@ struct TerrainDev {
 };
 
 // ---- per-warp shared scratch (floats) ----
+// The frames / joint axes / body velocities / contact list / aux rows are consumed by the time the constraint rows are
+// built; the Delassus matrix A is written after that point and is dead before the next substep's kinematics rewrites
+// them, so A shares their storage.  7 KB per env lets 28 envs (7 CTAs of 4 warps) live on one SM: at 4096 envs per GPU
+// the whole batch is resident in a single wave.
 #define WS_FR 0                         // frames [13][12]  R(9) o(3)
 #define WS_AX (WS_FR + 13 * 12)         // joint axes [12][3]
 #define WS_VEL (WS_AX + 36)             // body spatial velocity [13][6] (w, v)
-#define WS_MI (WS_VEL + 78)             // per chain: Dinv(6) G(18) ; then Sinv(21)
+#define WS_CT (WS_VEL + 78)             // contacts [8][12]
+#define WS_AUX (WS_CT + 96)             // aux rows [8][4]: joint, sign, pos, bound
+#define WS_AM 0                         // A [32][33], aliases everything above (398 floats)
+#define WS_MI (WS_AM + 32 * 33)         // per chain: Dinv(6) G(18) ; then Sinv(21)
 #define WS_NU (WS_MI + 4 * 24 + 24)     // generalized velocity [18]
 #define WS_AF (WS_NU + 18)              // smooth acceleration [18]
-#define WS_CT (WS_AF + 18)              // contacts [8][12]
-#define WS_AUX (WS_CT + 96)             // aux rows [8][4]: joint, sign, pos, bound
-#define WS_JR (WS_AUX + 32)             // J rows [32][10]: Jb(6) Jl(3) chain
-#define WS_AM (WS_JR + 320)             // A [32][33]
-#define WS_FV (WS_AM + 32 * 33)         // row force vectors [32][4]
+#define WS_JR (WS_AF + 18)              // J rows [32][10]: Jb(6) Jl(3) chain
+#define WS_FV (WS_JR + 320)             // row force vectors [32][4]
 #define WS_LF (WS_FV + 128)             // link forces [17*3]
-#define WS_Q (WS_LF + 52)               // joint q [12]
-#define WS_WARM (WS_Q + 12)             // PGS warm start [48]: 8 x (sphere id + 1, f_n, f_t1, f_t2), 8 x (aux code + 1, f)
+#define WS_WARM (WS_LF + 52)            // PGS warm start [48]: 8 x (sphere id + 1, f_n, f_t1, f_t2), 8 x (aux code + 1, f)
 #define WS_TOTAL (WS_WARM + 48)
+static_assert(WS_AUX + 32 <= WS_MI, "aliased inputs must fit under the A matrix");
 
 #define MS_BODY 0
 #define MS_LINK (MS_BODY + B200_MAX_BODIES * B200_BODY_STRIDE)
@@ -433,7 +437,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         }
         if (leg) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) { ws[WS_NU + 6 + 3 * c + k] = qd[k]; ws[WS_AF + 6 + 3 * c + k] = al[k]; ws[WS_Q + 3 * c + k] = q[k]; }
+            for (int k = 0; k < 3; k++) { ws[WS_NU + 6 + 3 * c + k] = qd[k]; ws[WS_AF + 6 + 3 * c + k] = al[k]; }
         }
         if (lane == 0) {
             ws[WS_NU + 0] = vb.x; ws[WS_NU + 1] = vb.y; ws[WS_NU + 2] = vb.z; ws[WS_NU + 3] = wb.x; ws[WS_NU + 4] = wb.y; ws[WS_NU + 5] = wb.z;
