@@ -38,6 +38,14 @@ METRIC = "env-steps/sec (physics substeps x envs), Go2 rough terrain, 4096 envs/
 UNIT = "env-substeps/s"
 ENVS_PER_GPU = 4096
 TASK = "go2_ts"
+WORKLOADS = {   # BASELINE.json configs; the metric is quoted on go2_ts (config 2), the others are selectable with --task
+    "go2": "Go2 flat-terrain velocity tracking (base go2 task)",
+    "go2_ts": "Go2 rough-terrain heightfield curriculum with height-scan obs",
+    "go2_cat": "Go2 CaT constraints-as-terminations, rough terrain",
+    "go2_wtw": "Go2 Walk-These-Ways with periodic gait rewards",
+    "tron1_pf": "TRON1_PF point-foot biped rough terrain with domain randomisation",
+    "tron1_pf_ee": "TRON1_PF biped with explicit estimator, periodic gait, rough terrain",
+}
 
 
 def _peaks():
@@ -89,19 +97,19 @@ def run_reference(args):
     if rank != 0:
         return
     from hcr_genesis_lr_cl_b200 import task_spec as T
-    from hcr_genesis_lr_cl_b200.terrain_assets import load_go2_rough_terrain
+    from hcr_genesis_lr_cl_b200.terrain_assets import terrain_for
     from oracle.cpu_baseline import time_cpu_baseline
     from oracle import physics
     physics.build()
-    spec = T.PRESETS[TASK]()
+    spec = T.PRESETS[args.task]()
     cores = os.cpu_count() or 1
     sample_envs = 256 * cores
-    res = time_cpu_baseline(spec, load_go2_rough_terrain(), sample_envs, steps=max(args.steps, 1), threads=cores, warmup=max(args.warmup, 1))
+    res = time_cpu_baseline(spec, terrain_for(spec), sample_envs, steps=max(args.steps, 1), threads=cores, warmup=max(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{TASK}: Go2 rough-terrain heightfield curriculum with height-scan obs, {ENVS_PER_GPU} envs/GPU "
+        "config": {"workload": f"{args.task}: {WORKLOADS[args.task]}, {ENVS_PER_GPU} envs/GPU "
                                f"(bounded CPU sample per step: {sample_envs} envs)", "decimation": spec.decimation},
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -116,7 +124,7 @@ def run_gpu(args):
     import torch.distributed as dist
     from hcr_genesis_lr_cl_b200 import accounting, build, task_spec as T
     from hcr_genesis_lr_cl_b200.fused_env import FusedLeggedEnv
-    from hcr_genesis_lr_cl_b200.terrain_assets import load_go2_rough_terrain
+    from hcr_genesis_lr_cl_b200.terrain_assets import terrain_for
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -127,8 +135,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     build.build()
-    spec = T.PRESETS[TASK]()
-    terrain = load_go2_rough_terrain()
+    spec = T.PRESETS[args.task]()
+    terrain = terrain_for(spec)
     N = args.envs
     env = FusedLeggedEnv(spec, N, dev, terrain=terrain, env_offset=rank * N, num_envs_global=world * N)
     sim = env.simulator
@@ -162,6 +170,7 @@ def run_gpu(args):
         ev[i][1].record()
         env.common_step_counter += 1
         env._apply_pending_curriculum()
+        env._set_step_flags()
         sim.fused_post_step(env.common_step_counter, env.command_ranges["lin_vel_x"])
         ev[i][2].record()
         env._fill_extras()
@@ -210,7 +219,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{TASK}: Go2 rough-terrain heightfield curriculum with height-scan obs, {N} envs/GPU",
+        "config": {"workload": f"{args.task}: {WORKLOADS[args.task]}, {N} envs/GPU",
                    "envs_per_gpu": N, "decimation": spec.decimation, "pgs_iterations": spec.pgs_iterations,
                    "actions": "N(0,1) (policy at init)", "l2": "flushed between timed steps (256 MB write)",
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
@@ -246,6 +255,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--task", default=TASK, choices=sorted(WORKLOADS), help="task preset (default: the metric's config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

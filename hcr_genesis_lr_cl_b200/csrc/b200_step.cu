@@ -29,6 +29,12 @@ struct B200Handle {
     float beh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int gait_cb = 0, gait_reset = 0;
     EnvStageTab stage{};
+    // side stream of b200_history_shift: forked at the event b200_dynamics_step records before its launch, joined by the
+    // next b200_env_post_step
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool fork_recorded = false;
+    int preshift_parity = -1;      // parity the stacks have been shifted for (-1: none pending)
 };
 
 extern "C" {
@@ -57,8 +63,7 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
     h->model.body = h->d_model_f; h->model.link_off = h->d_model_f + nb * B200_BODY_STRIDE; h->model.sph = h->model.link_off + 3 * L;
     h->model.link_body = h->d_model_i + 8; h->model.sph_body = h->model.link_body + L; h->model.sph_link = h->model.sph_body + NS;
     h->dyn_smem = dyn_smem_bytes(DYN_WARPS_PER_BLOCK);
-    h->env_smem = env_smem_bytes(ENV_WARPS_PER_BLOCK, ti[TI_OBS_KIND] >= 1 ? ti[TI_FRAME_STACK] * ti[TI_NUM_OBS] : 0,
-                                 ti[TI_OBS_KIND] >= 1 ? ti[TI_C_FRAME_STACK] * ti[TI_SINGLE_CRITIC] : 0);
+    h->env_smem = env_smem_bytes(ENV_WARPS_PER_BLOCK);
     if (h->env_smem > 48 * 1024) CK(cudaFuncSetAttribute(env_post_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->env_smem));
     CK(cudaFuncSetAttribute(dynamics_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
     CK(cudaFuncSetAttribute(dynamics_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
@@ -69,6 +74,9 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
 void b200_destroy(B200Handle *h) {
     if (!h) return;
     cudaFree(h->d_model_f); cudaFree(h->d_model_i);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
 }
 
@@ -109,10 +117,37 @@ int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
     const dim3 grid((N + DYN_WARPS_PER_BLOCK - 1) / DYN_WARPS_PER_BLOCK), block(DYN_WARPS_PER_BLOCK * 32);
     cudaStream_t s = (cudaStream_t)stream;
     if (h->task.i[TI_CAT]) CK(cudaMemsetAsync(h->bufs.global_flags, 0, 4 * sizeof(int32_t), s));
+    if (h->task.i[TI_OBS_KIND] >= 1) {               // fork point of b200_history_shift: everything enqueued before this step
+        if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventRecord(h->ev_fork, s));
+        h->fork_recorded = true;
+    }
     if (h->task.i[TI_C] == 4) dynamics_step_kernel<4><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions);
     else dynamics_step_kernel<2><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions);
     h->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+int b200_history_shift(B200Handle *h, int parity, void *stream) {
+    if (check_ready(h, "b200_history_shift")) return 1;
+    const int *ti = h->task.i;
+    if (ti[TI_OBS_KIND] < 1) return 0;               // the task keeps no frame stacks
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h->side) CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    if (!h->ev_join) CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    if (!h->fork_recorded) CK(cudaEventRecord(h->ev_fork, s));     // no dynamics step before us: fork here
+    h->fork_recorded = false;
+    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    const int N = ti[TI_NUM_ENVS], p = parity & 1;
+    const int Wh = ti[TI_FRAME_STACK] * ti[TI_NUM_OBS], Wc = ti[TI_C_FRAME_STACK] * ti[TI_SINGLE_CRITIC];
+    history_shift_kernel<<<(N + 7) / 8, 256, 0, h->side>>>(h->bufs.obs_history[p], h->bufs.obs_history[p ^ 1], Wh, ti[TI_NUM_OBS],
+                                                           h->bufs.critic_obs[p], h->bufs.critic_obs[p ^ 1], Wc, ti[TI_SINGLE_CRITIC], N);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_join, h->side));
+    h->preshift_parity = p;
     return 0;
 }
 
@@ -124,6 +159,12 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.parity = parity & 1; call.phase_mask = mask; call.force_reset = force; call.sit_pose = h->sit_pose;
     for (int k = 0; k < 8; k++) call.beh[k] = h->beh[k];
     call.gait_cb = h->gait_cb; call.gait_reset = h->gait_reset;
+    call.preshifted = 0;
+    if (h->preshift_parity >= 0) {                   // join the side stream; use its work only if it was for this parity and phase set
+        CK(cudaStreamWaitEvent(s, h->ev_join, 0));
+        call.preshifted = (h->preshift_parity == (parity & 1) && !force && (mask & PHASE_OBSERVE)) ? 1 : 0;
+        h->preshift_parity = -1;
+    }
     const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
     env_post_step_kernel<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call, h->stage);
     h->launches++;

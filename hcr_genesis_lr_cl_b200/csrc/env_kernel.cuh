@@ -28,7 +28,7 @@
 #define ENV_WARPS_PER_BLOCK 4
 #endif
 #ifndef ENV_MIN_BLOCKS
-#define ENV_MIN_BLOCKS 5
+#define ENV_MIN_BLOCKS 7
 #endif
 #define ES_OBS 0                   // clean obs [B200_MAX_OBS = 64]
 #define ES_NOISY 64                // noisy obs [64]
@@ -40,8 +40,6 @@
 #define ES_NV 596                  // terrain normals around feet [4*3]
 #define ES_TOTAL 608
 #define ENV_IN_WORDS 288           // staged per-env input rows (all small state tensors), words per env
-// CTA-level staging of the two history stacks (TMA bulk copies): the rows of a CTA's ENV_WARPS_PER_BLOCK consecutive
-// envs form one contiguous, 16-byte aligned slab in HBM even though a single 885-float critic row is not.
 
 #define ENV_STATS_RING 32           // per-step episode statistics are kept for this many policy steps
 
@@ -54,13 +52,11 @@ struct EnvCall {
     int sit_pose;        // envs resetting in this call start in the sit pose (one host coin per step, tron1_pf_ee.py:204-210)
     float beh[8];        // go2_wtw behaviour ranges {gait period, base height, foot clearance, pitch} x {lo, span}
     int gait_cb, gait_reset;   // gait index the host drew for the callback / reset resampling of this step
+    int preshifted;      // history_shift_kernel already moved the kept frames of both stacks for this parity
 };
 
-// shared memory per CTA: mbarrier + per warp (scratch, staged history row, staged critic row, staged input rows)
-__host__ __device__ inline int env_row_words(int w) { return (w + 3) & ~3; }
-__host__ __device__ inline int env_smem_bytes(int warps, int hist_words, int crit_words) {
-    return 16 + warps * (ES_TOTAL + env_row_words(hist_words) + env_row_words(crit_words) + ENV_IN_WORDS) * 4;
-}
+// shared memory per CTA: mbarrier + per warp (scratch, staged input rows)
+__host__ __device__ inline int env_smem_bytes(int warps) { return 16 + warps * (ES_TOTAL + ENV_IN_WORDS) * 4; }
 
 // quat_rotate_inverse (math_utils.py:63-76), q = xyzw
 __device__ __forceinline__ f3 rot_inv(float qx, float qy, float qz, float qw, f3 v) {
@@ -101,28 +97,34 @@ __device__ __forceinline__ void shift_copy(float *__restrict__ dst, const float 
     for (; e < n; e += 32) dst[e] = cleared ? 0.f : __ldcs(src + e);
 }
 
-// in-place shift of a staged row by `frame` floats (drop the oldest frame), then append `newf`; writes trail reads
-__device__ __forceinline__ void smem_shift_append(float *row, int W, int frame, const float *newf, bool cleared, int lane) {
+// One env's row of a frame stack: drop the oldest frame, append `newf`.  When history_shift_kernel has already moved the
+// kept frames into `dst` (preshifted), only the new frame is written here -- and a reset clears what was moved.
+__device__ __forceinline__ void history_append(float *dst, const float *src, int env, int W, int frame, const float *newf, bool cleared,
+                                               int preshifted, int lane) {
     const int keepw = W - frame;
-    for (int i0 = 0; i0 < keepw; i0 += 256) {
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) { const int e = i0 + 32 * k + lane; v[k] = (e < keepw && !cleared) ? row[e + frame] : 0.f; }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 8; k++) { const int e = i0 + 32 * k + lane; if (e < keepw) row[e] = v[k]; }
-        __syncwarp();
-    }
-    for (int e = lane; e < frame; e += 32) row[keepw + e] = newf[e];
+    float *d = dst + (size_t)env * W;
+    if (!preshifted) shift_copy(d, src + (size_t)env * W + frame, keepw, cleared, lane);
+    else if (cleared) for (int e = lane; e < keepw; e += 32) d[e] = 0.f;
+    for (int e = lane; e < frame; e += 32) d[keepw + e] = newf[e];
 }
 
-// `hrow` / `crow`: this env's rows of the CTA's staged history slabs (nullptr -> direct global copies), `bar`: the
-// mbarrier the TMA loads complete on.
+// The shift of both frame stacks for the coming env_post_step (b200_history_shift): out[env][0 : W - frame] =
+// in[env][frame : W].  It depends on nothing the dynamics kernel produces, so it is launched on a side stream and runs
+// in the shadow of the dynamics kernel; one warp per env row, 8 independent 128-byte requests in flight per warp.
+__global__ void history_shift_kernel(const float *in_h, float *out_h, int Wh, int fh, const float *in_c, float *out_c, int Wc, int fc, int N) {
+    const int lane = threadIdx.x & 31;
+    const int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (env >= N) return;
+    shift_copy(out_h + (size_t)env * Wh, in_h + (size_t)env * Wh + fh, Wh - fh, false, lane);
+    shift_copy(out_c + (size_t)env * Wc, in_c + (size_t)env * Wc + fc, Wc - fc, false, lane);
+}
+
+// `staged`: the CTA's inputs were brought into shared memory by bulk copies completing on the mbarrier `bar`.
 // `R` is the view all per-env *inputs* are read through: B itself, or (staged CTAs) a copy whose pointers are biased so
 // that R.x[env * k + i] lands in the CTA's shared-memory slab that TMA filled -- one exposed DRAM latency per CTA
 // instead of one per dependent load.  All stores go to B (global memory).
 __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const B200Buffers &R, const TerrainDev &tr, const EnvCall &call,
-                                   float *es, int env, int lane, float *hrow, float *crow, uint64_t *bar) {
+                                   float *es, int env, int lane, bool staged, uint64_t *bar) {
     const float *tf = T.f;
     const int *ti = T.i;
     const int A = ti[TI_A], F = ti[TI_F], L = ti[TI_L], P = ti[TI_PX] * ti[TI_PY];
@@ -130,12 +132,12 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     const int pm = call.force_reset ? PHASE_RESET : call.phase_mask;
     EnvRng rng; rng.k0 = (uint32_t)ti[TI_SEED_LO]; rng.k1 = (uint32_t)ti[TI_SEED_HI]; rng.env = (uint32_t)(env + ti[TI_ENV_OFFSET]); rng.step = call.step;
     const float dt = tf[TF_POLICY_DT];
-    if (hrow != nullptr) mbar_wait(bar, 0);                     // staged CTA: every input slab (state + history) has landed
+    if (staged) mbar_wait(bar, 0);                              // staged CTA: every input slab has landed
     // Staged CTAs hold only live envs, so their warps can meet at CTA barriers between the sections below: the warps of
     // an SM then walk the (several hundred KB of) straight-line code together and share instruction-cache lines instead
     // of each missing on its own (ncu: `no_instruction` was the second-largest stall).  Uniform per CTA by construction.
 #ifndef ENV_NO_SECTION_SYNC
-#define ENV_SECTION_SYNC() do { if (hrow != nullptr) __syncthreads(); } while (0)
+#define ENV_SECTION_SYNC() do { if (staged) __syncthreads(); } while (0)
 #else
 #define ENV_SECTION_SYNC()
 #endif
@@ -687,23 +689,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             __syncwarp();
             for (int e = lane; e < SC; e += 32) cr[e] = fminf(fmaxf(cr[e], -clipo), clipo);
             __syncwarp();
-            if (hrow != nullptr) {
-                smem_shift_append(hrow, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, lane);
-                smem_shift_append(crow, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, lane);
-            } else {
-                {
-                    const int W = ti[TI_FRAME_STACK] * NO, keepw = W - NO;
-                    shift_copy(B.obs_history[call.parity ^ 1] + (size_t)env * W, B.obs_history[call.parity] + (size_t)env * W + NO, keepw, cleared, lane);
-                    float *dst = B.obs_history[call.parity ^ 1] + (size_t)env * W;
-                    for (int e = lane; e < NO; e += 32) dst[keepw + e] = nz[e];
-                }
-                {
-                    const int W = ti[TI_C_FRAME_STACK] * SC, keepw = W - SC;
-                    shift_copy(B.critic_obs[call.parity ^ 1] + (size_t)env * W, B.critic_obs[call.parity] + (size_t)env * W + SC, keepw, cleared, lane);
-                    float *dst = B.critic_obs[call.parity ^ 1] + (size_t)env * W;
-                    for (int e = lane; e < SC; e += 32) dst[keepw + e] = cr[e];
-                }
-            }
+            history_append(B.obs_history[call.parity ^ 1], B.obs_history[call.parity], env, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, call.preshifted, lane);
+            history_append(B.critic_obs[call.parity ^ 1], B.critic_obs[call.parity], env, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, call.preshifted, lane);
         } else if (ti[TI_OBS_KIND] == 4) {   // tron1_pf_ee.py:53-141: features = 10 x 31 noisy frames, labels 17, critic = 10 x 134
             const int SC = ti[TI_SINGLE_CRITIC], NP = ti[TI_NUM_PRIV], NCS = ti[TI_N_CS], NB = NO - 4;   // NB = 9 + 3A
             float *cr = es + ES_CRIT, *pv = es + ES_PRIV;
@@ -754,23 +741,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             for (int e = lane; e < NP; e += 32) B.privileged_obs_buf[env * NP + e] = pv[e];          // estimator labels (unclipped)
             for (int e = lane; e < SC; e += 32) cr[e] = fminf(fmaxf(cr[e], -clipo), clipo);
             __syncwarp();
-            if (hrow != nullptr) {
-                smem_shift_append(hrow, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, lane);
-                smem_shift_append(crow, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, lane);
-            } else {
-                {
-                    const int W = ti[TI_FRAME_STACK] * NO, keepw = W - NO;
-                    shift_copy(B.obs_history[call.parity ^ 1] + (size_t)env * W, B.obs_history[call.parity] + (size_t)env * W + NO, keepw, cleared, lane);
-                    float *dst = B.obs_history[call.parity ^ 1] + (size_t)env * W;
-                    for (int e = lane; e < NO; e += 32) dst[keepw + e] = nz[e];
-                }
-                {
-                    const int W = ti[TI_C_FRAME_STACK] * SC, keepw = W - SC;
-                    shift_copy(B.critic_obs[call.parity ^ 1] + (size_t)env * W, B.critic_obs[call.parity] + (size_t)env * W + SC, keepw, cleared, lane);
-                    float *dst = B.critic_obs[call.parity ^ 1] + (size_t)env * W;
-                    for (int e = lane; e < SC; e += 32) dst[keepw + e] = cr[e];
-                }
-            }
+            history_append(B.obs_history[call.parity ^ 1], B.obs_history[call.parity], env, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, call.preshifted, lane);
+            history_append(B.critic_obs[call.parity ^ 1], B.critic_obs[call.parity], env, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, call.preshifted, lane);
         } else if (ti[TI_OBS_KIND] == 3) {   // tron1_pf.py:15-70: obs_buf = stack of noisy frames, privileged_obs_buf = stack of critic frames
             const int SC = ti[TI_SINGLE_CRITIC];
             float *cr = es + ES_CRIT;
@@ -786,23 +758,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             }
             if (fl) cr[3 + NO + A + 7 + lane] = fat;
             __syncwarp();
-            if (hrow != nullptr) {
-                smem_shift_append(hrow, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, lane);
-                smem_shift_append(crow, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, lane);
-            } else {
-                {
-                    const int W = ti[TI_FRAME_STACK] * NO, keepw = W - NO;
-                    shift_copy(B.obs_history[call.parity ^ 1] + (size_t)env * W, B.obs_history[call.parity] + (size_t)env * W + NO, keepw, cleared, lane);
-                    float *dst = B.obs_history[call.parity ^ 1] + (size_t)env * W;
-                    for (int e = lane; e < NO; e += 32) dst[keepw + e] = nz[e];
-                }
-                {
-                    const int W = ti[TI_C_FRAME_STACK] * SC, keepw = W - SC;
-                    shift_copy(B.critic_obs[call.parity ^ 1] + (size_t)env * W, B.critic_obs[call.parity] + (size_t)env * W + SC, keepw, cleared, lane);
-                    float *dst = B.critic_obs[call.parity ^ 1] + (size_t)env * W;
-                    for (int e = lane; e < SC; e += 32) dst[keepw + e] = cr[e];
-                }
-            }
+            history_append(B.obs_history[call.parity ^ 1], B.obs_history[call.parity], env, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, call.preshifted, lane);
+            history_append(B.critic_obs[call.parity ^ 1], B.critic_obs[call.parity], env, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, call.preshifted, lane);
         } else if (ti[TI_OBS_KIND] >= 1) {   // go2_ts (1) / go2_cat (2): critic frame, privileged obs, history stacks
             const bool cat = ti[TI_OBS_KIND] == 2;      // go2_cat.py:19-99: 3 more DR entries, no base_lin_vel, raw feet heights
             const int SC = ti[TI_SINGLE_CRITIC], NP = ti[TI_NUM_PRIV], NCS = ti[TI_CONTACT_STATES] ? ti[TI_N_CS] : 0;
@@ -844,23 +801,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             for (int e = lane; e < NP; e += 32) B.privileged_obs_buf[env * NP + e] = fminf(fmaxf(pv[e], -clipo), clipo);
             // history stacks: shift one frame out, append the new one (legged_robot_ts.py:29-47); cleared on reset (:120-125)
             const bool cleared = (pm & PHASE_RESET) && reset;
-            if (hrow != nullptr) {
-                smem_shift_append(hrow, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, lane);
-                smem_shift_append(crow, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, lane);
-            } else {
-                {
-                    const int W = ti[TI_FRAME_STACK] * NO, keepw = W - NO;
-                    shift_copy(B.obs_history[call.parity ^ 1] + (size_t)env * W, B.obs_history[call.parity] + (size_t)env * W + NO, keepw, cleared, lane);
-                    float *dst = B.obs_history[call.parity ^ 1] + (size_t)env * W;
-                    for (int e = lane; e < NO; e += 32) dst[keepw + e] = nz[e];
-                }
-                {
-                    const int W = ti[TI_C_FRAME_STACK] * SC, keepw = W - SC;
-                    shift_copy(B.critic_obs[call.parity ^ 1] + (size_t)env * W, B.critic_obs[call.parity] + (size_t)env * W + SC, keepw, cleared, lane);
-                    float *dst = B.critic_obs[call.parity ^ 1] + (size_t)env * W;
-                    for (int e = lane; e < SC; e += 32) dst[keepw + e] = cr[e];
-                }
-            }
+            history_append(B.obs_history[call.parity ^ 1], B.obs_history[call.parity], env, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, call.preshifted, lane);
+            history_append(B.critic_obs[call.parity ^ 1], B.critic_obs[call.parity], env, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, call.preshifted, lane);
         }
     }
     // Tasks that shift the history again at the end of post_physics_step (go2_cat.py:127-130): the dynamics
@@ -899,18 +841,16 @@ struct EnvStageTab {
     uint32_t off[ENV_MAX_STAGED];
     int n;                 // entries
     uint32_t in_bytes;     // bytes the staged entries of one CTA bring in
-    int ok;                // the task's CTAs can be staged at all (history slabs satisfy the bulk-copy size rule)
+    int ok;                // staging enabled
 };
 
 inline EnvStageTab env_stage_table(const TaskDev &T, const B200Buffers &B, int nwarps) {
     EnvStageTab tab;
     const int A = T.i[TI_A], F = T.i[TI_F], L = T.i[TI_L], NSUM = T.i[TI_N_SUMS];
-    const uint32_t hbytes = (uint32_t)(nwarps * T.i[TI_FRAME_STACK] * T.i[TI_NUM_OBS] * 4), cbytes = (uint32_t)(nwarps * T.i[TI_C_FRAME_STACK] * T.i[TI_SINGLE_CRITIC] * 4);
-    tab.n = 0; tab.in_bytes = 0;
-    tab.ok = T.i[TI_OBS_KIND] >= 1 && B200_TMA_SIZE_OK(hbytes) && B200_TMA_SIZE_OK(cbytes);
+    tab.n = 0; tab.in_bytes = 0; tab.ok = 1;
     uint32_t off = 0;
 #define X_TAB(field, type, k) { const uint32_t row_ = (uint32_t)((k) * sizeof(type)), b_ = (uint32_t)nwarps * row_;                \
-        const bool st_ = B.field != nullptr && B200_TMA_SIZE_OK(b_) && off + b_ <= (uint32_t)(nwarps * ENV_IN_WORDS * 4);           \
+        const bool st_ = B.field != nullptr && b_ > 0 && B200_TMA_SIZE_OK(b_) && off + b_ <= (uint32_t)(nwarps * ENV_IN_WORDS * 4); \
         tab.src[tab.n] = (const char *)B.field; tab.row_bytes[tab.n] = row_; tab.off[tab.n] = st_ ? off : ENV_NOT_STAGED;           \
         if (st_) { tab.in_bytes += b_; off += (b_ + 15u) & ~15u; }                                                                  \
         tab.n++; }
@@ -928,39 +868,28 @@ env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, 
     const int env0 = blockIdx.x * nwarps, env = env0 + warp;
     const int N = T.i[TI_NUM_ENVS];
     uint64_t *bar = (uint64_t *)smem;
-    const int HW = T.i[TI_FRAME_STACK] * T.i[TI_NUM_OBS], CW = T.i[TI_C_FRAME_STACK] * T.i[TI_SINGLE_CRITIC];
-    float *hslab = smem + 4, *cslab = hslab + nwarps * env_row_words(HW), *es = cslab + nwarps * env_row_words(CW);
+    float *es = smem + 4;
     char *inslab = (char *)(es + nwarps * ES_TOTAL);
-    const uint32_t hbytes = (uint32_t)(nwarps * HW * 4), cbytes = (uint32_t)(nwarps * CW * 4);
     const bool full = !call.force_reset && (call.phase_mask & PHASE_ALL) == PHASE_ALL;
     const bool staged = full && tab.ok && env0 + nwarps <= N;
     if (staged) {
-        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_expect_tx(bar, tab.in_bytes + hbytes + cbytes); }
+        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_expect_tx(bar, tab.in_bytes); }
         __syncthreads();                                   // barrier armed before any copy can complete on it
-        // thread t issues the bulk copy of table entry t; the last two threads bring in the history slabs
+        // thread t issues the bulk copy of table entry t
         for (int t = (int)threadIdx.x; t < tab.n; t += (int)blockDim.x)
             if (tab.off[t] != ENV_NOT_STAGED)
                 tma_load_1d(inslab + tab.off[t], tab.src[t] + (size_t)env0 * tab.row_bytes[t], (uint32_t)nwarps * tab.row_bytes[t], bar);
-        if (threadIdx.x == blockDim.x - 1) tma_load_1d(hslab, B.obs_history[call.parity] + (size_t)env0 * HW, hbytes, bar);
-        if (threadIdx.x == blockDim.x - 2) tma_load_1d(cslab, B.critic_obs[call.parity] + (size_t)env0 * CW, cbytes, bar);
         // every thread builds the same read view R: staged tensors point into the slab, biased so that R.x[env * k + i] works
         B200Buffers R = B;
         int t = 0;
 #define X_VIEW(field, type, k) { if (tab.off[t] != ENV_NOT_STAGED) R.field = (type *)(inslab + tab.off[t]) - (size_t)env0 * (k); t++; }
         ENV_STAGED_INPUTS(X_VIEW, T.i[TI_A], T.i[TI_F], T.i[TI_L], T.i[TI_N_SUMS])
 #undef X_VIEW
-        env_post_step_warp(T, B, R, tr, call, es + warp * ES_TOTAL, env, lane, hslab + warp * HW, cslab + warp * CW, bar);
-        fence_proxy_async();                               // generic-proxy smem writes -> visible to the bulk store
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tma_store_1d(B.obs_history[call.parity ^ 1] + (size_t)env0 * HW, hslab, hbytes);
-            tma_store_1d(B.critic_obs[call.parity ^ 1] + (size_t)env0 * CW, cslab, cbytes);
-            tma_store_commit_wait();
-        }
+        env_post_step_warp(T, B, R, tr, call, es + warp * ES_TOTAL, env, lane, true, bar);
         return;
     }
     if (env >= N) return;
-    env_post_step_warp(T, B, B, tr, call, es + warp * ES_TOTAL, env, lane, nullptr, nullptr, bar);
+    env_post_step_warp(T, B, B, tr, call, es + warp * ES_TOTAL, env, lane, false, bar);
 }
 
 // extras["episode"] (legged_robot.py:127-141): means over the envs that reset this step, from the reductions the env

@@ -33,6 +33,7 @@ class FusedLeggedEnv:
         self.simulator = B200Simulator(spec, None, device, True, num_envs=num_envs, terrain=terrain, env_offset=env_offset,
                                        num_envs_global=num_envs_global, debug_cells=debug_cells)
         sim = self.simulator
+        sim.fused_histories = True
         self._b = sim._buf
         self.widths = spec.obs_widths(sim._model)
         self.stacked = spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw")   # obs / privileged obs are the frame stacks themselves

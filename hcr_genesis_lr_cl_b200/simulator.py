@@ -64,6 +64,7 @@ class B200Simulator:
         self._tdev = torch.device(sim_device)
         self._handle = ctypes.c_void_p()
         self._parity = 0
+        self.fused_histories = False   # set by FusedLeggedEnv: b200_history_shift follows every dynamics step
         self._parse_cfg()
         self._create_sim()
         self._create_envs()
@@ -243,6 +244,8 @@ class B200Simulator:
         a = actions if (actions.dtype == torch.float32 and actions.is_contiguous() and actions.device == self._tdev) \
             else actions.to(self._tdev, torch.float32).contiguous()
         self._ck(self._lib.b200_dynamics_step(self._handle, a.data_ptr(), self._stream()))
+        if self.fused_histories:      # fused mode: the frame stacks are shifted on a side stream in the shadow of the dynamics kernel
+            self._ck(self._lib.b200_history_shift(self._handle, self._parity, self._stream()))
 
     def post_physics_step(self):
         """State extraction, contact states, height scan (genesis_simulator.py:35-60) -- PHASE_SIM_POST only."""

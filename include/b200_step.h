@@ -243,6 +243,14 @@ int b200_bind_buffers(B200Handle *h, const B200Buffers *bufs);
 /* clip + shift action history, save last_*, then `decimation` x (PD torque, rigid-body substep). */
 int b200_dynamics_step(B200Handle *h, const float *dev_actions, void *cuda_stream);
 
+/* Optional, fused mode only: start moving the kept frames of both frame stacks (obs_history / critic_obs, [parity] ->
+ * [parity^1]) for the b200_env_post_step that will follow with the same `parity`.  The copy depends on nothing the
+ * dynamics kernel produces; call it right after b200_dynamics_step with the same stream: it runs on an internal side
+ * stream forked at the point where b200_dynamics_step was enqueued (so it overlaps the dynamics kernel) and the next
+ * b200_env_post_step joins it.  Without this call b200_env_post_step shifts the stacks itself.  Replaces the deque /
+ * torch.cat frame stacking of legged_robot_ts.py:86-97, tron1_pf.py:57-70, go2_wtw.py:92-111. */
+int b200_history_shift(B200Handle *h, int parity, void *cuda_stream);
+
 /* Fused post_physics_step. `step_counter` is LeggedRobot.common_step_counter *after* its increment;
  * `cmd_vx_lo/span` is the (curriculum-mutable) lin_vel_x command range as (lower, fp32(upper-lower)); `parity` (0/1) selects which of the
  * ping-pong history buffers is read (parity) and written (parity^1). */

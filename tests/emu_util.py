@@ -73,7 +73,7 @@ class EmuSim:
         self.lib.emu_dynamics_step(self._p(self.tf), self._p(self.ti), self._p(self.mi), self._p(self.mf), self._p(self.hs),
                                    ctypes.c_int(rows), ctypes.c_int(cols), ctypes.byref(self.cbuf), self._p(a))
 
-    def env_post_step(self, phase_mask=63, force_reset=0, sit_pose=None):
+    def env_post_step(self, phase_mask=63, force_reset=0, sit_pose=None, preshift=True):
         rows, cols = (self.hs.shape if self.hs is not None else (0, 0))
         lv, ty = (self.origins.shape[:2] if self.origins is not None else (0, 0))
         self.step_counter += 1
@@ -92,7 +92,7 @@ class EmuSim:
                                    self._p(self.origins), ctypes.c_int(lv), ctypes.c_int(ty), ctypes.byref(self.cbuf),
                                    ctypes.c_longlong(self.step_counter), ctypes.c_float(lo), ctypes.c_float(np.float32(hi - lo)),
                                    ctypes.c_int(self.parity), ctypes.c_int(phase_mask), ctypes.c_int(force_reset), ctypes.c_int(int(bool(sit_pose))),
-                                   self._p(beh), ctypes.c_int(gaits[0]), ctypes.c_int(gaits[1]))
+                                   self._p(beh), ctypes.c_int(gaits[0]), ctypes.c_int(gaits[1]), ctypes.c_int(int(preshift)))
         self.parity ^= 1
 
     @property

@@ -48,12 +48,22 @@ def test_library_is_the_cuda_path(built_library):
 @pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32", "go2_wtw_n32"])
 def test_env_kernel_matches_reference_golden(name):
     """Injected post-physics states from the reference run -> every output of the fused kernel."""
+    _golden_run(name, fused_histories=True)
+
+
+def test_env_kernel_shifts_histories_itself_without_preshift():
+    """Plugin-mode / fallback path: no b200_history_shift call, the env kernel moves the frame stacks."""
+    _golden_run("go2_ts_n32", fused_histories=False)
+
+
+def _golden_run(name, fused_histories):
     g, s0 = load_golden(name)
     spec = spec_for(g)
     terrain = load_terrain(spec) if spec.heightfield else None
     N, T_ = g["actions"].shape[1], g["actions"].shape[0]
     env = _env(spec, N, terrain)
     sim = env.simulator
+    sim.fused_histories = fused_histories
     sim.load_state(s0)
     env.common_step_counter = int(s0["common_step_counter"])
     env.command_ranges["lin_vel_x"] = [float(x) for x in s0["cmd_range_x"]]
@@ -307,7 +317,7 @@ def test_full_size_properties():
         assert torch.equal(sa[k][half:], sc[k]), f"shard != full job for {k}"
     assert torch.isfinite(sa["obs_buf"]).all() and torch.isfinite(sa["rew_buf"]).all()
     assert sa["height_cells"].min() >= 0 and sa["height_cells"].max() <= 1198
-    assert env_a.simulator.launch_count == 1 + 3 * (len(acts) + 1)     # reset_all + (dynamics, env, stats finalize) per step
+    assert env_a.simulator.launch_count == 1 + 4 * (len(acts) + 1)     # reset_all + (dynamics, history shift, env, stats finalize) per step
 
 
 def test_short_rollout_against_oracle(golden):

@@ -16,6 +16,15 @@ INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contact
 
 @pytest.mark.parametrize("name,steps", [("go2_ts_n32", 5), ("go2_n32", 4), ("go2_cat_n32", 5), ("tron1_pf_n32", 5), ("tron1_pf_ee_n32", 5), ("go2_wtw_n32", 5)])
 def test_emulated_env_kernel_matches_reference_golden(name, steps):
+    _run_golden(name, steps, preshift=True)
+
+
+def test_emulated_env_kernel_in_kernel_history_shift():
+    """Without b200_history_shift the env kernel moves the frame stacks itself (plugin-mode / fallback path)."""
+    _run_golden("go2_ts_n32", 4, preshift=False)
+
+
+def _run_golden(name, steps, preshift):
     g, s0 = load_golden(name)
     spec = spec_for(g)
     hs, origins = (load_terrain(spec) if spec.heightfield else (None, None))
@@ -32,7 +41,7 @@ def test_emulated_env_kernel_matches_reference_golden(name, steps):
             B[b][...] = phys_at(g, t)[k].reshape(B[b].shape)
         B["global_flags"][0] = int((np.abs(phys_at(g, t)["qd"]) > 4).any())      # what the dynamics kernel leaves (CaT R4)
         B["stats"][:] = 0
-        sim.env_post_step()
+        sim.env_post_step(preshift=preshift)
         ref = out_at(g, t)
         mine = dict(B, actions_buf=B["actions"], end_q=B["dof_pos"], end_qd=B["dof_vel"])
         if spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw"):     # the returned obs / privileged obs are the frame stacks

@@ -36,9 +36,11 @@ int emu_dynamics_step(const float *tf, const int *ti, const int *mi, const float
 
 #ifdef EMU_WITH_ENV
 struct EnvArgs { TaskDev T; B200Buffers B; TerrainDev tr; EnvCall call; EnvStageTab tab; };
+struct ShiftArgs { const float *in_h; float *out_h; int Wh, fh; const float *in_c; float *out_c; int Wc, fc, N; };
+static void shift_body(void *p) { ShiftArgs *a = (ShiftArgs *)p; history_shift_kernel(a->in_h, a->out_h, a->Wh, a->fh, a->in_c, a->out_c, a->Wc, a->fc, a->N); }
 static void env_body(void *p) { EnvArgs *a = (EnvArgs *)p; env_post_step_kernel(a->T, a->B, a->tr, a->call, a->tab); }
 int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int rows, int cols, const float *origins, int levels, int types,
-                      const B200Buffers *bufs, long long step, float vx_lo, float vx_span, int parity, int phase_mask, int force_reset, int sit_pose, const float *beh8, int gait_cb, int gait_reset) {
+                      const B200Buffers *bufs, long long step, float vx_lo, float vx_span, int parity, int phase_mask, int force_reset, int sit_pose, const float *beh8, int gait_cb, int gait_reset, int preshift) {
     static EnvArgs a;
     memcpy(a.T.f, tf, sizeof a.T.f); memcpy(a.T.i, ti, sizeof a.T.i);
     a.B = *bufs;
@@ -48,6 +50,16 @@ int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int row
     for (int k = 0; k < 8; k++) a.call.beh[k] = beh8 ? beh8[k] : 0.f;
     a.call.gait_cb = gait_cb; a.call.gait_reset = gait_reset;
     a.tab = env_stage_table(a.T, a.B, 1);          // the emulator runs one warp per block
+    a.call.preshifted = 0;
+    if (preshift && a.T.i[TI_OBS_KIND] >= 1 && !force_reset && (phase_mask & PHASE_OBSERVE)) {   // what b200_history_shift launches
+        static ShiftArgs sh;
+        const int p = parity & 1;
+        sh.in_h = a.B.obs_history[p]; sh.out_h = a.B.obs_history[p ^ 1]; sh.Wh = a.T.i[TI_FRAME_STACK] * a.T.i[TI_NUM_OBS]; sh.fh = a.T.i[TI_NUM_OBS];
+        sh.in_c = a.B.critic_obs[p]; sh.out_c = a.B.critic_obs[p ^ 1]; sh.Wc = a.T.i[TI_C_FRAME_STACK] * a.T.i[TI_SINGLE_CRITIC]; sh.fc = a.T.i[TI_SINGLE_CRITIC];
+        sh.N = a.T.i[TI_NUM_ENVS];
+        emu_launch(shift_body, &sh, sh.N);
+        a.call.preshifted = 1;
+    }
     emu_launch(env_body, &a, a.T.i[TI_NUM_ENVS]);
     return 0;
 }
