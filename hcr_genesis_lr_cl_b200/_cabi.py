@@ -287,6 +287,8 @@ def load_library() -> ctypes.CDLL:
     lib.b200_set_step_flags.restype = ctypes.c_int
     lib.b200_history_shift.argtypes = [vp, ctypes.c_int, vp]
     lib.b200_history_shift.restype = ctypes.c_int
+    lib.b200_set_history_side_stream.argtypes = [vp, ctypes.c_int]
+    lib.b200_set_history_side_stream.restype = ctypes.c_int
     lib.b200_set_behavior.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
     lib.b200_set_behavior.restype = ctypes.c_int
     lib.b200_reset_all.argtypes = [vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, vp]
@@ -302,4 +304,4 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = ["b200_create", "b200_destroy", "b200_set_terrain", "b200_bind_buffers", "b200_dynamics_step",
-                    "b200_history_shift", "b200_env_post_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_launch_count", "b200_last_error"]
+                    "b200_history_shift", "b200_set_history_side_stream", "b200_env_post_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_launch_count", "b200_last_error"]

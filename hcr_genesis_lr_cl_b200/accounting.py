@@ -3,7 +3,7 @@
 Accounting rules: every distinct per-env tensor a kernel must read counts once for the read and
 every tensor it must produce counts once for the write, per policy step; terrain gathers count the int16 bytes
 touched; random numbers, constants and the task/model descriptors count zero.  `tools/algorithmic_bytes.py` prints
-the table; bench.py computes `roofline.achieved` from `env_kernel_bytes`.
+the table; bench.py computes `roofline.achieved` from `env_path_bytes` (env kernel + history shift kernel).
 """
 from __future__ import annotations
 
@@ -39,19 +39,39 @@ def env_kernel_items(spec: T.TaskSpec, model: RobotModel):
             writes["height_around_feet, normals"] = (9 + 3) * F * f
     if spec.terrain_curriculum:
         reads["terrain_levels, terrain_types (int64)"] = 16
-    if spec.obs_kind == "go2_ts":
+    if w["hist"]:                                   # tasks with frame stacks: the env kernel appends one frame to each
         reads["DR params (friction, mass, com, kp, kd scales)"] = (5 + 2 * A) * f
-        reads["obs_history shift-in"] = (w["hist"] - w["obs"]) * f
-        reads["critic stack shift-in"] = (w["critic"] - w["single_critic"]) * f
-        writes["privileged_obs_buf"] = w["priv"] * f
-        writes["obs_history"] = w["hist"] * f
-        writes["critic_obs_buf"] = w["critic"] * f
+        if w["priv"]:
+            writes["privileged_obs_buf"] = w["priv"] * f
+        writes["obs_history (new frame)"] = w["obs"] * f
+        writes["critic_obs_buf (new frame)"] = w["single_critic"] * f
+    if spec.gait_enabled:
+        reads["gait_state"] = 20 * f
+        writes["gait_state"] = 20 * f
     return reads, writes
+
+
+def history_shift_items(spec: T.TaskSpec, model: RobotModel):
+    """history_shift_kernel: both frame stacks lose their oldest frame (read the kept frames, write them one slot down)."""
+    w = spec.obs_widths(model)
+    keep_h, keep_c = max(w["hist"] - w["obs"], 0) * 4, max(w["critic"] - w["single_critic"], 0) * 4
+    return {"obs_history kept frames": keep_h, "critic stack kept frames": keep_c}, \
+           {"obs_history kept frames": keep_h, "critic stack kept frames": keep_c}
 
 
 def env_kernel_bytes(spec: T.TaskSpec, model: RobotModel) -> int:
     r, w = env_kernel_items(spec, model)
     return int(sum(r.values()) + sum(w.values()))
+
+
+def history_shift_bytes(spec: T.TaskSpec, model: RobotModel) -> int:
+    r, w = history_shift_items(spec, model)
+    return int(sum(r.values()) + sum(w.values()))
+
+
+def env_path_bytes(spec: T.TaskSpec, model: RobotModel) -> int:
+    """The reference's post_physics_step = env_post_step_kernel + history_shift_kernel."""
+    return env_kernel_bytes(spec, model) + history_shift_bytes(spec, model)
 
 
 def dynamics_kernel_bytes(spec: T.TaskSpec, model: RobotModel) -> int:
@@ -64,4 +84,4 @@ def dynamics_kernel_bytes(spec: T.TaskSpec, model: RobotModel) -> int:
 
 
 def step_bytes(spec: T.TaskSpec, model: RobotModel) -> int:
-    return env_kernel_bytes(spec, model) + dynamics_kernel_bytes(spec, model)
+    return env_path_bytes(spec, model) + dynamics_kernel_bytes(spec, model)

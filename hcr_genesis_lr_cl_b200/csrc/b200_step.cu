@@ -34,6 +34,8 @@ struct B200Handle {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool fork_recorded = false;
+    bool side_enabled = true;
+    bool preshift_on_side = false;
     int preshift_parity = -1;      // parity the stacks have been shifted for (-1: none pending)
 };
 
@@ -133,21 +135,30 @@ int b200_history_shift(B200Handle *h, int parity, void *stream) {
     if (check_ready(h, "b200_history_shift")) return 1;
     const int *ti = h->task.i;
     if (ti[TI_OBS_KIND] < 1) return 0;               // the task keeps no frame stacks
-    cudaStream_t s = (cudaStream_t)stream;
-    if (!h->side) CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-    if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    if (!h->ev_join) CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-    if (!h->fork_recorded) CK(cudaEventRecord(h->ev_fork, s));     // no dynamics step before us: fork here
+    cudaStream_t s = (cudaStream_t)stream, run = s;
+    if (h->side_enabled) {
+        if (!h->side) CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        if (!h->ev_join) CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        if (!h->fork_recorded) CK(cudaEventRecord(h->ev_fork, s));     // no dynamics step before us: fork here
+        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        run = h->side;
+    }
     h->fork_recorded = false;
-    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     const int N = ti[TI_NUM_ENVS], p = parity & 1;
     const int Wh = ti[TI_FRAME_STACK] * ti[TI_NUM_OBS], Wc = ti[TI_C_FRAME_STACK] * ti[TI_SINGLE_CRITIC];
-    history_shift_kernel<<<(N + 7) / 8, 256, 0, h->side>>>(h->bufs.obs_history[p], h->bufs.obs_history[p ^ 1], Wh, ti[TI_NUM_OBS],
+    history_shift_kernel<<<dim3((N * HIST_SHIFT_PARTS + 7) / 8, 2), 256, 0, run>>>(h->bufs.obs_history[p], h->bufs.obs_history[p ^ 1], Wh, ti[TI_NUM_OBS],
                                                            h->bufs.critic_obs[p], h->bufs.critic_obs[p ^ 1], Wc, ti[TI_SINGLE_CRITIC], N);
     h->launches++;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev_join, h->side));
-    h->preshift_parity = p;
+    if (h->side_enabled) CK(cudaEventRecord(h->ev_join, h->side));
+    h->preshift_parity = p; h->preshift_on_side = h->side_enabled;
+    return 0;
+}
+
+int b200_set_history_side_stream(B200Handle *h, int enabled) {
+    if (!h) return fail("b200_set_history_side_stream: null handle");
+    h->side_enabled = enabled != 0;
     return 0;
 }
 
@@ -161,7 +172,7 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     call.gait_cb = h->gait_cb; call.gait_reset = h->gait_reset;
     call.preshifted = 0;
     if (h->preshift_parity >= 0) {                   // join the side stream; use its work only if it was for this parity and phase set
-        CK(cudaStreamWaitEvent(s, h->ev_join, 0));
+        if (h->preshift_on_side) CK(cudaStreamWaitEvent(s, h->ev_join, 0));
         call.preshifted = (h->preshift_parity == (parity & 1) && !force && (mask & PHASE_OBSERVE)) ? 1 : 0;
         h->preshift_parity = -1;
     }

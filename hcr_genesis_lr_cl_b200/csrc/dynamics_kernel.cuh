@@ -26,7 +26,7 @@
 #include "../../include/b200_step.h"
 
 #ifndef DYN_WARPS_PER_BLOCK
-#define DYN_WARPS_PER_BLOCK 4
+#define DYN_WARPS_PER_BLOCK 7
 #endif
 // The substep body is ~7k SASS instructions of mostly straight-line code (~110 KB), larger than the 32 KB L1.5
 // instruction cache: warps that drift apart each stream it from L2 and the kernel becomes instruction-fetch bound
@@ -39,7 +39,7 @@
 #define PHASE_SYNC()
 #endif
 #ifndef DYN_MIN_BLOCKS
-#define DYN_MIN_BLOCKS 7      // resident CTAs per SM the register allocator must allow (72 regs/thread, 28 warps/SM)
+#define DYN_MIN_BLOCKS 4      // resident CTAs per SM the register allocator must allow: 4 x 7 warps = 28 envs per SM at 72 regs/thread
 #endif
 
 struct TaskDev {

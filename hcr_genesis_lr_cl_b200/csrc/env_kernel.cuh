@@ -111,12 +111,19 @@ __device__ __forceinline__ void history_append(float *dst, const float *src, int
 // The shift of both frame stacks for the coming env_post_step (b200_history_shift): out[env][0 : W - frame] =
 // in[env][frame : W].  It depends on nothing the dynamics kernel produces, so it is launched on a side stream and runs
 // in the shadow of the dynamics kernel; one warp per env row, 8 independent 128-byte requests in flight per warp.
+#define HIST_SHIFT_PARTS 2          // warps per row: enough 128-byte requests in flight per SM to cover the DRAM latency
 __global__ void history_shift_kernel(const float *in_h, float *out_h, int Wh, int fh, const float *in_c, float *out_c, int Wc, int fc, int N) {
     const int lane = threadIdx.x & 31;
-    const int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (env, part)
+    const int env = unit / HIST_SHIFT_PARTS, part = unit - env * HIST_SHIFT_PARTS;
     if (env >= N) return;
-    shift_copy(out_h + (size_t)env * Wh, in_h + (size_t)env * Wh + fh, Wh - fh, false, lane);
-    shift_copy(out_c + (size_t)env * Wc, in_c + (size_t)env * Wc + fc, Wc - fc, false, lane);
+    const bool critic = blockIdx.y != 0;                                       // grid.y: 0 = obs_history, 1 = critic stack
+    const float *in = critic ? in_c : in_h;
+    float *out = critic ? out_c : out_h;
+    const int W = critic ? Wc : Wh, f = critic ? fc : fh, keep = W - f;
+    const int chunk = (((keep + HIST_SHIFT_PARTS - 1) / HIST_SHIFT_PARTS) + 31) & ~31;   // whole 128-byte store segments per part
+    const int lo = part * chunk, n = min(chunk, keep - lo);
+    if (n > 0) shift_copy(out + (size_t)env * W + lo, in + (size_t)env * W + f + lo, n, false, lane);
 }
 
 // `staged`: the CTA's inputs were brought into shared memory by bulk copies completing on the mbarrier `bar`.

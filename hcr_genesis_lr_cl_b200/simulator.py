@@ -247,6 +247,12 @@ class B200Simulator:
         if self.fused_histories:      # fused mode: the frame stacks are shifted on a side stream in the shadow of the dynamics kernel
             self._ck(self._lib.b200_history_shift(self._handle, self._parity, self._stream()))
 
+    def history_shift(self, side_stream: bool = True):
+        """Launch the frame-stack shift for the coming fused post step (normally done by `step` in fused mode)."""
+        self._ck(self._lib.b200_set_history_side_stream(self._handle, int(side_stream)))
+        self._ck(self._lib.b200_history_shift(self._handle, self._parity, self._stream()))
+        self._ck(self._lib.b200_set_history_side_stream(self._handle, 1))
+
     def post_physics_step(self):
         """State extraction, contact states, height scan (genesis_simulator.py:35-60) -- PHASE_SIM_POST only."""
         self._ck(self._lib.b200_env_post_step(self._handle, 0, 0.0, 0.0, self._parity, H["PHASE_SIM_POST"], self._stream()))

@@ -250,6 +250,9 @@ int b200_dynamics_step(B200Handle *h, const float *dev_actions, void *cuda_strea
  * b200_env_post_step joins it.  Without this call b200_env_post_step shifts the stacks itself.  Replaces the deque /
  * torch.cat frame stacking of legged_robot_ts.py:86-97, tron1_pf.py:57-70, go2_wtw.py:92-111. */
 int b200_history_shift(B200Handle *h, int parity, void *cuda_stream);
+/* enabled = 0: b200_history_shift launches on the caller's stream instead of the side stream (profiling, timing the
+ * copy alone, or callers that must keep every launch on one stream).  Default: enabled. */
+int b200_set_history_side_stream(B200Handle *h, int enabled);
 
 /* Fused post_physics_step. `step_counter` is LeggedRobot.common_step_counter *after* its increment;
  * `cmd_vx_lo/span` is the (curriculum-mutable) lin_vel_x command range as (lower, fp32(upper-lower)); `parity` (0/1) selects which of the

@@ -42,12 +42,13 @@ static void lane_main() {
     yield_to_sched();
 }
 
-void emu_launch(EmuKernelBody body, void *args, int blocks) {
+void emu_launch(EmuKernelBody body, void *args, int blocks, int blocks_y) {
     if (!g_stacks) g_stacks = (char *)malloc(kStack * 32);
     g_body = body; g_args = args;
-    emu_grid_dim = {blocks, 1, 1};
-    for (int b = 0; b < blocks; b++) {
-        emu_block_idx = {b, 0, 0};
+    emu_grid_dim = {blocks, blocks_y, 1};
+    for (int bb = 0; bb < blocks * blocks_y; bb++) {
+        const int b = bb % blocks;
+        emu_block_idx = {b, bb / blocks, 0};
         for (int l = 0; l < 32; l++) {
             emu_thread_idx[l] = {l, 0, 0};
             g_done[l] = false; g_count[l] = 0;

@@ -64,5 +64,5 @@ using std::max;
 using std::min;
 
 typedef void (*EmuKernelBody)(void *args);
-// run `body` on a grid of `blocks` blocks of one warp each
-void emu_launch(EmuKernelBody body, void *args, int blocks);
+// run `body` on a grid of `blocks` x `blocks_y` blocks of one warp each
+void emu_launch(EmuKernelBody body, void *args, int blocks, int blocks_y = 1);

@@ -57,7 +57,7 @@ int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int row
         sh.in_h = a.B.obs_history[p]; sh.out_h = a.B.obs_history[p ^ 1]; sh.Wh = a.T.i[TI_FRAME_STACK] * a.T.i[TI_NUM_OBS]; sh.fh = a.T.i[TI_NUM_OBS];
         sh.in_c = a.B.critic_obs[p]; sh.out_c = a.B.critic_obs[p ^ 1]; sh.Wc = a.T.i[TI_C_FRAME_STACK] * a.T.i[TI_SINGLE_CRITIC]; sh.fc = a.T.i[TI_SINGLE_CRITIC];
         sh.N = a.T.i[TI_NUM_ENVS];
-        emu_launch(shift_body, &sh, sh.N);
+        emu_launch(shift_body, &sh, sh.N * HIST_SHIFT_PARTS, 2);
         a.call.preshifted = 1;
     }
     emu_launch(env_body, &a, a.T.i[TI_NUM_ENVS]);
