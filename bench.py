@@ -229,6 +229,13 @@ def run_gpu(args):
     dyn_bytes = accounting.dynamics_kernel_bytes(spec, model) * N
     # the reference's post_physics_step = env kernel + history shift kernel: their bytes over the sum of their durations
     achieved = (env_bytes + shift_bytes) / ((t_env + t_shift) * 1e-3) / 1e9
+    traffic = None                          # DRAM bytes per launch of the same kernels from the committed ncu capture
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        if tj.get("workload") == f"{args.task}/{N}":
+            traffic = tj["env_post_step_kernel"] + tj["history_shift_kernel"]
     ki_env, ki_dyn = sim.kernel_info("env"), sim.kernel_info("dynamics")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -243,7 +250,7 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "env_post_step_kernel + history_shift_kernel (the fused post_physics_step)", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": env_bytes + shift_bytes,
                      "avg_launch_ms": t_env + t_shift,
                      "note": "history_shift_kernel runs on a side stream under the dynamics kernel; its stand-alone time is "
