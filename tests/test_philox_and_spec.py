@@ -86,7 +86,8 @@ def test_algorithmic_bytes_close_to_survey():
     model = spec.load_model()
     whole = accounting.step_bytes(spec, model)
     assert 15_000 < whole < 19_000            # ~16.7 KB per env per policy step
-    assert accounting.env_kernel_bytes(spec, model) > 10 * accounting.dynamics_kernel_bytes(spec, model)
+    assert accounting.env_path_bytes(spec, model) > 10 * accounting.dynamics_kernel_bytes(spec, model)
+    assert accounting.env_path_bytes(spec, model) == accounting.env_kernel_bytes(spec, model) + accounting.history_shift_bytes(spec, model)
 
 
 def test_robot_model_invariants():
