@@ -45,6 +45,9 @@ WORKLOADS = {   # BASELINE.json configs; the metric is quoted on go2_ts (config 
     "go2_wtw": "Go2 Walk-These-Ways with periodic gait rewards",
     "tron1_pf": "TRON1_PF point-foot biped rough terrain with domain randomisation",
     "tron1_pf_ee": "TRON1_PF biped with explicit estimator, periodic gait, rough terrain",
+    "go2_cts": "Go2 concurrent teacher-student, rough terrain",
+    "go2_ee": "Go2 explicit estimator, rough terrain",
+    "go2_dreamwaq": "Go2 DreamWaQ (labels + next-state decoder target), rough terrain",
 }
 
 

@@ -194,6 +194,7 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     si("TI_CAT", spec.cat_enabled); si("TI_CAT_GLOBAL_STANDSTILL", spec.cat_stand_still_global)
     si("TI_DOUBLE_SHIFT", spec.double_shift_actions); si("TI_N_SUMS", len(spec.episode_sum_names()))
     si("TI_GAIT", spec.gait_enabled); si("TI_CLEARANCE_MODE", spec.foot_clearance_mode)
+    si("TI_NUM_TEACHER", spec.num_teacher)
     si("TI_BEHAVIOR", spec.behavior_enabled); si("TI_BEHAVIOR_INTERVAL", max(int(spec.behavior_resampling_time / spec.dt), 1))
     for k, v in enumerate(feet):
         si("TI_FEET_LINKS", v, k)
@@ -240,7 +241,8 @@ def buffer_shapes(spec: T.TaskSpec, model: RobotModel, N: int) -> "OrderedDict[s
         obs_buf=(N, w["obs"]), privileged_obs_buf=(N, max(w["priv"], 1)),
         obs_history0=(N, max(w["hist"], 1)), obs_history1=(N, max(w["hist"], 1)),
         critic_obs0=(N, max(w["critic"], 1)), critic_obs1=(N, max(w["critic"], 1)),
-        rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), gait_state=(N, H["B200_GAIT_STATE"]), height_cells=(N, P, 2), stats=(stats_base(nsum) + STATS_RING * (max(nsum, 1) + 2),), cstr_prob=(N,), global_flags=(4,),
+        rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), gait_state=(N, H["B200_GAIT_STATE"]), height_cells=(N, P, 2), stats=(stats_base(nsum) + STATS_RING * (max(nsum, 1) + H["B200_STATS_EXTRA"]),), cstr_prob=(N,), global_flags=(4,),
+        next_state_buf=(N, w["obs"] if spec.obs_kind == "go2_dreamwaq" else 1),
     )
     return OrderedDict((name, (shp[name], _NP[ct])) for name, ct in BUFFER_FIELDS)
 

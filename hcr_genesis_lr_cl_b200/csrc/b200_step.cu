@@ -166,7 +166,7 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     const int N = h->task.i[TI_NUM_ENVS];
     const int n_sums = h->task.i[TI_N_SUMS];
     cudaStream_t s = (cudaStream_t)stream;
-    if (mask & PHASE_RESET) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 3), s));
+    if (mask & PHASE_RESET) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 4), s));
     EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.parity = parity & 1; call.phase_mask = mask; call.force_reset = force; call.sit_pose = h->sit_pose;
     for (int k = 0; k < 8; k++) call.beh[k] = h->beh[k];
     call.gait_cb = h->gait_cb; call.gait_reset = h->gait_reset;
@@ -181,7 +181,11 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     h->launches++;
     CK(cudaGetLastError());
     if ((mask & PHASE_RESET) && !force) {
-        stats_finalize_kernel<<<1, 64, 0, s>>>(h->bufs.stats, n_sums, 1.0f / h->task.f[TF_EPISODE_LENGTH_S], 1.0f / (float)N, (int)(step % ENV_STATS_RING));
+        // go2_cts: this rank's teacher envs are the global ids [0, num_teacher) that fall inside its block
+        const int n_teach = max(0, min(N, h->task.i[TI_NUM_TEACHER] - h->task.i[TI_ENV_OFFSET]));
+        const float inv_t = h->task.i[TI_NUM_TEACHER] > 0 ? 1.0f / (float)max(n_teach, 1) : 0.f, inv_s = 1.0f / (float)max(N - n_teach, 1);
+        stats_finalize_kernel<<<1, 64, 0, s>>>(h->bufs.stats, n_sums, 1.0f / h->task.f[TF_EPISODE_LENGTH_S], 1.0f / (float)N, inv_t, inv_s,
+                                               (int)(step % ENV_STATS_RING));
         h->launches++;
         CK(cudaGetLastError());
     }

@@ -615,7 +615,10 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         ep_len = 0; fail_cnt = 0;
     }
     if ((pm & PHASE_RESET) && ti[TI_TERRAIN_CURRICULUM] && !call.force_reset && lane == 0)
-        atomicAdd(B.stats + n_sums + 1, (float)new_level);          // terrain_level mean of extras["episode"]
+        {   // terrain_level means of extras["episode"] (all envs; go2_cts: teacher envs separately, go2_cts.py:93-99)
+            atomicAdd(B.stats + n_sums + 1, (float)new_level);
+            if (env + ti[TI_ENV_OFFSET] < ti[TI_NUM_TEACHER]) atomicAdd(B.stats + n_sums + 3, (float)new_level);
+        }
     // ---- write back the small per-env state
     if (pm & (PHASE_CALLBACK | PHASE_RESET)) {
         if (lane < 4) B.commands[env * 4 + lane] = lane == 0 ? cmd0 : (lane == 1 ? cmd1 : (lane == 2 ? cmd2 : cmd3));
@@ -662,7 +665,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         }
         __syncwarp();
         const float clipo = tf[TF_CLIP_OBS];
-        for (int e = lane; e < (ti[TI_OBS_KIND] >= 4 ? 0 : NO); e += 32) {
+        for (int e = lane; e < ((ti[TI_OBS_KIND] == 4 || ti[TI_OBS_KIND] == 5) ? 0 : NO); e += 32) {
             float v = ob[e];
             if (ti[TI_ADD_NOISE]) {
                 const float u = rng.u(SITE_OBS_NOISE, e);
@@ -767,12 +770,18 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             __syncwarp();
             history_append(B.obs_history[call.parity ^ 1], B.obs_history[call.parity], env, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, call.preshifted, lane);
             history_append(B.critic_obs[call.parity ^ 1], B.critic_obs[call.parity], env, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, call.preshifted, lane);
-        } else if (ti[TI_OBS_KIND] >= 1) {   // go2_ts (1) / go2_cat (2): critic frame, privileged obs, history stacks
-            const bool cat = ti[TI_OBS_KIND] == 2;      // go2_cat.py:19-99: 3 more DR entries, no base_lin_vel, raw feet heights
+        } else if (ti[TI_OBS_KIND] >= 1) {   // go2_ts (1) / go2_cat (2) / go2_cts (6) / go2_ee (7) / go2_dreamwaq (8)
+            const int kind = ti[TI_OBS_KIND];
+            const bool cat = kind == 2;      // go2_cat.py:19-99: 3 more DR entries, no base_lin_vel, raw feet heights
+            const bool cts = kind == 6;      // go2_cts.py:36-91: go2_ts with raw feet heights in the privileged obs
+            const bool ee = kind == 7;       // go2_ee.py:10-73: critic without base_lin_vel, estimator labels, clipped stacks
+            const bool dwq = kind == 8;      // go2_dreamwaq.py:7-90: base_lin_vel leads the critic frame, labels, next state
+            const bool labels = ee || dwq;
             const int SC = ti[TI_SINGLE_CRITIC], NP = ti[TI_NUM_PRIV], NCS = ti[TI_CONTACT_STATES] ? ti[TI_N_CS] : 0;
             float *cr = es + ES_CRIT, *pv = es + ES_PRIV;
-            const int DRN = (cat ? 10 : 7) + 2 * A, LIN = cat ? 0 : 3;
-            for (int e = lane; e < NO; e += 32) cr[e] = ob[e];
+            const int DRN = (cat ? 10 : 7) + 2 * A, LIN = (cat || ee) ? 0 : 3;
+            const int c_ob = dwq ? 3 : 0, c_lin = dwq ? 0 : NO + DRN;     // critic frame = [ob, dr, lin | lin, ob, dr], lcs, heights
+            for (int e = lane; e < NO; e += 32) cr[c_ob + e] = ob[e];
             // domain_randomization_info (go2_ts.py:16-28)
             for (int e = lane; e < DRN; e += 32) {
                 float v;
@@ -783,15 +792,19 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 else if (e < 7 + A) v = __fsub_rn(R.kp_scale[env * A + e - 7], tf[TF_KPS_OFFSET]);
                 else if (e < 7 + 2 * A) v = __fsub_rn(R.kd_scale[env * A + e - 7 - A], tf[TF_KDS_OFFSET]);
                 else v = e == 7 + 2 * A ? B.joint_armature[env] : (e == 8 + 2 * A ? B.joint_friction[env] : B.joint_damping[env]);
-                cr[NO + e] = v; pv[e] = v;
+                cr[c_ob + NO + e] = v;
+                if (!labels) pv[e] = v;
             }
-            if (lane < LIN) {
+            if (lane < 3) {
                 const float v = __fmul_rn(comp3(lin_b, lane), tf[TF_OS_LIN_VEL]);
-                cr[NO + DRN + lane] = v; pv[DRN + 12 * F + lane] = v;
+                if (LIN) cr[c_lin + lane] = v;
+                if (labels) pv[lane] = dwq ? __fmul_rn(v, 0.5f) : v;                  // go2_ee.py:67 / go2_dreamwaq.py:84
+                else if (LIN) pv[DRN + 12 * F + lane] = v;
             }
             for (int e = lane; e < NCS; e += 32) {
                 const float v = es[ES_LCS + e];
-                cr[NO + DRN + LIN + e] = v; pv[DRN + 12 * F + LIN + e] = v;
+                cr[NO + DRN + LIN + e] = v;
+                if (labels) pv[3 + e] = v; else pv[DRN + 12 * F + LIN + e] = v;
             }
             if (ti[TI_MEASURE_HEIGHTS]) {
                 for (int pt = lane; pt < P; pt += 32) {
@@ -799,13 +812,27 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                     cr[NO + DRN + LIN + NCS + pt] = __fmul_rn(fminf(fmaxf(d, -1.0f), 1.0f), tf[TF_OS_HEIGHT]);
                 }
             }
-            for (int e = lane; e < 9 * F; e += 32) {
-                const float fz = R.feet_pos[(env * F + e / 9) * 3 + 2];
-                pv[DRN + e] = cat ? es[ES_HAF + e] : fminf(fmaxf(__fsub_rn(fz, es[ES_HAF + e]), -1.0f), 1.0f);
+            if (labels) {                                                            // foot clearance above the mean terrain height
+                if (fl) pv[3 + NCS + lane] = fminf(fmaxf(__fsub_rn(__fsub_rn(fpos.z, hmean), tf[TF_FOOT_HEIGHT_OFFSET]), -1.0f), 1.0f);
+            } else {
+                for (int e = lane; e < 9 * F; e += 32) {
+                    const float fz = R.feet_pos[(env * F + e / 9) * 3 + 2];
+                    pv[DRN + e] = (cat || cts) ? es[ES_HAF + e] : fminf(fmaxf(__fsub_rn(fz, es[ES_HAF + e]), -1.0f), 1.0f);
+                }
+                for (int e = lane; e < 3 * F; e += 32) pv[DRN + 9 * F + e] = es[ES_NV + e];
             }
-            for (int e = lane; e < 3 * F; e += 32) pv[DRN + 9 * F + e] = es[ES_NV + e];
+            if (dwq) {                                                               // decoder target, go2_dreamwaq.py:72-80
+                for (int e = lane; e < 9 + 2 * A; e += 32) B.next_state_buf[env * NO + e] = ob[e];
+                if (jl) B.next_state_buf[env * NO + 9 + 2 * A + lane] = __fmul_rn(actj, tf[TF_ACTION_SCALE]);
+            }
             __syncwarp();
-            for (int e = lane; e < NP; e += 32) B.privileged_obs_buf[env * NP + e] = fminf(fmaxf(pv[e], -clipo), clipo);
+            // estimator labels are handed out unclipped (legged_robot_ee.py:56-73, legged_robot_dreamwaq.py:63-79)
+            for (int e = lane; e < NP; e += 32) B.privileged_obs_buf[env * NP + e] = labels ? pv[e] : fminf(fmaxf(pv[e], -clipo), clipo);
+            if (labels) {       // these steps return the clipped stacks: clip the frame going in (ee: both stacks, dreamwaq: critic only)
+                for (int e = lane; e < SC; e += 32) cr[e] = fminf(fmaxf(cr[e], -clipo), clipo);
+                if (ee) for (int e = lane; e < NO; e += 32) nz[e] = fminf(fmaxf(nz[e], -clipo), clipo);
+                __syncwarp();
+            }
             // history stacks: shift one frame out, append the new one (legged_robot_ts.py:29-47); cleared on reset (:120-125)
             const bool cleared = (pm & PHASE_RESET) && reset;
             history_append(B.obs_history[call.parity ^ 1], B.obs_history[call.parity], env, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, call.preshifted, lane);
@@ -902,11 +929,14 @@ env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, 
 // extras["episode"] (legged_robot.py:127-141): means over the envs that reset this step, from the reductions the env
 // kernel left in stats[0..n_sums] (+ reset count, + sum of terrain levels); written to slot (step % ENV_STATS_RING) of
 // the ring that follows the work area so that the host can hand out per-step values without any further launch.
-__global__ void stats_finalize_kernel(float *stats, int n_sums, float inv_episode_length_s, float inv_num_envs, int slot) {
+__global__ void stats_finalize_kernel(float *stats, int n_sums, float inv_episode_length_s, float inv_num_envs, float inv_teacher,
+                                      float inv_student, int slot) {
     const int i = threadIdx.x;
-    float *ring = stats + (2 * n_sums + 4) + slot * (n_sums + 2);
+    float *ring = stats + (2 * n_sums + 4) + slot * (n_sums + B200_STATS_EXTRA);
     const float cnt = fmaxf(stats[n_sums], 1.0f);
     if (i < n_sums) ring[i] = stats[i] / cnt * inv_episode_length_s;
     if (i == n_sums) ring[i] = stats[n_sums + 1] * inv_num_envs;            // mean terrain level
-    if (i == n_sums + 1) ring[i] = stats[n_sums + 2] * inv_num_envs;        // mean CaT termination probability
+    if (i == n_sums + 1) ring[i] = inv_teacher > 0.f ? stats[n_sums + 3] * inv_teacher     // go2_cts: teacher terrain level
+                                                     : stats[n_sums + 2] * inv_num_envs;   // mean CaT termination probability
+    if (i == n_sums + 2) ring[i] = (stats[n_sums + 1] - stats[n_sums + 3]) * inv_student;  // go2_cts: student terrain level
 }

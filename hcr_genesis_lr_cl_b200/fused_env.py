@@ -36,11 +36,13 @@ class FusedLeggedEnv:
         sim.fused_histories = True
         self._b = sim._buf
         self.widths = spec.obs_widths(sim._model)
-        self.stacked = spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw")   # obs / privileged obs are the frame stacks themselves
+        self.stacked = spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw", "go2_ee")   # obs / privileged obs are the frame stacks themselves
+        self.estimator = spec.obs_kind in ("tron1_pf_ee", "go2_ee")             # LeggedRobotEE return tuples
+        self.teacher_student = spec.obs_kind in ("go2_ts", "go2_cat", "go2_cts")  # LeggedRobotTS / LeggedRobotCTS return tuples
         self.num_obs = self.widths["hist"] if self.stacked else self.widths["obs"]
         self.num_estimator_features, self.num_estimator_labels = self.widths["hist"], self.widths["priv"]
         self.num_privileged_obs = self.widths["critic"] if self.stacked else (
-            self.widths["priv"] if spec.obs_kind in ("go2_ts", "go2_cat") else None)
+            self.widths["priv"] if self.teacher_student else (self.widths["critic"] if spec.obs_kind == "go2_dreamwaq" else None))
         self.num_actions = spec.num_actions
         self.num_history_obs = self.widths["hist"]
         self.num_critic_obs = self.widths["critic"]
@@ -60,7 +62,8 @@ class FusedLeggedEnv:
         self.rew_buf = b["rew_buf"]
         if not self.stacked:
             self.obs_buf = b["obs_buf"]
-            self.privileged_obs_buf = b["privileged_obs_buf"] if self.num_privileged_obs is not None else None
+            if spec.obs_kind != "go2_dreamwaq":                  # dreamwaq: the critic stack (property below)
+                self.privileged_obs_buf = b["privileged_obs_buf"] if self.num_privileged_obs is not None else None
         self.reset_buf = b["reset_buf"].view(torch.bool)
         self.time_out_buf = b["time_out_buf"].view(torch.bool)
         self.commands, self.actions = b["commands"], b["actions"]
@@ -95,7 +98,7 @@ class FusedLeggedEnv:
     def __getattr__(self, name):
         if name == "obs_buf" and self.__dict__.get("stacked"):
             return self.obs_history
-        if name == "privileged_obs_buf" and self.__dict__.get("stacked"):
+        if name == "privileged_obs_buf" and (self.__dict__.get("stacked") or self.__dict__["spec"].obs_kind == "go2_dreamwaq"):
             return self.critic_obs_buf
         raise AttributeError(name)
 
@@ -139,10 +142,21 @@ class FusedLeggedEnv:
     def estimator_labels_buf(self):
         return self._b["privileged_obs_buf"]
 
+    @property
+    def explicit_labels_buf(self):
+        return self._b["privileged_obs_buf"]
+
+    @property
+    def next_state_buf(self):
+        return self._b["next_state_buf"]
+
     def _returns(self):
-        if self.spec.obs_kind == "tron1_pf_ee":          # LeggedRobotEE.step, legged_robot_ee.py:56-73
+        if self.estimator:                               # LeggedRobotEE.step, legged_robot_ee.py:56-73
             return (self.obs_history, self.estimator_labels_buf, self.critic_obs_buf, self.rew_buf, self.reset_buf, self.extras)
-        if self.spec.obs_kind in ("go2_ts", "go2_cat"):
+        if self.spec.obs_kind == "go2_dreamwaq":         # LeggedRobotDreamwaq.step, legged_robot_dreamwaq.py:63-79
+            return (self.obs_buf, self.critic_obs_buf, self.obs_history, self.explicit_labels_buf, self.next_state_buf,
+                    self.rew_buf, self.reset_buf, self.extras)
+        if self.teacher_student:
             return (self.obs_buf, self.privileged_obs_buf, self.obs_history, self.critic_obs_buf, self.rew_buf,
                     self.reset_buf, self.extras)
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
@@ -152,14 +166,18 @@ class FusedLeggedEnv:
         self._set_step_flags()
         self.simulator.fused_reset_all(self.common_step_counter, self.command_ranges["lin_vel_x"])
         out = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
-        if self.spec.obs_kind == "tron1_pf_ee":
+        if self.estimator:
             return out[:3]
-        return out[:4] if self.spec.obs_kind in ("go2_ts", "go2_cat") else out[:2]
+        if self.spec.obs_kind == "go2_dreamwaq":
+            return out[:5]
+        return out[:4] if self.teacher_student else out[:2]
 
     def get_observations(self):
-        if self.spec.obs_kind == "tron1_pf_ee":
+        if self.estimator:
             return self.obs_history, self.estimator_labels_buf, self.critic_obs_buf
-        if self.spec.obs_kind in ("go2_ts", "go2_cat"):
+        if self.spec.obs_kind == "go2_dreamwaq":
+            return self.obs_buf, self.critic_obs_buf, self.obs_history, self.explicit_labels_buf, self.next_state_buf
+        if self.teacher_student:
             return self.obs_buf, self.privileged_obs_buf, self.obs_history, self.critic_obs_buf
         return self.obs_buf
 
@@ -169,18 +187,20 @@ class FusedLeggedEnv:
     # ------------------------------------------------------------------ extras / curricula (device side, no sync)
     def _build_extras_ring(self):
         """Per-slot dicts of 0-dim views into the statistics ring the finalize kernel fills (no launch per step)."""
-        from ._cabi import STATS_RING
+        from ._cabi import STATS_RING, H
         n = len(self.sum_names)
         stats = self._b["stats"]
         base = 2 * max(n, 1) + 4
-        ring = []
+        ring, w = [], n + H["B200_STATS_EXTRA"]
         for slot in range(STATS_RING):
-            row = stats[base + slot * (n + 2): base + (slot + 1) * (n + 2)]
+            row = stats[base + slot * w: base + (slot + 1) * w]
             ep = {"rew_" + name: row[i] for i, name in enumerate(self.sum_names)}
             if self.spec.terrain_curriculum:
                 ep["terrain_level"] = row[n]
             if self.spec.cat_enabled:
                 ep["cstr_probs"] = row[n + 1]               # go2_cat.py:101-104
+            if self.spec.num_teacher > 0 and self.spec.terrain_curriculum:    # go2_cts.py:93-99
+                ep["teacher_terrain_level"], ep["student_terrain_level"] = row[n + 1], row[n + 2]
             ring.append(ep)
         return ring
 

@@ -39,7 +39,8 @@ REWARD_ID: Dict[str, int] = {n: i for i, n in enumerate(REWARD_TERMS)}
 NUM_REWARD_TERMS = len(REWARD_TERMS)
 
 #: observation layouts the fused kernel knows (per-task ``compute_observations``)
-OBS_KINDS = {"go2": 0, "go2_ts": 1, "go2_cat": 2, "tron1_pf": 3, "tron1_pf_ee": 4, "go2_wtw": 5}
+OBS_KINDS = {"go2": 0, "go2_ts": 1, "go2_cat": 2, "tron1_pf": 3, "tron1_pf_ee": 4, "go2_wtw": 5, "go2_cts": 6, "go2_ee": 7,
+             "go2_dreamwaq": 8}
 
 CAT_CONSTRAINTS = ["torque", "dof_vel", "action_rate", "base_height", "collision", "feet_stumble", "dof_pos",
                    "base_orientation", "stand_still"]      # order of ConstraintManager.add calls, go2_cat.py:197-208
@@ -195,6 +196,7 @@ class TaskSpec:
     double_shift_actions: bool = False      # go2_cat.py:127-130 shifts the action history a second time (R6)
     dof_vel_limits: List[float] = field(default_factory=list)
     # engine knobs (no reference counterpart; DESIGN.md "physics formulation")
+    num_teacher: int = 0              # go2_cts: envs [0, num_teacher) are teacher envs (extras only, go2_cts.py:93-99)
     pgs_iterations: int = 30          # sweep cap of the projected Gauss-Seidel contact solver
     pgs_tolerance: float = 1e-4       # stop when max|df| over a sweep <= tol * (1 + max|f|)
     seed: int = 1
@@ -289,7 +291,14 @@ class TaskSpec:
             sc = single + dr + len(cs) + (self.num_height_points if self.measure_heights else 0)
             priv = dr + 9 * len(feet) + 3 * len(feet) + len(cs)
             return dict(obs=single, priv=priv, single_critic=sc, hist=self.frame_stack * single, critic=self.c_frame_stack * sc)
-        if self.obs_kind == "go2_ts":
+        if self.obs_kind in ("go2_ee", "go2_dreamwaq"):    # go2_ee.py:10-73 / go2_dreamwaq.py:7-90: labels instead of priv
+            single = 9 + 3 * A
+            dr = 7 + 2 * A
+            lin = 3 if self.obs_kind == "go2_dreamwaq" else 0
+            sc = lin + single + dr + len(cs) + (self.num_height_points if self.measure_heights else 0)
+            labels = 3 + len(cs) + len(feet)
+            return dict(obs=single, priv=labels, single_critic=sc, hist=self.frame_stack * single, critic=self.c_frame_stack * sc)
+        if self.obs_kind in ("go2_ts", "go2_cts"):
             single = 9 + 3 * A
             dr = 7 + 2 * A
             sc = single + dr + 3 + len(cs) + (self.num_height_points if self.measure_heights else 0)
@@ -331,7 +340,8 @@ class TaskSpec:
     @classmethod
     def from_reference_cfg(cls, cfg, task: str) -> "TaskSpec":
         """Read a LeggedGym-Ex config object (nested classes/instances) into a TaskSpec."""
-        kinds = {"go2": "go2", "go2_ts": "go2_ts", "go2_cat": "go2_cat", "tron1_pf": "tron1_pf", "tron1_pf_ee": "tron1_pf_ee", "go2_wtw": "go2_wtw"}
+        kinds = {"go2": "go2", "go2_ts": "go2_ts", "go2_cat": "go2_cat", "tron1_pf": "tron1_pf", "tron1_pf_ee": "tron1_pf_ee", "go2_wtw": "go2_wtw",
+                 "go2_cts": "go2_cts", "go2_ee": "go2_ee", "go2_dreamwaq": "go2_dreamwaq"}
         if task not in kinds:
             raise ValueError(f"task {task!r} has no fused descriptor yet (supported: {sorted(kinds)})")
 
@@ -396,9 +406,9 @@ class TaskSpec:
             foot_clearance_target=r.foot_clearance_target, foot_height_offset=r.foot_height_offset,
             foot_clearance_tracking_sigma=r.foot_clearance_tracking_sigma,
             about_landing_threshold=getattr(r, "about_landing_threshold", 0.03),
-            feet_air_time_threshold=0.25 if task in ("go2_ts", "go2_cat", "tron1_pf", "tron1_pf_ee") else 0.3,
+            feet_air_time_threshold=0.25 if task in ("go2_ts", "go2_cat", "tron1_pf", "tron1_pf_ee", "go2_cts", "go2_ee", "go2_dreamwaq") else 0.3,
             foot_distance_threshold=getattr(r, "foot_distance_threshold", 0.115),
-            foot_clearance_uses_terrain=task in ("go2_ts", "go2_cat"),
+            foot_clearance_uses_terrain=task in ("go2_ts", "go2_cat", "go2_cts", "go2_ee", "go2_dreamwaq"),
             dof_vel_limits=list(getattr(a, "dof_vel_limits", [])),
             foot_name=a.foot_name, penalize_contacts_on=list(a.penalize_contacts_on),
             terminate_after_contacts_on=list(a.terminate_after_contacts_on),
@@ -432,6 +442,9 @@ class TaskSpec:
             spec.sit_joint_angles = [float(cfg.init_state.sit_joint_angles[n_]) for n_ in a.dof_names]
             spec.double_shift_actions = True
             spec.height_obs_offset = 0.6
+        if task == "go2_cts":
+            spec.foot_clearance_mode = 2                               # go2_cts.py:169: max of the 9 heights under the foot
+            spec.num_teacher = int(e.num_teacher)
         if task == "go2_cat":
             cc = cfg.constraints
             spec.cat_enabled = cc.enable == "cat"
@@ -512,6 +525,43 @@ def go2_cat_spec(**over) -> TaskSpec:
                            hip_pos=-0.2, dof_close_to_default=-0.05, foot_clearance=0.2)
     s.cat_enabled, s.double_shift_actions = True, True
     s.dof_vel_limits = [30.1, 30.1, 15.7] * 4
+    for k, v in over.items():
+        setattr(s, k, v)
+    return s
+
+
+def go2_cts_spec(**over) -> TaskSpec:
+    """`go2_cts` concurrent teacher-student (go2_cts_config.py:5-66): go2_ts with raw terrain heights in the privileged
+    obs, max-height foot clearance and teacher / student terrain-level logging."""
+    s = go2_ts_spec()
+    s.task, s.obs_kind = "go2_cts", "go2_cts"
+    s.env_spacing = 1.0
+    s.joint_friction_range = [0.0, 0.1]
+    s.foot_clearance_mode = 2
+    s.num_teacher = 4096 // 4 * 3
+    for k, v in over.items():
+        setattr(s, k, v)
+    return s
+
+
+def go2_ee_spec(**over) -> TaskSpec:
+    """`go2_ee` explicit-estimator task (go2_ee_config.py:5-68): estimator features / labels / critic stack."""
+    s = go2_ts_spec()
+    s.task, s.obs_kind = "go2_ee", "go2_ee"
+    s.env_spacing = 2.0
+    s.num_obs = 48                          # inherited LeggedRobotEECfg value; the produced frame is 45 wide (obs_widths)
+    s.num_privileged_obs = 5 * (45 + 31 + 81 + 17)
+    for k, v in over.items():
+        setattr(s, k, v)
+    return s
+
+
+def go2_dreamwaq_spec(**over) -> TaskSpec:
+    """`go2_dreamwaq` (go2_dreamwaq_config.py:5-70): obs, critic stack, history, explicit labels, next state."""
+    s = go2_ts_spec()
+    s.task, s.obs_kind = "go2_dreamwaq", "go2_dreamwaq"
+    s.env_spacing = 1.0
+    s.num_privileged_obs = 5 * (45 + 31 + 81 + 17 + 3)
     for k, v in over.items():
         setattr(s, k, v)
     return s
@@ -610,4 +660,5 @@ def go2_wtw_spec(**over) -> TaskSpec:
 
 
 PRESETS = {"go2": go2_spec, "go2_ts": go2_ts_spec, "go2_cat": go2_cat_spec, "tron1_pf": tron1_pf_spec,
-           "tron1_pf_ee": tron1_pf_ee_spec, "go2_wtw": go2_wtw_spec}
+           "tron1_pf_ee": tron1_pf_ee_spec, "go2_wtw": go2_wtw_spec, "go2_cts": go2_cts_spec, "go2_ee": go2_ee_spec,
+           "go2_dreamwaq": go2_dreamwaq_spec}

@@ -44,6 +44,7 @@ extern "C" {
 #define B200_RMAX 32       /* constraint rows = 3*KMAX + AUXMAX = one warp */
 #define B200_MAX_REWARDS 33
 #define B200_MAX_GAITS 4
+#define B200_STATS_EXTRA 3    /* per-step statistics beyond the episode sums: terrain level, cstr prob | teacher level, student level */
 #define B200_GAIT_STATE 20   /* floats per env in gait_state */
 /* columns of one gait_state row: theta[4] (FL,FR,RL,RR or L,R), gait time, phase, gait period, base-height /
  * foot-clearance / pitch targets (go2_wtw behaviour parameters), clock[8] = sin[feet], cos[feet] */
@@ -114,6 +115,7 @@ enum B200TaskI {
     TI_GAIT,                                                     /* 1: biped periodic-gait state (theta, gait time, phi, clock) */
     TI_BEHAVIOR,                                                 /* 1: per-env behaviour params (gait period, targets) resampled (go2_wtw) */
     TI_BEHAVIOR_INTERVAL,                                        /* int(behavior resampling_time / dt) */
+    TI_NUM_TEACHER,                                              /* go2_cts: global envs [0, num_teacher) are teacher envs (go2_cts.py:93-99) */
     TI_CLEARANCE_MODE,                                           /* foot clearance / labels relative to: 0 nothing, 1 mean, 2 max of the 9 heights */
     TI_N_SUMS,                                                   /* columns of episode_sums: rewards (+termination) (+9 cstr_*) */                                               /* global id of local env 0 (multi-GPU sharding; keys the RNG) */
     TI_REWARD_IDS,                                               /* [B200_MAX_REWARDS] active term ids, evaluation order */
@@ -229,6 +231,7 @@ typedef struct B200Buffers {
     int32_t *global_flags;      /* [4] int32: [0] any env with |dof_vel| > 4 after the physics step (CaT stand-still, R4) */
     float *contact_warm;        /* [N,48] contact-solver warm start carried between substeps and policy steps: 8 x (sphere id + 1,
                                    f_n, f_t1, f_t2) then 8 x (aux-row code + 1, f); zero = empty */
+    float *next_state_buf;      /* [N,num_obs] go2_dreamwaq decoder target (go2_dreamwaq.py:72-80); [N,1] otherwise */
 } B200Buffers;
 
 typedef struct B200Handle B200Handle;

@@ -681,12 +681,18 @@ class EnvOracle:
         dr = [st["friction"] - f32((s.friction_range[0] + s.friction_range[1]) / 2), st["added_mass"], st["com_bias"],
               st["rand_push_vels"][:, :2], st["kp_scale"] - f32((s.kp_range[0] + s.kp_range[1]) / 2),
               st["kd_scale"] - f32((s.kd_range[0] + s.kd_range[1]) / 2)]
-        cat = s.obs_kind == "go2_cat"
+        kind = s.obs_kind
+        cat = kind == "go2_cat"
         if cat:                                                    # go2_cat.py:40-42
             dr += [st["joint_armature"], st["joint_friction"], st["joint_damping"]]
         dr = np.concatenate(dr, axis=1).astype(f32)
         lin = (st["base_lin_vel"] * f32(s.obs_scale_lin_vel)).astype(f32)
-        parts = [clean, dr] if cat else [clean, dr, lin]
+        if kind == "go2_dreamwaq":                                 # go2_dreamwaq.py:31-35: base_lin_vel leads the critic frame
+            parts = [lin, clean, dr]
+        elif cat or kind == "go2_ee":                              # go2_cat.py:45-48 / go2_ee.py:34-37: no base_lin_vel
+            parts = [clean, dr]
+        else:                                                      # go2_ts.py:30-34 / go2_cts.py:36-40
+            parts = [clean, dr, lin]
         if s.obtain_link_contact_states:
             parts.append(o["link_contact_states"])
         if s.measure_heights:
@@ -698,8 +704,29 @@ class EnvOracle:
         st["critic_hist"][:] = np.concatenate([st["critic_hist"][:, sc:], critic], axis=1)
         st["obs_hist"][:] = np.concatenate([st["obs_hist"][:, so:], obs], axis=1)
         fz = o["feet_pos"][:, :, 2:3]
+        if kind in ("go2_ee", "go2_dreamwaq"):                     # go2_ee.py:66-73 / go2_dreamwaq.py:83-90: estimator labels
+            clr = np.clip(o["feet_pos"][:, :, 2] - np.mean(o["height_around_feet"], axis=-1, dtype=f32) - f32(s.foot_height_offset),
+                          f32(-1), f32(1)).astype(f32)
+            lab_lin = lin if kind == "go2_ee" else (lin * f32(0.5)).astype(f32)
+            labels = np.concatenate([lab_lin, o["link_contact_states"], clr], axis=1).astype(f32)
+            if kind == "go2_ee":                                   # LeggedRobotEE.step, legged_robot_ee.py:56-73
+                o["estimator_labels_buf"] = labels
+                o["estimator_features_buf"] = np.clip(st["obs_hist"], -c, c)
+                o["privileged_obs_buf"] = np.clip(st["critic_hist"], -c, c)
+                o["obs_history"], o["critic_obs_buf"] = o["estimator_features_buf"], o["privileged_obs_buf"]
+                o["obs_buf"] = o["estimator_features_buf"]
+            else:                                                  # LeggedRobotDreamwaq.step, legged_robot_dreamwaq.py:63-79
+                A = s.num_actions
+                o["explicit_labels_buf"] = labels
+                o["next_state_buf"] = np.concatenate([clean[:, :9 + 2 * A], (st["actions"] * f32(s.action_scale)).astype(f32)], axis=1)
+                o["obs_buf"] = np.clip(obs, -c, c)
+                o["privileged_obs_buf"] = np.clip(st["critic_hist"], -c, c)
+                o["obs_history"], o["critic_obs_buf"] = st["obs_hist"].copy(), o["privileged_obs_buf"]
+            return
         if cat:                                                    # go2_cat.py:82-99: raw heights, no base_lin_vel
             priv = [dr, o["height_around_feet"].reshape(self.N, -1), o["normal_vector_around_feet"]]
+        elif kind == "go2_cts":                                    # go2_cts.py:74-81: raw heights
+            priv = [dr, o["height_around_feet"].reshape(self.N, -1), o["normal_vector_around_feet"], lin]
         else:
             priv = [dr, np.clip((fz - o["height_around_feet"]).reshape(self.N, -1), f32(-1), f32(1)),
                     o["normal_vector_around_feet"], lin]

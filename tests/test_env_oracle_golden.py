@@ -9,7 +9,8 @@ from oracle.env_oracle import EnvOracle
 INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels")
 
 
-@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32", "go2_wtw_n32"])
+@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32", "go2_wtw_n32", "go2_cts_n32", "go2_ee_n32",
+                                  "go2_dreamwaq_n32"])
 def test_env_oracle_reproduces_reference(name):
     g, s0 = load_golden(name)
     spec = spec_for(g)

@@ -45,7 +45,8 @@ def test_library_is_the_cuda_path(built_library):
     assert all(hasattr(lib, s) for s in _cabi.EXPORTED_SYMBOLS)
 
 
-@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32", "go2_wtw_n32"])
+@pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32", "go2_wtw_n32", "go2_cts_n32", "go2_ee_n32",
+                                  "go2_dreamwaq_n32"])
 def test_env_kernel_matches_reference_golden(name):
     """Injected post-physics states from the reference run -> every output of the fused kernel."""
     _golden_run(name, fused_histories=True)
@@ -80,9 +81,11 @@ def _golden_run(name, fused_histories):
         st = sim.get_state()
         ref = out_at(g, t)
         mine = dict(st, actions_buf=st["actions"], end_q=st["dof_pos"], end_qd=st["dof_vel"])
-        if spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw"):     # the returned obs / privileged obs are the frame stacks
+        if spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw", "go2_ee"):     # the returned obs / privileged obs are the frame stacks
             mine["estimator_labels_buf"] = st["privileged_obs_buf"]
             mine["obs_buf"], mine["privileged_obs_buf"] = st[f"obs_history{sim._parity}"], st[f"critic_obs{sim._parity}"]
+        if spec.obs_kind == "go2_dreamwaq":                              # labels travel in privileged_obs_buf, the critic stack is returned
+            mine["explicit_labels_buf"], mine["privileged_obs_buf"] = st["privileged_obs_buf"], st[f"critic_obs{sim._parity}"]
         skip0 = spec.obs_kind in ("tron1_pf_ee", "go2_wtw")  # R18: env 0 is coupled to all envs in the reference; not reproduced
         for k, r in ref.items():
             if k not in mine or k in ("end_state",):
@@ -178,7 +181,7 @@ def test_dynamics_kernel_matches_oracle(task):
             assert err.max() < tol * scale(r), f"{k}: abs err {err.max():.3e} (scale {scale(r):.2f})"
 
 
-@pytest.mark.parametrize("task", ["go2_ts", "go2_cat", "tron1_pf_ee", "go2_wtw"])
+@pytest.mark.parametrize("task", ["go2_ts", "go2_cat", "tron1_pf_ee", "go2_wtw", "go2_cts", "go2_ee", "go2_dreamwaq"])
 def test_env_kernel_matches_numpy_oracle_seeded(task):
     """Seeded random states at N=512 through several fused steps vs the numpy restatement (all phases, with resets)."""
     from hcr_genesis_lr_cl_b200 import task_spec as T
@@ -256,6 +259,12 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
         if spec.obs_kind == "tron1_pf_ee":
             _close(out["privileged_obs_buf"], o["estimator_labels_buf"], what=f"step {t}: labels")
             _close(out["gait_state"], eo.st["gait_state"], what=f"step {t}: gait_state")
+        elif spec.obs_kind == "go2_ee":
+            _close(out["privileged_obs_buf"], o["estimator_labels_buf"], what=f"step {t}: labels")
+        elif spec.obs_kind == "go2_dreamwaq":
+            _close(out["obs_buf"], o["obs_buf"], what=f"step {t}: obs")
+            _close(out["privileged_obs_buf"], o["explicit_labels_buf"], what=f"step {t}: labels")
+            _close(out["next_state_buf"], o["next_state_buf"], what=f"step {t}: next_state")
         elif spec.obs_kind == "go2_wtw":
             _close(out["gait_state"], eo.st["gait_state"], what=f"step {t}: gait_state")
         else:
@@ -271,8 +280,8 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
             _close(out[k], eo.st[k], what=f"step {t}: {k}")
         if o["episode_means"] is not None:                                   # extras["episode"] of this step (device ring)
             n = len(eo.sum_names)
-            base = 2 * n + 4 + (env.common_step_counter % 32) * (n + 2)
-            ring = out["stats"][base:base + n + 2]
+            base = 2 * n + 4 + (env.common_step_counter % 32) * (n + 3)
+            ring = out["stats"][base:base + n + 3]
             for i, name in enumerate(eo.sum_names):
                 assert abs(ring[i] - o["episode_means"]["rew_" + name]) <= 1e-4 * abs(o["episode_means"]["rew_" + name]) + 1e-6, name
             if spec.terrain_curriculum:

@@ -14,7 +14,8 @@ PH = dict(base_pos="base_pos", base_quat_wxyz="base_quat_wxyz", base_lin_w="base
 INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels")
 
 
-@pytest.mark.parametrize("name,steps", [("go2_ts_n32", 5), ("go2_n32", 4), ("go2_cat_n32", 5), ("tron1_pf_n32", 5), ("tron1_pf_ee_n32", 5), ("go2_wtw_n32", 5)])
+@pytest.mark.parametrize("name,steps", [("go2_ts_n32", 5), ("go2_n32", 4), ("go2_cat_n32", 5), ("tron1_pf_n32", 5), ("tron1_pf_ee_n32", 5), ("go2_wtw_n32", 5),
+                                        ("go2_cts_n32", 5), ("go2_ee_n32", 5), ("go2_dreamwaq_n32", 5)])
 def test_emulated_env_kernel_matches_reference_golden(name, steps):
     _run_golden(name, steps, preshift=True)
 
@@ -44,9 +45,11 @@ def _run_golden(name, steps, preshift):
         sim.env_post_step(preshift=preshift)
         ref = out_at(g, t)
         mine = dict(B, actions_buf=B["actions"], end_q=B["dof_pos"], end_qd=B["dof_vel"])
-        if spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw"):     # the returned obs / privileged obs are the frame stacks
+        if spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw", "go2_ee"):     # the returned obs / privileged obs are the frame stacks
             mine["estimator_labels_buf"] = B["privileged_obs_buf"]
             mine["obs_buf"], mine["privileged_obs_buf"] = sim.obs_history, sim.critic_obs
+        if spec.obs_kind == "go2_dreamwaq":                              # labels travel in privileged_obs_buf, the critic stack is returned
+            mine["explicit_labels_buf"], mine["privileged_obs_buf"] = B["privileged_obs_buf"], sim.critic_obs
         skip0 = spec.obs_kind in ("tron1_pf_ee", "go2_wtw")  # R18: the reference couples env 0 to all envs; not reproduced
         for k, r in ref.items():
             if k not in mine or k == "end_state":

@@ -310,15 +310,20 @@ def main():
         if args.task == "go2_wtw":
             o["privileged_obs_buf"] = n(ret[1])
             o["gait_state"] = pack_gait(env)
-        elif args.task == "tron1_pf_ee":
+        elif args.task == "go2_dreamwaq":                 # obs, critic stack, history, explicit labels, next state
+            o["privileged_obs_buf"] = n(ret[1])
+            o["explicit_labels_buf"] = n(ret[3])
+            o["next_state_buf"] = n(ret[4])
+        elif args.task in ("tron1_pf_ee", "go2_ee"):
             o["estimator_labels_buf"] = n(ret[1])
             o["privileged_obs_buf"] = n(ret[2])
-            o["gait_state"] = pack_gait(env)
+            if hasattr(env, "gait_time"):
+                o["gait_state"] = pack_gait(env)
         elif ret[1] is not None:
             o["privileged_obs_buf"] = n(ret[1])
-        if hasattr(env, "obs_history") and args.task not in ("tron1_pf_ee", "go2_wtw") and t in (args.steps // 2, args.steps - 1):
+        if hasattr(env, "obs_history") and args.task not in ("tron1_pf_ee", "go2_wtw", "go2_ee") and t in (args.steps // 2, args.steps - 1):
             rec[f"hist{t}/obs_history"] = n(env.obs_history)
-            rec[f"hist{t}/critic_obs_buf"] = n(env.critic_obs_buf)
+            rec[f"hist{t}/critic_obs_buf"] = n(env.critic_obs_buf if hasattr(env, "critic_obs_buf") else env.privileged_obs_buf)
         for k, v in o.items():
             put(t, "out/" + k, v)
     for k, v in per.items():
