@@ -198,18 +198,14 @@ def run_gpu(args):
     # ---- end to end through the public API with host buffers
     rew_host = torch.empty(N, dtype=torch.float32).pin_memory()
     rst_host = torch.empty(N, dtype=torch.bool).pin_memory()
-    act_dev = torch.empty(N, spec.num_actions, device=dev)
+    # FusedLeggedEnv.step_host = ONE C-ABI call (b200_env_step): H2D of the pinned actions, the kernels, D2H of rew / reset
     for i in range(W):
-        act_dev.copy_(host_pool[i % 16], non_blocking=True)
-        env.step(act_dev)
+        env.step_host(host_pool[i % 16], rew_host, rst_host)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        act_dev.copy_(host_pool[(W + i) % 16], non_blocking=True)
-        out = env.step(act_dev)
-        rew_host.copy_(env.rew_buf, non_blocking=True)
-        rst_host.copy_(env.reset_buf, non_blocking=True)
+        env.step_host(host_pool[(W + i) % 16], rew_host, rst_host)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)

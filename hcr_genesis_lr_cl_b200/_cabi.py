@@ -285,6 +285,8 @@ def load_library() -> ctypes.CDLL:
     lib.b200_dynamics_step.restype = ctypes.c_int
     lib.b200_env_post_step.argtypes = [vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, vp]
     lib.b200_env_post_step.restype = ctypes.c_int
+    lib.b200_env_step.argtypes = [vp, vp, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, vp, vp, vp, vp]
+    lib.b200_env_step.restype = ctypes.c_int
     lib.b200_set_step_flags.argtypes = [vp, ctypes.c_int]
     lib.b200_set_step_flags.restype = ctypes.c_int
     lib.b200_history_shift.argtypes = [vp, ctypes.c_int, vp]
@@ -306,4 +308,4 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = ["b200_create", "b200_destroy", "b200_set_terrain", "b200_bind_buffers", "b200_dynamics_step",
-                    "b200_history_shift", "b200_set_history_side_stream", "b200_env_post_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_launch_count", "b200_last_error"]
+                    "b200_history_shift", "b200_set_history_side_stream", "b200_env_post_step", "b200_env_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_launch_count", "b200_last_error"]

@@ -2,6 +2,7 @@
 // (hcr_genesis_lr_cl_b200/build.py); there is no CPU implementation behind these symbols.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include "dynamics_kernel.cuh"
@@ -37,7 +38,19 @@ struct B200Handle {
     bool side_enabled = true;
     bool preshift_on_side = false;
     int preshift_parity = -1;      // parity the stacks have been shifted for (-1: none pending)
+    int env_preset = -1;           // instantiation of the env kernel: index into env_presets.inc, -1 = generic
+    float *d_actions = nullptr;    // staging of b200_env_step's host actions
 };
+
+typedef void (*EnvKernelFn)(const TaskDev, const B200Buffers, const TerrainDev, const EnvCall, const EnvStageTab);
+static EnvKernelFn env_kernel_fn(int preset) {
+    switch (preset) {
+#define X_CASE(P) case P: return env_post_step_kernel_preset<P>;
+        ENV_FOR_EACH_PRESET(X_CASE)
+#undef X_CASE
+    default: return env_post_step_kernel;
+    }
+}
 
 extern "C" {
 
@@ -66,7 +79,11 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
     h->model.link_body = h->d_model_i + 8; h->model.sph_body = h->model.link_body + L; h->model.sph_link = h->model.sph_body + NS;
     h->dyn_smem = dyn_smem_bytes(DYN_WARPS_PER_BLOCK);
     h->env_smem = env_smem_bytes(ENV_WARPS_PER_BLOCK);
-    if (h->env_smem > 48 * 1024) CK(cudaFuncSetAttribute(env_post_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->env_smem));
+    {   // specialised instantiation when the descriptor is one of the built-in presets (B200_ENV_GENERIC=1 forces the generic one)
+        const char *g = getenv("B200_ENV_GENERIC");
+        h->env_preset = (g && g[0] == '1') ? -1 : env_match_preset(ti);
+    }
+    if (h->env_smem > 48 * 1024) CK(cudaFuncSetAttribute(env_kernel_fn(h->env_preset), cudaFuncAttributeMaxDynamicSharedMemorySize, h->env_smem));
     CK(cudaFuncSetAttribute(dynamics_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
     CK(cudaFuncSetAttribute(dynamics_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
     *out = h;
@@ -75,7 +92,7 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
 
 void b200_destroy(B200Handle *h) {
     if (!h) return;
-    cudaFree(h->d_model_f); cudaFree(h->d_model_i);
+    cudaFree(h->d_model_f); cudaFree(h->d_model_i); cudaFree(h->d_actions);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -119,8 +136,8 @@ int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
     const dim3 grid((N + DYN_WARPS_PER_BLOCK - 1) / DYN_WARPS_PER_BLOCK), block(DYN_WARPS_PER_BLOCK * 32);
     cudaStream_t s = (cudaStream_t)stream;
     if (h->task.i[TI_CAT]) CK(cudaMemsetAsync(h->bufs.global_flags, 0, 4 * sizeof(int32_t), s));
-    if (h->task.i[TI_OBS_KIND] >= 1) {               // fork point of b200_history_shift: everything enqueued before this step
-        if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    if (h->task.i[TI_OBS_KIND] >= 1 && h->preshift_parity < 0) {   // fork point of a b200_history_shift that follows: everything
+        if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));   // enqueued before this step
         CK(cudaEventRecord(h->ev_fork, s));
         h->fork_recorded = true;
     }
@@ -146,9 +163,14 @@ int b200_history_shift(B200Handle *h, int parity, void *stream) {
     }
     h->fork_recorded = false;
     const int N = ti[TI_NUM_ENVS], p = parity & 1;
-    const int Wh = ti[TI_FRAME_STACK] * ti[TI_NUM_OBS], Wc = ti[TI_C_FRAME_STACK] * ti[TI_SINGLE_CRITIC];
-    history_shift_kernel<<<dim3((N * HIST_SHIFT_PARTS + 7) / 8, 2), 256, 0, run>>>(h->bufs.obs_history[p], h->bufs.obs_history[p ^ 1], Wh, ti[TI_NUM_OBS],
-                                                           h->bufs.critic_obs[p], h->bufs.critic_obs[p ^ 1], Wc, ti[TI_SINGLE_CRITIC], N);
+    const long long Mh = (long long)N * ti[TI_FRAME_STACK] * ti[TI_NUM_OBS], Mc = (long long)N * ti[TI_C_FRAME_STACK] * ti[TI_SINGLE_CRITIC];
+    // one warp-iteration moves 32 x HIST_SHIFT_UNROLL vectors; enough blocks for the larger stack, capped at a few per SM
+    const long long per_block = (long long)(HIST_SHIFT_BLOCK / 32) * 32 * HIST_SHIFT_UNROLL * 4;
+    long long blocks = ((Mh > Mc ? Mh : Mc) + per_block - 1) / per_block;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    history_shift_kernel<<<dim3((unsigned)blocks, 2), HIST_SHIFT_BLOCK, 0, run>>>(h->bufs.obs_history[p], h->bufs.obs_history[p ^ 1], Mh, ti[TI_NUM_OBS],
+                                                                                 h->bufs.critic_obs[p], h->bufs.critic_obs[p ^ 1], Mc, ti[TI_SINGLE_CRITIC]);
     h->launches++;
     CK(cudaGetLastError());
     if (h->side_enabled) CK(cudaEventRecord(h->ev_join, h->side));
@@ -177,7 +199,7 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
         h->preshift_parity = -1;
     }
     const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
-    env_post_step_kernel<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call, h->stage);
+    env_kernel_fn(h->env_preset)<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call, h->stage);
     h->launches++;
     CK(cudaGetLastError());
     if ((mask & PHASE_RESET) && !force) {
@@ -196,6 +218,27 @@ int b200_env_post_step(B200Handle *h, long long step, float lo, float span, int 
     if (check_ready(h, "b200_env_post_step")) return 1;
     if ((mask & PHASE_ALL) == 0) return fail("b200_env_post_step: empty phase mask");
     return launch_env(h, step, lo, span, parity, mask & PHASE_ALL, 0, stream);
+}
+
+int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long long step, float lo, float span, int parity,
+                  float *host_rew, uint8_t *host_reset, uint8_t *host_time_out, void *stream) {
+    if (check_ready(h, "b200_env_step")) return 1;
+    if (!actions) return fail("b200_env_step: null actions");
+    const int N = h->task.i[TI_NUM_ENVS], A = h->task.i[TI_A];
+    cudaStream_t s = (cudaStream_t)stream;
+    const float *dev_actions = actions;
+    if (actions_on_host) {
+        if (!h->d_actions) CK(cudaMalloc(&h->d_actions, sizeof(float) * (size_t)N * A));
+        CK(cudaMemcpyAsync(h->d_actions, actions, sizeof(float) * (size_t)N * A, cudaMemcpyHostToDevice, s));
+        dev_actions = h->d_actions;
+    }
+    if (b200_dynamics_step(h, dev_actions, stream)) return 1;
+    if (b200_history_shift(h, parity, stream)) return 1;
+    if (launch_env(h, step, lo, span, parity, PHASE_ALL, 0, stream)) return 1;
+    if (host_rew) CK(cudaMemcpyAsync(host_rew, h->bufs.rew_buf, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));
+    if (host_reset) CK(cudaMemcpyAsync(host_reset, h->bufs.reset_buf, (size_t)N, cudaMemcpyDeviceToHost, s));
+    if (host_time_out) CK(cudaMemcpyAsync(host_time_out, h->bufs.time_out_buf, (size_t)N, cudaMemcpyDeviceToHost, s));
+    return 0;
 }
 
 int b200_set_step_flags(B200Handle *h, int sit_pose) {
@@ -227,7 +270,7 @@ int b200_kernel_info(B200Handle *h, const char *kernel, int *regs, int *smem, in
         else { CK(cudaFuncGetAttributes(&fa, dynamics_step_kernel<2>)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dynamics_step_kernel<2>, threads, dyn)); }
     } else if (!strcmp(kernel, "env")) {
         threads = ENV_WARPS_PER_BLOCK * 32; dyn = h->env_smem;
-        CK(cudaFuncGetAttributes(&fa, env_post_step_kernel)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, env_post_step_kernel, threads, dyn));
+        CK(cudaFuncGetAttributes(&fa, env_kernel_fn(h->env_preset))); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, env_kernel_fn(h->env_preset), threads, dyn));
     } else return fail("b200_kernel_info: unknown kernel name");
     if (regs) *regs = fa.numRegs;
     if (smem) *smem = (int)fa.sharedSizeBytes + dyn;

@@ -44,6 +44,27 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// sum over the first C lanes (C = 2 or 4), result in every lane: two butterfly rounds inside the aligned 4-lane group,
+// then one broadcast -- the chain quantities of the dynamics kernel live in lanes 0..C-1 only.
+template <int C>
+__device__ __forceinline__ float lead_sum(float v) {
+    if (C == 4) v += __shfl_xor_sync(B200_FULL_MASK, v, 2);
+    v += __shfl_xor_sync(B200_FULL_MASK, v, 1);
+    return __shfl_sync(B200_FULL_MASK, v, 0);
+}
+
+// max over the warp of a non-negative float: IEEE ordering of non-negative floats is the ordering of their bit patterns,
+// so one integer REDUX does it (SASS REDUX.MAX.U32) instead of five shuffle + max rounds.
+__device__ __forceinline__ float warp_max_nonneg(float v) {
+#ifdef B200_WARP_EMU
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(B200_FULL_MASK, v, o));
+    return v;
+#else
+    return __uint_as_float(__reduce_max_sync(B200_FULL_MASK, __float_as_uint(v)));
+#endif
+}
+
 // ---- TMA (bulk async copy) + mbarrier helpers: 1-D cp.async.bulk between global and shared memory (sm_90+; SASS UBLKCP).
 // Sizes and both addresses must be multiples of 16 bytes.  Under the test emulator they degrade to memcpy.
 #ifdef B200_WARP_EMU

@@ -162,7 +162,8 @@ __device__ __forceinline__ float impedance(const float *tf, float pos) {
     if (x >= 1.f) return tf[TF_DMAX];
     const float mid = tf[TF_MID], p = tf[TF_POWER];
     float y;
-    if (x < mid) y = powf(x, p) / powf(mid, p - 1.f);
+    if (p == 2.f) y = x < mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);     // the shipped solimp: no powf
+    else if (x < mid) y = powf(x, p) / powf(mid, p - 1.f);
     else y = 1.f - powf(1.f - x, p) / powf(1.f - mid, p - 1.f);
     return tf[TF_D0] + y * (tf[TF_DMAX] - tf[TF_D0]);
 }
@@ -172,13 +173,14 @@ __device__ __forceinline__ constexpr int tri(int i, int j) { return i >= j ? i *
 
 // in: S (lower tri, SPD).  out: Sinv (lower tri)
 __device__ __forceinline__ void spd6_inverse(const float *S, float *Sinv) {
-    float L[21], Li[21];
+    float L[21], Li[21], rd[6];        // rd[j] = 1 / L[j][j]
 #pragma unroll
     for (int j = 0; j < 6; j++) {
         float d = S[tri(j, j)];
 #pragma unroll
         for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)];
         const float r = rsqrtf(d);
+        rd[j] = r;
         L[tri(j, j)] = d * r;
 #pragma unroll
         for (int i = j + 1; i < 6; i++) {
@@ -191,13 +193,13 @@ __device__ __forceinline__ void spd6_inverse(const float *S, float *Sinv) {
     // Li = L^-1 (lower)
 #pragma unroll
     for (int j = 0; j < 6; j++) {
-        Li[tri(j, j)] = 1.f / L[tri(j, j)];
+        Li[tri(j, j)] = rd[j];
 #pragma unroll
         for (int i = j + 1; i < 6; i++) {
             float s = 0.f;
 #pragma unroll
             for (int k = j; k < i; k++) s += L[tri(i, k)] * Li[tri(k, j)];
-            Li[tri(i, j)] = -s / L[tri(i, i)];
+            Li[tri(i, j)] = -s * rd[i];
         }
     }
 #pragma unroll
@@ -221,7 +223,6 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     const float h = tf[TF_SIM_DT];
     const bool leg = lane < C;
     const int c = leg ? lane : C - 1;       // chain walked by this lane (lanes >= C shadow the last chain, results masked)
-    const float legm = leg ? 1.f : 0.f;
 
     // ---------------- load state ----------------
     f3 p = mk3(B.base_pos[env * 3], B.base_pos[env * 3 + 1], B.base_pos[env * 3 + 2]);
@@ -350,20 +351,19 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             fnb = LA + cross3(wb, LV) + cross3(vb, PV);
             ffb = PA + cross3(wb, PV);
             cb = sb;
-            cb.m += warp_sum(comp.m * legm);
-            cb.h.x += warp_sum(comp.h.x * legm); cb.h.y += warp_sum(comp.h.y * legm); cb.h.z += warp_sum(comp.h.z * legm);
+            cb.m += lead_sum<C>(comp.m);
+            cb.h.x += lead_sum<C>(comp.h.x); cb.h.y += lead_sum<C>(comp.h.y); cb.h.z += lead_sum<C>(comp.h.z);
 #pragma unroll
-            for (int e = 0; e < 6; e++) cb.I[e] += warp_sum(comp.I[e] * legm);
-            fnb.x += warp_sum(fns.x * legm); fnb.y += warp_sum(fns.y * legm); fnb.z += warp_sum(fns.z * legm);
-            ffb.x += warp_sum(ffs.x * legm); ffb.y += warp_sum(ffs.y * legm); ffb.z += warp_sum(ffs.z * legm);
+            for (int e = 0; e < 6; e++) cb.I[e] += lead_sum<C>(comp.I[e]);
+            fnb.x += lead_sum<C>(fns.x); fnb.y += lead_sum<C>(fns.y); fnb.z += lead_sum<C>(fns.z);
+            ffb.x += lead_sum<C>(ffs.x); ffb.y += lead_sum<C>(ffs.y); ffb.z += lead_sum<C>(ffs.z);
         }
         // chain block inverse (3x3 SPD), G = Dinv B^T, Schur complement
         float Di[6], G[3][6];
         {
-            const float l00 = sqrtf(Dm[0]), l10 = Dm[1] / l00, l20 = Dm[3] / l00;
-            const float l11 = sqrtf(Dm[2] - l10 * l10), l21 = (Dm[4] - l20 * l10) / l11;
-            const float l22 = sqrtf(Dm[5] - l20 * l20 - l21 * l21);
-            const float i00 = 1.f / l00, i11 = 1.f / l11, i22 = 1.f / l22;
+            const float i00 = rsqrtf(Dm[0]), l10 = Dm[1] * i00, l20 = Dm[3] * i00;
+            const float i11 = rsqrtf(Dm[2] - l10 * l10), l21 = (Dm[4] - l20 * l10) * i11;
+            const float i22 = rsqrtf(Dm[5] - l20 * l20 - l21 * l21);
             const float i10 = -l10 * i00 * i11, i21 = -l21 * i11 * i22, i20 = -(l20 * i00 + l21 * i10) * i22;
             Di[0] = i00 * i00 + i10 * i10 + i20 * i20; Di[1] = i10 * i11 + i20 * i21; Di[2] = i11 * i11 + i21 * i21;
             Di[3] = i20 * i22; Di[4] = i21 * i22; Di[5] = i22 * i22;
@@ -388,7 +388,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 #pragma unroll
                 for (int j2 = 0; j2 <= i2; j2++) {
                     const float t = Bt[0][i2] * G[0][j2] + Bt[1][i2] * G[1][j2] + Bt[2][i2] * G[2][j2];
-                    S[tri(i2, j2)] -= warp_sum(t * legm);
+                    S[tri(i2, j2)] -= lead_sum<C>(t);
                 }
         }
         float Sinv[21];
@@ -419,7 +419,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             for (int a2 = 0; a2 < 3; a2++) tl[a2] = Di[tri(a2, 0)] * rl[0] + Di[tri(a2, 1)] * rl[1] + Di[tri(a2, 2)] * rl[2];
             float rb[6] = {-ffb.x, -ffb.y, -ffb.z, -fnb.x, -fnb.y, -fnb.z};
 #pragma unroll
-            for (int e = 0; e < 6; e++) rb[e] -= warp_sum((Bt[0][e] * tl[0] + Bt[1][e] * tl[1] + Bt[2][e] * tl[2]) * legm);
+            for (int e = 0; e < 6; e++) rb[e] -= lead_sum<C>(Bt[0][e] * tl[0] + Bt[1][e] * tl[1] + Bt[2][e] * tl[2]);
 #pragma unroll
             for (int i2 = 0; i2 < 6; i2++) {
                 float s = 0.f;
@@ -658,50 +658,50 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         }
         __syncwarp();
         // ---------------- projected Gauss-Seidel with friction-cone projection ----------------
-        // One row per lane; a sweep visits the rows in order, the owner lane updates its force and broadcasts the
-        // change, every lane folds it into its residual with its entry of the (symmetric) row of A.
+        // One row per lane; a sweep visits the rows in order.  Every lane evaluates the update of its own row,
+        //     delta = clamp(f - (wres + Rr f) / (A_rr + Rr), lo, hi) - f = clamp(-idd wres - c1 f, lo - f, hi - f),
+        // the owner of the visited row keeps it and broadcasts the change, every lane folds it into its residual with its
+        // entry of the (symmetric) row of A.  Only {FFMA, 2 x FMNMX, SHFL, FFMA} sit on the wres -> wres dependency chain
+        // that bounds the slowest env of the batch (the terms in f are ready before the previous broadcast lands); the
+        // updated force is broadcast beside the change so that the cone projection needs no further exchange.
         const int iters = T.i[TI_PGS_ITERS];
         const float *Arow = ws + WS_AM + lane;            // A[r][lane] at Arow[33 * r]
         const bool clamp0 = (kind == 0 || kind == 3);
         const float fhi = kind == 4 ? bound : 3.0e38f, flo = clamp0 ? 0.f : -fhi;
+        const float c1n = -(Rr * idd), iddn = -idd;
         for (int it = 0; it < iters; it++) {
             const float fprev = f;
             // contacts: normal, tangent 1, tangent 2, then projection of the tangential pair onto the friction disc
             for (int c2 = 0; c2 < nc; c2++) {
                 const int r0 = 3 * c2;
+                float fb[3];                                   // the contact's three forces after their updates, in every lane
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                    const float fnew = fminf(fmaxf(f - (wres + Rr * f) * idd, flo), fhi);   // every lane: candidate for its own row
-                    const float delta = __shfl_sync(B200_FULL_MASK, fnew - f, r0 + d);
-                    if (lane == r0 + d) f = fnew;
-                    wres += Arow[33 * (r0 + d)] * delta;
+                    const float dl = fminf(fmaxf(fmaf(iddn, wres, c1n * f), flo - f), fhi - f);
+                    const float fn = f + dl;
+                    const float delta = __shfl_sync(B200_FULL_MASK, dl, r0 + d);
+                    fb[d] = __shfl_sync(B200_FULL_MASK, fn, r0 + d);
+                    if (lane == r0 + d) f = fn;
+                    wres = fmaf(Arow[33 * (r0 + d)], delta, wres);
                 }
-                const float fnn = __shfl_sync(B200_FULL_MASK, f, r0);
-                const float f1 = __shfl_sync(B200_FULL_MASK, f, r0 + 1);
-                const float f2 = __shfl_sync(B200_FULL_MASK, f, r0 + 2);
-                const float lim = mu * fnn, t2 = f1 * f1 + f2 * f2;
+                const float lim = mu * fb[0], t2 = fb[1] * fb[1] + fb[2] * fb[2];
                 if (t2 > lim * lim) {                                 // warp-uniform
                     const float sc = lim * rsqrtf(t2);
-                    const float n1 = f1 * sc, n2 = f2 * sc;
+                    const float n1 = fb[1] * sc, n2 = fb[2] * sc;
                     if (lane == r0 + 1) f = n1;
                     if (lane == r0 + 2) f = n2;
-                    wres += Arow[33 * (r0 + 1)] * (n1 - f1) + Arow[33 * (r0 + 2)] * (n2 - f2);
+                    wres += Arow[33 * (r0 + 1)] * (n1 - fb[1]) + Arow[33 * (r0 + 2)] * (n2 - fb[2]);
                 }
             }
             // joint-limit (f >= 0) and frictionloss (|f| <= bound) rows
             for (int r = 3 * nc; r < R; r++) {
-                const float fnew = fminf(fmaxf(f - (wres + Rr * f) * idd, flo), fhi);
-                const float delta = __shfl_sync(B200_FULL_MASK, fnew - f, r);
-                if (lane == r) f = fnew;
-                wres += Arow[33 * r] * delta;
+                const float dl = fminf(fmaxf(fmaf(iddn, wres, c1n * f), flo - f), fhi - f);
+                const float delta = __shfl_sync(B200_FULL_MASK, dl, r);
+                if (lane == r) f += dl;
+                wres = fmaf(Arow[33 * r], delta, wres);
             }
             // convergence: largest change of any row over the sweep relative to the largest force (warp-uniform exit)
-            float dmax = fabsf(f - fprev), fmx = fabsf(f);
-#pragma unroll
-            for (int o2 = 16; o2 > 0; o2 >>= 1) {
-                dmax = fmaxf(dmax, __shfl_xor_sync(B200_FULL_MASK, dmax, o2));
-                fmx = fmaxf(fmx, __shfl_xor_sync(B200_FULL_MASK, fmx, o2));
-            }
+            const float dmax = warp_max_nonneg(fabsf(f - fprev)), fmx = warp_max_nonneg(fabsf(f));
             if (dmax <= tf[TF_PGS_TOL] * (1.f + fmx)) break;
         }
         __syncwarp();
@@ -736,14 +736,13 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             fv[0] = fz * dir.x; fv[1] = fz * dir.y; fv[2] = fz * dir.z; fv[3] = __int_as_float(lane < 3 * nc ? rlink : -1);
         }
         __syncwarp();
-        for (int e = lane; e < 3 * L; e += 32) {
-            const int l2 = e / 3, k = e - 3 * l2;
-            float s = 0.f;
-            for (int r = 0; r < 3 * nc; r++) {
-                const float *fv = ws + WS_FV + r * 4;
-                if (__float_as_int(fv[3]) == l2) s += fv[k];
+        for (int e = lane; e < 3 * L; e += 32) ws[WS_LF + e] = 0.f;
+        __syncwarp();
+        if (lane < 3) {                        // contact order, one component per lane: deterministic accumulation per link
+            for (int c2 = 0; c2 < nc; c2++) {
+                const float *fv = ws + WS_FV + 12 * c2;
+                ws[WS_LF + 3 * __float_as_int(fv[3]) + lane] += fv[lane] + fv[4 + lane] + fv[8 + lane];
             }
-            ws[WS_LF + e] = s;
         }
         // semi-implicit Euler
         vb = vb + mk3(accb[0], accb[1], accb[2]) * h;

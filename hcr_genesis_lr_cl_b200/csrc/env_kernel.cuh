@@ -23,6 +23,21 @@
 #include "cuda_compat.cuh"
 #include "philox.cuh"
 #include "dynamics_kernel.cuh"   // TaskDev, TerrainDev
+#include "env_presets.inc"       // generated: the int descriptor of every built-in task preset as compile-time tables
+
+// The kernel is instantiated once per built-in preset with the structural ints of the task descriptor (widths, link
+// lists, reward list, feature flags) as compile-time constants, and once generically.  `ti[k]` reads through this view:
+// a constant for the specialised instantiations (except the run-time entries, env_ti_is_runtime), the descriptor else.
+// 70 % of the generic kernel's instructions are integer/branch work on exactly these values.
+struct EnvSpecGeneric {
+    static constexpr bool fixed = false;
+    __host__ __device__ static constexpr int get(int) { return 0; }
+};
+template <class S> struct TiView {
+    const int *rt;
+    __device__ __forceinline__ int operator[](int k) const { return (S::fixed && !env_ti_is_runtime(k)) ? S::get(k) : rt[k]; }
+    __device__ __forceinline__ int dyn(int k) const { return rt[k]; }      // lane-indexed lists: always the run-time table
+};
 
 #ifndef ENV_WARPS_PER_BLOCK
 #define ENV_WARPS_PER_BLOCK 4
@@ -110,30 +125,75 @@ __device__ __forceinline__ void history_append(float *dst, const float *src, int
 
 // The shift of both frame stacks for the coming env_post_step (b200_history_shift): out[env][0 : W - frame] =
 // in[env][frame : W].  It depends on nothing the dynamics kernel produces, so it is launched on a side stream and runs
-// in the shadow of the dynamics kernel; one warp per env row, 8 independent 128-byte requests in flight per warp.
-#define HIST_SHIFT_PARTS 2          // warps per row: enough 128-byte requests in flight per SM to cover the DRAM latency
-__global__ void history_shift_kernel(const float *in_h, float *out_h, int Wh, int fh, const float *in_c, float *out_c, int Wc, int fc, int N) {
+// in the shadow of the dynamics kernel.  Seen over the whole [N * W] array the shift is ONE flat copy with a constant
+// offset, out[d] = in[d + frame]: the `frame` slots at the end of each row receive the head of the next row, which is
+// harmless because env_post_step_kernel writes the new frame there (and clears the rows of envs that reset) before
+// anyone reads it.  So the kernel is a streaming copy: aligned 16-byte loads and stores, the (frame mod 4) words of
+// misalignment between source and destination are fixed up in registers with the neighbour lane's vector.
+#define HIST_SHIFT_UNROLL 4         // independent 16-byte loads in flight per thread
+#define HIST_SHIFT_BLOCK 256
+__device__ __forceinline__ void history_shift_flat(const float *__restrict__ in, float *__restrict__ out, long long M, int f) {
+    if (M <= f) return;
     const int lane = threadIdx.x & 31;
-    const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (env, part)
-    const int env = unit / HIST_SHIFT_PARTS, part = unit - env * HIST_SHIFT_PARTS;
-    if (env >= N) return;
-    const bool critic = blockIdx.y != 0;                                       // grid.y: 0 = obs_history, 1 = critic stack
-    const float *in = critic ? in_c : in_h;
-    float *out = critic ? out_c : out_h;
-    const int W = critic ? Wc : Wh, f = critic ? fc : fh, keep = W - f;
-    const int chunk = (((keep + HIST_SHIFT_PARTS - 1) / HIST_SHIFT_PARTS) + 31) & ~31;   // whole 128-byte store segments per part
-    const int lo = part * chunk, n = min(chunk, keep - lo);
-    if (n > 0) shift_copy(out + (size_t)env * W + lo, in + (size_t)env * W + f + lo, n, false, lane);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5), warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int a = f >> 2, b = f & 3;
+    const bool vec = (M & 3) == 0 && ((((size_t)in) | ((size_t)out)) & 15) == 0;
+    const long long nvec = vec ? (M - f) >> 2 : 0;                       // whole destination vectors
+    const float4 *in4 = (const float4 *)in;
+    float4 *out4 = (float4 *)out;
+    for (long long v0 = warp * (32 * HIST_SHIFT_UNROLL); v0 < nvec; v0 += nwarps * (32 * HIST_SHIFT_UNROLL)) {
+        float4 s[HIST_SHIFT_UNROLL];
+        float tail[HIST_SHIFT_UNROLL][3];
+#pragma unroll
+        for (int k = 0; k < HIST_SHIFT_UNROLL; k++) {
+            const long long v = v0 + 32 * k + lane;
+            s[k] = v < nvec ? __ldcs(in4 + v + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // lane 31 (and the owner of the very last vector) has no neighbour holding the next source vector: it fetches
+            // the b words it needs from it itself
+            tail[k][0] = tail[k][1] = tail[k][2] = 0.f;
+            if (b > 0 && (lane == 31 || v == nvec - 1) && v < nvec) {
+                const float *nx = in + 4 * (v + a + 1);
+                tail[k][0] = __ldcs(nx);
+                if (b > 1) tail[k][1] = __ldcs(nx + 1);
+                if (b > 2) tail[k][2] = __ldcs(nx + 2);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < HIST_SHIFT_UNROLL; k++) {
+            const long long v = v0 + 32 * k + lane;
+            float4 o = s[k];
+            if (b > 0) {                                                 // warp-uniform
+                float nx = __shfl_down_sync(B200_FULL_MASK, s[k].x, 1), ny = 0.f, nz = 0.f;
+                if (b > 1) ny = __shfl_down_sync(B200_FULL_MASK, s[k].y, 1);
+                if (b > 2) nz = __shfl_down_sync(B200_FULL_MASK, s[k].z, 1);
+                if (lane == 31 || v == nvec - 1) { nx = tail[k][0]; ny = tail[k][1]; nz = tail[k][2]; }
+                if (b == 1) o = make_float4(s[k].y, s[k].z, s[k].w, nx);
+                else if (b == 2) o = make_float4(s[k].z, s[k].w, nx, ny);
+                else o = make_float4(s[k].w, nx, ny, nz);
+            }
+            if (v < nvec) out4[v] = o;
+        }
+    }
+    // scalar remainder (and the whole array when it is not 16-byte tileable)
+    const long long tid = warp * 32 + lane, nthreads = nwarps * 32;
+    for (long long d = 4 * nvec + tid; d < M - f; d += nthreads) out[d] = __ldcs(in + d + f);
+}
+
+__global__ void B200_LAUNCH_BOUNDS(HIST_SHIFT_BLOCK, 1)
+history_shift_kernel(const float *in_h, float *out_h, long long Mh, int fh, const float *in_c, float *out_c, long long Mc, int fc) {
+    if (blockIdx.y == 0) history_shift_flat(in_h, out_h, Mh, fh);         // grid.y: 0 = obs_history, 1 = critic stack
+    else history_shift_flat(in_c, out_c, Mc, fc);
 }
 
 // `staged`: the CTA's inputs were brought into shared memory by bulk copies completing on the mbarrier `bar`.
 // `R` is the view all per-env *inputs* are read through: B itself, or (staged CTAs) a copy whose pointers are biased so
 // that R.x[env * k + i] lands in the CTA's shared-memory slab that TMA filled -- one exposed DRAM latency per CTA
 // instead of one per dependent load.  All stores go to B (global memory).
+template <class S>
 __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const B200Buffers &R, const TerrainDev &tr, const EnvCall &call,
                                    float *es, int env, int lane, bool staged, uint64_t *bar) {
     const float *tf = T.f;
-    const int *ti = T.i;
+    const TiView<S> ti{T.i};
     const int A = ti[TI_A], F = ti[TI_F], L = ti[TI_L], P = ti[TI_PX] * ti[TI_PY];
     const int n_sums = ti[TI_N_SUMS];
     const int pm = call.force_reset ? PHASE_RESET : call.phase_mask;
@@ -196,7 +256,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         const float *a = R.feet_pos + (env * F + lane) * 3, *b = R.feet_vel + (env * F + lane) * 3;
         fpos = mk3(a[0], a[1], a[2]); fvel = mk3(b[0], b[1], b[2]);
     }
-    float ffz = fl ? R.link_contact_forces[(env * L + ti[TI_FEET_LINKS + lane]) * 3 + 2] : 0.f;   // foot contact force z
+    float ffz = fl ? R.link_contact_forces[(env * L + ti.dyn(TI_FEET_LINKS + lane)) * 3 + 2] : 0.f;   // foot contact force z
     float hmean = 0.f, hmax = 0.f;   // mean / max of the 9 terrain heights around this lane's foot
 
     if (pm & PHASE_CALLBACK) ep_len += 1;                       // legged_robot.py:60
@@ -232,7 +292,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             B.base_euler[env * 3 + 2] = atan2f(siny, cosy);
         }
         if (ti[TI_CONTACT_STATES] && lane < ti[TI_N_CS]) {
-            const float *f = R.link_contact_forces + (env * L + ti[TI_CS_LINKS + lane]) * 3;
+            const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_CS_LINKS + lane)) * 3;
             const float cs = norm3_rn(f[0], f[1], f[2]) > 1.0f ? 1.f : 0.f;
             B.link_contact_states[env * ti[TI_N_CS] + lane] = cs; es[ES_LCS + lane] = cs;
         }
@@ -332,7 +392,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     if (pm & PHASE_TERMINATION) {
         bool hit = false;
         if (lane < ti[TI_N_TERM]) {
-            const float *f = R.link_contact_forces + (env * L + ti[TI_TERM_LINKS + lane]) * 3;
+            const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_TERM_LINKS + lane)) * 3;
             hit = norm3_rn(f[0], f[1], f[2]) > 10.0f;
         }
         const bool fail = (__ballot_sync(B200_FULL_MASK, hit) != 0u) || (grav.z > tf[TF_MAX_PROJ_GRAV]);
@@ -363,10 +423,10 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         for (int pt = lane; pt < P; pt += 32) hs += bp.z - (ti[TI_MEASURE_HEIGHTS] ? es[ES_MH + pt] : 0.f);
         const bool c_height = warp_sum(hs) / (float)P < tf[TF_CAT_MIN_BASE_HEIGHT];
         bool hit = false;
-        if (lane < ti[TI_N_PEN]) { const float *f = R.link_contact_forces + (env * L + ti[TI_PEN_LINKS + lane]) * 3; hit = norm3_rn(f[0], f[1], f[2]) > 10.0f; }
+        if (lane < ti[TI_N_PEN]) { const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_PEN_LINKS + lane)) * 3; hit = norm3_rn(f[0], f[1], f[2]) > 10.0f; }
         const bool c_coll = __ballot_sync(B200_FULL_MASK, hit) != 0u;
         bool stumble = false;
-        if (fl) { const float *f = R.link_contact_forces + (env * L + ti[TI_FEET_LINKS + lane]) * 3; stumble = norm3_rn(f[0], f[1], f[2]) > __fmul_rn(4.0f, fabsf(f[2])); }
+        if (fl) { const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_FEET_LINKS + lane)) * 3; stumble = norm3_rn(f[0], f[1], f[2]) > __fmul_rn(4.0f, fabsf(f[2])); }
         const bool c_stumble = __ballot_sync(B200_FULL_MASK, stumble) != 0u;
         const bool below = __ballot_sync(B200_FULL_MASK, jl && qj < tf[TF_DOF_LIM_LO + lane]) != 0u;
         const bool above = __ballot_sync(B200_FULL_MASK, jl && qj > tf[TF_DOF_LIM_HI + lane]) != 0u;
@@ -391,6 +451,9 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         const float dqj = qj - q0j;
         float rew = 0.f;
         const int nr = ti[TI_N_REWARDS];
+        // specialised instantiations unroll the loop: ids are constants, the switch folds to the active terms in order
+        constexpr int kRewardUnroll = S::fixed ? B200_MAX_REWARDS : 1;
+#pragma unroll kRewardUnroll
         for (int i = 0; i < nr; i++) {
             const int id = ti[TI_REWARD_IDS + i];
             float r = 0.f;
@@ -409,7 +472,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 const int nf = id == RW_BIPED_PERIODIC_GAIT ? 2 : 4;
                 float term = 0.f;
                 if (lane < nf) {
-                    const float *f = R.link_contact_forces + (env * L + ti[TI_FEET_LINKS + lane]) * 3;
+                    const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_FEET_LINKS + lane)) * 3;
                     const float q_frc = norm3_rn(f[0], f[1], f[2]), q_spd = norm3_rn(fvel.x, fvel.y, fvel.z);
                     const float thl = lane == 0 ? th0 : (lane == 1 ? th1 : (lane == 2 ? th2 : th3));
                     const float ph = __fmul_rn(fmodf(__fadd_rn(gphi, thl), 1.0f), 6.2831853071795862f);
@@ -420,7 +483,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 r = expf(warp_sum(term)); break; }
             case RW_COLLISION: {
                 float hitf = 0.f;
-                if (lane < ti[TI_N_PEN]) { const float *f = R.link_contact_forces + (env * L + ti[TI_PEN_LINKS + lane]) * 3; hitf = norm3_rn(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f; }
+                if (lane < ti[TI_N_PEN]) { const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_PEN_LINKS + lane)) * 3; hitf = norm3_rn(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f; }
                 r = warp_sum(hitf); break; }
             case RW_DOF_ACC: { const float d = (lqdj - qdj) / dt; r = warp_sum(d * d); break; }
             case RW_DOF_CLOSE_TO_DEFAULT: r = warp_sum(dqj * dqj); break;
@@ -894,13 +957,14 @@ inline EnvStageTab env_stage_table(const TaskDev &T, const B200Buffers &B, int n
     return tab;
 }
 
-__global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, ENV_MIN_BLOCKS)
-env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call, const EnvStageTab tab) {
+template <class S>
+__device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const EnvCall &call, const EnvStageTab &tab) {
     extern __shared__ float smem[];
+    const TiView<S> ti{T.i};
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env0 = blockIdx.x * nwarps, env = env0 + warp;
-    const int N = T.i[TI_NUM_ENVS];
+    const int N = ti[TI_NUM_ENVS];
     uint64_t *bar = (uint64_t *)smem;
     float *es = smem + 4;
     char *inslab = (char *)(es + nwarps * ES_TOTAL);
@@ -917,13 +981,36 @@ env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, 
         B200Buffers R = B;
         int t = 0;
 #define X_VIEW(field, type, k) { if (tab.off[t] != ENV_NOT_STAGED) R.field = (type *)(inslab + tab.off[t]) - (size_t)env0 * (k); t++; }
-        ENV_STAGED_INPUTS(X_VIEW, T.i[TI_A], T.i[TI_F], T.i[TI_L], T.i[TI_N_SUMS])
+        ENV_STAGED_INPUTS(X_VIEW, ti[TI_A], ti[TI_F], ti[TI_L], ti[TI_N_SUMS])
 #undef X_VIEW
-        env_post_step_warp(T, B, R, tr, call, es + warp * ES_TOTAL, env, lane, true, bar);
+        env_post_step_warp<S>(T, B, R, tr, call, es + warp * ES_TOTAL, env, lane, true, bar);
         return;
     }
     if (env >= N) return;
-    env_post_step_warp(T, B, B, tr, call, es + warp * ES_TOTAL, env, lane, false, bar);
+    env_post_step_warp<S>(T, B, B, tr, call, es + warp * ES_TOTAL, env, lane, false, bar);
+}
+
+// generic instantiation: every descriptor int is read at run time (any task configuration)
+__global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, ENV_MIN_BLOCKS)
+env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call, const EnvStageTab tab) {
+    env_post_step_body<EnvSpecGeneric>(T, B, tr, call, tab);
+}
+
+// one instantiation per built-in preset (env_presets.inc); selected by b200_create when the descriptor matches the table
+template <int P>
+__global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, ENV_MIN_BLOCKS)
+env_post_step_kernel_preset(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call, const EnvStageTab tab) {
+    env_post_step_body<EnvPresetSpec<P>>(T, B, tr, call, tab);
+}
+
+// index of the preset whose compile-time ints all equal this descriptor's, or -1 (-> generic kernel)
+inline int env_match_preset(const int *ti) {
+    for (int p = 0; p < ENV_NUM_PRESETS; p++) {
+        bool same = true;
+        for (int k = 0; k < TI_COUNT && same; k++) same = env_ti_is_runtime(k) || kEnvPresetTI[p][k] == ti[k];
+        if (same) return p;
+    }
+    return -1;
 }
 
 // extras["episode"] (legged_robot.py:127-141): means over the envs that reset this step, from the reductions the env

@@ -121,6 +121,20 @@ class FusedLeggedEnv:
         self._fill_extras()
         return self._returns()
 
+    def step_host(self, actions_pinned: torch.Tensor, rew_out: Optional[torch.Tensor] = None,
+                  reset_out: Optional[torch.Tensor] = None, time_out_out: Optional[torch.Tensor] = None):
+        """`step` for a rollout loop that keeps actions / rewards / dones in pinned host memory: the host->device copy of
+        the actions, the three kernels and the device->host copies of rew / reset / time_out are enqueued by ONE C-ABI
+        call (b200_env_step) on the current stream.  Nothing is synchronised here; wait on the stream (or an event)
+        before reading the host buffers.  Returns the same tuple as `step` (device views)."""
+        self.common_step_counter += 1
+        self._apply_pending_curriculum()
+        self._set_step_flags()
+        self.simulator.fused_env_step(actions_pinned, self.common_step_counter, self.command_ranges["lin_vel_x"],
+                                      rew_out, reset_out, time_out_out)
+        self._fill_extras()
+        return self._returns()
+
     def _set_step_flags(self):
         """Host scalars of the step: the sit-pose coin (one per reset batch, tron1_pf_ee.py:204-210)."""
         if self.spec.sit_init_percent > 0:

@@ -266,6 +266,28 @@ class B200Simulator:
         if mask & H["PHASE_OBSERVE"]:
             self._parity ^= 1
 
+    def fused_env_step(self, actions, step_counter: int, cmd_range_x: Sequence[float], host_rew=None, host_reset=None,
+                       host_time_out=None):
+        """One whole env.step in ONE C-ABI call (b200_env_step): `actions` is a pinned host tensor (copied to the device
+        inside the call) or a device tensor; optional pinned host tensors receive rew / reset / time_out."""
+        on_host = not actions.is_cuda
+        if on_host:
+            if not (actions.is_pinned() and actions.dtype == torch.float32 and actions.is_contiguous()):
+                raise ValueError("host actions must be a pinned, contiguous float32 tensor")
+            a = actions
+        else:
+            a = actions if (actions.dtype == torch.float32 and actions.is_contiguous() and actions.device == self._tdev) \
+                else actions.to(self._tdev, torch.float32).contiguous()
+        for t in (host_rew, host_reset, host_time_out):
+            if t is not None and not t.is_pinned():
+                raise ValueError("host output buffers must be pinned")
+        lo, hi = float(cmd_range_x[0]), float(cmd_range_x[1])
+        self._ck(self._lib.b200_env_step(self._handle, a.data_ptr(), int(on_host), int(step_counter), lo, float(np.float32(hi - lo)),
+                                         self._parity, host_rew.data_ptr() if host_rew is not None else None,
+                                         host_reset.data_ptr() if host_reset is not None else None,
+                                         host_time_out.data_ptr() if host_time_out is not None else None, self._stream()))
+        self._parity ^= 1
+
     def set_step_flags(self, sit_pose: bool) -> None:
         self._ck(self._lib.b200_set_step_flags(self._handle, int(bool(sit_pose))))
 

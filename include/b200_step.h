@@ -263,6 +263,15 @@ int b200_set_history_side_stream(B200Handle *h, int enabled);
 int b200_env_post_step(B200Handle *h, long long step_counter, float cmd_vx_lo, float cmd_vx_span, int parity,
                        int phase_mask, void *cuda_stream);
 
+/* One whole env.step (LeggedRobot.step, legged_robot.py:37-53) with HOST buffers, one call: copies `actions` ([N,A] fp32;
+ * pinned host memory when `actions_on_host`, device memory otherwise) to the device, then b200_dynamics_step,
+ * b200_history_shift (when the task keeps frame stacks) and b200_env_post_step(PHASE_ALL), then copies rew_buf ([N] fp32),
+ * reset_buf and time_out_buf ([N] bool bytes) into the given pinned host buffers (each may be NULL).  Everything is
+ * enqueued on `cuda_stream`; nothing is synchronised -- the caller waits on the stream before reading the host buffers.
+ * This is the call the rollout loop makes (on_policy_runner.py:118-139: env.step(actions) followed by host reads). */
+int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long long step_counter, float cmd_vx_lo, float cmd_vx_span,
+                  int parity, float *host_rew, uint8_t *host_reset, uint8_t *host_time_out, void *cuda_stream);
+
 /* Per-step host scalars for the next b200_env_post_step / b200_reset_all: `sit_pose` != 0 -> envs that reset in that
  * call start in the sit pose (tron1_pf_ee.py:204-210 draws ONE coin per reset batch). */
 int b200_set_step_flags(B200Handle *h, int sit_pose);

@@ -28,8 +28,9 @@ def build_emu(with_env=True):
 class EmuSim:
     """numpy-buffer twin of the device-side state; the emulated kernels read/write it in place."""
 
-    def __init__(self, spec, num_envs, height_samples=None, terrain_origins=None, with_env=True):
+    def __init__(self, spec, num_envs, height_samples=None, terrain_origins=None, with_env=True, specialized=True):
         self.lib = build_emu(with_env)
+        self.specialized, self.last_preset = specialized, -1      # preset instantiation of the env kernel, like b200_create picks it
         self.spec, self.N = spec, num_envs
         self.model = spec.load_model()
         self.hs = None if height_samples is None else np.ascontiguousarray(height_samples, np.int16)
@@ -88,7 +89,8 @@ class EmuSim:
         beh = np.zeros(8, np.float32)
         beh[0::2] = self.beh_ranges[:, 0]
         beh[1::2] = self.beh_ranges[:, 1] - self.beh_ranges[:, 0]
-        self.lib.emu_env_post_step(self._p(self.tf), self._p(self.ti), self._p(self.hs), ctypes.c_int(rows), ctypes.c_int(cols),
+        self.lib.emu_set_env_specialized(ctypes.c_int(int(self.specialized)))
+        self.last_preset = self.lib.emu_env_post_step(self._p(self.tf), self._p(self.ti), self._p(self.hs), ctypes.c_int(rows), ctypes.c_int(cols),
                                    self._p(self.origins), ctypes.c_int(lv), ctypes.c_int(ty), ctypes.byref(self.cbuf),
                                    ctypes.c_longlong(self.step_counter), ctypes.c_float(lo), ctypes.c_float(np.float32(hi - lo)),
                                    ctypes.c_int(self.parity), ctypes.c_int(phase_mask), ctypes.c_int(force_reset), ctypes.c_int(int(bool(sit_pose))),

@@ -17,7 +17,14 @@ INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contact
 @pytest.mark.parametrize("name,steps", [("go2_ts_n32", 5), ("go2_n32", 4), ("go2_cat_n32", 5), ("tron1_pf_n32", 5), ("tron1_pf_ee_n32", 5), ("go2_wtw_n32", 5),
                                         ("go2_cts_n32", 5), ("go2_ee_n32", 5), ("go2_dreamwaq_n32", 5)])
 def test_emulated_env_kernel_matches_reference_golden(name, steps):
+    """The preset-specialised instantiation b200_create selects for this descriptor (asserted: not the generic one)."""
     _run_golden(name, steps, preshift=True)
+
+
+@pytest.mark.parametrize("name", ["go2_ts_n32", "tron1_pf_ee_n32", "go2_wtw_n32", "go2_cat_n32"])
+def test_emulated_generic_env_kernel_matches_reference_golden(name):
+    """The generic instantiation (any edited configuration runs on it): descriptor ints read at run time."""
+    _run_golden(name, 3, preshift=True, specialized=False)
 
 
 def test_emulated_env_kernel_in_kernel_history_shift():
@@ -25,12 +32,12 @@ def test_emulated_env_kernel_in_kernel_history_shift():
     _run_golden("go2_ts_n32", 4, preshift=False)
 
 
-def _run_golden(name, steps, preshift):
+def _run_golden(name, steps, preshift, specialized=True):
     g, s0 = load_golden(name)
     spec = spec_for(g)
     hs, origins = (load_terrain(spec) if spec.heightfield else (None, None))
     N = g["actions"].shape[1]
-    sim = EmuSim(spec, N, hs, origins)
+    sim = EmuSim(spec, N, hs, origins, specialized=specialized)
     sim.load_state(s0)
     B = sim.buf
     for t in range(steps):
@@ -43,6 +50,7 @@ def _run_golden(name, steps, preshift):
         B["global_flags"][0] = int((np.abs(phys_at(g, t)["qd"]) > 4).any())      # what the dynamics kernel leaves (CaT R4)
         B["stats"][:] = 0
         sim.env_post_step(preshift=preshift)
+        assert (sim.last_preset >= 0) == specialized, "preset selection"
         ref = out_at(g, t)
         mine = dict(B, actions_buf=B["actions"], end_q=B["dof_pos"], end_qd=B["dof_vel"])
         if spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw", "go2_ee"):     # the returned obs / privileged obs are the frame stacks

@@ -99,3 +99,14 @@ def test_robot_model_invariants():
         assert np.allclose(np.linalg.norm(m.body[1:, 3:6], axis=1), 1.0)
     with pytest.raises(ValueError):
         load_robot_model("go2", list(reversed(T.GO2_DOF_NAMES)))
+
+
+def test_generated_env_presets_are_current():
+    """csrc/env_presets.inc (compile-time int descriptors of the built-in presets) matches what pack_task produces now."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sp = importlib.util.spec_from_file_location("gen_env_presets", os.path.join(root, "tools", "gen_env_presets.py"))
+    gen = importlib.util.module_from_spec(sp)
+    sp.loader.exec_module(gen)
+    assert open(gen.path()).read() == gen.render(), "run tools/gen_env_presets.py"

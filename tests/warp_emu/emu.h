@@ -40,6 +40,9 @@ static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu_exchan
 static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return emu_exchange(v, src & 31); }
 static inline float __shfl_xor_sync(unsigned, float v, int m) { return emu_float(emu_exchange(emu_bits(v), emu_cur_lane ^ m)); }
 static inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)emu_exchange((uint32_t)v, emu_cur_lane ^ m); }
+static inline float __shfl_down_sync(unsigned, float v, int d) { return emu_float(emu_exchange(emu_bits(v), emu_cur_lane + d < 32 ? emu_cur_lane + d : emu_cur_lane)); }
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 static inline unsigned __ballot_sync(unsigned, bool p) { return emu_ballot(p); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_sync(); }
 static inline void __syncthreads() { emu_sync(); }   // the emulator runs one warp per block

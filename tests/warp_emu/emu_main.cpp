@@ -36,9 +36,18 @@ int emu_dynamics_step(const float *tf, const int *ti, const int *mi, const float
 
 #ifdef EMU_WITH_ENV
 struct EnvArgs { TaskDev T; B200Buffers B; TerrainDev tr; EnvCall call; EnvStageTab tab; };
-struct ShiftArgs { const float *in_h; float *out_h; int Wh, fh; const float *in_c; float *out_c; int Wc, fc, N; };
-static void shift_body(void *p) { ShiftArgs *a = (ShiftArgs *)p; history_shift_kernel(a->in_h, a->out_h, a->Wh, a->fh, a->in_c, a->out_c, a->Wc, a->fc, a->N); }
-static void env_body(void *p) { EnvArgs *a = (EnvArgs *)p; env_post_step_kernel(a->T, a->B, a->tr, a->call, a->tab); }
+struct ShiftArgs { const float *in_h; float *out_h; long long Mh; int fh; const float *in_c; float *out_c; long long Mc; int fc; };
+static void shift_body(void *p) { ShiftArgs *a = (ShiftArgs *)p; history_shift_kernel(a->in_h, a->out_h, a->Mh, a->fh, a->in_c, a->out_c, a->Mc, a->fc); }
+static int g_env_preset = -1, g_env_specialized = 1;
+static void env_body(void *p) {
+    EnvArgs *a = (EnvArgs *)p;
+    switch (g_env_preset) {            // same selection as launch_env in csrc/b200_step.cu
+#define X_CASE(P) case P: env_post_step_kernel_preset<P>(a->T, a->B, a->tr, a->call, a->tab); break;
+        ENV_FOR_EACH_PRESET(X_CASE)
+#undef X_CASE
+    default: env_post_step_kernel(a->T, a->B, a->tr, a->call, a->tab);
+    }
+}
 int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int rows, int cols, const float *origins, int levels, int types,
                       const B200Buffers *bufs, long long step, float vx_lo, float vx_span, int parity, int phase_mask, int force_reset, int sit_pose, const float *beh8, int gait_cb, int gait_reset, int preshift) {
     static EnvArgs a;
@@ -54,14 +63,16 @@ int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int row
     if (preshift && a.T.i[TI_OBS_KIND] >= 1 && !force_reset && (phase_mask & PHASE_OBSERVE)) {   // what b200_history_shift launches
         static ShiftArgs sh;
         const int p = parity & 1;
-        sh.in_h = a.B.obs_history[p]; sh.out_h = a.B.obs_history[p ^ 1]; sh.Wh = a.T.i[TI_FRAME_STACK] * a.T.i[TI_NUM_OBS]; sh.fh = a.T.i[TI_NUM_OBS];
-        sh.in_c = a.B.critic_obs[p]; sh.out_c = a.B.critic_obs[p ^ 1]; sh.Wc = a.T.i[TI_C_FRAME_STACK] * a.T.i[TI_SINGLE_CRITIC]; sh.fc = a.T.i[TI_SINGLE_CRITIC];
-        sh.N = a.T.i[TI_NUM_ENVS];
-        emu_launch(shift_body, &sh, sh.N * HIST_SHIFT_PARTS, 2);
+        const long long N = a.T.i[TI_NUM_ENVS];
+        sh.in_h = a.B.obs_history[p]; sh.out_h = a.B.obs_history[p ^ 1]; sh.Mh = N * a.T.i[TI_FRAME_STACK] * a.T.i[TI_NUM_OBS]; sh.fh = a.T.i[TI_NUM_OBS];
+        sh.in_c = a.B.critic_obs[p]; sh.out_c = a.B.critic_obs[p ^ 1]; sh.Mc = N * a.T.i[TI_C_FRAME_STACK] * a.T.i[TI_SINGLE_CRITIC]; sh.fc = a.T.i[TI_SINGLE_CRITIC];
+        emu_launch(shift_body, &sh, 3, 2);          // fewer blocks than work: exercises the grid-stride loop
         a.call.preshifted = 1;
     }
+    g_env_preset = g_env_specialized ? env_match_preset(a.T.i) : -1;
     emu_launch(env_body, &a, a.T.i[TI_NUM_ENVS]);
-    return 0;
+    return g_env_preset;
 }
+void emu_set_env_specialized(int on) { g_env_specialized = on; }
 #endif
 }

@@ -14,7 +14,7 @@ from hcr_genesis_lr_cl_b200.terrain_assets import terrain_for  # noqa: E402
 N = 4096
 spec = T.go2_ts_spec()
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda:0")
-for mode in ("side", "inline", "in_env_kernel", "side"):
+for mode in ("side", "side_first", "inline", "in_env_kernel", "side"):
     env = FusedLeggedEnv(spec, N, "cuda:0", terrain=terrain_for(spec))
     sim = env.simulator
     env.reset()
@@ -29,6 +29,8 @@ for mode in ("side", "inline", "in_env_kernel", "side"):
         ev[k][0].record()
         if mode == "inline":
             sim.history_shift(side_stream=False)
+        if mode == "side_first":                 # side stream, enqueued before the dynamics kernel: gets the SMs first
+            sim.history_shift(side_stream=True)
         sim.step(pool[i % 8])
         ev[k][1].record()
         env.common_step_counter += 1
