@@ -184,15 +184,32 @@ int b200_set_history_side_stream(B200Handle *h, int enabled) {
     return 0;
 }
 
+static EnvCall make_call(B200Handle *h, long long step, float lo, float span, int parity, int mask, int force) {
+    EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.parity = parity & 1; call.phase_mask = mask; call.force_reset = force; call.sit_pose = h->sit_pose;
+    for (int k = 0; k < 8; k++) call.beh[k] = h->beh[k];
+    call.gait_cb = h->gait_cb; call.gait_reset = h->gait_reset;
+    call.preshifted = 0;
+    return call;
+}
+
+static int finalize_stats(B200Handle *h, long long step, cudaStream_t s) {
+    const int N = h->task.i[TI_NUM_ENVS], n_sums = h->task.i[TI_N_SUMS];
+    // go2_cts: this rank's teacher envs are the global ids [0, num_teacher) that fall inside its block
+    const int n_teach = max(0, min(N, h->task.i[TI_NUM_TEACHER] - h->task.i[TI_ENV_OFFSET]));
+    const float inv_t = h->task.i[TI_NUM_TEACHER] > 0 ? 1.0f / (float)max(n_teach, 1) : 0.f, inv_s = 1.0f / (float)max(N - n_teach, 1);
+    stats_finalize_kernel<<<1, 64, 0, s>>>(h->bufs.stats, n_sums, 1.0f / h->task.f[TF_EPISODE_LENGTH_S], 1.0f / (float)N, inv_t, inv_s,
+                                           (int)(step % ENV_STATS_RING));
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static int launch_env(B200Handle *h, long long step, float lo, float span, int parity, int mask, int force, void *stream) {
     const int N = h->task.i[TI_NUM_ENVS];
     const int n_sums = h->task.i[TI_N_SUMS];
     cudaStream_t s = (cudaStream_t)stream;
     if (mask & PHASE_RESET) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 4), s));
-    EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.parity = parity & 1; call.phase_mask = mask; call.force_reset = force; call.sit_pose = h->sit_pose;
-    for (int k = 0; k < 8; k++) call.beh[k] = h->beh[k];
-    call.gait_cb = h->gait_cb; call.gait_reset = h->gait_reset;
-    call.preshifted = 0;
+    EnvCall call = make_call(h, step, lo, span, parity, mask, force);
     if (h->preshift_parity >= 0) {                   // join the side stream; use its work only if it was for this parity and phase set
         if (h->preshift_on_side) CK(cudaStreamWaitEvent(s, h->ev_join, 0));
         call.preshifted = (h->preshift_parity == (parity & 1) && !force && (mask & PHASE_OBSERVE)) ? 1 : 0;
@@ -202,15 +219,7 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     env_kernel_fn(h->env_preset)<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call, h->stage);
     h->launches++;
     CK(cudaGetLastError());
-    if ((mask & PHASE_RESET) && !force) {
-        // go2_cts: this rank's teacher envs are the global ids [0, num_teacher) that fall inside its block
-        const int n_teach = max(0, min(N, h->task.i[TI_NUM_TEACHER] - h->task.i[TI_ENV_OFFSET]));
-        const float inv_t = h->task.i[TI_NUM_TEACHER] > 0 ? 1.0f / (float)max(n_teach, 1) : 0.f, inv_s = 1.0f / (float)max(N - n_teach, 1);
-        stats_finalize_kernel<<<1, 64, 0, s>>>(h->bufs.stats, n_sums, 1.0f / h->task.f[TF_EPISODE_LENGTH_S], 1.0f / (float)N, inv_t, inv_s,
-                                               (int)(step % ENV_STATS_RING));
-        h->launches++;
-        CK(cudaGetLastError());
-    }
+    if ((mask & PHASE_RESET) && !force) return finalize_stats(h, step, s);
     return 0;
 }
 

@@ -218,7 +218,7 @@ template <int C>
 __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const float *ms, float *ws,
                               const float *actions_in, int env, int lane) {
     const float *tf = T.f;
-    const int A = 3 * C, NB = 1 + 3 * C, L = T.i[TI_L], NS = T.i[TI_NSPHERES];
+    const int A = 3 * C, L = T.i[TI_L], NS = T.i[TI_NSPHERES];
     const int *msi = (const int *)(ms + MS_INT);
     const float h = tf[TF_SIM_DT];
     const bool leg = lane < C;

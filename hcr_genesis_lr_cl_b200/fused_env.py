@@ -3,10 +3,12 @@
 Mirrors the call contract of ``LeggedRobot.step`` / ``LeggedRobotTS.step`` (legged_gym/envs/base/legged_robot.py:37-53,
 legged_robot_ts.py:59-76): same return tuples, same attribute names the runners read (``num_envs``, ``num_obs``,
 ``num_privileged_obs``, ``num_actions``, ``max_episode_length``, ``episode_length_buf``, ``extras``, ``device``,
-``get_observations``, ``reset``).  Per policy step it issues
+``get_observations``, ``reset``).  Per policy step it makes ONE C-ABI call, b200_env_step, which launches
 
-    b200_dynamics_step   (clip/shift actions, 4 x [PD torque + rigid-body substep])
-    b200_env_post_step   (fused post_physics_step)
+    dynamics_step_kernel   (clip/shift actions, 4 x [PD torque + rigid-body substep])
+    history_shift_kernel   (side stream, in the shadow of the dynamics kernel)
+    env_post_step_kernel   (fused post_physics_step)
+    stats_finalize_kernel
 
 and nothing else on the GPU; there is no host synchronisation inside ``step`` (SURVEY 8b "Threading").
 """
@@ -112,6 +114,18 @@ class FusedLeggedEnv:
 
     # ------------------------------------------------------------------ VecEnv API
     def step(self, actions: torch.Tensor):
+        """LeggedRobot.step: one C-ABI call (b200_env_step) = _pre_sim_step + simulator.step + post_physics_step:
+        dynamics kernel -> env kernel, with the frame-stack shift on a side stream under the dynamics kernel."""
+        self.common_step_counter += 1
+        self._apply_pending_curriculum()
+        self._set_step_flags()
+        self.simulator.fused_env_step(actions, self.common_step_counter, self.command_ranges["lin_vel_x"])
+        self._fill_extras()
+        return self._returns()
+
+    def step_two_kernels(self, actions: torch.Tensor):
+        """The same step call by call (b200_dynamics_step, b200_history_shift, b200_env_post_step): what the plugin path
+        does between `Simulator.step` and `post_physics_step`; kept for per-kernel timing and as a cross-check."""
         sim = self.simulator
         sim.step(actions)                                      # _pre_sim_step + simulator.step
         self.common_step_counter += 1

@@ -366,3 +366,26 @@ def test_short_rollout_against_oracle(golden):
         same = ~o["reset_buf"]
         worst = max(worst, float(np.abs(out[0].cpu().numpy() - o["obs_buf"])[same].max()))
     assert worst < 5e-2, f"5-step rollout observation drift {worst:.3e}"
+
+
+def test_one_call_host_step_equals_the_three_call_step(golden):
+    """b200_env_step (pinned host actions in, rew / reset / time_out out, ONE C-ABI call) is bit-identical to the step
+    made call by call (b200_dynamics_step, b200_history_shift, b200_env_post_step)."""
+    g, s0, spec, terrain = golden
+    N = 512
+    rng = np.random.default_rng(2)
+    a_env, b_env = _env(spec, N, terrain), _env(spec, N, terrain)
+    a_env.reset(); b_env.reset()
+    rew = torch.empty(N, dtype=torch.float32).pin_memory()
+    rst = torch.empty(N, dtype=torch.bool).pin_memory()
+    tmo = torch.empty(N, dtype=torch.bool).pin_memory()
+    for t in range(6):
+        act = torch.from_numpy(rng.normal(size=(N, spec.num_actions)).astype(np.float32)).pin_memory()
+        out_a = a_env.step_two_kernels(act.cuda())
+        out_b = b_env.step_host(act, rew, rst, tmo)
+        torch.cuda.synchronize()
+        for x, y in zip(out_a[:6], out_b[:6]):
+            assert torch.equal(x, y)
+        assert torch.equal(rew, a_env.rew_buf.cpu()) and torch.equal(rst, a_env.reset_buf.cpu()) and torch.equal(tmo, a_env.time_out_buf.cpu())
+    with pytest.raises(ValueError):
+        b_env.step_host(torch.zeros(N, spec.num_actions))          # pageable host memory is refused, not silently staged

@@ -100,3 +100,4 @@ def test_emulated_dynamics_kernel_matches_oracle():
     assert np.array_equal(sim.buf["last_actions"], before["actions"])
     assert np.array_equal(sim.buf["llast_actions"], before["last_actions"])
     assert np.array_equal(sim.buf["last_dof_vel"], before["dof_vel"])
+

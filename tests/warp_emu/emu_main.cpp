@@ -74,5 +74,6 @@ int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int row
     return g_env_preset;
 }
 void emu_set_env_specialized(int on) { g_env_specialized = on; }
+
 #endif
 }
