@@ -208,16 +208,15 @@ def run_gpu(args):
         launches += K
         t_shift = sum(e[0].elapsed_time(e[1]) for e in evs) / K
     # ---- end to end through the public API with host buffers
-    rew_host = torch.empty(N, dtype=torch.float32).pin_memory()
-    rst_host = torch.empty(N, dtype=torch.bool).pin_memory()
-    # FusedLeggedEnv.step_host = ONE C-ABI call (b200_env_step): H2D of the pinned actions, the kernels, D2H of rew / reset
+    rew_host, rst_host, tmo_host = sim.make_host_step_buffers()       # one pinned slab: rew f32[N] | reset u8[N] | time_out u8[N]
+    # FusedLeggedEnv.step_host = ONE C-ABI call (b200_env_step): H2D of the pinned actions, the kernels, one D2H of the slab
     for i in range(W):
-        env.step_host(host_pool[i % 16], rew_host, rst_host)
+        env.step_host(host_pool[i % 16], rew_host, rst_host, tmo_host)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        env.step_host(host_pool[(W + i) % 16], rew_host, rst_host)
+        env.step_host(host_pool[(W + i) % 16], rew_host, rst_host, tmo_host)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -256,7 +255,7 @@ def run_gpu(args):
                    "envs_per_gpu": N, "decimation": spec.decimation, "pgs_iterations": spec.pgs_iterations,
                    "actions": "N(0,1) (policy at init)", "l2": "flushed between timed steps (256 MB write)",
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": N * spec.num_actions * 4 * world, "d2h_bytes_per_step": N * 5 * world,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": N * spec.num_actions * 4 * world, "d2h_bytes_per_step": N * 6 * world,
                 "ms_per_step": e2e_ms / K},
         "gpu_launches": int(launches),
         "clocks": clocks,

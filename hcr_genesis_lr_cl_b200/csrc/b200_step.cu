@@ -40,6 +40,7 @@ struct B200Handle {
     int preshift_parity = -1;      // parity the stacks have been shifted for (-1: none pending)
     int env_preset = -1;           // instantiation of the env kernel: index into env_presets.inc, -1 = generic
     float *d_actions = nullptr;    // staging of b200_env_step's host actions
+    bool stats_zeroed = false;     // the dynamics kernel of this step already cleared the env kernel's reduction area
 };
 
 typedef void (*EnvKernelFn)(const TaskDev, const B200Buffers, const TerrainDev, const EnvCall, const EnvStageTab);
@@ -144,6 +145,7 @@ int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
     if (h->task.i[TI_C] == 4) dynamics_step_kernel<4><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions);
     else dynamics_step_kernel<2><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions);
     h->launches++;
+    h->stats_zeroed = true;
     CK(cudaGetLastError());
     return 0;
 }
@@ -189,26 +191,24 @@ static EnvCall make_call(B200Handle *h, long long step, float lo, float span, in
     for (int k = 0; k < 8; k++) call.beh[k] = h->beh[k];
     call.gait_cb = h->gait_cb; call.gait_reset = h->gait_reset;
     call.preshifted = 0;
+    // extras["episode"] means are finalised by the env kernel's last CTA when the reset phase ran for real
+    const int N = h->task.i[TI_NUM_ENVS];
+    const int n_teach = max(0, min(N, h->task.i[TI_NUM_TEACHER] - h->task.i[TI_ENV_OFFSET]));   // go2_cts: teacher envs of this rank
+    call.finalize = ((mask & PHASE_RESET) && !force) ? 1 : 0;
+    call.stats_slot = (int)(step % ENV_STATS_RING);
+    call.inv_episode_length_s = 1.0f / h->task.f[TF_EPISODE_LENGTH_S];
+    call.inv_num_envs = 1.0f / (float)N;
+    call.inv_teacher = h->task.i[TI_NUM_TEACHER] > 0 ? 1.0f / (float)max(n_teach, 1) : 0.f;
+    call.inv_student = 1.0f / (float)max(N - n_teach, 1);
     return call;
-}
-
-static int finalize_stats(B200Handle *h, long long step, cudaStream_t s) {
-    const int N = h->task.i[TI_NUM_ENVS], n_sums = h->task.i[TI_N_SUMS];
-    // go2_cts: this rank's teacher envs are the global ids [0, num_teacher) that fall inside its block
-    const int n_teach = max(0, min(N, h->task.i[TI_NUM_TEACHER] - h->task.i[TI_ENV_OFFSET]));
-    const float inv_t = h->task.i[TI_NUM_TEACHER] > 0 ? 1.0f / (float)max(n_teach, 1) : 0.f, inv_s = 1.0f / (float)max(N - n_teach, 1);
-    stats_finalize_kernel<<<1, 64, 0, s>>>(h->bufs.stats, n_sums, 1.0f / h->task.f[TF_EPISODE_LENGTH_S], 1.0f / (float)N, inv_t, inv_s,
-                                           (int)(step % ENV_STATS_RING));
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
 }
 
 static int launch_env(B200Handle *h, long long step, float lo, float span, int parity, int mask, int force, void *stream) {
     const int N = h->task.i[TI_NUM_ENVS];
     const int n_sums = h->task.i[TI_N_SUMS];
     cudaStream_t s = (cudaStream_t)stream;
-    if (mask & PHASE_RESET) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 4), s));
+    if ((mask & PHASE_RESET) && !h->stats_zeroed) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 4), s));
+    h->stats_zeroed = false;
     EnvCall call = make_call(h, step, lo, span, parity, mask, force);
     if (h->preshift_parity >= 0) {                   // join the side stream; use its work only if it was for this parity and phase set
         if (h->preshift_on_side) CK(cudaStreamWaitEvent(s, h->ev_join, 0));
@@ -219,7 +219,6 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     env_kernel_fn(h->env_preset)<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call, h->stage);
     h->launches++;
     CK(cudaGetLastError());
-    if ((mask & PHASE_RESET) && !force) return finalize_stats(h, step, s);
     return 0;
 }
 
@@ -244,9 +243,17 @@ int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long
     if (b200_dynamics_step(h, dev_actions, stream)) return 1;
     if (b200_history_shift(h, parity, stream)) return 1;
     if (launch_env(h, step, lo, span, parity, PHASE_ALL, 0, stream)) return 1;
-    if (host_rew) CK(cudaMemcpyAsync(host_rew, h->bufs.rew_buf, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));
-    if (host_reset) CK(cudaMemcpyAsync(host_reset, h->bufs.reset_buf, (size_t)N, cudaMemcpyDeviceToHost, s));
-    if (host_time_out) CK(cudaMemcpyAsync(host_time_out, h->bufs.time_out_buf, (size_t)N, cudaMemcpyDeviceToHost, s));
+    // rew | reset | time_out laid out back to back on both sides (B200Simulator allocates them so): one copy
+    const uint8_t *d_rew = (const uint8_t *)h->bufs.rew_buf;
+    const bool packed = host_rew && host_reset && host_time_out && h->bufs.reset_buf == d_rew + 4 * (size_t)N &&
+                        h->bufs.time_out_buf == d_rew + 5 * (size_t)N && host_reset == (uint8_t *)host_rew + 4 * (size_t)N &&
+                        host_time_out == (uint8_t *)host_rew + 5 * (size_t)N;
+    if (packed) CK(cudaMemcpyAsync(host_rew, d_rew, 6 * (size_t)N, cudaMemcpyDeviceToHost, s));
+    else {
+        if (host_rew) CK(cudaMemcpyAsync(host_rew, h->bufs.rew_buf, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));
+        if (host_reset) CK(cudaMemcpyAsync(host_reset, h->bufs.reset_buf, (size_t)N, cudaMemcpyDeviceToHost, s));
+        if (host_time_out) CK(cudaMemcpyAsync(host_time_out, h->bufs.time_out_buf, (size_t)N, cudaMemcpyDeviceToHost, s));
+    }
     return 0;
 }
 
@@ -289,5 +296,14 @@ int b200_kernel_info(B200Handle *h, const char *kernel, int *regs, int *smem, in
 }
 
 long long b200_launch_count(B200Handle *h) { return h ? h->launches : 0; }
+
+#ifdef DYN_TIMING
+/* diagnosis build only (-DDYN_TIMING, tools/probe_dyn_timing.py): per-env {start ns, end ns, sweeps, sweep-rows} of the last launch */
+int b200_debug_dyn_timing(unsigned long long *out, int n_envs) {
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out, g_dyn_timing, sizeof(unsigned long long) * 4 * (size_t)n_envs));
+    return 0;
+}
+#endif
 
 }  // extern "C"

@@ -91,6 +91,10 @@ static_assert(WS_AUX + 32 <= WS_MI, "aliased inputs must fit under the A matrix"
 
 __host__ __device__ inline int dyn_smem_bytes(int warps) { return (MS_TOTAL + warps * WS_TOTAL) * 4; }
 
+#ifdef DYN_TIMING     // diagnosis build (tools/probe_dyn_timing.py): per-env start / end time, sweeps, rows
+__device__ unsigned long long g_dyn_timing[65536 * 4];
+__device__ __forceinline__ unsigned long long dyn_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 struct SIn { float m; f3 h; float I[6]; };  // spatial inertia about O: I = xx yy zz xy xz yz
 
 __device__ __forceinline__ void si_apply(const SIn &s, f3 w, f3 v, f3 &L, f3 &P) {
@@ -224,6 +228,10 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     const bool leg = lane < C;
     const int c = leg ? lane : C - 1;       // chain walked by this lane (lanes >= C shadow the last chain, results masked)
 
+#ifdef DYN_TIMING
+    const unsigned long long t_begin = dyn_now();
+    unsigned dbg_sweeps = 0, dbg_rows = 0;
+#endif
     // ---------------- load state ----------------
     f3 p = mk3(B.base_pos[env * 3], B.base_pos[env * 3 + 1], B.base_pos[env * 3 + 2]);
     float Qw = B.base_quat_wxyz[env * 4], Qx = B.base_quat_wxyz[env * 4 + 1], Qy = B.base_quat_wxyz[env * 4 + 2], Qz = B.base_quat_wxyz[env * 4 + 3];
@@ -702,6 +710,9 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             }
             // convergence: largest change of any row over the sweep relative to the largest force (warp-uniform exit)
             const float dmax = warp_max_nonneg(fabsf(f - fprev)), fmx = warp_max_nonneg(fabsf(f));
+#ifdef DYN_TIMING
+            dbg_sweeps++; dbg_rows += R;
+#endif
             if (dmax <= tf[TF_PGS_TOL] * (1.f + fmx)) break;
         }
         __syncwarp();
@@ -767,6 +778,9 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         __syncwarp();
     }
 
+#ifdef DYN_TIMING
+    if (lane == 0 && env < 65536) { g_dyn_timing[env * 4] = t_begin; g_dyn_timing[env * 4 + 1] = dyn_now(); g_dyn_timing[env * 4 + 2] = dbg_sweeps; g_dyn_timing[env * 4 + 3] = dbg_rows; }
+#endif
     // ---------------- write back (frames/velocities of the final state are in shared memory) ----------------
     if (lane < 3) {
         B.base_pos[env * 3 + lane] = comp3(p, lane);
@@ -819,6 +833,9 @@ dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, con
     extern __shared__ float smem[];
     float *ms = smem;
     stage_model(M, T, ms);
+    // the per-step reduction area of the env kernel that follows (episode sums, reset count, level sums): zeroed here so
+    // that the step needs no memset node between the kernels
+    if (blockIdx.x == 0 && (int)threadIdx.x < T.i[TI_N_SUMS] + 4) B.stats[threadIdx.x] = 0.f;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * (blockDim.x >> 5) + warp;

@@ -68,6 +68,9 @@ struct EnvCall {
     float beh[8];        // go2_wtw behaviour ranges {gait period, base height, foot clearance, pitch} x {lo, span}
     int gait_cb, gait_reset;   // gait index the host drew for the callback / reset resampling of this step
     int preshifted;      // history_shift_kernel already moved the kept frames of both stacks for this parity
+    // extras["episode"] means: the last CTA to finish turns the per-step reductions into ring slot `stats_slot`
+    int finalize, stats_slot;
+    float inv_episode_length_s, inv_num_envs, inv_teacher, inv_student;
 };
 
 // shared memory per CTA: mbarrier + per warp (scratch, staged input rows)
@@ -957,6 +960,20 @@ inline EnvStageTab env_stage_table(const TaskDev &T, const B200Buffers &B, int n
     return tab;
 }
 
+// extras["episode"] (legged_robot.py:127-141): means over the envs that reset this step, from the reductions the env
+// kernel left in stats[0..n_sums] (+ reset count, + sum of terrain levels); written to slot (step % ENV_STATS_RING) of
+// the ring that follows the work area so that the host can hand out per-step values without any further launch.
+// Run by the last CTA of env_post_step_kernel (thread i < n_sums + B200_STATS_EXTRA writes entry i).
+__device__ __forceinline__ void stats_finalize(float *stats, int n_sums, const EnvCall &call, int i) {
+    float *ring = stats + (2 * n_sums + 4) + call.stats_slot * (n_sums + B200_STATS_EXTRA);
+    const float cnt = fmaxf(__ldcg(stats + n_sums), 1.0f);
+    if (i < n_sums) ring[i] = __ldcg(stats + i) / cnt * call.inv_episode_length_s;
+    if (i == n_sums) ring[i] = __ldcg(stats + n_sums + 1) * call.inv_num_envs;            // mean terrain level
+    if (i == n_sums + 1) ring[i] = call.inv_teacher > 0.f ? __ldcg(stats + n_sums + 3) * call.inv_teacher     // go2_cts: teacher terrain level
+                                                          : __ldcg(stats + n_sums + 2) * call.inv_num_envs;   // mean CaT termination probability
+    if (i == n_sums + 2) ring[i] = (__ldcg(stats + n_sums + 1) - __ldcg(stats + n_sums + 3)) * call.inv_student;  // go2_cts: student terrain level
+}
+
 template <class S>
 __device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const EnvCall &call, const EnvStageTab &tab) {
     extern __shared__ float smem[];
@@ -984,10 +1001,21 @@ __device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200B
         ENV_STAGED_INPUTS(X_VIEW, ti[TI_A], ti[TI_F], ti[TI_L], ti[TI_N_SUMS])
 #undef X_VIEW
         env_post_step_warp<S>(T, B, R, tr, call, es + warp * ES_TOTAL, env, lane, true, bar);
-        return;
+    } else if (env < N) {
+        env_post_step_warp<S>(T, B, B, tr, call, es + warp * ES_TOTAL, env, lane, false, bar);
     }
-    if (env >= N) return;
-    env_post_step_warp<S>(T, B, B, tr, call, es + warp * ES_TOTAL, env, lane, false, bar);
+    if (call.finalize) {       // CTA-uniform.  The CTA that takes the last ticket sees every CTA's reductions (fence + atomic)
+        int *last = (int *)(smem + 2);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) *last = atomicAdd(B.global_flags + 1, 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (*last) {
+            __threadfence();
+            stats_finalize(B.stats, ti[TI_N_SUMS], call, (int)threadIdx.x);
+            if (threadIdx.x == 0) B.global_flags[1] = 0;
+        }
+    }
 }
 
 // generic instantiation: every descriptor int is read at run time (any task configuration)
@@ -1013,17 +1041,3 @@ inline int env_match_preset(const int *ti) {
     return -1;
 }
 
-// extras["episode"] (legged_robot.py:127-141): means over the envs that reset this step, from the reductions the env
-// kernel left in stats[0..n_sums] (+ reset count, + sum of terrain levels); written to slot (step % ENV_STATS_RING) of
-// the ring that follows the work area so that the host can hand out per-step values without any further launch.
-__global__ void stats_finalize_kernel(float *stats, int n_sums, float inv_episode_length_s, float inv_num_envs, float inv_teacher,
-                                      float inv_student, int slot) {
-    const int i = threadIdx.x;
-    float *ring = stats + (2 * n_sums + 4) + slot * (n_sums + B200_STATS_EXTRA);
-    const float cnt = fmaxf(stats[n_sums], 1.0f);
-    if (i < n_sums) ring[i] = stats[i] / cnt * inv_episode_length_s;
-    if (i == n_sums) ring[i] = stats[n_sums + 1] * inv_num_envs;            // mean terrain level
-    if (i == n_sums + 1) ring[i] = inv_teacher > 0.f ? stats[n_sums + 3] * inv_teacher     // go2_cts: teacher terrain level
-                                                     : stats[n_sums + 2] * inv_num_envs;   // mean CaT termination probability
-    if (i == n_sums + 2) ring[i] = (stats[n_sums + 1] - stats[n_sums + 3]) * inv_student;  // go2_cts: student terrain level
-}

@@ -7,8 +7,7 @@ legged_robot_ts.py:59-76): same return tuples, same attribute names the runners 
 
     dynamics_step_kernel   (clip/shift actions, 4 x [PD torque + rigid-body substep])
     history_shift_kernel   (side stream, in the shadow of the dynamics kernel)
-    env_post_step_kernel   (fused post_physics_step)
-    stats_finalize_kernel
+    env_post_step_kernel   (fused post_physics_step; its last CTA finalises extras["episode"])
 
 and nothing else on the GPU; there is no host synchronisation inside ``step`` (SURVEY 8b "Threading").
 """
@@ -234,7 +233,7 @@ class FusedLeggedEnv:
 
     def _fill_extras(self):
         """extras["episode"]["rew_*"] = mean over resetting envs of episode_sums / episode_length_s
-        (legged_robot.py:127-141): computed on the device by stats_finalize_kernel into slot step % 32."""
+        (legged_robot.py:127-141): computed on the device by the env kernel's last CTA into slot step % 32."""
         from ._cabi import STATS_RING
         n = len(self.sum_names)
         stats = self._b["stats"]

@@ -149,10 +149,15 @@ class B200Simulator:
                                                 self._terrain_origins.data_ptr(), lv, ty))
         # device buffers
         self._buf = {}
+        # rew_buf | reset_buf | time_out_buf share one allocation (4N + N + N bytes) so that b200_env_step can hand all three
+        # to the host with a single device->host copy
+        self._step_out = torch.zeros(6 * N, dtype=torch.uint8, device=self._tdev)
+        shared = {"rew_buf": self._step_out[:4 * N].view(torch.float32), "reset_buf": self._step_out[4 * N:5 * N],
+                  "time_out_buf": self._step_out[5 * N:]}
         for name, (shape, dt) in _cabi.buffer_shapes(s, m, N).items():
             if name == "height_cells" and not self._debug_cells:
                 continue
-            self._buf[name] = torch.zeros(shape, dtype=_TORCH_DT[np.dtype(dt)], device=self._tdev)
+            self._buf[name] = shared[name] if name in shared else torch.zeros(shape, dtype=_TORCH_DT[np.dtype(dt)], device=self._tdev)
         b = self._buf
         b["base_quat_wxyz"][:, 0] = 1.0
         b["base_quat"][:, 3] = 1.0
@@ -265,6 +270,13 @@ class B200Simulator:
                                               mask, self._stream()))
         if mask & H["PHASE_OBSERVE"]:
             self._parity ^= 1
+
+    def make_host_step_buffers(self):
+        """Pinned host (rew [N] f32, reset [N] bool, time_out [N] bool) carved from one slab laid out like the device side,
+        so that b200_env_step moves all three with one copy."""
+        N = self._num_envs
+        slab = torch.zeros(6 * N, dtype=torch.uint8).pin_memory()
+        return slab[:4 * N].view(torch.float32), slab[4 * N:5 * N].view(torch.bool), slab[5 * N:].view(torch.bool)
 
     def fused_env_step(self, actions, step_counter: int, cmd_range_x: Sequence[float], host_rew=None, host_reset=None,
                        host_time_out=None):

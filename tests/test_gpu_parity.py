@@ -326,7 +326,7 @@ def test_full_size_properties():
         assert torch.equal(sa[k][half:], sc[k]), f"shard != full job for {k}"
     assert torch.isfinite(sa["obs_buf"]).all() and torch.isfinite(sa["rew_buf"]).all()
     assert sa["height_cells"].min() >= 0 and sa["height_cells"].max() <= 1198
-    assert env_a.simulator.launch_count == 1 + 4 * (len(acts) + 1)     # reset_all + (dynamics, history shift, env, stats finalize) per step
+    assert env_a.simulator.launch_count == 1 + 3 * (len(acts) + 1)     # reset_all + (dynamics, history shift, env) per step
 
 
 def test_short_rollout_against_oracle(golden):
@@ -376,14 +376,16 @@ def test_one_call_host_step_equals_the_three_call_step(golden):
     rng = np.random.default_rng(2)
     a_env, b_env = _env(spec, N, terrain), _env(spec, N, terrain)
     a_env.reset(); b_env.reset()
-    rew = torch.empty(N, dtype=torch.float32).pin_memory()
-    rst = torch.empty(N, dtype=torch.bool).pin_memory()
-    tmo = torch.empty(N, dtype=torch.bool).pin_memory()
+    rew, rst, tmo = b_env.simulator.make_host_step_buffers()        # one slab -> one device->host copy per step
+    rew2 = torch.empty(N, dtype=torch.float32).pin_memory()         # separate buffers -> three copies; same values
+    rst2 = torch.empty(N, dtype=torch.bool).pin_memory()
     for t in range(6):
         act = torch.from_numpy(rng.normal(size=(N, spec.num_actions)).astype(np.float32)).pin_memory()
         out_a = a_env.step_two_kernels(act.cuda())
-        out_b = b_env.step_host(act, rew, rst, tmo)
+        out_b = b_env.step_host(act, rew, rst, tmo) if t % 2 == 0 else b_env.step_host(act, rew2, rst2, tmo)
         torch.cuda.synchronize()
+        if t % 2:
+            rew.copy_(rew2); rst.copy_(rst2)
         for x, y in zip(out_a[:6], out_b[:6]):
             assert torch.equal(x, y)
         assert torch.equal(rew, a_env.rew_buf.cpu()) and torch.equal(rst, a_env.reset_buf.cpu()) and torch.equal(tmo, a_env.time_out_buf.cpu())

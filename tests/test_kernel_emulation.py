@@ -74,6 +74,13 @@ def _run_golden(name, steps, preshift, specialized=True):
             assert np.allclose(sim.critic_obs, g[f"hist{t}/critic_obs_buf"], rtol=1e-4, atol=1e-5)
         n = len(spec.episode_sum_names())
         assert B["stats"][n] == ref["reset_buf"].sum()            # reset counter of the per-step reductions
+        # the last block finalised extras["episode"] into the ring slot of this step and re-armed the ticket counter
+        assert B["global_flags"][1] == 0
+        ring = B["stats"][2 * n + 4 + (sim.step_counter % 32) * (n + 3):][:n + 3]
+        cnt = max(float(ref["reset_buf"].sum()), 1.0)
+        assert np.allclose(ring[:n], B["stats"][:n] / cnt / np.float32(spec.episode_length_s), rtol=1e-6, atol=0)
+        if spec.terrain_curriculum:
+            assert np.isclose(ring[n], B["terrain_levels"].mean(), rtol=1e-5)
 
 
 def test_emulated_dynamics_kernel_matches_oracle():

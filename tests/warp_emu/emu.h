@@ -50,6 +50,8 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T __ldcs(const T *p) { return *p; }
+template <typename T> static inline T __ldcg(const T *p) { return *p; }
+static inline void __threadfence() {}
 #define __restrict__
 static inline int __float_as_int(float v) { return (int)emu_bits(v); }
 static inline float __int_as_float(int v) { return emu_float((uint32_t)v); }

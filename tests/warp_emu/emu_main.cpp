@@ -60,6 +60,10 @@ int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int row
     a.call.gait_cb = gait_cb; a.call.gait_reset = gait_reset;
     a.tab = env_stage_table(a.T, a.B, 1);          // the emulator runs one warp per block
     a.call.preshifted = 0;
+    a.call.finalize = (!force_reset && (phase_mask & PHASE_RESET)) ? 1 : 0;      // like make_call in csrc/b200_step.cu
+    a.call.stats_slot = (int)(step % ENV_STATS_RING);
+    a.call.inv_episode_length_s = 1.0f / a.T.f[TF_EPISODE_LENGTH_S]; a.call.inv_num_envs = 1.0f / (float)a.T.i[TI_NUM_ENVS];
+    a.call.inv_teacher = 0.f; a.call.inv_student = 1.0f / (float)a.T.i[TI_NUM_ENVS];
     if (preshift && a.T.i[TI_OBS_KIND] >= 1 && !force_reset && (phase_mask & PHASE_OBSERVE)) {   // what b200_history_shift launches
         static ShiftArgs sh;
         const int p = parity & 1;
