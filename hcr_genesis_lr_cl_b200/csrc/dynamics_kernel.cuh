@@ -827,6 +827,17 @@ __device__ __forceinline__ void stage_model(const ModelDev &M, const TaskDev &T,
     for (int e = threadIdx.x; e < NS; e += blockDim.x) { msi[B200_MAX_LINKS + e] = M.sph_body[e]; msi[B200_MAX_LINKS + B200_MAX_SPHERES + e] = M.sph_link[e]; }
 }
 
+// ragged last CTA: idle warps still take part in the phase barriers of dynamics_warp (1 + 4 per substep, 1 in the last pass)
+__device__ __forceinline__ void dynamics_idle_warp(const TaskDev &T) {
+#ifndef DYN_NO_PHASE_SYNC
+    for (int sub = 0; sub <= T.i[TI_DECIMATION]; sub++) {
+        __syncthreads();
+        if (sub == T.i[TI_DECIMATION]) break;
+        __syncthreads(); __syncthreads(); __syncthreads(); __syncthreads();
+    }
+#endif
+}
+
 template <int C>
 __global__ void B200_LAUNCH_BOUNDS(DYN_WARPS_PER_BLOCK * 32, DYN_MIN_BLOCKS)
 dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, const TerrainDev tr, const float *actions) {
@@ -839,16 +850,6 @@ dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, con
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (env >= T.i[TI_NUM_ENVS]) {
-#ifndef DYN_NO_PHASE_SYNC
-        // ragged last CTA: idle warps still take part in the phase barriers of dynamics_warp (1 + 4 per substep, 1 in the last pass)
-        for (int sub = 0; sub <= T.i[TI_DECIMATION]; sub++) {
-            __syncthreads();
-            if (sub == T.i[TI_DECIMATION]) break;
-            __syncthreads(); __syncthreads(); __syncthreads(); __syncthreads();
-        }
-#endif
-        return;
-    }
+    if (env >= T.i[TI_NUM_ENVS]) { dynamics_idle_warp(T); return; }
     dynamics_warp<C>(T, B, tr, ms, smem + MS_TOTAL + warp * WS_TOTAL, actions, env, lane);
 }

@@ -194,7 +194,7 @@ history_shift_kernel(const float *in_h, float *out_h, long long Mh, int fh, cons
 // instead of one per dependent load.  All stores go to B (global memory).
 template <class S>
 __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const B200Buffers &R, const TerrainDev &tr, const EnvCall &call,
-                                   float *es, int env, int lane, bool staged, uint64_t *bar) {
+                                   float *es, int env, int lane, bool staged, bool cta_sync, uint64_t *bar) {
     const float *tf = T.f;
     const TiView<S> ti{T.i};
     const int A = ti[TI_A], F = ti[TI_F], L = ti[TI_L], P = ti[TI_PX] * ti[TI_PY];
@@ -207,7 +207,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     // an SM then walk the (several hundred KB of) straight-line code together and share instruction-cache lines instead
     // of each missing on its own (ncu: `no_instruction` was the second-largest stall).  Uniform per CTA by construction.
 #ifndef ENV_NO_SECTION_SYNC
-#define ENV_SECTION_SYNC() do { if (staged) __syncthreads(); } while (0)
+#define ENV_SECTION_SYNC() do { if (cta_sync) __syncthreads(); } while (0)
 #else
 #define ENV_SECTION_SYNC()
 #endif
@@ -974,6 +974,20 @@ __device__ __forceinline__ void stats_finalize(float *stats, int n_sums, const E
     if (i == n_sums + 2) ring[i] = (__ldcg(stats + n_sums + 1) - __ldcg(stats + n_sums + 3)) * call.inv_student;  // go2_cts: student terrain level
 }
 
+// The CTA that takes the last ticket sees every CTA's reductions (fence + atomic) and finalises them.  Called by every
+// thread of every CTA; `last` is one shared-memory word nobody else uses at this point.
+__device__ __forceinline__ void env_finalize_cta(const B200Buffers &B, int n_sums, const EnvCall &call, int *last) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *last = atomicAdd(B.global_flags + 1, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (*last) {
+        __threadfence();
+        stats_finalize(B.stats, n_sums, call, (int)threadIdx.x);
+        if (threadIdx.x == 0) B.global_flags[1] = 0;
+    }
+}
+
 template <class S>
 __device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const EnvCall &call, const EnvStageTab &tab) {
     extern __shared__ float smem[];
@@ -1000,22 +1014,11 @@ __device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200B
 #define X_VIEW(field, type, k) { if (tab.off[t] != ENV_NOT_STAGED) R.field = (type *)(inslab + tab.off[t]) - (size_t)env0 * (k); t++; }
         ENV_STAGED_INPUTS(X_VIEW, ti[TI_A], ti[TI_F], ti[TI_L], ti[TI_N_SUMS])
 #undef X_VIEW
-        env_post_step_warp<S>(T, B, R, tr, call, es + warp * ES_TOTAL, env, lane, true, bar);
+        env_post_step_warp<S>(T, B, R, tr, call, es + warp * ES_TOTAL, env, lane, true, true, bar);
     } else if (env < N) {
-        env_post_step_warp<S>(T, B, B, tr, call, es + warp * ES_TOTAL, env, lane, false, bar);
+        env_post_step_warp<S>(T, B, B, tr, call, es + warp * ES_TOTAL, env, lane, false, false, bar);
     }
-    if (call.finalize) {       // CTA-uniform.  The CTA that takes the last ticket sees every CTA's reductions (fence + atomic)
-        int *last = (int *)(smem + 2);
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) *last = atomicAdd(B.global_flags + 1, 1) == (int)gridDim.x - 1;
-        __syncthreads();
-        if (*last) {
-            __threadfence();
-            stats_finalize(B.stats, ti[TI_N_SUMS], call, (int)threadIdx.x);
-            if (threadIdx.x == 0) B.global_flags[1] = 0;
-        }
-    }
+    if (call.finalize) env_finalize_cta(B, ti[TI_N_SUMS], call, (int *)(smem + 2));
 }
 
 // generic instantiation: every descriptor int is read at run time (any task configuration)
