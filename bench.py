@@ -151,6 +151,16 @@ def run_gpu(args):
     pool = [torch.randn(N, spec.num_actions, generator=g).to(dev) for _ in range(16)]          # policy at init: N(0,1) actions
     host_pool = [p.cpu().pin_memory() for p in pool]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)                    # > 126 MB L2
+    flush_rd = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)                # 256 MB, only ever read
+    sink = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def flush_l2():
+        """Evict the step's working set: write 256 MB, then read another 256 MB so that the L2 is left full of CLEAN
+        lines (after the write alone it is full of dirty zeros whose write-back competes with the timed kernels' reads:
+        a cold streaming copy then measures ~half of the HBM bandwidth, profiles/r1v_sweep_history_shift.log)."""
+        flush.zero_()
+        sink.copy_(flush_rd.sum())
+
     K, W = args.steps, args.warmup
 
     def barrier():
@@ -168,7 +178,7 @@ def run_gpu(args):
         sampler.start()
     launches0 = sim.launch_count
     for i in range(K):
-        flush.zero_()
+        flush_l2()
         evf[i][0].record()
         env.step(pool[(W + i) % 16])
         evf[i][1].record()
@@ -179,7 +189,7 @@ def run_gpu(args):
     # explain the fused number and give the env kernel's own HBM figure
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     for i in range(K):
-        flush.zero_()
+        flush_l2()
         a = pool[(W + i) % 16]
         ev[i][0].record()
         sim.step(a)
@@ -200,7 +210,7 @@ def run_gpu(args):
     if env.widths["hist"]:
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
         for i in range(K):
-            flush.zero_()
+            flush_l2()
             evs[i][0].record()
             sim.history_shift(side_stream=False)
             evs[i][1].record()
@@ -253,7 +263,7 @@ def run_gpu(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.task}: {WORKLOADS[args.task]}, {N} envs/GPU",
                    "envs_per_gpu": N, "decimation": spec.decimation, "pgs_iterations": spec.pgs_iterations,
-                   "actions": "N(0,1) (policy at init)", "l2": "flushed between timed steps (256 MB write)",
+                   "actions": "N(0,1) (policy at init)", "l2": "flushed between timed steps (256 MB write, then 256 MB read: no dirty lines left)",
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": N * spec.num_actions * 4 * world, "d2h_bytes_per_step": N * 6 * world,
                 "ms_per_step": e2e_ms / K},
@@ -270,7 +280,7 @@ def run_gpu(args):
                      "kernel, stats finalize; the entries below are a second loop that times the kernels call by call"},
             "dynamics_step_kernel": {"avg_ms": t_dyn, "share": t_dyn / (t_dyn + t_env), "bound": "latency/issue", **ki_dyn,
                                      "algorithmic_bytes_per_launch": dyn_bytes, "hbm_gbs": dyn_bytes / (t_dyn * 1e-3) / 1e9},
-            "env_post_step_kernel": {"avg_ms": t_env, "share": t_env / (t_dyn + t_env), "bound": "latency/issue", **ki_env,
+            "env_post_step_kernel": {"variant": sim.env_kernel_variant, "avg_ms": t_env, "share": t_env / (t_dyn + t_env), "bound": "latency/issue", **ki_env,
                                      "algorithmic_bytes_per_launch": env_bytes, "hbm_gbs": env_bytes / (t_env * 1e-3) / 1e9},
             "history_shift_kernel": {"avg_ms_alone": t_shift, "bound": "hbm", "algorithmic_bytes_per_launch": shift_bytes,
                                      "hbm_gbs": (shift_bytes / (t_shift * 1e-3) / 1e9) if t_shift else None,

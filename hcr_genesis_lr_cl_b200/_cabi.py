@@ -299,6 +299,8 @@ def load_library() -> ctypes.CDLL:
     lib.b200_reset_all.restype = ctypes.c_int
     lib.b200_kernel_info.argtypes = [vp, ctypes.c_char_p, ip, ip, ip, ip]
     lib.b200_kernel_info.restype = ctypes.c_int
+    lib.b200_env_kernel_variant.argtypes = [vp]
+    lib.b200_env_kernel_variant.restype = ctypes.c_char_p
     lib.b200_launch_count.argtypes = [vp]
     lib.b200_launch_count.restype = ctypes.c_longlong
     lib.b200_last_error.argtypes = []
@@ -308,4 +310,4 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = ["b200_create", "b200_destroy", "b200_set_terrain", "b200_bind_buffers", "b200_dynamics_step",
-                    "b200_history_shift", "b200_set_history_side_stream", "b200_env_post_step", "b200_env_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_launch_count", "b200_last_error"]
+                    "b200_history_shift", "b200_set_history_side_stream", "b200_env_post_step", "b200_env_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_env_kernel_variant", "b200_launch_count", "b200_last_error"]

@@ -8,6 +8,9 @@
 #include "dynamics_kernel.cuh"
 #include "env_kernel.cuh"
 
+#ifndef HIST_SHIFT_GRID_PER_SM
+#define HIST_SHIFT_GRID_PER_SM 8       // cap of history_shift_kernel's grid.x per SM (grid-stride loop beyond)
+#endif
 static thread_local std::string g_err;
 static int fail(const char *what, cudaError_t e = cudaSuccess) {
     g_err = what;
@@ -169,7 +172,7 @@ int b200_history_shift(B200Handle *h, int parity, void *stream) {
     // one warp-iteration moves 32 x HIST_SHIFT_UNROLL vectors; enough blocks for the larger stack, capped at a few per SM
     const long long per_block = (long long)(HIST_SHIFT_BLOCK / 32) * 32 * HIST_SHIFT_UNROLL * 4;
     long long blocks = ((Mh > Mc ? Mh : Mc) + per_block - 1) / per_block;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 148 * HIST_SHIFT_GRID_PER_SM) blocks = 148 * HIST_SHIFT_GRID_PER_SM;
     if (blocks < 1) blocks = 1;
     history_shift_kernel<<<dim3((unsigned)blocks, 2), HIST_SHIFT_BLOCK, 0, run>>>(h->bufs.obs_history[p], h->bufs.obs_history[p ^ 1], Mh, ti[TI_NUM_OBS],
                                                                                  h->bufs.critic_obs[p], h->bufs.critic_obs[p ^ 1], Mc, ti[TI_SINGLE_CRITIC]);
@@ -294,6 +297,8 @@ int b200_kernel_info(B200Handle *h, const char *kernel, int *regs, int *smem, in
     if (block_threads) *block_threads = threads;
     return 0;
 }
+
+const char *b200_env_kernel_variant(B200Handle *h) { return (h && h->env_preset >= 0) ? kEnvPresetName[h->env_preset] : "generic"; }
 
 long long b200_launch_count(B200Handle *h) { return h ? h->launches : 0; }
 

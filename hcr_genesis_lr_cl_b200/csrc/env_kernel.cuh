@@ -133,8 +133,15 @@ __device__ __forceinline__ void history_append(float *dst, const float *src, int
 // harmless because env_post_step_kernel writes the new frame there (and clears the rows of envs that reset) before
 // anyone reads it.  So the kernel is a streaming copy: aligned 16-byte loads and stores, the (frame mod 4) words of
 // misalignment between source and destination are fixed up in registers with the neighbour lane's vector.
+#ifndef HIST_SHIFT_UNROLL
 #define HIST_SHIFT_UNROLL 4         // independent 16-byte loads in flight per thread
+#endif
+#ifndef HIST_SHIFT_BLOCK
 #define HIST_SHIFT_BLOCK 256
+#endif
+#ifndef HIST_SHIFT_MIN_BLOCKS
+#define HIST_SHIFT_MIN_BLOCKS 1
+#endif
 __device__ __forceinline__ void history_shift_flat(const float *__restrict__ in, float *__restrict__ out, long long M, int f) {
     if (M <= f) return;
     const int lane = threadIdx.x & 31;
@@ -182,19 +189,80 @@ __device__ __forceinline__ void history_shift_flat(const float *__restrict__ in,
     for (long long d = 4 * nvec + tid; d < M - f; d += nthreads) out[d] = __ldcs(in + d + f);
 }
 
-__global__ void B200_LAUNCH_BOUNDS(HIST_SHIFT_BLOCK, 1)
+__global__ void B200_LAUNCH_BOUNDS(HIST_SHIFT_BLOCK, HIST_SHIFT_MIN_BLOCKS)
 history_shift_kernel(const float *in_h, float *out_h, long long Mh, int fh, const float *in_c, float *out_c, long long Mc, int fc) {
     if (blockIdx.y == 0) history_shift_flat(in_h, out_h, Mh, fh);         // grid.y: 0 = obs_history, 1 = critic stack
     else history_shift_flat(in_c, out_c, Mc, fc);
 }
 
+// per-env input tensors staged per CTA: X(field, element type, elements per env)
+#define ENV_STAGED_INPUTS(X, A_, F_, L_, NS_)                                                                          \
+    X(base_pos, float, 3) X(base_quat_wxyz, float, 4) X(base_lin_w, float, 3) X(base_ang_w, float, 3) X(env_origins, float, 3) \
+    X(commands, float, 4) X(episode_length, int32_t, 1) X(fail_buf, int32_t, 1) X(terrain_levels, int64_t, 1)          \
+    X(terrain_types, int64_t, 1) X(rand_push_vels, float, 3) X(dof_pos, float, A_) X(dof_vel, float, A_)               \
+    X(actions, float, A_) X(last_actions, float, A_) X(llast_actions, float, A_) X(torques, float, A_)                 \
+    X(last_dof_vel, float, A_) X(feet_pos, float, 3 * F_) X(feet_vel, float, 3 * F_) X(last_feet_vel, float, 3 * F_)   \
+    X(link_contact_forces, float, 3 * L_) X(episode_sums, float, NS_) X(feet_air_time, float, F_)                      \
+    X(last_contacts, uint8_t, F_) X(friction, float, 1) X(added_mass, float, 1) X(com_bias, float, 3)                  \
+    X(kp_scale, float, A_) X(kd_scale, float, A_) X(gait_state, float, B200_GAIT_STATE)
+#define ENV_MAX_STAGED 40
+#define ENV_NOT_STAGED 0xFFFFFFFFu
+
+// The per-env inputs as the warp code reads them, `R.field[row * k + i]`: in a staged CTA the pointers lead into the
+// CTA's shared-memory slab that TMA filled and row = warp; otherwise they are the global tensors and row = env.
+#define X_DECL(field, type, k) const type *field;
+struct EnvInputs { ENV_STAGED_INPUTS(X_DECL, 0, 0, 0, 0) };
+#undef X_DECL
+
+// Byte offset of staged input `idx` inside a CTA's slab (ENV_NOT_STAGED when its CTA slice breaks the 16-byte rule of
+// cp.async.bulk or the slab is full -- that tensor is then read straight from global memory), and the bytes one CTA
+// brings in (idx = -1).  One definition for the host-built copy table and for the kernel: the specialised
+// instantiations fold the offsets into the load instructions.
+__host__ __device__ constexpr uint32_t env_stage_layout(int idx, int A, int F, int L, int NSUM, int nwarps) {
+    uint32_t off = 0, total = 0, res = ENV_NOT_STAGED;
+    int t = 0;
+#define X_LAY(field, type, k) { const uint32_t b_ = (uint32_t)nwarps * (uint32_t)((k) * sizeof(type));                               \
+        const bool st_ = b_ > 0 && (b_ & 15u) == 0u && off + b_ <= (uint32_t)(nwarps * ENV_IN_WORDS * 4);                            \
+        if (t == idx) res = st_ ? off : ENV_NOT_STAGED;                                                                              \
+        if (st_) { total += b_; off += (b_ + 15u) & ~15u; }                                                                          \
+        t++; }
+    ENV_STAGED_INPUTS(X_LAY, A, F, L, NSUM)
+#undef X_LAY
+    return idx < 0 ? total : res;
+}
+
+// Copy table, built once on the host when the buffers are bound: for every per-env input tensor its base pointer, bytes
+// per env and byte offset inside a CTA's input slab.  Thread t of a CTA issues the bulk copy of entry t, so the
+// per-thread set-up is a handful of instructions instead of the address arithmetic of all tensors.
+struct EnvStageTab {
+    const char *src[ENV_MAX_STAGED];
+    uint32_t row_bytes[ENV_MAX_STAGED];
+    uint32_t off[ENV_MAX_STAGED];
+    int n;                 // entries
+    uint32_t in_bytes;     // bytes the staged entries of one CTA bring in
+    int ok;                // staging enabled
+};
+
+inline EnvStageTab env_stage_table(const TaskDev &T, const B200Buffers &B, int nwarps) {
+    EnvStageTab tab;
+    const int A = T.i[TI_A], F = T.i[TI_F], L = T.i[TI_L], NSUM = T.i[TI_N_SUMS];
+    tab.n = 0; tab.ok = 1;
+#define X_TAB(field, type, k) { tab.src[tab.n] = (const char *)B.field; tab.row_bytes[tab.n] = (uint32_t)((k) * sizeof(type));   \
+        tab.off[tab.n] = env_stage_layout(tab.n, A, F, L, NSUM, nwarps); if (!B.field) tab.ok = 0; tab.n++; }
+    ENV_STAGED_INPUTS(X_TAB, A, F, L, NSUM)
+#undef X_TAB
+    tab.in_bytes = env_stage_layout(-1, A, F, L, NSUM, nwarps);
+    for (int k = tab.n; k < ENV_MAX_STAGED; k++) { tab.src[k] = nullptr; tab.row_bytes[k] = 0; tab.off[k] = ENV_NOT_STAGED; }
+    return tab;
+}
+
 // `staged`: the CTA's inputs were brought into shared memory by bulk copies completing on the mbarrier `bar`.
-// `R` is the view all per-env *inputs* are read through: B itself, or (staged CTAs) a copy whose pointers are biased so
-// that R.x[env * k + i] lands in the CTA's shared-memory slab that TMA filled -- one exposed DRAM latency per CTA
-// instead of one per dependent load.  All stores go to B (global memory).
+// `R` / `row` is the view all per-env *inputs* are read through (EnvInputs): the global tensors with row = env, or (staged
+// CTAs) the CTA's shared-memory slab that TMA filled with row = warp -- one exposed DRAM latency per CTA instead of one
+// per dependent load.  All stores go to B (global memory).
 template <class S>
-__device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const B200Buffers &R, const TerrainDev &tr, const EnvCall &call,
-                                   float *es, int env, int lane, bool staged, bool cta_sync, uint64_t *bar) {
+__device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const EnvInputs &R, const int row, const TerrainDev &tr,
+                                   const EnvCall &call, float *es, int env, int lane, bool staged, bool cta_sync, uint64_t *bar) {
     const float *tf = T.f;
     const TiView<S> ti{T.i};
     const int A = ti[TI_A], F = ti[TI_F], L = ti[TI_L], P = ti[TI_PX] * ti[TI_PY];
@@ -213,18 +281,18 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
 #endif
 
     // ------------------------------------------------------------------ per-env scalars (replicated in all lanes)
-    f3 bp = mk3(R.base_pos[env * 3], R.base_pos[env * 3 + 1], R.base_pos[env * 3 + 2]);
-    const float Qw = R.base_quat_wxyz[env * 4], Qx = R.base_quat_wxyz[env * 4 + 1], Qy = R.base_quat_wxyz[env * 4 + 2], Qz = R.base_quat_wxyz[env * 4 + 3];
-    f3 vw = mk3(R.base_lin_w[env * 3], R.base_lin_w[env * 3 + 1], R.base_lin_w[env * 3 + 2]);
-    f3 ww = mk3(R.base_ang_w[env * 3], R.base_ang_w[env * 3 + 1], R.base_ang_w[env * 3 + 2]);
-    f3 origin = mk3(R.env_origins[env * 3], R.env_origins[env * 3 + 1], R.env_origins[env * 3 + 2]);
-    float cmd0 = R.commands[env * 4], cmd1 = R.commands[env * 4 + 1], cmd2 = R.commands[env * 4 + 2], cmd3 = R.commands[env * 4 + 3];
-    int ep_len = R.episode_length[env];
-    int fail_cnt = R.fail_buf[env];
+    f3 bp = mk3(R.base_pos[row * 3], R.base_pos[row * 3 + 1], R.base_pos[row * 3 + 2]);
+    const float Qw = R.base_quat_wxyz[row * 4], Qx = R.base_quat_wxyz[row * 4 + 1], Qy = R.base_quat_wxyz[row * 4 + 2], Qz = R.base_quat_wxyz[row * 4 + 3];
+    f3 vw = mk3(R.base_lin_w[row * 3], R.base_lin_w[row * 3 + 1], R.base_lin_w[row * 3 + 2]);
+    f3 ww = mk3(R.base_ang_w[row * 3], R.base_ang_w[row * 3 + 1], R.base_ang_w[row * 3 + 2]);
+    f3 origin = mk3(R.env_origins[row * 3], R.env_origins[row * 3 + 1], R.env_origins[row * 3 + 2]);
+    float cmd0 = R.commands[row * 4], cmd1 = R.commands[row * 4 + 1], cmd2 = R.commands[row * 4 + 2], cmd3 = R.commands[row * 4 + 3];
+    int ep_len = R.episode_length[row];
+    int fail_cnt = R.fail_buf[row];
     // read before any lane may overwrite them below (lanes are not in lock-step between collectives)
-    const int level0 = ti[TI_TERRAIN_CURRICULUM] ? (int)R.terrain_levels[env] : 0;
-    const int ttype = ti[TI_TERRAIN_CURRICULUM] ? (int)R.terrain_types[env] : 0;
-    f3 push_vel = mk3(R.rand_push_vels[env * 3], R.rand_push_vels[env * 3 + 1], 0.f);
+    const int level0 = ti[TI_TERRAIN_CURRICULUM] ? (int)R.terrain_levels[row] : 0;
+    const int ttype = ti[TI_TERRAIN_CURRICULUM] ? (int)R.terrain_types[row] : 0;
+    f3 push_vel = mk3(R.rand_push_vels[row * 3], R.rand_push_vels[row * 3 + 1], 0.f);
     f3 lin_b, ang_b, grav;           // body-frame velocities, projected gravity
     float e_roll = 0.f, e_pitch = 0.f;   // base_euler (get_euler_xyz) for tracking_orientation
     if (ti[TI_BEHAVIOR]) {
@@ -235,7 +303,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     // periodic-gait state (tron1_pf_ee.py:186-197): theta_left/right, gait time, phase
     float th0 = 0.f, th1 = 0.f, th2 = 0.f, th3 = 0.f, gtime = 0.f, gphi = 0.f, gper = tf[TF_GAIT_PERIOD], bh_t = 0.f, fc_t = 0.f, pt_t = 0.f, expc_frc = 0.f;
     if (ti[TI_GAIT]) {
-        const float *gs = R.gait_state + env * B200_GAIT_STATE;
+        const float *gs = R.gait_state + row * B200_GAIT_STATE;
         th0 = gs[B200_GS_TH]; th1 = gs[B200_GS_TH + 1]; th2 = gs[B200_GS_TH + 2]; th3 = gs[B200_GS_TH + 3]; gtime = gs[B200_GS_GT]; gphi = gs[B200_GS_PHI];
         if (ti[TI_BEHAVIOR]) { gper = gs[B200_GS_PER]; bh_t = gs[B200_GS_BH]; fc_t = gs[B200_GS_FC]; pt_t = gs[B200_GS_PT]; }
     }
@@ -251,15 +319,15 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     };
     // ------------------------------------------------------------------ per-lane values
     const bool jl = lane < A, fl = lane < F;
-    float qj = jl ? R.dof_pos[env * A + lane] : 0.f, qdj = jl ? R.dof_vel[env * A + lane] : 0.f;
-    float actj = jl ? R.actions[env * A + lane] : 0.f;
+    float qj = jl ? R.dof_pos[row * A + lane] : 0.f, qdj = jl ? R.dof_vel[row * A + lane] : 0.f;
+    float actj = jl ? R.actions[row * A + lane] : 0.f;
     const float q0j = jl ? tf[TF_DEFAULT_DOF_POS + lane] : 0.f;
     f3 fpos = mk3(0.f, 0.f, 0.f), fvel = mk3(0.f, 0.f, 0.f);
     if (fl) {
-        const float *a = R.feet_pos + (env * F + lane) * 3, *b = R.feet_vel + (env * F + lane) * 3;
+        const float *a = R.feet_pos + (row * F + lane) * 3, *b = R.feet_vel + (row * F + lane) * 3;
         fpos = mk3(a[0], a[1], a[2]); fvel = mk3(b[0], b[1], b[2]);
     }
-    float ffz = fl ? R.link_contact_forces[(env * L + ti.dyn(TI_FEET_LINKS + lane)) * 3 + 2] : 0.f;   // foot contact force z
+    float ffz = fl ? R.link_contact_forces[(row * L + ti.dyn(TI_FEET_LINKS + lane)) * 3 + 2] : 0.f;   // foot contact force z
     float hmean = 0.f, hmax = 0.f;   // mean / max of the 9 terrain heights around this lane's foot
 
     if (pm & PHASE_CALLBACK) ep_len += 1;                       // legged_robot.py:60
@@ -271,7 +339,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             const f3 nb = mk3(__fadd_rn(tf[TF_INIT_POS], origin.x), __fadd_rn(tf[TF_INIT_POS + 1], origin.y), __fadd_rn(tf[TF_INIT_POS + 2], origin.z));
             fpos = fpos + (nb - bp);
             if (fl) {
-                float *a = B.feet_pos + (env * F + lane) * 3, *b = const_cast<float *>(R.feet_pos) + (env * F + lane) * 3;
+                float *a = B.feet_pos + (env * F + lane) * 3, *b = const_cast<float *>(R.feet_pos) + (row * F + lane) * 3;
                 a[0] = fpos.x; a[1] = fpos.y; a[2] = fpos.z; b[0] = fpos.x; b[1] = fpos.y; b[2] = fpos.z;
             }
             bp = nb;
@@ -295,7 +363,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             B.base_euler[env * 3 + 2] = atan2f(siny, cosy);
         }
         if (ti[TI_CONTACT_STATES] && lane < ti[TI_N_CS]) {
-            const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_CS_LINKS + lane)) * 3;
+            const float *f = R.link_contact_forces + (row * L + ti.dyn(TI_CS_LINKS + lane)) * 3;
             const float cs = norm3_rn(f[0], f[1], f[2]) > 1.0f ? 1.f : 0.f;
             B.link_contact_states[env * ti[TI_N_CS] + lane] = cs; es[ES_LCS + lane] = cs;
         }
@@ -395,7 +463,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     if (pm & PHASE_TERMINATION) {
         bool hit = false;
         if (lane < ti[TI_N_TERM]) {
-            const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_TERM_LINKS + lane)) * 3;
+            const float *f = R.link_contact_forces + (row * L + ti.dyn(TI_TERM_LINKS + lane)) * 3;
             hit = norm3_rn(f[0], f[1], f[2]) > 10.0f;
         }
         const bool fail = (__ballot_sync(B200_FULL_MASK, hit) != 0u) || (grav.z > tf[TF_MAX_PROJ_GRAV]);
@@ -408,12 +476,12 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     // per-joint / per-foot history values used by the constraints and the rewards
     float lastj = 0.f, llastj = 0.f, tauj = 0.f, lqdj = 0.f;
     if ((pm & PHASE_REWARD) && jl) {
-        lastj = R.last_actions[env * A + lane]; llastj = R.llast_actions[env * A + lane];
-        tauj = R.torques[env * A + lane]; lqdj = R.last_dof_vel[env * A + lane];
+        lastj = R.last_actions[row * A + lane]; llastj = R.llast_actions[row * A + lane];
+        tauj = R.torques[row * A + lane]; lqdj = R.last_dof_vel[row * A + lane];
     }
     // ================================================================== compute_reward
-    float my_sum = (lane < n_sums) ? R.episode_sums[env * n_sums + lane] : 0.f;
-    float fat = fl ? R.feet_air_time[env * F + lane] : 0.f;
+    float my_sum = (lane < n_sums) ? R.episode_sums[row * n_sums + lane] : 0.f;
+    float fat = fl ? R.feet_air_time[row * F + lane] : 0.f;
     float cprob = 0.f;
     if ((pm & PHASE_REWARD) && ti[TI_CAT]) {
         // ============================================================== compute_constraints_cat (go2_cat.py:135-215)
@@ -426,17 +494,17 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         for (int pt = lane; pt < P; pt += 32) hs += bp.z - (ti[TI_MEASURE_HEIGHTS] ? es[ES_MH + pt] : 0.f);
         const bool c_height = warp_sum(hs) / (float)P < tf[TF_CAT_MIN_BASE_HEIGHT];
         bool hit = false;
-        if (lane < ti[TI_N_PEN]) { const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_PEN_LINKS + lane)) * 3; hit = norm3_rn(f[0], f[1], f[2]) > 10.0f; }
+        if (lane < ti[TI_N_PEN]) { const float *f = R.link_contact_forces + (row * L + ti.dyn(TI_PEN_LINKS + lane)) * 3; hit = norm3_rn(f[0], f[1], f[2]) > 10.0f; }
         const bool c_coll = __ballot_sync(B200_FULL_MASK, hit) != 0u;
         bool stumble = false;
-        if (fl) { const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_FEET_LINKS + lane)) * 3; stumble = norm3_rn(f[0], f[1], f[2]) > __fmul_rn(4.0f, fabsf(f[2])); }
+        if (fl) { const float *f = R.link_contact_forces + (row * L + ti.dyn(TI_FEET_LINKS + lane)) * 3; stumble = norm3_rn(f[0], f[1], f[2]) > __fmul_rn(4.0f, fabsf(f[2])); }
         const bool c_stumble = __ballot_sync(B200_FULL_MASK, stumble) != 0u;
         const bool below = __ballot_sync(B200_FULL_MASK, jl && qj < tf[TF_DOF_LIM_LO + lane]) != 0u;
         const bool above = __ballot_sync(B200_FULL_MASK, jl && qj > tf[TF_DOF_LIM_HI + lane]) != 0u;
         const bool c_dofpos = below && above;                                 // product of two any() as written (go2_cat.py:168-169)
         const bool c_orient = grav.z > tf[TF_CAT_MAX_PROJ_GRAV];
         const bool fast_here = __ballot_sync(B200_FULL_MASK, jl && fabsf(qdj) > 4.0f) != 0u;
-        const bool fast = ti[TI_CAT_GLOBAL_STANDSTILL] ? (R.global_flags[0] != 0) : fast_here;
+        const bool fast = ti[TI_CAT_GLOBAL_STANDSTILL] ? (B.global_flags[0] != 0) : fast_here;
         const bool c_still = (norm3_rn(cmd0, cmd1, cmd2) < 0.1f) && fast;
         const float sp = tf[TF_CAT_SOFT_P];
         const bool cv[9] = {c_torque, c_dofvel, c_arate, c_height, c_coll, c_stumble, c_dofpos, c_orient, c_still};
@@ -475,7 +543,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 const int nf = id == RW_BIPED_PERIODIC_GAIT ? 2 : 4;
                 float term = 0.f;
                 if (lane < nf) {
-                    const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_FEET_LINKS + lane)) * 3;
+                    const float *f = R.link_contact_forces + (row * L + ti.dyn(TI_FEET_LINKS + lane)) * 3;
                     const float q_frc = norm3_rn(f[0], f[1], f[2]), q_spd = norm3_rn(fvel.x, fvel.y, fvel.z);
                     const float thl = lane == 0 ? th0 : (lane == 1 ? th1 : (lane == 2 ? th2 : th3));
                     const float ph = __fmul_rn(fmodf(__fadd_rn(gphi, thl), 1.0f), 6.2831853071795862f);
@@ -486,7 +554,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 r = expf(warp_sum(term)); break; }
             case RW_COLLISION: {
                 float hitf = 0.f;
-                if (lane < ti[TI_N_PEN]) { const float *f = R.link_contact_forces + (env * L + ti.dyn(TI_PEN_LINKS + lane)) * 3; hitf = norm3_rn(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f; }
+                if (lane < ti[TI_N_PEN]) { const float *f = R.link_contact_forces + (row * L + ti.dyn(TI_PEN_LINKS + lane)) * 3; hitf = norm3_rn(f[0], f[1], f[2]) > 0.1f ? 1.f : 0.f; }
                 r = warp_sum(hitf); break; }
             case RW_DOF_ACC: { const float d = (lqdj - qdj) / dt; r = warp_sum(d * d); break; }
             case RW_DOF_CLOSE_TO_DEFAULT: r = warp_sum(dqj * dqj); break;
@@ -500,7 +568,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             case RW_DOF_VEL_STAND_STILL: r = warp_sum(fabsf(qdj)) * small_cmd; break;
             case RW_FEET_AIR_TIME: {                              // stateful; go2_ts.py:133-145
                 const bool contact = ffz > 1.0f;
-                const bool lastc = fl ? (R.last_contacts[env * F + lane] != 0) : false;
+                const bool lastc = fl ? (R.last_contacts[row * F + lane] != 0) : false;
                 const bool filt = contact || lastc;
                 if (fl) B.last_contacts[env * F + lane] = contact ? 1 : 0;
                 const bool first = (fat > 0.f) && filt;
@@ -522,7 +590,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 r = cnt == 1.f ? 1.f : 0.f; break; }
             case RW_FOOT_ACC: {
                 float s = 0.f;
-                if (fl) { const float *lv = R.last_feet_vel + (env * F + lane) * 3;
+                if (fl) { const float *lv = R.last_feet_vel + (row * F + lane) * 3;
                     const float ax = (fvel.x - lv[0]) / dt, ay = (fvel.y - lv[1]) / dt, az = (fvel.z - lv[2]) / dt; s = ax * ax + ay * ay + az * az; }
                 r = warp_sum(s); break; }
             case RW_FOOT_CLEARANCE: {                             // legged_robot.py:575-588; go2_ts.py:147-161
@@ -653,19 +721,19 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         }
         // domain randomisation (genesis_simulator.py:62-82,665-739)
         // (stored to global memory and to the view the observation phase reads them back through)
-#define DR_PUT(field, idx, val) do { const float v_ = (val); B.field[idx] = v_; const_cast<float *>(R.field)[idx] = v_; } while (0)
+#define DR_PUT(field, k, i, val) do { const float v_ = (val); B.field[env * (k) + (i)] = v_; const_cast<float *>(R.field)[row * (k) + (i)] = v_; } while (0)
         if (lane == 0) {
-            if (ti[TI_RAND_FRICTION]) DR_PUT(friction, env, rand_range(tf[TF_FRICTION_LO], tf[TF_FRICTION_SPAN], rng.u(SITE_FRICTION, 0)));
-            if (ti[TI_RAND_MASS]) DR_PUT(added_mass, env, rand_range(tf[TF_MASS_LO], tf[TF_MASS_SPAN], rng.u(SITE_MASS, 0)));
+            if (ti[TI_RAND_FRICTION]) DR_PUT(friction, 1, 0, rand_range(tf[TF_FRICTION_LO], tf[TF_FRICTION_SPAN], rng.u(SITE_FRICTION, 0)));
+            if (ti[TI_RAND_MASS]) DR_PUT(added_mass, 1, 0, rand_range(tf[TF_MASS_LO], tf[TF_MASS_SPAN], rng.u(SITE_MASS, 0)));
             if (ti[TI_RAND_ARMATURE]) B.joint_armature[env] = rand_range(tf[TF_ARM_LO], tf[TF_ARM_SPAN], rng.u(SITE_ARMATURE, 0));
             if (ti[TI_RAND_JFRICTION]) B.joint_friction[env] = rand_range(tf[TF_JFR_LO], tf[TF_JFR_SPAN], rng.u(SITE_JFRICTION, 0));
             if (ti[TI_RAND_JDAMPING]) B.joint_damping[env] = rand_range(tf[TF_JDA_LO], tf[TF_JDA_SPAN], rng.u(SITE_JDAMPING, 0));
         }
         if (ti[TI_RAND_COM] && lane < 3)
-            DR_PUT(com_bias, env * 3 + lane, rand_range(tf[TF_COMX_LO + 2 * lane], tf[TF_COMX_SPAN + 2 * lane], rng.u(SITE_COM, lane)));
+            DR_PUT(com_bias, 3, lane, rand_range(tf[TF_COMX_LO + 2 * lane], tf[TF_COMX_SPAN + 2 * lane], rng.u(SITE_COM, lane)));
         if (ti[TI_RAND_PD] && jl) {
-            DR_PUT(kp_scale, env * A + lane, rand_range(tf[TF_KPS_LO], tf[TF_KPS_SPAN], rng.u(SITE_KP, lane)));
-            DR_PUT(kd_scale, env * A + lane, rand_range(tf[TF_KDS_LO], tf[TF_KDS_SPAN], rng.u(SITE_KD, lane)));
+            DR_PUT(kp_scale, A, lane, rand_range(tf[TF_KPS_LO], tf[TF_KPS_SPAN], rng.u(SITE_KP, lane)));
+            DR_PUT(kd_scale, A, lane, rand_range(tf[TF_KDS_LO], tf[TF_KDS_SPAN], rng.u(SITE_KD, lane)));
         }
 #undef DR_PUT
         if (lane < 3 * F) B.last_feet_vel[env * 3 * F + lane] = 0.f;
@@ -757,10 +825,10 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             if (lane < 3) cr[NO + lane] = __fmul_rn(comp3(lin_b, lane), tf[TF_OS_LIN_VEL]);
             if (lane == 0) {
                 float *d = cr + NO + 3;
-                d[0] = push_vel.x; d[1] = push_vel.y; d[2] = R.added_mass[env]; d[3] = R.friction[env];
-                d[4] = R.com_bias[env * 3]; d[5] = R.com_bias[env * 3 + 1]; d[6] = R.com_bias[env * 3 + 2];
+                d[0] = push_vel.x; d[1] = push_vel.y; d[2] = R.added_mass[row]; d[3] = R.friction[row];
+                d[4] = R.com_bias[row * 3]; d[5] = R.com_bias[row * 3 + 1]; d[6] = R.com_bias[row * 3 + 2];
             }
-            if (jl) { cr[NO + 10 + lane] = R.kp_scale[env * A + lane]; cr[NO + 10 + A + lane] = R.kd_scale[env * A + lane]; }
+            if (jl) { cr[NO + 10 + lane] = R.kp_scale[row * A + lane]; cr[NO + 10 + A + lane] = R.kd_scale[row * A + lane]; }
             if (fl) cr[NO + 10 + 2 * A + lane] = expc_frc;      // exp_C_frc of FL, FR, RL, RR as left by the reward (R13)
             __syncwarp();
             for (int e = lane; e < SC; e += 32) cr[e] = fminf(fmaxf(cr[e], -clipo), clipo);
@@ -784,12 +852,12 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             }
             for (int e = lane; e < DRN; e += 32) {
                 float v;
-                if (e == 0) v = __fsub_rn(R.friction[env], tf[TF_FRICTION_OFFSET]);
-                else if (e == 1) v = R.added_mass[env];
-                else if (e < 5) v = R.com_bias[env * 3 + e - 2];
+                if (e == 0) v = __fsub_rn(R.friction[row], tf[TF_FRICTION_OFFSET]);
+                else if (e == 1) v = R.added_mass[row];
+                else if (e < 5) v = R.com_bias[row * 3 + e - 2];
                 else if (e < 7) v = e == 5 ? push_vel.x : push_vel.y;
-                else if (e < 7 + A) v = __fsub_rn(R.kp_scale[env * A + e - 7], tf[TF_KPS_OFFSET]);
-                else if (e < 7 + 2 * A) v = __fsub_rn(R.kd_scale[env * A + e - 7 - A], tf[TF_KDS_OFFSET]);
+                else if (e < 7 + A) v = __fsub_rn(R.kp_scale[row * A + e - 7], tf[TF_KPS_OFFSET]);
+                else if (e < 7 + 2 * A) v = __fsub_rn(R.kd_scale[row * A + e - 7 - A], tf[TF_KDS_OFFSET]);
                 else v = e == 7 + 2 * A ? B.joint_armature[env] : (e == 8 + 2 * A ? B.joint_friction[env] : B.joint_damping[env]);
                 cr[NO + e] = v;
             }
@@ -808,7 +876,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             for (int e = lane; e < 3 * F; e += 32) { cr[off + e] = es[ES_NV + e]; pv[3 + NCS + F + e] = es[ES_NV + e]; }
             off += 3 * F;
             for (int e = lane; e < 9 * F; e += 32) {
-                const float fz = R.feet_pos[(env * F + e / 9) * 3 + 2];
+                const float fz = R.feet_pos[(row * F + e / 9) * 3 + 2];
                 cr[off + e] = fminf(fmaxf(__fsub_rn(fz, es[ES_HAF + e]), -1.0f), 1.0f);
             }
             if (lane < 3) pv[lane] = __fmul_rn(comp3(lin_b, lane), tf[TF_OS_LIN_VEL]);
@@ -828,8 +896,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             if (jl) cr[3 + NO + lane] = cleared ? 0.f : lastj;
             if (lane == 0) {
                 float *d = cr + 3 + NO + A;
-                d[0] = __fsub_rn(R.friction[env], tf[TF_FRICTION_OFFSET]); d[1] = R.added_mass[env];
-                d[2] = R.com_bias[env * 3]; d[3] = R.com_bias[env * 3 + 1]; d[4] = R.com_bias[env * 3 + 2];
+                d[0] = __fsub_rn(R.friction[row], tf[TF_FRICTION_OFFSET]); d[1] = R.added_mass[row];
+                d[2] = R.com_bias[row * 3]; d[3] = R.com_bias[row * 3 + 1]; d[4] = R.com_bias[row * 3 + 2];
                 d[5] = push_vel.x; d[6] = push_vel.y;
             }
             if (fl) cr[3 + NO + A + 7 + lane] = fat;
@@ -851,12 +919,12 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             // domain_randomization_info (go2_ts.py:16-28)
             for (int e = lane; e < DRN; e += 32) {
                 float v;
-                if (e == 0) v = __fsub_rn(R.friction[env], tf[TF_FRICTION_OFFSET]);
-                else if (e == 1) v = R.added_mass[env];
-                else if (e < 5) v = R.com_bias[env * 3 + e - 2];
+                if (e == 0) v = __fsub_rn(R.friction[row], tf[TF_FRICTION_OFFSET]);
+                else if (e == 1) v = R.added_mass[row];
+                else if (e < 5) v = R.com_bias[row * 3 + e - 2];
                 else if (e < 7) v = e == 5 ? push_vel.x : push_vel.y;
-                else if (e < 7 + A) v = __fsub_rn(R.kp_scale[env * A + e - 7], tf[TF_KPS_OFFSET]);
-                else if (e < 7 + 2 * A) v = __fsub_rn(R.kd_scale[env * A + e - 7 - A], tf[TF_KDS_OFFSET]);
+                else if (e < 7 + A) v = __fsub_rn(R.kp_scale[row * A + e - 7], tf[TF_KPS_OFFSET]);
+                else if (e < 7 + 2 * A) v = __fsub_rn(R.kd_scale[row * A + e - 7 - A], tf[TF_KDS_OFFSET]);
                 else v = e == 7 + 2 * A ? B.joint_armature[env] : (e == 8 + 2 * A ? B.joint_friction[env] : B.joint_damping[env]);
                 cr[c_ob + NO + e] = v;
                 if (!labels) pv[e] = v;
@@ -882,7 +950,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 if (fl) pv[3 + NCS + lane] = fminf(fmaxf(__fsub_rn(__fsub_rn(fpos.z, hmean), tf[TF_FOOT_HEIGHT_OFFSET]), -1.0f), 1.0f);
             } else {
                 for (int e = lane; e < 9 * F; e += 32) {
-                    const float fz = R.feet_pos[(env * F + e / 9) * 3 + 2];
+                    const float fz = R.feet_pos[(row * F + e / 9) * 3 + 2];
                     pv[DRN + e] = (cat || cts) ? es[ES_HAF + e] : fminf(fmaxf(__fsub_rn(fz, es[ES_HAF + e]), -1.0f), 1.0f);
                 }
                 for (int e = lane; e < 3 * F; e += 32) pv[DRN + 9 * F + e] = es[ES_NV + e];
@@ -918,48 +986,6 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     }
 }
 
-// per-env input tensors staged per CTA: X(field, element type, elements per env)
-#define ENV_STAGED_INPUTS(X, A_, F_, L_, NS_)                                                                          \
-    X(base_pos, float, 3) X(base_quat_wxyz, float, 4) X(base_lin_w, float, 3) X(base_ang_w, float, 3) X(env_origins, float, 3) \
-    X(commands, float, 4) X(episode_length, int32_t, 1) X(fail_buf, int32_t, 1) X(terrain_levels, int64_t, 1)          \
-    X(terrain_types, int64_t, 1) X(rand_push_vels, float, 3) X(dof_pos, float, A_) X(dof_vel, float, A_)               \
-    X(actions, float, A_) X(last_actions, float, A_) X(llast_actions, float, A_) X(torques, float, A_)                 \
-    X(last_dof_vel, float, A_) X(feet_pos, float, 3 * F_) X(feet_vel, float, 3 * F_) X(last_feet_vel, float, 3 * F_)   \
-    X(link_contact_forces, float, 3 * L_) X(episode_sums, float, NS_) X(feet_air_time, float, F_)                      \
-    X(last_contacts, uint8_t, F_) X(friction, float, 1) X(added_mass, float, 1) X(com_bias, float, 3)                  \
-    X(kp_scale, float, A_) X(kd_scale, float, A_) X(gait_state, float, B200_GAIT_STATE)
-
-// Staging table, built once on the host when the buffers are bound: for every per-env input tensor its base pointer,
-// bytes per env and byte offset inside a CTA's input slab (ENV_NOT_STAGED when a CTA's slice is not a multiple of 16
-// bytes -- that tensor is then read straight from global memory).  Thread t of a CTA issues the bulk copy of entry t,
-// so the per-thread set-up is a handful of instructions instead of the address arithmetic of all tensors.
-#define ENV_MAX_STAGED 40
-#define ENV_NOT_STAGED 0xFFFFFFFFu
-struct EnvStageTab {
-    const char *src[ENV_MAX_STAGED];
-    uint32_t row_bytes[ENV_MAX_STAGED];
-    uint32_t off[ENV_MAX_STAGED];
-    int n;                 // entries
-    uint32_t in_bytes;     // bytes the staged entries of one CTA bring in
-    int ok;                // staging enabled
-};
-
-inline EnvStageTab env_stage_table(const TaskDev &T, const B200Buffers &B, int nwarps) {
-    EnvStageTab tab;
-    const int A = T.i[TI_A], F = T.i[TI_F], L = T.i[TI_L], NSUM = T.i[TI_N_SUMS];
-    tab.n = 0; tab.in_bytes = 0; tab.ok = 1;
-    uint32_t off = 0;
-#define X_TAB(field, type, k) { const uint32_t row_ = (uint32_t)((k) * sizeof(type)), b_ = (uint32_t)nwarps * row_;                \
-        const bool st_ = B.field != nullptr && b_ > 0 && B200_TMA_SIZE_OK(b_) && off + b_ <= (uint32_t)(nwarps * ENV_IN_WORDS * 4); \
-        tab.src[tab.n] = (const char *)B.field; tab.row_bytes[tab.n] = row_; tab.off[tab.n] = st_ ? off : ENV_NOT_STAGED;           \
-        if (st_) { tab.in_bytes += b_; off += (b_ + 15u) & ~15u; }                                                                  \
-        tab.n++; }
-    ENV_STAGED_INPUTS(X_TAB, A, F, L, NSUM)
-#undef X_TAB
-    for (int k = tab.n; k < ENV_MAX_STAGED; k++) { tab.src[k] = nullptr; tab.row_bytes[k] = 0; tab.off[k] = ENV_NOT_STAGED; }
-    return tab;
-}
-
 // extras["episode"] (legged_robot.py:127-141): means over the envs that reset this step, from the reductions the env
 // kernel left in stats[0..n_sums] (+ reset count, + sum of terrain levels); written to slot (step % ENV_STATS_RING) of
 // the ring that follows the work area so that the host can hand out per-step values without any further launch.
@@ -977,9 +1003,11 @@ __device__ __forceinline__ void stats_finalize(float *stats, int n_sums, const E
 // The CTA that takes the last ticket sees every CTA's reductions (fence + atomic) and finalises them.  Called by every
 // thread of every CTA; `last` is one shared-memory word nobody else uses at this point.
 __device__ __forceinline__ void env_finalize_cta(const B200Buffers &B, int n_sums, const EnvCall &call, int *last) {
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) *last = atomicAdd(B.global_flags + 1, 1) == (int)gridDim.x - 1;
+    __syncthreads();           // the CTA's reductions are ordered before thread 0 ...
+    if (threadIdx.x == 0) {    // ... whose fence (cumulative) publishes them device-wide before it takes the ticket
+        __threadfence();
+        *last = atomicAdd(B.global_flags + 1, 1) == (int)gridDim.x - 1;
+    }
     __syncthreads();
     if (*last) {
         __threadfence();
@@ -992,7 +1020,7 @@ template <class S>
 __device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const EnvCall &call, const EnvStageTab &tab) {
     extern __shared__ float smem[];
     const TiView<S> ti{T.i};
-    const int nwarps = blockDim.x >> 5;
+    constexpr int nwarps = ENV_WARPS_PER_BLOCK;            // the launch geometry is fixed: slab offsets fold to constants
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env0 = blockIdx.x * nwarps, env = env0 + warp;
     const int N = ti[TI_NUM_ENVS];
@@ -1008,15 +1036,21 @@ __device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200B
         for (int t = (int)threadIdx.x; t < tab.n; t += (int)blockDim.x)
             if (tab.off[t] != ENV_NOT_STAGED)
                 tma_load_1d(inslab + tab.off[t], tab.src[t] + (size_t)env0 * tab.row_bytes[t], (uint32_t)nwarps * tab.row_bytes[t], bar);
-        // every thread builds the same read view R: staged tensors point into the slab, biased so that R.x[env * k + i] works
-        B200Buffers R = B;
+        // every thread builds the same read view: staged tensors lead into the slab (offsets are compile-time constants in
+        // the specialised instantiations), the few that could not be staged are biased to the CTA's first env; row = warp
+        EnvInputs R;
         int t = 0;
-#define X_VIEW(field, type, k) { if (tab.off[t] != ENV_NOT_STAGED) R.field = (type *)(inslab + tab.off[t]) - (size_t)env0 * (k); t++; }
+#define X_VIEW(field, type, k) { const uint32_t o_ = S::fixed ? env_stage_layout(t, ti[TI_A], ti[TI_F], ti[TI_L], ti[TI_N_SUMS], nwarps) : tab.off[t]; \
+        R.field = o_ != ENV_NOT_STAGED ? (const type *)(inslab + o_) : B.field + (size_t)env0 * (k); t++; }
         ENV_STAGED_INPUTS(X_VIEW, ti[TI_A], ti[TI_F], ti[TI_L], ti[TI_N_SUMS])
 #undef X_VIEW
-        env_post_step_warp<S>(T, B, R, tr, call, es + warp * ES_TOTAL, env, lane, true, true, bar);
+        env_post_step_warp<S>(T, B, R, warp, tr, call, es + warp * ES_TOTAL, env, lane, true, true, bar);
     } else if (env < N) {
-        env_post_step_warp<S>(T, B, B, tr, call, es + warp * ES_TOTAL, env, lane, false, false, bar);
+        EnvInputs R;
+#define X_VIEW(field, type, k) R.field = B.field;
+        ENV_STAGED_INPUTS(X_VIEW, 0, 0, 0, 0)
+#undef X_VIEW
+        env_post_step_warp<S>(T, B, R, env, tr, call, es + warp * ES_TOTAL, env, lane, false, false, bar);
     }
     if (call.finalize) env_finalize_cta(B, ti[TI_N_SUMS], call, (int *)(smem + 2));
 }

@@ -451,6 +451,11 @@ class B200Simulator:
         return dict(registers=r.value, smem_bytes=s.value, blocks_per_sm=b.value, block_threads=t.value)
 
     @property
+    def env_kernel_variant(self) -> str:
+        """Name of the task preset the env kernel in use was compiled for, or "generic"."""
+        return self._lib.b200_env_kernel_variant(self._handle).decode()
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.b200_launch_count(self._handle))
 

@@ -287,6 +287,11 @@ int b200_reset_all(B200Handle *h, long long step_counter, float cmd_vx_lo, float
 /* static resource usage of a kernel ("dynamics" | "env"): registers/thread, static+dynamic smem/block, max blocks/SM */
 int b200_kernel_info(B200Handle *h, const char *kernel, int *regs, int *smem_bytes, int *blocks_per_sm, int *block_threads);
 
+/* which instantiation of the fused post_physics_step kernel this handle launches: the name of the built-in task preset
+ * whose structural descriptor ints all equal the handle's (the kernel compiled with them as constants), or "generic"
+ * (descriptor read at run time; any edited configuration).  Same results either way. */
+const char *b200_env_kernel_variant(B200Handle *h);
+
 /* number of kernel launches issued through this handle since creation */
 long long b200_launch_count(B200Handle *h);
 

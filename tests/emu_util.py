@@ -19,7 +19,7 @@ def build_emu(with_env=True):
     srcs += [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
     srcs.append(os.path.join(os.path.dirname(_EMU_DIR), "..", "include", "b200_step.h"))
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
-        cmd = ["g++", "-DEMU_WITH_ENV", "-O1", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-I", _EMU_DIR, "-o", out,
+        cmd = ["g++", "-DEMU_WITH_ENV", "-DENV_WARPS_PER_BLOCK=1", "-O1", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-I", _EMU_DIR, "-o", out,
                os.path.join(_EMU_DIR, "emu.cpp"), os.path.join(_EMU_DIR, "emu_main.cpp")]
         subprocess.check_call(cmd)
     return ctypes.CDLL(out)
