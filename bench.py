@@ -212,7 +212,7 @@ def run_gpu(args):
         for i in range(K):
             flush_l2()
             evs[i][0].record()
-            sim.history_shift(side_stream=False)
+            sim.history_shift(side_stream=False, reorder=False)
             evs[i][1].record()
         barrier()
         launches += K

@@ -242,7 +242,7 @@ def buffer_shapes(spec: T.TaskSpec, model: RobotModel, N: int) -> "OrderedDict[s
         obs_history0=(N, max(w["hist"], 1)), obs_history1=(N, max(w["hist"], 1)),
         critic_obs0=(N, max(w["critic"], 1)), critic_obs1=(N, max(w["critic"], 1)),
         rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), gait_state=(N, H["B200_GAIT_STATE"]), height_cells=(N, P, 2), stats=(stats_base(nsum) + STATS_RING * (max(nsum, 1) + H["B200_STATS_EXTRA"]),), cstr_prob=(N,), global_flags=(4,),
-        next_state_buf=(N, w["obs"] if spec.obs_kind == "go2_dreamwaq" else 1),
+        next_state_buf=(N, w["obs"] if spec.obs_kind == "go2_dreamwaq" else 1), dyn_cost=(2, N), dyn_order=(2, N),
     )
     return OrderedDict((name, (shp[name], _NP[ct])) for name, ct in BUFFER_FIELDS)
 
@@ -293,6 +293,8 @@ def load_library() -> ctypes.CDLL:
     lib.b200_history_shift.restype = ctypes.c_int
     lib.b200_set_history_side_stream.argtypes = [vp, ctypes.c_int]
     lib.b200_set_history_side_stream.restype = ctypes.c_int
+    lib.b200_set_dynamics_order.argtypes = [vp, ctypes.c_int]
+    lib.b200_set_dynamics_order.restype = ctypes.c_int
     lib.b200_set_behavior.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
     lib.b200_set_behavior.restype = ctypes.c_int
     lib.b200_reset_all.argtypes = [vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, vp]
@@ -310,4 +312,4 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = ["b200_create", "b200_destroy", "b200_set_terrain", "b200_bind_buffers", "b200_dynamics_step",
-                    "b200_history_shift", "b200_set_history_side_stream", "b200_env_post_step", "b200_env_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_env_kernel_variant", "b200_launch_count", "b200_last_error"]
+                    "b200_history_shift", "b200_set_history_side_stream", "b200_set_dynamics_order", "b200_env_post_step", "b200_env_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_env_kernel_variant", "b200_launch_count", "b200_last_error"]

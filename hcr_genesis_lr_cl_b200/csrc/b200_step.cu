@@ -43,7 +43,11 @@ struct B200Handle {
     int preshift_parity = -1;      // parity the stacks have been shifted for (-1: none pending)
     int env_preset = -1;           // instantiation of the env kernel: index into env_presets.inc, -1 = generic
     float *d_actions = nullptr;    // staging of b200_env_step's host actions
-    bool stats_zeroed = false;     // the dynamics kernel of this step already cleared the env kernel's reduction area
+    bool stats_zeroed = false;
+    bool order_enabled = true;     // dynamics warps take envs sorted by solver cost (dynamics_order_kernel); B200_DYN_ORDER=0: slot w = env w
+    long long dyn_launches = 0;    // parity of the cost / order buffers
+    int sm_count = 148;
+    bool side_pending = false;     // work on the side stream that the next env launch has to join     // the dynamics kernel of this step already cleared the env kernel's reduction area
 };
 
 typedef void (*EnvKernelFn)(const TaskDev, const B200Buffers, const TerrainDev, const EnvCall, const EnvStageTab);
@@ -86,6 +90,9 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
     {   // specialised instantiation when the descriptor is one of the built-in presets (B200_ENV_GENERIC=1 forces the generic one)
         const char *g = getenv("B200_ENV_GENERIC");
         h->env_preset = (g && g[0] == '1') ? -1 : env_match_preset(ti);
+        CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, 0));
+        const char *o = getenv("B200_DYN_ORDER");
+        h->order_enabled = !(o && o[0] == '0');
     }
     if (h->env_smem > 48 * 1024) CK(cudaFuncSetAttribute(env_kernel_fn(h->env_preset), cudaFuncAttributeMaxDynamicSharedMemorySize, h->env_smem));
     CK(cudaFuncSetAttribute(dynamics_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
@@ -118,7 +125,8 @@ int b200_bind_buffers(B200Handle *h, const B200Buffers *b) {
     const void *const *p = (const void *const *)b;
     const size_t n = sizeof(B200Buffers) / sizeof(void *);
     for (size_t k = 0; k < n; k++) {
-        const bool optional = (&p[k] == (const void *const *)&b->height_cells);
+        const bool optional = (&p[k] == (const void *const *)&b->height_cells) || (&p[k] == (const void *const *)&b->dyn_cost) ||
+                              (&p[k] == (const void *const *)&b->dyn_order);
         if (!p[k] && !optional) return fail("b200_bind_buffers: null buffer pointer");
     }
     h->bufs = *b; h->bound = true;
@@ -140,13 +148,15 @@ int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
     const dim3 grid((N + DYN_WARPS_PER_BLOCK - 1) / DYN_WARPS_PER_BLOCK), block(DYN_WARPS_PER_BLOCK * 32);
     cudaStream_t s = (cudaStream_t)stream;
     if (h->task.i[TI_CAT]) CK(cudaMemsetAsync(h->bufs.global_flags, 0, 4 * sizeof(int32_t), s));
-    if (h->task.i[TI_OBS_KIND] >= 1 && h->preshift_parity < 0) {   // fork point of a b200_history_shift that follows: everything
+    if (h->preshift_parity < 0 && !h->side_pending) {              // fork point of a b200_history_shift that follows: everything
         if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));   // enqueued before this step
         CK(cudaEventRecord(h->ev_fork, s));
         h->fork_recorded = true;
     }
-    if (h->task.i[TI_C] == 4) dynamics_step_kernel<4><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions);
-    else dynamics_step_kernel<2><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions);
+    const int par = (h->order_enabled && h->bufs.dyn_order && h->bufs.dyn_cost) ? (int)(h->dyn_launches & 1) : -1;
+    if (h->task.i[TI_C] == 4) dynamics_step_kernel<4><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions, par);
+    else dynamics_step_kernel<2><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions, par);
+    h->dyn_launches++;
     h->launches++;
     h->stats_zeroed = true;
     CK(cudaGetLastError());
@@ -156,7 +166,10 @@ int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
 int b200_history_shift(B200Handle *h, int parity, void *stream) {
     if (check_ready(h, "b200_history_shift")) return 1;
     const int *ti = h->task.i;
-    if (ti[TI_OBS_KIND] < 1) return 0;               // the task keeps no frame stacks
+    const bool stacks = ti[TI_OBS_KIND] >= 1;        // the task keeps frame stacks
+    // the order of the NEXT dynamics launch from the cost of the PREVIOUS one (the launch in flight writes the other halves)
+    const bool reorder = h->order_enabled && h->bufs.dyn_order && h->bufs.dyn_cost && h->dyn_launches >= 2;
+    if (!stacks && !reorder) return 0;
     cudaStream_t s = (cudaStream_t)stream, run = s;
     if (h->side_enabled) {
         if (!h->side) CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
@@ -168,18 +181,33 @@ int b200_history_shift(B200Handle *h, int parity, void *stream) {
     }
     h->fork_recorded = false;
     const int N = ti[TI_NUM_ENVS], p = parity & 1;
-    const long long Mh = (long long)N * ti[TI_FRAME_STACK] * ti[TI_NUM_OBS], Mc = (long long)N * ti[TI_C_FRAME_STACK] * ti[TI_SINGLE_CRITIC];
-    // one warp-iteration moves 32 x HIST_SHIFT_UNROLL vectors; enough blocks for the larger stack, capped at a few per SM
-    const long long per_block = (long long)(HIST_SHIFT_BLOCK / 32) * 32 * HIST_SHIFT_UNROLL * 4;
-    long long blocks = ((Mh > Mc ? Mh : Mc) + per_block - 1) / per_block;
-    if (blocks > 148 * HIST_SHIFT_GRID_PER_SM) blocks = 148 * HIST_SHIFT_GRID_PER_SM;
-    if (blocks < 1) blocks = 1;
-    history_shift_kernel<<<dim3((unsigned)blocks, 2), HIST_SHIFT_BLOCK, 0, run>>>(h->bufs.obs_history[p], h->bufs.obs_history[p ^ 1], Mh, ti[TI_NUM_OBS],
-                                                                                 h->bufs.critic_obs[p], h->bufs.critic_obs[p ^ 1], Mc, ti[TI_SINGLE_CRITIC]);
-    h->launches++;
-    CK(cudaGetLastError());
-    if (h->side_enabled) CK(cudaEventRecord(h->ev_join, h->side));
-    h->preshift_parity = p; h->preshift_on_side = h->side_enabled;
+    if (reorder) {
+        const int next = (int)(h->dyn_launches & 1);                    // parity of the next dynamics launch; its cost half is two launches old
+        dynamics_order_kernel<<<1, 1024, 0, run>>>(h->bufs.dyn_cost + (size_t)next * N, h->bufs.dyn_order + (size_t)next * N, N,
+                                                   h->sm_count * DYN_WARPS_PER_BLOCK);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    if (stacks) {
+        const long long Mh = (long long)N * ti[TI_FRAME_STACK] * ti[TI_NUM_OBS], Mc = (long long)N * ti[TI_C_FRAME_STACK] * ti[TI_SINGLE_CRITIC];
+        // one warp-iteration moves 32 x HIST_SHIFT_UNROLL vectors; enough blocks for the larger stack, capped at a few per SM
+        const long long per_block = (long long)(HIST_SHIFT_BLOCK / 32) * 32 * HIST_SHIFT_UNROLL * 4;
+        long long blocks = ((Mh > Mc ? Mh : Mc) + per_block - 1) / per_block;
+        if (blocks > 148 * HIST_SHIFT_GRID_PER_SM) blocks = 148 * HIST_SHIFT_GRID_PER_SM;
+        if (blocks < 1) blocks = 1;
+        history_shift_kernel<<<dim3((unsigned)blocks, 2), HIST_SHIFT_BLOCK, 0, run>>>(h->bufs.obs_history[p], h->bufs.obs_history[p ^ 1], Mh, ti[TI_NUM_OBS],
+                                                                                     h->bufs.critic_obs[p], h->bufs.critic_obs[p ^ 1], Mc, ti[TI_SINGLE_CRITIC]);
+        h->launches++;
+        CK(cudaGetLastError());
+        h->preshift_parity = p;
+    }
+    if (h->side_enabled) { CK(cudaEventRecord(h->ev_join, h->side)); h->side_pending = true; }
+    return 0;
+}
+
+int b200_set_dynamics_order(B200Handle *h, int enabled) {
+    if (!h) return fail("b200_set_dynamics_order: null handle");
+    h->order_enabled = enabled != 0;
     return 0;
 }
 
@@ -213,8 +241,8 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     if ((mask & PHASE_RESET) && !h->stats_zeroed) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 4), s));
     h->stats_zeroed = false;
     EnvCall call = make_call(h, step, lo, span, parity, mask, force);
-    if (h->preshift_parity >= 0) {                   // join the side stream; use its work only if it was for this parity and phase set
-        if (h->preshift_on_side) CK(cudaStreamWaitEvent(s, h->ev_join, 0));
+    if (h->side_pending) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->side_pending = false; }      // join the side stream
+    if (h->preshift_parity >= 0) {                   // use the shifted stacks only if they were made for this parity and phase set
         call.preshifted = (h->preshift_parity == (parity & 1) && !force && (mask & PHASE_OBSERVE)) ? 1 : 0;
         h->preshift_parity = -1;
     }

@@ -220,7 +220,7 @@ __device__ __forceinline__ void spd6_inverse(const float *S, float *Sinv) {
 // One env, `decimation` substeps.  C chains of 3 joints.  All 32 lanes execute every collective.
 template <int C>
 __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const float *ms, float *ws,
-                              const float *actions_in, int env, int lane) {
+                              const float *actions_in, int env, int lane, int *cost_out) {
     const float *tf = T.f;
     const int A = 3 * C, L = T.i[TI_L], NS = T.i[TI_NSPHERES];
     const int *msi = (const int *)(ms + MS_INT);
@@ -270,6 +270,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     const float kk = 1.f / (tf[TF_DMAX] * tf[TF_DMAX] * tf[TF_TC] * tf[TF_TC] * tf[TF_DAMPRATIO] * tf[TF_DAMPRATIO]);
     const float bd = 2.f / (tf[TF_DMAX] * tf[TF_TC]);
 
+    int cost = 0;                    // solver work of this env in this launch (sweeps x rows, + rows built): feeds the next launches' order
     for (int sub = 0; sub <= T.i[TI_DECIMATION]; sub++) {
         const bool last_pass = sub == T.i[TI_DECIMATION];   // kinematics-only pass for the outputs
         PHASE_SYNC();
@@ -677,7 +678,8 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         const bool clamp0 = (kind == 0 || kind == 3);
         const float fhi = kind == 4 ? bound : 3.0e38f, flo = clamp0 ? 0.f : -fhi;
         const float c1n = -(Rr * idd), iddn = -idd;
-        for (int it = 0; it < iters; it++) {
+        int it = 0;
+        for (; it < iters; it++) {
             const float fprev = f;
             // contacts: normal, tangent 1, tangent 2, then projection of the tangential pair onto the friction disc
             for (int c2 = 0; c2 < nc; c2++) {
@@ -715,6 +717,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 #endif
             if (dmax <= tf[TF_PGS_TOL] * (1.f + fmx)) break;
         }
+        cost += (min(it + 1, iters) + 4) * R;          // sweeps made (+ the work of building the rows)
         __syncwarp();
         for (int e = lane; e < 48; e += 32) ws[WS_WARM + e] = 0.f;
         __syncwarp();
@@ -779,8 +782,13 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     }
 
 #ifdef DYN_TIMING
-    if (lane == 0 && env < 65536) { g_dyn_timing[env * 4] = t_begin; g_dyn_timing[env * 4 + 1] = dyn_now(); g_dyn_timing[env * 4 + 2] = dbg_sweeps; g_dyn_timing[env * 4 + 3] = dbg_rows; }
+    if (lane == 0 && env < 65536) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_dyn_timing[env * 4] = t_begin; g_dyn_timing[env * 4 + 1] = dyn_now();
+        g_dyn_timing[env * 4 + 2] = dbg_sweeps | ((unsigned long long)smid << 32); g_dyn_timing[env * 4 + 3] = dbg_rows | ((unsigned long long)blockIdx.x << 32);
+    }
 #endif
+    if (cost_out && lane == 0) *cost_out = cost;
     // ---------------- write back (frames/velocities of the final state are in shared memory) ----------------
     if (lane < 3) {
         B.base_pos[env * 3 + lane] = comp3(p, lane);
@@ -838,9 +846,40 @@ __device__ __forceinline__ void dynamics_idle_warp(const TaskDev &T) {
 #endif
 }
 
+// Which env a warp slot takes.  Inside a CTA the warps wait for each other at the phase barriers, and an SM's four CTAs
+// share its issue slots, so a launch is fastest when the envs of a CTA cost the same and every SM gets the same mix.
+// dynamics_order_kernel sorts the envs by the solver work they needed two launches ago (contact configurations persist
+// over many policy steps), heaviest first: with the block scheduler filling the SMs breadth-first, CTAs 0..147 (the
+// heaviest 7 x 148 envs) land one per SM, the next 148 likewise, and so on.  The permutation is delta-encoded
+// (slot w runs env w + delta[w]) so that a zeroed buffer is the identity.  Pure scheduling: every env computes exactly
+// what it would in any other slot.
+#define DYN_COST_BUCKETS 64
+#define DYN_COST_PER_BUCKET 48
+__global__ void dynamics_order_kernel(const int32_t *cost, int32_t *order_delta, int N, int slots_per_round) {
+    __shared__ int start[DYN_COST_BUCKETS];
+    for (int b = threadIdx.x; b < DYN_COST_BUCKETS; b += blockDim.x) start[b] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&start[min(cost[i] / DYN_COST_PER_BUCKET, DYN_COST_BUCKETS - 1)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {          // exclusive prefix over the buckets, heaviest bucket first
+        int acc = 0;
+        for (int b = DYN_COST_BUCKETS - 1; b >= 0; b--) { const int n = start[b]; start[b] = acc; acc += n; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int pos = atomicAdd(&start[min(cost[i] / DYN_COST_PER_BUCKET, DYN_COST_BUCKETS - 1)], 1);     // unique rank: a permutation
+        // ranks -> warp slots in boustrophedon over the rounds of the block scheduler (one CTA per SM per round): the SM
+        // that got the heaviest CTA of a round gets the lightest of the next, so the SMs' total work evens out
+        const int round = pos / slots_per_round, r = pos - round * slots_per_round;
+        const int len = min(slots_per_round, N - round * slots_per_round);
+        const int slot = round * slots_per_round + ((round & 1) ? len - 1 - r : r);
+        order_delta[slot] = i - slot;
+    }
+}
+
 template <int C>
 __global__ void B200_LAUNCH_BOUNDS(DYN_WARPS_PER_BLOCK * 32, DYN_MIN_BLOCKS)
-dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, const TerrainDev tr, const float *actions) {
+dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, const TerrainDev tr, const float *actions, const int parity) {
     extern __shared__ float smem[];
     float *ms = smem;
     stage_model(M, T, ms);
@@ -849,7 +888,10 @@ dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, con
     if (blockIdx.x == 0 && (int)threadIdx.x < T.i[TI_N_SUMS] + 4) B.stats[threadIdx.x] = 0.f;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (env >= T.i[TI_NUM_ENVS]) { dynamics_idle_warp(T); return; }
-    dynamics_warp<C>(T, B, tr, ms, smem + MS_TOTAL + warp * WS_TOTAL, actions, env, lane);
+    const int slot = blockIdx.x * (blockDim.x >> 5) + warp, N = T.i[TI_NUM_ENVS];
+    if (slot >= N) { dynamics_idle_warp(T); return; }
+    const bool ordered = parity >= 0 && B.dyn_order != nullptr;
+    const int env = ordered ? slot + B.dyn_order[(size_t)parity * N + slot] : slot;
+    dynamics_warp<C>(T, B, tr, ms, smem + MS_TOTAL + warp * WS_TOTAL, actions, env, lane,
+                     (parity >= 0 && B.dyn_cost) ? B.dyn_cost + (size_t)parity * N + env : nullptr);
 }

@@ -15,6 +15,7 @@ the physics or the environment step, and construction fails if the CUDA library 
 from __future__ import annotations
 
 import ctypes
+import os
 from types import SimpleNamespace
 from typing import Optional, Sequence
 
@@ -64,6 +65,7 @@ class B200Simulator:
         self._tdev = torch.device(sim_device)
         self._handle = ctypes.c_void_p()
         self._parity = 0
+        self._dyn_order = os.environ.get("B200_DYN_ORDER", "1") != "0"
         self.fused_histories = False   # set by FusedLeggedEnv: b200_history_shift follows every dynamics step
         self._parse_cfg()
         self._create_sim()
@@ -252,11 +254,21 @@ class B200Simulator:
         if self.fused_histories:      # fused mode: the frame stacks are shifted on a side stream in the shadow of the dynamics kernel
             self._ck(self._lib.b200_history_shift(self._handle, self._parity, self._stream()))
 
-    def history_shift(self, side_stream: bool = True):
-        """Launch the frame-stack shift for the coming fused post step (normally done by `step` in fused mode)."""
+    def history_shift(self, side_stream: bool = True, reorder: bool = True):
+        """Launch the frame-stack shift for the coming fused post step (normally done by `step` in fused mode);
+        `reorder=False` leaves out the env-ordering kernel that shares its side-stream slot (timing the copy alone)."""
         self._ck(self._lib.b200_set_history_side_stream(self._handle, int(side_stream)))
+        if not reorder:
+            self._ck(self._lib.b200_set_dynamics_order(self._handle, 0))
         self._ck(self._lib.b200_history_shift(self._handle, self._parity, self._stream()))
+        if not reorder:
+            self._ck(self._lib.b200_set_dynamics_order(self._handle, int(self._dyn_order)))
         self._ck(self._lib.b200_set_history_side_stream(self._handle, 1))
+
+    def set_dynamics_order(self, enabled: bool) -> None:
+        """Cost-ordered env -> warp-slot assignment of the dynamics kernel (scheduling only; results are identical)."""
+        self._dyn_order = bool(enabled)
+        self._ck(self._lib.b200_set_dynamics_order(self._handle, int(enabled)))
 
     def post_physics_step(self):
         """State extraction, contact states, height scan (genesis_simulator.py:35-60) -- PHASE_SIM_POST only."""

@@ -232,6 +232,10 @@ typedef struct B200Buffers {
     float *contact_warm;        /* [N,48] contact-solver warm start carried between substeps and policy steps: 8 x (sphere id + 1,
                                    f_n, f_t1, f_t2) then 8 x (aux-row code + 1, f); zero = empty */
     float *next_state_buf;      /* [N,num_obs] go2_dreamwaq decoder target (go2_dreamwaq.py:72-80); [N,1] otherwise */
+    /* scheduling state of the dynamics kernel (no reference counterpart; results do not depend on it): per-env cost of the
+     * last two launches and the env each warp slot takes in the next ones */
+    int32_t *dyn_cost;          /* [2,N] solver work (sweeps x rows) of each env in the launches of either parity */
+    int32_t *dyn_order;         /* [2,N] warp slot w runs env w + dyn_order[parity][w] (delta-encoded permutation: zeros = identity) */
 } B200Buffers;
 
 typedef struct B200Handle B200Handle;
@@ -251,11 +255,18 @@ int b200_dynamics_step(B200Handle *h, const float *dev_actions, void *cuda_strea
  * dynamics kernel produces; call it right after b200_dynamics_step with the same stream: it runs on an internal side
  * stream forked at the point where b200_dynamics_step was enqueued (so it overlaps the dynamics kernel) and the next
  * b200_env_post_step joins it.  Without this call b200_env_post_step shifts the stacks itself.  Replaces the deque /
- * torch.cat frame stacking of legged_robot_ts.py:86-97, tron1_pf.py:57-70, go2_wtw.py:92-111. */
+ * torch.cat frame stacking of legged_robot_ts.py:86-97, tron1_pf.py:57-70, go2_wtw.py:92-111.  The same side-stream
+ * slot carries the env ordering of the next dynamics launch (b200_set_dynamics_order). */
 int b200_history_shift(B200Handle *h, int parity, void *cuda_stream);
 /* enabled = 0: b200_history_shift launches on the caller's stream instead of the side stream (profiling, timing the
  * copy alone, or callers that must keep every launch on one stream).  Default: enabled. */
 int b200_set_history_side_stream(B200Handle *h, int enabled);
+
+/* enabled = 0: warp slot w of the dynamics kernel runs env w.  Default (enabled, B200_DYN_ORDER=0 in the environment
+ * disables it at creation): b200_history_shift also launches dynamics_order_kernel on the side stream, which sorts the
+ * envs by the contact-solver work they needed two launches ago into B200Buffers.dyn_order so that the envs of a CTA
+ * cost the same and the SMs get the same mix.  Pure scheduling: results are identical either way. */
+int b200_set_dynamics_order(B200Handle *h, int enabled);
 
 /* Fused post_physics_step. `step_counter` is LeggedRobot.common_step_counter *after* its increment;
  * `cmd_vx_lo/span` is the (curriculum-mutable) lin_vel_x command range as (lower, fp32(upper-lower)); `parity` (0/1) selects which of the

@@ -316,9 +316,12 @@ def test_full_size_properties():
     env_a, sa = rollout(N)
     env_b, sb = rollout(N)
     for k in sa:                                                     # determinism: bit-identical reruns
-        if k == "stats":
+        if k in ("stats", "dyn_order"):            # float atomics (logging only) / scheduling state (ties broken by atomics)
             continue
         assert torch.equal(sa[k], sb[k]), f"non-deterministic buffer {k}"
+    for par in range(2):                           # the scheduling state is a permutation, whatever the tie-breaking
+        assert torch.equal(torch.sort(sa["dyn_order"][par] + torch.arange(N, device="cuda", dtype=torch.int32)).values,
+                           torch.arange(N, device="cuda", dtype=torch.int32))
     # sharding invariance: the second half computed as its own shard equals the same envs inside the full job
     half = N // 2
     env_c, sc = rollout(half, offset=half, total=N, a_slice=slice(half, N))
@@ -326,7 +329,8 @@ def test_full_size_properties():
         assert torch.equal(sa[k][half:], sc[k]), f"shard != full job for {k}"
     assert torch.isfinite(sa["obs_buf"]).all() and torch.isfinite(sa["rew_buf"]).all()
     assert sa["height_cells"].min() >= 0 and sa["height_cells"].max() <= 1198
-    assert env_a.simulator.launch_count == 1 + 3 * (len(acts) + 1)     # reset_all + (dynamics, history shift, env) per step
+    n_steps = len(acts) + 1                                           # reset() = reset_all + one zero-action step
+    assert env_a.simulator.launch_count == 1 + 3 * n_steps + (n_steps - 1)   # (dynamics, history shift, env) per step + the env-order kernel from the 2nd step on
 
 
 def test_short_rollout_against_oracle(golden):

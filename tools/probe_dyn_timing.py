@@ -33,7 +33,22 @@ for i in range(120):
         t0 = buf[:, 0].min()
         start, end = (buf[:, 0] - t0).astype(np.float64) / 1e3, (buf[:, 1] - t0).astype(np.float64) / 1e3
         dur = end - start
-        sw, rows = buf[:, 2].astype(np.float64), buf[:, 3].astype(np.float64)
+        smid, cta = (buf[:, 2] >> np.uint64(32)).astype(np.int64), (buf[:, 3] >> np.uint64(32)).astype(np.int64)
+        sw, rows = (buf[:, 2] & np.uint64(0xFFFFFFFF)).astype(np.float64), (buf[:, 3] & np.uint64(0xFFFFFFFF)).astype(np.float64)
+        # where does the spread of the end times come from: the SM, the CTA, or the env itself?
+        sm_mean = np.array([end[smid == m].mean() for m in np.unique(smid)])
+        sm_cnt = np.array([(smid == m).sum() for m in np.unique(smid)])
+        cta_max = np.array([end[cta == c].max() for c in np.unique(cta)])
+        cta_spread = np.array([end[cta == c].max() - end[cta == c].min() for c in np.unique(cta)])
+        sm_rows = np.array([rows[smid == m].sum() for m in np.unique(smid)])
+        sm_end = np.array([end[smid == m].max() for m in np.unique(smid)])
+        print(f"   SMs used {len(sm_mean)}, envs per SM min {sm_cnt.min()} max {sm_cnt.max()}; per-SM mean end: min {sm_mean.min():.0f} p50 {np.median(sm_mean):.0f} max {sm_mean.max():.0f} us; "
+              f"per-SM last end: min {sm_end.min():.0f} p50 {np.median(sm_end):.0f} max {sm_end.max():.0f}")
+        print(f"   within-CTA spread of end times: mean {cta_spread.mean():.1f} max {cta_spread.max():.1f} us; CTA end p50 {np.median(cta_max):.0f} max {cta_max.max():.0f}")
+        print(f"   corr(per-SM sum of sweep-rows, per-SM last end) = {np.corrcoef(sm_rows, sm_end)[0, 1]:.2f}; corr(per-SM envs, last end) = {np.corrcoef(sm_cnt, sm_end)[0, 1]:.2f}")
+        cta_rows_max = np.array([rows[cta == c].max() for c in np.unique(cta)])
+        cta_rows_sum = np.array([rows[cta == c].sum() for c in np.unique(cta)])
+        print(f"   corr(CTA max sweep-rows, CTA end) = {np.corrcoef(cta_rows_max, cta_max)[0, 1]:.2f}; corr(CTA sum sweep-rows, CTA end) = {np.corrcoef(cta_rows_sum, cta_max)[0, 1]:.2f}")
         print(f"step {i}: kernel span {end.max():.1f} us; env start p50 {np.median(start):.1f} max {start.max():.1f}; "
               f"env duration mean {dur.mean():.1f} p50 {np.median(dur):.1f} p90 {np.percentile(dur, 90):.1f} p99 {np.percentile(dur, 99):.1f} max {dur.max():.1f}")
         print(f"   end-time percentiles us: " + " ".join(f"p{q}={np.percentile(end, q):.0f}" for q in (10, 50, 90, 99, 99.9, 100)))

@@ -28,7 +28,7 @@ for mode in ("side", "side_first", "inline", "in_env_kernel", "side"):
         k = max(i - 20, 0)
         ev[k][0].record()
         if mode == "inline":
-            sim.history_shift(side_stream=False)
+            sim.history_shift(side_stream=False, reorder=False)
         if mode == "side_first":                 # side stream, enqueued before the dynamics kernel: gets the SMs first
             sim.history_shift(side_stream=True)
         sim.step(pool[i % 8])
