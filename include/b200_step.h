@@ -13,6 +13,9 @@
  *                        GenesisSimulator.post_physics_step   legged_gym/simulator/genesis_simulator.py:35-60
  *                        (+ everything those call: height scan :552-610, OOB :612-628, callbacks,
  *                        check_termination, compute_reward, reset_idx, compute_observations)
+ *   b200_history_shift   deque / torch.cat frame stacking     legged_gym/envs/base/legged_robot_ts.py:86-97 (side stream)
+ *   b200_env_step        LeggedRobot.step, all of the above   legged_gym/envs/base/legged_robot.py:37-53, with HOST buffers:
+ *                        + the host copies of the rollout     rsl_rl/runners/on_policy_runner.py:118-139
  *   b200_reset_all       BaseTask.reset -> reset_idx(all)     legged_gym/envs/base/base_task.py:60-64
  *
  * All state lives in caller-owned device buffers (torch CUDA tensors in the Python host layer) that are
