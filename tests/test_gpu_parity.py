@@ -454,3 +454,30 @@ def test_edited_config_runs_on_the_generic_instantiation(golden):
         _close(out["rew_buf"], o["rew_buf"], what=f"step {t}: rew")
         _close(out["obs_buf"], o["obs_buf"], what=f"step {t}: obs")
         _close(out[f"critic_obs{sim._parity}"], o["critic_obs_buf"], what=f"step {t}: critic")
+
+
+@pytest.mark.parametrize("task", ["go2", "go2_ts", "go2_cat", "go2_wtw", "go2_cts", "go2_ee", "go2_dreamwaq", "tron1_pf", "tron1_pf_ee"])
+def test_every_preset_steps_and_resets_with_ragged_ctas(task):
+    """Every preset through all three step entry points at an env count that leaves ragged CTAs in both kernels, then a
+    forced time-out of every env: finite outputs, all envs reset, the preset instantiation of the env kernel in use, and
+    the return tuple of the reference's step for that task family."""
+    from hcr_genesis_lr_cl_b200 import task_spec as T
+    spec = T.PRESETS[task]()
+    N = 45
+    env = _env(spec, N, load_terrain(spec) if spec.heightfield else None)
+    assert env.simulator.env_kernel_variant == task
+    first = env.reset()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    rew, rst, tmo = env.simulator.make_host_step_buffers()
+    arity = {"go2": 5, "go2_wtw": 5, "tron1_pf": 5, "go2_ts": 7, "go2_cat": 7, "go2_cts": 7, "go2_ee": 6, "tron1_pf_ee": 6, "go2_dreamwaq": 8}[task]
+    for t in range(3):
+        a = torch.randn(N, spec.num_actions, generator=g)
+        for out in (env.step(a.cuda()), env.step_host(a.pin_memory(), rew, rst, tmo), env.step_two_kernels(a.cuda())):
+            assert len(out) == arity and len(first) == arity - 3
+    env.episode_length_buf = torch.full((N,), int(env.max_episode_length), dtype=torch.int32)
+    out = env.step(torch.zeros(N, spec.num_actions).cuda())
+    torch.cuda.synchronize()
+    assert bool(env.reset_buf.all()) and bool(env.time_out_buf.all()) and int(env.episode_length_buf.max()) == 0
+    for x in out[:arity - 3]:
+        assert x is None or torch.isfinite(x).all()
+    assert torch.isfinite(env.rew_buf).all()
