@@ -139,3 +139,33 @@ def test_heightfield_contact_normal_on_a_slope():
     assert abs(tot[2] / 300 - m.total_mass * 9.81) < 0.1 * m.total_mass * 9.81
     assert abs(tot[0]) < 0.1 * tot[2] and abs(tot[1]) < 0.1 * tot[2]
     assert np.abs(st[0, 7:9]).max() < 0.05
+
+
+@pytest.mark.parametrize("robot,names", [("go2", GO2_DOF_NAMES), ("tron1_pf", TRON1_PF_DOF_NAMES)])
+def test_work_energy_balance_with_joint_torques_and_gravity(robot, names):
+    """dE/dt = tau . qd for the floating-base tree in flight (E = kinetic + potential from the independent numpy
+    kinematics): pins M^-1, the RNE bias incl. gravity and the applied-torque path of the oracle together."""
+    m = load_robot_model(robot, names, armature=0.0)
+    nj = len(names)
+    dt = 0.0002
+    o = PhysicsOracle(m, default_params(dt=dt))
+    rng = np.random.default_rng(5)
+    st = _state(1, z=3.0)
+    qq = rng.normal(size=4)
+    st[0, 3:7] = qq / np.linalg.norm(qq)
+    st[0, 7:13] = rng.normal(size=6)
+    q = rng.uniform(-0.1, 0.1, (1, nj)) + (Q0[None] if robot == "go2" else 0)
+    qd = rng.normal(size=(1, nj))
+    envp, jp = _env(1, nj, arm=0.0)
+    tau = rng.uniform(-1, 1, (1, nj)) * 0.13 * m.effort[None, :]   # small / short enough that no joint reaches a limit in the window
+    E0 = momentum_energy(m, st[0], q[0], qd[0], gravity=9.81)[2]
+    work = 0.0
+    lim = m.dof_limits
+    for _ in range(100):
+        qd_before = qd[0].copy()
+        o.substep(st, q, qd, tau, envp, jp)
+        work += float(tau[0] @ (0.5 * (qd_before + qd[0]))) * dt       # trapezoid of the joint power
+    E1 = momentum_energy(m, st[0], q[0], qd[0], gravity=9.81)[2]
+    assert (q[0] > lim[:, 0]).all() and (q[0] < lim[:, 1]).all()
+    assert abs(work) > 0.5                                             # the torques did inject a visible amount of energy
+    assert abs((E1 - E0) - work) < 0.02 * abs(work) + 0.02, (E1 - E0, work)
