@@ -39,7 +39,6 @@ struct B200Handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool fork_recorded = false;
     bool side_enabled = true;
-    bool preshift_on_side = false;
     int preshift_parity = -1;      // parity the stacks have been shifted for (-1: none pending)
     int env_preset = -1;           // instantiation of the env kernel: index into env_presets.inc, -1 = generic
     float *d_actions = nullptr;    // staging of b200_env_step's host actions

@@ -111,7 +111,7 @@ enum B200TaskI {
     TI_NUM_LEVELS, TI_NUM_TYPES, TI_HF_ROWS, TI_HF_COLS, TI_SEED_LO, TI_SEED_HI,
     TI_N_REWARDS, TI_TERMINATION_COL,                            /* column of "termination" in episode_sums or -1 */
     TI_N_PEN, TI_N_TERM, TI_N_CS,
-    TI_ENV_OFFSET,
+    TI_ENV_OFFSET,                                               /* global id of local env 0 (multi-GPU sharding; keys the RNG) */
     TI_CAT,                                                      /* 1: compute CaT constraint probabilities (9 constraints) */
     TI_CAT_GLOBAL_STANDSTILL,                                    /* 1: reproduce the [N,N] broadcast of go2_cat.py:177-178 */
     TI_DOUBLE_SHIFT,                                             /* 1: tasks that shift the action history again after the step (R6) */
@@ -120,7 +120,7 @@ enum B200TaskI {
     TI_BEHAVIOR_INTERVAL,                                        /* int(behavior resampling_time / dt) */
     TI_NUM_TEACHER,                                              /* go2_cts: global envs [0, num_teacher) are teacher envs (go2_cts.py:93-99) */
     TI_CLEARANCE_MODE,                                           /* foot clearance / labels relative to: 0 nothing, 1 mean, 2 max of the 9 heights */
-    TI_N_SUMS,                                                   /* columns of episode_sums: rewards (+termination) (+9 cstr_*) */                                               /* global id of local env 0 (multi-GPU sharding; keys the RNG) */
+    TI_N_SUMS,                                                   /* columns of episode_sums: rewards (+termination) (+9 cstr_*) */
     TI_REWARD_IDS,                                               /* [B200_MAX_REWARDS] active term ids, evaluation order */
     TI_FEET_LINKS = TI_REWARD_IDS + B200_MAX_REWARDS,            /* [B200_MAX_FEET]  */
     TI_PEN_LINKS = TI_FEET_LINKS + B200_MAX_FEET,                /* [B200_MAX_LINKS] */
