@@ -167,7 +167,10 @@ int b200_history_shift(B200Handle *h, int parity, void *stream) {
     const int *ti = h->task.i;
     const bool stacks = ti[TI_OBS_KIND] >= 1;        // the task keeps frame stacks
     // the order of the NEXT dynamics launch from the cost of the PREVIOUS one (the launch in flight writes the other halves)
-    const bool reorder = h->order_enabled && h->bufs.dyn_order && h->bufs.dyn_cost && h->dyn_launches >= 2;
+    // (only when the dynamics launch of this step is already enqueued -- fork_recorded -- or we run in order on the caller's
+    // stream: a side-stream sort racing ahead of a dynamics launch that reads the same half would be a data race)
+    const bool reorder = h->order_enabled && h->bufs.dyn_order && h->bufs.dyn_cost && h->dyn_launches >= 2 &&
+                         (h->fork_recorded || !h->side_enabled);
     if (!stacks && !reorder) return 0;
     cudaStream_t s = (cudaStream_t)stream, run = s;
     if (h->side_enabled) {
