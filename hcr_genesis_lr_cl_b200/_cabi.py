@@ -195,6 +195,11 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     si("TI_DOUBLE_SHIFT", spec.double_shift_actions); si("TI_N_SUMS", len(spec.episode_sum_names()))
     si("TI_GAIT", spec.gait_enabled); si("TI_CLEARANCE_MODE", spec.foot_clearance_mode)
     si("TI_NUM_TEACHER", spec.num_teacher)
+    if spec.randomize_ctrl_delay:
+        lo, hi = (int(v) for v in spec.ctrl_delay_step_range)
+        if not 0 <= lo <= hi <= H["B200_MAX_CTRL_DELAY"]:
+            raise ValueError("ctrl_delay_step_range outside [0, B200_MAX_CTRL_DELAY]")
+        si("TI_CTRL_DELAY", 1); si("TI_CTRL_DELAY_LO", lo); si("TI_CTRL_DELAY_HI", hi)
     si("TI_BEHAVIOR", spec.behavior_enabled); si("TI_BEHAVIOR_INTERVAL", max(int(spec.behavior_resampling_time / spec.dt), 1))
     for k, v in enumerate(feet):
         si("TI_FEET_LINKS", v, k)
@@ -243,6 +248,7 @@ def buffer_shapes(spec: T.TaskSpec, model: RobotModel, N: int) -> "OrderedDict[s
         critic_obs0=(N, max(w["critic"], 1)), critic_obs1=(N, max(w["critic"], 1)),
         rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), gait_state=(N, H["B200_GAIT_STATE"]), height_cells=(N, P, 2), stats=(stats_base(nsum) + STATS_RING * (max(nsum, 1) + H["B200_STATS_EXTRA"]),), cstr_prob=(N,), global_flags=(4,),
         next_state_buf=(N, w["obs"] if spec.obs_kind == "go2_dreamwaq" else 1), dyn_cost=(2, N), dyn_order=(2, N),
+        action_queue=(N, (int(spec.ctrl_delay_step_range[1]) + 1) * A if spec.randomize_ctrl_delay else 1), action_delay=(N,),
     )
     return OrderedDict((name, (shp[name], _NP[ct])) for name, ct in BUFFER_FIELDS)
 

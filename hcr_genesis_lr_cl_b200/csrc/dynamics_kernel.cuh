@@ -244,12 +244,21 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 
     for (int e = lane; e < 48; e += 32) ws[WS_WARM + e] = B.contact_warm[env * 48 + e];
     // ---------------- pre-step: action history, last_* (legged_robot.py:230-252, genesis_simulator.py:21-24) ----------------
+    float a_applied = 0.f;           // lane j < A: the action joint j is driven with (the clipped action, or a delayed one)
     if (lane < A) {
         const int o = env * A + lane;
         const float a = fminf(fmaxf(actions_in[o], -tf[TF_CLIP_ACTIONS]), tf[TF_CLIP_ACTIONS]);
         B.llast_actions[o] = B.last_actions[o];
         B.last_actions[o] = B.actions[o];
         B.actions[o] = a;
+        a_applied = a;
+        if (T.i[TI_CTRL_DELAY]) {        // legged_robot.py:240-245: push the action into the env's queue, drive with slot action_delay
+            const int depth = T.i[TI_CTRL_DELAY_HI] + 1, dly = min(max(B.action_delay[env], 0), depth - 1);
+            float *qu = B.action_queue + (size_t)env * depth * A + lane;
+            for (int d = depth - 1; d > 0; d--) qu[d * A] = qu[(d - 1) * A];
+            qu[0] = a;
+            a_applied = qu[dly * A];
+        }
         B.last_dof_vel[o] = B.dof_vel[o];
         if (lane < 3 * T.i[TI_F]) B.last_feet_vel[env * 3 * T.i[TI_F] + lane] = B.feet_vel[env * 3 * T.i[TI_F] + lane];
         if (lane < 3) { B.last_base_lin_vel[env * 3 + lane] = B.base_lin_vel[env * 3 + lane]; B.last_base_ang_vel[env * 3 + lane] = B.base_ang_vel[env * 3 + lane]; }
@@ -258,7 +267,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     for (int k = 0; k < 3; k++) {
         const int j = 3 * c + k, o = env * A + j;
         q[k] = B.dof_pos[o]; qd[k] = B.dof_vel[o];
-        const float a = fminf(fmaxf(actions_in[o], -tf[TF_CLIP_ACTIONS]), tf[TF_CLIP_ACTIONS]);
+        const float a = __shfl_sync(B200_FULL_MASK, a_applied, j);
         tgt[k] = a * tf[TF_ACTION_SCALE] + tf[TF_DEFAULT_DOF_POS + j];
         kp[k] = B.kp_scale[o] * tf[TF_KP]; kd[k] = B.kd_scale[o] * tf[TF_KD];
         arm[k] = T.i[TI_RAND_ARMATURE] ? env_arm : ms[MS_BODY + (1 + j) * B200_BODY_STRIDE + 19];

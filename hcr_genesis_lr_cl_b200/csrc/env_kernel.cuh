@@ -738,6 +738,11 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
 #undef DR_PUT
         if (lane < 3 * F) B.last_feet_vel[env * 3 * F + lane] = 0.f;
         for (int e = lane; e < 48; e += 32) B.contact_warm[env * 48 + e] = 0.f;    // teleported: the contact warm start is stale
+        if (ti[TI_CTRL_DELAY]) {                                                     // legged_robot.py:144-148
+            const int depth = ti[TI_CTRL_DELAY_HI] + 1, span = ti[TI_CTRL_DELAY_HI] - ti[TI_CTRL_DELAY_LO] + 1;
+            for (int e = lane; e < depth * A; e += 32) B.action_queue[(size_t)env * depth * A + e] = 0.f;
+            if (lane == 0) B.action_delay[env] = ti[TI_CTRL_DELAY_LO] + min((int)__fmul_rn(rng.u(SITE_CTRL_DELAY, 0), (float)span), span - 1);
+        }
         if (ti[TI_BEHAVIOR]) { gtime = 0.f; gphi = 0.f; }                               // go2_wtw.py:139-142
         else if (ti[TI_GAIT]) {                                                     // tron1_pf_ee.py:221-228
             th0 = __fadd_rn(tf[TF_GAIT_THETA_LEFT], rng.u(SITE_GAIT, 0));

@@ -72,6 +72,9 @@ class FusedLeggedEnv:
         self.feet_air_time, self.fail_buf = b["feet_air_time"], b["fail_buf"]
         self.episode_sums = {n: b["episode_sums"][:, i] for i, n in enumerate(self.sum_names)}
         self.cstr_prob = b["cstr_prob"]
+        if spec.randomize_ctrl_delay:                         # legged_robot.py:405-409
+            self.action_queue = b["action_queue"].view(self.num_envs, -1, spec.num_actions)
+            self.action_delay = b["action_delay"]
         if spec.behavior_enabled:                             # go2_wtw.py:354-375 + 320-352: ranges start at mid / min
             def mid(r):
                 return [(r[0] + r[1]) / 2] * 2

@@ -196,6 +196,9 @@ class B200Simulator:
             self._randomize_joint_damping(ids)
         if s.randomize_pd_gain:
             self._randomize_pd_gain(ids)
+        if s.randomize_ctrl_delay:                     # legged_robot.py:405-409 (drawn by LeggedRobot there; the queue is ours)
+            lo, hi = (int(v) for v in s.ctrl_delay_step_range)
+            b["action_delay"][:] = torch.randint(lo, hi + 1, (N,), generator=gen).to(self._tdev, torch.int32)
 
     def _init_buffers(self):
         s = self.spec

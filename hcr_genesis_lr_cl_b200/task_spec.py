@@ -47,7 +47,8 @@ CAT_CONSTRAINTS = ["torque", "dof_vel", "action_rate", "base_height", "collision
 
 # Philox draw sites (see oracle/philox.py and csrc/philox.cuh)
 SITE_CMD_RESAMPLE, SITE_PUSH, SITE_LEVEL, SITE_CMD_RESET, SITE_DOF, SITE_ROOT, SITE_FRICTION, SITE_MASS, SITE_COM, \
-    SITE_KP, SITE_KD, SITE_ARMATURE, SITE_JFRICTION, SITE_JDAMPING, SITE_OBS_NOISE, SITE_GAIT, SITE_HOST, SITE_BEHAVIOR, SITE_BEHAVIOR_RESET = range(19)
+    SITE_KP, SITE_KD, SITE_ARMATURE, SITE_JFRICTION, SITE_JDAMPING, SITE_OBS_NOISE, SITE_GAIT, SITE_HOST, SITE_BEHAVIOR, SITE_BEHAVIOR_RESET, \
+    SITE_CTRL_DELAY = range(20)
 
 
 @dataclass
@@ -196,6 +197,8 @@ class TaskSpec:
     double_shift_actions: bool = False      # go2_cat.py:127-130 shifts the action history a second time (R6)
     dof_vel_limits: List[float] = field(default_factory=list)
     # engine knobs (no reference counterpart; DESIGN.md "physics formulation")
+    randomize_ctrl_delay: bool = False     # legged_robot.py:240-245: the simulator is driven with a per-env delayed action
+    ctrl_delay_step_range: List[int] = field(default_factory=lambda: [0, 1])
     num_teacher: int = 0              # go2_cts: envs [0, num_teacher) are teacher envs (extras only, go2_cts.py:93-99)
     pgs_iterations: int = 30          # sweep cap of the projected Gauss-Seidel contact solver
     pgs_tolerance: float = 1e-4       # stop when max|df| over a sweep <= tol * (1 + max|f|)
@@ -393,6 +396,8 @@ class TaskSpec:
             randomize_joint_armature=d.randomize_joint_armature, joint_armature_range=list(d.joint_armature_range),
             randomize_joint_friction=d.randomize_joint_friction, joint_friction_range=list(d.joint_friction_range),
             randomize_joint_damping=d.randomize_joint_damping, joint_damping_range=list(d.joint_damping_range),
+            randomize_ctrl_delay=bool(getattr(d, "randomize_ctrl_delay", False)),
+            ctrl_delay_step_range=[int(x) for x in getattr(d, "ctrl_delay_step_range", [0, 1])],
             obs_scale_lin_vel=n.obs_scales.lin_vel, obs_scale_ang_vel=n.obs_scales.ang_vel,
             obs_scale_dof_pos=n.obs_scales.dof_pos, obs_scale_dof_vel=n.obs_scales.dof_vel,
             obs_scale_height=n.obs_scales.height_measurements,

@@ -48,6 +48,7 @@ extern "C" {
 #define B200_MAX_REWARDS 33
 #define B200_MAX_GAITS 4
 #define B200_STATS_EXTRA 3    /* per-step statistics beyond the episode sums: terrain level, cstr prob | teacher level, student level */
+#define B200_MAX_CTRL_DELAY 7 /* largest ctrl_delay_step_range[1] */
 #define B200_GAIT_STATE 20   /* floats per env in gait_state */
 /* columns of one gait_state row: theta[4] (FL,FR,RL,RR or L,R), gait time, phase, gait period, base-height /
  * foot-clearance / pitch targets (go2_wtw behaviour parameters), clock[8] = sin[feet], cos[feet] */
@@ -118,6 +119,8 @@ enum B200TaskI {
     TI_GAIT,                                                     /* 1: biped periodic-gait state (theta, gait time, phi, clock) */
     TI_BEHAVIOR,                                                 /* 1: per-env behaviour params (gait period, targets) resampled (go2_wtw) */
     TI_BEHAVIOR_INTERVAL,                                        /* int(behavior resampling_time / dt) */
+    TI_CTRL_DELAY,                                               /* 1: per-env action delay queue (legged_robot.py:240-245) */
+    TI_CTRL_DELAY_LO, TI_CTRL_DELAY_HI,                          /* domain_rand.ctrl_delay_step_range (inclusive); queue depth = HI + 1 */
     TI_NUM_TEACHER,                                              /* go2_cts: global envs [0, num_teacher) are teacher envs (go2_cts.py:93-99) */
     TI_CLEARANCE_MODE,                                           /* foot clearance / labels relative to: 0 nothing, 1 mean, 2 max of the 9 heights */
     TI_N_SUMS,                                                   /* columns of episode_sums: rewards (+termination) (+9 cstr_*) */
@@ -147,7 +150,8 @@ enum B200Site {
     SITE_HOST,        /* host-side scalar draws keyed env = 0xffffffff: idx 0 = sit-pose coin (R8), 1 / 2 = gait choice of the
                          callback / reset resampling of the step (R7) */
     SITE_BEHAVIOR,    /* idx 0..3: gait period, base height, foot clearance, pitch targets (callback resampling) */
-    SITE_BEHAVIOR_RESET
+    SITE_BEHAVIOR_RESET,
+    SITE_CTRL_DELAY   /* idx 0: action delay of an env that resets (legged_robot.py:144-148) */
 };
 
 /* phases of b200_env_post_step (bit mask) */
@@ -235,6 +239,8 @@ typedef struct B200Buffers {
     float *contact_warm;        /* [N,48] contact-solver warm start carried between substeps and policy steps: 8 x (sphere id + 1,
                                    f_n, f_t1, f_t2) then 8 x (aux-row code + 1, f); zero = empty */
     float *next_state_buf;      /* [N,num_obs] go2_dreamwaq decoder target (go2_dreamwaq.py:72-80); [N,1] otherwise */
+    float *action_queue;        /* [N, ctrl_delay_hi + 1, A] clipped actions of the last steps, newest first (legged_robot.py:240-245); [N,1] when off */
+    int32_t *action_delay;      /* [N] slot of action_queue the simulator is driven with (re-drawn on reset, legged_robot.py:144-148) */
     /* scheduling state of the dynamics kernel (no reference counterpart; results do not depend on it): per-env cost of the
      * last two launches and the env each warp slot takes in the next ones */
     int32_t *dyn_cost;          /* [2,N] solver work (sweeps x rows) of each env in the launches of either parity */

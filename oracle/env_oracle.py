@@ -116,6 +116,9 @@ class EnvOracle:
             gait_state=z(N, 20),     # theta[4], gait_time, phi, gait_period, base_height_t, foot_clearance_t, pitch_t, clock[8]
         )
         self.st["gait_state"][:, G_PER] = spec.gait_period
+        if spec.randomize_ctrl_delay:                          # legged_robot.py:405-409
+            self.st["action_queue"] = z(N, int(spec.ctrl_delay_step_range[1]) + 1, A)
+            self.st["action_delay"] = np.zeros(N, np.int32)
         # go2_wtw host-side behaviour state (go2_wtw.py:352-372): curriculum-mutable ranges and the number of unlocked gaits
         mid = lambda r: [(r[0] + r[1]) / 2] * 2
         self.beh_ranges = dict(gait_period=mid(spec.gait_period_range), base_height=mid(spec.base_height_target_range),
@@ -153,6 +156,11 @@ class EnvOracle:
         st["last_base_ang_vel"][:] = st["base_ang_vel"]
         st["last_feet_vel"][:] = st["feet_vel"]
         st["last_dof_vel"][:] = st["qd"]
+        if s.randomize_ctrl_delay:                             # legged_robot.py:240-245: the simulator gets a delayed action
+            qu = st["action_queue"]
+            qu[:, 1:] = qu[:, :-1].copy()
+            qu[:, 0] = a
+            a = qu[np.arange(self.N), st["action_delay"]].copy()
         return a
 
     def pd_torque(self, a, q, qd):
@@ -602,6 +610,11 @@ class EnvOracle:
         o["episode_means"] = {"rew_" + n: np.mean(st["episode_sums"][ids, i], dtype=f32) / f32(s.episode_length_s)
                               for i, n in enumerate(self.sum_names)}
         st["episode_sums"][ids] = 0
+        if s.randomize_ctrl_delay:                             # legged_robot.py:144-148: randint(lo, hi + 1) from one uniform draw
+            lo, hi = (int(v) for v in s.ctrl_delay_step_range)
+            st["action_queue"][ids] = 0
+            ud = self.u(T.SITE_CTRL_DELAY, [0], ids)[:, 0]
+            st["action_delay"][ids] = lo + np.minimum((ud * f32(hi - lo + 1)).astype(np.int32), hi - lo)
         if self.widths["hist"]:
             st["obs_hist"][ids] = 0
             st["critic_hist"][ids] = 0

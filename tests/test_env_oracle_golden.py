@@ -6,11 +6,11 @@ import pytest
 from golden_util import load_golden, load_terrain, out_at, phys_at, spec_for
 from oracle.env_oracle import EnvOracle
 
-INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels")
+INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels", "action_delay")
 
 
 @pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32", "go2_wtw_n32", "go2_cts_n32", "go2_ee_n32",
-                                  "go2_dreamwaq_n32"])
+                                  "go2_dreamwaq_n32", "go2_ts_delay_n32"])
 def test_env_oracle_reproduces_reference(name):
     g, s0 = load_golden(name)
     spec = spec_for(g)
@@ -28,7 +28,8 @@ def test_env_oracle_reproduces_reference(name):
         eo.num_gaits = int(s0["num_gaits"])
     resets = 0
     for t in range(T_):
-        eo.pre_step(g["actions"][t])
+        delay_before = eo.st["action_delay"].copy() if spec.randomize_ctrl_delay else None
+        applied = eo.pre_step(g["actions"][t])
         o = eo.post_step(phys_at(g, t))
         ref = out_at(g, t)
         st = eo.st
@@ -39,6 +40,12 @@ def test_env_oracle_reproduces_reference(name):
                     com_bias=st["com_bias"], kp_scale=st["kp_scale"], kd_scale=st["kd_scale"], rand_push_vels=st["rand_push_vels"],
                     actions_buf=st["actions"], last_actions=st["last_actions"], llast_actions=st["llast_actions"],
                     terrain_levels=st["terrain_levels"], end_q=st["q"], end_qd=st["qd"], gait_state=st["gait_state"])
+        if spec.randomize_ctrl_delay:
+            mine.update(action_queue=st["action_queue"], action_delay=st["action_delay"])
+            # what the simulator was driven with (legged_robot.py:240-245) = the recorded queue at the env's delay slot
+            keep = ~ref["reset_buf"].astype(bool)
+            rq = ref["action_queue"].reshape(N, -1, spec.num_actions)
+            assert np.array_equal(applied[keep], rq[np.arange(N), delay_before][keep]) and (delay_before > 0).any()
         for k, r in ref.items():
             if k not in mine:
                 continue

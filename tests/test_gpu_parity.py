@@ -52,6 +52,13 @@ def test_env_kernel_matches_reference_golden(name):
     _golden_run(name, fused_histories=True)
 
 
+def test_control_delay_queue_matches_reference_golden():
+    """domain_rand.randomize_ctrl_delay (legged_robot.py:144-148,240-245): the dynamics kernel pushes the clipped action
+    into the env's queue and drives the joints with the delayed slot, the env kernel clears the queue and redraws the
+    delay on reset; runs on the generic env-kernel instantiation (no shipped config enables the delay)."""
+    _golden_run("go2_ts_delay_n32", fused_histories=True)
+
+
 def test_env_kernel_shifts_histories_itself_without_preshift():
     """Plugin-mode / fallback path: no b200_history_shift call, the env kernel moves the frame stacks."""
     _golden_run("go2_ts_n32", fused_histories=False)
@@ -69,7 +76,7 @@ def _golden_run(name, fused_histories):
     env.common_step_counter = int(s0["common_step_counter"])
     env.command_ranges["lin_vel_x"] = [float(x) for x in s0["cmd_range_x"]]
     _load_behavior(env, s0)
-    ints = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels")
+    ints = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels", "action_delay")
     for t in range(T_):
         a = torch.from_numpy(g["actions"][t]).cuda()
         sim.step(a)                                   # pre-step bookkeeping (+ our own physics, overwritten below)
@@ -539,3 +546,37 @@ def test_long_closed_loop_rollout_tracks_the_oracle(task):
     for w in range(0, TT, 10):
         g, r = np.mean(rew_g[w:w + 10]), np.mean(rew_o[w:w + 10])
         assert abs(g - r) <= 1e-3 * abs(r) + 2e-5, f"steps {w}-{w + 9}: mean reward {g:.6f} vs {r:.6f}"
+
+
+def test_dynamics_kernel_drives_joints_with_the_delayed_action():
+    """randomize_ctrl_delay: joints are driven with action_queue[env, action_delay[env]] after the push of the new
+    action (legged_robot.py:240-245); compared with the oracle substep fed that action."""
+    from emu_util import oracle_params, oracle_policy_step
+    from hcr_genesis_lr_cl_b200 import task_spec as T
+    from oracle.physics import PhysicsOracle
+    spec = T.go2_spec()
+    spec.randomize_ctrl_delay, spec.ctrl_delay_step_range = True, [0, 3]
+    N, A, depth = 128, spec.num_actions, 4
+    st, model = _random_state(spec, N, None, seed=17)
+    rng = np.random.default_rng(6)
+    queue = rng.normal(size=(N, depth, A)).astype(np.float32)
+    delay = rng.integers(0, depth, N).astype(np.int32)
+    st["action_queue"], st["action_delay"] = queue.reshape(N, -1), delay
+    env = _env(spec, N, None)
+    sim = env.simulator
+    assert sim.env_kernel_variant == "generic"
+    sim.load_state(st)
+    full = sim.get_state()
+    actions = rng.normal(size=(N, A)).astype(np.float32)
+    sim.step(torch.from_numpy(actions).cuda())
+    out = sim.get_state()
+    pushed = np.concatenate([actions[:, None], queue[:, :-1]], axis=1)
+    assert np.array_equal(out["action_queue"].reshape(N, depth, A), pushed)
+    assert np.array_equal(out["actions"], actions)                       # the undelayed action feeds obs / rewards
+    applied = pushed[np.arange(N), delay]
+    assert (delay > 0).any() and not np.array_equal(applied, actions)
+    orc = PhysicsOracle(model, oracle_params(spec, model), None, precision="f32")
+    ref = oracle_policy_step(spec, model, orc, full, applied)
+    for k, name in (("q", "dof_pos"), ("qd", "dof_vel"), ("torques", "torques"), ("base_pos", "base_pos")):
+        r = np.asarray(ref[k], np.float64)
+        assert np.abs(out[name].reshape(r.shape) - r).max() < 1e-4 * max(1.0, np.abs(r).max()), k

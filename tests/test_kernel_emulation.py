@@ -11,7 +11,7 @@ from oracle.physics import PhysicsOracle
 
 PH = dict(base_pos="base_pos", base_quat_wxyz="base_quat_wxyz", base_lin_w="base_lin_w", base_ang_w="base_ang_w",
           q="dof_pos", qd="dof_vel", torques="torques", link_force="link_contact_forces", feet_pos="feet_pos", feet_vel="feet_vel")
-INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels")
+INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contacts", "terrain_levels", "action_delay")
 
 
 @pytest.mark.parametrize("name,steps", [("go2_ts_n32", 5), ("go2_n32", 4), ("go2_cat_n32", 5), ("tron1_pf_n32", 5), ("tron1_pf_ee_n32", 5), ("go2_wtw_n32", 5),
@@ -19,6 +19,12 @@ INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contact
 def test_emulated_env_kernel_matches_reference_golden(name, steps):
     """The preset-specialised instantiation b200_create selects for this descriptor (asserted: not the generic one)."""
     _run_golden(name, steps, preshift=True)
+
+
+def test_emulated_env_kernel_with_control_delay_matches_reference_golden():
+    """domain_rand.randomize_ctrl_delay on (no shipped config enables it -> generic instantiation): the env kernel clears
+    the action queue and redraws the delay of envs that reset (legged_robot.py:144-148)."""
+    _run_golden("go2_ts_delay_n32", 8, preshift=True, specialized=False)
 
 
 @pytest.mark.parametrize("name", ["go2_ts_n32", "tron1_pf_ee_n32", "go2_wtw_n32", "go2_cat_n32"])
@@ -44,6 +50,9 @@ def _run_golden(name, steps, preshift, specialized=True):
         # pre-step bookkeeping of the dynamics kernel, then the recorded post-physics state
         a = np.clip(g["actions"][t], -spec.clip_actions, spec.clip_actions)
         B["llast_actions"][:] = B["last_actions"]; B["last_actions"][:] = B["actions"]; B["actions"][:] = a
+        if spec.randomize_ctrl_delay:          # the queue push of the dynamics kernel's pre-step (legged_robot.py:240-245)
+            qu = B["action_queue"].reshape(N, -1, spec.num_actions)
+            qu[:, 1:] = qu[:, :-1].copy(); qu[:, 0] = a
         B["last_dof_vel"][:] = B["dof_vel"]; B["last_feet_vel"][:] = B["feet_vel"]
         for k, b in PH.items():
             B[b][...] = phys_at(g, t)[k].reshape(B[b].shape)

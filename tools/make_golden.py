@@ -115,6 +115,16 @@ class Injector:
                 u = float(philox.uniform(self.seed, self.env.common_step_counter, 0xFFFFFFFF, T.SITE_HOST, 2 if self.in_reset else 1))
                 return torch.tensor([min(int(u * high), high - 1)])
             torch.randint = randint
+        elif getattr(env.cfg.domain_rand, "randomize_ctrl_delay", False):
+            def randint_delay(low, high, size, **k):        # legged_robot.py:147-148: per-env action delay on reset
+                prev = (self.site, self.col, self.call)
+                self.site, self.col, self.call = T.SITE_CTRL_DELAY, 0, 0
+                try:
+                    u = self.draw(tuple(size))
+                finally:
+                    self.site, self.col, self.call = prev
+                return low + torch.clamp((u * (high - low)).to(torch.long), max=high - low - 1)
+            torch.randint = randint_delay
         env._reset_dofs = self.ctx(env._reset_dofs, T.SITE_DOF)
         env._reset_root_states = self.ctx(env._reset_root_states, T.SITE_ROOT)
         if hasattr(env, "_reset_root_states_sit_pose"):
@@ -184,6 +194,8 @@ def snapshot(env, spec, sum_names):
         st["terrain_levels"] = st["terrain_types"] = np.zeros(env.num_envs, np.int32)
     if hasattr(env, "gait_time"):
         st["gait_state"] = pack_gait(env)
+    if getattr(env.cfg.domain_rand, "randomize_ctrl_delay", False):
+        st["action_queue"], st["action_delay"] = n(env.action_queue), n(env.action_delay)
     if hasattr(env, "critic_history"):                       # go2_wtw names its deques obs_history / critic_history
         st["obs_hist"] = np.concatenate([n(x) for x in env.obs_history], axis=1)
         st["critic_hist"] = np.concatenate([n(x) for x in env.critic_history], axis=1)
@@ -212,12 +224,16 @@ def main():
     ap.add_argument("--name", default=None)
     ap.add_argument("--contact-links", nargs="*", default=None, help="override asset.contact_state_link_names (SURVEY R1)")
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--ctrl-delay", type=int, default=0, help="enable domain_rand.randomize_ctrl_delay with step range [0, N]")
     args = ap.parse_args()
     import torch
 
     def edit(cfg):
         if args.contact_links is not None:
             cfg.asset.contact_state_link_names = list(args.contact_links)
+        if args.ctrl_delay > 0:
+            cfg.domain_rand.randomize_ctrl_delay = True
+            cfg.domain_rand.ctrl_delay_step_range = [0, args.ctrl_delay]
 
     env, cfg, _ = make_env(args.task, args.envs, cfg_edit=edit)
     spec = T.TaskSpec.from_reference_cfg(cfg, args.task)
@@ -307,6 +323,8 @@ def main():
             o["link_contact_states"] = n(sim._link_contact_states)
         if hasattr(env, "cstr_prob"):
             o["cstr_prob"] = n(env.cstr_prob)
+        if args.ctrl_delay > 0:
+            o["action_queue"], o["action_delay"] = n(env.action_queue).reshape(N, -1), n(env.action_delay).astype(np.int32)
         if args.task == "go2_wtw":
             o["privileged_obs_buf"] = n(ret[1])
             o["gait_state"] = pack_gait(env)
@@ -334,6 +352,7 @@ def main():
         rec["terrain_crc"] = np.int64(int(np.asarray(sim._height_samples.numpy(), np.int64).sum()))
     rec["meta/task"] = np.array(args.task)
     rec["meta/seed"] = np.int64(spec.seed)
+    rec["meta/ctrl_delay"] = np.int64(args.ctrl_delay)
     rec["meta/contact_links"] = np.array(spec.contact_state_link_names)
     rec["meta/sum_names"] = np.array(sum_names)
     out = os.path.join(ROOT, "tests", "golden", name + ".npz")
