@@ -199,6 +199,8 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
     N = 512
     st, model = _random_state(spec, N, terrain, seed=11)
     rng = np.random.default_rng(5)
+    st["base_pos"][7::61, 0] += 500.0                        # out of the terrain bounds: teleported home (genesis_simulator.py:612-628)
+    st["base_pos"][11::61, 1] -= 500.0
     st["episode_length"] = rng.integers(0, 1001, N).astype(np.int32)
     st["episode_length"][::7] = 499
     st["fail_buf"] = rng.integers(0, 6, N).astype(np.int32)
@@ -283,6 +285,9 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
         _close(out["commands"], eo.st["commands"], what=f"step {t}: commands")
         _close(out["dof_pos"], eo.st["q"], what=f"step {t}: reset dof_pos")
         _close(out["base_pos"], eo.st["base_pos"], what=f"step {t}: reset base_pos")
+        if t == 0:                                           # the out-of-bounds envs are back inside after the first post step
+            assert np.abs(out["base_pos"][7::61, 0] - st["base_pos"][7::61, 0]).min() > 100 and np.abs(mid["base_pos"][7::61, 0] - st["base_pos"][7::61, 0]).max() < 10
+            _close(out["feet_pos"], o["feet_pos"], what="step 0: feet_pos after the out-of-bounds teleport")
         for k in ("friction", "added_mass", "com_bias", "kp_scale", "kd_scale"):
             _close(out[k], eo.st[k], what=f"step {t}: {k}")
         if o["episode_means"] is not None:                                   # extras["episode"] of this step (device ring)
