@@ -255,9 +255,14 @@ class FusedLeggedEnv:
         if self.spec.cmd_curriculum and self.common_step_counter % int(self.max_episode_length) == 0 \
                 and "tracking_lin_vel" in self.sum_names:
             i = self.sum_names.index("tracking_lin_vel")
-            cnt = stats[n].clamp(min=1.0)
-            self._pending_curriculum = (stats[i] / cnt / self.max_episode_length, stats[n].clone(),
-                                        (stats[:n] / cnt / self.max_episode_length) if self.spec.behavior_enabled else None)
+            tot = stats[:n + 1].clone()                       # episode sums of the envs that reset this step + their count
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                # env-sharded job: the curricula are scalars of the WHOLE job; 4 (n + 1) bytes once per max_episode_length steps
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            cnt = tot[n].clamp(min=1.0)
+            self._pending_curriculum = (tot[i] / cnt / self.max_episode_length, tot[n].clone(),
+                                        (tot[:n] / cnt / self.max_episode_length) if self.spec.behavior_enabled else None)
 
     def _apply_pending_curriculum(self):
         if self._pending_curriculum is None:
