@@ -44,6 +44,15 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// sin / cos of a bounded angle on the special-function unit (2 MUFU instead of the ~40-instruction sincosf)
+__device__ __forceinline__ void fast_sincosf(float x, float *s, float *c) {
+#ifdef B200_WARP_EMU
+    *s = sinf(x); *c = cosf(x);
+#else
+    __sincosf(x, s, c);
+#endif
+}
+
 // sum over the first C lanes (C = 2 or 4), result in every lane: two butterfly rounds inside the aligned 4-lane group,
 // then one broadcast -- the chain quantities of the dynamics kernel live in lanes 0..C-1 only.
 template <int C>

@@ -136,7 +136,7 @@ __device__ __forceinline__ m33 quat_to_mat(float w, float x, float y, float z) {
     return R;
 }
 __device__ __forceinline__ m33 axis_angle(f3 a, float th) {
-    float s, c; sincosf(th, &s, &c);
+    float s, c; fast_sincosf(th, &s, &c);               // |th| stays within the joint limits (< 2 pi): MUFU precision, ~5e-7
     const float t = 1 - c; m33 R;
     R.m[0] = c + a.x * a.x * t;       R.m[1] = a.x * a.y * t - a.z * s; R.m[2] = a.x * a.z * t + a.y * s;
     R.m[3] = a.y * a.x * t + a.z * s; R.m[4] = c + a.y * a.y * t;       R.m[5] = a.y * a.z * t - a.x * s;
@@ -157,8 +157,9 @@ __device__ __forceinline__ void terrain_query(const TerrainDev &tr, float hs, fl
     float dhx, dhy;
     if (u + w <= 1.f) { dhx = h10 - h00; dhy = h01 - h00; h = h00 + u * dhx + w * dhy; }
     else { dhx = h11 - h01; dhy = h11 - h10; h = h11 - (1.f - u) * dhx - (1.f - w) * dhy; }
-    const f3 g = mk3(-dhx / hs, -dhy / hs, 1.f);
-    n = g * (1.f / sqrtf(dot3(g, g)));
+    const float ihs = 1.f / hs;
+    const f3 g = mk3(-dhx * ihs, -dhy * ihs, 1.f);
+    n = g * rsqrtf(dot3(g, g));
 }
 
 __device__ __forceinline__ float impedance(const float *tf, float pos) {
@@ -563,7 +564,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             const int d = lane - 3 * (lane / 3);
             const f3 xc = mk3(ct[0], ct[1], ct[2]), n = mk3(ct[3], ct[4], ct[5]);
             const f3 e = fabsf(n.x) < 0.9f ? mk3(1.f, 0.f, 0.f) : mk3(0.f, 1.f, 0.f);
-            f3 t1 = e - n * dot3(e, n); t1 = t1 * (1.f / sqrtf(dot3(t1, t1)));
+            f3 t1 = e - n * dot3(e, n); t1 = t1 * rsqrtf(dot3(t1, t1));
             const f3 t2 = cross3(n, t1);
             dir = d == 0 ? n : (d == 1 ? t1 : t2);
             kind = d; rpos = d == 0 ? ct[6] : 0.f; wkey = ct[9];
@@ -777,14 +778,14 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             const float wn = sqrtf(dot3(wb, wb));
             float dw = 1.f, dx = 0.f, dy = 0.f, dz = 0.f;
             if (wn > 1e-12f) {
-                float sn2, cs2; sincosf(0.5f * wn * h, &sn2, &cs2);
+                float sn2, cs2; fast_sincosf(0.5f * wn * h, &sn2, &cs2);
                 const float s = sn2 / wn; dw = cs2; dx = wb.x * s; dy = wb.y * s; dz = wb.z * s;
             }
             const float nw = dw * Qw - dx * Qx - dy * Qy - dz * Qz;
             const float nx = dw * Qx + dx * Qw + dy * Qz - dz * Qy;
             const float ny = dw * Qy - dx * Qz + dy * Qw + dz * Qx;
             const float nz = dw * Qz + dx * Qy - dy * Qx + dz * Qw;
-            const float inv = 1.f / sqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
+            const float inv = rsqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
             Qw = nw * inv; Qx = nx * inv; Qy = ny * inv; Qz = nz * inv;
         }
         __syncwarp();
