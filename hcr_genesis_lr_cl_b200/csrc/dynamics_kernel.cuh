@@ -147,7 +147,8 @@ __device__ __forceinline__ m33 axis_angle(f3 a, float th) {
 // terrain height and unit normal under world point (x, y): the triangle of the heightfield cell below it
 __device__ __forceinline__ void terrain_query(const TerrainDev &tr, float hs, float vs, float border, float x, float y, float &h, f3 &n) {
     if (tr.hf == nullptr) { h = 0.f; n = mk3(0.f, 0.f, 1.f); return; }
-    const float gx = (x + border) / hs, gy = (y + border) / hs;
+    const float ihs = 1.f / hs;                    // grid coordinates by the reciprocal, like the oracle (same cell on both sides)
+    const float gx = (x + border) * ihs, gy = (y + border) * ihs;
     int i = (int)floorf(gx), j = (int)floorf(gy);
     i = max(0, min(i, tr.rows - 2)); j = max(0, min(j, tr.cols - 2));
     const float u = fminf(fmaxf(gx - (float)i, 0.f), 1.f), w = fminf(fmaxf(gy - (float)j, 0.f), 1.f);
@@ -157,17 +158,16 @@ __device__ __forceinline__ void terrain_query(const TerrainDev &tr, float hs, fl
     float dhx, dhy;
     if (u + w <= 1.f) { dhx = h10 - h00; dhy = h01 - h00; h = h00 + u * dhx + w * dhy; }
     else { dhx = h11 - h01; dhy = h11 - h10; h = h11 - (1.f - u) * dhx - (1.f - w) * dhy; }
-    const float ihs = 1.f / hs;
     const f3 g = mk3(-dhx * ihs, -dhy * ihs, 1.f);
     n = g * rsqrtf(dot3(g, g));
 }
 
 __device__ __forceinline__ float impedance(const float *tf, float pos) {
-    const float x = fabsf(pos) / tf[TF_WIDTH];
+    const float x = __fdividef(fabsf(pos), tf[TF_WIDTH]);
     if (x >= 1.f) return tf[TF_DMAX];
     const float mid = tf[TF_MID], p = tf[TF_POWER];
     float y;
-    if (p == 2.f) y = x < mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);     // the shipped solimp: no powf
+    if (p == 2.f) y = x < mid ? __fdividef(x * x, mid) : 1.f - __fdividef((1.f - x) * (1.f - x), 1.f - mid);     // the shipped solimp: no powf
     else if (x < mid) y = powf(x, p) / powf(mid, p - 1.f);
     else y = 1.f - powf(1.f - x, p) / powf(1.f - mid, p - 1.f);
     return tf[TF_D0] + y * (tf[TF_DMAX] - tf[TF_D0]);
@@ -670,8 +670,8 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         __syncwarp();
         if (lane < R) {
             const float aref = -bd * vel - kk * imp * rpos;
-            Rr = (1.f - imp) / imp * Arr;
-            idd = 1.f / (Arr + Rr);
+            Rr = __fdividef(1.f - imp, imp) * Arr;
+            idd = __fdividef(1.f, Arr + Rr);
             wres = ja - aref;
             for (int s2 = 0; s2 < R; s2++) wres += ws[WS_AM + s2 * 33 + lane] * ws[WS_FV + s2 * 4];
         }
@@ -779,7 +779,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             float dw = 1.f, dx = 0.f, dy = 0.f, dz = 0.f;
             if (wn > 1e-12f) {
                 float sn2, cs2; fast_sincosf(0.5f * wn * h, &sn2, &cs2);
-                const float s = sn2 / wn; dw = cs2; dx = wb.x * s; dy = wb.y * s; dz = wb.z * s;
+                const float s = __fdividef(sn2, wn); dw = cs2; dx = wb.x * s; dy = wb.y * s; dz = wb.z * s;
             }
             const float nw = dw * Qw - dx * Qx - dy * Qy - dz * Qz;
             const float nx = dw * Qx + dx * Qw + dy * Qz - dz * Qy;

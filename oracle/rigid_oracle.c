@@ -123,7 +123,8 @@ typedef struct {
 static void terrain_query(const int16_t *hf, int rows, int cols, const float *prm, real x, real y, real *h, v3 *n) {
     if (rows == 0) { *h = 0; *n = V(0, 0, 1); return; }
     real hs = prm[P_HSCALE], vs = prm[P_VSCALE];
-    real gx = (x + prm[P_BORDER]) / hs, gy = (y + prm[P_BORDER]) / hs;
+    real ihs = (real)1 / hs;                       /* grid coordinates by the reciprocal (one division per query, as the kernel) */
+    real gx = (x + prm[P_BORDER]) * ihs, gy = (y + prm[P_BORDER]) * ihs;
     int i = (int)floor(gx), j = (int)floor(gy);
     if (i < 0) i = 0; if (i > rows - 2) i = rows - 2;
     if (j < 0) j = 0; if (j > cols - 2) j = cols - 2;
@@ -134,7 +135,7 @@ static void terrain_query(const int16_t *hf, int rows, int cols, const float *pr
     real dhx, dhy;
     if (u + w <= 1) { dhx = h10 - h00; dhy = h01 - h00; *h = h00 + u * dhx + w * dhy; }
     else { dhx = h11 - h01; dhy = h11 - h10; *h = h11 - (1 - u) * dhx - (1 - w) * dhy; }
-    v3 g = V(-dhx / hs, -dhy / hs, 1);
+    v3 g = V(-dhx * ihs, -dhy * ihs, 1);
     *n = scl(g, 1 / sqrt(dot(g, g)));
 }
 

@@ -62,6 +62,7 @@ static inline float __fsub_rn(float a, float b) { volatile float r = a - b; retu
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
+static inline float __fdividef(float a, float b) { return a / b; }
 static inline float atomicAdd(float *p, float v) { float o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline int atomicOr(int *p, int v) { int o = *p; *p = o | v; return o; }
