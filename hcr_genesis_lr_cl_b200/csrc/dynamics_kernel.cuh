@@ -80,7 +80,8 @@ struct TerrainDev {
 #define WS_FV (WS_JR + 320)             // row force vectors [32][4]
 #define WS_LF (WS_FV + 128)             // link forces [17*3]
 #define WS_WARM (WS_LF + 52)            // PGS warm start [48]: 8 x (sphere id + 1, f_n, f_t1, f_t2), 8 x (aux code + 1, f)
-#define WS_TOTAL (WS_WARM + 48)
+#define WS_PD (WS_WARM + 48)             // per chain lane [4][16]: tgt(3) kp(3) kd(3) arm+h*dmp(3) dmp(3) -- constant over the substeps,
+#define WS_TOTAL (WS_PD + 64)            // kept here rather than in 15 registers that are live across the whole substep
 static_assert(WS_AUX + 32 <= WS_MI, "aliased inputs must fit under the A matrix");
 
 #define MS_BODY 0
@@ -238,7 +239,8 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     float Qw = B.base_quat_wxyz[env * 4], Qx = B.base_quat_wxyz[env * 4 + 1], Qy = B.base_quat_wxyz[env * 4 + 2], Qz = B.base_quat_wxyz[env * 4 + 3];
     f3 vb = mk3(B.base_lin_w[env * 3], B.base_lin_w[env * 3 + 1], B.base_lin_w[env * 3 + 2]);
     f3 wb = mk3(B.base_ang_w[env * 3], B.base_ang_w[env * 3 + 1], B.base_ang_w[env * 3 + 2]);
-    float q[3], qd[3], tgt[3], kp[3], kd[3], arm[3], dmp[3], fls[3], tau[3];
+    float q[3], qd[3], fls[3], tau[3];
+    float *pd = ws + WS_PD + 16 * c;        // this lane's chain (lanes >= C alias the last chain and write the same values)
     const float mass_add = B.added_mass[env], fric_ratio = B.friction[env];
     const f3 com_shift = mk3(B.com_bias[env * 3], B.com_bias[env * 3 + 1], B.com_bias[env * 3 + 2]);
     const float env_arm = B.joint_armature[env], env_dmp = B.joint_damping[env], env_fls = B.joint_friction[env];
@@ -269,10 +271,11 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         const int j = 3 * c + k, o = env * A + j;
         q[k] = B.dof_pos[o]; qd[k] = B.dof_vel[o];
         const float a = __shfl_sync(B200_FULL_MASK, a_applied, j);
-        tgt[k] = a * tf[TF_ACTION_SCALE] + tf[TF_DEFAULT_DOF_POS + j];
-        kp[k] = B.kp_scale[o] * tf[TF_KP]; kd[k] = B.kd_scale[o] * tf[TF_KD];
-        arm[k] = T.i[TI_RAND_ARMATURE] ? env_arm : ms[MS_BODY + (1 + j) * B200_BODY_STRIDE + 19];
-        dmp[k] = T.i[TI_RAND_JDAMPING] ? env_dmp : 0.f;
+        const float arm_k = T.i[TI_RAND_ARMATURE] ? env_arm : ms[MS_BODY + (1 + j) * B200_BODY_STRIDE + 19];
+        const float dmp_k = T.i[TI_RAND_JDAMPING] ? env_dmp : 0.f;
+        pd[k] = a * tf[TF_ACTION_SCALE] + tf[TF_DEFAULT_DOF_POS + j];
+        pd[3 + k] = B.kp_scale[o] * tf[TF_KP]; pd[6 + k] = B.kd_scale[o] * tf[TF_KD];
+        pd[9 + k] = arm_k + h * dmp_k; pd[12 + k] = dmp_k;
         fls[k] = T.i[TI_RAND_JFRICTION] ? env_fls : 0.f;
         tau[k] = 0.f;
     }
@@ -287,7 +290,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         // ---------------- PD torque (genesis_simulator.py:630-642) ----------------
         if (!last_pass) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) tau[k] = kp[k] * (tgt[k] - q[k]) - kd[k] * qd[k];
+            for (int k = 0; k < 3; k++) tau[k] = pd[3 + k] * (pd[k] - q[k]) - pd[6 + k] * qd[k];
         }
         // ---------------- forward kinematics, velocities, RNE, CRBA along this lane's chain ----------------
         const m33 R0 = quat_to_mat(Qw, Qx, Qy, Qz);
@@ -354,7 +357,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             BP[k] = Pk; BL[k] = Lk;
 #pragma unroll
             for (int i2 = 0; i2 <= k; i2++) Dm[tri(k, i2)] = dot3(a_[i2], Lk) + dot3(sv_[i2], Pk);
-            Dm[tri(k, k)] += arm[k] + h * dmp[k];
+            Dm[tri(k, k)] += pd[9 + k];
         }
         // base body + reduction of chain roots
         SIn cb;
@@ -432,7 +435,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 const float eff = ms[MS_BODY + (1 + 3 * c + k) * B200_BODY_STRIDE + 18];
-                rl[k] = fminf(fmaxf(tau[k], -eff), eff) - dmp[k] * qd[k] - biasl[k];
+                rl[k] = fminf(fmaxf(tau[k], -eff), eff) - pd[12 + k] * qd[k] - biasl[k];
             }
 #pragma unroll
             for (int a2 = 0; a2 < 3; a2++) tl[a2] = Di[tri(a2, 0)] * rl[0] + Di[tri(a2, 1)] * rl[1] + Di[tri(a2, 2)] * rl[2];
