@@ -1026,7 +1026,7 @@ __device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200B
     extern __shared__ float smem[];
     const TiView<S> ti{T.i};
     constexpr int nwarps = ENV_WARPS_PER_BLOCK;            // the launch geometry is fixed: slab offsets fold to constants
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // (pinning them like the dynamics kernel does costs 1 us here)
     const int env0 = blockIdx.x * nwarps, env = env0 + warp;
     const int N = ti[TI_NUM_ENVS];
     uint64_t *bar = (uint64_t *)smem;
