@@ -624,8 +624,9 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 #pragma unroll
                 for (int a2 = 0; a2 < 3; a2++) {
                     float s = (l2 == cl) ? tl[a2] : 0.f;
-#pragma unroll
-                    for (int e = 0; e < 6; e++) s -= mi[6 + a2 * 6 + e] * Yb[e];
+                    const float2 *g2 = reinterpret_cast<const float2 *>(mi + 6 + a2 * 6);      // 8-byte aligned rows of G
+                    const float2 g01 = g2[0], g23 = g2[1], g45 = g2[2];
+                    s -= g01.x * Yb[0]; s -= g01.y * Yb[1]; s -= g23.x * Yb[2]; s -= g23.y * Yb[3]; s -= g45.x * Yb[4]; s -= g45.y * Yb[5];
                     Yl[l2][a2] = s;
                 }
             }
@@ -644,14 +645,15 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         // this lane's column of A = J M^-1 J^T
         float Arr = 1.f;
         for (int r = 0; r < R; r++) {
-            const float *jr = ws + WS_JR + r * 10;
+            // one row of J, the same for every lane: five 8-byte broadcast loads (rows are 40 bytes apart, WS_JR is 16-byte aligned)
+            const float2 *jr2 = reinterpret_cast<const float2 *>(ws + WS_JR + r * 10);
+            const float2 j01 = jr2[0], j23 = jr2[1], j45 = jr2[2], j67 = jr2[3], j89 = jr2[4];
             float a2 = 0.f;
-#pragma unroll
-            for (int e = 0; e < 6; e++) a2 += jr[e] * Yb[e];
-            const int clr = __float_as_int(jr[9]);
+            a2 += j01.x * Yb[0]; a2 += j01.y * Yb[1]; a2 += j23.x * Yb[2]; a2 += j23.y * Yb[3]; a2 += j45.x * Yb[4]; a2 += j45.y * Yb[5];
+            const int clr = __float_as_int(j89.y);
 #pragma unroll
             for (int l2 = 0; l2 < C; l2++)
-                if (clr == l2) a2 += jr[6] * Yl[l2][0] + jr[7] * Yl[l2][1] + jr[8] * Yl[l2][2];
+                if (clr == l2) a2 += j67.x * Yl[l2][0] + j67.y * Yl[l2][1] + j89.x * Yl[l2][2];
             ws[WS_AM + r * 33 + lane] = a2;
             if (r == lane) Arr = a2;
         }
