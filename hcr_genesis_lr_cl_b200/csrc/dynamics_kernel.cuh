@@ -80,7 +80,7 @@ struct TerrainDev {
 #define WS_FV (WS_JR + 320)             // row force vectors [32][4]
 #define WS_LF (WS_FV + 128)             // link forces [17*3]
 #define WS_WARM (WS_LF + 52)            // PGS warm start [48]: 8 x (sphere id + 1, f_n, f_t1, f_t2), 8 x (aux code + 1, f)
-#define WS_PD (WS_WARM + 48)             // per chain lane [4][16]: tgt(3) kp(3) kd(3) arm+h*dmp(3) dmp(3) -- constant over the substeps,
+#define WS_PD (WS_WARM + 48)             // per chain lane [4][16]: tgt(3) kp(3) kd(3) arm+h*dmp(3) dmp(3) frictionloss(1) -- constant over the substeps,
 #define WS_TOTAL (WS_PD + 64)            // kept here rather than in 15 registers that are live across the whole substep
 static_assert(WS_AUX + 32 <= WS_MI, "aliased inputs must fit under the A matrix");
 
@@ -239,7 +239,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     float Qw = B.base_quat_wxyz[env * 4], Qx = B.base_quat_wxyz[env * 4 + 1], Qy = B.base_quat_wxyz[env * 4 + 2], Qz = B.base_quat_wxyz[env * 4 + 3];
     f3 vb = mk3(B.base_lin_w[env * 3], B.base_lin_w[env * 3 + 1], B.base_lin_w[env * 3 + 2]);
     f3 wb = mk3(B.base_ang_w[env * 3], B.base_ang_w[env * 3 + 1], B.base_ang_w[env * 3 + 2]);
-    float q[3], qd[3], fls[3], tau[3];
+    float q[3], qd[3], tau[3];
     float *pd = ws + WS_PD + 16 * c;        // this lane's chain (lanes >= C alias the last chain and write the same values)
     const float mass_add = B.added_mass[env], fric_ratio = B.friction[env];
     const f3 com_shift = mk3(B.com_bias[env * 3], B.com_bias[env * 3 + 1], B.com_bias[env * 3 + 2]);
@@ -276,7 +276,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         pd[k] = a * tf[TF_ACTION_SCALE] + tf[TF_DEFAULT_DOF_POS + j];
         pd[3 + k] = B.kp_scale[o] * tf[TF_KP]; pd[6 + k] = B.kd_scale[o] * tf[TF_KD];
         pd[9 + k] = arm_k + h * dmp_k; pd[12 + k] = dmp_k;
-        fls[k] = T.i[TI_RAND_JFRICTION] ? env_fls : 0.f;
+        if (k == 0) pd[15] = T.i[TI_RAND_JFRICTION] ? env_fls : 0.f;       // frictionloss bound: one value per env
         tau[k] = 0.f;
     }
     float mu = tf[TF_GEOM_MU] * fric_ratio; mu = fmaxf(mu, tf[TF_TERRAIN_MU]);
@@ -530,7 +530,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             limsign[k] = lo_v ? 1.f : -1.f;
             limpos[k] = lo_v ? q[k] - Bd[16] : Bd[17] - q[k];
             const unsigned bl = __ballot_sync(B200_FULL_MASK, leg && (lo_v || hi_v));
-            const unsigned bf = __ballot_sync(B200_FULL_MASK, leg && fls[k] > 0.f);
+            const unsigned bf = __ballot_sync(B200_FULL_MASK, leg && pd[15] > 0.f);
 #pragma unroll
             for (int cc = 0; cc < C; cc++) { limmask |= ((bl >> cc) & 1u) << (3 * cc + k); flsmask |= ((bf >> cc) & 1u) << (3 * cc + k); }
         }
@@ -547,7 +547,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                 }
                 if ((flsmask >> j) & 1u) {
                     const int slot = nlim + __popc(flsmask & below);
-                    if (slot < nlim + nfls) { float *ax = ws + WS_AUX + 4 * slot; ax[0] = __int_as_float(j); ax[1] = 1.f; ax[2] = 0.f; ax[3] = fls[k]; }
+                    if (slot < nlim + nfls) { float *ax = ws + WS_AUX + 4 * slot; ax[0] = __int_as_float(j); ax[1] = 1.f; ax[2] = 0.f; ax[3] = pd[15]; }
                 }
             }
         }
@@ -611,11 +611,14 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 #pragma unroll
                 for (int e = 0; e < 6; e++) rb[e] -= mi[6 + e] * Jl[0] + mi[12 + e] * Jl[1] + mi[18 + e] * Jl[2];
             }
+            float Sv[21];                        // the Schur inverse back from shared memory (21 registers not carried through
+#pragma unroll                                   // the collision / aux-row phases)
+            for (int e = 0; e < 21; e++) Sv[e] = ws[WS_MI + 4 * 24 + e];
 #pragma unroll
             for (int i2 = 0; i2 < 6; i2++) {
                 float s = 0.f;
 #pragma unroll
-                for (int j2 = 0; j2 < 6; j2++) s += Sinv[tri(i2, j2)] * rb[j2];
+                for (int j2 = 0; j2 < 6; j2++) s += Sv[tri(i2, j2)] * rb[j2];
                 Yb[i2] = s;
             }
 #pragma unroll
@@ -746,11 +749,13 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         }
         PHASE_SYNC();
         // ---------------- total acceleration, contact forces, integration ----------------
-        float accb[6], accl[3] = {al[0], al[1], al[2]};
+        float accb[6], accl[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) accl[k] = ws[WS_AF + 6 + 3 * c + k];     // smooth accelerations back from shared memory
         {
             const float fz = lane < R ? f : 0.f;
 #pragma unroll
-            for (int e = 0; e < 6; e++) accb[e] = ab[e] + warp_sum(Yb[e] * fz);
+            for (int e = 0; e < 6; e++) accb[e] = ws[WS_AF + e] + warp_sum(Yb[e] * fz);
 #pragma unroll
             for (int l2 = 0; l2 < C; l2++)
 #pragma unroll
