@@ -30,14 +30,24 @@
 #endif
 // The substep body is ~7k SASS instructions of mostly straight-line code (~110 KB), larger than the 32 KB L1.5
 // instruction cache: warps that drift apart each stream it from L2 and the kernel becomes instruction-fetch bound
-// (ncu: stall_no_instruction on top, profiles/r1b).  A CTA barrier at each phase boundary keeps the 4 warps of a CTA
-// in the same code region so one fetch serves all of them: 0.545 -> 0.414 ms per launch at 4096 envs.
+// (ncu: stall_no_instruction on top, profiles/r1b).  A CTA barrier at the top of a substep and after its
+// contact solve keeps the warps of a CTA in the same code region so one fetch serves all of them.
 #ifndef DYN_NO_PHASE_SYNC
 #define PHASE_SYNC() __syncthreads()
 #define DYN_PHASE_SYNCS_PER_SUBSTEP 5
 #else
 #define PHASE_SYNC()
 #endif
+#ifndef DYN_SYNC_MASK
+#define DYN_SYNC_MASK 17          // which of the five phase barriers are kept: A top of the substep, B after FK, C before collision, D before
+                                  // the rows, E after the PGS.  A + E do all the good (profiles/r1B_sweep_sync_mask.log: none 0.313, A 0.284,
+                                  // A+E 0.281, all five 0.284 ms per step)
+#endif
+#define PHASE_SYNC_A() do { if (DYN_SYNC_MASK & 1) PHASE_SYNC(); } while (0)
+#define PHASE_SYNC_B() do { if (DYN_SYNC_MASK & 2) PHASE_SYNC(); } while (0)
+#define PHASE_SYNC_C() do { if (DYN_SYNC_MASK & 4) PHASE_SYNC(); } while (0)
+#define PHASE_SYNC_D() do { if (DYN_SYNC_MASK & 8) PHASE_SYNC(); } while (0)
+#define PHASE_SYNC_E() do { if (DYN_SYNC_MASK & 16) PHASE_SYNC(); } while (0)
 #ifndef DYN_MIN_BLOCKS
 #define DYN_MIN_BLOCKS 4      // resident CTAs per SM the register allocator must allow: 4 x 7 warps = 28 envs per SM at 72 regs/thread
 #endif
@@ -286,7 +296,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     int cost = 0;                    // solver work of this env in this launch (sweeps x rows, + rows built): feeds the next launches' order
     for (int sub = 0; sub <= T.i[TI_DECIMATION]; sub++) {
         const bool last_pass = sub == T.i[TI_DECIMATION];   // kinematics-only pass for the outputs
-        PHASE_SYNC();
+        PHASE_SYNC_A();
         // ---------------- PD torque (genesis_simulator.py:630-642) ----------------
         if (!last_pass) {
 #pragma unroll
@@ -342,7 +352,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         __syncwarp();
         if (last_pass) break;
 
-        PHASE_SYNC();
+        PHASE_SYNC_B();
         // backward pass along the chain: composite inertias, bias forces, CRBA columns
         float Dm[6];           // chain block, lower tri (00,10,11,20,21,22)
         f3 BP[3], BL[3];       // base coupling: column k of B^T = (P_k (lin rows), L_k (ang rows))
@@ -467,7 +477,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             for (int e = 0; e < 6; e++) ws[WS_AF + e] = ab[e];
         }
 
-        PHASE_SYNC();
+        PHASE_SYNC_C();
         // ---------------- collision detection: two spheres per lane ----------------
         float sdist[2]; f3 sn[2], sx[2]; bool act[2];
 #pragma unroll
@@ -554,7 +564,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         __syncwarp();
         const int R = 3 * nc + nlim + nfls;
 
-        PHASE_SYNC();
+        PHASE_SYNC_D();
         // ---------------- constraint rows: one per lane ----------------
         float Jb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Jl[3] = {0.f, 0.f, 0.f};
         int cl = -1, kind = 5;          // 0 normal, 1/2 tangents, 3 limit, 4 frictionloss, 5 unused
@@ -747,7 +757,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             const int a2 = lane - 3 * nc;
             ws[WS_WARM + 32 + 2 * a2] = wkey; ws[WS_WARM + 32 + 2 * a2 + 1] = f;
         }
-        PHASE_SYNC();
+        PHASE_SYNC_E();
         // ---------------- total acceleration, contact forces, integration ----------------
         float accb[6], accl[3];
 #pragma unroll
@@ -859,9 +869,9 @@ __device__ __forceinline__ void stage_model(const ModelDev &M, const TaskDev &T,
 __device__ __forceinline__ void dynamics_idle_warp(const TaskDev &T) {
 #ifndef DYN_NO_PHASE_SYNC
     for (int sub = 0; sub <= T.i[TI_DECIMATION]; sub++) {
-        __syncthreads();
+        PHASE_SYNC_A();
         if (sub == T.i[TI_DECIMATION]) break;
-        __syncthreads(); __syncthreads(); __syncthreads(); __syncthreads();
+        PHASE_SYNC_B(); PHASE_SYNC_C(); PHASE_SYNC_D(); PHASE_SYNC_E();
     }
 #endif
 }
