@@ -48,6 +48,8 @@ def env_kernel_items(spec: T.TaskSpec, model: RobotModel):
     if spec.gait_enabled:
         reads["gait_state"] = 20 * f
         writes["gait_state"] = 20 * f
+    if spec.obs_kind == "go2_dreamwaq":
+        writes["next_state_buf"] = w["obs"] * f
     return reads, writes
 
 
