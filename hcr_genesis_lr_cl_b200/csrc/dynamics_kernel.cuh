@@ -369,28 +369,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             for (int i2 = 0; i2 <= k; i2++) Dm[tri(k, i2)] = dot3(a_[i2], Lk) + dot3(sv_[i2], Pk);
             Dm[tri(k, k)] += pd[9 + k];
         }
-        // base body + reduction of chain roots
-        SIn cb;
-        f3 fnb, ffb;
-        {
-            const float *Bd = ms + MS_BODY;
-            const f3 cm = mul(R0, mk3(Bd[6], Bd[7], Bd[8]) + com_shift);
-            SIn sb = si_body(Bd[9] + mass_add, cm, Bd + 10, R0);
-            const f3 aw = mk3(0.f, 0.f, 0.f), av = cross3(vb, wb) + mk3(0.f, 0.f, tf[TF_GRAV]);
-            f3 LA, PA, LV, PV;
-            si_apply(sb, aw, av, LA, PA);
-            si_apply(sb, wb, vb, LV, PV);
-            fnb = LA + cross3(wb, LV) + cross3(vb, PV);
-            ffb = PA + cross3(wb, PV);
-            cb = sb;
-            cb.m += lead_sum<C>(comp.m);
-            cb.h.x += lead_sum<C>(comp.h.x); cb.h.y += lead_sum<C>(comp.h.y); cb.h.z += lead_sum<C>(comp.h.z);
-#pragma unroll
-            for (int e = 0; e < 6; e++) cb.I[e] += lead_sum<C>(comp.I[e]);
-            fnb.x += lead_sum<C>(fns.x); fnb.y += lead_sum<C>(fns.y); fnb.z += lead_sum<C>(fns.z);
-            ffb.x += lead_sum<C>(ffs.x); ffb.y += lead_sum<C>(ffs.y); ffb.z += lead_sum<C>(ffs.z);
-        }
-        // chain block inverse (3x3 SPD), G = Dinv B^T, Schur complement
+        // chain block inverse (3x3 SPD), G = Dinv B^T
         float Di[6], G[3][6];
         {
             const float i00 = rsqrtf(Dm[0]), l10 = Dm[1] * i00, l20 = Dm[3] * i00;
@@ -407,21 +386,85 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         for (int a2 = 0; a2 < 3; a2++)
 #pragma unroll
             for (int e = 0; e < 6; e++) G[a2][e] = Di[tri(a2, 0)] * Bt[0][e] + Di[tri(a2, 1)] * Bt[1][e] + Di[tri(a2, 2)] * Bt[2][e];
+        // chain-local part of the smooth acceleration: tl = Dinv (tau_applied - damping qd - bias)
+        float tl[3];
+        {
+            float rl[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float eff = ms[MS_BODY + (1 + 3 * c + k) * B200_BODY_STRIDE + 18];
+                rl[k] = fminf(fmaxf(tau[k], -eff), eff) - pd[12 + k] * qd[k] - biasl[k];
+            }
+#pragma unroll
+            for (int a2 = 0; a2 < 3; a2++) tl[a2] = Di[tri(a2, 0)] * rl[0] + Di[tri(a2, 1)] * rl[1] + Di[tri(a2, 2)] * rl[2];
+        }
+        // Everything the base needs from the chains is a sum over the C chain lanes of 43 per-chain numbers (composite
+        // inertia 10, bias force 6, Schur terms B D^-1 B^T 21, B tl 6).  Transposed through shared memory: the chain
+        // lanes park their numbers in rows, lane e adds up column e, every lane reads the 43 totals back with vector
+        // loads -- ~75 instructions instead of 43 shuffle reductions of 5.  The scratch is the part of the A matrix that
+        // does not alias the frames (A is only written after the collision phase).
+        constexpr int NRED = 43, RLD = 45, TOT = B200_MAX_CHAINS * RLD;     // totals row: 16-byte aligned for any C
+        float *red = ws + WS_AM + 400;
+        __syncwarp();
+        if (leg) {
+            float *row = red + c * RLD;
+            row[0] = comp.m; row[1] = comp.h.x; row[2] = comp.h.y; row[3] = comp.h.z;
+#pragma unroll
+            for (int e = 0; e < 6; e++) row[4 + e] = comp.I[e];
+            row[10] = fns.x; row[11] = fns.y; row[12] = fns.z; row[13] = ffs.x; row[14] = ffs.y; row[15] = ffs.z;
+#pragma unroll
+            for (int i2 = 0; i2 < 6; i2++)
+#pragma unroll
+                for (int j2 = 0; j2 <= i2; j2++) row[16 + tri(i2, j2)] = Bt[0][i2] * G[0][j2] + Bt[1][i2] * G[1][j2] + Bt[2][i2] * G[2][j2];
+#pragma unroll
+            for (int e = 0; e < 6; e++) row[37 + e] = Bt[0][e] * tl[0] + Bt[1][e] * tl[1] + Bt[2][e] * tl[2];
+        }
+        __syncwarp();
+        {
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < C; cc++) { t0 += red[cc * RLD + lane]; if (lane + 32 < NRED) t1 += red[cc * RLD + lane + 32]; }
+            red[TOT + lane] = t0;
+            if (lane + 32 < NRED) red[TOT + lane + 32] = t1;
+        }
+        __syncwarp();
+        float tot[NRED + 1];
+#pragma unroll
+        for (int e4 = 0; e4 < (NRED + 1) / 4; e4++) {
+            const float4 v = reinterpret_cast<const float4 *>(red + TOT)[e4];
+            tot[4 * e4] = v.x; tot[4 * e4 + 1] = v.y; tot[4 * e4 + 2] = v.z; tot[4 * e4 + 3] = v.w;
+        }
+        // base body + the chain roots
+        SIn cb;
+        f3 fnb, ffb;
+        {
+            const float *Bd = ms + MS_BODY;
+            const f3 cm = mul(R0, mk3(Bd[6], Bd[7], Bd[8]) + com_shift);
+            SIn sb = si_body(Bd[9] + mass_add, cm, Bd + 10, R0);
+            const f3 aw = mk3(0.f, 0.f, 0.f), av = cross3(vb, wb) + mk3(0.f, 0.f, tf[TF_GRAV]);
+            f3 LA, PA, LV, PV;
+            si_apply(sb, aw, av, LA, PA);
+            si_apply(sb, wb, vb, LV, PV);
+            fnb = LA + cross3(wb, LV) + cross3(vb, PV);
+            ffb = PA + cross3(wb, PV);
+            cb = sb;
+            cb.m += tot[0];
+            cb.h.x += tot[1]; cb.h.y += tot[2]; cb.h.z += tot[3];
+#pragma unroll
+            for (int e = 0; e < 6; e++) cb.I[e] += tot[4 + e];
+            fnb.x += tot[10]; fnb.y += tot[11]; fnb.z += tot[12];
+            ffb.x += tot[13]; ffb.y += tot[14]; ffb.z += tot[15];
+        }
         float S[21];
         {
-            // base block: [m 1, [h]x^T ; [h]x, I]  ordering lin(0..2), ang(3..5)
+            // base block: [m 1, [h]x^T ; [h]x, I]  ordering lin(0..2), ang(3..5); minus the Schur terms of the chains
 #pragma unroll
             for (int e = 0; e < 21; e++) S[e] = 0.f;
             S[tri(0, 0)] = S[tri(1, 1)] = S[tri(2, 2)] = cb.m;
             S[tri(3, 1)] = -cb.h.z; S[tri(3, 2)] = cb.h.y; S[tri(4, 0)] = cb.h.z; S[tri(4, 2)] = -cb.h.x; S[tri(5, 0)] = -cb.h.y; S[tri(5, 1)] = cb.h.x;
             S[tri(3, 3)] = cb.I[0]; S[tri(4, 4)] = cb.I[1]; S[tri(5, 5)] = cb.I[2]; S[tri(4, 3)] = cb.I[3]; S[tri(5, 3)] = cb.I[4]; S[tri(5, 4)] = cb.I[5];
 #pragma unroll
-            for (int i2 = 0; i2 < 6; i2++)
-#pragma unroll
-                for (int j2 = 0; j2 <= i2; j2++) {
-                    const float t = Bt[0][i2] * G[0][j2] + Bt[1][i2] * G[1][j2] + Bt[2][i2] * G[2][j2];
-                    S[tri(i2, j2)] -= lead_sum<C>(t);
-                }
+            for (int e = 0; e < 21; e++) S[e] -= tot[16 + e];
         }
         float Sinv[21];
         spd6_inverse(S, Sinv);
@@ -441,17 +484,9 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         // smooth acceleration: a = M^-1 (tau_applied - damping qd - bias)
         float ab[6], al[3];
         {
-            float rl[3], tl[3];
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const float eff = ms[MS_BODY + (1 + 3 * c + k) * B200_BODY_STRIDE + 18];
-                rl[k] = fminf(fmaxf(tau[k], -eff), eff) - pd[12 + k] * qd[k] - biasl[k];
-            }
-#pragma unroll
-            for (int a2 = 0; a2 < 3; a2++) tl[a2] = Di[tri(a2, 0)] * rl[0] + Di[tri(a2, 1)] * rl[1] + Di[tri(a2, 2)] * rl[2];
             float rb[6] = {-ffb.x, -ffb.y, -ffb.z, -fnb.x, -fnb.y, -fnb.z};
 #pragma unroll
-            for (int e = 0; e < 6; e++) rb[e] -= lead_sum<C>(Bt[0][e] * tl[0] + Bt[1][e] * tl[1] + Bt[2][e] * tl[2]);
+            for (int e = 0; e < 6; e++) rb[e] -= tot[37 + e];
 #pragma unroll
             for (int i2 = 0; i2 < 6; i2++) {
                 float s = 0.f;
