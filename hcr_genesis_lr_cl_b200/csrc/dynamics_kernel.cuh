@@ -750,7 +750,10 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                 float fb[3];                                   // the contact's three forces after their updates, in every lane
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                    const float dl = fminf(fmaxf(fmaf(iddn, wres, c1n * f), flo - f), fhi - f);
+                    // only the owner's value is used, and the owner of row r0 + d is a normal row (f >= 0) for d = 0, a
+                    // tangent row (free until the projection) else: no generic box needed here
+                    const float un = fmaf(iddn, wres, c1n * f);
+                    const float dl = d == 0 ? fmaxf(un, -f) : un;
                     const float fn = f + dl;
                     const float delta = __shfl_sync(B200_FULL_MASK, dl, r0 + d);
                     fb[d] = __shfl_sync(B200_FULL_MASK, fn, r0 + d);
