@@ -692,8 +692,27 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         __syncwarp();
         // this lane's column of A = J M^-1 J^T
         float Arr = 1.f;
-        for (int r = 0; r < R; r++) {
-            // one row of J, the same for every lane: five 8-byte broadcast loads (rows are 40 bytes apart, WS_JR is 16-byte aligned)
+        // contact rows: the three rows of a sphere sit on the same chain, whose Y columns are picked once per contact
+        for (int c2 = 0; c2 < nc; c2++) {
+            const float *jc = ws + WS_JR + 30 * c2;
+            const int clr = __float_as_int(jc[9]);
+            float y0 = 0.f, y1 = 0.f, y2 = 0.f;
+#pragma unroll
+            for (int l2 = 0; l2 < C; l2++)
+                if (clr == l2) { y0 = Yl[l2][0]; y1 = Yl[l2][1]; y2 = Yl[l2][2]; }
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                // one row of J, the same for every lane: five 8-byte broadcast loads (rows are 40 bytes apart, WS_JR is 16-byte aligned)
+                const float2 *jr2 = reinterpret_cast<const float2 *>(jc + 10 * d);
+                const float2 j01 = jr2[0], j23 = jr2[1], j45 = jr2[2], j67 = jr2[3], j89 = jr2[4];
+                float a2 = 0.f;
+                a2 += j01.x * Yb[0]; a2 += j01.y * Yb[1]; a2 += j23.x * Yb[2]; a2 += j23.y * Yb[3]; a2 += j45.x * Yb[4]; a2 += j45.y * Yb[5];
+                a2 += j67.x * y0 + j67.y * y1 + j89.x * y2;
+                ws[WS_AM + (3 * c2 + d) * 33 + lane] = a2;
+                if (3 * c2 + d == lane) Arr = a2;
+            }
+        }
+        for (int r = 3 * nc; r < R; r++) {     // auxiliary rows (joint limits, friction loss): any chain
             const float2 *jr2 = reinterpret_cast<const float2 *>(ws + WS_JR + r * 10);
             const float2 j01 = jr2[0], j23 = jr2[1], j45 = jr2[2], j67 = jr2[3], j89 = jr2[4];
             float a2 = 0.f;
