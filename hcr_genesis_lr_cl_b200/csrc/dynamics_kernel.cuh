@@ -762,7 +762,9 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         const float c1n = -(Rr * idd), iddn = -idd;
         int it = 0;
         for (; it < iters; it++) {
-            const float fprev = f;
+            // a lane's force changes only when its own row is visited (or projected, after that), so the terms in f of its
+            // update are those of the sweep's start: once per sweep instead of once per visited row
+            const float fprev = f, cf = c1n * f, dlo = flo - f, dhi = fhi - f;
             // contacts: normal, tangent 1, tangent 2, then projection of the tangential pair onto the friction disc
             for (int c2 = 0; c2 < nc; c2++) {
                 const int r0 = 3 * c2;
@@ -771,9 +773,9 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                 for (int d = 0; d < 3; d++) {
                     // only the owner's value is used, and the owner of row r0 + d is a normal row (f >= 0) for d = 0, a
                     // tangent row (free until the projection) else: no generic box needed here
-                    const float un = fmaf(iddn, wres, c1n * f);
-                    const float dl = d == 0 ? fmaxf(un, -f) : un;
-                    const float fn = f + dl;
+                    const float un = fmaf(iddn, wres, cf);
+                    const float dl = d == 0 ? fmaxf(un, -fprev) : un;
+                    const float fn = fprev + dl;
                     const float delta = __shfl_sync(B200_FULL_MASK, dl, r0 + d);
                     fb[d] = __shfl_sync(B200_FULL_MASK, fn, r0 + d);
                     if (lane == r0 + d) f = fn;
@@ -790,7 +792,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             }
             // joint-limit (f >= 0) and frictionloss (|f| <= bound) rows
             for (int r = 3 * nc; r < R; r++) {
-                const float dl = fminf(fmaxf(fmaf(iddn, wres, c1n * f), flo - f), fhi - f);
+                const float dl = fminf(fmaxf(fmaf(iddn, wres, cf), dlo), dhi);
                 const float delta = __shfl_sync(B200_FULL_MASK, dl, r);
                 if (lane == r) f += dl;
                 wres = fmaf(Arow[33 * r], delta, wres);
