@@ -304,8 +304,15 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         }
         // ---------------- forward kinematics, velocities, RNE, CRBA along this lane's chain ----------------
         const m33 R0 = quat_to_mat(Qw, Qx, Qy, Qz);
-        f3 a_[3], sv_[3], fn_[3], ff_[3];
-        SIn si_[3];
+        f3 a_[3], sv_[3], fn_last = mk3(0.f, 0.f, 0.f), ff_last = fn_last;
+        SIn si_last;
+        si_last.m = 0.f; si_last.h = fn_last;
+#pragma unroll
+        for (int e = 0; e < 6; e++) si_last.I[e] = 0.f;
+        // inertia and bias forces of the chain's first two bodies wait for the backward pass in a part of the A matrix's
+        // storage that nothing else touches before the constraint rows are built (this lane's slot: no barrier needed),
+        // not in 32 registers that the compiler would spill to local memory
+        float *park = ws + WS_AM + 640 + (leg ? lane : C) * 33;
         {
             m33 Rp = R0; f3 op = mk3(0.f, 0.f, 0.f), wp = wb, vp = vb;
             f3 awp = mk3(0.f, 0.f, 0.f), avp = cross3(vb, wb) + mk3(0.f, 0.f, tf[TF_GRAV]);
@@ -331,12 +338,21 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                     const f3 aw = awp + cross3(w, a) * qd[k];
                     const f3 av = avp + (cross3(w, sv) + cross3(v, a)) * qd[k];
                     const f3 cm = o + mul(Rk, mk3(Bd[6], Bd[7], Bd[8]));
-                    si_[k] = si_body(Bd[9], cm, Bd + 10, Rk);
+                    const SIn sik = si_body(Bd[9], cm, Bd + 10, Rk);
                     f3 LA, PA, LV, PV;
-                    si_apply(si_[k], aw, av, LA, PA);
-                    si_apply(si_[k], w, v, LV, PV);
-                    fn_[k] = LA + cross3(w, LV) + cross3(v, PV);
-                    ff_[k] = PA + cross3(w, PV);
+                    si_apply(sik, aw, av, LA, PA);
+                    si_apply(sik, w, v, LV, PV);
+                    const f3 fnk = LA + cross3(w, LV) + cross3(v, PV);
+                    const f3 ffk = PA + cross3(w, PV);
+                    if (k < 2) {
+                        float *pk = park + 16 * k;
+                        pk[0] = sik.m; pk[1] = sik.h.x; pk[2] = sik.h.y; pk[3] = sik.h.z;
+#pragma unroll
+                        for (int e = 0; e < 6; e++) pk[4 + e] = sik.I[e];
+                        pk[10] = fnk.x; pk[11] = fnk.y; pk[12] = fnk.z; pk[13] = ffk.x; pk[14] = ffk.y; pk[15] = ffk.z;
+                    } else {
+                        si_last = sik; fn_last = fnk; ff_last = ffk;
+                    }
                     awp = aw; avp = av;
                 }
                 a_[k] = a; sv_[k] = sv; Rp = Rk; op = o; wp = w; vp = v;
@@ -357,11 +373,18 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         float Dm[6];           // chain block, lower tri (00,10,11,20,21,22)
         f3 BP[3], BL[3];       // base coupling: column k of B^T = (P_k (lin rows), L_k (ang rows))
         float biasl[3];
-        SIn comp = si_[2];
-        f3 fns = fn_[2], ffs = ff_[2];
+        SIn comp = si_last;
+        f3 fns = fn_last, ffs = ff_last;
 #pragma unroll
         for (int k = 2; k >= 0; k--) {
-            if (k < 2) { si_acc(comp, si_[k]); fns = fns + fn_[k]; ffs = ffs + ff_[k]; }
+            if (k < 2) {
+                const float *pk = park + 16 * k;
+                SIn sik;
+                sik.m = pk[0]; sik.h = mk3(pk[1], pk[2], pk[3]);
+#pragma unroll
+                for (int e = 0; e < 6; e++) sik.I[e] = pk[4 + e];
+                si_acc(comp, sik); fns = fns + mk3(pk[10], pk[11], pk[12]); ffs = ffs + mk3(pk[13], pk[14], pk[15]);
+            }
             biasl[k] = dot3(a_[k], fns) + dot3(sv_[k], ffs);
             f3 Lk, Pk; si_apply(comp, a_[k], sv_[k], Lk, Pk);
             BP[k] = Pk; BL[k] = Lk;
