@@ -304,7 +304,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         }
         // ---------------- forward kinematics, velocities, RNE, CRBA along this lane's chain ----------------
         const m33 R0 = quat_to_mat(Qw, Qx, Qy, Qz);
-        f3 a_[3], sv_[3], fn_last = mk3(0.f, 0.f, 0.f), ff_last = fn_last;
+        f3 fn_last = mk3(0.f, 0.f, 0.f), ff_last = fn_last;
         SIn si_last;
         si_last.m = 0.f; si_last.h = fn_last;
 #pragma unroll
@@ -312,7 +312,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         // inertia and bias forces of the chain's first two bodies wait for the backward pass in a part of the A matrix's
         // storage that nothing else touches before the constraint rows are built (this lane's slot: no barrier needed),
         // not in 32 registers that the compiler would spill to local memory
-        float *park = ws + WS_AM + 640 + (leg ? lane : C) * 33;
+        float *park = ws + WS_AM + 640 + (leg ? lane : C) * 41;
         {
             m33 Rp = R0; f3 op = mk3(0.f, 0.f, 0.f), wp = wb, vp = vb;
             f3 awp = mk3(0.f, 0.f, 0.f), avp = cross3(vb, wb) + mk3(0.f, 0.f, tf[TF_GRAV]);
@@ -355,7 +355,8 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                     }
                     awp = aw; avp = av;
                 }
-                a_[k] = a; sv_[k] = sv; Rp = Rk; op = o; wp = w; vp = v;
+                park[32 + 3 * k] = sv.x; park[33 + 3 * k] = sv.y; park[34 + 3 * k] = sv.z;
+                Rp = Rk; op = o; wp = w; vp = v;
             }
         }
         if (lane == 0) {
@@ -373,6 +374,13 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         float Dm[6];           // chain block, lower tri (00,10,11,20,21,22)
         f3 BP[3], BL[3];       // base coupling: column k of B^T = (P_k (lin rows), L_k (ang rows))
         float biasl[3];
+        f3 a_[3], sv_[3];       // joint axes (written by this chain's lane before the barrier above) and their moment arms
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float *axp = ws + WS_AX + (3 * c + k) * 3;
+            a_[k] = mk3(axp[0], axp[1], axp[2]);
+            sv_[k] = mk3(park[32 + 3 * k], park[33 + 3 * k], park[34 + 3 * k]);
+        }
         SIn comp = si_last;
         f3 fns = fn_last, ffs = ff_last;
 #pragma unroll
