@@ -429,6 +429,17 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 #pragma unroll
             for (int a2 = 0; a2 < 3; a2++) tl[a2] = Di[tri(a2, 0)] * rl[0] + Di[tri(a2, 1)] * rl[1] + Di[tri(a2, 2)] * rl[2];
         }
+        // D^-1 and G go to their place for the constraint rows now: the base block below does not keep them in registers
+        // (it reads G back), which is 24 registers less across the 6x6 inverse
+        if (leg) {
+            float *mi = ws + WS_MI + c * 24;
+#pragma unroll
+            for (int e = 0; e < 6; e++) mi[e] = Di[e];
+#pragma unroll
+            for (int a2 = 0; a2 < 3; a2++)
+#pragma unroll
+                for (int e = 0; e < 6; e++) mi[6 + a2 * 6 + e] = G[a2][e];
+        }
         // Everything the base needs from the chains is a sum over the C chain lanes of 43 per-chain numbers (composite
         // inertia 10, bias force 6, Schur terms B D^-1 B^T 21, B tl 6).  Transposed through shared memory: the chain
         // lanes park their numbers in rows, lane e adds up column e, every lane reads the 43 totals back with vector
@@ -499,15 +510,6 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         }
         float Sinv[21];
         spd6_inverse(S, Sinv);
-        if (leg) {
-            float *mi = ws + WS_MI + c * 24;
-#pragma unroll
-            for (int e = 0; e < 6; e++) mi[e] = Di[e];
-#pragma unroll
-            for (int a2 = 0; a2 < 3; a2++)
-#pragma unroll
-                for (int e = 0; e < 6; e++) mi[6 + a2 * 6 + e] = G[a2][e];
-        }
         if (lane == 0) {
 #pragma unroll
             for (int e = 0; e < 21; e++) ws[WS_MI + 4 * 24 + e] = Sinv[e];
@@ -529,7 +531,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             for (int a2 = 0; a2 < 3; a2++) {
                 float s = tl[a2];
 #pragma unroll
-                for (int e = 0; e < 6; e++) s -= G[a2][e] * ab[e];
+                for (int e = 0; e < 6; e++) s -= ws[WS_MI + c * 24 + 6 + a2 * 6 + e] * ab[e];
                 al[a2] = s;
             }
         }
