@@ -55,7 +55,7 @@ def _parse_header():
 
 
 H, BUFFER_FIELDS = _parse_header()
-STATS_RING = 32      # ENV_STATS_RING in csrc/env_kernel.cuh
+STATS_RING = 32      # ENV_STATS_RING in csrc/env_kernel.cuh; load_library() checks it against b200_stats_ring()
 
 
 def stats_base(nsum: int) -> int:
@@ -277,7 +277,12 @@ def load_library() -> ctypes.CDLL:
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: build the CUDA extension first (python -m hcr_genesis_lr_cl_b200.build); "
                            "this backend has no CPU or PyTorch fallback")
-    lib = ctypes.CDLL(path)
+    _lib = bind(ctypes.CDLL(path))
+    return _lib
+
+
+def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
+    """Declare the argument / result types of every entry point of include/b200_step.h on a loaded library."""
     vp, ip, fp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)
     lib.b200_create.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.POINTER(vp)]
     lib.b200_create.restype = ctypes.c_int
@@ -289,6 +294,12 @@ def load_library() -> ctypes.CDLL:
     lib.b200_bind_buffers.restype = ctypes.c_int
     lib.b200_dynamics_step.argtypes = [vp, vp, vp]
     lib.b200_dynamics_step.restype = ctypes.c_int
+    lib.b200_simulator_step.argtypes = [vp, vp, vp]
+    lib.b200_simulator_step.restype = ctypes.c_int
+    lib.b200_stats_ring.argtypes = []
+    lib.b200_stats_ring.restype = ctypes.c_int
+    lib.b200_device.argtypes = [vp]
+    lib.b200_device.restype = ctypes.c_int
     lib.b200_env_post_step.argtypes = [vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, vp]
     lib.b200_env_post_step.restype = ctypes.c_int
     lib.b200_env_step.argtypes = [vp, vp, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, vp, vp, vp, vp]
@@ -313,9 +324,11 @@ def load_library() -> ctypes.CDLL:
     lib.b200_launch_count.restype = ctypes.c_longlong
     lib.b200_last_error.argtypes = []
     lib.b200_last_error.restype = ctypes.c_char_p
-    _lib = lib
+    if lib.b200_stats_ring() != STATS_RING:
+        raise RuntimeError("libb200step.so and _cabi.py disagree on the extras ring length (rebuild the extension)")
     return lib
 
 
-EXPORTED_SYMBOLS = ["b200_create", "b200_destroy", "b200_set_terrain", "b200_bind_buffers", "b200_dynamics_step",
+EXPORTED_SYMBOLS = ["b200_create", "b200_destroy", "b200_set_terrain", "b200_bind_buffers", "b200_dynamics_step", "b200_simulator_step",
+                    "b200_stats_ring", "b200_device",
                     "b200_history_shift", "b200_set_history_side_stream", "b200_set_dynamics_order", "b200_env_post_step", "b200_env_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_env_kernel_variant", "b200_launch_count", "b200_last_error"]

@@ -1,6 +1,14 @@
-// b200_step.cu -- C ABI (include/b200_step.h) over the two sm_100a kernels.  Built by nvcc only
-// (hcr_genesis_lr_cl_b200/build.py); there is no CPU implementation behind these symbols.
+// b200_step.cu -- C ABI (include/b200_step.h) over the sm_100a kernels.  The product library is built by nvcc only
+// (hcr_genesis_lr_cl_b200/build.py); there is no CPU implementation behind these symbols.  With B200_WARP_EMU defined
+// (tests/warp_emu, host g++, TEST ONLY) the same host logic runs over the single-warp emulator and a synchronous stand-in
+// for the CUDA runtime, so that the host layers above the C ABI can be tested in a container without a GPU.
+#ifdef B200_WARP_EMU
+#include "cuda_shim.h"
+#define B200_LAUNCH(kern, grid, block, smem, stream, ...) emu_launch_fn([&] { kern(__VA_ARGS__); }, (int)dim3(grid).x, (int)dim3(grid).y)
+#else
 #include <cuda_runtime.h>
+#define B200_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -46,7 +54,20 @@ struct B200Handle {
     bool order_enabled = true;     // dynamics warps take envs sorted by solver cost (dynamics_order_kernel); B200_DYN_ORDER=0: slot w = env w
     long long dyn_launches = 0;    // parity of the cost / order buffers
     int sm_count = 148;
-    bool side_pending = false;     // work on the side stream that the next env launch has to join     // the dynamics kernel of this step already cleared the env kernel's reduction area
+    int device = 0;                // the CUDA device the handle was created on (current at b200_create); every entry point runs there
+    bool side_pending = false;     // work on the side stream that the next env launch has to join
+};
+
+// Every entry point runs on the device the handle was created on, whatever the caller's current device is (the
+// reference passes only a device string around, task_registry.py:65,117): a launch on a stream of another device fails.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(const B200Handle *h) {
+        if (!h) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != h->device && cudaSetDevice(h->device) == cudaSuccess) prev = cur;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 typedef void (*EnvKernelFn)(const TaskDev, const B200Buffers, const TerrainDev, const EnvCall, const EnvStageTab);
@@ -71,6 +92,7 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
     CK(cudaGetDeviceCount(&ndev));
     if (ndev == 0) return fail("b200_create: no CUDA device");
     B200Handle *h = new B200Handle();
+    if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return fail("b200_create: cudaGetDevice failed"); }
     memcpy(h->task.f, tf, sizeof(float) * TF_COUNT);
     memcpy(h->task.i, ti, sizeof(int) * TI_COUNT);
     const int C = ti[TI_C], A = ti[TI_A], L = ti[TI_L], NS = ti[TI_NSPHERES];
@@ -78,10 +100,11 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
     if (L > B200_MAX_LINKS || NS > B200_MAX_SPHERES || ti[TI_F] > B200_MAX_FEET) { delete h; return fail("b200_create: robot exceeds compiled limits"); }
     const int nb = 1 + A;
     if (n_mf != nb * B200_BODY_STRIDE + 3 * L + 4 * NS || n_mi != 8 + L + 2 * NS) { delete h; return fail("b200_create: packed model size mismatch"); }
-    CK(cudaMalloc(&h->d_model_f, sizeof(float) * n_mf));
-    CK(cudaMalloc(&h->d_model_i, sizeof(int) * n_mi));
-    CK(cudaMemcpy(h->d_model_f, mf, sizeof(float) * n_mf, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_model_i, mi, sizeof(int) * n_mi, cudaMemcpyHostToDevice));
+#define CKH(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { b200_destroy(h); return fail(#x, e_); } } while (0)   /* no leak on failure */
+    CKH(cudaMalloc(&h->d_model_f, sizeof(float) * n_mf));
+    CKH(cudaMalloc(&h->d_model_i, sizeof(int) * n_mi));
+    CKH(cudaMemcpy(h->d_model_f, mf, sizeof(float) * n_mf, cudaMemcpyHostToDevice));
+    CKH(cudaMemcpy(h->d_model_i, mi, sizeof(int) * n_mi, cudaMemcpyHostToDevice));
     h->model.body = h->d_model_f; h->model.link_off = h->d_model_f + nb * B200_BODY_STRIDE; h->model.sph = h->model.link_off + 3 * L;
     h->model.link_body = h->d_model_i + 8; h->model.sph_body = h->model.link_body + L; h->model.sph_link = h->model.sph_body + NS;
     h->dyn_smem = dyn_smem_bytes(DYN_WARPS_PER_BLOCK);
@@ -89,19 +112,21 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
     {   // specialised instantiation when the descriptor is one of the built-in presets (B200_ENV_GENERIC=1 forces the generic one)
         const char *g = getenv("B200_ENV_GENERIC");
         h->env_preset = (g && g[0] == '1') ? -1 : env_match_preset(ti);
-        CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, 0));
+        CKH(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
         const char *o = getenv("B200_DYN_ORDER");
         h->order_enabled = !(o && o[0] == '0');
     }
-    if (h->env_smem > 48 * 1024) CK(cudaFuncSetAttribute(env_kernel_fn(h->env_preset), cudaFuncAttributeMaxDynamicSharedMemorySize, h->env_smem));
-    CK(cudaFuncSetAttribute(dynamics_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
-    CK(cudaFuncSetAttribute(dynamics_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
+    if (h->env_smem > 48 * 1024) CKH(cudaFuncSetAttribute(env_kernel_fn(h->env_preset), cudaFuncAttributeMaxDynamicSharedMemorySize, h->env_smem));
+    CKH(cudaFuncSetAttribute(dynamics_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
+    CKH(cudaFuncSetAttribute(dynamics_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
+#undef CKH
     *out = h;
     return 0;
 }
 
 void b200_destroy(B200Handle *h) {
     if (!h) return;
+    DeviceGuard guard(h);
     cudaFree(h->d_model_f); cudaFree(h->d_model_i); cudaFree(h->d_actions);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -140,9 +165,8 @@ static int check_ready(B200Handle *h, const char *who) {
     return 0;
 }
 
-int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
-    if (check_ready(h, "b200_dynamics_step")) return 1;
-    if (!actions) return fail("b200_dynamics_step: null actions");
+static int launch_dynamics(B200Handle *h, const float *actions, void *stream, int sim_only) {
+    DeviceGuard guard(h);
     const int N = h->task.i[TI_NUM_ENVS];
     const dim3 grid((N + DYN_WARPS_PER_BLOCK - 1) / DYN_WARPS_PER_BLOCK), block(DYN_WARPS_PER_BLOCK * 32);
     cudaStream_t s = (cudaStream_t)stream;
@@ -153,8 +177,8 @@ int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
         h->fork_recorded = true;
     }
     const int par = (h->order_enabled && h->bufs.dyn_order && h->bufs.dyn_cost) ? (int)(h->dyn_launches & 1) : -1;
-    if (h->task.i[TI_C] == 4) dynamics_step_kernel<4><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions, par);
-    else dynamics_step_kernel<2><<<grid, block, h->dyn_smem, s>>>(h->task, h->bufs, h->model, h->terrain, actions, par);
+    if (h->task.i[TI_C] == 4) B200_LAUNCH(dynamics_step_kernel<4>, grid, block, h->dyn_smem, s, h->task, h->bufs, h->model, h->terrain, actions, par, sim_only);
+    else B200_LAUNCH(dynamics_step_kernel<2>, grid, block, h->dyn_smem, s, h->task, h->bufs, h->model, h->terrain, actions, par, sim_only);
     h->dyn_launches++;
     h->launches++;
     h->stats_zeroed = true;
@@ -162,8 +186,21 @@ int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
     return 0;
 }
 
+int b200_dynamics_step(B200Handle *h, const float *actions, void *stream) {
+    if (check_ready(h, "b200_dynamics_step")) return 1;
+    if (!actions) return fail("b200_dynamics_step: null actions");
+    return launch_dynamics(h, actions, stream, 0);
+}
+
+int b200_simulator_step(B200Handle *h, const float *actions, void *stream) {
+    if (check_ready(h, "b200_simulator_step")) return 1;
+    if (!actions) return fail("b200_simulator_step: null actions");
+    return launch_dynamics(h, actions, stream, 1);
+}
+
 int b200_history_shift(B200Handle *h, int parity, void *stream) {
     if (check_ready(h, "b200_history_shift")) return 1;
+    DeviceGuard guard(h);
     const int *ti = h->task.i;
     const bool stacks = ti[TI_OBS_KIND] >= 1;        // the task keeps frame stacks
     // the order of the NEXT dynamics launch from the cost of the PREVIOUS one (the launch in flight writes the other halves)
@@ -185,8 +222,8 @@ int b200_history_shift(B200Handle *h, int parity, void *stream) {
     const int N = ti[TI_NUM_ENVS], p = parity & 1;
     if (reorder) {
         const int next = (int)(h->dyn_launches & 1);                    // parity of the next dynamics launch; its cost half is two launches old
-        dynamics_order_kernel<<<1, 1024, 0, run>>>(h->bufs.dyn_cost + (size_t)next * N, h->bufs.dyn_order + (size_t)next * N, N,
-                                                   h->sm_count * DYN_WARPS_PER_BLOCK);
+        B200_LAUNCH(dynamics_order_kernel, 1, 1024, 0, run, h->bufs.dyn_cost + (size_t)next * N, h->bufs.dyn_order + (size_t)next * N, N,
+                    h->sm_count * DYN_WARPS_PER_BLOCK);
         h->launches++;
         CK(cudaGetLastError());
     }
@@ -195,10 +232,10 @@ int b200_history_shift(B200Handle *h, int parity, void *stream) {
         // one warp-iteration moves 32 x HIST_SHIFT_UNROLL vectors; enough blocks for the larger stack, capped at a few per SM
         const long long per_block = (long long)(HIST_SHIFT_BLOCK / 32) * 32 * HIST_SHIFT_UNROLL * 4;
         long long blocks = ((Mh > Mc ? Mh : Mc) + per_block - 1) / per_block;
-        if (blocks > 148 * HIST_SHIFT_GRID_PER_SM) blocks = 148 * HIST_SHIFT_GRID_PER_SM;
+        if (blocks > (long long)h->sm_count * HIST_SHIFT_GRID_PER_SM) blocks = (long long)h->sm_count * HIST_SHIFT_GRID_PER_SM;
         if (blocks < 1) blocks = 1;
-        history_shift_kernel<<<dim3((unsigned)blocks, 2), HIST_SHIFT_BLOCK, 0, run>>>(h->bufs.obs_history[p], h->bufs.obs_history[p ^ 1], Mh, ti[TI_NUM_OBS],
-                                                                                     h->bufs.critic_obs[p], h->bufs.critic_obs[p ^ 1], Mc, ti[TI_SINGLE_CRITIC]);
+        B200_LAUNCH(history_shift_kernel, dim3((unsigned)blocks, 2), HIST_SHIFT_BLOCK, 0, run, h->bufs.obs_history[p], h->bufs.obs_history[p ^ 1], Mh, ti[TI_NUM_OBS],
+                    h->bufs.critic_obs[p], h->bufs.critic_obs[p ^ 1], Mc, ti[TI_SINGLE_CRITIC]);
         h->launches++;
         CK(cudaGetLastError());
         h->preshift_parity = p;
@@ -237,6 +274,7 @@ static EnvCall make_call(B200Handle *h, long long step, float lo, float span, in
 }
 
 static int launch_env(B200Handle *h, long long step, float lo, float span, int parity, int mask, int force, void *stream) {
+    DeviceGuard guard(h);
     const int N = h->task.i[TI_NUM_ENVS];
     const int n_sums = h->task.i[TI_N_SUMS];
     cudaStream_t s = (cudaStream_t)stream;
@@ -249,7 +287,7 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
         h->preshift_parity = -1;
     }
     const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
-    env_kernel_fn(h->env_preset)<<<grid, block, h->env_smem, s>>>(h->task, h->bufs, h->terrain, call, h->stage);
+    B200_LAUNCH(env_kernel_fn(h->env_preset), grid, block, h->env_smem, s, h->task, h->bufs, h->terrain, call, h->stage);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -265,6 +303,7 @@ int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long
                   float *host_rew, uint8_t *host_reset, uint8_t *host_time_out, void *stream) {
     if (check_ready(h, "b200_env_step")) return 1;
     if (!actions) return fail("b200_env_step: null actions");
+    DeviceGuard guard(h);
     const int N = h->task.i[TI_NUM_ENVS], A = h->task.i[TI_A];
     cudaStream_t s = (cudaStream_t)stream;
     const float *dev_actions = actions;
@@ -312,6 +351,7 @@ int b200_reset_all(B200Handle *h, long long step, float lo, float span, int pari
 
 int b200_kernel_info(B200Handle *h, const char *kernel, int *regs, int *smem, int *blocks_per_sm, int *block_threads) {
     if (!h || !kernel) return fail("b200_kernel_info: null argument");
+    DeviceGuard guard(h);
     cudaFuncAttributes fa; int nb = 0, threads = 0, dyn = 0;
     if (!strcmp(kernel, "dynamics")) {
         threads = DYN_WARPS_PER_BLOCK * 32; dyn = h->dyn_smem;
@@ -331,6 +371,10 @@ int b200_kernel_info(B200Handle *h, const char *kernel, int *regs, int *smem, in
 const char *b200_env_kernel_variant(B200Handle *h) { return (h && h->env_preset >= 0) ? kEnvPresetName[h->env_preset] : "generic"; }
 
 long long b200_launch_count(B200Handle *h) { return h ? h->launches : 0; }
+
+int b200_stats_ring(void) { return ENV_STATS_RING; }
+
+int b200_device(B200Handle *h) { return h ? h->device : -1; }
 
 #ifdef DYN_TIMING
 /* diagnosis build only (-DDYN_TIMING, tools/probe_dyn_timing.py): per-env {start ns, end ns, sweeps, sweep-rows} of the last launch */

@@ -232,7 +232,7 @@ __device__ __forceinline__ void spd6_inverse(const float *S, float *Sinv) {
 // One env, `decimation` substeps.  C chains of 3 joints.  All 32 lanes execute every collective.
 template <int C>
 __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const float *ms, float *ws,
-                              const float *actions_in, int env, int lane, int *cost_out) {
+                              const float *actions_in, int env, int lane, int *cost_out, const int sim_only) {
     const float *tf = T.f;
     const int A = 3 * C, L = T.i[TI_L], NS = T.i[TI_NSPHERES];
     const int *msi = (const int *)(ms + MS_INT);
@@ -251,7 +251,10 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     f3 wb = mk3(B.base_ang_w[env * 3], B.base_ang_w[env * 3 + 1], B.base_ang_w[env * 3 + 2]);
     float q[3], qd[3], tau[3];
     float *pd = ws + WS_PD + 16 * c;        // this lane's chain (lanes >= C alias the last chain and write the same values)
-    const float mass_add = B.added_mass[env], fric_ratio = B.friction[env];
+    // the reference shifts the base mass / scales the geom friction only when the DR switch is on (set_mass_shift /
+    // set_friction_ratio are called from _randomize_* alone, genesis_simulator.py:62-82,665-697); the observation-side
+    // buffers start at 1 / 0 (genesis_simulator.py:648) and must not leak into the physics otherwise
+    const float mass_add = T.i[TI_RAND_MASS] ? B.added_mass[env] : 0.f, fric_ratio = T.i[TI_RAND_FRICTION] ? B.friction[env] : 1.f;
     const f3 com_shift = mk3(B.com_bias[env * 3], B.com_bias[env * 3 + 1], B.com_bias[env * 3 + 2]);
     const float env_arm = B.joint_armature[env], env_dmp = B.joint_damping[env], env_fls = B.joint_friction[env];
 
@@ -260,12 +263,16 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     float a_applied = 0.f;           // lane j < A: the action joint j is driven with (the clipped action, or a delayed one)
     if (lane < A) {
         const int o = env * A + lane;
-        const float a = fminf(fmaxf(actions_in[o], -tf[TF_CLIP_ACTIONS]), tf[TF_CLIP_ACTIONS]);
-        B.llast_actions[o] = B.last_actions[o];
-        B.last_actions[o] = B.actions[o];
-        B.actions[o] = a;
+        // sim_only (b200_simulator_step, plugin mode): LeggedRobot._pre_sim_step already clipped / delayed the actions and
+        // keeps the action history itself; only GenesisSimulator.step's part runs here
+        const float a = sim_only ? actions_in[o] : fminf(fmaxf(actions_in[o], -tf[TF_CLIP_ACTIONS]), tf[TF_CLIP_ACTIONS]);
+        if (!sim_only) {
+            B.llast_actions[o] = B.last_actions[o];
+            B.last_actions[o] = B.actions[o];
+            B.actions[o] = a;
+        }
         a_applied = a;
-        if (T.i[TI_CTRL_DELAY]) {        // legged_robot.py:240-245: push the action into the env's queue, drive with slot action_delay
+        if (T.i[TI_CTRL_DELAY] && !sim_only) {        // legged_robot.py:240-245: push the action into the env's queue, drive with slot action_delay
             const int depth = T.i[TI_CTRL_DELAY_HI] + 1, dly = min(max(B.action_delay[env], 0), depth - 1);
             float *qu = B.action_queue + (size_t)env * depth * A + lane;
             for (int d = depth - 1; d > 0; d--) qu[d * A] = qu[(d - 1) * A];
@@ -1013,7 +1020,8 @@ __global__ void dynamics_order_kernel(const int32_t *cost, int32_t *order_delta,
 
 template <int C>
 __global__ void B200_LAUNCH_BOUNDS(DYN_WARPS_PER_BLOCK * 32, DYN_MIN_BLOCKS)
-dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, const TerrainDev tr, const float *actions, const int parity) {
+dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, const TerrainDev tr, const float *actions, const int parity,
+                     const int sim_only) {
     extern __shared__ float smem[];
     float *ms = smem;
     stage_model(M, T, ms);
@@ -1032,5 +1040,5 @@ dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, con
     const bool ordered = parity >= 0 && B.dyn_order != nullptr;
     const int env = ordered ? slot + B.dyn_order[(size_t)parity * N + slot] : slot;
     dynamics_warp<C>(T, B, tr, ms, smem + MS_TOTAL + warp * WS_TOTAL, actions, env, lane,
-                     (parity >= 0 && B.dyn_cost) ? B.dyn_cost + (size_t)parity * N + env : nullptr);
+                     (parity >= 0 && B.dyn_cost) ? B.dyn_cost + (size_t)parity * N + env : nullptr, sim_only);
 }

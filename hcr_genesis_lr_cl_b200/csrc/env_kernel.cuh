@@ -997,8 +997,11 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
 // Run by the last CTA of env_post_step_kernel (thread i < n_sums + B200_STATS_EXTRA writes entry i).
 __device__ __forceinline__ void stats_finalize(float *stats, int n_sums, const EnvCall &call, int i) {
     float *ring = stats + (2 * n_sums + 4) + call.stats_slot * (n_sums + B200_STATS_EXTRA);
-    const float cnt = fmaxf(__ldcg(stats + n_sums), 1.0f);
-    if (i < n_sums) ring[i] = __ldcg(stats + i) / cnt * call.inv_episode_length_s;
+    const float cnt = __ldcg(stats + n_sums);
+    // no env reset in this step: the reference leaves the previous extras["episode"]["rew_*"] in place (reset_idx returns
+    // early, legged_robot.py:105-106), so the slot carries the previous step's means forward
+    const float *prev = stats + (2 * n_sums + 4) + ((call.stats_slot + ENV_STATS_RING - 1) % ENV_STATS_RING) * (n_sums + B200_STATS_EXTRA);
+    if (i < n_sums) ring[i] = cnt > 0.f ? __ldcg(stats + i) / cnt * call.inv_episode_length_s : __ldcg(prev + i);
     if (i == n_sums) ring[i] = __ldcg(stats + n_sums + 1) * call.inv_num_envs;            // mean terrain level
     if (i == n_sums + 1) ring[i] = call.inv_teacher > 0.f ? __ldcg(stats + n_sums + 3) * call.inv_teacher     // go2_cts: teacher terrain level
                                                           : __ldcg(stats + n_sums + 2) * call.inv_num_envs;   // mean CaT termination probability

@@ -24,6 +24,8 @@ from .simulator import B200Simulator
 
 
 class FusedLeggedEnv:
+    simulator_class = B200Simulator
+
     def __init__(self, spec: T.TaskSpec, num_envs: int, device: str = "cuda:0", terrain=None, env_offset: int = 0,
                  num_envs_global: Optional[int] = None, cfg=None, debug_cells: bool = False):
         self.spec = spec
@@ -31,7 +33,7 @@ class FusedLeggedEnv:
         self.device = device
         self.headless = True
         self.num_envs = int(num_envs)
-        self.simulator = B200Simulator(spec, None, device, True, num_envs=num_envs, terrain=terrain, env_offset=env_offset,
+        self.simulator = self.simulator_class(spec, None, device, True, num_envs=num_envs, terrain=terrain, env_offset=env_offset,
                                        num_envs_global=num_envs_global, debug_cells=debug_cells)
         sim = self.simulator
         sim.fused_histories = True

@@ -1,0 +1,104 @@
+"""Wire the B200 backend into an UNMODIFIED LeggedGym-Ex tree at run time (the import-hook twin of
+``overlay/b200_backend.patch``).
+
+``install()`` makes ``BaseTask.__init__`` (legged_gym/envs/base/base_task.py:41-48) build a ``B200Simulator`` -- a
+subclass of the reference's own ``Simulator`` ABC -- wherever it would have built a ``GenesisSimulator``; nothing in the
+reference tree is edited:
+
+* ``SIMULATOR=genesis`` is what the unpatched ``legged_gym/__init__.py:9-15`` accepts and what makes every config class
+  pick the heightfield terrain and the Genesis run names (common_cfgs.py:76-79, tron1_pf_ee_config.py:19-22), i.e. the
+  configuration this backend implements;
+* when the ``genesis`` engine is not installed a placeholder module satisfies ``import genesis as gs``
+  (legged_gym/__init__.py:21, scripts/train.py:10-12 call ``gs.init``); the B200 path never calls into it;
+* ``base_task.GenesisSimulator`` (the module-global name the dispatch uses) is rebound to the B200 backend class.
+
+Usage::
+
+    import hcr_genesis_lr_cl_b200.plugin as b200
+    b200.install()                      # imports legged_gym.envs (registers the tasks) and rebinds the backend
+    from legged_gym.utils import task_registry ...   # train.py / play.py as shipped
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+from typing import Optional
+
+_BACKEND = None
+_ORIGINAL = None     # base_task.GenesisSimulator before install()
+
+
+def _placeholder_genesis() -> types.ModuleType:
+    m = types.ModuleType("genesis")
+    m.__doc__ = "placeholder installed by hcr_genesis_lr_cl_b200.plugin: the Genesis engine is absent and the B200 backend does not use it"
+    m.cpu, m.gpu = "cpu", "gpu"
+    m.init = lambda *a, **k: None
+
+    def _unavailable(name):
+        raise AttributeError(f"genesis.{name}: the Genesis engine is not installed (B200 backend active)")
+    m.__getattr__ = _unavailable
+    return m
+
+
+def backend_class(impl=None):
+    """``B200Simulator`` as a subclass of ``legged_gym.simulator.simulator.Simulator`` (what the overlay file defines).
+    ``impl`` replaces the implementation class (tests run the host layer over the warp emulator this way)."""
+    from legged_gym.simulator.simulator import Simulator
+    if impl is None:
+        from .simulator import B200Simulator as impl
+
+    class B200Simulator(impl, Simulator):
+        def __init__(self, cfg, sim_params, sim_device="cuda:0", headless=True):
+            impl.__init__(self, cfg, sim_params, sim_device, headless)
+
+    B200Simulator.__doc__ = impl.__doc__
+    return B200Simulator
+
+
+def install(reference_root: Optional[str] = None, impl=None, fix_reference_defects: bool = True):
+    """Route the reference's backend dispatch to the B200 backend; returns the backend class.
+
+    ``fix_reference_defects``: also add the two harness-level aliases without which ``go2_wtw`` / ``tron1_pf_ee`` crash on
+    any backend as shipped (``update_command_curriculum`` is called but only ``_update_command_curriculum``
+    exists, go2_wtw.py:121, tron1_pf_ee.py:201).  ``dof_names`` (R3) is a property of the backend itself."""
+    global _BACKEND
+    if reference_root and reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    os.environ.setdefault("SIMULATOR", "genesis")
+    if os.environ["SIMULATOR"] != "genesis":
+        raise RuntimeError("plugin.install() rides on the SIMULATOR=genesis configuration branches; unset SIMULATOR or use the patch overlay")
+    if "genesis" not in sys.modules:
+        try:
+            importlib.import_module("genesis")
+        except ImportError:
+            sys.modules["genesis"] = _placeholder_genesis()
+    importlib.import_module("legged_gym.envs")     # the entry module of the reference's own scripts (train.py:4); importing
+    import legged_gym.simulator as sim_pkg         # legged_gym.simulator first trips over the tree's circular imports
+    cls = backend_class(impl)
+    sim_pkg.B200Simulator = cls
+    bt = importlib.import_module("legged_gym.envs.base.base_task")
+    global _ORIGINAL
+    if _ORIGINAL is None:
+        _ORIGINAL = bt.GenesisSimulator
+    bt.GenesisSimulator = cls
+    if fix_reference_defects:
+        from legged_gym.envs.base.legged_robot import LeggedRobot
+        if not hasattr(LeggedRobot, "update_command_curriculum"):
+            LeggedRobot.update_command_curriculum = LeggedRobot._update_command_curriculum
+    _BACKEND = cls
+    return cls
+
+
+def installed():
+    return _BACKEND
+
+
+def uninstall() -> None:
+    """Give BaseTask its original Genesis backend back (tests that run both harnesses in one process)."""
+    global _BACKEND, _ORIGINAL
+    if _ORIGINAL is not None:
+        bt = importlib.import_module("legged_gym.envs.base.base_task")
+        bt.GenesisSimulator = _ORIGINAL
+    _BACKEND = _ORIGINAL = None

@@ -25,13 +25,28 @@ import torch
 from . import _cabi
 from . import task_spec as T
 from ._cabi import H
+from .host_rng import uniform_block
 
 _TORCH_DT = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8,
              np.dtype(np.int64): torch.int64}
 
 
 class B200Simulator:
-    """Drop-in for ``GenesisSimulator`` (legged_gym/simulator/genesis_simulator.py:14)."""
+    """Drop-in for ``GenesisSimulator`` (legged_gym/simulator/genesis_simulator.py:14).
+
+    Two ways in:
+
+    * **plugin mode** -- ``B200Simulator(cfg, sim_params, sim_device, headless)`` exactly as ``BaseTask.__init__`` builds
+      its backend (legged_gym/envs/base/base_task.py:41-48): ``cfg`` is the live reference config of ANY task class, the
+      descriptor is derived from it (robot, terrain, control, domain randomisation, link groups; no task name, no reward
+      terms -- rewards / observations stay the task's own torch code over the properties below).  ``step`` then runs
+      ``GenesisSimulator.step`` alone (b200_simulator_step: the stock ``_pre_sim_step`` has already clipped / delayed the
+      actions) and ``post_physics_step`` the ``PHASE_SIM_POST`` slice of the env kernel.  The overlay file
+      ``overlay/legged_gym/simulator/b200_simulator.py`` / ``plugin.install()`` make this class a subclass of the
+      reference's ``Simulator`` ABC.
+    * **fused mode** -- built by ``FusedLeggedEnv`` from a ``TaskSpec`` (or a reference cfg plus ``task=``): the whole
+      ``LeggedRobot.step`` is b200_env_step.
+    """
 
     def __init__(self, cfg, sim_params: Optional[dict] = None, sim_device: str = "cuda:0", headless: bool = True, *,
                  task: Optional[str] = None, num_envs: Optional[int] = None, terrain=None, env_offset: int = 0,
@@ -51,26 +66,44 @@ class B200Simulator:
             self.spec = cfg
             self._num_envs = int(num_envs) if num_envs is not None else 4096
         else:
-            self.spec = T.TaskSpec.from_reference_cfg(cfg, task or getattr(cfg, "b200_task", "go2"))
+            # task=None: plugin mode, the descriptor carries what a *simulator* needs and nothing task specific
+            self.spec = T.TaskSpec.from_reference_cfg(cfg, task)
             self._num_envs = int(num_envs) if num_envs is not None else int(cfg.env.num_envs)
+        self.fused = self.spec.task != T.PLUGIN_TASK
         self._num_actions = self.spec.num_actions
         self._env_offset = int(env_offset)
         self._num_envs_global = int(num_envs_global) if num_envs_global is not None else self._num_envs
         self._terrain_arg = terrain
         self._debug_cells = bool(debug_cells)   # also export the int32 height-scan cell indices (tests)
         self._dof_indices = list(range(self._num_actions))
-        self._lib = _cabi.load_library()          # raises when the extension is not built
-        if not torch.cuda.is_available() or not str(sim_device).startswith("cuda"):
-            raise RuntimeError("B200Simulator needs a CUDA device (sim_device='cuda:N'); there is no CPU path")
-        self._tdev = torch.device(sim_device)
+        self._lib = self._load_library()          # raises when the extension is not built
+        self._tdev = self._check_device(sim_device)
         self._handle = ctypes.c_void_p()
         self._parity = 0
+        self._step_counter = 0         # plugin mode: post_physics_step calls == LeggedRobot.common_step_counter (keys the Philox draws)
         self._dyn_order = os.environ.get("B200_DYN_ORDER", "1") != "0"
         self.fused_histories = False   # set by FusedLeggedEnv: b200_history_shift follows every dynamics step
         self._parse_cfg()
         self._create_sim()
         self._create_envs()
         self._init_buffers()
+
+    # ------------------------------------------------------------------ the native library and the device (no fallback)
+    def _load_library(self):
+        return _cabi.load_library()
+
+    def _check_device(self, sim_device) -> torch.device:
+        if not torch.cuda.is_available() or not str(sim_device).startswith("cuda"):
+            raise RuntimeError("B200Simulator needs a CUDA device (sim_device='cuda:N'); there is no CPU path")
+        dev = torch.device(sim_device)
+        return torch.device("cuda", torch.cuda.current_device()) if dev.index is None else dev
+
+    def _device_ctx(self):
+        """The handle lives on the device that is current at b200_create: make `sim_device` current for that call."""
+        return torch.cuda.device(self._tdev)
+
+    def _sync(self):
+        torch.cuda.synchronize(self._tdev)
 
     # ------------------------------------------------------------------ errors / stream
     def _ck(self, rc: int) -> None:
@@ -79,6 +112,17 @@ class B200Simulator:
 
     def _stream(self) -> ctypes.c_void_p:
         return ctypes.c_void_p(torch.cuda.current_stream(self._tdev).cuda_stream)
+
+    def _pinned(self, nbytes: int) -> torch.Tensor:
+        return torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+
+    @staticmethod
+    def _on_device(t: torch.Tensor) -> bool:
+        return t.is_cuda
+
+    @staticmethod
+    def _is_pinned(t: torch.Tensor) -> bool:
+        return t.is_pinned()
 
     def __del__(self):
         try:
@@ -143,8 +187,9 @@ class B200Simulator:
         hf_shape = tuple(self._height_samples.shape) if self._height_samples is not None else (0, 0)
         tf, ti = _cabi.pack_task(s, m, N, hf_shape, self._env_offset)
         mi, mf = m.packed_ints(), m.packed_floats()
-        self._ck(self._lib.b200_create(mi.ctypes.data, mi.size, mf.ctypes.data, mf.size, ti.ctypes.data, ti.size,
-                                       tf.ctypes.data, tf.size, ctypes.byref(self._handle)))
+        with self._device_ctx():
+            self._ck(self._lib.b200_create(mi.ctypes.data, mi.size, mf.ctypes.data, mf.size, ti.ctypes.data, ti.size,
+                                           tf.ctypes.data, tf.size, ctypes.byref(self._handle)))
         if s.heightfield:
             lv, ty = self._terrain_origins.shape[:2]
             self._ck(self._lib.b200_set_terrain(self._handle, self._height_samples.data_ptr(), hf_shape[0], hf_shape[1],
@@ -179,9 +224,8 @@ class B200Simulator:
         # initial placement: default pose at the env origin
         b["base_pos"][:] = torch.tensor(s.init_pos, device=self._tdev) + b["env_origins"]
         b["dof_pos"][:] = torch.tensor(s.default_dof_pos, device=self._tdev)
+        # initial domain randomisation (genesis_simulator.py:384-405): the step-0 draws of the same Philox sites the resets use
         ids = torch.arange(N, device=self._tdev)
-        gen = torch.Generator(device="cpu").manual_seed(s.seed * 7919 + self._env_offset)
-        self._init_gen = gen
         if s.randomize_friction:
             self._randomize_friction(ids)
         if s.randomize_base_mass:
@@ -198,7 +242,8 @@ class B200Simulator:
             self._randomize_pd_gain(ids)
         if s.randomize_ctrl_delay:                     # legged_robot.py:405-409 (drawn by LeggedRobot there; the queue is ours)
             lo, hi = (int(v) for v in s.ctrl_delay_step_range)
-            b["action_delay"][:] = torch.randint(lo, hi + 1, (N,), generator=gen).to(self._tdev, torch.int32)
+            u = self._uniform(T.SITE_CTRL_DELAY, ids, [0])[:, 0]
+            b["action_delay"][:] = (lo + torch.clamp((u * (hi - lo + 1)).to(torch.int32), max=hi - lo)).to(torch.int32)
 
     def _init_buffers(self):
         s = self.spec
@@ -250,9 +295,16 @@ class B200Simulator:
 
     # ------------------------------------------------------------------ public methods (simulator.py:21-103)
     def step(self, actions):
-        """Decimated PD + rigid-body substeps (genesis_simulator.py:20-33) -- one kernel launch."""
+        """Decimated PD + rigid-body substeps (genesis_simulator.py:20-33) -- one kernel launch.
+
+        Plugin mode: ``actions`` come from ``LeggedRobot._pre_sim_step`` (already clipped, delayed and recorded in the
+        task's own action history, legged_robot.py:230-252) -> b200_simulator_step, which repeats none of that.
+        Fused mode: raw policy actions -> b200_dynamics_step (pre-step bookkeeping included)."""
         a = actions if (actions.dtype == torch.float32 and actions.is_contiguous() and actions.device == self._tdev) \
             else actions.to(self._tdev, torch.float32).contiguous()
+        if not self.fused:
+            self._ck(self._lib.b200_simulator_step(self._handle, a.data_ptr(), self._stream()))
+            return
         self._ck(self._lib.b200_dynamics_step(self._handle, a.data_ptr(), self._stream()))
         if self.fused_histories:      # fused mode: the frame stacks are shifted on a side stream in the shadow of the dynamics kernel
             self._ck(self._lib.b200_history_shift(self._handle, self._parity, self._stream()))
@@ -274,8 +326,12 @@ class B200Simulator:
         self._ck(self._lib.b200_set_dynamics_order(self._handle, int(enabled)))
 
     def post_physics_step(self):
-        """State extraction, contact states, height scan (genesis_simulator.py:35-60) -- PHASE_SIM_POST only."""
-        self._ck(self._lib.b200_env_post_step(self._handle, 0, 0.0, 0.0, self._parity, H["PHASE_SIM_POST"], self._stream()))
+        """State extraction, OOB teleport, contact states, height scan, feet terrain info (genesis_simulator.py:35-60,
+        552-628) -- the PHASE_SIM_POST slice of the env kernel.  Called once per policy step right after
+        ``LeggedRobot.post_physics_step`` incremented ``common_step_counter`` (legged_robot.py:60-63), so the count of
+        these calls is that counter: it keys the simulator-side Philox draws of the step (push, reset DR)."""
+        self._step_counter += 1
+        self._ck(self._lib.b200_env_post_step(self._handle, self._step_counter, 0.0, 0.0, self._parity, H["PHASE_SIM_POST"], self._stream()))
 
     def fused_post_step(self, step_counter: int, cmd_range_x: Sequence[float], phase_mask: Optional[int] = None):
         """Whole LeggedRobot.post_physics_step in one launch (used by FusedLeggedEnv)."""
@@ -290,23 +346,23 @@ class B200Simulator:
         """Pinned host (rew [N] f32, reset [N] bool, time_out [N] bool) carved from one slab laid out like the device side,
         so that b200_env_step moves all three with one copy."""
         N = self._num_envs
-        slab = torch.zeros(6 * N, dtype=torch.uint8).pin_memory()
+        slab = self._pinned(6 * N)
         return slab[:4 * N].view(torch.float32), slab[4 * N:5 * N].view(torch.bool), slab[5 * N:].view(torch.bool)
 
     def fused_env_step(self, actions, step_counter: int, cmd_range_x: Sequence[float], host_rew=None, host_reset=None,
                        host_time_out=None):
         """One whole env.step in ONE C-ABI call (b200_env_step): `actions` is a pinned host tensor (copied to the device
         inside the call) or a device tensor; optional pinned host tensors receive rew / reset / time_out."""
-        on_host = not actions.is_cuda
+        on_host = not self._on_device(actions)
         if on_host:
-            if not (actions.is_pinned() and actions.dtype == torch.float32 and actions.is_contiguous()):
+            if not (self._is_pinned(actions) and actions.dtype == torch.float32 and actions.is_contiguous()):
                 raise ValueError("host actions must be a pinned, contiguous float32 tensor")
             a = actions
         else:
             a = actions if (actions.dtype == torch.float32 and actions.is_contiguous() and actions.device == self._tdev) \
                 else actions.to(self._tdev, torch.float32).contiguous()
         for t in (host_rew, host_reset, host_time_out):
-            if t is not None and not t.is_pinned():
+            if t is not None and not self._is_pinned(t):
                 raise ValueError("host output buffers must be pinned")
         lo, hi = float(cmd_range_x[0]), float(cmd_range_x[1])
         self._ck(self._lib.b200_env_step(self._handle, a.data_ptr(), int(on_host), int(step_counter), lo, float(np.float32(hi - lo)),
@@ -332,6 +388,8 @@ class B200Simulator:
     def reset_idx(self, env_ids):
         """Domain randomisation of reset envs (genesis_simulator.py:62-82); plugin (non-fused) path."""
         s = self.spec
+        if len(env_ids) == 0:
+            return
         if s.randomize_friction:
             self._randomize_friction(env_ids)
         if s.randomize_base_mass:
@@ -353,13 +411,17 @@ class B200Simulator:
         b["last_base_ang_vel"][env_ids] = 0.0
 
     def reset_dofs(self, env_ids, dof_pos, dof_vel):
+        """genesis_simulator.py:84-102: joint positions as given, joint AND base velocities zeroed
+        (set_dofs_position(zero_velocity=True) + zero_all_dofs_velocity)."""
         b = self._buf
         b["dof_pos"][env_ids] = dof_pos[:]
-        b["dof_vel"][env_ids] = 0.0          # set_dofs_position(zero_velocity=True), genesis_simulator.py:96-102
+        b["dof_vel"][env_ids] = 0.0
         b["base_lin_w"][env_ids] = 0.0
         b["base_ang_w"][env_ids] = 0.0
+        b["contact_warm"][env_ids] = 0.0     # the contact set of the old pose is no warm start for the new one
 
     def reset_root_states(self, env_ids, base_pos, base_quat, base_lin_vel, base_ang_vel):
+        """genesis_simulator.py:104-133."""
         b = self._buf
         b["base_pos"][env_ids] = base_pos[:]
         b["base_quat"][env_ids] = base_quat[:]
@@ -372,21 +434,25 @@ class B200Simulator:
         b["base_ang_vel"][env_ids] = base_ang_vel[:]
         b["base_lin_w"][env_ids] = base_lin_vel[:]
         b["base_ang_w"][env_ids] = base_ang_vel[:]
+        b["contact_warm"][env_ids] = 0.0
 
     def update_sensors(self):
         return None                          # depth sensors are outside the hot path (north_star)
 
     def update_terrain_curriculum(self, env_ids, move_up, move_down):
+        """genesis_simulator.py:140-148; the random level of robots that solved the last one is the kernel's SITE_LEVEL draw."""
         b = self._buf
-        b["terrain_levels"][env_ids] += 1 * move_up - 1 * move_down
-        lv = b["terrain_levels"][env_ids]
-        b["terrain_levels"][env_ids] = torch.where(lv >= self._max_terrain_level,
-                                                   torch.randint_like(lv, self._max_terrain_level), torch.clip(lv, 0))
+        lv = b["terrain_levels"][env_ids] + (1 * move_up - 1 * move_down)
+        nl = self._max_terrain_level
+        rnd = torch.clamp((self._uniform(T.SITE_LEVEL, env_ids, [0])[:, 0] * nl).to(lv.dtype), max=nl - 1)
+        b["terrain_levels"][env_ids] = torch.where(lv >= nl, rnd, torch.clip(lv, 0))
         b["env_origins"][env_ids] = self._terrain_origins[b["terrain_levels"][env_ids], b["terrain_types"][env_ids]]
 
     def push_robots(self):
-        m = self.spec.max_push_vel_xy
-        push = (2 * m) * torch.rand(self._num_envs, 2, device=self._tdev) - m
+        """genesis_simulator.py:150-158: U(-max, max) added to the base's world xy velocity (SITE_PUSH draws 0, 1)."""
+        m = np.float32(self.spec.max_push_vel_xy)
+        u = self._uniform(T.SITE_PUSH, None, [0, 1])
+        push = u * float(np.float32(2.0) * m) + float(-m)
         self._buf["rand_push_vels"][:, :2] = push
         self._buf["base_lin_w"][:, :2] += push
 
@@ -412,40 +478,44 @@ class B200Simulator:
     def _init_domain_params(self):
         pass                                  # buffers were created zero/one-initialised in _create_envs
 
-    def _rand(self, n, k=1):
-        return torch.rand(n, k, generator=self._init_gen).to(self._tdev)
+    def _uniform(self, site: int, env_ids, cols) -> torch.Tensor:
+        """Philox draws u(seed, step, global env id, site, idx) for (env_ids x cols) -- the stream of csrc/philox.cuh, so
+        that the plugin path and the fused kernels randomise identically.  `step` = the policy-step counter (0 during
+        construction and the initial reset, like LeggedRobot.common_step_counter)."""
+        ids = np.arange(self._num_envs) if env_ids is None else \
+            (env_ids.detach().cpu().numpy() if isinstance(env_ids, torch.Tensor) else np.asarray(env_ids))
+        u = uniform_block(self.spec.seed, self._step_counter, ids.astype(np.int64) + self._env_offset, site, cols)
+        return torch.from_numpy(u).to(self._tdev)
+
+    def _draw_range(self, site: int, env_ids, cols, rng) -> torch.Tensor:
+        """lower + fp32(upper - lower) * u, rounded like the kernel's rand_range / torch_rand_float (math_utils.py:78-81)."""
+        lo, span = float(np.float32(rng[0])), float(np.float32(float(rng[1]) - float(rng[0])))
+        return self._uniform(site, env_ids, cols) * span + lo
 
     def _randomize_friction(self, env_ids=None):
-        lo, hi = self.spec.friction_range
-        self._buf["friction"][env_ids] = self._rand(len(env_ids)) * (hi - lo) + lo
+        self._buf["friction"][env_ids] = self._draw_range(T.SITE_FRICTION, env_ids, [0], self.spec.friction_range)
 
     def _randomize_base_mass(self, env_ids=None):
-        lo, hi = self.spec.added_mass_range
-        self._buf["added_mass"][env_ids] = self._rand(len(env_ids)) * (hi - lo) + lo
+        self._buf["added_mass"][env_ids] = self._draw_range(T.SITE_MASS, env_ids, [0], self.spec.added_mass_range)
 
     def _randomize_com_displacement(self, env_ids):
         s = self.spec
-        r = self._rand(len(env_ids), 3)
-        lo = torch.tensor([s.com_pos_x_range[0], s.com_pos_y_range[0], s.com_pos_z_range[0]], device=self._tdev)
-        hi = torch.tensor([s.com_pos_x_range[1], s.com_pos_y_range[1], s.com_pos_z_range[1]], device=self._tdev)
-        self._buf["com_bias"][env_ids] = r * (hi - lo) + lo
+        for k, rng in enumerate((s.com_pos_x_range, s.com_pos_y_range, s.com_pos_z_range)):
+            self._buf["com_bias"][env_ids, k] = self._draw_range(T.SITE_COM, env_ids, [k], rng)[:, 0]
 
     def _randomize_joint_armature(self, env_ids):
-        lo, hi = self.spec.joint_armature_range
-        self._buf["joint_armature"][env_ids] = self._rand(len(env_ids)) * (hi - lo) + lo
+        self._buf["joint_armature"][env_ids] = self._draw_range(T.SITE_ARMATURE, env_ids, [0], self.spec.joint_armature_range)
 
     def _randomize_joint_friction(self, env_ids):
-        lo, hi = self.spec.joint_friction_range
-        self._buf["joint_friction"][env_ids] = self._rand(len(env_ids)) * (hi - lo) + lo
+        self._buf["joint_friction"][env_ids] = self._draw_range(T.SITE_JFRICTION, env_ids, [0], self.spec.joint_friction_range)
 
     def _randomize_joint_damping(self, env_ids):
-        lo, hi = self.spec.joint_damping_range
-        self._buf["joint_damping"][env_ids] = self._rand(len(env_ids)) * (hi - lo) + lo
+        self._buf["joint_damping"][env_ids] = self._draw_range(T.SITE_JDAMPING, env_ids, [0], self.spec.joint_damping_range)
 
     def _randomize_pd_gain(self, env_ids):
         s, A = self.spec, self._num_actions
-        self._buf["kp_scale"][env_ids] = self._rand(len(env_ids), A) * (s.kp_range[1] - s.kp_range[0]) + s.kp_range[0]
-        self._buf["kd_scale"][env_ids] = self._rand(len(env_ids), A) * (s.kd_range[1] - s.kd_range[0]) + s.kd_range[0]
+        self._buf["kp_scale"][env_ids] = self._draw_range(T.SITE_KP, env_ids, list(range(A)), s.kp_range)
+        self._buf["kd_scale"][env_ids] = self._draw_range(T.SITE_KD, env_ids, list(range(A)), s.kd_range)
 
     # ------------------------------------------------------------------ state snapshots (tests, checkpointing)
     def load_state(self, st: dict) -> None:
@@ -457,7 +527,7 @@ class B200Simulator:
                 self._buf[name].copy_(t.reshape(self._buf[name].shape).to(self._buf[name].dtype))
 
     def get_state(self) -> dict:
-        torch.cuda.synchronize(self._tdev)
+        self._sync()
         return {k: v.detach().cpu().numpy().copy() for k, v in self._buf.items()}
 
     def kernel_info(self, kernel: str) -> dict:

@@ -42,6 +42,24 @@ NUM_REWARD_TERMS = len(REWARD_TERMS)
 OBS_KINDS = {"go2": 0, "go2_ts": 1, "go2_cat": 2, "tron1_pf": 3, "tron1_pf_ee": 4, "go2_wtw": 5, "go2_cts": 6, "go2_ee": 7,
              "go2_dreamwaq": 8}
 
+#: `task` of the descriptor B200Simulator derives in plugin mode (no task name is handed to a Simulator backend,
+#: base_task.py:41-48): physics, terrain, DR and link groups only -- rewards / observations stay the task class's own code
+PLUGIN_TASK = "plugin"
+
+#: reference config class -> registered task name (legged_gym/envs/__init__.py:80-93); lets the fused registration of
+#: INTEGRATION.md derive its descriptor from the cfg object alone
+CFG_CLASS_TO_TASK = {"GO2Cfg": "go2", "GO2WTWCfg": "go2_wtw", "Go2TSCfg": "go2_ts", "Go2EECfg": "go2_ee", "Go2CTSCfg": "go2_cts",
+                     "Go2DreamwaqCfg": "go2_dreamwaq", "Go2CaTCfg": "go2_cat", "TRON1PFCfg": "tron1_pf", "TRON1PF_EECfg": "tron1_pf_ee"}
+
+
+def task_of_cfg(cfg) -> Optional[str]:
+    """Registered task name of a reference config object (most derived known class wins), or None."""
+    for klass in type(cfg).__mro__:
+        if klass.__name__ in CFG_CLASS_TO_TASK:
+            return CFG_CLASS_TO_TASK[klass.__name__]
+    return None
+
+
 CAT_CONSTRAINTS = ["torque", "dof_vel", "action_rate", "base_height", "collision", "feet_stumble", "dof_pos",
                    "base_orientation", "stand_still"]      # order of ConstraintManager.add calls, go2_cat.py:197-208
 
@@ -341,10 +359,17 @@ class TaskSpec:
 
     # ------------------------------------------------------------------ from a live reference cfg
     @classmethod
-    def from_reference_cfg(cls, cfg, task: str) -> "TaskSpec":
-        """Read a LeggedGym-Ex config object (nested classes/instances) into a TaskSpec."""
+    def from_reference_cfg(cls, cfg, task: Optional[str] = None) -> "TaskSpec":
+        """Read a LeggedGym-Ex config object (nested classes/instances) into a TaskSpec.
+
+        ``task=None`` (plugin mode): the descriptor of the *simulator* -- robot, control, terrain, domain randomisation,
+        link groups -- for any task class; reward terms are not read (they stay torch code), the observation layout is
+        the plain 9 + 3A one (unused) and the control-delay queue stays with ``LeggedRobot._pre_sim_step``."""
         kinds = {"go2": "go2", "go2_ts": "go2_ts", "go2_cat": "go2_cat", "tron1_pf": "tron1_pf", "tron1_pf_ee": "tron1_pf_ee", "go2_wtw": "go2_wtw",
-                 "go2_cts": "go2_cts", "go2_ee": "go2_ee", "go2_dreamwaq": "go2_dreamwaq"}
+                 "go2_cts": "go2_cts", "go2_ee": "go2_ee", "go2_dreamwaq": "go2_dreamwaq", PLUGIN_TASK: "go2"}
+        plugin = task is None or task == PLUGIN_TASK
+        if plugin:
+            task = PLUGIN_TASK
         if task not in kinds:
             raise ValueError(f"task {task!r} has no fused descriptor yet (supported: {sorted(kinds)})")
 
@@ -358,14 +383,17 @@ class TaskSpec:
         kd = {v for k, v in damp.items() if any(k in dn for dn in a.dof_names)}
         if len(kp) != 1 or len(kd) != 1:
             raise ValueError("per-joint PD gains are not supported by the fused descriptor yet")
-        robot = {"go2": "go2", "PF_TRON1A": "tron1_pf"}[next(k for k in ("go2", "PF_TRON1A") if k in a.file)]
+        known = [k for k in ("go2", "PF_TRON1A") if k in a.file]
+        if not known:
+            raise ValueError(f"no packed robot model for asset {a.file!r} (available: go2, PF_TRON1A)")
+        robot = {"go2": "go2", "PF_TRON1A": "tron1_pf"}[known[0]]
         hip_thigh_calf = [0.2, 0.4, 0.4] * (len(a.dof_names) // 3)   # go2.py:30-35 / go2_ts.py:86-91
         if task == "tron1_pf":
             hip_thigh_calf = [0.2] * len(a.dof_names)                  # base class, legged_robot.py:279-280
         spec = cls(
             task=task, obs_kind=kinds[task], robot=robot, dof_names=list(a.dof_names),
             num_obs=e.num_observations, num_privileged_obs=e.num_privileged_obs,
-            frame_stack=getattr(e, "frame_stack", 1), c_frame_stack=getattr(e, "c_frame_stack", 1),
+            frame_stack=1 if plugin else getattr(e, "frame_stack", 1), c_frame_stack=1 if plugin else getattr(e, "c_frame_stack", 1),
             sim_dt=cfg.sim.dt, decimation=cfg.control.decimation, action_scale=cfg.control.action_scale,
             kp=float(kp.pop()), kd=float(kd.pop()),
             default_dof_pos=[float(cfg.init_state.default_joint_angles[n_]) for n_ in a.dof_names],
@@ -396,7 +424,7 @@ class TaskSpec:
             randomize_joint_armature=d.randomize_joint_armature, joint_armature_range=list(d.joint_armature_range),
             randomize_joint_friction=d.randomize_joint_friction, joint_friction_range=list(d.joint_friction_range),
             randomize_joint_damping=d.randomize_joint_damping, joint_damping_range=list(d.joint_damping_range),
-            randomize_ctrl_delay=bool(getattr(d, "randomize_ctrl_delay", False)),
+            randomize_ctrl_delay=bool(getattr(d, "randomize_ctrl_delay", False)) and not plugin,
             ctrl_delay_step_range=[int(x) for x in getattr(d, "ctrl_delay_step_range", [0, 1])],
             obs_scale_lin_vel=n.obs_scales.lin_vel, obs_scale_ang_vel=n.obs_scales.ang_vel,
             obs_scale_dof_pos=n.obs_scales.dof_pos, obs_scale_dof_vel=n.obs_scales.dof_vel,
@@ -405,7 +433,7 @@ class TaskSpec:
             noise_dof_vel=ns.noise_scales.dof_vel, noise_lin_vel=ns.noise_scales.lin_vel,
             noise_ang_vel=ns.noise_scales.ang_vel, noise_gravity=ns.noise_scales.gravity,
             noise_height=ns.noise_scales.height_measurements,
-            reward_scales={k: float(v) for k, v in to_dict(r.scales).items()},
+            reward_scales={} if plugin else {k: float(v) for k, v in to_dict(r.scales).items()},
             only_positive_rewards=r.only_positive_rewards, tracking_sigma=r.tracking_sigma,
             soft_dof_pos_limit=r.soft_dof_pos_limit, base_height_target=r.base_height_target,
             foot_clearance_target=r.foot_clearance_target, foot_height_offset=r.foot_height_offset,
@@ -414,7 +442,7 @@ class TaskSpec:
             feet_air_time_threshold=0.25 if task in ("go2_ts", "go2_cat", "tron1_pf", "tron1_pf_ee", "go2_cts", "go2_ee", "go2_dreamwaq") else 0.3,
             foot_distance_threshold=getattr(r, "foot_distance_threshold", 0.115),
             foot_clearance_uses_terrain=task in ("go2_ts", "go2_cat", "go2_cts", "go2_ee", "go2_dreamwaq"),
-            dof_vel_limits=list(getattr(a, "dof_vel_limits", [])),
+            dof_vel_limits=list(getattr(a, "dof_vel_limits", []) or []),
             foot_name=a.foot_name, penalize_contacts_on=list(a.penalize_contacts_on),
             terminate_after_contacts_on=list(a.terminate_after_contacts_on),
             obtain_link_contact_states=a.obtain_link_contact_states,

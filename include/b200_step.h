@@ -9,6 +9,8 @@
  *                        GenesisSimulator.step                legged_gym/simulator/genesis_simulator.py:20-33
  *                        GenesisSimulator._compute_torques    legged_gym/simulator/genesis_simulator.py:630-642
  *                        scene.step() (third-party engine)    legged_gym/simulator/genesis_simulator.py:29
+ *   b200_simulator_step  GenesisSimulator.step alone          legged_gym/simulator/genesis_simulator.py:20-33 (plugin mode:
+ *                        the stock LeggedRobot._pre_sim_step has already clipped / delayed the actions it passes in)
  *   b200_env_post_step   LeggedRobot.post_physics_step        legged_gym/envs/base/legged_robot.py:55-76
  *                        GenesisSimulator.post_physics_step   legged_gym/simulator/genesis_simulator.py:35-60
  *                        (+ everything those call: height scan :552-610, OOB :612-628, callbacks,
@@ -259,6 +261,13 @@ int b200_bind_buffers(B200Handle *h, const B200Buffers *bufs);
 /* clip + shift action history, save last_*, then `decimation` x (PD torque, rigid-body substep). */
 int b200_dynamics_step(B200Handle *h, const float *dev_actions, void *cuda_stream);
 
+/* Plugin mode (the stock LeggedRobot drives the backend through the Simulator API): GenesisSimulator.step only
+ * (genesis_simulator.py:20-33) -- save last_*, then `decimation` x (PD torque, rigid-body substep) with `dev_actions`
+ * taken as given.  LeggedRobot._pre_sim_step (legged_robot.py:230-252) has already clipped them, shifted its own action
+ * history and applied its control-delay queue, so none of that is repeated here (B200Buffers.actions / last_actions /
+ * llast_actions / action_queue are left untouched). */
+int b200_simulator_step(B200Handle *h, const float *dev_actions, void *cuda_stream);
+
 /* Optional, fused mode only: start moving the kept frames of both frame stacks (obs_history / critic_obs, [parity] ->
  * [parity^1]) for the b200_env_post_step that will follow with the same `parity`.  The copy depends on nothing the
  * dynamics kernel produces; call it right after b200_dynamics_step with the same stream: it runs on an internal side
@@ -314,6 +323,13 @@ const char *b200_env_kernel_variant(B200Handle *h);
 
 /* number of kernel launches issued through this handle since creation */
 long long b200_launch_count(B200Handle *h);
+
+/* slots of the extras["episode"] ring inside B200Buffers.stats (a step's means live in slot step % ring) */
+int b200_stats_ring(void);
+
+/* CUDA device ordinal the handle lives on: the device that was current when b200_create ran.  Every entry point switches
+ * to it for the duration of the call, so callers need not keep it current (legged_gym passes device strings only). */
+int b200_device(B200Handle *h);
 
 const char *b200_last_error(void);
 

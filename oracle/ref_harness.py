@@ -10,7 +10,18 @@ import sys
 from types import SimpleNamespace
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-REFERENCE_ROOT = os.environ.get("HCR_REFERENCE_ROOT", "/root/reference")
+
+
+def _find_reference() -> str:
+    """/root/reference in the build container; on the GPU box the staged copy under baseline/_ref (git-ignored, made by
+    tools/stage_reference.py: python sources only, nothing of it is committed)."""
+    for p in (os.environ.get("HCR_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")):
+        if p and os.path.isdir(os.path.join(p, "legged_gym")):
+            return p
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available() -> bool:
@@ -22,7 +33,7 @@ def import_reference():
     if not reference_available():
         raise RuntimeError("reference tree not present")
     os.environ["SIMULATOR"] = "genesis"
-    for p in (REFERENCE_ROOT, os.path.join(_HERE, "stubs")):
+    for p in (REFERENCE_ROOT, os.path.join(_HERE, "stubs"), os.path.join(_HERE, "stubs_thirdparty")):
         if p not in sys.path:
             sys.path.insert(0, p)
     import legged_gym.envs  # noqa: F401

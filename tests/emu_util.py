@@ -25,6 +25,22 @@ def build_emu(with_env=True):
     return ctypes.CDLL(out)
 
 
+def build_emu_cabi():
+    """TEST-ONLY: hcr_genesis_lr_cl_b200/csrc/b200_step.cu compiled by g++ over the warp emulator and a synchronous CUDA-runtime
+    shim (warp_emu/cuda_shim.h) -> tests/warp_emu/libb200step_emu.so with the same C ABI as the product library, host memory
+    instead of device memory.  Lets the host layers above the C ABI (B200Simulator, FusedLeggedEnv, the plugin overlay) run in
+    a container without a GPU; the product never loads it."""
+    out = os.path.join(_EMU_DIR, "libb200step_emu.so")
+    srcs = [os.path.join(_EMU_DIR, f) for f in ("emu.cpp", "emu.h", "cuda_shim.h")]
+    srcs += [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)]
+    srcs.append(os.path.join(os.path.dirname(_EMU_DIR), "..", "include", "b200_step.h"))
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        cmd = ["g++", "-DB200_WARP_EMU=1", "-DENV_WARPS_PER_BLOCK=1", "-DDYN_WARPS_PER_BLOCK=1", "-O1", "-fPIC", "-shared", "-std=c++17",
+               "-ffp-contract=off", "-I", _EMU_DIR, "-o", out, os.path.join(_EMU_DIR, "emu.cpp"), "-x", "c++", os.path.join(_CSRC, "b200_step.cu")]
+        subprocess.check_call(cmd)
+    return _cabi.bind(ctypes.CDLL(out))
+
+
 class EmuSim:
     """numpy-buffer twin of the device-side state; the emulated kernels read/write it in place."""
 

@@ -11,8 +11,8 @@ struct DynArgs { TaskDev T; B200Buffers B; ModelDev M; TerrainDev tr; const floa
 
 static void dyn_body(void *p) {
     DynArgs *a = (DynArgs *)p;
-    if (a->T.i[TI_C] == 4) dynamics_step_kernel<4>(a->T, a->B, a->M, a->tr, a->actions, 0);      // parity 0: zeroed order = identity
-    else dynamics_step_kernel<2>(a->T, a->B, a->M, a->tr, a->actions, 0);
+    if (a->T.i[TI_C] == 4) dynamics_step_kernel<4>(a->T, a->B, a->M, a->tr, a->actions, 0, 0);      // parity 0: zeroed order = identity
+    else dynamics_step_kernel<2>(a->T, a->B, a->M, a->tr, a->actions, 0, 0);
 }
 
 static ModelDev mk_model(const TaskDev &T, const int *mi, const float *mf) {
