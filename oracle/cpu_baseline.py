@@ -14,7 +14,7 @@ import time
 import numpy as np
 
 from oracle.env_oracle import EnvOracle
-from oracle.physics import PhysicsOracle, default_params
+from oracle.physics import PhysicsOracle, default_params, env_params
 
 PH = dict(base_pos="base_pos", base_quat_wxyz="base_quat_wxyz", base_lin_w="base_lin_w", base_ang_w="base_ang_w", q="q", qd="qd")
 
@@ -50,9 +50,12 @@ class OracleEnv:
         a = self.eo.pre_step(actions)
         state = np.concatenate([st["base_pos"], st["base_quat_wxyz"], st["base_lin_w"], st["base_ang_w"]], axis=1).astype(np.float64)
         q, qd = st["q"].astype(np.float64), st["qd"].astype(np.float64)
-        envp = np.concatenate([st["added_mass"], st["com_bias"], st["friction"]], axis=1).astype(np.float64)
-        arm = np.tile(self.model.body[1:, 19][None, :], (N, 1)).astype(np.float64)
-        jp = np.concatenate([arm, np.zeros((N, 2 * A))], axis=1)
+        envp = env_params(spec, st)
+        arm = np.tile(st["joint_armature"], (1, A)).astype(np.float64) if spec.randomize_joint_armature else \
+            np.tile(self.model.body[1:, 19][None, :], (N, 1)).astype(np.float64)
+        dmp = np.tile(st["joint_damping"], (1, A)).astype(np.float64) if spec.randomize_joint_damping else np.zeros((N, A))
+        fls = np.tile(st["joint_friction"], (1, A)).astype(np.float64) if spec.randomize_joint_friction else np.zeros((N, A))
+        jp = np.concatenate([arm, dmp, fls], axis=1)
         q0 = np.asarray(spec.default_dof_pos, f32)[None, :]
         kp, kd = (st["kp_scale"] * f32(spec.kp)).astype(f32), (st["kd_scale"] * f32(spec.kd)).astype(f32)
         tgt = (a * f32(spec.action_scale) + q0).astype(f32)
@@ -71,10 +74,10 @@ class OracleEnv:
 def _worker(args):
     task_overrides, per, offset, steps, warmup, seed, barrier = args
     from hcr_genesis_lr_cl_b200 import task_spec as T
-    from hcr_genesis_lr_cl_b200.terrain_assets import load_go2_rough_terrain
+    from hcr_genesis_lr_cl_b200.terrain_assets import terrain_for
     task, over = task_overrides
     spec = T.PRESETS[task](**over)
-    terrain = load_go2_rough_terrain() if spec.heightfield else None
+    terrain = terrain_for(spec) if spec.heightfield else None      # the task's own heightfield (go2 rough / tron1 rough)
     env = OracleEnv(spec, per, terrain, env_offset=offset)
     rng = np.random.default_rng(seed + offset)
     acts = [rng.normal(size=(per, spec.num_actions)).astype(np.float32) for _ in range(steps + warmup)]

@@ -84,3 +84,52 @@ class PhysicsOracle:
                                         self._p(np.ascontiguousarray(q, np.float64)),
                                         self._p(np.ascontiguousarray(qd, np.float64)), self._p(lp), self._p(lv))
         return lp, lv
+
+
+def oracle_params(spec, model=None, hf=None):
+    return default_params(dt=spec.sim_dt, iters=spec.pgs_iterations, hscale=spec.horizontal_scale,
+                                vscale=spec.vertical_scale, border=spec.border_size if spec.heightfield else 0.0,
+                                terrain_mu=spec.static_friction, geom_mu=1.0, tol=spec.pgs_tolerance)
+
+
+def env_params(spec, st) -> np.ndarray:
+    """Per-env engine parameters [added base mass, COM shift xyz, geom friction ratio] as the reference hands them to the
+    engine: `set_mass_shift` / `set_friction_ratio` are only ever called from `_randomize_base_mass` / `_randomize_friction`
+    (genesis_simulator.py:62-82,384-405,665-697), i.e. with the DR switch off the engine keeps mass shift 0 and ratio 1
+    whatever the observation-side buffers (`_added_base_mass` starts at ones, `_friction_values` at zeros, :644-650) hold."""
+    n = st["added_mass"].shape[0]
+    mass = st["added_mass"] if spec.randomize_base_mass else np.zeros((n, 1))
+    fric = st["friction"] if spec.randomize_friction else np.ones((n, 1))
+    com = st["com_bias"] if spec.randomize_com_displacement else np.zeros((n, 3))
+    return np.concatenate([mass, com, fric], axis=1).astype(np.float64)
+
+
+def oracle_policy_step(spec, model, oracle, st, actions, clip=True):
+    """Reference statement of one decimated physics step (genesis_simulator.py:20-33) on a state dict `st` of fp32
+    arrays (keys as B200Buffers).  Returns the post-physics dict the env half consumes (float64 internally).
+    `clip=False`: the actions are what LeggedRobot._pre_sim_step hands over (plugin mode: already clipped / delayed)."""
+    f32 = np.float32
+    N, A = actions.shape
+    a = np.clip(actions.astype(f32), f32(-spec.clip_actions), f32(spec.clip_actions)) if clip else actions.astype(f32)
+    state = np.concatenate([st["base_pos"], st["base_quat_wxyz"], st["base_lin_w"], st["base_ang_w"]], axis=1).astype(np.float64)
+    q, qd = st["dof_pos"].astype(np.float64).copy(), st["dof_vel"].astype(np.float64).copy()
+    envp = env_params(spec, st)
+    arm = np.tile(model.body[1:, 19][None, :], (N, 1)).astype(np.float64)
+    if spec.randomize_joint_armature:
+        arm = np.tile(st["joint_armature"], (1, A)).astype(np.float64)
+    dmp = np.tile(st["joint_damping"], (1, A)).astype(np.float64) if spec.randomize_joint_damping else np.zeros((N, A))
+    fls = np.tile(st["joint_friction"], (1, A)).astype(np.float64) if spec.randomize_joint_friction else np.zeros((N, A))
+    jp = np.concatenate([arm, dmp, fls], axis=1)
+    q0 = np.asarray(spec.default_dof_pos, f32)[None, :]
+    kp, kd = (st["kp_scale"] * f32(spec.kp)).astype(f32), (st["kd_scale"] * f32(spec.kd)).astype(f32)
+    tgt = (a * f32(spec.action_scale) + q0).astype(f32)
+    tau = np.zeros((N, A), f32)
+    lf = nc = None
+    warm = np.ascontiguousarray(st.get("contact_warm", np.zeros((N, 48))), np.float64).copy()
+    for _ in range(spec.decimation):
+        tau = (kp * (tgt - q.astype(f32)) - kd * qd.astype(f32)).astype(f32)
+        lf, nc = oracle.substep(state, q, qd, tau, envp, jp, warm)
+    lp, lv = oracle.link_kinematics(state, q, qd)
+    feet = spec.link_groups(model)[0]
+    return dict(base_pos=state[:, 0:3], base_quat_wxyz=state[:, 3:7], base_lin_w=state[:, 7:10], base_ang_w=state[:, 10:13],
+                q=q, qd=qd, torques=tau, link_force=lf, feet_pos=lp[:, feet], feet_vel=lv[:, feet], ncontact=nc, contact_warm=warm)

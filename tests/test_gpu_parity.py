@@ -188,6 +188,92 @@ def test_dynamics_kernel_matches_oracle(task):
             assert err.max() < tol * scale(r), f"{k}: abs err {err.max():.3e} (scale {scale(r):.2f})"
 
 
+def test_dynamics_kernel_without_domain_randomisation():
+    """randomize_base_mass / randomize_friction off: mass shift 0 and friction ratio 1 whatever the observation-side
+    buffers hold (ones / zeros as the reference initialises them, genesis_simulator.py:644-650)."""
+    from emu_util import oracle_params, oracle_policy_step
+    from hcr_genesis_lr_cl_b200 import task_spec as T
+    from oracle.physics import PhysicsOracle
+    spec = T.go2_ts_spec(randomize_base_mass=False, randomize_friction=False, randomize_com_displacement=False)
+    terrain = load_terrain(spec)
+    N = 256
+    st, model = _random_state(spec, N, terrain, seed=17)
+    st["added_mass"] = np.ones((N, 1), np.float32)
+    st["friction"] = np.zeros((N, 1), np.float32)
+    env = _env(spec, N, terrain)
+    sim = env.simulator
+    assert sim.env_kernel_variant == "generic"          # an edited configuration runs the generic env kernel
+    sim.load_state(st)
+    full = sim.get_state()
+    actions = np.random.default_rng(5).normal(size=(N, spec.num_actions)).astype(np.float32)
+    sim.step(torch.from_numpy(actions).cuda())
+    out = sim.get_state()
+    orc = PhysicsOracle(model, oracle_params(spec, model), terrain[0], precision="f32")
+    ref = oracle_policy_step(spec, model, orc, full, actions)
+    assert ref["ncontact"].max() > 0
+    for k in ("base_pos", "q", "qd", "base_lin_w", "base_ang_w"):
+        r = np.asarray(ref[k], np.float64)
+        err = np.abs(out[PH[k]].reshape(r.shape) - r).max()
+        assert err < 1e-4 * max(1.0, float(np.abs(r).max())), f"{k}: {err:.3e}"
+
+
+def test_full_size_one_step_matches_the_oracle_pair():
+    """BASELINE config C2 at its full size: 4096 envs of go2_ts, ONE policy step, CUDA path vs the oracle pair (C substep
+    + numpy env half) on the same seeded state -- every output, ints exact (the CPU port steps 4096 envs in well under a second)."""
+    from emu_util import oracle_params, oracle_policy_step
+    from hcr_genesis_lr_cl_b200 import task_spec as T
+    from oracle.env_oracle import EnvOracle
+    from oracle.physics import PhysicsOracle
+    spec = T.go2_ts_spec()
+    terrain = load_terrain(spec)
+    N = 4096
+    st, model = _random_state(spec, N, terrain, seed=23)
+    rng = np.random.default_rng(31)
+    st["episode_length"] = rng.integers(0, 1001, N).astype(np.int32)      # time-outs, command resampling (every 500 steps)
+    st["fail_buf"] = rng.integers(0, 6, N).astype(np.int32)
+    st["commands"] = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
+    env = _env(spec, N, terrain)
+    sim = env.simulator
+    sim.load_state(st)
+    env.common_step_counter = 1499           # the step under test is a push step (push_interval 500)
+    full = sim.get_state()
+    actions = np.random.default_rng(29).normal(size=(N, spec.num_actions)).astype(np.float32)
+    # dynamics kernel vs the C oracle
+    sim.step(torch.from_numpy(actions).cuda())
+    mid = sim.get_state()
+    orc = PhysicsOracle(model, oracle_params(spec, model), terrain[0], precision="f32")
+    ref = oracle_policy_step(spec, model, orc, full, actions)
+    for k in ("base_pos", "q", "qd", "base_lin_w", "base_ang_w"):
+        r = np.asarray(ref[k], np.float64)
+        err = np.abs(mid[PH[k]].reshape(r.shape) - r).max()
+        assert err < 1e-4 * max(1.0, float(np.abs(r).max())), f"{k}: {err:.3e}"
+    # env kernel vs the numpy oracle on the kernel's own post-physics state
+    eo = EnvOracle(spec, N, terrain[0], terrain[1])
+    alias = {"dof_pos": "q", "dof_vel": "qd", f"obs_history{sim._parity}": "obs_hist", f"critic_obs{sim._parity}": "critic_hist"}
+    for k, v in full.items():
+        kk = alias.get(k, k)
+        if kk in eo.st:
+            eo.st[kk][...] = v.reshape(eo.st[kk].shape)
+    eo.common_step_counter = env.common_step_counter
+    eo.pre_step(actions)
+    o = eo.post_step(dict(base_pos=mid["base_pos"], base_quat_wxyz=mid["base_quat_wxyz"], base_lin_w=mid["base_lin_w"],
+                          base_ang_w=mid["base_ang_w"], q=mid["dof_pos"], qd=mid["dof_vel"], torques=mid["torques"],
+                          link_force=mid["link_contact_forces"], feet_pos=mid["feet_pos"], feet_vel=mid["feet_vel"]))
+    env.common_step_counter += 1
+    sim.fused_post_step(env.common_step_counter, env.command_ranges["lin_vel_x"])
+    out = sim.get_state()
+    assert int(o["reset_buf"].sum()) > 0
+    for k in ("reset_buf", "time_out_buf"):
+        assert np.array_equal(out[k].astype(bool), np.asarray(o[k]).astype(bool)), k
+    assert np.array_equal(out["height_cells"], o["height_cells"]), "height-scan cells"
+    _close(out["rew_buf"], o["rew_buf"], what="rew_buf")
+    _close(out["obs_buf"], o["obs_buf"], what="obs_buf")
+    _close(out["privileged_obs_buf"], o["privileged_obs_buf"], what="privileged_obs_buf")
+    _close(out[f"critic_obs{sim._parity}"], o["critic_obs_buf"], what="critic stack")
+    _close(out[f"obs_history{sim._parity}"], o["obs_history"], what="obs history")
+    _close(out["rand_push_vels"], eo.st["rand_push_vels"], what="push")
+
+
 @pytest.mark.parametrize("task", ["go2_ts", "go2_cat", "tron1_pf_ee", "go2_wtw", "go2_cts", "go2_ee", "go2_dreamwaq"])
 def test_env_kernel_matches_numpy_oracle_seeded(task):
     """Seeded random states at N=512 through several fused steps vs the numpy restatement (all phases, with resets)."""

@@ -117,3 +117,65 @@ def test_emulated_dynamics_kernel_matches_oracle():
     assert np.array_equal(sim.buf["llast_actions"], before["last_actions"])
     assert np.array_equal(sim.buf["last_dof_vel"], before["dof_vel"])
 
+
+
+def test_emulated_dynamics_without_domain_randomisation_keeps_nominal_mass_and_friction():
+    """randomize_base_mass / randomize_friction off (go2_sysid-style cfg): the reference never calls set_mass_shift /
+    set_friction_ratio, so the engine runs the nominal robot although `_added_base_mass` is ones and `_friction_values`
+    zeros (genesis_simulator.py:644-650).  Kernel vs oracle with the switches off, and: the result must differ from what
+    the buffers' values would give if they leaked into the physics."""
+    g, s0 = load_golden("go2_ts_n32")
+    hs, origins = load_terrain()
+    N = 6
+    sub = {k: (v[:N] if getattr(v, "ndim", 0) > 0 and v.shape[0] == 32 else v) for k, v in s0.items()}
+    outs = {}
+    for off in (True, False):
+        spec = spec_for(g)
+        if off:
+            spec.randomize_base_mass = spec.randomize_friction = False
+        sim = EmuSim(spec, N, hs, origins)
+        sim.load_state(sub)
+        sim.buf["added_mass"][:] = 1.0
+        sim.buf["friction"][:] = 0.0
+        before = {k: v.copy() for k, v in sim.buf.items()}
+        a = g["actions"][0][:N]
+        sim.dynamics_step(a)
+        orc = PhysicsOracle(sim.model, oracle_params(spec, sim.model), hs, precision="f32")
+        ref = oracle_policy_step(spec, sim.model, orc, before, a)
+        for k, name in PH.items():
+            r = np.asarray(ref[k], np.float64)
+            err = np.abs(sim.buf[name].reshape(r.shape) - r).max()
+            tol = (2e-3 if k == "link_force" else 1e-4) * max(1.0, np.abs(r).max())
+            assert err < tol, f"DR off={off} {k}: {err:.3e} >= {tol:.1e}"
+        outs[off] = sim.buf["dof_vel"].copy()
+    assert np.abs(outs[True] - outs[False]).max() > 1e-3      # +1 kg and mu = terrain_mu only would have changed the step
+
+
+def test_emulated_simulator_step_skips_the_pre_step_bookkeeping():
+    """b200_simulator_step (plugin mode): same physics as b200_dynamics_step on already clipped actions, but the action
+    history / delay queue of B200Buffers stay untouched (LeggedRobot._pre_sim_step owns them, legged_robot.py:230-252)."""
+    import ctypes
+    import torch
+    from emu_backend import EmuB200Simulator
+    g, s0 = load_golden("go2_ts_n32")
+    spec = spec_for(g)
+    hs, origins = load_terrain()
+    N = 4
+    sub = {k: (v[:N] if getattr(v, "ndim", 0) > 0 and v.shape[0] == 32 else v) for k, v in s0.items()}
+    res = {}
+    for mode in ("full", "sim_only"):
+        sim = EmuB200Simulator(spec, None, "cpu", True, num_envs=N, terrain=(hs, origins))
+        sim.load_state(sub)
+        before = sim.get_state()
+        a = torch.from_numpy(np.clip(g["actions"][0][:N], -5, 5).copy())
+        if mode == "full":
+            sim.step(a)
+        else:
+            sim._ck(sim._lib.b200_simulator_step(sim._handle, a.data_ptr(), ctypes.c_void_p(0)))
+        res[mode] = (before, sim.get_state())
+    (b0, full), (b1, only) = res["full"], res["sim_only"]
+    for k in ("base_pos", "base_quat_wxyz", "dof_pos", "dof_vel", "torques", "link_contact_forces", "feet_pos", "last_dof_vel", "last_feet_vel"):
+        assert np.array_equal(full[k], only[k]), k
+    for k in ("actions", "last_actions", "llast_actions"):
+        assert np.array_equal(only[k], b1[k]), k
+    assert not np.array_equal(full["actions"], b0["actions"])

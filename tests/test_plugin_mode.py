@@ -146,3 +146,62 @@ def test_reference_task_classes_run_over_the_backend_gpu(task):
     """B200: stock LeggedRobot / task classes over libb200step.so vs FusedLeggedEnv, 24 policy steps, 64 envs."""
     from hcr_genesis_lr_cl_b200.fused_env import FusedLeggedEnv
     _run(task, None, FusedLeggedEnv, cpu=False, N=64, steps=24, skip_env0=task in ("go2_wtw", "tron1_pf_ee"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The two ways of wiring the backend in (INTEGRATION.md section 2), each in a fresh interpreter
+def _smoke(variant, impl, task, n_envs=8, steps=6):
+    import json
+    import os
+    import shutil
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = reference_root()
+    tmp = None
+    try:
+        if variant == "patched":
+            tmp = tempfile.mkdtemp(prefix="b200_overlay_")
+            tree = os.path.join(tmp, "ref")
+            shutil.copytree(ref, tree, ignore=shutil.ignore_patterns("*.STL", "*.stl", "*.dae", "*.obj", "*.png", "*.jpg", ".git"))
+            subprocess.run(["patch", "-p1", "-s", "-i", os.path.join(root, "overlay", "b200_backend.patch")], cwd=tree, check=True)
+            shutil.copy(os.path.join(root, "overlay", "legged_gym", "simulator", "b200_simulator.py"), os.path.join(tree, "legged_gym", "simulator"))
+            ref = tree
+        env = dict(os.environ)
+        env.pop("SIMULATOR", None)
+        out = subprocess.run([sys.executable, os.path.join(root, "tests", "run_backend_smoke.py"), ref, variant, impl, task, str(n_envs), str(steps)],
+                             capture_output=True, text=True, env=env, timeout=900)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+        line = [ln for ln in out.stdout.splitlines() if ln.startswith("DIGEST ")][-1]
+        return json.loads(line[7:])
+    finally:
+        if tmp:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
+def _check_wiring(impl, task):
+    hook = _smoke("hook", impl, task)
+    patched = _smoke("patched", impl, task)
+    # import-hook variant: unmodified tree, SIMULATOR=genesis branches, the placeholder stands in for the absent engine
+    assert hook["simulator"] == "genesis" and hook["backend"] == "B200Simulator" and hook["is_simulator_abc"] and hook["finite"]
+    assert "placeholder" in hook["genesis"]
+    # maintainer variant: patch + overlay file, SIMULATOR=b200, no `genesis` module at all
+    assert patched["simulator"] == "b200" and patched["backend"] == "B200Simulator" and patched["is_simulator_abc"] and patched["finite"]
+    assert patched["backend_module"] == "legged_gym.simulator.b200_simulator" and patched["genesis"] == ""
+    assert hook["mesh_type"] == patched["mesh_type"]
+    assert hook["sha"] == patched["sha"], "the two wirings step differently"
+    assert hook["launches"] == patched["launches"] > 0
+
+
+@needs_reference
+@pytest.mark.parametrize("task", ["go2_ts", "tron1_pf_ee"])
+def test_overlay_patch_and_import_hook_wire_the_same_backend_emulated(task):
+    _check_wiring("emu", task)
+
+
+@needs_reference
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["go2_ts", "tron1_pf_ee"])
+def test_overlay_patch_and_import_hook_wire_the_same_backend_gpu(task):
+    _check_wiring("cuda", task)
