@@ -78,7 +78,7 @@ class Injector:
         self.call += 1
         ids = self.ids
         assert len(ids) == k, (len(ids), shape, site)
-        return self.torch.from_numpy(self.u(site, ids, cols).reshape(shape).astype(np.float32))
+        return self.torch.from_numpy(self.u(site, ids, cols).reshape(shape).astype(np.float32)).to(self.env.device)
 
     def ctx(self, fn, site, ids_arg=True, name=None):
         inj = self

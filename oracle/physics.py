@@ -100,8 +100,8 @@ def env_params(spec, st) -> np.ndarray:
     n = st["added_mass"].shape[0]
     mass = st["added_mass"] if spec.randomize_base_mass else np.zeros((n, 1))
     fric = st["friction"] if spec.randomize_friction else np.ones((n, 1))
-    com = st["com_bias"] if spec.randomize_com_displacement else np.zeros((n, 3))
-    return np.concatenate([mass, com, fric], axis=1).astype(np.float64)
+    # the COM shift needs no switch: `_base_com_bias` starts at zeros and only _randomize_com_displacement writes it
+    return np.concatenate([mass, st["com_bias"], fric], axis=1).astype(np.float64)
 
 
 def oracle_policy_step(spec, model, oracle, st, actions, clip=True):
