@@ -143,7 +143,7 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     build.build()
-    spec = T.PRESETS[args.task]()
+    spec = T.PRESETS[args.task](**({"pgs_iterations": args.pgs_iters} if args.pgs_iters else {}))
     terrain = terrain_for(spec)
     N = args.envs
     env = FusedLeggedEnv(spec, N, dev, terrain=terrain, env_offset=rank * N, num_envs_global=world * N)
@@ -342,6 +342,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--task", default=TASK, choices=sorted(WORKLOADS), help="task preset (default: the metric's config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pgs-iters", type=int, default=0, help="override the contact solver's sweep cap (tuning experiments)")
     ap.add_argument("--pre-roll", type=int, default=300, help="un-timed policy steps before the warm-up (steady-state workload)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -74,6 +74,38 @@ __device__ __forceinline__ float warp_max_nonneg(float v) {
 #endif
 }
 
+// 1 / sqrt(x) for x well inside the normal range: the bare MUFU.RSQ (rsqrtf() wraps it in a denormal fix-up, 4 instructions)
+__device__ __forceinline__ float fast_rsqrtf(float x) {
+#ifdef B200_WARP_EMU
+    return 1.0f / sqrtf(x);
+#else
+    float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#endif
+}
+
+// ---- explicit shared-memory accesses by 32-bit shared-window address: the inner loop of the contact solver keeps ONE
+// address register and immediate offsets, instead of generic pointers that the compiler re-derives from SR_TID /
+// SR_CgaCtaId under register pressure (S2R on the address path of every access).
+#ifdef B200_WARP_EMU
+typedef uintptr_t smaddr_t;
+__device__ __forceinline__ smaddr_t sm_addr(const void *p) { return (smaddr_t)p; }
+__device__ __forceinline__ float4 lds128(smaddr_t a) { return *(const float4 *)a; }
+__device__ __forceinline__ float2 lds64(smaddr_t a) { return *(const float2 *)a; }
+__device__ __forceinline__ float lds32(smaddr_t a) { return *(const float *)a; }
+__device__ __forceinline__ void sts128(smaddr_t a, float x, float y, float z, float w) { float *p = (float *)a; p[0] = x; p[1] = y; p[2] = z; p[3] = w; }
+#else
+typedef uint32_t smaddr_t;
+__device__ __forceinline__ smaddr_t sm_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(smaddr_t a) {
+    float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ float2 lds64(smaddr_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ float lds32(smaddr_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts128(smaddr_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+#endif
+
 // ---- TMA (bulk async copy) + mbarrier helpers: 1-D cp.async.bulk between global and shared memory (sm_90+; SASS UBLKCP).
 // Sizes and both addresses must be multiples of 16 bytes.  Under the test emulator they degrade to memcpy.
 #ifdef B200_WARP_EMU

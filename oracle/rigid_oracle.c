@@ -30,6 +30,7 @@
  * Build: see oracle/Makefile (REAL=double -> liboracle_f64.so, float -> _f32).
  */
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
 
@@ -63,6 +64,8 @@ enum { P_DT, P_GRAV, P_TC, P_DAMPRATIO, P_D0, P_DMAX, P_WIDTH, P_MID, P_POWER,
        P_TERRAIN_MU, P_GEOM_MU, P_ITERS, P_HSCALE, P_VSCALE, P_BORDER, P_TOL, P_NPARAM };
 
 static long long g_sweeps, g_substeps, g_rows, g_contacts;
+static long long g_hist[64];
+static long long g_hist_nc[9][2];   /* by contact count: solves, sweeps */   /* solves by the number of sweeps they took (diagnostics) */
 typedef struct { real x, y, z; } v3;
 static v3 V(real x, real y, real z) { v3 r = {x, y, z}; return r; }
 static v3 add(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -347,25 +350,50 @@ static void substep_one(const Model *M, const float *prm, const int16_t *hf, int
             bb[r] = ja - aref;
         }
         int iters = (int)prm[P_ITERS];
+        real Binv[KMAX][6];      /* per contact: inverse of the 3x3 block A_cc + diag(R_c), upper triangle */
+        for (int c = 0; c < nc; c++) {
+            const int r = 3 * c;
+            const real a00 = A[r][r] + Rr[r], a01 = A[r][r + 1], a02 = A[r][r + 2], a11 = A[r + 1][r + 1] + Rr[r + 1], a12 = A[r + 1][r + 2],
+                       a22 = A[r + 2][r + 2] + Rr[r + 2];
+            const real c00 = a11 * a22 - a12 * a12, c01 = a02 * a12 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+            const real idet = 1 / (a00 * c00 + a01 * c01 + a02 * c02);
+            Binv[c][0] = c00 * idet; Binv[c][1] = c01 * idet; Binv[c][2] = c02 * idet; Binv[c][3] = (a00 * a22 - a02 * a02) * idet;
+            Binv[c][4] = (a01 * a02 - a00 * a12) * idet; Binv[c][5] = (a00 * a11 - a01 * a01) * idet;
+        }
         for (int it = 0; it < iters; it++) {
             real fprev[RMAX]; memcpy(fprev, f, sizeof f);
-            for (int r = 0; r < R; r++) {
+            /* contacts: block Gauss-Seidel, the three rows of a contact solved together against the 3x3 block
+               A_cc + diag(R_c), then f_n >= 0 and the tangential pair projected onto the friction disc */
+            for (int c = 0; c < nc; c++) {
+                const int r = 3 * c;
+                real g[3];
+                for (int d = 0; d < 3; d++) {
+                    g[d] = bb[r + d] + Rr[r + d] * f[r + d];
+                    for (int s2 = 0; s2 < R; s2++) g[d] += A[r + d][s2] * f[s2];
+                }
+                const real *bi = Binv[c];   /* b00 b01 b02 b11 b12 b22 */
+                real n0 = f[r] - (bi[0] * g[0] + bi[1] * g[1] + bi[2] * g[2]);
+                real n1 = f[r + 1] - (bi[1] * g[0] + bi[3] * g[1] + bi[4] * g[2]);
+                real n2 = f[r + 2] - (bi[2] * g[0] + bi[4] * g[1] + bi[5] * g[2]);
+                if (n0 < 0) n0 = 0;
+                real lim = cmu[c] * n0, t2 = n1 * n1 + n2 * n2;
+                if (t2 > lim * lim) { real sc = lim / sqrt(t2); n1 *= sc; n2 *= sc; }
+                f[r] = n0; f[r + 1] = n1; f[r + 2] = n2;
+            }
+            /* joint-limit and frictionloss rows: row-wise */
+            for (int r = 3 * nc; r < R; r++) {
                 real res = bb[r] + Rr[r] * f[r];
                 for (int s = 0; s < R; s++) res += A[r][s] * f[s];
                 real fnew = f[r] - res / (A[r][r] + Rr[r]);
-                if (kind[r] == 0 || kind[r] == 3) { if (fnew < 0) fnew = 0; }
+                if (kind[r] == 3) { if (fnew < 0) fnew = 0; }
                 else if (kind[r] == 4) { if (fnew < lo[r]) fnew = lo[r]; if (fnew > hi[r]) fnew = hi[r]; }
                 f[r] = fnew;
-                if (kind[r] == 2) { /* after both tangents: project onto the friction disc */
-                    real lim = cmu[r / 3] * f[r - 2], t = sqrt(f[r - 1] * f[r - 1] + f[r] * f[r]);
-                    if (t > lim) { real sc = (t > 0) ? lim / t : 0; f[r - 1] *= sc; f[r] *= sc; }
-                }
             }
             /* convergence: largest change of any row over this sweep, relative to the largest force */
             real dmax = 0, fmax = 0;
             for (int r = 0; r < R; r++) { real d = fabs(f[r] - fprev[r]); if (d > dmax) dmax = d; if (fabs(f[r]) > fmax) fmax = fabs(f[r]); }
             g_sweeps++;
-            if (dmax <= prm[P_TOL] * (1 + fmax)) break;
+            if (dmax <= prm[P_TOL] * (1 + fmax) || it == iters - 1) { g_hist[it + 1 < 64 ? it + 1 : 63]++; g_hist_nc[nc][0]++; g_hist_nc[nc][1] += it + 1; break; }
         }
         for (int r = 0; r < R; r++) for (int k = 0; k < nv; k++) acc[k] += Y[r][k] * f[r];
     }
@@ -422,6 +450,8 @@ static void link_kinematics(const Model *M, const real *st, const real *q, const
 
 /* ------------------------------ exported (ctypes) ------------------------------ */
 /* diagnostics (single-threaded use): totals since the last oracle_counters() call */
+void oracle_sweep_hist_nc(long long *out) { for (int k = 0; k < 9; k++) { out[2 * k] = g_hist_nc[k][0]; out[2 * k + 1] = g_hist_nc[k][1]; g_hist_nc[k][0] = g_hist_nc[k][1] = 0; } }
+void oracle_sweep_hist(long long *out) { for (int k = 0; k < 64; k++) { out[k] = g_hist[k]; g_hist[k] = 0; } }
 void oracle_counters(long long *out) { out[0] = g_sweeps; out[1] = g_substeps; out[2] = g_rows; out[3] = g_contacts; g_sweeps = g_substeps = g_rows = g_contacts = 0; }
 
 static Model mk_model(const int *mi, const float *mf) {
