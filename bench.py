@@ -5,8 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one policy step of BASELINE config C2 (`go2_ts`, heightfield curriculum, height-scan obs) = one
-`FusedLeggedEnv.step` = one C-ABI call `b200_env_step`: the decimated PD + rigid-body kernel, the frame-stack shift on a
-side stream under it, the fused post_physics_step kernel.  Envs shard as contiguous blocks, one process per
+`FusedLeggedEnv.step` = one C-ABI call `b200_env_step`: the decimated PD + rigid-body kernel and the fused
+post_physics_step kernel.  Envs shard as contiguous blocks, one process per
 GPU, no collective on the data path (weak scaling).  The line printed by rank 0 carries
 
   value        whole-job env-substeps/s, inputs resident in HBM: K steps timed one by one with CUDA events (L2 flushed between
@@ -15,8 +15,8 @@ GPU, no collective on the data path (weak scaling).  The line printed by rank 0 
                (`config.pre_roll_steps`, `workload_state`)
   e2e          the same metric through FusedLeggedEnv.step_host() = b200_env_step with HOST buffers: pinned actions H2D,
                kernels, rewards + resets D2H inside the timed region, every step
-  roofline     the post_physics_step as its own kernels (env_post_step_kernel + history_shift_kernel, timed call by call
-               in a second loop) against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline     the post_physics_step as its own kernel (env_post_step_kernel, timed call by call in a second loop) against
+               the measured HBM copy bandwidth (MEASURED_PEAKS.json); `whole_step` = all kernels' bytes over the step time
   kernels      the step, and its kernels timed call by call: average duration, share of the step, static resources (the
                dynamics kernel is latency / issue bound)
   cpu_baseline the oracle port timed on host cores on a bounded sample (rank 0, N=1 only)
@@ -205,7 +205,7 @@ def run_gpu(args):
         "solver_work_per_env": float(b["dyn_cost"].float().mean()),       # sum over the 4 substeps of (sweeps + 4) x constraint rows
         "mean_terrain_level": float(b["terrain_levels"].float().mean()) if spec.heightfield else 0.0,
     }
-    # ---- the same step call by call (dynamics kernel | side-stream history shift | env kernel): per-kernel times that
+    # ---- the same step call by call (dynamics kernel | env kernel): per-kernel times that
     # explain the fused number and give the env kernel's own HBM figure
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     for i in range(K):
@@ -224,19 +224,6 @@ def run_gpu(args):
     launches = sim.launch_count - launches0
     t_dyn = statistics.median(e[0].elapsed_time(e[1]) for e in ev)
     t_env = statistics.median(e[1].elapsed_time(e[2]) for e in ev)
-    # ---- the history shift kernel alone (it normally hides under the dynamics kernel on a side stream): timed on the
-    # launching stream with the side stream disabled, L2 flushed, so that the env path's HBM figure counts its time too
-    t_shift = 0.0
-    if env.widths["hist"]:
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
-        for i in range(K):
-            flush_l2()
-            evs[i][0].record()
-            sim.history_shift(side_stream=False, reorder=False)
-            evs[i][1].record()
-        barrier()
-        launches += K
-        t_shift = statistics.median(e[0].elapsed_time(e[1]) for e in evs)
     # ---- end to end through the public API with host buffers
     rew_host, rst_host, tmo_host = sim.make_host_step_buffers()       # one pinned slab: rew f32[N] | reset u8[N] | time_out u8[N]
     # FusedLeggedEnv.step_host = ONE C-ABI call (b200_env_step): H2D of the pinned actions, the kernels, one D2H of the slab
@@ -268,11 +255,10 @@ def run_gpu(args):
     model = sim._model
     peak, peak_src = _peaks()
     env_bytes = accounting.env_kernel_bytes(spec, model) * N
-    shift_bytes = accounting.history_shift_bytes(spec, model) * N
     dyn_bytes = accounting.dynamics_kernel_bytes(spec, model) * N
-    # the reference's post_physics_step = env kernel + history shift kernel: their bytes over the sum of their durations
-    achieved = (env_bytes + shift_bytes) / ((t_env + t_shift) * 1e-3) / 1e9
-    step_bytes = env_bytes + shift_bytes + dyn_bytes
+    # the reference's post_physics_step = the env kernel (the frame stacks are double-written rings: nothing is moved)
+    achieved = env_bytes / (t_env * 1e-3) / 1e9
+    step_bytes = env_bytes + dyn_bytes
     whole = step_bytes / (total_ms / K * 1e-3) / 1e9
     on_device = 4 * N * sum(env.widths[k] for k in ("obs", "priv", "hist", "critic"))     # observation tensors the policy reads in HBM
     traffic = None                          # DRAM bytes per launch of the same kernels from the committed ncu capture
@@ -281,7 +267,7 @@ def run_gpu(args):
         with open(tpath) as fh:
             tj = json.load(fh)
         if tj.get("workload") == f"{args.task}/{N}":
-            traffic = tj["env_post_step_kernel"] + tj["history_shift_kernel"]
+            traffic = tj["env_post_step_kernel"]
     ki_env, ki_dyn = sim.kernel_info("env"), sim.kernel_info("dynamics")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -299,26 +285,25 @@ def run_gpu(args):
         "workload_state": workload_state,
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "env_post_step_kernel + history_shift_kernel (the fused post_physics_step)", "bound": "hbm",
+        "roofline": {"kernel": "env_post_step_kernel (the fused post_physics_step)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": env_bytes + shift_bytes,
-                     "avg_launch_ms": t_env + t_shift,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": env_bytes,
+                     "avg_launch_ms": t_env,
+                     "bytes_variant": "ring: frame stacks are double-written rings handed out as strided views, a step writes each new "
+                                      "frame twice and moves nothing (SURVEY 8d names this variant); re-writing the stacks every step, "
+                                      f"as round 1 did, would add {accounting.shifted_stack_bytes(spec, model) * N} B per launch",
                      "whole_step": {"algorithmic_bytes": step_bytes, "ms": total_ms / K, "achieved": whole, "frac": whole / peak,
                                     "note": "all three kernels' bytes over the step time; the dynamics kernel (most of the step) is "
                                             "latency / issue bound by construction, SURVEY 8d"},
-                     "note": "history_shift_kernel runs on a side stream under the dynamics kernel; its stand-alone time is "
-                             "counted here although it is off the step's critical path"},
+                     "note": "at 4096 envs the kernel's whole working set (19 MB) is L2 resident and one warp per env leaves 28 warps "
+                             "per SM: it is bound by instruction latency, not by HBM -- time, not this fraction, is what to read"},
         "kernels": {
-            "step": {"avg_ms": t_step, "note": "one b200_env_step call: dynamics kernel, history shift on the side stream, env "
+            "step": {"avg_ms": t_step, "note": "one b200_env_step call: dynamics kernel (the env-ordering kernel on a side stream under it), env "
                      "kernel, stats finalize; the entries below are a second loop that times the kernels call by call"},
             "dynamics_step_kernel": {"avg_ms": t_dyn, "share": t_dyn / (t_dyn + t_env), "bound": "latency/issue", **ki_dyn,
                                      "algorithmic_bytes_per_launch": dyn_bytes, "hbm_gbs": dyn_bytes / (t_dyn * 1e-3) / 1e9},
             "env_post_step_kernel": {"variant": sim.env_kernel_variant, "avg_ms": t_env, "share": t_env / (t_dyn + t_env), "bound": "latency/issue", **ki_env,
                                      "algorithmic_bytes_per_launch": env_bytes, "hbm_gbs": env_bytes / (t_env * 1e-3) / 1e9},
-            "history_shift_kernel": {"avg_ms_alone": t_shift, "bound": "hbm", "algorithmic_bytes_per_launch": shift_bytes,
-                                     "hbm_gbs": (shift_bytes / (t_shift * 1e-3) / 1e9) if t_shift else None,
-                                     "frac_of_peak": (shift_bytes / (t_shift * 1e-3) / 1e9 / peak) if t_shift else None,
-                                     "stream": "side (overlaps dynamics_step_kernel)"},
         },
     }
     if world == 1 and not args.no_cpu_baseline:

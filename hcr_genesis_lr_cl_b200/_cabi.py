@@ -244,8 +244,7 @@ def buffer_shapes(spec: T.TaskSpec, model: RobotModel, N: int) -> "OrderedDict[s
         normal_vector_around_feet=(N, 3 * F), last_dof_vel=(N, A), last_feet_vel=(N, F, 3), last_base_lin_vel=(N, 3),
         last_base_ang_vel=(N, 3),
         obs_buf=(N, w["obs"]), privileged_obs_buf=(N, max(w["priv"], 1)),
-        obs_history0=(N, max(w["hist"], 1)), obs_history1=(N, max(w["hist"], 1)),
-        critic_obs0=(N, max(w["critic"], 1)), critic_obs1=(N, max(w["critic"], 1)),
+        obs_history=(N, 2 * max(w["hist"], 1)), critic_obs=(N, 2 * max(w["critic"], 1)),     # double-written rings (b200_step.h)
         rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), gait_state=(N, H["B200_GAIT_STATE"]), height_cells=(N, P, 2), stats=(stats_base(nsum) + STATS_RING * (max(nsum, 1) + H["B200_STATS_EXTRA"]),), cstr_prob=(N,), global_flags=(4,),
         next_state_buf=(N, w["obs"] if spec.obs_kind == "go2_dreamwaq" else 1), dyn_cost=(2, N), dyn_order=(2, N),
         action_queue=(N, (int(spec.ctrl_delay_step_range[1]) + 1) * A if spec.randomize_ctrl_delay else 1), action_delay=(N,),
@@ -300,21 +299,19 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.b200_stats_ring.restype = ctypes.c_int
     lib.b200_device.argtypes = [vp]
     lib.b200_device.restype = ctypes.c_int
-    lib.b200_env_post_step.argtypes = [vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, vp]
+    lib.b200_env_post_step.argtypes = [vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_longlong, ctypes.c_int, vp]
     lib.b200_env_post_step.restype = ctypes.c_int
-    lib.b200_env_step.argtypes = [vp, vp, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, vp, vp, vp, vp]
+    lib.b200_env_step.argtypes = [vp, vp, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_longlong, vp, vp, vp, vp]
     lib.b200_env_step.restype = ctypes.c_int
     lib.b200_set_step_flags.argtypes = [vp, ctypes.c_int]
     lib.b200_set_step_flags.restype = ctypes.c_int
-    lib.b200_history_shift.argtypes = [vp, ctypes.c_int, vp]
-    lib.b200_history_shift.restype = ctypes.c_int
-    lib.b200_set_history_side_stream.argtypes = [vp, ctypes.c_int]
-    lib.b200_set_history_side_stream.restype = ctypes.c_int
+    lib.b200_set_side_stream.argtypes = [vp, ctypes.c_int]
+    lib.b200_set_side_stream.restype = ctypes.c_int
     lib.b200_set_dynamics_order.argtypes = [vp, ctypes.c_int]
     lib.b200_set_dynamics_order.restype = ctypes.c_int
     lib.b200_set_behavior.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
     lib.b200_set_behavior.restype = ctypes.c_int
-    lib.b200_reset_all.argtypes = [vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int, vp]
+    lib.b200_reset_all.argtypes = [vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, vp]
     lib.b200_reset_all.restype = ctypes.c_int
     lib.b200_kernel_info.argtypes = [vp, ctypes.c_char_p, ip, ip, ip, ip]
     lib.b200_kernel_info.restype = ctypes.c_int
@@ -331,4 +328,4 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = ["b200_create", "b200_destroy", "b200_set_terrain", "b200_bind_buffers", "b200_dynamics_step", "b200_simulator_step",
                     "b200_stats_ring", "b200_device",
-                    "b200_history_shift", "b200_set_history_side_stream", "b200_set_dynamics_order", "b200_env_post_step", "b200_env_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_env_kernel_variant", "b200_launch_count", "b200_last_error"]
+                    "b200_set_side_stream", "b200_set_dynamics_order", "b200_env_post_step", "b200_env_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_env_kernel_variant", "b200_launch_count", "b200_last_error"]

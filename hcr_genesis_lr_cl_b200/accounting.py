@@ -3,7 +3,10 @@
 Accounting rules: every distinct per-env tensor a kernel must read counts once for the read and
 every tensor it must produce counts once for the write, per policy step; terrain gathers count the int16 bytes
 touched; random numbers, constants and the task/model descriptors count zero.  `tools/algorithmic_bytes.py` prints
-the table; bench.py computes `roofline.achieved` from `env_path_bytes` (env kernel + history shift kernel).
+the table; bench.py computes `roofline.achieved` from `env_path_bytes`.  The frame stacks are double-written rings
+handed out as strided views (include/b200_step.h), so a step writes each new frame twice and moves nothing else: the
+"ring" variant SURVEY 8d asks to be named (its shift read of 1 563 floats and the 1 785-float stack re-write are gone;
+10.4 KB per env and step in SURVEY's hand count with materialised outputs, 5.5 KB here without).
 """
 from __future__ import annotations
 
@@ -43,8 +46,8 @@ def env_kernel_items(spec: T.TaskSpec, model: RobotModel):
         reads["DR params (friction, mass, com, kp, kd scales)"] = (5 + 2 * A) * f
         if w["priv"]:
             writes["privileged_obs_buf"] = w["priv"] * f
-        writes["obs_history (new frame)"] = w["obs"] * f
-        writes["critic_obs_buf (new frame)"] = w["single_critic"] * f
+        writes["obs_history (new frame, both ring slots)"] = 2 * w["obs"] * f
+        writes["critic_obs_buf (new frame, both ring slots)"] = 2 * w["single_critic"] * f
     if spec.gait_enabled:
         reads["gait_state"] = 20 * f
         writes["gait_state"] = 20 * f
@@ -53,27 +56,21 @@ def env_kernel_items(spec: T.TaskSpec, model: RobotModel):
     return reads, writes
 
 
-def history_shift_items(spec: T.TaskSpec, model: RobotModel):
-    """history_shift_kernel: both frame stacks lose their oldest frame (read the kept frames, write them one slot down)."""
-    w = spec.obs_widths(model)
-    keep_h, keep_c = max(w["hist"] - w["obs"], 0) * 4, max(w["critic"] - w["single_critic"], 0) * 4
-    return {"obs_history kept frames": keep_h, "critic stack kept frames": keep_c}, \
-           {"obs_history kept frames": keep_h, "critic stack kept frames": keep_c}
-
-
 def env_kernel_bytes(spec: T.TaskSpec, model: RobotModel) -> int:
     r, w = env_kernel_items(spec, model)
     return int(sum(r.values()) + sum(w.values()))
 
 
-def history_shift_bytes(spec: T.TaskSpec, model: RobotModel) -> int:
-    r, w = history_shift_items(spec, model)
-    return int(sum(r.values()) + sum(w.values()))
-
-
 def env_path_bytes(spec: T.TaskSpec, model: RobotModel) -> int:
-    """The reference's post_physics_step = env_post_step_kernel + history_shift_kernel."""
-    return env_kernel_bytes(spec, model) + history_shift_bytes(spec, model)
+    """The reference's post_physics_step = env_post_step_kernel."""
+    return env_kernel_bytes(spec, model)
+
+
+def shifted_stack_bytes(spec: T.TaskSpec, model: RobotModel) -> int:
+    """What moving the K - 1 kept frames of both stacks every step would cost (read + write): the traffic the ring layout
+    removed (round 1's history_shift_kernel), kept for the comparison in DESIGN.md."""
+    w = spec.obs_widths(model)
+    return 2 * 4 * (max(w["hist"] - w["obs"], 0) + max(w["critic"] - w["single_critic"], 0))
 
 
 def dynamics_kernel_bytes(spec: T.TaskSpec, model: RobotModel) -> int:

@@ -16,9 +16,6 @@
 #include "dynamics_kernel.cuh"
 #include "env_kernel.cuh"
 
-#ifndef HIST_SHIFT_GRID_PER_SM
-#define HIST_SHIFT_GRID_PER_SM 8       // cap of history_shift_kernel's grid.x per SM (grid-stride loop beyond)
-#endif
 static thread_local std::string g_err;
 static int fail(const char *what, cudaError_t e = cudaSuccess) {
     g_err = what;
@@ -41,13 +38,11 @@ struct B200Handle {
     float beh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int gait_cb = 0, gait_reset = 0;
     EnvStageTab stage{};
-    // side stream of b200_history_shift: forked at the event b200_dynamics_step records before its launch, joined by the
-    // next b200_env_post_step
+    // side stream of dynamics_order_kernel: forked at an event recorded before the dynamics launch, joined by the next
+    // b200_env_post_step
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool fork_recorded = false;
     bool side_enabled = true;
-    int preshift_parity = -1;      // parity the stacks have been shifted for (-1: none pending)
     int env_preset = -1;           // instantiation of the env kernel: index into env_presets.inc, -1 = generic
     float *d_actions = nullptr;    // staging of b200_env_step's host actions
     bool stats_zeroed = false;
@@ -171,18 +166,34 @@ static int launch_dynamics(B200Handle *h, const float *actions, void *stream, in
     const dim3 grid((N + DYN_WARPS_PER_BLOCK - 1) / DYN_WARPS_PER_BLOCK), block(DYN_WARPS_PER_BLOCK * 32);
     cudaStream_t s = (cudaStream_t)stream;
     if (h->task.i[TI_CAT]) CK(cudaMemsetAsync(h->bufs.global_flags, 0, 4 * sizeof(int32_t), s));
-    if (h->preshift_parity < 0 && !h->side_pending) {              // fork point of a b200_history_shift that follows: everything
-        if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));   // enqueued before this step
+    // the env -> warp-slot order of the NEXT dynamics launch, from the cost of the PREVIOUS one (the launch enqueued below
+    // reads / writes the other halves of dyn_order / dyn_cost): a one-CTA sort on the side stream, under this launch
+    const bool ordered = h->order_enabled && h->bufs.dyn_order && h->bufs.dyn_cost;
+    const bool reorder = ordered && h->dyn_launches >= 1;
+    if (reorder && h->side_enabled) {
+        if (!h->side) CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        if (!h->ev_join) CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        if (h->side_pending) CK(cudaStreamWaitEvent(s, h->ev_join, 0));        // an order kernel nobody joined yet: before this launch reads its half
         CK(cudaEventRecord(h->ev_fork, s));
-        h->fork_recorded = true;
+        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     }
-    const int par = (h->order_enabled && h->bufs.dyn_order && h->bufs.dyn_cost) ? (int)(h->dyn_launches & 1) : -1;
+    const int par = ordered ? (int)(h->dyn_launches & 1) : -1;
     if (h->task.i[TI_C] == 4) B200_LAUNCH(dynamics_step_kernel<4>, grid, block, h->dyn_smem, s, h->task, h->bufs, h->model, h->terrain, actions, par, sim_only);
     else B200_LAUNCH(dynamics_step_kernel<2>, grid, block, h->dyn_smem, s, h->task, h->bufs, h->model, h->terrain, actions, par, sim_only);
     h->dyn_launches++;
     h->launches++;
     h->stats_zeroed = true;
     CK(cudaGetLastError());
+    if (reorder) {
+        const int next = (int)(h->dyn_launches & 1);                    // parity of the next dynamics launch; its cost half is two launches old
+        cudaStream_t run = h->side_enabled ? h->side : s;
+        B200_LAUNCH(dynamics_order_kernel, 1, 1024, 0, run, h->bufs.dyn_cost + (size_t)next * N, h->bufs.dyn_order + (size_t)next * N, N,
+                    h->sm_count * DYN_WARPS_PER_BLOCK);
+        h->launches++;
+        CK(cudaGetLastError());
+        if (h->side_enabled) { CK(cudaEventRecord(h->ev_join, h->side)); h->side_pending = true; }
+    }
     return 0;
 }
 
@@ -198,69 +209,22 @@ int b200_simulator_step(B200Handle *h, const float *actions, void *stream) {
     return launch_dynamics(h, actions, stream, 1);
 }
 
-int b200_history_shift(B200Handle *h, int parity, void *stream) {
-    if (check_ready(h, "b200_history_shift")) return 1;
-    DeviceGuard guard(h);
-    const int *ti = h->task.i;
-    const bool stacks = ti[TI_OBS_KIND] >= 1;        // the task keeps frame stacks
-    // the order of the NEXT dynamics launch from the cost of the PREVIOUS one (the launch in flight writes the other halves)
-    // (only when the dynamics launch of this step is already enqueued -- fork_recorded -- or we run in order on the caller's
-    // stream: a side-stream sort racing ahead of a dynamics launch that reads the same half would be a data race)
-    const bool reorder = h->order_enabled && h->bufs.dyn_order && h->bufs.dyn_cost && h->dyn_launches >= 2 &&
-                         (h->fork_recorded || !h->side_enabled);
-    if (!stacks && !reorder) return 0;
-    cudaStream_t s = (cudaStream_t)stream, run = s;
-    if (h->side_enabled) {
-        if (!h->side) CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-        if (!h->ev_fork) CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        if (!h->ev_join) CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-        if (!h->fork_recorded) CK(cudaEventRecord(h->ev_fork, s));     // no dynamics step before us: fork here
-        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        run = h->side;
-    }
-    h->fork_recorded = false;
-    const int N = ti[TI_NUM_ENVS], p = parity & 1;
-    if (reorder) {
-        const int next = (int)(h->dyn_launches & 1);                    // parity of the next dynamics launch; its cost half is two launches old
-        B200_LAUNCH(dynamics_order_kernel, 1, 1024, 0, run, h->bufs.dyn_cost + (size_t)next * N, h->bufs.dyn_order + (size_t)next * N, N,
-                    h->sm_count * DYN_WARPS_PER_BLOCK);
-        h->launches++;
-        CK(cudaGetLastError());
-    }
-    if (stacks) {
-        const long long Mh = (long long)N * ti[TI_FRAME_STACK] * ti[TI_NUM_OBS], Mc = (long long)N * ti[TI_C_FRAME_STACK] * ti[TI_SINGLE_CRITIC];
-        // one warp-iteration moves 32 x HIST_SHIFT_UNROLL vectors; enough blocks for the larger stack, capped at a few per SM
-        const long long per_block = (long long)(HIST_SHIFT_BLOCK / 32) * 32 * HIST_SHIFT_UNROLL * 4;
-        long long blocks = ((Mh > Mc ? Mh : Mc) + per_block - 1) / per_block;
-        if (blocks > (long long)h->sm_count * HIST_SHIFT_GRID_PER_SM) blocks = (long long)h->sm_count * HIST_SHIFT_GRID_PER_SM;
-        if (blocks < 1) blocks = 1;
-        B200_LAUNCH(history_shift_kernel, dim3((unsigned)blocks, 2), HIST_SHIFT_BLOCK, 0, run, h->bufs.obs_history[p], h->bufs.obs_history[p ^ 1], Mh, ti[TI_NUM_OBS],
-                    h->bufs.critic_obs[p], h->bufs.critic_obs[p ^ 1], Mc, ti[TI_SINGLE_CRITIC]);
-        h->launches++;
-        CK(cudaGetLastError());
-        h->preshift_parity = p;
-    }
-    if (h->side_enabled) { CK(cudaEventRecord(h->ev_join, h->side)); h->side_pending = true; }
-    return 0;
-}
-
 int b200_set_dynamics_order(B200Handle *h, int enabled) {
     if (!h) return fail("b200_set_dynamics_order: null handle");
     h->order_enabled = enabled != 0;
     return 0;
 }
 
-int b200_set_history_side_stream(B200Handle *h, int enabled) {
-    if (!h) return fail("b200_set_history_side_stream: null handle");
+int b200_set_side_stream(B200Handle *h, int enabled) {
+    if (!h) return fail("b200_set_side_stream: null handle");
     h->side_enabled = enabled != 0;
     return 0;
 }
 
-static EnvCall make_call(B200Handle *h, long long step, float lo, float span, int parity, int mask, int force) {
-    EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.parity = parity & 1; call.phase_mask = mask; call.force_reset = force; call.sit_pose = h->sit_pose;
+static EnvCall make_call(B200Handle *h, long long step, float lo, float span, long long hist_step, int mask, int force) {
+    EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.hist_step = (uint32_t)(hist_step < 0 ? 0 : hist_step); call.phase_mask = mask; call.force_reset = force; call.sit_pose = h->sit_pose;
     for (int k = 0; k < 8; k++) call.beh[k] = h->beh[k];
     call.gait_cb = h->gait_cb; call.gait_reset = h->gait_reset;
-    call.preshifted = 0;
     // extras["episode"] means are finalised by the env kernel's last CTA when the reset phase ran for real
     const int N = h->task.i[TI_NUM_ENVS];
     const int n_teach = max(0, min(N, h->task.i[TI_NUM_TEACHER] - h->task.i[TI_ENV_OFFSET]));   // go2_cts: teacher envs of this rank
@@ -273,19 +237,15 @@ static EnvCall make_call(B200Handle *h, long long step, float lo, float span, in
     return call;
 }
 
-static int launch_env(B200Handle *h, long long step, float lo, float span, int parity, int mask, int force, void *stream) {
+static int launch_env(B200Handle *h, long long step, float lo, float span, long long hist_step, int mask, int force, void *stream) {
     DeviceGuard guard(h);
     const int N = h->task.i[TI_NUM_ENVS];
     const int n_sums = h->task.i[TI_N_SUMS];
     cudaStream_t s = (cudaStream_t)stream;
     if ((mask & PHASE_RESET) && !h->stats_zeroed) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 4), s));
     h->stats_zeroed = false;
-    EnvCall call = make_call(h, step, lo, span, parity, mask, force);
+    EnvCall call = make_call(h, step, lo, span, hist_step, mask, force);
     if (h->side_pending) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->side_pending = false; }      // join the side stream
-    if (h->preshift_parity >= 0) {                   // use the shifted stacks only if they were made for this parity and phase set
-        call.preshifted = (h->preshift_parity == (parity & 1) && !force && (mask & PHASE_OBSERVE)) ? 1 : 0;
-        h->preshift_parity = -1;
-    }
     const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
     B200_LAUNCH(env_kernel_fn(h->env_preset), grid, block, h->env_smem, s, h->task, h->bufs, h->terrain, call, h->stage);
     h->launches++;
@@ -293,13 +253,13 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, int p
     return 0;
 }
 
-int b200_env_post_step(B200Handle *h, long long step, float lo, float span, int parity, int mask, void *stream) {
+int b200_env_post_step(B200Handle *h, long long step, float lo, float span, long long hist_step, int mask, void *stream) {
     if (check_ready(h, "b200_env_post_step")) return 1;
     if ((mask & PHASE_ALL) == 0) return fail("b200_env_post_step: empty phase mask");
-    return launch_env(h, step, lo, span, parity, mask & PHASE_ALL, 0, stream);
+    return launch_env(h, step, lo, span, hist_step, mask & PHASE_ALL, 0, stream);
 }
 
-int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long long step, float lo, float span, int parity,
+int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long long step, float lo, float span, long long hist_step,
                   float *host_rew, uint8_t *host_reset, uint8_t *host_time_out, void *stream) {
     if (check_ready(h, "b200_env_step")) return 1;
     if (!actions) return fail("b200_env_step: null actions");
@@ -313,8 +273,7 @@ int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long
         dev_actions = h->d_actions;
     }
     if (b200_dynamics_step(h, dev_actions, stream)) return 1;
-    if (b200_history_shift(h, parity, stream)) return 1;
-    if (launch_env(h, step, lo, span, parity, PHASE_ALL, 0, stream)) return 1;
+    if (launch_env(h, step, lo, span, hist_step, PHASE_ALL, 0, stream)) return 1;
     // rew | reset | time_out laid out back to back on both sides (B200Simulator allocates them so): one copy
     const uint8_t *d_rew = (const uint8_t *)h->bufs.rew_buf;
     const bool packed = host_rew && host_reset && host_time_out && h->bufs.reset_buf == d_rew + 4 * (size_t)N &&
@@ -344,9 +303,9 @@ int b200_set_behavior(B200Handle *h, const float *ranges8, int gait_callback, in
     return 0;
 }
 
-int b200_reset_all(B200Handle *h, long long step, float lo, float span, int parity, void *stream) {
+int b200_reset_all(B200Handle *h, long long step, float lo, float span, void *stream) {
     if (check_ready(h, "b200_reset_all")) return 1;
-    return launch_env(h, step, lo, span, parity, PHASE_RESET, 1, stream);
+    return launch_env(h, step, lo, span, 0, PHASE_RESET, 1, stream);
 }
 
 int b200_kernel_info(B200Handle *h, const char *kernel, int *regs, int *smem, int *blocks_per_sm, int *block_threads) {

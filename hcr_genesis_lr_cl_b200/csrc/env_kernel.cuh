@@ -61,13 +61,12 @@ template <class S> struct TiView {
 struct EnvCall {
     uint32_t step;       // LeggedRobot.common_step_counter after its increment
     float vx_lo, vx_span;
-    int parity;          // history buffers: read [parity], write [parity ^ 1]
+    uint32_t hist_step;  // observation frames appended to the frame stacks so far: this step's frame goes to ring slot hist_step mod K
     int phase_mask;
     int force_reset;     // b200_reset_all: run only the reset phase, for every env
     int sit_pose;        // envs resetting in this call start in the sit pose (one host coin per step, tron1_pf_ee.py:204-210)
     float beh[8];        // go2_wtw behaviour ranges {gait period, base height, foot clearance, pitch} x {lo, span}
     int gait_cb, gait_reset;   // gait index the host drew for the callback / reset resampling of this step
-    int preshifted;      // history_shift_kernel already moved the kept frames of both stacks for this parity
     // extras["episode"] means: the last CTA to finish turns the per-step reductions into ring slot `stats_slot`
     int finalize, stats_slot;
     float inv_episode_length_s, inv_num_envs, inv_teacher, inv_student;
@@ -102,97 +101,20 @@ __device__ __forceinline__ int cell_of(float p, float border, float hscale) {
 
 __device__ __forceinline__ int wrap_idx(int i, int n) { return i < 0 ? i + n : i; }   // torch negative-index wrap
 
-// dst[0..n) = cleared ? 0 : src[0..n): coalesced, 8 independent 128-byte requests in flight per warp
-__device__ __forceinline__ void shift_copy(float *__restrict__ dst, const float *__restrict__ src, int n, bool cleared, int lane) {
-    int e = lane;
-    for (; e + 7 * 32 < n; e += 8 * 32) {
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = cleared ? 0.f : __ldcs(src + e + 32 * k);
-#pragma unroll
-        for (int k = 0; k < 8; k++) dst[e + 32 * k] = v[k];
-    }
-    for (; e < n; e += 32) dst[e] = cleared ? 0.f : __ldcs(src + e);
+// Frame stacks (obs_history: K = frame_stack frames of num_obs floats; critic stack: c_frame_stack frames) live in HBM as
+// DOUBLE-WRITTEN RINGS: a row holds 2K frame slots and the frame of observation step t is stored twice, in slot t mod K
+// and in slot t mod K + K.  The K most recent frames, oldest first -- exactly the tensor the reference re-concatenates
+// from its deque every step (legged_robot_ts.py:29-47) -- are then ALWAYS the contiguous slots [t mod K + 1, t mod K + K]
+// of the row: the host hands them out as a strided view (row stride 2K frames) and a step costs two frame writes per
+// stack instead of moving the K - 1 kept frames (12.5 KB per env and step for go2_ts, 77 % of what the path used to
+// touch).  A reset clears the env's whole row first (legged_robot_ts.py:120-125 zeroes every deque entry).
+__device__ __forceinline__ void ring_clear(float *ring, int env, int K, int frame, int lane) {
+    float *d = ring + (size_t)env * 2 * K * frame;
+    for (int e = lane; e < 2 * K * frame; e += 32) d[e] = 0.f;
 }
-
-// One env's row of a frame stack: drop the oldest frame, append `newf`.  When history_shift_kernel has already moved the
-// kept frames into `dst` (preshifted), only the new frame is written here -- and a reset clears what was moved.
-__device__ __forceinline__ void history_append(float *dst, const float *src, int env, int W, int frame, const float *newf, bool cleared,
-                                               int preshifted, int lane) {
-    const int keepw = W - frame;
-    float *d = dst + (size_t)env * W;
-    if (!preshifted) shift_copy(d, src + (size_t)env * W + frame, keepw, cleared, lane);
-    else if (cleared) for (int e = lane; e < keepw; e += 32) d[e] = 0.f;
-    for (int e = lane; e < frame; e += 32) d[keepw + e] = newf[e];
-}
-
-// The shift of both frame stacks for the coming env_post_step (b200_history_shift): out[env][0 : W - frame] =
-// in[env][frame : W].  It depends on nothing the dynamics kernel produces, so it is launched on a side stream and runs
-// in the shadow of the dynamics kernel.  Seen over the whole [N * W] array the shift is ONE flat copy with a constant
-// offset, out[d] = in[d + frame]: the `frame` slots at the end of each row receive the head of the next row, which is
-// harmless because env_post_step_kernel writes the new frame there (and clears the rows of envs that reset) before
-// anyone reads it.  So the kernel is a streaming copy: aligned 16-byte loads and stores, the (frame mod 4) words of
-// misalignment between source and destination are fixed up in registers with the neighbour lane's vector.
-#ifndef HIST_SHIFT_UNROLL
-#define HIST_SHIFT_UNROLL 4         // independent 16-byte loads in flight per thread
-#endif
-#ifndef HIST_SHIFT_BLOCK
-#define HIST_SHIFT_BLOCK 256
-#endif
-#ifndef HIST_SHIFT_MIN_BLOCKS
-#define HIST_SHIFT_MIN_BLOCKS 1
-#endif
-__device__ __forceinline__ void history_shift_flat(const float *__restrict__ in, float *__restrict__ out, long long M, int f) {
-    if (M <= f) return;
-    const int lane = threadIdx.x & 31;
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5), warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int a = f >> 2, b = f & 3;
-    const bool vec = (M & 3) == 0 && ((((size_t)in) | ((size_t)out)) & 15) == 0;
-    const long long nvec = vec ? (M - f) >> 2 : 0;                       // whole destination vectors
-    const float4 *in4 = (const float4 *)in;
-    float4 *out4 = (float4 *)out;
-    for (long long v0 = warp * (32 * HIST_SHIFT_UNROLL); v0 < nvec; v0 += nwarps * (32 * HIST_SHIFT_UNROLL)) {
-        float4 s[HIST_SHIFT_UNROLL];
-        float tail[HIST_SHIFT_UNROLL][3];
-#pragma unroll
-        for (int k = 0; k < HIST_SHIFT_UNROLL; k++) {
-            const long long v = v0 + 32 * k + lane;
-            s[k] = v < nvec ? __ldcs(in4 + v + a) : make_float4(0.f, 0.f, 0.f, 0.f);
-            // lane 31 (and the owner of the very last vector) has no neighbour holding the next source vector: it fetches
-            // the b words it needs from it itself
-            tail[k][0] = tail[k][1] = tail[k][2] = 0.f;
-            if (b > 0 && (lane == 31 || v == nvec - 1) && v < nvec) {
-                const float *nx = in + 4 * (v + a + 1);
-                tail[k][0] = __ldcs(nx);
-                if (b > 1) tail[k][1] = __ldcs(nx + 1);
-                if (b > 2) tail[k][2] = __ldcs(nx + 2);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < HIST_SHIFT_UNROLL; k++) {
-            const long long v = v0 + 32 * k + lane;
-            float4 o = s[k];
-            if (b > 0) {                                                 // warp-uniform
-                float nx = __shfl_down_sync(B200_FULL_MASK, s[k].x, 1), ny = 0.f, nz = 0.f;
-                if (b > 1) ny = __shfl_down_sync(B200_FULL_MASK, s[k].y, 1);
-                if (b > 2) nz = __shfl_down_sync(B200_FULL_MASK, s[k].z, 1);
-                if (lane == 31 || v == nvec - 1) { nx = tail[k][0]; ny = tail[k][1]; nz = tail[k][2]; }
-                if (b == 1) o = make_float4(s[k].y, s[k].z, s[k].w, nx);
-                else if (b == 2) o = make_float4(s[k].z, s[k].w, nx, ny);
-                else o = make_float4(s[k].w, nx, ny, nz);
-            }
-            if (v < nvec) out4[v] = o;
-        }
-    }
-    // scalar remainder (and the whole array when it is not 16-byte tileable)
-    const long long tid = warp * 32 + lane, nthreads = nwarps * 32;
-    for (long long d = 4 * nvec + tid; d < M - f; d += nthreads) out[d] = __ldcs(in + d + f);
-}
-
-__global__ void B200_LAUNCH_BOUNDS(HIST_SHIFT_BLOCK, HIST_SHIFT_MIN_BLOCKS)
-history_shift_kernel(const float *in_h, float *out_h, long long Mh, int fh, const float *in_c, float *out_c, long long Mc, int fc) {
-    if (blockIdx.y == 0) history_shift_flat(in_h, out_h, Mh, fh);         // grid.y: 0 = obs_history, 1 = critic stack
-    else history_shift_flat(in_c, out_c, Mc, fc);
+__device__ __forceinline__ void ring_put(float *ring, int env, int K, int frame, int slot, const float *newf, int lane) {
+    float *d = ring + ((size_t)env * 2 * K + slot) * frame;
+    for (int e = lane; e < frame; e += 32) { const float v = newf[e]; d[e] = v; d[(size_t)K * frame + e] = v; }
 }
 
 // per-env input tensors staged per CTA: X(field, element type, elements per env)
@@ -654,6 +576,11 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     f3 grav_obs = grav;
     int new_level = level0;
     if ((pm & PHASE_RESET) && reset) {
+        if (ti[TI_OBS_KIND] >= 1) {                                               // history deques cleared (legged_robot_ts.py:120-125)
+            ring_clear(B.obs_history, env, ti[TI_FRAME_STACK], ti[TI_NUM_OBS], lane);
+            ring_clear(B.critic_obs, env, ti[TI_C_FRAME_STACK], ti[TI_SINGLE_CRITIC], lane);
+            __syncwarp();                                                         // before the observation phase writes the new frame
+        }
         if (lane < n_sums) atomicAdd(B.stats + lane, my_sum);                    // extras["episode"] numerators
         if (lane == 0) atomicAdd(B.stats + n_sums, 1.0f);
         my_sum = 0.f;
@@ -816,7 +743,6 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         if (ti[TI_OBS_KIND] == 5) {   // go2_wtw.py:53-111: obs_buf = 5 x 61 noisy frames, privileged_obs_buf = 5 x 99 critic frames
             const int SC = ti[TI_SINGLE_CRITIC], NB = 9 + 3 * A;
             float *cr = es + ES_CRIT;
-            const bool cleared = (pm & PHASE_RESET) && reset;
             if (lane < 2 * F) ob[NB + lane] = clk;
             if (lane == 0) { float *d = ob + NB + 2 * F; d[0] = gper; d[1] = bh_t; d[2] = fc_t; d[3] = pt_t; d[4] = th0; d[5] = th1; d[6] = th2; d[7] = th3; }
             __syncwarp();
@@ -838,12 +764,11 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             __syncwarp();
             for (int e = lane; e < SC; e += 32) cr[e] = fminf(fmaxf(cr[e], -clipo), clipo);
             __syncwarp();
-            history_append(B.obs_history[call.parity ^ 1], B.obs_history[call.parity], env, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, call.preshifted, lane);
-            history_append(B.critic_obs[call.parity ^ 1], B.critic_obs[call.parity], env, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, call.preshifted, lane);
+            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, (int)(call.hist_step % (uint32_t)ti[TI_FRAME_STACK]), nz, lane);
+            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, (int)(call.hist_step % (uint32_t)ti[TI_C_FRAME_STACK]), cr, lane);
         } else if (ti[TI_OBS_KIND] == 4) {   // tron1_pf_ee.py:53-141: features = 10 x 31 noisy frames, labels 17, critic = 10 x 134
             const int SC = ti[TI_SINGLE_CRITIC], NP = ti[TI_NUM_PRIV], NCS = ti[TI_N_CS], NB = NO - 4;   // NB = 9 + 3A
             float *cr = es + ES_CRIT, *pv = es + ES_PRIV;
-            const bool cleared = (pm & PHASE_RESET) && reset;
             const int DRN = 10 + 2 * A;
             if (lane < 2 * F) ob[NB + lane] = clk;
             __syncwarp();
@@ -890,8 +815,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             for (int e = lane; e < NP; e += 32) B.privileged_obs_buf[env * NP + e] = pv[e];          // estimator labels (unclipped)
             for (int e = lane; e < SC; e += 32) cr[e] = fminf(fmaxf(cr[e], -clipo), clipo);
             __syncwarp();
-            history_append(B.obs_history[call.parity ^ 1], B.obs_history[call.parity], env, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, call.preshifted, lane);
-            history_append(B.critic_obs[call.parity ^ 1], B.critic_obs[call.parity], env, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, call.preshifted, lane);
+            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, (int)(call.hist_step % (uint32_t)ti[TI_FRAME_STACK]), nz, lane);
+            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, (int)(call.hist_step % (uint32_t)ti[TI_C_FRAME_STACK]), cr, lane);
         } else if (ti[TI_OBS_KIND] == 3) {   // tron1_pf.py:15-70: obs_buf = stack of noisy frames, privileged_obs_buf = stack of critic frames
             const int SC = ti[TI_SINGLE_CRITIC];
             float *cr = es + ES_CRIT;
@@ -907,8 +832,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             }
             if (fl) cr[3 + NO + A + 7 + lane] = fat;
             __syncwarp();
-            history_append(B.obs_history[call.parity ^ 1], B.obs_history[call.parity], env, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, call.preshifted, lane);
-            history_append(B.critic_obs[call.parity ^ 1], B.critic_obs[call.parity], env, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, call.preshifted, lane);
+            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, (int)(call.hist_step % (uint32_t)ti[TI_FRAME_STACK]), nz, lane);
+            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, (int)(call.hist_step % (uint32_t)ti[TI_C_FRAME_STACK]), cr, lane);
         } else if (ti[TI_OBS_KIND] >= 1) {   // go2_ts (1) / go2_cat (2) / go2_cts (6) / go2_ee (7) / go2_dreamwaq (8)
             const int kind = ti[TI_OBS_KIND];
             const bool cat = kind == 2;      // go2_cat.py:19-99: 3 more DR entries, no base_lin_vel, raw feet heights
@@ -972,10 +897,9 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 if (ee) for (int e = lane; e < NO; e += 32) nz[e] = fminf(fmaxf(nz[e], -clipo), clipo);
                 __syncwarp();
             }
-            // history stacks: shift one frame out, append the new one (legged_robot_ts.py:29-47); cleared on reset (:120-125)
-            const bool cleared = (pm & PHASE_RESET) && reset;
-            history_append(B.obs_history[call.parity ^ 1], B.obs_history[call.parity], env, ti[TI_FRAME_STACK] * NO, NO, nz, cleared, call.preshifted, lane);
-            history_append(B.critic_obs[call.parity ^ 1], B.critic_obs[call.parity], env, ti[TI_C_FRAME_STACK] * SC, SC, cr, cleared, call.preshifted, lane);
+            // history stacks: the new frame goes into both of its ring slots (legged_robot_ts.py:29-47)
+            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, (int)(call.hist_step % (uint32_t)ti[TI_FRAME_STACK]), nz, lane);
+            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, (int)(call.hist_step % (uint32_t)ti[TI_C_FRAME_STACK]), cr, lane);
         }
     }
     // Tasks that shift the history again at the end of post_physics_step (go2_cat.py:127-130): the dynamics

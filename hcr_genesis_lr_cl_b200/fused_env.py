@@ -6,8 +6,12 @@ legged_robot_ts.py:59-76): same return tuples, same attribute names the runners 
 ``get_observations``, ``reset``).  Per policy step it makes ONE C-ABI call, b200_env_step, which launches
 
     dynamics_step_kernel   (clip/shift actions, 4 x [PD torque + rigid-body substep])
-    history_shift_kernel   (side stream, in the shadow of the dynamics kernel)
     env_post_step_kernel   (fused post_physics_step; its last CTA finalises extras["episode"])
+
+(plus the one-CTA dynamics_order_kernel on a side stream).  The frame stacks (`obs_history`, `critic_obs_buf`) are strided
+[N, K * width] views of double-written rings in HBM (include/b200_step.h): same values and frame order as the tensors the
+reference concatenates from its deques every step, row stride 2 K * width, nothing is moved between steps.  The view of a
+step stays valid until K further steps have overwritten its slots; copy it (`RolloutStorage.add_transitions` does) to keep it.
 
 and nothing else on the GPU; there is no host synchronisation inside ``step`` (SURVEY 8b "Threading").
 """
@@ -36,7 +40,6 @@ class FusedLeggedEnv:
         self.simulator = self.simulator_class(spec, None, device, True, num_envs=num_envs, terrain=terrain, env_offset=env_offset,
                                        num_envs_global=num_envs_global, debug_cells=debug_cells)
         sim = self.simulator
-        sim.fused_histories = True
         self._b = sim._buf
         self.widths = spec.obs_widths(sim._model)
         self.stacked = spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw", "go2_ee")   # obs / privileged obs are the frame stacks themselves
@@ -110,11 +113,11 @@ class FusedLeggedEnv:
 
     @property
     def obs_history(self):
-        return self._b[f"obs_history{self.simulator._parity}"]
+        return self.simulator.obs_history
 
     @property
     def critic_obs_buf(self):
-        return self._b[f"critic_obs{self.simulator._parity}"]
+        return self.simulator.critic_obs
 
     # ------------------------------------------------------------------ VecEnv API
     def step(self, actions: torch.Tensor):
@@ -128,7 +131,7 @@ class FusedLeggedEnv:
         return self._returns()
 
     def step_two_kernels(self, actions: torch.Tensor):
-        """The same step call by call (b200_dynamics_step, b200_history_shift, b200_env_post_step): what the plugin path
+        """The same step call by call (b200_dynamics_step, b200_env_post_step): what the plugin path
         does between `Simulator.step` and `post_physics_step`; kept for per-kernel timing and as a cross-check."""
         sim = self.simulator
         sim.step(actions)                                      # _pre_sim_step + simulator.step

@@ -79,10 +79,9 @@ class B200Simulator:
         self._lib = self._load_library()          # raises when the extension is not built
         self._tdev = self._check_device(sim_device)
         self._handle = ctypes.c_void_p()
-        self._parity = 0
+        self._hist_count = 0           # observation frames appended to the frame stacks so far (ring position, include/b200_step.h)
         self._step_counter = 0         # plugin mode: post_physics_step calls == LeggedRobot.common_step_counter (keys the Philox draws)
         self._dyn_order = os.environ.get("B200_DYN_ORDER", "1") != "0"
-        self.fused_histories = False   # set by FusedLeggedEnv: b200_history_shift follows every dynamics step
         self._parse_cfg()
         self._create_sim()
         self._create_envs()
@@ -306,19 +305,6 @@ class B200Simulator:
             self._ck(self._lib.b200_simulator_step(self._handle, a.data_ptr(), self._stream()))
             return
         self._ck(self._lib.b200_dynamics_step(self._handle, a.data_ptr(), self._stream()))
-        if self.fused_histories:      # fused mode: the frame stacks are shifted on a side stream in the shadow of the dynamics kernel
-            self._ck(self._lib.b200_history_shift(self._handle, self._parity, self._stream()))
-
-    def history_shift(self, side_stream: bool = True, reorder: bool = True):
-        """Launch the frame-stack shift for the coming fused post step (normally done by `step` in fused mode);
-        `reorder=False` leaves out the env-ordering kernel that shares its side-stream slot (timing the copy alone)."""
-        self._ck(self._lib.b200_set_history_side_stream(self._handle, int(side_stream)))
-        if not reorder:
-            self._ck(self._lib.b200_set_dynamics_order(self._handle, 0))
-        self._ck(self._lib.b200_history_shift(self._handle, self._parity, self._stream()))
-        if not reorder:
-            self._ck(self._lib.b200_set_dynamics_order(self._handle, int(self._dyn_order)))
-        self._ck(self._lib.b200_set_history_side_stream(self._handle, 1))
 
     def set_dynamics_order(self, enabled: bool) -> None:
         """Cost-ordered env -> warp-slot assignment of the dynamics kernel (scheduling only; results are identical)."""
@@ -331,16 +317,16 @@ class B200Simulator:
         ``LeggedRobot.post_physics_step`` incremented ``common_step_counter`` (legged_robot.py:60-63), so the count of
         these calls is that counter: it keys the simulator-side Philox draws of the step (push, reset DR)."""
         self._step_counter += 1
-        self._ck(self._lib.b200_env_post_step(self._handle, self._step_counter, 0.0, 0.0, self._parity, H["PHASE_SIM_POST"], self._stream()))
+        self._ck(self._lib.b200_env_post_step(self._handle, self._step_counter, 0.0, 0.0, self._hist_count, H["PHASE_SIM_POST"], self._stream()))
 
     def fused_post_step(self, step_counter: int, cmd_range_x: Sequence[float], phase_mask: Optional[int] = None):
         """Whole LeggedRobot.post_physics_step in one launch (used by FusedLeggedEnv)."""
         lo, hi = float(cmd_range_x[0]), float(cmd_range_x[1])
         mask = H["PHASE_ALL"] if phase_mask is None else int(phase_mask)
-        self._ck(self._lib.b200_env_post_step(self._handle, int(step_counter), lo, float(np.float32(hi - lo)), self._parity,
+        self._ck(self._lib.b200_env_post_step(self._handle, int(step_counter), lo, float(np.float32(hi - lo)), self._hist_count,
                                               mask, self._stream()))
         if mask & H["PHASE_OBSERVE"]:
-            self._parity ^= 1
+            self._hist_count += 1
 
     def make_host_step_buffers(self):
         """Pinned host (rew [N] f32, reset [N] bool, time_out [N] bool) carved from one slab laid out like the device side,
@@ -366,10 +352,10 @@ class B200Simulator:
                 raise ValueError("host output buffers must be pinned")
         lo, hi = float(cmd_range_x[0]), float(cmd_range_x[1])
         self._ck(self._lib.b200_env_step(self._handle, a.data_ptr(), int(on_host), int(step_counter), lo, float(np.float32(hi - lo)),
-                                         self._parity, host_rew.data_ptr() if host_rew is not None else None,
+                                         self._hist_count, host_rew.data_ptr() if host_rew is not None else None,
                                          host_reset.data_ptr() if host_reset is not None else None,
                                          host_time_out.data_ptr() if host_time_out is not None else None, self._stream()))
-        self._parity ^= 1
+        self._hist_count += 1
 
     def set_step_flags(self, sit_pose: bool) -> None:
         self._ck(self._lib.b200_set_step_flags(self._handle, int(bool(sit_pose))))
@@ -383,7 +369,7 @@ class B200Simulator:
 
     def fused_reset_all(self, step_counter: int, cmd_range_x: Sequence[float]):
         lo, hi = float(cmd_range_x[0]), float(cmd_range_x[1])
-        self._ck(self._lib.b200_reset_all(self._handle, int(step_counter), lo, float(np.float32(hi - lo)), self._parity, self._stream()))
+        self._ck(self._lib.b200_reset_all(self._handle, int(step_counter), lo, float(np.float32(hi - lo)), self._stream()))
 
     def reset_idx(self, env_ids):
         """Domain randomisation of reset envs (genesis_simulator.py:62-82); plugin (non-fused) path."""
@@ -518,17 +504,56 @@ class B200Simulator:
         self._buf["kd_scale"][env_ids] = self._draw_range(T.SITE_KD, env_ids, list(range(A)), s.kd_range)
 
     # ------------------------------------------------------------------ state snapshots (tests, checkpointing)
+    # ------------------------------------------------------------------ frame stacks (double-written rings, include/b200_step.h)
+    def _stack_view(self, name: str, frames: int, width: int) -> torch.Tensor:
+        """The `frames` most recent frames of a stack, oldest first, as a [N, frames * width] view of its ring (row stride
+        2 * frames * width, last dimension contiguous): what the reference re-concatenates from its deque every step."""
+        last = (self._hist_count - 1) % frames
+        return self._buf[name][:, (last + 1) * width:(last + 1 + frames) * width]
+
+    @property
+    def obs_history(self) -> torch.Tensor:
+        w = self.spec.obs_widths(self._model)
+        return self._stack_view("obs_history", self.spec.frame_stack, w["obs"])
+
+    @property
+    def critic_obs(self) -> torch.Tensor:
+        w = self.spec.obs_widths(self._model)
+        return self._stack_view("critic_obs", self.spec.c_frame_stack, w["single_critic"])
+
+    def _load_stack(self, name: str, frames: int, width: int, window) -> None:
+        """Put a [N, frames * width] window (oldest frame first) into the ring at the current position."""
+        win = torch.from_numpy(np.ascontiguousarray(np.asarray(window, np.float32))).to(self._tdev).reshape(self._num_envs, frames, width)
+        ring = self._buf[name].view(self._num_envs, 2 * frames, width)
+        for i in range(frames):
+            slot = (self._hist_count - frames + i) % frames
+            ring[:, slot] = win[:, i]
+            ring[:, slot + frames] = win[:, i]
+
+    # ------------------------------------------------------------------ state snapshots (tests, checkpointing)
     def load_state(self, st: dict) -> None:
-        alias = {"q": "dof_pos", "qd": "dof_vel", "obs_hist": f"obs_history{self._parity}", "critic_hist": f"critic_obs{self._parity}"}
+        alias = {"q": "dof_pos", "qd": "dof_vel"}
+        w = self.spec.obs_widths(self._model)
         for k, v in st.items():
             name = alias.get(k, k)
-            if name in self._buf and np.asarray(v).size == self._buf[name].numel():
+            if name in ("obs_hist", "obs_history") and w["hist"] and np.asarray(v).size == self._num_envs * w["hist"]:
+                self._load_stack("obs_history", self.spec.frame_stack, w["obs"], v)
+            elif name in ("critic_hist", "critic_obs") and w["critic"] and np.asarray(v).size == self._num_envs * w["critic"]:
+                self._load_stack("critic_obs", self.spec.c_frame_stack, w["single_critic"], v)
+            elif name in self._buf and np.asarray(v).size == self._buf[name].numel():
                 t = torch.from_numpy(np.ascontiguousarray(np.asarray(v))).to(self._tdev)
                 self._buf[name].copy_(t.reshape(self._buf[name].shape).to(self._buf[name].dtype))
 
     def get_state(self) -> dict:
+        """Every buffer as numpy; `obs_history` / `critic_obs` are the current K-frame windows (the rings themselves are
+        returned as `obs_history_ring` / `critic_obs_ring`)."""
         self._sync()
-        return {k: v.detach().cpu().numpy().copy() for k, v in self._buf.items()}
+        out = {k: v.detach().cpu().numpy().copy() for k, v in self._buf.items()}
+        out["obs_history_ring"], out["critic_obs_ring"] = out["obs_history"], out["critic_obs"]
+        w = self.spec.obs_widths(self._model)
+        out["obs_history"] = self.obs_history.detach().cpu().numpy().copy() if w["hist"] else np.zeros((self._num_envs, 1), np.float32)
+        out["critic_obs"] = self.critic_obs.detach().cpu().numpy().copy() if w["critic"] else np.zeros((self._num_envs, 1), np.float32)
+        return out
 
     def kernel_info(self, kernel: str) -> dict:
         r, s, b, t = (ctypes.c_int32() for _ in range(4))

@@ -15,7 +15,6 @@
  *                        GenesisSimulator.post_physics_step   legged_gym/simulator/genesis_simulator.py:35-60
  *                        (+ everything those call: height scan :552-610, OOB :612-628, callbacks,
  *                        check_termination, compute_reward, reset_idx, compute_observations)
- *   b200_history_shift   deque / torch.cat frame stacking     legged_gym/envs/base/legged_robot_ts.py:86-97 (side stream)
  *   b200_env_step        LeggedRobot.step, all of the above   legged_gym/envs/base/legged_robot.py:37-53, with HOST buffers:
  *                        + the host copies of the rollout     rsl_rl/runners/on_policy_runner.py:118-139
  *   b200_reset_all       BaseTask.reset -> reset_idx(all)     legged_gym/envs/base/base_task.py:60-64
@@ -223,8 +222,10 @@ typedef struct B200Buffers {
     /* outputs */
     float *obs_buf;             /* [N,num_obs]   */
     float *privileged_obs_buf;  /* [N,num_priv]  */
-    float *obs_history[2];      /* [N,frame_stack*num_obs]      ping-pong, see b200_env_post_step */
-    float *critic_obs[2];       /* [N,c_frame_stack*single]     ping-pong */
+    float *obs_history;         /* [N, 2*frame_stack, num_obs]   frame stack as a double-written ring: the frame of observation step t sits in
+                                   slots t mod K and t mod K + K, so the K most recent frames (oldest first: the tensor the reference
+                                   concatenates from its deque, legged_robot_ts.py:29-47) are the contiguous slots [t mod K + 1, t mod K + K] */
+    float *critic_obs;          /* [N, 2*c_frame_stack, single_critic]   same, for the critic stack */
     float *rew_buf;             /* [N] */
     uint8_t *reset_buf;         /* [N] uint8 (torch.bool storage) */
     uint8_t *time_out_buf;      /* [N] uint8 */
@@ -268,38 +269,31 @@ int b200_dynamics_step(B200Handle *h, const float *dev_actions, void *cuda_strea
  * llast_actions / action_queue are left untouched). */
 int b200_simulator_step(B200Handle *h, const float *dev_actions, void *cuda_stream);
 
-/* Optional, fused mode only: start moving the kept frames of both frame stacks (obs_history / critic_obs, [parity] ->
- * [parity^1]) for the b200_env_post_step that will follow with the same `parity`.  The copy depends on nothing the
- * dynamics kernel produces; call it right after b200_dynamics_step with the same stream: it runs on an internal side
- * stream forked at the point where b200_dynamics_step was enqueued (so it overlaps the dynamics kernel) and the next
- * b200_env_post_step joins it.  Without this call b200_env_post_step shifts the stacks itself.  Replaces the deque /
- * torch.cat frame stacking of legged_robot_ts.py:86-97, tron1_pf.py:57-70, go2_wtw.py:92-111.  The same side-stream
- * slot carries the env ordering of the next dynamics launch (b200_set_dynamics_order). */
-int b200_history_shift(B200Handle *h, int parity, void *cuda_stream);
-/* enabled = 0: b200_history_shift launches on the caller's stream instead of the side stream (profiling, timing the
- * copy alone, or callers that must keep every launch on one stream).  Default: enabled. */
-int b200_set_history_side_stream(B200Handle *h, int enabled);
-
 /* enabled = 0: warp slot w of the dynamics kernel runs env w.  Default (enabled, B200_DYN_ORDER=0 in the environment
- * disables it at creation): b200_history_shift also launches dynamics_order_kernel on the side stream, which sorts the
- * envs by the contact-solver work they needed two launches ago into B200Buffers.dyn_order so that the envs of a CTA
- * cost the same and the SMs get the same mix.  Pure scheduling: results are identical either way. */
+ * disables it at creation): every b200_dynamics_step / b200_simulator_step also launches dynamics_order_kernel on an
+ * internal side stream (forked before the dynamics launch, joined by the next b200_env_post_step), which sorts the envs
+ * by the contact-solver work they needed two launches ago into B200Buffers.dyn_order so that the envs of a CTA cost the
+ * same and the SMs get the same mix.  Pure scheduling: results are identical either way. */
 int b200_set_dynamics_order(B200Handle *h, int enabled);
+/* enabled = 0: dynamics_order_kernel is launched on the caller's stream instead of the internal side stream (profiling, or
+ * callers that must keep every launch on one stream).  Default: enabled. */
+int b200_set_side_stream(B200Handle *h, int enabled);
 
 /* Fused post_physics_step. `step_counter` is LeggedRobot.common_step_counter *after* its increment;
- * `cmd_vx_lo/span` is the (curriculum-mutable) lin_vel_x command range as (lower, fp32(upper-lower)); `parity` (0/1) selects which of the
- * ping-pong history buffers is read (parity) and written (parity^1). */
-int b200_env_post_step(B200Handle *h, long long step_counter, float cmd_vx_lo, float cmd_vx_span, int parity,
+ * `cmd_vx_lo/span` is the (curriculum-mutable) lin_vel_x command range as (lower, fp32(upper-lower)); `hist_step` is the number of
+ * observation frames appended to the frame stacks so far (the caller counts the calls that ran PHASE_OBSERVE): this call's
+ * frame goes to ring slots hist_step mod K and hist_step mod K + K of B200Buffers.obs_history / critic_obs. */
+int b200_env_post_step(B200Handle *h, long long step_counter, float cmd_vx_lo, float cmd_vx_span, long long hist_step,
                        int phase_mask, void *cuda_stream);
 
 /* One whole env.step (LeggedRobot.step, legged_robot.py:37-53) with HOST buffers, one call: copies `actions` ([N,A] fp32;
- * pinned host memory when `actions_on_host`, device memory otherwise) to the device, then b200_dynamics_step,
- * b200_history_shift (when the task keeps frame stacks) and b200_env_post_step(PHASE_ALL), then copies rew_buf ([N] fp32),
+ * pinned host memory when `actions_on_host`, device memory otherwise) to the device, then b200_dynamics_step and
+ * b200_env_post_step(PHASE_ALL), then copies rew_buf ([N] fp32),
  * reset_buf and time_out_buf ([N] bool bytes) into the given pinned host buffers (each may be NULL).  Everything is
  * enqueued on `cuda_stream`; nothing is synchronised -- the caller waits on the stream before reading the host buffers.
  * This is the call the rollout loop makes (on_policy_runner.py:118-139: env.step(actions) followed by host reads). */
 int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long long step_counter, float cmd_vx_lo, float cmd_vx_span,
-                  int parity, float *host_rew, uint8_t *host_reset, uint8_t *host_time_out, void *cuda_stream);
+                  long long hist_step, float *host_rew, uint8_t *host_reset, uint8_t *host_time_out, void *cuda_stream);
 
 /* Per-step host scalars for the next b200_env_post_step / b200_reset_all: `sit_pose` != 0 -> envs that reset in that
  * call start in the sit pose (tron1_pf_ee.py:204-210 draws ONE coin per reset batch). */
@@ -311,7 +305,7 @@ int b200_set_step_flags(B200Handle *h, int sit_pose);
 int b200_set_behavior(B200Handle *h, const float *ranges8, int gait_callback, int gait_reset);
 
 /* reset_idx(all envs) without a preceding step (BaseTask.reset). */
-int b200_reset_all(B200Handle *h, long long step_counter, float cmd_vx_lo, float cmd_vx_span, int parity, void *cuda_stream);
+int b200_reset_all(B200Handle *h, long long step_counter, float cmd_vx_lo, float cmd_vx_span, void *cuda_stream);
 
 /* static resource usage of a kernel ("dynamics" | "env"): registers/thread, static+dynamic smem/block, max blocks/SM */
 int b200_kernel_info(B200Handle *h, const char *kernel, int *regs, int *smem_bytes, int *blocks_per_sm, int *block_threads);

@@ -60,7 +60,7 @@ class EmuSim:
         self.buf["kp_scale"][:] = 1
         self.buf["kd_scale"][:] = 1
         self.cbuf = _cabi.fill_buffers(lambda n: self.buf[n].ctypes.data)
-        self.parity = 0
+        self.hist_count = 0          # observation frames appended so far (ring position of the frame stacks)
         self.step_counter = 0
         self.cmd_range_x = [float(spec.cmd_lin_vel_x[0]), float(spec.cmd_lin_vel_x[1])]
         self.beh_ranges = np.zeros((4, 2), np.float64)      # go2_wtw behaviour ranges (period, height, clearance, pitch)
@@ -70,11 +70,34 @@ class EmuSim:
     def _p(a):
         return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
+    def _stack(self, name):
+        w = self.spec.obs_widths(self.model)
+        return (self.spec.frame_stack, w["obs"]) if name == "obs_history" else (self.spec.c_frame_stack, w["single_critic"])
+
+    def _load_stack(self, name, window):
+        K, W = self._stack(name)
+        win = np.asarray(window, np.float32).reshape(self.N, K, W)
+        ring = self.buf[name].reshape(self.N, 2 * K, W)
+        for i in range(K):
+            slot = (self.hist_count - K + i) % K
+            ring[:, slot] = win[:, i]
+            ring[:, slot + K] = win[:, i]
+
+    def _window(self, name):
+        K, W = self._stack(name)
+        last = (self.hist_count - 1) % K
+        return self.buf[name][:, (last + 1) * W:(last + 1 + K) * W]
+
     def load_state(self, st):
-        alias = {"q": "dof_pos", "qd": "dof_vel", "obs_hist": f"obs_history{self.parity}", "critic_hist": f"critic_obs{self.parity}"}
+        alias = {"q": "dof_pos", "qd": "dof_vel"}
+        w = self.spec.obs_widths(self.model)
         for k, v in st.items():
             name = alias.get(k, k)
-            if name in self.buf and np.asarray(v).size == self.buf[name].size:
+            if name in ("obs_hist", "obs_history") and w["hist"] and np.asarray(v).size == self.N * w["hist"]:
+                self._load_stack("obs_history", v)
+            elif name in ("critic_hist", "critic_obs") and w["critic"] and np.asarray(v).size == self.N * w["critic"]:
+                self._load_stack("critic_obs", v)
+            elif name in self.buf and np.asarray(v).size == self.buf[name].size:
                 self.buf[name][...] = np.asarray(v).reshape(self.buf[name].shape)
         if "common_step_counter" in st:
             self.step_counter = int(st["common_step_counter"])
@@ -90,7 +113,7 @@ class EmuSim:
         self.lib.emu_dynamics_step(self._p(self.tf), self._p(self.ti), self._p(self.mi), self._p(self.mf), self._p(self.hs),
                                    ctypes.c_int(rows), ctypes.c_int(cols), ctypes.byref(self.cbuf), self._p(a))
 
-    def env_post_step(self, phase_mask=63, force_reset=0, sit_pose=None, preshift=True):
+    def env_post_step(self, phase_mask=63, force_reset=0, sit_pose=None):
         rows, cols = (self.hs.shape if self.hs is not None else (0, 0))
         lv, ty = (self.origins.shape[:2] if self.origins is not None else (0, 0))
         self.step_counter += 1
@@ -109,17 +132,18 @@ class EmuSim:
         self.last_preset = self.lib.emu_env_post_step(self._p(self.tf), self._p(self.ti), self._p(self.hs), ctypes.c_int(rows), ctypes.c_int(cols),
                                    self._p(self.origins), ctypes.c_int(lv), ctypes.c_int(ty), ctypes.byref(self.cbuf),
                                    ctypes.c_longlong(self.step_counter), ctypes.c_float(lo), ctypes.c_float(np.float32(hi - lo)),
-                                   ctypes.c_int(self.parity), ctypes.c_int(phase_mask), ctypes.c_int(force_reset), ctypes.c_int(int(bool(sit_pose))),
-                                   self._p(beh), ctypes.c_int(gaits[0]), ctypes.c_int(gaits[1]), ctypes.c_int(int(preshift)))
-        self.parity ^= 1
+                                   ctypes.c_longlong(self.hist_count), ctypes.c_int(phase_mask), ctypes.c_int(force_reset), ctypes.c_int(int(bool(sit_pose))),
+                                   self._p(beh), ctypes.c_int(gaits[0]), ctypes.c_int(gaits[1]))
+        if phase_mask & 32:
+            self.hist_count += 1
 
     @property
     def obs_history(self):
-        return self.buf[f"obs_history{self.parity}"]
+        return self._window("obs_history")
 
     @property
     def critic_obs(self):
-        return self.buf[f"critic_obs{self.parity}"]
+        return self._window("critic_obs")
 
 
 from oracle.physics import oracle_params, oracle_policy_step  # noqa: E402,F401  (historic home of these helpers)

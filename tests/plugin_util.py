@@ -97,15 +97,13 @@ def transfer_state(ref_env, fused_env, sum_names):
     fb["episode_sums"].copy_(torch.stack([ref_env.episode_sums[k] for k in sum_names], dim=1))
     if hasattr(ref_env, "gait_time"):
         fb["gait_state"].copy_(torch.from_numpy(pack_gait(ref_env)).to(fb["gait_state"].device))
-    par = fs._parity
     hist = crit = None
     if hasattr(ref_env, "critic_history"):                      # go2_wtw names its deques obs_history / critic_history
         hist, crit = ref_env.obs_history, ref_env.critic_history
     elif hasattr(ref_env, "obs_history_deque"):
         hist, crit = ref_env.obs_history_deque, ref_env.critic_obs_deque
     if hist is not None:
-        fb[f"obs_history{par}"].copy_(torch.cat(list(hist), dim=1))
-        fb[f"critic_obs{par}"].copy_(torch.cat(list(crit), dim=1))
+        fs.load_state(dict(obs_history=torch.cat(list(hist), dim=1).cpu().numpy(), critic_obs=torch.cat(list(crit), dim=1).cpu().numpy()))
     if getattr(ref_env.cfg.domain_rand, "randomize_ctrl_delay", False):
         fb["action_queue"].copy_(ref_env.action_queue.reshape(fb["action_queue"].shape))
         fb["action_delay"].copy_(ref_env.action_delay.to(torch.int32))

@@ -52,29 +52,40 @@ def test_library_is_the_cuda_path(built_library):
                                   "go2_dreamwaq_n32"])
 def test_env_kernel_matches_reference_golden(name):
     """Injected post-physics states from the reference run -> every output of the fused kernel."""
-    _golden_run(name, fused_histories=True)
+    _golden_run(name)
 
 
 def test_control_delay_queue_matches_reference_golden():
     """domain_rand.randomize_ctrl_delay (legged_robot.py:144-148,240-245): the dynamics kernel pushes the clipped action
     into the env's queue and drives the joints with the delayed slot, the env kernel clears the queue and redraws the
     delay on reset; runs on the generic env-kernel instantiation (no shipped config enables the delay)."""
-    _golden_run("go2_ts_delay_n32", fused_histories=True)
+    _golden_run("go2_ts_delay_n32")
 
 
-def test_env_kernel_shifts_histories_itself_without_preshift():
-    """Plugin-mode / fallback path: no b200_history_shift call, the env kernel moves the frame stacks."""
-    _golden_run("go2_ts_n32", fused_histories=False)
+def test_frame_stack_views_are_strided_windows_of_the_rings():
+    """The frame stacks handed to the runner are [N, K * width] views of the double-written rings: row stride 2 K width,
+    contiguous rows, no copy -- and they hold exactly the reference's stacks (checked against the goldens above)."""
+    from hcr_genesis_lr_cl_b200 import task_spec as T
+    spec = T.go2_ts_spec()
+    env = _env(spec, 64, load_terrain(spec))
+    env.reset()
+    for _ in range(7):
+        env.step(torch.randn(64, 12, device="cuda"))
+        h, c = env.obs_history, env.critic_obs_buf
+        assert h.shape == (64, 900) and c.shape == (64, 885) and h.stride() == (1800, 1) and c.stride() == (1770, 1)
+        assert h.untyped_storage().data_ptr() == env.simulator._buf["obs_history"].untyped_storage().data_ptr()
+        assert torch.equal(h[:, -45:], env.obs_buf)                      # newest frame last (legged_robot_ts.py:41-47)
+        w = torch.nn.Linear(900, 8, device="cuda")
+        assert torch.allclose(w(h), w(h.contiguous()), atol=1e-5)         # a strided batch feeds nn.Linear as it is
 
 
-def _golden_run(name, fused_histories):
+def _golden_run(name):
     g, s0 = load_golden(name)
     spec = spec_for(g)
     terrain = load_terrain(spec) if spec.heightfield else None
     N, T_ = g["actions"].shape[1], g["actions"].shape[0]
     env = _env(spec, N, terrain)
     sim = env.simulator
-    sim.fused_histories = fused_histories
     sim.load_state(s0)
     env.common_step_counter = int(s0["common_step_counter"])
     env.command_ranges["lin_vel_x"] = [float(x) for x in s0["cmd_range_x"]]
@@ -93,9 +104,9 @@ def _golden_run(name, fused_histories):
         mine = dict(st, actions_buf=st["actions"], end_q=st["dof_pos"], end_qd=st["dof_vel"])
         if spec.obs_kind in ("tron1_pf", "tron1_pf_ee", "go2_wtw", "go2_ee"):     # the returned obs / privileged obs are the frame stacks
             mine["estimator_labels_buf"] = st["privileged_obs_buf"]
-            mine["obs_buf"], mine["privileged_obs_buf"] = st[f"obs_history{sim._parity}"], st[f"critic_obs{sim._parity}"]
+            mine["obs_buf"], mine["privileged_obs_buf"] = st["obs_history"], st["critic_obs"]
         if spec.obs_kind == "go2_dreamwaq":                              # labels travel in privileged_obs_buf, the critic stack is returned
-            mine["explicit_labels_buf"], mine["privileged_obs_buf"] = st["privileged_obs_buf"], st[f"critic_obs{sim._parity}"]
+            mine["explicit_labels_buf"], mine["privileged_obs_buf"] = st["privileged_obs_buf"], st["critic_obs"]
         skip0 = spec.obs_kind in ("tron1_pf_ee", "go2_wtw")  # R18: env 0 is coupled to all envs in the reference; not reproduced
         for k, r in ref.items():
             if k not in mine or k in ("end_state",):
@@ -107,7 +118,7 @@ def _golden_run(name, fused_histories):
                 assert np.array_equal(m.astype(np.int64), r.astype(np.int64)), f"step {t}: {k} not bit-exact"
             else:
                 _close(m, r, what=f"step {t}: {k}")
-        for hk, name in (("obs_history", f"obs_history{sim._parity}"), ("critic_obs_buf", f"critic_obs{sim._parity}")):
+        for hk, name in (("obs_history", "obs_history"), ("critic_obs_buf", "critic_obs")):
             if f"hist{t}/{hk}" in g:
                 _close(st[name], g[f"hist{t}/{hk}"], what=f"step {t}: {hk}")
     assert int(g["out/reset_buf"].sum()) > 0          # the window did contain resets
@@ -252,7 +263,7 @@ def test_full_size_one_step_matches_the_oracle_pair():
         assert err < 1e-4 * max(1.0, float(np.abs(r).max())), f"{k}: {err:.3e}"
     # env kernel vs the numpy oracle on the kernel's own post-physics state
     eo = EnvOracle(spec, N, terrain[0], terrain[1])
-    alias = {"dof_pos": "q", "dof_vel": "qd", f"obs_history{sim._parity}": "obs_hist", f"critic_obs{sim._parity}": "critic_hist"}
+    alias = {"dof_pos": "q", "dof_vel": "qd", "obs_history": "obs_hist", "critic_obs": "critic_hist"}
     for k, v in full.items():
         kk = alias.get(k, k)
         if kk in eo.st:
@@ -272,8 +283,8 @@ def test_full_size_one_step_matches_the_oracle_pair():
     _close(out["rew_buf"], o["rew_buf"], what="rew_buf")
     _close(out["obs_buf"], o["obs_buf"], what="obs_buf")
     _close(out["privileged_obs_buf"], o["privileged_obs_buf"], what="privileged_obs_buf")
-    _close(out[f"critic_obs{sim._parity}"], o["critic_obs_buf"], what="critic stack")
-    _close(out[f"obs_history{sim._parity}"], o["obs_history"], what="obs history")
+    _close(out["critic_obs"], o["critic_obs_buf"], what="critic stack")
+    _close(out["obs_history"], o["obs_history"], what="obs history")
     _close(out["rand_push_vels"], eo.st["rand_push_vels"], what="push")
 
 
@@ -368,8 +379,8 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
         else:
             _close(out["obs_buf"], o["obs_buf"], what=f"step {t}: obs")
             _close(out["privileged_obs_buf"], o["privileged_obs_buf"], what=f"step {t}: priv")
-        _close(out[f"obs_history{sim._parity}"], o["obs_history"], what=f"step {t}: obs_history")
-        _close(out[f"critic_obs{sim._parity}"], o["critic_obs_buf"], what=f"step {t}: critic")
+        _close(out["obs_history"], o["obs_history"], what=f"step {t}: obs_history")
+        _close(out["critic_obs"], o["critic_obs_buf"], what=f"step {t}: critic")
         _close(out["episode_sums"], eo.st["episode_sums"], what=f"step {t}: episode_sums")
         _close(out["commands"], eo.st["commands"], what=f"step {t}: commands")
         _close(out["dof_pos"], eo.st["q"], what=f"step {t}: reset dof_pos")
@@ -431,7 +442,7 @@ def test_full_size_properties():
     assert torch.isfinite(sa["obs_buf"]).all() and torch.isfinite(sa["rew_buf"]).all()
     assert sa["height_cells"].min() >= 0 and sa["height_cells"].max() <= 1198
     n_steps = len(acts) + 1                                           # reset() = reset_all + one zero-action step
-    assert env_a.simulator.launch_count == 1 + 3 * n_steps + (n_steps - 1)   # (dynamics, history shift, env) per step + the env-order kernel from the 2nd step on
+    assert env_a.simulator.launch_count == 1 + 2 * n_steps + (n_steps - 1)   # (dynamics, env) per step + the env-order kernel from the 2nd step on
 
 
 def test_short_rollout_against_oracle(golden):
@@ -475,7 +486,7 @@ def test_short_rollout_against_oracle(golden):
 
 def test_one_call_host_step_equals_the_three_call_step(golden):
     """b200_env_step (pinned host actions in, rew / reset / time_out out, ONE C-ABI call) is bit-identical to the step
-    made call by call (b200_dynamics_step, b200_history_shift, b200_env_post_step)."""
+    made call by call (b200_dynamics_step, b200_env_post_step)."""
     g, s0, spec, terrain = golden
     N = 512
     rng = np.random.default_rng(2)
@@ -554,7 +565,7 @@ def test_edited_config_runs_on_the_generic_instantiation(golden):
         assert np.array_equal(out["height_cells"], o["height_cells"])
         _close(out["rew_buf"], o["rew_buf"], what=f"step {t}: rew")
         _close(out["obs_buf"], o["obs_buf"], what=f"step {t}: obs")
-        _close(out[f"critic_obs{sim._parity}"], o["critic_obs_buf"], what=f"step {t}: critic")
+        _close(out["critic_obs"], o["critic_obs_buf"], what=f"step {t}: critic")
 
 
 @pytest.mark.parametrize("task", ["go2", "go2_ts", "go2_cat", "go2_wtw", "go2_cts", "go2_ee", "go2_dreamwaq", "tron1_pf", "tron1_pf_ee"])
@@ -606,7 +617,7 @@ def test_long_closed_loop_rollout_tracks_the_oracle(task):
     model = sim._model
     orc = PhysicsOracle(model, oracle_params(spec, model), terrain[0] if terrain else None, precision="f32")
     eo = EnvOracle(spec, N, *(terrain if terrain else (None, None)))
-    alias = {"dof_pos": "q", "dof_vel": "qd", f"obs_history{sim._parity}": "obs_hist", f"critic_obs{sim._parity}": "critic_hist"}
+    alias = {"dof_pos": "q", "dof_vel": "qd", "obs_history": "obs_hist", "critic_obs": "critic_hist"}
     for k, v in s0.items():
         kk = alias.get(k, k)
         if kk in eo.st:

@@ -18,27 +18,27 @@ INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contact
                                         ("go2_cts_n32", 5), ("go2_ee_n32", 5), ("go2_dreamwaq_n32", 5)])
 def test_emulated_env_kernel_matches_reference_golden(name, steps):
     """The preset-specialised instantiation b200_create selects for this descriptor (asserted: not the generic one)."""
-    _run_golden(name, steps, preshift=True)
+    _run_golden(name, steps)
 
 
 def test_emulated_env_kernel_with_control_delay_matches_reference_golden():
     """domain_rand.randomize_ctrl_delay on (no shipped config enables it -> generic instantiation): the env kernel clears
     the action queue and redraws the delay of envs that reset (legged_robot.py:144-148)."""
-    _run_golden("go2_ts_delay_n32", 8, preshift=True, specialized=False)
+    _run_golden("go2_ts_delay_n32", 8, specialized=False)
 
 
 @pytest.mark.parametrize("name", ["go2_ts_n32", "tron1_pf_ee_n32", "go2_wtw_n32", "go2_cat_n32"])
 def test_emulated_generic_env_kernel_matches_reference_golden(name):
     """The generic instantiation (any edited configuration runs on it): descriptor ints read at run time."""
-    _run_golden(name, 3, preshift=True, specialized=False)
+    _run_golden(name, 3, specialized=False)
 
 
-def test_emulated_env_kernel_in_kernel_history_shift():
-    """Without b200_history_shift the env kernel moves the frame stacks itself (plugin-mode / fallback path)."""
-    _run_golden("go2_ts_n32", 4, preshift=False)
+def test_emulated_frame_stack_rings_wrap_around():
+    """More steps than the critic stack has slots (5): the ring position wraps and the window stays the last K frames."""
+    _run_golden("go2_ts_n32", 9)
 
 
-def _run_golden(name, steps, preshift, specialized=True):
+def _run_golden(name, steps, specialized=True):
     g, s0 = load_golden(name)
     spec = spec_for(g)
     hs, origins = (load_terrain(spec) if spec.heightfield else (None, None))
@@ -58,7 +58,7 @@ def _run_golden(name, steps, preshift, specialized=True):
             B[b][...] = phys_at(g, t)[k].reshape(B[b].shape)
         B["global_flags"][0] = int((np.abs(phys_at(g, t)["qd"]) > 4).any())      # what the dynamics kernel leaves (CaT R4)
         B["stats"][:] = 0
-        sim.env_post_step(preshift=preshift)
+        sim.env_post_step()
         assert (sim.last_preset >= 0) == specialized, "preset selection"
         ref = out_at(g, t)
         mine = dict(B, actions_buf=B["actions"], end_q=B["dof_pos"], end_qd=B["dof_vel"])

@@ -36,8 +36,6 @@ int emu_dynamics_step(const float *tf, const int *ti, const int *mi, const float
 
 #ifdef EMU_WITH_ENV
 struct EnvArgs { TaskDev T; B200Buffers B; TerrainDev tr; EnvCall call; EnvStageTab tab; };
-struct ShiftArgs { const float *in_h; float *out_h; long long Mh; int fh; const float *in_c; float *out_c; long long Mc; int fc; };
-static void shift_body(void *p) { ShiftArgs *a = (ShiftArgs *)p; history_shift_kernel(a->in_h, a->out_h, a->Mh, a->fh, a->in_c, a->out_c, a->Mc, a->fc); }
 static int g_env_preset = -1, g_env_specialized = 1;
 static void env_body(void *p) {
     EnvArgs *a = (EnvArgs *)p;
@@ -49,30 +47,20 @@ static void env_body(void *p) {
     }
 }
 int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int rows, int cols, const float *origins, int levels, int types,
-                      const B200Buffers *bufs, long long step, float vx_lo, float vx_span, int parity, int phase_mask, int force_reset, int sit_pose, const float *beh8, int gait_cb, int gait_reset, int preshift) {
+                      const B200Buffers *bufs, long long step, float vx_lo, float vx_span, long long hist_step, int phase_mask, int force_reset, int sit_pose, const float *beh8, int gait_cb, int gait_reset) {
     static EnvArgs a;
     memcpy(a.T.f, tf, sizeof a.T.f); memcpy(a.T.i, ti, sizeof a.T.i);
     a.B = *bufs;
     a.tr.hf = rows > 0 ? hf : nullptr; a.tr.origins = origins; a.tr.rows = rows; a.tr.cols = cols; a.tr.levels = levels; a.tr.types = types;
-    a.call.step = (uint32_t)step; a.call.vx_lo = vx_lo; a.call.vx_span = vx_span; a.call.parity = parity; a.call.phase_mask = phase_mask;
+    a.call.step = (uint32_t)step; a.call.vx_lo = vx_lo; a.call.vx_span = vx_span; a.call.hist_step = (uint32_t)hist_step; a.call.phase_mask = phase_mask;
     a.call.force_reset = force_reset; a.call.sit_pose = sit_pose;
     for (int k = 0; k < 8; k++) a.call.beh[k] = beh8 ? beh8[k] : 0.f;
     a.call.gait_cb = gait_cb; a.call.gait_reset = gait_reset;
     a.tab = env_stage_table(a.T, a.B, 1);          // the emulator runs one warp per block
-    a.call.preshifted = 0;
     a.call.finalize = (!force_reset && (phase_mask & PHASE_RESET)) ? 1 : 0;      // like make_call in csrc/b200_step.cu
     a.call.stats_slot = (int)(step % ENV_STATS_RING);
     a.call.inv_episode_length_s = 1.0f / a.T.f[TF_EPISODE_LENGTH_S]; a.call.inv_num_envs = 1.0f / (float)a.T.i[TI_NUM_ENVS];
     a.call.inv_teacher = 0.f; a.call.inv_student = 1.0f / (float)a.T.i[TI_NUM_ENVS];
-    if (preshift && a.T.i[TI_OBS_KIND] >= 1 && !force_reset && (phase_mask & PHASE_OBSERVE)) {   // what b200_history_shift launches
-        static ShiftArgs sh;
-        const int p = parity & 1;
-        const long long N = a.T.i[TI_NUM_ENVS];
-        sh.in_h = a.B.obs_history[p]; sh.out_h = a.B.obs_history[p ^ 1]; sh.Mh = N * a.T.i[TI_FRAME_STACK] * a.T.i[TI_NUM_OBS]; sh.fh = a.T.i[TI_NUM_OBS];
-        sh.in_c = a.B.critic_obs[p]; sh.out_c = a.B.critic_obs[p ^ 1]; sh.Mc = N * a.T.i[TI_C_FRAME_STACK] * a.T.i[TI_SINGLE_CRITIC]; sh.fc = a.T.i[TI_SINGLE_CRITIC];
-        emu_launch(shift_body, &sh, 3, 2);          // fewer blocks than work: exercises the grid-stride loop
-        a.call.preshifted = 1;
-    }
     g_env_preset = g_env_specialized ? env_match_preset(a.T.i) : -1;
     emu_launch(env_body, &a, a.T.i[TI_NUM_ENVS]);
     return g_env_preset;

@@ -15,11 +15,6 @@ for task in (sys.argv[1:] or sorted(T.PRESETS)):
         print(f"   read  {v:6d} B  {k}")
     for k, v in w.items():
         print(f"   write {v:6d} B  {k}")
-    hr, hw = accounting.history_shift_items(spec, model)
-    for k, v in hr.items():
-        print(f"   shift read  {v:6d} B  {k}")
-    for k, v in hw.items():
-        print(f"   shift write {v:6d} B  {k}")
-    e, sh, d = accounting.env_kernel_bytes(spec, model), accounting.history_shift_bytes(spec, model), accounting.dynamics_kernel_bytes(spec, model)
-    print(f"   env kernel {e} B/env/policy-step; history shift kernel {sh} B; dynamics kernel {d} B; whole step {e + sh + d} B "
-          f"({(e + sh + d) / spec.decimation:.0f} B per env-substep)")
+    e, d = accounting.env_kernel_bytes(spec, model), accounting.dynamics_kernel_bytes(spec, model)
+    print(f"   env kernel {e} B/env/policy-step; dynamics kernel {d} B; whole step {e + d} B ({(e + d) / spec.decimation:.0f} B per env-substep); "
+          f"moving the kept frames of the stacks every step would add {accounting.shifted_stack_bytes(spec, model)} B")
