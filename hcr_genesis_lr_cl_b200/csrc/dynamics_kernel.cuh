@@ -91,7 +91,15 @@ struct TerrainDev {
 #define WS_LF (WS_FV + 128)             // link forces [17*3]
 #define WS_WARM (WS_LF + 52)            // PGS warm start [48]: 8 x (sphere id + 1, f_n, f_t1, f_t2), 8 x (aux code + 1, f)
 #define WS_PD (WS_WARM + 48)             // per chain lane [4][16]: tgt(3) kp(3) kd(3) arm+h*dmp(3) dmp(3) frictionloss(1) -- constant over the substeps,
-#define WS_TOTAL (WS_PD + 64)            // kept here rather than in 15 registers that are live across the whole substep
+                                         // kept here rather than in 15 registers that are live across the whole substep
+// The env's state between the phases of a substep.  It used to live in ~30 registers across the row assembly and the contact
+// solve, which the 72-register cap turned into local-memory spills -- and with 186 KB of stack per SM against ~36 KB of L1
+// those reloads came from L2 (ncu: 30 % hit rate, long-scoreboard 13.6 % of the warp time).  Parked here, each phase reloads
+// what it needs with broadcast LDS.128 at shared-memory latency.
+#define WS_ST (WS_PD + 64)               // [20]: p(3) mass_add | Q wxyz(4) | vb(3) mu | wb(3) - | com_shift(3) -
+#define WS_QS (WS_ST + 20)               // per chain lane [4][12]: q(3) - | qd(3) - | tau(3) -
+#define WS_TOTAL (WS_QS + 48)
+static_assert((WS_ST % 4) == 0 && (WS_QS % 4) == 0 && (WS_TOTAL % 4) == 0, "16-byte aligned vector loads");
 static_assert(WS_AUX + 32 <= WS_MI, "aliased inputs must fit under the A matrix");
 
 #define MS_BODY 0
@@ -245,18 +253,20 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     unsigned dbg_sweeps = 0, dbg_rows = 0;
 #endif
     // ---------------- load state ----------------
-    f3 p = mk3(B.base_pos[env * 3], B.base_pos[env * 3 + 1], B.base_pos[env * 3 + 2]);
-    float Qw = B.base_quat_wxyz[env * 4], Qx = B.base_quat_wxyz[env * 4 + 1], Qy = B.base_quat_wxyz[env * 4 + 2], Qz = B.base_quat_wxyz[env * 4 + 3];
-    f3 vb = mk3(B.base_lin_w[env * 3], B.base_lin_w[env * 3 + 1], B.base_lin_w[env * 3 + 2]);
-    f3 wb = mk3(B.base_ang_w[env * 3], B.base_ang_w[env * 3 + 1], B.base_ang_w[env * 3 + 2]);
-    float q[3], qd[3], tau[3];
     float *pd = ws + WS_PD + 16 * c;        // this lane's chain (lanes >= C alias the last chain and write the same values)
+    const smaddr_t st_a = sm_addr(ws + WS_ST), qs_a = sm_addr(ws + WS_QS + 12 * c);
     // the reference shifts the base mass / scales the geom friction only when the DR switch is on (set_mass_shift /
     // set_friction_ratio are called from _randomize_* alone, genesis_simulator.py:62-82,665-697); the observation-side
     // buffers start at 1 / 0 (genesis_simulator.py:648) and must not leak into the physics otherwise
-    const float mass_add = T.i[TI_RAND_MASS] ? B.added_mass[env] : 0.f, fric_ratio = T.i[TI_RAND_FRICTION] ? B.friction[env] : 1.f;
-    const f3 com_shift = mk3(B.com_bias[env * 3], B.com_bias[env * 3 + 1], B.com_bias[env * 3 + 2]);
     const float env_arm = B.joint_armature[env], env_dmp = B.joint_damping[env], env_fls = B.joint_friction[env];
+    if (lane == 0) {
+        const float mass_add = T.i[TI_RAND_MASS] ? B.added_mass[env] : 0.f, fric_ratio = T.i[TI_RAND_FRICTION] ? B.friction[env] : 1.f;
+        sts128(st_a, B.base_pos[env * 3], B.base_pos[env * 3 + 1], B.base_pos[env * 3 + 2], mass_add);
+        sts128(st_a + 16u, B.base_quat_wxyz[env * 4], B.base_quat_wxyz[env * 4 + 1], B.base_quat_wxyz[env * 4 + 2], B.base_quat_wxyz[env * 4 + 3]);
+        sts128(st_a + 32u, B.base_lin_w[env * 3], B.base_lin_w[env * 3 + 1], B.base_lin_w[env * 3 + 2], fmaxf(tf[TF_GEOM_MU] * fric_ratio, tf[TF_TERRAIN_MU]));
+        sts128(st_a + 48u, B.base_ang_w[env * 3], B.base_ang_w[env * 3 + 1], B.base_ang_w[env * 3 + 2], 0.f);
+        sts128(st_a + 64u, B.com_bias[env * 3], B.com_bias[env * 3 + 1], B.com_bias[env * 3 + 2], 0.f);
+    }
 
     for (int e = lane; e < 48; e += 32) ws[WS_WARM + e] = B.contact_warm[env * 48 + e];
     // ---------------- pre-step: action history, last_* (legged_robot.py:230-252, genesis_simulator.py:21-24) ----------------
@@ -286,7 +296,6 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const int j = 3 * c + k, o = env * A + j;
-        q[k] = B.dof_pos[o]; qd[k] = B.dof_vel[o];
         const float a = __shfl_sync(B200_FULL_MASK, a_applied, j);
         const float arm_k = T.i[TI_RAND_ARMATURE] ? env_arm : ms[MS_BODY + (1 + j) * B200_BODY_STRIDE + 19];
         const float dmp_k = T.i[TI_RAND_JDAMPING] ? env_dmp : 0.f;
@@ -294,20 +303,32 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         pd[3 + k] = B.kp_scale[o] * tf[TF_KP]; pd[6 + k] = B.kd_scale[o] * tf[TF_KD];
         pd[9 + k] = arm_k + h * dmp_k; pd[12 + k] = dmp_k;
         if (k == 0) pd[15] = T.i[TI_RAND_JFRICTION] ? env_fls : 0.f;       // frictionloss bound: one value per env
-        tau[k] = 0.f;
     }
-    float mu = tf[TF_GEOM_MU] * fric_ratio; mu = fmaxf(mu, tf[TF_TERRAIN_MU]);
-    const float kk = 1.f / (tf[TF_DMAX] * tf[TF_DMAX] * tf[TF_TC] * tf[TF_TC] * tf[TF_DAMPRATIO] * tf[TF_DAMPRATIO]);
-    const float bd = 2.f / (tf[TF_DMAX] * tf[TF_TC]);
+    if (leg) {
+        const int o = env * A + 3 * c;
+        sts128(qs_a, B.dof_pos[o], B.dof_pos[o + 1], B.dof_pos[o + 2], 0.f);
+        sts128(qs_a + 16u, B.dof_vel[o], B.dof_vel[o + 1], B.dof_vel[o + 2], 0.f);
+        sts128(qs_a + 32u, 0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
 
     int cost = 0;                    // solver work of this env in this launch (sweeps x rows, + rows built): feeds the next launches' order
     for (int sub = 0; sub <= T.i[TI_DECIMATION]; sub++) {
         const bool last_pass = sub == T.i[TI_DECIMATION];   // kinematics-only pass for the outputs
         PHASE_SYNC_A();
+        // the state this phase needs, from its parking place (live until the smooth accelerations are out)
+        float q[3], qd[3], tau[3] = {0.f, 0.f, 0.f}, Qw, Qx, Qy, Qz;
+        f3 vb, wb;
+        {
+            const float4 a4 = lds128(st_a + 16u), b4 = lds128(st_a + 32u), c4 = lds128(st_a + 48u), q4 = lds128(qs_a), v4 = lds128(qs_a + 16u);
+            Qw = a4.x; Qx = a4.y; Qy = a4.z; Qz = a4.w; vb = mk3(b4.x, b4.y, b4.z); wb = mk3(c4.x, c4.y, c4.z);
+            q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; qd[0] = v4.x; qd[1] = v4.y; qd[2] = v4.z;
+        }
         // ---------------- PD torque (genesis_simulator.py:630-642) ----------------
         if (!last_pass) {
 #pragma unroll
             for (int k = 0; k < 3; k++) tau[k] = pd[3 + k] * (pd[k] - q[k]) - pd[6 + k] * qd[k];
+            if (leg) sts128(qs_a + 32u, tau[0], tau[1], tau[2], 0.f);      // the last substep's is the reported torque
         }
         // ---------------- forward kinematics, velocities, RNE, CRBA along this lane's chain ----------------
         const m33 R0 = quat_to_mat(Qw, Qx, Qy, Qz);
@@ -488,8 +509,9 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         f3 fnb, ffb;
         {
             const float *Bd = ms + MS_BODY;
-            const f3 cm = mul(R0, mk3(Bd[6], Bd[7], Bd[8]) + com_shift);
-            SIn sb = si_body(Bd[9] + mass_add, cm, Bd + 10, R0);
+            const float4 cs4 = lds128(st_a + 64u);                              // per-env COM shift; base mass shift
+            const f3 cm = mul(R0, mk3(Bd[6] + cs4.x, Bd[7] + cs4.y, Bd[8] + cs4.z));
+            SIn sb = si_body(Bd[9] + lds32(st_a + 12u), cm, Bd + 10, R0);
             const f3 aw = mk3(0.f, 0.f, 0.f), av = cross3(vb, wb) + mk3(0.f, 0.f, tf[TF_GRAV]);
             f3 LA, PA, LV, PV;
             si_apply(sb, aw, av, LA, PA);
@@ -555,6 +577,8 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         PHASE_SYNC_C();
         // ---------------- collision detection: two spheres per lane ----------------
         float sdist[2]; f3 sn[2], sx[2]; bool act[2];
+        const float4 p4 = lds128(st_a);
+        const f3 p = mk3(p4.x, p4.y, p4.z);
 #pragma unroll
         for (int t = 0; t < 2; t++) {
             const int s = lane + 32 * t;
@@ -608,12 +632,14 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         // ---------------- aux rows: joint limits first, then frictionloss, joint order ----------------
         unsigned limmask = 0, flsmask = 0;
         float limpos[3], limsign[3];
+        const float4 qa4 = lds128(qs_a);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const float *Bd = ms + MS_BODY + (1 + 3 * c + k) * B200_BODY_STRIDE;
-            const bool lo_v = q[k] < Bd[16], hi_v = q[k] > Bd[17];
+            const float qk = k == 0 ? qa4.x : (k == 1 ? qa4.y : qa4.z);
+            const bool lo_v = qk < Bd[16], hi_v = qk > Bd[17];
             limsign[k] = lo_v ? 1.f : -1.f;
-            limpos[k] = lo_v ? q[k] - Bd[16] : Bd[17] - q[k];
+            limpos[k] = lo_v ? qk - Bd[16] : Bd[17] - qk;
             const unsigned bl = __ballot_sync(B200_FULL_MASK, leg && (lo_v || hi_v));
             const unsigned bf = __ballot_sync(B200_FULL_MASK, leg && pd[15] > 0.f);
 #pragma unroll
@@ -781,6 +807,8 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         ws[WS_FV + lane * 4] = lane < R ? f : 0.f;
         __syncwarp();
         if (lane < R) {
+            const float kk = 1.f / (tf[TF_DMAX] * tf[TF_DMAX] * tf[TF_TC] * tf[TF_TC] * tf[TF_DAMPRATIO] * tf[TF_DAMPRATIO]);
+            const float bd = 2.f / (tf[TF_DMAX] * tf[TF_TC]);
             const float aref = -bd * vel - kk * imp * rpos;
             Rr = __fdividef(1.f - imp, imp) * Arr;
             idd = __fdividef(1.f, Arr + Rr);
@@ -804,6 +832,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         const bool clamp0 = (kind == 0 || kind == 3);
         const float fhi = kind == 4 ? bound : 3.0e38f, flo = clamp0 ? 0.f : -fhi;
         const float c1n = -(Rr * idd), iddn = -idd;
+        const float mu = lds32(st_a + 44u);               // max(terrain mu, geom mu x friction ratio) of this env
         float *blk = ws + WS_JR;                          // per contact 16 floats: b00 b01 b02 b11 | b12 b22 - - | f0 f1 f2 - | f0 f1 f2 -
                                                           // (the forces twice: sweep k reads copy k & 1 and writes the other, so no lane can
                                                           // read a force its first lane has already replaced)
@@ -922,25 +951,35 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                 ws[WS_LF + 3 * __float_as_int(fv[3]) + lane] += fv[lane] + fv[4 + lane] + fv[8 + lane];
             }
         }
-        // semi-implicit Euler
-        vb = vb + mk3(accb[0], accb[1], accb[2]) * h;
-        wb = wb + mk3(accb[3], accb[4], accb[5]) * h;
-        p = p + vb * h;
-#pragma unroll
-        for (int k = 0; k < 3; k++) { qd[k] += h * accl[k]; q[k] += h * qd[k]; }
+        // semi-implicit Euler on the parked state: reload, advance, park again
         {
-            const float wn = sqrtf(dot3(wb, wb));
+            const float4 p4i = lds128(st_a), a4 = lds128(st_a + 16u), b4 = lds128(st_a + 32u), c4 = lds128(st_a + 48u), q4 = lds128(qs_a), v4 = lds128(qs_a + 16u);
+            const f3 vn = mk3(b4.x, b4.y, b4.z) + mk3(accb[0], accb[1], accb[2]) * h;
+            const f3 wn3 = mk3(c4.x, c4.y, c4.z) + mk3(accb[3], accb[4], accb[5]) * h;
+            const f3 pn = mk3(p4i.x, p4i.y, p4i.z) + vn * h;
+            const float qd0 = v4.x + h * accl[0], qd1 = v4.y + h * accl[1], qd2 = v4.z + h * accl[2];
+            const float wn = sqrtf(dot3(wn3, wn3));
             float dw = 1.f, dx = 0.f, dy = 0.f, dz = 0.f;
             if (wn > 1e-12f) {
                 float sn2, cs2; fast_sincosf(0.5f * wn * h, &sn2, &cs2);
-                const float s = __fdividef(sn2, wn); dw = cs2; dx = wb.x * s; dy = wb.y * s; dz = wb.z * s;
+                const float s2 = __fdividef(sn2, wn); dw = cs2; dx = wn3.x * s2; dy = wn3.y * s2; dz = wn3.z * s2;
             }
-            const float nw = dw * Qw - dx * Qx - dy * Qy - dz * Qz;
-            const float nx = dw * Qx + dx * Qw + dy * Qz - dz * Qy;
-            const float ny = dw * Qy - dx * Qz + dy * Qw + dz * Qx;
-            const float nz = dw * Qz + dx * Qy - dy * Qx + dz * Qw;
+            const float nw = dw * a4.x - dx * a4.y - dy * a4.z - dz * a4.w;
+            const float nx = dw * a4.y + dx * a4.x + dy * a4.w - dz * a4.z;
+            const float ny = dw * a4.z - dx * a4.w + dy * a4.x + dz * a4.y;
+            const float nz = dw * a4.w + dx * a4.z - dy * a4.y + dz * a4.x;
             const float inv = rsqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
-            Qw = nw * inv; Qx = nx * inv; Qy = ny * inv; Qz = nz * inv;
+            __syncwarp();                                  // every lane has read the old state
+            if (lane == 0) {
+                sts128(st_a, pn.x, pn.y, pn.z, p4i.w);
+                sts128(st_a + 16u, nw * inv, nx * inv, ny * inv, nz * inv);
+                sts128(st_a + 32u, vn.x, vn.y, vn.z, b4.w);
+                sts128(st_a + 48u, wn3.x, wn3.y, wn3.z, 0.f);
+            }
+            if (leg) {
+                sts128(qs_a, q4.x + h * qd0, q4.y + h * qd1, q4.z + h * qd2, 0.f);
+                sts128(qs_a + 16u, qd0, qd1, qd2, 0.f);
+            }
         }
         __syncwarp();
     }
@@ -953,19 +992,21 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     }
 #endif
     if (cost_out && lane == 0) *cost_out = cost;
-    // ---------------- write back (frames/velocities of the final state are in shared memory) ----------------
+    // ---------------- write back (state, frames and velocities of the final state are in shared memory) ----------------
+    const float4 pf4 = lds128(st_a), qf4 = lds128(qs_a), vf4 = lds128(qs_a + 16u), tf4 = lds128(qs_a + 32u);
+    const f3 p = mk3(pf4.x, pf4.y, pf4.z);
+    const float qd[3] = {vf4.x, vf4.y, vf4.z};
     if (lane < 3) {
-        B.base_pos[env * 3 + lane] = comp3(p, lane);
-        B.base_lin_w[env * 3 + lane] = comp3(vb, lane);
-        B.base_ang_w[env * 3 + lane] = comp3(wb, lane);
+        B.base_pos[env * 3 + lane] = ws[WS_ST + lane];
+        B.base_lin_w[env * 3 + lane] = ws[WS_ST + 8 + lane];
+        B.base_ang_w[env * 3 + lane] = ws[WS_ST + 12 + lane];
     }
-    if (lane < 4) B.base_quat_wxyz[env * 4 + lane] = lane == 0 ? Qw : (lane == 1 ? Qx : (lane == 2 ? Qy : Qz));
+    if (lane < 4) B.base_quat_wxyz[env * 4 + lane] = ws[WS_ST + 4 + lane];
     if (leg) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int o = env * A + 3 * c + k;
-            B.dof_pos[o] = q[k]; B.dof_vel[o] = qd[k]; B.torques[o] = tau[k];
-        }
+        const int o = env * A + 3 * c;
+        B.dof_pos[o] = qf4.x; B.dof_pos[o + 1] = qf4.y; B.dof_pos[o + 2] = qf4.z;
+        B.dof_vel[o] = vf4.x; B.dof_vel[o + 1] = vf4.y; B.dof_vel[o + 2] = vf4.z;
+        B.torques[o] = tf4.x; B.torques[o + 1] = tf4.y; B.torques[o + 2] = tf4.z;
     }
     if (T.i[TI_CAT]) {   // CaT stand-still constraint couples all envs as shipped (go2_cat.py:177-178)
         const bool fast = leg && (fabsf(qd[0]) > 4.0f || fabsf(qd[1]) > 4.0f || fabsf(qd[2]) > 4.0f);

@@ -31,7 +31,7 @@ def main():
     tot_i = sum(v[1] for v in agg.values()) or 1
     src = open(src_path).read().split("\n")
     base = os.path.basename(src_path)
-    marks = [(i + 1, re.sub(r"[-/ ]+$", "", ln.strip().lstrip("/ -")).strip()[:48]) for i, ln in enumerate(src) if re.match(r"\s*// -{8,} ", ln) or re.match(r"\s*// ={8,} ", ln)]
+    marks = [(i + 1, re.sub(r"[-=/ ]+$", "", ln.strip().lstrip("/ -=")).strip()[:48]) for i, ln in enumerate(src) if re.match(r"\s*// [-=]{8,} ", ln)]
     marks = [(1, "(file head / helpers)")] + marks + [(len(src) + 1, "end")]
     ph = {}
     other = [0, 0]
