@@ -145,7 +145,7 @@ int b200_bind_buffers(B200Handle *h, const B200Buffers *b) {
     const size_t n = sizeof(B200Buffers) / sizeof(void *);
     for (size_t k = 0; k < n; k++) {
         const bool optional = (&p[k] == (const void *const *)&b->height_cells) || (&p[k] == (const void *const *)&b->dyn_cost) ||
-                              (&p[k] == (const void *const *)&b->dyn_order);
+                              (&p[k] == (const void *const *)&b->dyn_order) || (&p[k] == (const void *const *)&b->nonfinite);
         if (!p[k] && !optional) return fail("b200_bind_buffers: null buffer pointer");
     }
     h->bufs = *b; h->bound = true;
@@ -165,7 +165,7 @@ static int launch_dynamics(B200Handle *h, const float *actions, void *stream, in
     const int N = h->task.i[TI_NUM_ENVS];
     const dim3 grid((N + DYN_WARPS_PER_BLOCK - 1) / DYN_WARPS_PER_BLOCK), block(DYN_WARPS_PER_BLOCK * 32);
     cudaStream_t s = (cudaStream_t)stream;
-    if (h->task.i[TI_CAT]) CK(cudaMemsetAsync(h->bufs.global_flags, 0, 4 * sizeof(int32_t), s));
+    if (h->task.i[TI_CAT]) CK(cudaMemsetAsync(h->bufs.global_flags, 0, sizeof(int32_t), s));      // [0] only: [1] ticket, [2] cumulative counter
     // the env -> warp-slot order of the NEXT dynamics launch, from the cost of the PREVIOUS one (the launch enqueued below
     // reads / writes the other halves of dyn_order / dyn_cost): a one-CTA sort on the side stream, under this launch
     const bool ordered = h->order_enabled && h->bufs.dyn_order && h->bufs.dyn_cost;

@@ -66,9 +66,10 @@ __device__ __forceinline__ float lead_sum(float v) {
 // so one integer REDUX does it (SASS REDUX.MAX.U32) instead of five shuffle + max rounds.
 __device__ __forceinline__ float warp_max_nonneg(float v) {
 #ifdef B200_WARP_EMU
+    unsigned u = (unsigned)__float_as_int(v);       // the same integer max on the bit patterns as REDUX (NaN patterns included: warp-uniform)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(B200_FULL_MASK, v, o));
-    return v;
+    for (int o = 16; o > 0; o >>= 1) { const unsigned w = __shfl_xor_sync(B200_FULL_MASK, u, o); u = w > u ? w : u; }
+    return __int_as_float((int)u);
 #else
     return __uint_as_float(__reduce_max_sync(B200_FULL_MASK, __float_as_uint(v)));
 #endif

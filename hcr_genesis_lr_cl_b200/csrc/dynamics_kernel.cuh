@@ -996,6 +996,20 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     const float4 pf4 = lds128(st_a), qf4 = lds128(qs_a), vf4 = lds128(qs_a + 16u), tf4 = lds128(qs_a + 32u);
     const f3 p = mk3(pf4.x, pf4.y, pf4.z);
     const float qd[3] = {vf4.x, vf4.y, vf4.z};
+    // failure containment (no reference counterpart): a state that left the finite range is NOT written
+    // back -- the env keeps the pose it entered the step with, at rest, and is flagged for the env kernel to reset
+    bool finite_l = true;
+    if (lane < 13) finite_l = isfinite(ws[WS_ST + lane + (lane >= 3) + (lane >= 10)]);   // p | Q | vb | wb (the 4th words are parameters)
+    if (leg) finite_l = finite_l && isfinite(qf4.x + qf4.y + qf4.z + vf4.x + vf4.y + vf4.z);
+    if (__ballot_sync(B200_FULL_MASK, !finite_l) != 0u) {
+        if (lane < 3) { B.base_lin_w[env * 3 + lane] = 0.f; B.base_ang_w[env * 3 + lane] = 0.f; }
+        if (lane < A) { B.dof_vel[env * A + lane] = 0.f; B.torques[env * A + lane] = 0.f; B.last_dof_vel[env * A + lane] = 0.f; }
+        if (lane < 3 * T.i[TI_F]) { B.feet_vel[env * 3 * T.i[TI_F] + lane] = 0.f; B.last_feet_vel[env * 3 * T.i[TI_F] + lane] = 0.f; }
+        for (int e = lane; e < 3 * L; e += 32) B.link_contact_forces[env * 3 * L + e] = 0.f;
+        for (int e = lane; e < 48; e += 32) B.contact_warm[env * 48 + e] = 0.f;
+        if (lane == 0 && B.nonfinite) B.nonfinite[env] = 1;
+        return;
+    }
     if (lane < 3) {
         B.base_pos[env * 3 + lane] = ws[WS_ST + lane];
         B.base_lin_w[env * 3 + lane] = ws[WS_ST + 8 + lane];

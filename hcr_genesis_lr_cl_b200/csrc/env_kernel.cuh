@@ -392,6 +392,12 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         fail_cnt += fail ? 1 : 0;
         time_out = ep_len > ti[TI_MAX_EPISODE_LENGTH];
         reset = ((float)fail_cnt > tf[TF_FAIL_LIMIT]) || time_out;
+        const bool refused = B.nonfinite != nullptr && B.nonfinite[env] != 0;
+        __syncwarp();                                            // every lane has read the flag before lane 0 clears it
+        if (refused) {                                           // the dynamics kernel refused a non-finite state: reset now (a failure, not a time-out)
+            reset = true;
+            if (lane == 0) { B.nonfinite[env] = 0; atomicAdd(B.global_flags + 2, 1); }
+        }
     }
     if (call.force_reset) reset = true;
 

@@ -566,6 +566,17 @@ class B200Simulator:
         return self._lib.b200_env_kernel_variant(self._handle).decode()
 
     @property
+    def nonfinite_envs(self) -> torch.Tensor:
+        """[N] int32, 1 where the dynamics kernel refused to write back a non-finite state (the env kept its last finite pose,
+        at rest).  The fused env kernel resets such envs itself; in plugin mode the task can read this flag (and clear it)."""
+        return self._buf["nonfinite"]
+
+    @property
+    def nonfinite_resets(self) -> int:
+        """How many envs the fused env kernel has reset because their state went non-finite (cumulative; syncs)."""
+        return int(self._buf["global_flags"][2])
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.b200_launch_count(self._handle))
 

@@ -238,7 +238,8 @@ typedef struct B200Buffers {
     float *gait_state;          /* [N,20] theta[4], gait_time, phi, gait_period, base_height_target, foot_clearance_target,
                                    pitch_target, clock_input[8] = sin[F], cos[F] (periodic-gait tasks) */
     float *cstr_prob;           /* [N] CaT termination probability (Go2CaT.cstr_prob); unused (but bound) for other tasks */
-    int32_t *global_flags;      /* [4] int32: [0] any env with |dof_vel| > 4 after the physics step (CaT stand-still, R4) */
+    int32_t *global_flags;      /* [4] int32: [0] any env with |dof_vel| > 4 after the physics step (CaT stand-still, R4); [1] ticket of the
+                                   env kernel's last-CTA finalize; [2] envs reset because their state went non-finite (cumulative) */
     float *contact_warm;        /* [N,48] contact-solver warm start carried between substeps and policy steps: 8 x (sphere id + 1,
                                    f_n, f_t1, f_t2) then 8 x (aux-row code + 1, f); zero = empty */
     float *next_state_buf;      /* [N,num_obs] go2_dreamwaq decoder target (go2_dreamwaq.py:72-80); [N,1] otherwise */
@@ -248,6 +249,11 @@ typedef struct B200Buffers {
      * last two launches and the env each warp slot takes in the next ones */
     int32_t *dyn_cost;          /* [2,N] solver work (sweeps x rows) of each env in the launches of either parity */
     int32_t *dyn_order;         /* [2,N] warp slot w runs env w + dyn_order[parity][w] (delta-encoded permutation: zeros = identity) */
+    /* failure containment (no reference counterpart: the reference never checks): an env whose state left
+     * the finite range inside the dynamics kernel keeps its last finite pose with zero velocities, is flagged here, and the
+     * next b200_env_post_step that runs PHASE_TERMINATION resets it (counted in global_flags[2]); in plugin mode the flag is
+     * exposed as B200Simulator.nonfinite_envs for the task to act on */
+    int32_t *nonfinite;         /* [N] int32 */
 } B200Buffers;
 
 typedef struct B200Handle B200Handle;

@@ -685,3 +685,33 @@ def test_dynamics_kernel_drives_joints_with_the_delayed_action():
     for k, name in (("q", "dof_pos"), ("qd", "dof_vel"), ("torques", "torques"), ("base_pos", "base_pos")):
         r = np.asarray(ref[k], np.float64)
         assert np.abs(out[name].reshape(r.shape) - r).max() < 1e-4 * max(1.0, np.abs(r).max()), k
+
+
+def test_nonfinite_state_is_contained_and_reset():
+    """Failure containment (no reference counterpart): an env whose state goes non-finite inside the dynamics
+    kernel is not written back -- it keeps its pose, at rest, is flagged, and the env kernel resets it; the other envs of the
+    batch (same CTA included) are bit-identical to a run without the fault."""
+    from hcr_genesis_lr_cl_b200 import task_spec as T
+    spec = T.go2_ts_spec()
+    terrain = load_terrain(spec)
+    N = 64
+    env, ref = _env(spec, N, terrain), _env(spec, N, terrain)
+    for e in (env, ref):
+        e.reset()
+        e.step(torch.zeros(N, 12, device="cuda"))
+    b = env.simulator._buf
+    bad = [5, 33]
+    b["dof_vel"][5, 7] = float("nan")
+    b["base_lin_w"][33, 0] = float("inf")
+    a = 0.3 * torch.ones(N, 12, device="cuda")
+    env.step(a)
+    ref.step(a)
+    ok = [i for i in range(N) if i not in bad]
+    assert env.simulator.nonfinite_resets == 2 and bool(env.reset_buf[bad].all())
+    for k in ("base_pos", "base_quat_wxyz", "dof_pos", "dof_vel", "base_lin_w", "obs_buf", "rew_buf", "privileged_obs_buf"):
+        assert torch.isfinite(b[k]).all(), k
+        assert torch.equal(b[k][ok], ref.simulator._buf[k][ok]), k
+    assert int(b["nonfinite"].sum()) == 0 and int(b["episode_length"][bad].sum()) == 0
+    for _ in range(3):
+        env.step(a)
+    assert torch.isfinite(b["obs_buf"]).all() and torch.isfinite(env.obs_history).all() and env.simulator.nonfinite_resets == 2

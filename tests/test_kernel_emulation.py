@@ -179,3 +179,33 @@ def test_emulated_simulator_step_skips_the_pre_step_bookkeeping():
     for k in ("actions", "last_actions", "llast_actions"):
         assert np.array_equal(only[k], b1[k]), k
     assert not np.array_equal(full["actions"], b0["actions"])
+
+
+def test_emulated_nonfinite_state_is_contained_and_reset():
+    """An env whose state goes non-finite inside the dynamics kernel (here: a NaN joint velocity on entry) is not written
+    back: it keeps its pose, at rest, is flagged, and the env kernel resets it -- its neighbours are untouched."""
+    import torch
+    from emu_backend import EmuFusedLeggedEnv
+    from hcr_genesis_lr_cl_b200 import task_spec as T
+    hs, origins = load_terrain()
+    spec = T.go2_ts_spec()
+    N = 4
+    env = EmuFusedLeggedEnv(spec, N, "cpu", terrain=(hs, origins))
+    ref = EmuFusedLeggedEnv(spec, N, "cpu", terrain=(hs, origins))
+    for e in (env, ref):
+        e.reset()
+        e.step(torch.zeros(N, 12))
+    b = env.simulator._buf
+    pose = b["base_pos"][2].clone()
+    b["dof_vel"][2, 5] = float("nan")
+    a = 0.3 * torch.ones(N, 12)
+    env.step(a)
+    ref.step(a)
+    assert int(b["global_flags"][2]) == 1 and bool(env.reset_buf[2]) and not bool(env.reset_buf[0])
+    for k in ("base_pos", "dof_pos", "dof_vel", "base_lin_w", "obs_buf", "rew_buf"):
+        assert torch.isfinite(b[k]).all(), k
+        assert torch.equal(b[k][[0, 1, 3]], ref.simulator._buf[k][[0, 1, 3]]), k          # the other envs never noticed
+    assert int(b["nonfinite"].sum()) == 0 and int(b["episode_length"][2]) == 0              # flag consumed, episode restarted
+    assert not torch.equal(b["base_pos"][2], pose)                                          # re-placed by reset_idx
+    env.step(a)
+    assert torch.isfinite(b["obs_buf"]).all() and int(b["global_flags"][2]) == 1

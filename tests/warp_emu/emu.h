@@ -40,6 +40,7 @@ static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu_exchan
 static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return emu_exchange(v, src & 31); }
 static inline float __shfl_xor_sync(unsigned, float v, int m) { return emu_float(emu_exchange(emu_bits(v), emu_cur_lane ^ m)); }
 static inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)emu_exchange((uint32_t)v, emu_cur_lane ^ m); }
+static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int m) { return emu_exchange(v, emu_cur_lane ^ m); }
 static inline float __shfl_down_sync(unsigned, float v, int d) { return emu_float(emu_exchange(emu_bits(v), emu_cur_lane + d < 32 ? emu_cur_lane + d : emu_cur_lane)); }
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
