@@ -194,6 +194,13 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     si("TI_CAT", spec.cat_enabled); si("TI_CAT_GLOBAL_STANDSTILL", spec.cat_stand_still_global)
     si("TI_DOUBLE_SHIFT", spec.double_shift_actions); si("TI_N_SUMS", len(spec.episode_sum_names()))
     si("TI_GAIT", spec.gait_enabled); si("TI_CLEARANCE_MODE", spec.foot_clearance_mode)
+    si("TI_R18", spec.gait_enabled and spec.reproduce_r18)
+    if spec.gait_enabled and spec.gait_smooth:
+        p_terms, tab = spec.von_mises_series()
+        if p_terms > H["B200_VM_MAX"]:
+            raise ValueError("von Mises series longer than B200_VM_MAX")
+        si("TI_VM_TERMS", p_terms)
+        f[H["TF_VM_R"]:H["TF_VM_R"] + len(tab)] = tab
     si("TI_NUM_TEACHER", spec.num_teacher)
     if spec.randomize_ctrl_delay:
         lo, hi = (int(v) for v in spec.ctrl_delay_step_range)

@@ -165,7 +165,7 @@ static int launch_dynamics(B200Handle *h, const float *actions, void *stream, in
     const int N = h->task.i[TI_NUM_ENVS];
     const dim3 grid((N + DYN_WARPS_PER_BLOCK - 1) / DYN_WARPS_PER_BLOCK), block(DYN_WARPS_PER_BLOCK * 32);
     cudaStream_t s = (cudaStream_t)stream;
-    if (h->task.i[TI_CAT]) CK(cudaMemsetAsync(h->bufs.global_flags, 0, sizeof(int32_t), s));      // [0] only: [1] ticket, [2] cumulative counter
+    if (h->task.i[TI_CAT] || h->task.i[TI_R18]) CK(cudaMemsetAsync(h->bufs.global_flags, 0, sizeof(int32_t), s));      // [0] only: [1] ticket, [2] cumulative counter
     // the env -> warp-slot order of the NEXT dynamics launch, from the cost of the PREVIOUS one (the launch enqueued below
     // reads / writes the other halves of dyn_order / dyn_cost): a one-CTA sort on the side stream, under this launch
     const bool ordered = h->order_enabled && h->bufs.dyn_order && h->bufs.dyn_cost;
@@ -246,6 +246,11 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, long 
     h->stats_zeroed = false;
     EnvCall call = make_call(h, step, lo, span, hist_step, mask, force);
     if (h->side_pending) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->side_pending = false; }      // join the side stream
+    if (h->task.i[TI_R18] && (mask & PHASE_REWARD) && !force) {      // bug-compatible mode only: the "any env" bits row 0 follows (R18)
+        B200_LAUNCH(r18_flags_kernel, dim3((N + R18_FLAGS_BLOCK - 1) / R18_FLAGS_BLOCK), R18_FLAGS_BLOCK, 0, s, h->task, h->bufs, call);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
     const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
     B200_LAUNCH(env_kernel_fn(h->env_preset), grid, block, h->env_smem, s, h->task, h->bufs, h->terrain, call, h->stage);
     h->launches++;

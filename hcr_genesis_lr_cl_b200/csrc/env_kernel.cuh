@@ -101,6 +101,26 @@ __device__ __forceinline__ int cell_of(float p, float border, float hscale) {
 
 __device__ __forceinline__ int wrap_idx(int i, int n) { return i < 0 ? i + n : i; }   // torch negative-index wrap
 
+// scipy.stats.vonmises.cdf(x, kappa, loc) for kappa < 50, x - loc given: scipy's series (scipy/stats/_stats.pyx von_mises_cdf:
+// shift x into one period, backward recursion over p - 1 terms, clip to [0, 1], add the period count back).  `tab` holds the
+// kappa-only part of the recursion as pairs (R_n, R_n / n), n = p-1 .. 1 (TaskSpec.von_mises_series).  The reference evaluates
+// this on the host in float64 (go2_wtw.py:423-429); fp32 here, ~1e-6 absolute.
+__device__ __forceinline__ float von_mises_cdf(const float *tab, int p, float x) {
+    const float ix = rintf(x * 0.15915494309189535f);
+    x = fmaf(-ix, 6.2831853071795862f, x);
+    float s, c, sn, cn;
+    sincosf(x, &s, &c);
+    sincosf((float)p * x, &sn, &cn);
+    float V = 0.f;
+    for (int n = 0; n < p - 1; n++) {
+        const float sn2 = sn * c - cn * s;
+        cn = cn * c + sn * s; sn = sn2;
+        V = fmaf(tab[2 * n + 1], sn, tab[2 * n] * V);
+    }
+    const float F = fminf(fmaxf(0.5f + x * 0.15915494309189535f + V * 0.31830988618379069f, 0.f), 1.f);
+    return F + ix;
+}
+
 // Frame stacks (obs_history: K = frame_stack frames of num_obs floats; critic stack: c_frame_stack frames) live in HBM as
 // DOUBLE-WRITTEN RINGS: a row holds 2K frame slots and the frame of observation step t is stored twice, in slot t mod K
 // and in slot t mod K + K.  The K most recent frames, oldest first -- exactly the tensor the reference re-concatenates
@@ -224,6 +244,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     }
     // periodic-gait state (tron1_pf_ee.py:186-197): theta_left/right, gait time, phase
     float th0 = 0.f, th1 = 0.f, th2 = 0.f, th3 = 0.f, gtime = 0.f, gphi = 0.f, gper = tf[TF_GAIT_PERIOD], bh_t = 0.f, fc_t = 0.f, pt_t = 0.f, expc_frc = 0.f;
+    const bool r18_env0 = ti[TI_R18] && (env + ti[TI_ENV_OFFSET]) == 0;
+    const int r18_flags = r18_env0 ? (B.global_flags[0] >> 8) : 0;
     if (ti[TI_GAIT]) {
         const float *gs = R.gait_state + row * B200_GAIT_STATE;
         th0 = gs[B200_GS_TH]; th1 = gs[B200_GS_TH + 1]; th2 = gs[B200_GS_TH + 2]; th3 = gs[B200_GS_TH + 3]; gtime = gs[B200_GS_GT]; gphi = gs[B200_GS_PHI];
@@ -253,6 +275,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     float hmean = 0.f, hmax = 0.f;   // mean / max of the 9 terrain heights around this lane's foot
 
     if (pm & PHASE_CALLBACK) ep_len += 1;                       // legged_robot.py:60
+    __syncwarp();            // every lane holds its copy of the state read above before any lane overwrites it (OOB teleport, resets)
 
     // ================================================================== GenesisSimulator.post_physics_step
     if (pm & PHASE_SIM_POST) {
@@ -432,7 +455,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
         const bool c_dofpos = below && above;                                 // product of two any() as written (go2_cat.py:168-169)
         const bool c_orient = grav.z > tf[TF_CAT_MAX_PROJ_GRAV];
         const bool fast_here = __ballot_sync(B200_FULL_MASK, jl && fabsf(qdj) > 4.0f) != 0u;
-        const bool fast = ti[TI_CAT_GLOBAL_STANDSTILL] ? (B.global_flags[0] != 0) : fast_here;
+        const bool fast = ti[TI_CAT_GLOBAL_STANDSTILL] ? ((B.global_flags[0] & 1) != 0) : fast_here;
         const bool c_still = (norm3_rn(cmd0, cmd1, cmd2) < 0.1f) && fast;
         const float sp = tf[TF_CAT_SOFT_P];
         const bool cv[9] = {c_torque, c_dofvel, c_arate, c_height, c_coll, c_stumble, c_dofpos, c_orient, c_still};
@@ -476,8 +499,28 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                     const float thl = lane == 0 ? th0 : (lane == 1 ? th1 : (lane == 2 ? th2 : th3));
                     const float ph = __fmul_rn(fmodf(__fadd_rn(gphi, thl), 1.0f), 6.2831853071795862f);
                     const bool swing = ph >= 0.f && ph < tf[TF_GAIT_B_SWING], stance = ph >= tf[TF_GAIT_B_SWING] && ph < 6.2831853071795862f;
-                    expc_frc = swing ? -1.f : 0.f;
-                    term = __fadd_rn(__fmul_rn(stance ? -1.f : 0.f, q_spd), __fmul_rn(expc_frc, q_frc));
+                    float expc_spd;
+                    if (ti[TI_VM_TERMS] > 0) {                    // "smooth" indicator (go2_wtw.py:415-453, tron1_pf_ee.py:369-407)
+                        const float *vm = tf + TF_VM_R;
+                        const int pv = ti[TI_VM_TERMS];
+                        const float FA = fminf(fmaxf(von_mises_cdf(vm, pv, ph), 0.f), 1.f);                                   // loc = a_swing = 0
+                        const float FB = fminf(fmaxf(von_mises_cdf(vm, pv, ph - tf[TF_GAIT_B_SWING]), 0.f), 1.f);              // loc = b_swing
+                        const float FS = fminf(fmaxf(von_mises_cdf(vm, pv, ph - 6.2831853071795862f), 0.f), 1.f);              // loc = b_stance = 2 pi
+                        const float sw_ind = FA * (1.f - FB), st_ind = FB * (1.f - FS);
+                        // outside the swing window: C_spd = -stance, C_frc = -1 + stance; inside: C_frc = -swing, C_spd = -1 + swing
+                        const bool in_sw = swing || (r18_env0 && (r18_flags & (2 << lane)));      // R18: row 0 joins the swing set of any env
+                        expc_spd = in_sw ? -1.f + sw_ind : -st_ind;
+                        expc_frc = in_sw ? -sw_ind : -1.f + st_ind;
+                        if (tf[TF_GAIT_B_SWING] == 0.f) { expc_frc = 0.f; expc_spd = -1.f; }                                  // standing gait
+                    } else {
+                        expc_frc = swing ? -1.f : 0.f;
+                        expc_spd = stance ? -1.f : 0.f;
+                        if (r18_env0) {                           // R18: row 0 rides along with "any env in swing", then "any env in stance"
+                            if (r18_flags & (2 << lane)) { expc_frc = -1.f; expc_spd = 0.f; }
+                            if (r18_flags & (32 << lane)) { expc_frc = 0.f; expc_spd = -1.f; }
+                        }
+                    }
+                    term = __fadd_rn(__fmul_rn(expc_spd, q_spd), __fmul_rn(expc_frc, q_frc));
                 }
                 r = expf(warp_sum(term)); break; }
             case RW_COLLISION: {
@@ -575,6 +618,7 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
     if (ti[TI_GAIT] && (pm & PHASE_REWARD)) {                    // tron1_pf_ee.py:27-35: advance the gait clock after the reward
         gtime = __fadd_rn(gtime, dt);
         if (gtime >= __fsub_rn(gper, __fmul_rn(dt, 0.5f))) gtime = 0.f;
+        if (r18_env0 && (r18_flags & 1)) gtime = 0.f;           // R18: row 0 is zeroed whenever any env wraps
         gphi = __fdiv_rn(gtime, gper);
     }
     ENV_SECTION_SYNC();
@@ -918,6 +962,44 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             B.last_dof_vel[env * A + lane] = qdj;
         }
         if (fl) { float *lv = B.last_feet_vel + (env * F + lane) * 3; lv[0] = fvel.x; lv[1] = fvel.y; lv[2] = fvel.z; }
+    }
+}
+
+// Bug-compatible mode only (TaskSpec.reproduce_r18; never on the default path): the reference indexes per-env
+// gait tensors with the flattened nonzero() of [N,1] masks, so row 0 follows "any env" for the gait-clock wrap and for the
+// swing / stance indicator of each foot.  One thread per env evaluates exactly what env_post_step_warp is about to use --
+// the gait state after this step's behaviour resampling in the callback (go2_wtw.py:258-263) -- and ORs the bits into
+// global_flags[0] (bit 8: wrap, 9..12: swing per foot, 13..16: stance per foot); launched right before the env kernel.
+#ifdef B200_WARP_EMU
+#define R18_FLAGS_BLOCK 32          // the test emulator runs one warp per block
+#else
+#define R18_FLAGS_BLOCK 128
+#endif
+__global__ void r18_flags_kernel(const TaskDev T, const B200Buffers B, const EnvCall call) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    int bits = 0;
+    if (env < T.i[TI_NUM_ENVS]) {
+        const float *tf = T.f;
+        const float *gs = B.gait_state + (size_t)env * B200_GAIT_STATE;
+        float th[4] = {gs[B200_GS_TH], gs[B200_GS_TH + 1], gs[B200_GS_TH + 2], gs[B200_GS_TH + 3]};
+        float gper = T.i[TI_BEHAVIOR] ? gs[B200_GS_PER] : tf[TF_GAIT_PERIOD];
+        const float dt = tf[TF_POLICY_DT];
+        if (T.i[TI_BEHAVIOR] && (call.phase_mask & PHASE_CALLBACK) && (B.episode_length[env] + 1) % T.i[TI_BEHAVIOR_INTERVAL] == 0) {
+            EnvRng rng; rng.k0 = (uint32_t)T.i[TI_SEED_LO]; rng.k1 = (uint32_t)T.i[TI_SEED_HI]; rng.env = (uint32_t)(env + T.i[TI_ENV_OFFSET]); rng.step = call.step;
+            gper = rand_range(call.beh[0], call.beh[1], rng.u(SITE_BEHAVIOR, 0));
+            for (int k = 0; k < 4; k++) th[k] = tf[TF_GAIT_THETA + call.gait_cb * B200_MAX_FEET + k];
+        }
+        if (__fadd_rn(gs[B200_GS_GT], dt) >= __fsub_rn(gper, __fmul_rn(dt, 0.5f))) bits |= 1;
+        for (int f = 0; f < T.i[TI_F]; f++) {
+            const float ph = __fmul_rn(fmodf(__fadd_rn(gs[B200_GS_PHI], th[f]), 1.0f), 6.2831853071795862f);
+            if (ph >= 0.f && ph < tf[TF_GAIT_B_SWING]) bits |= 2 << f;
+            if (ph >= tf[TF_GAIT_B_SWING] && ph < 6.2831853071795862f) bits |= 32 << f;
+        }
+    }
+    const unsigned any = __ballot_sync(B200_FULL_MASK, bits != 0);
+    if (any) {                                                  // OR over the warp (bug-compat path: clarity over speed)
+        for (int o = 16; o > 0; o >>= 1) bits |= __shfl_xor_sync(B200_FULL_MASK, bits, o);
+        if ((threadIdx.x & 31) == 0) atomicOr(B.global_flags, bits << 8);
     }
 }
 

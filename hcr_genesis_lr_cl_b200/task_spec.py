@@ -190,6 +190,9 @@ class TaskSpec:
     gait_theta_left: float = 0.0
     gait_theta_right: float = 0.5
     gait_b_swing: float = 0.5
+    reproduce_r18: bool = False             # bug-compatible env-0 coupling of the periodic-gait tasks; default: per-env semantics
+    gait_smooth: bool = False               # gait_function_type "smooth": von Mises CDF indicator (go2_wtw.py:415-453) instead of "step"
+    gait_kappa: float = 20.0                # concentration of the von Mises transitions (go2_wtw_config.py:59, tron1_pf_ee_config.py:130)
     base_height_tracking_sigma: float = 0.01
     foot_clearance_mode: int = 0            # height under the foot: 0 none, 1 mean of the 9 samples, 2 max
     sit_init_percent: float = 0.0
@@ -275,6 +278,21 @@ class TaskSpec:
     def scaled_reward(self, name: str) -> np.float32:
         """scale * dt, rounded to fp32 where torch multiplies a python scalar into an fp32 tensor."""
         return np.float32(self.reward_scales.get(name, 0.0) * self.dt)
+
+    def von_mises_series(self):
+        """(p, table) of scipy's von Mises CDF series for `gait_kappa` (scipy/stats/_stats.pyx von_mises_cdf, the function
+        behind scipy.stats.vonmises.cdf that go2_wtw.py:423-429 calls): p = int(1 + 28 + 0.5 k - 100 / (k + 5)) terms and,
+        for n = p-1 .. 1, R_n = 1 / (2 n / k + R_{n+1}) stored as pairs (R_n, R_n / n).  Only kappa < 50 (scipy switches to
+        a normal approximation above)."""
+        k = float(self.gait_kappa)
+        if not 0 < k < 50:
+            raise ValueError("the fused 'smooth' gait indicator covers 0 < kappa < 50 (scipy's series branch)")
+        p = int(1 + 28.0 + 0.5 * k - 100.0 / (k + 5.0))
+        tab, R = [], 0.0
+        for n in range(p - 1, 0, -1):
+            R = 1.0 / (2.0 * n / k + R)
+            tab += [R, R / n]
+        return p, np.asarray(tab, np.float64)
 
     def load_model(self) -> RobotModel:
         return load_robot_model(self.robot, self.dof_names)
@@ -452,8 +470,7 @@ class TaskSpec:
         )
         if task == "go2_wtw":
             g, bp = r.periodic_reward_framework, r.behavior_params_range
-            if g.gait_function_type != "step":
-                raise ValueError("only the 'step' gait indicator is fused (the 'smooth' variant calls scipy on the host)")
+            spec.gait_smooth, spec.gait_kappa = g.gait_function_type == "smooth", float(g.kappa)
             spec.gait_enabled, spec.behavior_enabled, spec.double_shift_actions = True, True, True
             spec.gait_b_swing = g.b_swing
             spec.gait_theta_lists = [[g.theta_fl_list[k], g.theta_fr_list[k], g.theta_rl_list[k], g.theta_rr_list[k]]
@@ -465,8 +482,7 @@ class TaskSpec:
             spec.reset_dof_noise = [0.2] * len(a.dof_names)           # base class _reset_dofs, legged_robot.py:279-280
         if task == "tron1_pf_ee":
             g = r.periodic_reward_framework
-            if g.gait_function_type != "step":
-                raise ValueError("only the 'step' gait indicator is fused (the 'smooth' variant calls scipy on the host)")
+            spec.gait_smooth, spec.gait_kappa = g.gait_function_type == "smooth", float(g.kappa)
             spec.gait_enabled = True
             spec.gait_period, spec.gait_theta_left, spec.gait_theta_right, spec.gait_b_swing = g.gait_period, g.theta_left, g.theta_right, g.b_swing
             spec.base_height_tracking_sigma = r.base_height_tracking_sigma

@@ -50,6 +50,7 @@ extern "C" {
 #define B200_MAX_GAITS 4
 #define B200_STATS_EXTRA 3    /* per-step statistics beyond the episode sums: terrain level, cstr prob | teacher level, student level */
 #define B200_MAX_CTRL_DELAY 7 /* largest ctrl_delay_step_range[1] */
+#define B200_VM_MAX 56       /* most terms of the von Mises CDF series (kappa < 50, "smooth" gait indicator) */
 #define B200_GAIT_STATE 20   /* floats per env in gait_state */
 /* columns of one gait_state row: theta[4] (FL,FR,RL,RR or L,R), gait time, phase, gait period, base-height /
  * foot-clearance / pitch targets (go2_wtw behaviour parameters), clock[8] = sin[feet], cos[feet] */
@@ -99,7 +100,11 @@ enum B200TaskF {
     TF_DOF_VEL_LIMIT = TF_TORQUE_LIMIT + B200_MAX_JOINTS,       /* [B200_MAX_JOINTS] cfg.asset.dof_vel_limits */
     TF_SIT_DOF_POS = TF_DOF_VEL_LIMIT + B200_MAX_JOINTS,        /* [B200_MAX_JOINTS] sit-pose joint angles */
     TF_GAIT_THETA = TF_SIT_DOF_POS + B200_MAX_JOINTS,           /* [B200_MAX_GAITS][B200_MAX_FEET] phase offsets per gait (go2_wtw) */
-    TF_COUNT = TF_GAIT_THETA + B200_MAX_GAITS * B200_MAX_FEET
+    /* "smooth" periodic-gait indicator (go2_wtw.py:415-453, tron1_pf_ee.py:369-407): the von Mises CDF that the reference
+       gets from scipy.stats.vonmises.cdf on the host, as scipy's own series -- per term n = p-1 .. 1 the pair
+       (R_n, R_n / n) of the backward recursion R_n = 1 / (2 n / kappa + R_{n+1}), which depends on kappa alone */
+    TF_VM_R = TF_GAIT_THETA + B200_MAX_GAITS * B200_MAX_FEET,   /* [2 * B200_VM_MAX] */
+    TF_COUNT = TF_VM_R + 2 * B200_VM_MAX
 };
 
 /* ---- task descriptor: int section ---- */
@@ -125,6 +130,10 @@ enum B200TaskI {
     TI_NUM_TEACHER,                                              /* go2_cts: global envs [0, num_teacher) are teacher envs (go2_cts.py:93-99) */
     TI_CLEARANCE_MODE,                                           /* foot clearance / labels relative to: 0 nothing, 1 mean, 2 max of the 9 heights */
     TI_N_SUMS,                                                   /* columns of episode_sums: rewards (+termination) (+9 cstr_*) */
+    TI_R18,                                                      /* 1: reproduce the reference's env-0 coupling of the periodic-gait tasks: flattened
+                                                                    nonzero() of [N,1] masks makes env 0 follow "any env" for the gait-clock wrap and the swing /
+                                                                    stance indicator (go2_wtw.py:258-263,443-466, tron1_pf_ee.py:27-35,397-420); default 0 = per env */
+    TI_VM_TERMS,                                                 /* 0: "step" gait indicator; p > 0: "smooth" indicator, von Mises CDF series of p terms */
     TI_REWARD_IDS,                                               /* [B200_MAX_REWARDS] active term ids, evaluation order */
     TI_FEET_LINKS = TI_REWARD_IDS + B200_MAX_REWARDS,            /* [B200_MAX_FEET]  */
     TI_PEN_LINKS = TI_FEET_LINKS + B200_MAX_FEET,                /* [B200_MAX_LINKS] */
@@ -238,7 +247,8 @@ typedef struct B200Buffers {
     float *gait_state;          /* [N,20] theta[4], gait_time, phi, gait_period, base_height_target, foot_clearance_target,
                                    pitch_target, clock_input[8] = sin[F], cos[F] (periodic-gait tasks) */
     float *cstr_prob;           /* [N] CaT termination probability (Go2CaT.cstr_prob); unused (but bound) for other tasks */
-    int32_t *global_flags;      /* [4] int32: [0] any env with |dof_vel| > 4 after the physics step (CaT stand-still, R4); [1] ticket of the
+    int32_t *global_flags;      /* [4] int32: [0] bit 0: any env with |dof_vel| > 4 after the physics step (CaT stand-still, R4), bits 8..16
+                                   (TI_R18): any env wraps its gait clock this step | any env in swing, per foot | in stance, per foot; [1] ticket of the
                                    env kernel's last-CTA finalize; [2] envs reset because their state went non-finite (cumulative) */
     float *contact_warm;        /* [N,48] contact-solver warm start carried between substeps and policy steps: 8 x (sphere id + 1,
                                    f_n, f_t1, f_t2) then 8 x (aux-row code + 1, f); zero = empty */

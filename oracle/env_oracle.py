@@ -494,7 +494,7 @@ class EnvOracle:
         s, st = self.spec, self.st
         g = st["gait_state"]
         lf = o["link_contact_forces"]
-        total = np.zeros(self.N, f32)
+        total = np.zeros(self.N, np.float64 if s.gait_smooth else f32)
         o["exp_C_frc"] = np.zeros((self.N, nfeet), f32)
         for i in range(nfeet):
             q_frc = _norm3(lf[:, self.feet[i], :])
@@ -503,6 +503,26 @@ class EnvOracle:
             b_swing = f32(s.gait_b_swing * 2 * np.pi)
             swing = (phi >= 0) & (phi < b_swing)
             stance = (phi >= b_swing) & (phi < f32(2 * np.pi))
+            if s.gait_smooth:
+                # go2_wtw.py:415-453 / tron1_pf_ee.py:369-407: von Mises CDFs from scipy on the host, in float64
+                from scipy.stats import vonmises
+                FA = np.clip(vonmises.cdf(loc=0.0, kappa=s.gait_kappa, x=phi), 0.0, 1.0)
+                FB = np.clip(vonmises.cdf(loc=np.full(self.N, b_swing, f32), kappa=s.gait_kappa, x=phi), 0.0, 1.0)
+                FS = np.clip(vonmises.cdf(loc=2 * np.pi, kappa=s.gait_kappa, x=phi), 0.0, 1.0)
+                sw_ind, st_ind = FA * (1 - FB), FB * (1 - FS)
+                spd_ori, frc_ori = -st_ind, -sw_ind
+                c_frc = -0.5 + (-0.5 - spd_ori)
+                c_spd = spd_ori.copy()
+                in_swing = swing.copy()
+                if self.reproduce_r18 and swing.any():
+                    in_swing[0] = True                     # flattened nonzero() of the [N,1] mask also indexes row 0 (R18)
+                c_frc[in_swing] = frc_ori[in_swing]
+                c_spd[in_swing] = -0.5 + (-0.5 - frc_ori[in_swing])
+                if b_swing == 0:
+                    c_frc[:], c_spd[:] = 0, -1
+                o["exp_C_frc"][:, i] = c_frc.astype(f32)
+                total = total + (c_spd * q_spd + c_frc * q_frc)          # float64, like the reference's mixed-dtype sum
+                continue
             c_frc = np.where(swing, f32(-1), f32(0))
             c_spd = np.where(stance, f32(-1), f32(0))
             if self.reproduce_r18:

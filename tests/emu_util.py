@@ -110,6 +110,7 @@ class EmuSim:
     def dynamics_step(self, actions):
         a = np.ascontiguousarray(actions, np.float32)
         rows, cols = (self.hs.shape if self.hs is not None else (0, 0))
+        self.buf["global_flags"][0] = 0          # the memset launch_dynamics (csrc/b200_step.cu) enqueues before the kernel
         self.lib.emu_dynamics_step(self._p(self.tf), self._p(self.ti), self._p(self.mi), self._p(self.mf), self._p(self.hs),
                                    ctypes.c_int(rows), ctypes.c_int(cols), ctypes.byref(self.cbuf), self._p(a))
 

@@ -23,6 +23,10 @@ def spec_for(g):
     spec = T.PRESETS[str(g["meta/task"])]()
     spec.seed = int(g["meta/seed"])
     spec.contact_state_link_names = [str(x) for x in g["meta/contact_links"]]
+    if "meta/gait_smooth" in g and int(g["meta/gait_smooth"]):          # recorded with the von Mises ("smooth") gait indicator
+        spec.gait_smooth = True
+    if "meta/reward_names" in g:                                        # the reward scales of the recording (an edited config)
+        spec.reward_scales = {str(k): float(v) for k, v in zip(g["meta/reward_names"], g["meta/reward_scales"])}
     if "meta/ctrl_delay" in g and int(g["meta/ctrl_delay"]) > 0:       # recorded with domain_rand.randomize_ctrl_delay on
         spec.randomize_ctrl_delay, spec.ctrl_delay_step_range = True, [0, int(g["meta/ctrl_delay"])]
     return spec

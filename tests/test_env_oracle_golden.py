@@ -10,7 +10,12 @@ INTS = ("reset_buf", "time_out_buf", "episode_length", "fail_buf", "last_contact
 
 
 @pytest.mark.parametrize("name", ["go2_ts_n32", "go2_n32", "go2_cat_n32", "tron1_pf_n32", "tron1_pf_ee_n32", "go2_wtw_n32", "go2_cts_n32", "go2_ee_n32",
-                                  "go2_dreamwaq_n32", "go2_ts_delay_n32"])
+                                  "go2_dreamwaq_n32", "go2_ts_delay_n32",
+                                  # every reward term the Go2TS class defines switched on (incl. dof_*_stand_still, termination,
+                                  # thigh_pos, foot_landing_vel, ...) + robots thrown off the terrain inside the window (OOB teleport)
+                                  "go2_ts_allrew_oob_n32",
+                                  # the "smooth" (von Mises CDF) periodic-gait indicator of go2_wtw / tron1_pf_ee
+                                  "go2_wtw_smooth_n32", "tron1_pf_ee_smooth_n32"])
 def test_env_oracle_reproduces_reference(name):
     g, s0 = load_golden(name)
     spec = spec_for(g)
@@ -59,3 +64,9 @@ def test_env_oracle_reproduces_reference(name):
                 assert np.allclose(o[hk], g[f"hist{t}/{hk}"], rtol=2e-5, atol=2e-6), f"step {t}: {hk}"
         resets += int(ref["reset_buf"].sum())
     assert resets > 0
+    if "oob" in name:                  # the window did contain out-of-bounds teleports (base x / y jumps by hundreds of metres)
+        jump = np.abs(g["out/base_pos"][:, :, :2] - g["phys/base_pos"][:, :, :2]).max(axis=2)
+        assert (jump > 100).sum() >= 4
+    if "allrew" in name:
+        on = {k for k, v in spec.reward_scales.items() if v != 0}
+        assert {"dof_pos_stand_still", "dof_vel_stand_still", "termination", "thigh_pos", "foot_landing_vel", "keep_balance"} <= on

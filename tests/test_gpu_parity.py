@@ -55,6 +55,13 @@ def test_env_kernel_matches_reference_golden(name):
     _golden_run(name)
 
 
+@pytest.mark.parametrize("name", ["go2_ts_allrew_oob_n32", "go2_wtw_smooth_n32", "tron1_pf_ee_smooth_n32"])
+def test_env_kernel_matches_reference_golden_of_edited_configs(name):
+    """Generic instantiation: all reward terms of the Go2TS class on + an out-of-bounds teleport inside the window; the
+    von Mises ("smooth") periodic-gait indicator evaluated on the device (the reference calls scipy on the host)."""
+    _golden_run(name)
+
+
 def test_control_delay_queue_matches_reference_golden():
     """domain_rand.randomize_ctrl_delay (legged_robot.py:144-148,240-245): the dynamics kernel pushes the clipped action
     into the env's queue and drives the joints with the delayed slot, the env kernel clears the queue and redraws the
@@ -79,9 +86,16 @@ def test_frame_stack_views_are_strided_windows_of_the_rings():
         assert torch.allclose(w(h), w(h.contiguous()), atol=1e-5)         # a strided batch feeds nn.Linear as it is
 
 
-def _golden_run(name):
+@pytest.mark.parametrize("name", ["tron1_pf_ee_n32", "go2_wtw_n32"])
+def test_env_kernel_reproduces_the_env0_coupling_on_request(name):
+    """TaskSpec.reproduce_r18 (bug-compatible mode): every env of the reference golden, env 0 included."""
+    _golden_run(name, r18=True)
+
+
+def _golden_run(name, r18=False):
     g, s0 = load_golden(name)
     spec = spec_for(g)
+    spec.reproduce_r18 = r18
     terrain = load_terrain(spec) if spec.heightfield else None
     N, T_ = g["actions"].shape[1], g["actions"].shape[0]
     env = _env(spec, N, terrain)
@@ -95,7 +109,8 @@ def _golden_run(name):
         a = torch.from_numpy(g["actions"][t]).cuda()
         sim.step(a)                                   # pre-step bookkeeping (+ our own physics, overwritten below)
         sim.load_state({PH[k]: v for k, v in phys_at(g, t).items()})
-        sim._buf["global_flags"][0] = int((np.abs(phys_at(g, t)["qd"]) > 4).any())   # what the dynamics kernel would leave (CaT R4)
+        # what the dynamics kernel would leave for these joint velocities (CaT R4, bit 0); its R18 "any env" bits stay
+        sim._buf["global_flags"][0] = (int(sim._buf["global_flags"][0]) & ~1) | int((np.abs(phys_at(g, t)["qd"]) > 4).any())
         env.common_step_counter += 1
         env._set_step_flags()
         sim.fused_post_step(env.common_step_counter, env.command_ranges["lin_vel_x"])
@@ -107,7 +122,7 @@ def _golden_run(name):
             mine["obs_buf"], mine["privileged_obs_buf"] = st["obs_history"], st["critic_obs"]
         if spec.obs_kind == "go2_dreamwaq":                              # labels travel in privileged_obs_buf, the critic stack is returned
             mine["explicit_labels_buf"], mine["privileged_obs_buf"] = st["privileged_obs_buf"], st["critic_obs"]
-        skip0 = spec.obs_kind in ("tron1_pf_ee", "go2_wtw")  # R18: env 0 is coupled to all envs in the reference; not reproduced
+        skip0 = spec.obs_kind in ("tron1_pf_ee", "go2_wtw") and not r18  # R18: env 0 is coupled to all envs in the reference (reproduced on request only)
         for k, r in ref.items():
             if k not in mine or k in ("end_state",):
                 continue

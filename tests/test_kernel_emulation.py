@@ -21,6 +21,13 @@ def test_emulated_env_kernel_matches_reference_golden(name, steps):
     _run_golden(name, steps)
 
 
+@pytest.mark.parametrize("name", ["go2_ts_allrew_oob_n32", "go2_wtw_smooth_n32", "tron1_pf_ee_smooth_n32"])
+def test_emulated_env_kernel_matches_reference_golden_of_edited_configs(name):
+    """Edited configurations (generic instantiation): every reward term of the Go2TS class on + an out-of-bounds teleport
+    inside the window; the von Mises ("smooth") periodic-gait indicator, computed on the device instead of by scipy."""
+    _run_golden(name, 6, specialized=False)
+
+
 def test_emulated_env_kernel_with_control_delay_matches_reference_golden():
     """domain_rand.randomize_ctrl_delay on (no shipped config enables it -> generic instantiation): the env kernel clears
     the action queue and redraws the delay of envs that reset (legged_robot.py:144-148)."""
@@ -38,9 +45,18 @@ def test_emulated_frame_stack_rings_wrap_around():
     _run_golden("go2_ts_n32", 9)
 
 
-def _run_golden(name, steps, specialized=True):
+@pytest.mark.parametrize("name", ["tron1_pf_ee_n32", "go2_wtw_n32"])
+def test_emulated_env_kernel_reproduces_the_env0_coupling_on_request(name):
+    """TaskSpec.reproduce_r18: the reference's flattened-nonzero() indexing makes env 0 follow "any env" for the gait-clock
+    wrap and the swing / stance indicator.  With the switch on the dynamics kernel leaves the "any env"
+    bits and the env kernel applies them to row 0: every env of the golden is compared, env 0 included."""
+    _run_golden(name, 5, specialized=False, r18=True)
+
+
+def _run_golden(name, steps, specialized=True, r18=False):
     g, s0 = load_golden(name)
     spec = spec_for(g)
+    spec.reproduce_r18 = r18
     hs, origins = (load_terrain(spec) if spec.heightfield else (None, None))
     N = g["actions"].shape[1]
     sim = EmuSim(spec, N, hs, origins, specialized=specialized)
@@ -49,14 +65,18 @@ def _run_golden(name, steps, specialized=True):
     for t in range(steps):
         # pre-step bookkeeping of the dynamics kernel, then the recorded post-physics state
         a = np.clip(g["actions"][t], -spec.clip_actions, spec.clip_actions)
-        B["llast_actions"][:] = B["last_actions"]; B["last_actions"][:] = B["actions"]; B["actions"][:] = a
-        if spec.randomize_ctrl_delay:          # the queue push of the dynamics kernel's pre-step (legged_robot.py:240-245)
-            qu = B["action_queue"].reshape(N, -1, spec.num_actions)
-            qu[:, 1:] = qu[:, :-1].copy(); qu[:, 0] = a
-        B["last_dof_vel"][:] = B["dof_vel"]; B["last_feet_vel"][:] = B["feet_vel"]
+        if r18:                                # the real (emulated) dynamics kernel: pre-step bookkeeping + the R18 "any env" bits
+            sim.dynamics_step(g["actions"][t])
+        else:
+            B["llast_actions"][:] = B["last_actions"]; B["last_actions"][:] = B["actions"]; B["actions"][:] = a
+            if spec.randomize_ctrl_delay:          # the queue push of the dynamics kernel's pre-step (legged_robot.py:240-245)
+                qu = B["action_queue"].reshape(N, -1, spec.num_actions)
+                qu[:, 1:] = qu[:, :-1].copy(); qu[:, 0] = a
+            B["last_dof_vel"][:] = B["dof_vel"]; B["last_feet_vel"][:] = B["feet_vel"]
         for k, b in PH.items():
             B[b][...] = phys_at(g, t)[k].reshape(B[b].shape)
-        B["global_flags"][0] = int((np.abs(phys_at(g, t)["qd"]) > 4).any())      # what the dynamics kernel leaves (CaT R4)
+        # what the dynamics kernel would leave for these joint velocities (CaT R4, bit 0); its R18 "any env" bits stay
+        B["global_flags"][0] = (int(B["global_flags"][0]) & ~1) | int((np.abs(phys_at(g, t)["qd"]) > 4).any())
         B["stats"][:] = 0
         sim.env_post_step()
         assert (sim.last_preset >= 0) == specialized, "preset selection"
@@ -67,7 +87,7 @@ def _run_golden(name, steps, specialized=True):
             mine["obs_buf"], mine["privileged_obs_buf"] = sim.obs_history, sim.critic_obs
         if spec.obs_kind == "go2_dreamwaq":                              # labels travel in privileged_obs_buf, the critic stack is returned
             mine["explicit_labels_buf"], mine["privileged_obs_buf"] = B["privileged_obs_buf"], sim.critic_obs
-        skip0 = spec.obs_kind in ("tron1_pf_ee", "go2_wtw")  # R18: the reference couples env 0 to all envs; not reproduced
+        skip0 = spec.obs_kind in ("tron1_pf_ee", "go2_wtw") and not r18  # R18: the reference couples env 0 to all envs (reproduced on request only)
         for k, r in ref.items():
             if k not in mine or k == "end_state":
                 continue

@@ -32,14 +32,14 @@ def _n(t):
     return t.detach().float().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
 
 
-def _ref_outputs(env, ret, task):
+def _ref_outputs(env, ret, task, sum_names):
     """What the reference step returned / left behind, keyed like the fused env's buffers."""
     sim = env.simulator
     o = dict(rew_buf=_n(env.rew_buf), reset_buf=_n(env.reset_buf), time_out_buf=_n(env.time_out_buf), commands=_n(env.commands),
              episode_length=_n(env.episode_length_buf), fail_buf=_n(env.fail_buf), feet_air_time=_n(env.feet_air_time),
              last_contacts=_n(env.last_contacts), actions=_n(env.actions), last_actions=_n(env.last_actions),
              llast_actions=_n(env.llast_actions),
-             episode_sums=np.stack([_n(v) for v in env.episode_sums.values()], axis=1))
+             episode_sums=np.stack([_n(env.episode_sums[k]) for k in sum_names], axis=1))
     for k in ("base_pos", "dof_pos", "dof_vel", "base_lin_vel", "base_ang_vel", "projected_gravity", "friction", "added_mass", "com_bias",
               "kp_scale", "kd_scale", "rand_push_vels", "env_origins", "terrain_levels", "measured_heights", "link_contact_forces",
               "feet_pos", "feet_vel", "base_quat_wxyz", "base_lin_w", "base_ang_w", "height_around_feet", "link_contact_states"):
@@ -87,8 +87,8 @@ def _run(task, impl, fused_cls, cpu, N=16, steps=24, cfg_edit=None, skip_env0=Fa
                 ref.foot_clearance_target_range, ref.pitch_target_range = [0.05, 0.10], [-0.2, 0.2]
                 ep[4::8] = 250 - 2 - (torch.arange(len(ep[4::8])) % 4).to(ep.dtype).to(dev)
             ref.step(torch.zeros(N, A, device=dev))                                                 # API buffers consistent with the edits
-            sum_names = list(ref.episode_sums.keys())
-            assert sum_names == spec.episode_sum_names(), (sum_names, spec.episode_sum_names())
+            sum_names = spec.episode_sum_names()          # the reference's dict keys, "termination" moved behind the other terms
+            assert sorted(sum_names) == sorted(ref.episode_sums.keys()), (sum_names, list(ref.episode_sums.keys()))
             terrain = (sim._height_samples.cpu().numpy(), sim._terrain_origins.cpu().numpy()) if spec.heightfield else None
             fused = fused_cls(spec, N, dev, terrain=terrain)
             transfer_state(ref, fused, sum_names)
@@ -100,7 +100,7 @@ def _run(task, impl, fused_cls, cpu, N=16, steps=24, cfg_edit=None, skip_env0=Fa
                     a[0] = 150.0                                                                    # exercises clip_actions
                 r_ret = ref.step(a.clone())
                 fused.step(a.clone())
-                o = _ref_outputs(ref, r_ret, task)
+                o = _ref_outputs(ref, r_ret, task, sum_names)
                 fb = fused.simulator.get_state()
                 for k, rv in o.items():
                     if k not in fb:

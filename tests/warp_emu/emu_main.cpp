@@ -62,6 +62,8 @@ int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int row
     a.call.inv_episode_length_s = 1.0f / a.T.f[TF_EPISODE_LENGTH_S]; a.call.inv_num_envs = 1.0f / (float)a.T.i[TI_NUM_ENVS];
     a.call.inv_teacher = 0.f; a.call.inv_student = 1.0f / (float)a.T.i[TI_NUM_ENVS];
     g_env_preset = g_env_specialized ? env_match_preset(a.T.i) : -1;
+    if (a.T.i[TI_R18] && (phase_mask & PHASE_REWARD) && !force_reset)      // like launch_env in csrc/b200_step.cu
+        emu_launch([](void *p) { EnvArgs *e = (EnvArgs *)p; r18_flags_kernel(e->T, e->B, e->call); }, &a, (a.T.i[TI_NUM_ENVS] + R18_FLAGS_BLOCK - 1) / R18_FLAGS_BLOCK);
     emu_launch(env_body, &a, a.T.i[TI_NUM_ENVS]);
     return g_env_preset;
 }

@@ -103,6 +103,9 @@ def main():
     ap.add_argument("--contact-links", nargs="*", default=None, help="override asset.contact_state_link_names (SURVEY R1)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--ctrl-delay", type=int, default=0, help="enable domain_rand.randomize_ctrl_delay with step range [0, N]")
+    ap.add_argument("--gait-smooth", action="store_true", help="periodic_reward_framework.gait_function_type = 'smooth' (von Mises CDF indicator)")
+    ap.add_argument("--all-rewards", action="store_true", help="give every _reward_* term the task class defines a non-zero scale")
+    ap.add_argument("--oob", action="store_true", help="throw a few robots off the terrain inside the window (OOB teleport, genesis_simulator.py:612-628)")
     args = ap.parse_args()
     import torch
 
@@ -112,6 +115,20 @@ def main():
         if args.ctrl_delay > 0:
             cfg.domain_rand.randomize_ctrl_delay = True
             cfg.domain_rand.ctrl_delay_step_range = [0, args.ctrl_delay]
+        if args.gait_smooth:
+            cfg.rewards.periodic_reward_framework.gait_function_type = "smooth"
+        if args.all_rewards:
+            # every term this task class implements and the fused kernel knows, with a non-zero scale (the shipped configs
+            # never enable dof_pos_stand_still, dof_vel_stand_still, termination, thigh_pos, ...); small magnitudes so that the
+            # only_positive_rewards clip does not flatten everything
+            import legged_gym.envs  # noqa: F401
+            from legged_gym.utils.task_registry import task_registry as _reg
+            klass = _reg.get_task_class(args.task)
+            if not hasattr(cfg.rewards, "about_landing_threshold"):      # read by _reward_foot_landing_vel, missing from the rough-terrain configs
+                cfg.rewards.about_landing_threshold = 0.03
+            for k, name in enumerate(T.REWARD_TERMS):
+                if hasattr(klass, "_reward_" + name) and name not in ("torque_limits",) and float(getattr(cfg.rewards.scales, name, 0.0) or 0.0) == 0.0:
+                    setattr(cfg.rewards.scales, name, (-1.0 if name != "keep_balance" else 1.0) * 1e-3 * (1 + k % 5))
 
     env, cfg, _ = make_env(args.task, args.envs, cfg_edit=edit)
     spec = T.TaskSpec.from_reference_cfg(cfg, args.task)
@@ -146,8 +163,10 @@ def main():
         env.foot_clearance_target_range, env.pitch_target_range = [0.05, 0.10], [-0.2, 0.2]
         ep[4::8] = 250 - 2 - (torch.arange(len(ep[4::8])) % 4).to(ep.dtype)        # behaviour resampling inside the window
     env.step(torch.zeros(N, A))                                                    # make API buffers consistent
-    sum_names = list(env.episode_sums.keys())                                      # CaT adds its cstr_* keys lazily
-    assert sum_names == spec.episode_sum_names(), (sum_names, spec.episode_sum_names())
+    # the reference keeps episode_sums as a dict (alphabetical keys, CaT adds its cstr_* keys lazily); the recording stacks the
+    # columns in the descriptor's order, which differs only in that "termination" comes after the other reward terms
+    sum_names = spec.episode_sum_names()
+    assert sorted(sum_names) == sorted(env.episode_sums.keys()), (sum_names, list(env.episode_sums.keys()))
     inj = Injector(env, spec.seed)
     inj.install()
 
@@ -175,6 +194,9 @@ def main():
         a = 0.8 * torch.randn(N, A, generator=g)
         if t == 1:
             a[0] = 150.0                                                            # exercise clip_actions
+        if args.oob and t == 2:
+            rob.state[5::8, 0] += 400.0                                             # off the heightfield: teleported home in post_physics_step
+            rob.state[6::8, 1] -= 400.0
         ret = env.step(a.clone())
         put(t, "actions", n(a))
         for k, v in phys.items():
@@ -231,6 +253,9 @@ def main():
     rec["meta/task"] = np.array(args.task)
     rec["meta/seed"] = np.int64(spec.seed)
     rec["meta/ctrl_delay"] = np.int64(args.ctrl_delay)
+    rec["meta/gait_smooth"] = np.int64(int(args.gait_smooth))
+    rec["meta/reward_names"] = np.array(sorted(spec.reward_scales))
+    rec["meta/reward_scales"] = np.asarray([spec.reward_scales[k] for k in sorted(spec.reward_scales)], np.float64)
     rec["meta/contact_links"] = np.array(spec.contact_state_link_names)
     rec["meta/sum_names"] = np.array(sum_names)
     out = os.path.join(ROOT, "tests", "golden", name + ".npz")
