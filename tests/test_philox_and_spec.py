@@ -35,7 +35,7 @@ def test_header_enums_and_struct():
         [T.SITE_CMD_RESAMPLE, T.SITE_PUSH, T.SITE_LEVEL, T.SITE_CMD_RESET, T.SITE_DOF, T.SITE_ROOT]
     assert H["SITE_OBS_NOISE"] == T.SITE_OBS_NOISE
     names = [n for n, _ in _cabi.BUFFER_FIELDS]
-    assert names[0] == "base_pos" and names[-1] == "dyn_order" and "stats" in names and "obs_history" in names and "critic_obs" in names and len(set(names)) == len(names)
+    assert names[0] == "base_pos" and names[-1] == "nonfinite" and "dyn_order" in names and "stats" in names and "obs_history" in names and "critic_obs" in names and len(set(names)) == len(names)
 
 
 @pytest.mark.parametrize("task", ["go2", "go2_ts"])
