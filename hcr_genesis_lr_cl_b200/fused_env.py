@@ -93,6 +93,13 @@ class FusedLeggedEnv:
             g[:, H["B200_GS_PER"]], g[:, H["B200_GS_BH"]] = self.gait_period_range[0], self.base_height_target_range[0]
             g[:, H["B200_GS_FC"]], g[:, H["B200_GS_PT"]] = self.foot_clearance_target_range[0], self.pitch_target_range[0]
         self._extras_ring = self._build_extras_ring()
+        # go2_cat as shipped couples ALL envs through its stand-still constraint (go2_cat.py:177-178): under env
+        # sharding the "any env is moving fast" flag is a scalar of the whole job.  cat_global_allreduce=True keeps it one
+        # (a 4-byte NCCL MAX between the dynamics and the env kernel: the step then takes two C-ABI calls and ~one collective
+        # latency more); the default leaves the flag rank-local, i.e. results then depend on the sharding for this one task --
+        # which the per-env switch (cat_stand_still_global=False) avoids altogether.
+        import os
+        self.cat_global_allreduce = bool(spec.cat_enabled and spec.cat_stand_still_global and os.environ.get("B200_CAT_ALLREDUCE", "0") == "1")
 
     # runners assign a fresh tensor to env.episode_length_buf (on_policy_runner.py:169); keep the bound storage
     @property
@@ -123,10 +130,31 @@ class FusedLeggedEnv:
     def step(self, actions: torch.Tensor):
         """LeggedRobot.step: one C-ABI call (b200_env_step) = _pre_sim_step + simulator.step + post_physics_step:
         dynamics kernel -> env kernel, with the frame-stack shift on a side stream under the dynamics kernel."""
+        if self.cat_global_allreduce and self._world_size() > 1:
+            return self._step_with_global_flag(actions)
         self.common_step_counter += 1
         self._apply_pending_curriculum()
         self._set_step_flags()
         self.simulator.fused_env_step(actions, self.common_step_counter, self.command_ranges["lin_vel_x"])
+        self._fill_extras()
+        return self._returns()
+
+    @staticmethod
+    def _world_size() -> int:
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _step_with_global_flag(self, actions: torch.Tensor):
+        """go2_cat under env sharding with the job-wide stand-still flag (see __init__): dynamics kernel, 4-byte all-reduce
+        (MAX) of global_flags[0], env kernel."""
+        import torch.distributed as dist
+        sim = self.simulator
+        sim.step(actions)
+        dist.all_reduce(self._b["global_flags"][:1], op=dist.ReduceOp.MAX)
+        self.common_step_counter += 1
+        self._apply_pending_curriculum()
+        self._set_step_flags()
+        sim.fused_post_step(self.common_step_counter, self.command_ranges["lin_vel_x"])
         self._fill_extras()
         return self._returns()
 
@@ -238,6 +266,10 @@ class FusedLeggedEnv:
                 ep["teacher_terrain_level"], ep["student_terrain_level"] = row[n + 1], row[n + 2]
             ring.append(ep)
         return ring
+
+    #: a step's extras["episode"] values are views into slot (step % stats_ring) of a device ring: a runner that keeps them
+    #: for more than `stats_ring` steps before reading (num_steps_per_env > stats_ring) must clone them at append time
+    stats_ring = property(lambda self: int(self.simulator._lib.b200_stats_ring()))
 
     def _fill_extras(self):
         """extras["episode"]["rew_*"] = mean over resetting envs of episode_sums / episode_length_s

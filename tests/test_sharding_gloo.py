@@ -22,6 +22,27 @@ def _worker(rank, world, port, q):
         # reference: average of the two per-rank gradients
         expect = sum((torch.arange(16.0).reshape(2, 8) + r).sum(0) for r in range(world)) / world
         ok_grad = torch.allclose(g, expect.expand(3, 8))
+        # the edit-free PPO wiring: flat bucket, all-reduce fired by the last gradient hook inside backward(), zero_grad kept in place
+        torch.manual_seed(1)
+        net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ELU(), torch.nn.Linear(16, 3))
+        opt = torch.optim.SGD(net.parameters(), lr=0.1)
+        bucket = parallel.GradientBucket(net.parameters()).attach(opt)
+        ok_bucket = True
+        for it in range(3):
+            opt.zero_grad()                                   # rsl_rl calls it with the default set_to_none=True
+            xb = torch.arange(16.0).reshape(2, 8) * 0.01 + rank + it
+            net(xb).pow(2).sum().backward()                   # averaged over the ranks when this returns
+            ok_bucket &= all(p.grad._base is bucket.flat for p in net.parameters()) and bucket.calls == it + 1
+            ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ELU(), torch.nn.Linear(16, 3))
+            ref.load_state_dict(net.state_dict())
+            acc = [torch.zeros_like(p) for p in ref.parameters()]
+            for r in range(world):
+                ref.zero_grad()
+                ref(torch.arange(16.0).reshape(2, 8) * 0.01 + r + it).pow(2).sum().backward()
+                acc = [a + p.grad / world for a, p in zip(acc, ref.parameters())]
+            ok_bucket &= all(torch.allclose(p.grad, a, atol=1e-6) for p, a in zip(net.parameters(), acc))
+            torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+            opt.step()
         kl = parallel.allreduce_mean(torch.tensor([float(rank + 1)]))
         data = torch.arange(10.0) + 10 * rank
         mean, std = parallel.global_mean_std(data)
@@ -30,7 +51,7 @@ def _worker(rank, world, port, q):
         stats = torch.tensor([2.0 * (rank + 1), 4.0 * (rank + 1), float(rank + 1)])     # two sums + reset count
         ep = parallel.reduce_episode_stats(stats, 2, 20.0, ["a", "b"])
         ok_ep = abs(float(ep["rew_a"]) - (2 + 4) / (3 * 20.0)) < 1e-6 and abs(float(ep["rew_b"]) - (4 + 8) / (3 * 20.0)) < 1e-6
-        q.put((rank, ok_grad, abs(float(kl) - 1.5) < 1e-6, ok_stats, ok_ep))
+        q.put((rank, ok_grad, abs(float(kl) - 1.5) < 1e-6, ok_stats, ok_ep, bool(ok_bucket)))
     finally:
         dist.destroy_process_group()
 

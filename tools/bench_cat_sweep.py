@@ -8,7 +8,9 @@ gradients are all-reduced over NCCL (`parallel.allreduce_gradients`), the way rs
 One iteration = 24 policy steps of collection (actor MLP in PyTorch -> FusedLeggedEnv.step, no host sync) + 5 epochs x 4
 minibatches of a clipped-surrogate update of a 45->512->256->128->12 actor and a 99->512->256->128->1 critic (random
 init; the point is the shape of the work, not the learning).  Prints env-substeps/s of the collection alone and of the
-whole iteration, and the time spent inside the gradient all-reduce.  The policy MLP stays PyTorch (north_star)."""
+whole iteration, and the gradient all-reduce timed with CUDA events around the collective itself (one flat bucket whose
+views ARE the .grad tensors, fired by the last gradient hook inside backward(): `parallel.GradientBucket`).  The policy MLP
+stays PyTorch (north_star)."""
 import argparse
 import json
 import os
@@ -51,6 +53,8 @@ def main():
         actor, critic = mlp(obs.shape[1], spec.num_actions).to(dev), mlp(priv.shape[1], 1).to(dev)
         params = list(actor.parameters()) + list(critic.parameters())
         opt = torch.optim.Adam(params, lr=1e-3)
+        bucket = parallel.GradientBucket(params).attach(opt)       # edit-free wiring of rsl_rl's PPO.update
+        bucket.events = []
         H = args.horizon
         buf_o = torch.zeros(H, N, obs.shape[1], device=dev); buf_p = torch.zeros(H, N, priv.shape[1], device=dev)
         buf_a = torch.zeros(H, N, spec.num_actions, device=dev); buf_r = torch.zeros(H, N, device=dev)
@@ -79,15 +83,15 @@ def main():
                     logp = -0.5 * ((fa[idx] - actor(fo[idx])) ** 2).sum(-1)
                     ratio = torch.exp(logp - logp.detach())
                     loss = -torch.min(ratio * adv[idx], ratio.clamp(0.8, 1.2) * adv[idx]).mean() + (critic(fp[idx]).squeeze(-1) - adv[idx]).pow(2).mean()
-                    opt.zero_grad(set_to_none=True)
-                    loss.backward()
-                    torch.cuda.synchronize(); ta = time.perf_counter()
-                    parallel.allreduce_gradients(params)
-                    torch.cuda.synchronize(); ar += time.perf_counter() - ta
+                    opt.zero_grad()
+                    loss.backward()                                # the bucket's all-reduce fires inside, before the clip (ppo.py:136-137)
                     torch.nn.utils.clip_grad_norm_(params, 1.0)
                     opt.step()
             torch.cuda.synchronize()
             t2 = time.perf_counter()
+            ar = sum(a.elapsed_time(b) for a, b in bucket.events) * 1e-3
+            n_calls = max(len(bucket.events), 1)
+            bucket.events = []
             if it > 0:                       # iteration 0 is warm-up
                 t_col += t1 - t0; t_all += t2 - t0; t_ar += ar
         times = torch.tensor([t_col, t_all, t_ar], device=dev, dtype=torch.float64)
@@ -99,6 +103,8 @@ def main():
                               "collection_env_substeps_per_s": sub / float(times[0]), "iteration_env_substeps_per_s": sub / float(times[1]),
                               "ms_per_policy_step_collection": 1e3 * float(times[0]) / (H * args.iters),
                               "allreduce_ms_per_iteration": 1e3 * float(times[2]) / args.iters,
+                              "allreduce_us_per_call": 1e6 * float(times[2]) / args.iters / 20, "gradient_bucket_bytes": bucket.nbytes,
+                              "allreduce_timing": "CUDA events around all_reduce + 1/world scaling on the flat bucket (device time, max over ranks)",
                               "env_kernel_variant": env.simulator.env_kernel_variant}), flush=True)
         del env
         torch.cuda.empty_cache()
