@@ -83,8 +83,11 @@ class GradientBucket:
         if self.events is not None and self.flat.is_cuda:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.mul_(1.0 / w)
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)        # ncclAvg: the 1 / world scaling inside the collective kernel
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / w)
         if ev is not None:
             ev[1].record()
             self.events.append(ev)

@@ -106,6 +106,22 @@ def main():
                               "allreduce_us_per_call": 1e6 * float(times[2]) / args.iters / 20, "gradient_bucket_bytes": bucket.nbytes,
                               "allreduce_timing": "CUDA events around all_reduce + 1/world scaling on the flat bucket (device time, max over ranks)",
                               "env_kernel_variant": env.simulator.env_kernel_variant}), flush=True)
+        if world > 1 and total == args.envs[-1]:
+            # the collective by itself: 50 all-reduces of the gradient bucket back to back (the ranks pace each other, so no
+            # arrival skew is inside the timed region, unlike the per-iteration figure above)
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(5):
+                dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG)
+            e0.record()
+            for _ in range(50):
+                dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG)
+            e1.record(); torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / 50], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(json.dumps({"allreduce_back_to_back_us": 1e3 * float(t[0]), "bucket_bytes": bucket.nbytes, "n_gpus": world}), flush=True)
+        bucket.detach()
         del env
         torch.cuda.empty_cache()
     if world > 1:
