@@ -107,7 +107,7 @@ def main():
         return name, p, R
 
     acc = {n: dict(m=0.0, h=np.zeros(3), parts=[]) for n in body_names}
-    report, spheres = [], []
+    report, spheres, primitives = [], [], []
     for ln in link_order:
         b, p, R = to_body(ln)
         l = links[ln]
@@ -129,12 +129,19 @@ def main():
         for col in l.findall("collision"):
             cp, cR = origin_of(col)
             g = list(col.find("geometry"))[0]
+            # the primitive itself, in the owning body's frame (numbers only): what the sphere set stands in for --
+            # tools/d1_contact_study.py measures the difference (DESIGN.md deviation D1)
+            gp, gR = p + R @ cp, R @ cR
+            dims = vec(g.attrib["size"]) if g.tag == "box" else np.array([float(g.attrib["radius"]), float(g.attrib.get("length", 0.0))])
+            primitives.append(dict(body=body_idx[b], link_name=(ln if (ln in body_idx or ln in args.keep) else b), type=g.tag,
+                                   pos=[float(x) for x in gp], rot=[[float(x) for x in row] for row in gR], dims=[float(x) for x in dims],
+                                   src=f"{ln}:{g.tag}"))
             for c, r in spheres_for_geom(g.tag, g.attrib, p + R @ cp, R @ cR):
                 spheres.append(dict(body=body_idx[b], link_name=(ln if (ln in body_idx or ln in args.keep) else b),
                                     pos=[float(x) for x in c], radius=float(r), src=f"{ln}:{g.tag}"))
 
     link_idx = {r["name"]: i for i, r in enumerate(report)}
-    for s in spheres:
+    for s in spheres + primitives:
         s["link"] = link_idx[s.pop("link_name")]
 
     bodies = []
@@ -177,7 +184,7 @@ def main():
     assert len({len(c) for c in chains}) == 1
     model = dict(name=args.name, source=args.urdf.split("resources/")[-1], base_link=base_name,
                  num_chains=len(chains), chain_len=len(chains[0]), chains=chains,
-                 bodies=bodies, links=report, spheres=spheres,
+                 bodies=bodies, links=report, spheres=spheres, primitives=primitives,
                  total_mass=sum(b["mass"] for b in bodies))
     with open(args.out, "w") as f:
         json.dump(model, f, indent=1)
