@@ -68,6 +68,13 @@ class B200Buffers(ctypes.Structure):
     _fields_ = [(name, ctypes.c_void_p) for name, _ in BUFFER_FIELDS]
 
 
+class B200RolloutTargets(ctypes.Structure):
+    """include/b200_step.h: extra destinations of the next fused post step (rollout-side fusion)."""
+    _fields_ = [("obs", ctypes.c_void_p), ("privileged_obs", ctypes.c_void_p), ("next_state", ctypes.c_void_p), ("rewards", ctypes.c_void_p), ("dones", ctypes.c_void_p),
+                ("values", ctypes.c_void_p), ("gamma", ctypes.c_float), ("ep_return", ctypes.c_void_p), ("ep_length", ctypes.c_void_p),
+                ("ep_stats", ctypes.c_void_p)]
+
+
 # ------------------------------------------------------------------ descriptor packing
 def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0), env_offset: int = 0) -> Tuple[np.ndarray, np.ndarray]:
     """TaskSpec -> (float[TF_COUNT], int[TI_COUNT])."""
@@ -251,7 +258,8 @@ def buffer_shapes(spec: T.TaskSpec, model: RobotModel, N: int) -> "OrderedDict[s
         normal_vector_around_feet=(N, 3 * F), last_dof_vel=(N, A), last_feet_vel=(N, F, 3), last_base_lin_vel=(N, 3),
         last_base_ang_vel=(N, 3),
         obs_buf=(N, w["obs"]), privileged_obs_buf=(N, max(w["priv"], 1)),
-        obs_history=(N, 2 * max(w["hist"], 1)), critic_obs=(N, 2 * max(w["critic"], 1)),     # double-written rings (b200_step.h)
+        # double-written rings of period K + 1 (b200_step.h)
+        obs_history=(N, 2 * (spec.frame_stack + 1) * w["obs"] if w["hist"] else 2), critic_obs=(N, 2 * (spec.c_frame_stack + 1) * w["single_critic"] if w["critic"] else 2),
         rew_buf=(N,), reset_buf=(N,), time_out_buf=(N,), contact_warm=(N, 48), gait_state=(N, H["B200_GAIT_STATE"]), height_cells=(N, P, 2), stats=(stats_base(nsum) + STATS_RING * (max(nsum, 1) + H["B200_STATS_EXTRA"]),), cstr_prob=(N,), global_flags=(4,),
         next_state_buf=(N, w["obs"] if spec.obs_kind == "go2_dreamwaq" else 1), dyn_cost=(2, N), dyn_order=(2, N),
         action_queue=(N, (int(spec.ctrl_delay_step_range[1]) + 1) * A if spec.randomize_ctrl_delay else 1), action_delay=(N,),
@@ -311,6 +319,8 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.b200_env_post_step.restype = ctypes.c_int
     lib.b200_env_step.argtypes = [vp, vp, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_longlong, vp, vp, vp, vp]
     lib.b200_env_step.restype = ctypes.c_int
+    lib.b200_set_rollout_targets.argtypes = [vp, ctypes.POINTER(B200RolloutTargets)]
+    lib.b200_set_rollout_targets.restype = ctypes.c_int
     lib.b200_set_step_flags.argtypes = [vp, ctypes.c_int]
     lib.b200_set_step_flags.restype = ctypes.c_int
     lib.b200_set_side_stream.argtypes = [vp, ctypes.c_int]
@@ -336,4 +346,4 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = ["b200_create", "b200_destroy", "b200_set_terrain", "b200_bind_buffers", "b200_dynamics_step", "b200_simulator_step",
                     "b200_stats_ring", "b200_device",
-                    "b200_set_side_stream", "b200_set_dynamics_order", "b200_env_post_step", "b200_env_step", "b200_set_step_flags", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_env_kernel_variant", "b200_launch_count", "b200_last_error"]
+                    "b200_set_side_stream", "b200_set_dynamics_order", "b200_env_post_step", "b200_env_step", "b200_set_step_flags", "b200_set_rollout_targets", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_env_kernel_variant", "b200_launch_count", "b200_last_error"]

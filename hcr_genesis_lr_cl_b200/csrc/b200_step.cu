@@ -49,6 +49,7 @@ struct B200Handle {
     bool order_enabled = true;     // dynamics warps take envs sorted by solver cost (dynamics_order_kernel); B200_DYN_ORDER=0: slot w = env w
     long long dyn_launches = 0;    // parity of the cost / order buffers
     int sm_count = 148;
+    B200RolloutTargets ro{};       // extra destinations of the next fused post step (b200_set_rollout_targets), cleared by it
     int device = 0;                // the CUDA device the handle was created on (current at b200_create); every entry point runs there
     bool side_pending = false;     // work on the side stream that the next env launch has to join
 };
@@ -225,6 +226,8 @@ static EnvCall make_call(B200Handle *h, long long step, float lo, float span, lo
     EnvCall call; call.step = (uint32_t)step; call.vx_lo = lo; call.vx_span = span; call.hist_step = (uint32_t)(hist_step < 0 ? 0 : hist_step); call.phase_mask = mask; call.force_reset = force; call.sit_pose = h->sit_pose;
     for (int k = 0; k < 8; k++) call.beh[k] = h->beh[k];
     call.gait_cb = h->gait_cb; call.gait_reset = h->gait_reset;
+    memset(&call.ro, 0, sizeof call.ro);
+    if ((mask & PHASE_ALL) == PHASE_ALL && !force) { call.ro = h->ro; memset(&h->ro, 0, sizeof h->ro); }     // one step only
     // extras["episode"] means are finalised by the env kernel's last CTA when the reset phase ran for real
     const int N = h->task.i[TI_NUM_ENVS];
     const int n_teach = max(0, min(N, h->task.i[TI_NUM_TEACHER] - h->task.i[TI_ENV_OFFSET]));   // go2_cts: teacher envs of this rank
@@ -290,6 +293,15 @@ int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long
         if (host_reset) CK(cudaMemcpyAsync(host_reset, h->bufs.reset_buf, (size_t)N, cudaMemcpyDeviceToHost, s));
         if (host_time_out) CK(cudaMemcpyAsync(host_time_out, h->bufs.time_out_buf, (size_t)N, cudaMemcpyDeviceToHost, s));
     }
+    return 0;
+}
+
+int b200_set_rollout_targets(B200Handle *h, const B200RolloutTargets *t) {
+    if (!h) return fail("b200_set_rollout_targets: null handle");
+    if (!t) { memset(&h->ro, 0, sizeof h->ro); return 0; }
+    if ((t->ep_return != nullptr) != (t->ep_length != nullptr) || (t->ep_return != nullptr) != (t->ep_stats != nullptr))
+        return fail("b200_set_rollout_targets: ep_return, ep_length and ep_stats go together");
+    h->ro = *t;
     return 0;
 }
 

@@ -67,6 +67,7 @@ struct EnvCall {
     int sit_pose;        // envs resetting in this call start in the sit pose (one host coin per step, tron1_pf_ee.py:204-210)
     float beh[8];        // go2_wtw behaviour ranges {gait period, base height, foot clearance, pitch} x {lo, span}
     int gait_cb, gait_reset;   // gait index the host drew for the callback / reset resampling of this step
+    B200RolloutTargets ro;   // rollout-side fusion: extra destinations of this step's results (all NULL: none)
     // extras["episode"] means: the last CTA to finish turns the per-step reductions into ring slot `stats_slot`
     int finalize, stats_slot;
     float inv_episode_length_s, inv_num_envs, inv_teacher, inv_student;
@@ -122,19 +123,23 @@ __device__ __forceinline__ float von_mises_cdf(const float *tab, int p, float x)
 }
 
 // Frame stacks (obs_history: K = frame_stack frames of num_obs floats; critic stack: c_frame_stack frames) live in HBM as
-// DOUBLE-WRITTEN RINGS: a row holds 2K frame slots and the frame of observation step t is stored twice, in slot t mod K
-// and in slot t mod K + K.  The K most recent frames, oldest first -- exactly the tensor the reference re-concatenates
-// from its deque every step (legged_robot_ts.py:29-47) -- are then ALWAYS the contiguous slots [t mod K + 1, t mod K + K]
-// of the row: the host hands them out as a strided view (row stride 2K frames) and a step costs two frame writes per
-// stack instead of moving the K - 1 kept frames (12.5 KB per env and step for go2_ts, 77 % of what the path used to
-// touch).  A reset clears the env's whole row first (legged_robot_ts.py:120-125 zeroes every deque entry).
+// DOUBLE-WRITTEN RINGS of period M = K + 1: a row holds 2 M frame slots and the frame of observation step t is stored twice,
+// in slot t mod M and in slot t mod M + M.  The K most recent frames, oldest first -- exactly the tensor the reference
+// re-concatenates from its deque every step (legged_robot_ts.py:29-47) -- are then ALWAYS the contiguous slots
+// [t mod M + 2, t mod M + M] of the row: the host hands them out as a strided view (row stride 2 M frames) and a step costs
+// two frame writes per stack instead of moving the K - 1 kept frames (12.5 KB per env and step for go2_ts, 77 % of what the
+// path used to touch).  The one spare slot per period is what keeps the view of step t intact while step t + 1 writes
+// (slots t mod M + 1 and t mod M + 1 + M lie just outside it): rsl_rl's algorithms keep a reference to the tensors they
+// acted on and copy them into the rollout storage only AFTER env.step (ppo.py:91-116), which the reference's freshly
+// concatenated tensors allow.  A reset clears the env's whole row first (legged_robot_ts.py:120-125 zeroes every deque entry).
 __device__ __forceinline__ void ring_clear(float *ring, int env, int K, int frame, int lane) {
-    float *d = ring + (size_t)env * 2 * K * frame;
-    for (int e = lane; e < 2 * K * frame; e += 32) d[e] = 0.f;
+    float *d = ring + (size_t)env * 2 * (K + 1) * frame;
+    for (int e = lane; e < 2 * (K + 1) * frame; e += 32) d[e] = 0.f;
 }
-__device__ __forceinline__ void ring_put(float *ring, int env, int K, int frame, int slot, const float *newf, int lane) {
-    float *d = ring + ((size_t)env * 2 * K + slot) * frame;
-    for (int e = lane; e < frame; e += 32) { const float v = newf[e]; d[e] = v; d[(size_t)K * frame + e] = v; }
+__device__ __forceinline__ void ring_put(float *ring, int env, int K, int frame, uint32_t hist_step, const float *newf, int lane) {
+    const int M = K + 1, slot = (int)(hist_step % (uint32_t)M);
+    float *d = ring + ((size_t)env * 2 * M + slot) * frame;
+    for (int e = lane; e < frame; e += 32) { const float v = newf[e]; d[e] = v; d[(size_t)M * frame + e] = v; }
 }
 
 // per-env input tensors staged per CTA: X(field, element type, elements per env)
@@ -611,9 +616,21 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             rew = __fadd_rn(rew, sr);
             if (lane == ti[TI_TERMINATION_COL]) my_sum = __fadd_rn(my_sum, sr);
         }
-        if (lane == 0) B.rew_buf[env] = rew;
+        if (lane == 0) {
+            B.rew_buf[env] = rew;
+            if (call.ro.rewards)               // ppo.py:107-109: bootstrapping on time-outs, with the value of the acting step
+                call.ro.rewards[env] = (call.ro.values && time_out) ? __fadd_rn(rew, __fmul_rn(call.ro.gamma, call.ro.values[env])) : rew;
+            if (call.ro.ep_return) {           // on_policy_runner.py:127-136 on the device
+                const float ret = call.ro.ep_return[env] + rew, len = call.ro.ep_length[env] + 1.f;
+                if (reset) { atomicAdd(call.ro.ep_stats, ret); atomicAdd(call.ro.ep_stats + 1, len); atomicAdd(call.ro.ep_stats + 2, 1.f); }
+                call.ro.ep_return[env] = reset ? 0.f : ret; call.ro.ep_length[env] = reset ? 0.f : len;
+            }
+        }
     }
-    if ((pm & PHASE_TERMINATION) && lane == 0) { B.reset_buf[env] = reset ? 1 : 0; B.time_out_buf[env] = time_out ? 1 : 0; }
+    if ((pm & PHASE_TERMINATION) && lane == 0) {
+        B.reset_buf[env] = reset ? 1 : 0; B.time_out_buf[env] = time_out ? 1 : 0;
+        if (call.ro.dones) call.ro.dones[env] = reset ? 1 : 0;
+    }
 
     if (ti[TI_GAIT] && (pm & PHASE_REWARD)) {                    // tron1_pf_ee.py:27-35: advance the gait clock after the reward
         gtime = __fadd_rn(gtime, dt);
@@ -788,7 +805,9 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(2.0f, u), 1.0f), tf[TF_NOISE_VEC + e]));
             }
             nz[e] = v;
-            B.obs_buf[env * NO + e] = fminf(fmaxf(v, -clipo), clipo);
+            const float vc = fminf(fmaxf(v, -clipo), clipo);
+            B.obs_buf[env * NO + e] = vc;
+            if (call.ro.obs) call.ro.obs[(size_t)env * NO + e] = vc;
         }
         if (ti[TI_OBS_KIND] == 5) {   // go2_wtw.py:53-111: obs_buf = 5 x 61 noisy frames, privileged_obs_buf = 5 x 99 critic frames
             const int SC = ti[TI_SINGLE_CRITIC], NB = 9 + 3 * A;
@@ -814,8 +833,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             __syncwarp();
             for (int e = lane; e < SC; e += 32) cr[e] = fminf(fmaxf(cr[e], -clipo), clipo);
             __syncwarp();
-            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, (int)(call.hist_step % (uint32_t)ti[TI_FRAME_STACK]), nz, lane);
-            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, (int)(call.hist_step % (uint32_t)ti[TI_C_FRAME_STACK]), cr, lane);
+            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, call.hist_step, nz, lane);
+            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, call.hist_step, cr, lane);
         } else if (ti[TI_OBS_KIND] == 4) {   // tron1_pf_ee.py:53-141: features = 10 x 31 noisy frames, labels 17, critic = 10 x 134
             const int SC = ti[TI_SINGLE_CRITIC], NP = ti[TI_NUM_PRIV], NCS = ti[TI_N_CS], NB = NO - 4;   // NB = 9 + 3A
             float *cr = es + ES_CRIT, *pv = es + ES_PRIV;
@@ -862,11 +881,14 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             if (lane < 3) pv[lane] = __fmul_rn(comp3(lin_b, lane), tf[TF_OS_LIN_VEL]);
             if (fl) pv[3 + NCS + lane] = fminf(fmaxf(__fsub_rn(__fsub_rn(fpos.z, hmax), tf[TF_FOOT_HEIGHT_OFFSET]), -1.0f), 1.0f);
             __syncwarp();
-            for (int e = lane; e < NP; e += 32) B.privileged_obs_buf[env * NP + e] = pv[e];          // estimator labels (unclipped)
+            for (int e = lane; e < NP; e += 32) {                                                   // estimator labels (unclipped)
+                B.privileged_obs_buf[env * NP + e] = pv[e];
+                if (call.ro.privileged_obs) call.ro.privileged_obs[(size_t)env * NP + e] = pv[e];
+            }
             for (int e = lane; e < SC; e += 32) cr[e] = fminf(fmaxf(cr[e], -clipo), clipo);
             __syncwarp();
-            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, (int)(call.hist_step % (uint32_t)ti[TI_FRAME_STACK]), nz, lane);
-            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, (int)(call.hist_step % (uint32_t)ti[TI_C_FRAME_STACK]), cr, lane);
+            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, call.hist_step, nz, lane);
+            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, call.hist_step, cr, lane);
         } else if (ti[TI_OBS_KIND] == 3) {   // tron1_pf.py:15-70: obs_buf = stack of noisy frames, privileged_obs_buf = stack of critic frames
             const int SC = ti[TI_SINGLE_CRITIC];
             float *cr = es + ES_CRIT;
@@ -882,8 +904,8 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
             }
             if (fl) cr[3 + NO + A + 7 + lane] = fat;
             __syncwarp();
-            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, (int)(call.hist_step % (uint32_t)ti[TI_FRAME_STACK]), nz, lane);
-            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, (int)(call.hist_step % (uint32_t)ti[TI_C_FRAME_STACK]), cr, lane);
+            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, call.hist_step, nz, lane);
+            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, call.hist_step, cr, lane);
         } else if (ti[TI_OBS_KIND] >= 1) {   // go2_ts (1) / go2_cat (2) / go2_cts (6) / go2_ee (7) / go2_dreamwaq (8)
             const int kind = ti[TI_OBS_KIND];
             const bool cat = kind == 2;      // go2_cat.py:19-99: 3 more DR entries, no base_lin_vel, raw feet heights
@@ -936,20 +958,28 @@ __device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const
                 for (int e = lane; e < 3 * F; e += 32) pv[DRN + 9 * F + e] = es[ES_NV + e];
             }
             if (dwq) {                                                               // decoder target, go2_dreamwaq.py:72-80
-                for (int e = lane; e < 9 + 2 * A; e += 32) B.next_state_buf[env * NO + e] = ob[e];
-                if (jl) B.next_state_buf[env * NO + 9 + 2 * A + lane] = __fmul_rn(actj, tf[TF_ACTION_SCALE]);
+                for (int e = lane; e < 9 + 2 * A; e += 32) { B.next_state_buf[env * NO + e] = ob[e]; if (call.ro.next_state) call.ro.next_state[(size_t)env * NO + e] = ob[e]; }
+                if (jl) {
+                    const float vn = __fmul_rn(actj, tf[TF_ACTION_SCALE]);
+                    B.next_state_buf[env * NO + 9 + 2 * A + lane] = vn;
+                    if (call.ro.next_state) call.ro.next_state[(size_t)env * NO + 9 + 2 * A + lane] = vn;
+                }
             }
             __syncwarp();
             // estimator labels are handed out unclipped (legged_robot_ee.py:56-73, legged_robot_dreamwaq.py:63-79)
-            for (int e = lane; e < NP; e += 32) B.privileged_obs_buf[env * NP + e] = labels ? pv[e] : fminf(fmaxf(pv[e], -clipo), clipo);
+            for (int e = lane; e < NP; e += 32) {
+                const float vp = labels ? pv[e] : fminf(fmaxf(pv[e], -clipo), clipo);
+                B.privileged_obs_buf[env * NP + e] = vp;
+                if (call.ro.privileged_obs) call.ro.privileged_obs[(size_t)env * NP + e] = vp;
+            }
             if (labels) {       // these steps return the clipped stacks: clip the frame going in (ee: both stacks, dreamwaq: critic only)
                 for (int e = lane; e < SC; e += 32) cr[e] = fminf(fmaxf(cr[e], -clipo), clipo);
                 if (ee) for (int e = lane; e < NO; e += 32) nz[e] = fminf(fmaxf(nz[e], -clipo), clipo);
                 __syncwarp();
             }
             // history stacks: the new frame goes into both of its ring slots (legged_robot_ts.py:29-47)
-            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, (int)(call.hist_step % (uint32_t)ti[TI_FRAME_STACK]), nz, lane);
-            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, (int)(call.hist_step % (uint32_t)ti[TI_C_FRAME_STACK]), cr, lane);
+            ring_put(B.obs_history, env, ti[TI_FRAME_STACK], NO, call.hist_step, nz, lane);
+            ring_put(B.critic_obs, env, ti[TI_C_FRAME_STACK], SC, call.hist_step, cr, lane);
         }
     }
     // Tasks that shift the history again at the end of post_physics_step (go2_cat.py:127-130): the dynamics

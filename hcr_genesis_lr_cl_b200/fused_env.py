@@ -66,6 +66,13 @@ class FusedLeggedEnv:
         # live views (same storage the kernels write)
         b = self._b
         self.rew_buf = b["rew_buf"]
+        # The per-step rows a step hands out (obs_buf, privileged_obs_buf / estimator labels, next_state_buf) alternate between
+        # two buffers: rsl_rl's algorithms keep a reference to the tensors they acted on and copy them into the rollout storage
+        # only AFTER env.step (ppo.py:91-116), which works in the reference because its step builds fresh tensors.  The kernel
+        # writes them through the rollout-target mechanism (b200_set_rollout_targets), so no copy is involved.
+        self._pp = [{k: torch.zeros_like(b[k]) for k in ("obs_buf", "privileged_obs_buf", "next_state_buf")} for _ in range(2)]
+        self._pp_i = 0
+        self._targets_set = False
         if not self.stacked:
             self.obs_buf = b["obs_buf"]
             if spec.obs_kind != "go2_dreamwaq":                  # dreamwaq: the critic stack (property below)
@@ -135,9 +142,38 @@ class FusedLeggedEnv:
         self.common_step_counter += 1
         self._apply_pending_curriculum()
         self._set_step_flags()
+        self._set_output_targets()
         self.simulator.fused_env_step(actions, self.common_step_counter, self.command_ranges["lin_vel_x"])
         self._fill_extras()
         return self._returns()
+
+    def set_rollout_targets(self, targets) -> None:
+        """Extra destinations of the NEXT step's results (`_cabi.B200RolloutTargets`, used by rollout.FusedRolloutCollector);
+        rows it does not redirect still alternate between the env's two output buffers."""
+        import ctypes
+        pp = self._pp[self._pp_i ^ 1]
+        if not targets.obs:
+            targets.obs = pp["obs_buf"].data_ptr()
+        if not targets.privileged_obs:
+            targets.privileged_obs = pp["privileged_obs_buf"].data_ptr()
+        if not targets.next_state and self.spec.obs_kind == "go2_dreamwaq":
+            targets.next_state = pp["next_state_buf"].data_ptr()
+        sim = self.simulator
+        sim._ck(sim._lib.b200_set_rollout_targets(sim._handle, ctypes.byref(targets)))
+        self._targets_set = True
+
+    def _set_output_targets(self) -> None:
+        """Point this step's per-step rows at the buffer the PREVIOUS step did not return."""
+        from ._cabi import B200RolloutTargets
+        if not self._targets_set:
+            self.set_rollout_targets(B200RolloutTargets())
+        self._targets_set = False
+        self._pp_i ^= 1
+        pp = self._pp[self._pp_i]
+        if not self.stacked:
+            self.obs_buf = pp["obs_buf"]
+            if self.spec.obs_kind != "go2_dreamwaq" and self.num_privileged_obs is not None:
+                self.privileged_obs_buf = pp["privileged_obs_buf"]
 
     @staticmethod
     def _world_size() -> int:
@@ -154,6 +190,7 @@ class FusedLeggedEnv:
         self.common_step_counter += 1
         self._apply_pending_curriculum()
         self._set_step_flags()
+        self._set_output_targets()
         sim.fused_post_step(self.common_step_counter, self.command_ranges["lin_vel_x"])
         self._fill_extras()
         return self._returns()
@@ -166,6 +203,7 @@ class FusedLeggedEnv:
         self.common_step_counter += 1
         self._apply_pending_curriculum()
         self._set_step_flags()
+        self._set_output_targets()
         sim.fused_post_step(self.common_step_counter, self.command_ranges["lin_vel_x"])
         self._fill_extras()
         return self._returns()
@@ -179,6 +217,7 @@ class FusedLeggedEnv:
         self.common_step_counter += 1
         self._apply_pending_curriculum()
         self._set_step_flags()
+        self._set_output_targets()
         self.simulator.fused_env_step(actions_pinned, self.common_step_counter, self.command_ranges["lin_vel_x"],
                                       rew_out, reset_out, time_out_out)
         self._fill_extras()
@@ -203,15 +242,15 @@ class FusedLeggedEnv:
 
     @property
     def estimator_labels_buf(self):
-        return self._b["privileged_obs_buf"]
+        return self._pp[self._pp_i]["privileged_obs_buf"]
 
     @property
     def explicit_labels_buf(self):
-        return self._b["privileged_obs_buf"]
+        return self._pp[self._pp_i]["privileged_obs_buf"]
 
     @property
     def next_state_buf(self):
-        return self._b["next_state_buf"]
+        return self._pp[self._pp_i]["next_state_buf"]
 
     def _returns(self):
         if self.estimator:                               # LeggedRobotEE.step, legged_robot_ee.py:56-73

@@ -507,9 +507,10 @@ class B200Simulator:
     # ------------------------------------------------------------------ frame stacks (double-written rings, include/b200_step.h)
     def _stack_view(self, name: str, frames: int, width: int) -> torch.Tensor:
         """The `frames` most recent frames of a stack, oldest first, as a [N, frames * width] view of its ring (row stride
-        2 * frames * width, last dimension contiguous): what the reference re-concatenates from its deque every step."""
-        last = (self._hist_count - 1) % frames
-        return self._buf[name][:, (last + 1) * width:(last + 1 + frames) * width]
+        2 * (frames + 1) * width, last dimension contiguous): what the reference re-concatenates from its deque every step.
+        The view of a step stays intact during the NEXT step (the ring's spare slot), not longer."""
+        last = (self._hist_count - 1) % (frames + 1)
+        return self._buf[name][:, (last + 2) * width:(last + 2 + frames) * width]
 
     @property
     def obs_history(self) -> torch.Tensor:
@@ -524,11 +525,12 @@ class B200Simulator:
     def _load_stack(self, name: str, frames: int, width: int, window) -> None:
         """Put a [N, frames * width] window (oldest frame first) into the ring at the current position."""
         win = torch.from_numpy(np.ascontiguousarray(np.asarray(window, np.float32))).to(self._tdev).reshape(self._num_envs, frames, width)
-        ring = self._buf[name].view(self._num_envs, 2 * frames, width)
+        M = frames + 1
+        ring = self._buf[name].view(self._num_envs, 2 * M, width)
         for i in range(frames):
-            slot = (self._hist_count - frames + i) % frames
+            slot = (self._hist_count - frames + i) % M
             ring[:, slot] = win[:, i]
-            ring[:, slot + frames] = win[:, i]
+            ring[:, slot + M] = win[:, i]
 
     # ------------------------------------------------------------------ state snapshots (tests, checkpointing)
     def load_state(self, st: dict) -> None:

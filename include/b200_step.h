@@ -231,10 +231,11 @@ typedef struct B200Buffers {
     /* outputs */
     float *obs_buf;             /* [N,num_obs]   */
     float *privileged_obs_buf;  /* [N,num_priv]  */
-    float *obs_history;         /* [N, 2*frame_stack, num_obs]   frame stack as a double-written ring: the frame of observation step t sits in
-                                   slots t mod K and t mod K + K, so the K most recent frames (oldest first: the tensor the reference
-                                   concatenates from its deque, legged_robot_ts.py:29-47) are the contiguous slots [t mod K + 1, t mod K + K] */
-    float *critic_obs;          /* [N, 2*c_frame_stack, single_critic]   same, for the critic stack */
+    float *obs_history;         /* [N, 2*(frame_stack+1), num_obs]   frame stack as a double-written ring of period M = K + 1: the frame of
+                                   observation step t sits in slots t mod M and t mod M + M, so the K most recent frames (oldest first: the
+                                   tensor the reference concatenates from its deque, legged_robot_ts.py:29-47) are the contiguous slots
+                                   [t mod M + 2, t mod M + M]; the spare slot keeps the window of step t intact while step t + 1 writes */
+    float *critic_obs;          /* [N, 2*(c_frame_stack+1), single_critic]   same, for the critic stack */
     float *rew_buf;             /* [N] */
     uint8_t *reset_buf;         /* [N] uint8 (torch.bool storage) */
     uint8_t *time_out_buf;      /* [N] uint8 */
@@ -298,7 +299,7 @@ int b200_set_side_stream(B200Handle *h, int enabled);
 /* Fused post_physics_step. `step_counter` is LeggedRobot.common_step_counter *after* its increment;
  * `cmd_vx_lo/span` is the (curriculum-mutable) lin_vel_x command range as (lower, fp32(upper-lower)); `hist_step` is the number of
  * observation frames appended to the frame stacks so far (the caller counts the calls that ran PHASE_OBSERVE): this call's
- * frame goes to ring slots hist_step mod K and hist_step mod K + K of B200Buffers.obs_history / critic_obs. */
+ * frame goes to ring slots hist_step mod (K + 1) and hist_step mod (K + 1) + K + 1 of B200Buffers.obs_history / critic_obs. */
 int b200_env_post_step(B200Handle *h, long long step_counter, float cmd_vx_lo, float cmd_vx_span, long long hist_step,
                        int phase_mask, void *cuda_stream);
 
@@ -310,6 +311,30 @@ int b200_env_post_step(B200Handle *h, long long step_counter, float cmd_vx_lo, f
  * This is the call the rollout loop makes (on_policy_runner.py:118-139: env.step(actions) followed by host reads). */
 int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long long step_counter, float cmd_vx_lo, float cmd_vx_span,
                   long long hist_step, float *host_rew, uint8_t *host_reset, uint8_t *host_time_out, void *cuda_stream);
+
+/* Rollout-side fusion: where the NEXT fused post step (b200_env_post_step with PHASE_ALL / b200_env_step)
+ * additionally writes its results, so that the runner's per-step copies disappear:
+ *   rsl_rl/storage/rollout_storage.py:89-103   add_transitions: observations[t+1] / privileged_observations[t+1] <- obs, rewards[t],
+ *                                              dones[t] -- the env kernel stores straight into those slabs;
+ *   rsl_rl/algorithms/ppo.py:103-116           process_env_step: rewards += gamma * values * time_outs (bootstrapping on time-outs),
+ *                                              applied in the kernel when `values` is given;
+ *   rsl_rl/runners/on_policy_runner.py:127-136 per-step .cpu().numpy().tolist() episode book-keeping -> device counters:
+ *                                              ep_return[env] += rew, ep_length[env] += 1; an env that resets adds both to
+ *                                              ep_stats[0], ep_stats[1] and 1 to ep_stats[2], then restarts at zero.
+ * All pointers are device pointers (any may be NULL); the targets apply to ONE step and are cleared by it. */
+typedef struct B200RolloutTargets {
+    float *obs;            /* [N, num_obs]   e.g. storage.observations[t + 1]           */
+    float *privileged_obs; /* [N, num_priv]  e.g. storage.privileged_observations[t + 1] (estimator labels for the EE / DreamWaQ tasks) */
+    float *next_state;     /* [N, num_obs]   go2_dreamwaq decoder target (next_state_buf), else NULL */
+    float *rewards;        /* [N]            e.g. storage.rewards[t] ([N,1] contiguous)  */
+    uint8_t *dones;        /* [N] uint8      e.g. storage.dones[t]                       */
+    const float *values;   /* [N] critic values of the acting step (bootstrapping), or NULL */
+    float gamma;
+    float *ep_return;      /* [N] running return of the current episode   */
+    float *ep_length;      /* [N] running length of the current episode   */
+    float *ep_stats;       /* [3] sum of returns, sum of lengths, count of the episodes that ended (caller zeroes it when read) */
+} B200RolloutTargets;
+int b200_set_rollout_targets(B200Handle *h, const B200RolloutTargets *targets);
 
 /* Per-step host scalars for the next b200_env_post_step / b200_reset_all: `sit_pose` != 0 -> envs that reset in that
  * call start in the sit pose (tron1_pf_ee.py:204-210 draws ONE coin per reset batch). */

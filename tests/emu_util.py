@@ -77,16 +77,17 @@ class EmuSim:
     def _load_stack(self, name, window):
         K, W = self._stack(name)
         win = np.asarray(window, np.float32).reshape(self.N, K, W)
-        ring = self.buf[name].reshape(self.N, 2 * K, W)
+        M = K + 1
+        ring = self.buf[name].reshape(self.N, 2 * M, W)
         for i in range(K):
-            slot = (self.hist_count - K + i) % K
+            slot = (self.hist_count - K + i) % M
             ring[:, slot] = win[:, i]
-            ring[:, slot + K] = win[:, i]
+            ring[:, slot + M] = win[:, i]
 
     def _window(self, name):
         K, W = self._stack(name)
-        last = (self.hist_count - 1) % K
-        return self.buf[name][:, (last + 1) * W:(last + 1 + K) * W]
+        last = (self.hist_count - 1) % (K + 1)
+        return self.buf[name][:, (last + 2) * W:(last + 2 + K) * W]
 
     def load_state(self, st):
         alias = {"q": "dof_pos", "qd": "dof_vel"}

@@ -79,9 +79,12 @@ def test_frame_stack_views_are_strided_windows_of_the_rings():
     for _ in range(7):
         env.step(torch.randn(64, 12, device="cuda"))
         h, c = env.obs_history, env.critic_obs_buf
-        assert h.shape == (64, 900) and c.shape == (64, 885) and h.stride() == (1800, 1) and c.stride() == (1770, 1)
+        assert h.shape == (64, 900) and c.shape == (64, 885) and h.stride() == (2 * 21 * 45, 1) and c.stride() == (2 * 6 * 177, 1)
         assert h.untyped_storage().data_ptr() == env.simulator._buf["obs_history"].untyped_storage().data_ptr()
         assert torch.equal(h[:, -45:], env.obs_buf)                      # newest frame last (legged_robot_ts.py:41-47)
+        if _ > 0:                                                        # the views of the previous step are still intact (ring's spare slot)
+            assert torch.equal(prev[0], prev[1]) and torch.equal(prev[2], prev[3])
+        prev = (h, h.clone(), c, c.clone())
         w = torch.nn.Linear(900, 8, device="cuda")
         assert torch.allclose(w(h), w(h.contiguous()), atol=1e-5)         # a strided batch feeds nn.Linear as it is
 

@@ -55,7 +55,7 @@ def test_pack_task_and_buffers(task):
     assert shapes["obs_buf"][0] == (64, 45)
     if task == "go2_ts":
         assert w == dict(obs=45, priv=99, single_critic=177, hist=900, critic=885)        # SURVEY Appendix A (as run)
-        assert shapes["obs_history"][0] == (64, 2 * 900) and shapes["critic_obs"][0] == (64, 2 * 885)      # double-written rings
+        assert shapes["obs_history"][0] == (64, 2 * 21 * 45) and shapes["critic_obs"][0] == (64, 2 * 6 * 177)      # double-written rings, period K + 1
         assert i[H["TI_RESAMPLE_INTERVAL"]] == 500 and i[H["TI_PUSH_INTERVAL"]] == 500
     else:
         assert i[H["TI_PUSH_INTERVAL"]] == 750 and list(i[H["TI_TERM_LINKS"]:H["TI_TERM_LINKS"] + 1]) == [0]
