@@ -208,7 +208,8 @@ inline EnvStageTab env_stage_table(const TaskDev &T, const B200Buffers &B, int n
 // CTAs) the CTA's shared-memory slab that TMA filled with row = warp -- one exposed DRAM latency per CTA instead of one
 // per dependent load.  All stores go to B (global memory).
 template <class S>
-__device__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const EnvInputs &R, const int row, const TerrainDev &tr,
+// Must inline: it takes the kernel parameters by reference (an out-of-line call would copy them to the stack).
+__device__ __forceinline__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const EnvInputs &R, const int row, const TerrainDev &tr,
                                    const EnvCall &call, float *es, int env, int lane, bool staged, bool cta_sync, uint64_t *bar) {
     const float *tf = T.f;
     const TiView<S> ti{T.i};
