@@ -73,8 +73,10 @@ struct EnvCall {
     float inv_episode_length_s, inv_num_envs, inv_teacher, inv_student;
 };
 
-// shared memory per CTA: mbarrier + per warp (scratch, staged input rows)
-__host__ __device__ inline int env_smem_bytes(int warps) { return 16 + warps * (ES_TOTAL + ENV_IN_WORDS) * 4; }
+// shared memory per CTA: header (mbarrier, last-CTA flag, the CTA's every-env statistics) + per warp (scratch, staged input rows)
+#define ENV_HDR_WORDS 8             // [0,1] mbarrier  [2] last-CTA flag  [4] sum of terrain levels  [5] of the teacher envs  [6] sum of cstr_prob
+#define ENV_HDR_ACC 4
+__host__ __device__ inline int env_smem_bytes(int warps) { return ENV_HDR_WORDS * 4 + warps * (ES_TOTAL + ENV_IN_WORDS) * 4; }
 
 // quat_rotate_inverse (math_utils.py:63-76), q = xyzw
 __device__ __forceinline__ f3 rot_inv(float qx, float qy, float qz, float qw, f3 v) {
@@ -209,8 +211,9 @@ inline EnvStageTab env_stage_table(const TaskDev &T, const B200Buffers &B, int n
 // per dependent load.  All stores go to B (global memory).
 template <class S>
 // Must inline: it takes the kernel parameters by reference (an out-of-line call would copy them to the stack).
-__device__ __forceinline__ void env_post_step_warp(const TaskDev &T, const B200Buffers &B, const EnvInputs &R, const int row, const TerrainDev &tr,
-                                   const EnvCall &call, float *es, int env, int lane, bool staged, bool cta_sync, uint64_t *bar) {
+// Returns (thread 0 of a CTA-synchronous CTA only) the finalize ticket the CTA took once its statistics were out, else -1.
+__device__ __forceinline__ int env_post_step_warp(const TaskDev &T, const B200Buffers &B, const EnvInputs &R, const int row, const TerrainDev &tr,
+                                   const EnvCall &call, float *es, int env, int lane, bool staged, bool cta_sync, uint64_t *bar, float *cta_acc) {
     const float *tf = T.f;
     const TiView<S> ti{T.i};
     const int A = ti[TI_A], F = ti[TI_F], L = ti[TI_L], P = ti[TI_PX] * ti[TI_PY];
@@ -472,7 +475,7 @@ __device__ __forceinline__ void env_post_step_warp(const TaskDev &T, const B200B
             if (cv[k]) cprob = fmaxf(cprob, cp[k]);
             if (lane == cbase + k && cv[k]) my_sum = __fadd_rn(my_sum, 1.0f);
         }
-        if (lane == 0) { B.cstr_prob[env] = cprob; atomicAdd(B.stats + n_sums + 2, cprob); }
+        if (lane == 0) { B.cstr_prob[env] = cprob; if (cta_sync) atomicAdd(cta_acc + 2, cprob); else atomicAdd(B.stats + n_sums + 2, cprob); }
     }
     if (pm & PHASE_REWARD) {
         const float small_cmd = norm3_rn(cmd0, cmd1, cmd2) < 0.1f ? 1.f : 0.f;
@@ -749,9 +752,11 @@ __device__ __forceinline__ void env_post_step_warp(const TaskDev &T, const B200B
         ep_len = 0; fail_cnt = 0;
     }
     if ((pm & PHASE_RESET) && ti[TI_TERRAIN_CURRICULUM] && !call.force_reset && lane == 0)
-        {   // terrain_level means of extras["episode"] (all envs; go2_cts: teacher envs separately, go2_cts.py:93-99)
-            atomicAdd(B.stats + n_sums + 1, (float)new_level);
-            if (env + ti[TI_ENV_OFFSET] < ti[TI_NUM_TEACHER]) atomicAdd(B.stats + n_sums + 3, (float)new_level);
+        {   // terrain_level means of extras["episode"] (all envs; go2_cts: teacher envs separately, go2_cts.py:93-99): every env
+            // contributes every step, so a CTA-synchronous CTA adds them up on chip first (one global reduction per CTA below)
+            const bool teacher = env + ti[TI_ENV_OFFSET] < ti[TI_NUM_TEACHER];
+            if (cta_sync) { atomicAdd(cta_acc, (float)new_level); if (teacher) atomicAdd(cta_acc + 1, (float)new_level); }
+            else { atomicAdd(B.stats + n_sums + 1, (float)new_level); if (teacher) atomicAdd(B.stats + n_sums + 3, (float)new_level); }
         }
     // ---- write back the small per-env state
     if (pm & (PHASE_CALLBACK | PHASE_RESET)) {
@@ -782,6 +787,18 @@ __device__ __forceinline__ void env_post_step_warp(const TaskDev &T, const B200B
     __syncwarp();   // DR parameters written above are re-read below by other lanes
 
     ENV_SECTION_SYNC();
+    // Every reduction extras["episode"] needs has been issued by now.  A CTA-synchronous CTA publishes its on-chip sums and
+    // takes its finalize ticket HERE: the fence only has the small state stores above to wait for, and the ticket's round
+    // trip runs under the observation phase instead of at the kernel's end, where every CTA of the (single) wave would
+    // queue up behind 4 k same-address reductions (ncu: 20 % of the warp time sat at that fence and the barrier after it).
+    int ticket = -1;
+    if (cta_sync && call.finalize && threadIdx.x == 0) {
+        if (cta_acc[0] != 0.f) atomicAdd(B.stats + n_sums + 1, cta_acc[0]);
+        if (cta_acc[1] != 0.f) atomicAdd(B.stats + n_sums + 3, cta_acc[1]);
+        if (cta_acc[2] != 0.f) atomicAdd(B.stats + n_sums + 2, cta_acc[2]);
+        __threadfence();                                        // cumulative: orders the whole CTA's reductions (barrier above)
+        ticket = atomicAdd(B.global_flags + 1, 1);
+    }
     // ================================================================== compute_observations
     if (pm & PHASE_OBSERVE) {
         const int NO = ti[TI_NUM_OBS];
@@ -994,6 +1011,7 @@ __device__ __forceinline__ void env_post_step_warp(const TaskDev &T, const B200B
         }
         if (fl) { float *lv = B.last_feet_vel + (env * F + lane) * 3; lv[0] = fvel.x; lv[1] = fvel.y; lv[2] = fvel.z; }
     }
+    return ticket;
 }
 
 // Bug-compatible mode only (TaskSpec.reproduce_r18; never on the default path): the reference indexes per-env
@@ -1051,6 +1069,17 @@ __device__ __forceinline__ void stats_finalize(float *stats, int n_sums, const E
     if (i == n_sums + 2) ring[i] = (__ldcg(stats + n_sums + 1) - __ldcg(stats + n_sums + 3)) * call.inv_student;  // go2_cts: student terrain level
 }
 
+// A CTA that took its ticket early (env_post_step_warp): its first warp finalises if the ticket was the last one.  No CTA
+// barrier, no fence unless last -- the other warps just leave.
+__device__ __forceinline__ void env_finalize_ticket(const B200Buffers &B, int n_sums, const EnvCall &call, int ticket) {
+    if (threadIdx.x >= 32) return;
+    const bool last = __shfl_sync(B200_FULL_MASK, ticket, 0) == (int)gridDim.x - 1;
+    if (!last) return;
+    __threadfence();
+    for (int i = (int)threadIdx.x; i < n_sums + B200_STATS_EXTRA; i += 32) stats_finalize(B.stats, n_sums, call, i);
+    if (threadIdx.x == 0) B.global_flags[1] = 0;
+}
+
 // The CTA that takes the last ticket sees every CTA's reductions (fence + atomic) and finalises them.  Called by every
 // thread of every CTA; `last` is one shared-memory word nobody else uses at this point.
 __device__ __forceinline__ void env_finalize_cta(const B200Buffers &B, int n_sums, const EnvCall &call, int *last) {
@@ -1076,12 +1105,12 @@ __device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200B
     const int env0 = blockIdx.x * nwarps, env = env0 + warp;
     const int N = ti[TI_NUM_ENVS];
     uint64_t *bar = (uint64_t *)smem;
-    float *es = smem + 4;
+    float *es = smem + ENV_HDR_WORDS, *cta_acc = smem + ENV_HDR_ACC;
     char *inslab = (char *)(es + nwarps * ES_TOTAL);
     const bool full = !call.force_reset && (call.phase_mask & PHASE_ALL) == PHASE_ALL;
     const bool staged = full && tab.ok && env0 + nwarps <= N;
     if (staged) {
-        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_expect_tx(bar, tab.in_bytes); }
+        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_expect_tx(bar, tab.in_bytes); cta_acc[0] = 0.f; cta_acc[1] = 0.f; cta_acc[2] = 0.f; }
         __syncthreads();                                   // barrier armed before any copy can complete on it
         // thread t issues the bulk copy of table entry t
         for (int t = (int)threadIdx.x; t < tab.n; t += (int)blockDim.x)
@@ -1095,13 +1124,19 @@ __device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200B
         R.field = o_ != ENV_NOT_STAGED ? (const type *)(inslab + o_) : B.field + (size_t)env0 * (k); t++; }
         ENV_STAGED_INPUTS(X_VIEW, ti[TI_A], ti[TI_F], ti[TI_L], ti[TI_N_SUMS])
 #undef X_VIEW
-        env_post_step_warp<S>(T, B, R, warp, tr, call, es + warp * ES_TOTAL, env, lane, true, true, bar);
+#ifndef ENV_NO_SECTION_SYNC
+        const int ticket = env_post_step_warp<S>(T, B, R, warp, tr, call, es + warp * ES_TOTAL, env, lane, true, true, bar, cta_acc);
+        if (call.finalize) env_finalize_ticket(B, ti[TI_N_SUMS], call, ticket);
+        return;
+#else
+        env_post_step_warp<S>(T, B, R, warp, tr, call, es + warp * ES_TOTAL, env, lane, true, false, bar, cta_acc);
+#endif
     } else if (env < N) {
         EnvInputs R;
 #define X_VIEW(field, type, k) R.field = B.field;
         ENV_STAGED_INPUTS(X_VIEW, 0, 0, 0, 0)
 #undef X_VIEW
-        env_post_step_warp<S>(T, B, R, env, tr, call, es + warp * ES_TOTAL, env, lane, false, false, bar);
+        env_post_step_warp<S>(T, B, R, env, tr, call, es + warp * ES_TOTAL, env, lane, false, false, bar, cta_acc);
     }
     if (call.finalize) env_finalize_cta(B, ti[TI_N_SUMS], call, (int *)(smem + 2));
 }
