@@ -319,6 +319,8 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.b200_env_post_step.restype = ctypes.c_int
     lib.b200_env_step.argtypes = [vp, vp, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_longlong, vp, vp, vp, vp]
     lib.b200_env_step.restype = ctypes.c_int
+    lib.b200_env_step_device.argtypes = [vp, vp, vp, ctypes.c_double, vp]
+    lib.b200_env_step_device.restype = ctypes.c_int
     lib.b200_set_rollout_targets.argtypes = [vp, ctypes.POINTER(B200RolloutTargets)]
     lib.b200_set_rollout_targets.restype = ctypes.c_int
     lib.b200_set_step_flags.argtypes = [vp, ctypes.c_int]
@@ -346,4 +348,4 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = ["b200_create", "b200_destroy", "b200_set_terrain", "b200_bind_buffers", "b200_dynamics_step", "b200_simulator_step",
                     "b200_stats_ring", "b200_device",
-                    "b200_set_side_stream", "b200_set_dynamics_order", "b200_env_post_step", "b200_env_step", "b200_set_step_flags", "b200_set_rollout_targets", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_env_kernel_variant", "b200_launch_count", "b200_last_error"]
+                    "b200_set_side_stream", "b200_set_dynamics_order", "b200_env_post_step", "b200_env_step", "b200_env_step_device", "b200_set_step_flags", "b200_set_rollout_targets", "b200_set_behavior", "b200_reset_all", "b200_kernel_info", "b200_env_kernel_variant", "b200_launch_count", "b200_last_error"]

@@ -9,7 +9,11 @@ import sys
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# translation units, compiled side by side: the C ABI with the dynamics kernels | the host-stepped env kernels | the
+# device-stepped env kernels (b200_env_step_device).  The env kernels restate torch fp32 eager arithmetic: no FMA contraction
+# beyond the explicit fmaf() calls (csrc/env_kernel.cuh).
+UNITS = [("b200_step.cu", []), ("env_kernels_host.cu", ["-fmad=false"]), ("env_kernels_dev.cu", ["-fmad=false"])]
 
 
 def sources():
@@ -24,14 +28,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: the CUDA extension cannot be built (and there is no fallback)")
     extra = os.environ.get("B200_NVCC_EXTRA", "").split()      # tuning experiments, e.g. -DDYN_MIN_BLOCKS=5
-    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", out, os.path.join(_CSRC, "b200_step.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
+    objdir = os.path.join(_PKG, "_build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = [os.path.join(objdir, u.replace(".cu", ".o")) for u, _ in UNITS]
+    cmds = [[nvcc] + NVCC_FLAGS + fl + extra + ["-c", "-o", o, os.path.join(_CSRC, u)] for (u, fl), o in zip(UNITS, objs)]
+    procs = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for c in cmds]
+    log, failed = "", False
+    for c, p in zip(cmds, procs):
+        o, _ = p.communicate()
+        log += " ".join(c) + "\n" + o
+        failed = failed or p.returncode != 0
+    if not failed:
+        link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs
+        res = subprocess.run(link, capture_output=True, text=True)
+        log += " ".join(link) + "\n" + res.stdout + res.stderr
+        failed = res.returncode != 0
     with open(os.path.join(_PKG, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if verbose or res.returncode != 0:
+        f.write(log)
+    if verbose or failed:
         print(log)
-    if res.returncode != 0:
+    if failed:
         raise RuntimeError("nvcc failed, see hcr_genesis_lr_cl_b200/build.log")
     return out
 

@@ -4,6 +4,7 @@
 // for the CUDA runtime, so that the host layers above the C ABI can be tested in a container without a GPU.
 #ifdef B200_WARP_EMU
 #include "cuda_shim.h"
+#define B200_ENV_DEFINE_KERNELS
 #define B200_LAUNCH(kern, grid, block, smem, stream, ...) emu_launch_fn([&] { kern(__VA_ARGS__); }, (int)dim3(grid).x, (int)dim3(grid).y)
 #else
 #include <cuda_runtime.h>
@@ -66,15 +67,6 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-typedef void (*EnvKernelFn)(const TaskDev, const B200Buffers, const TerrainDev, const EnvCall, const EnvStageTab);
-static EnvKernelFn env_kernel_fn(int preset) {
-    switch (preset) {
-#define X_CASE(P) case P: return env_post_step_kernel_preset<P>;
-        ENV_FOR_EACH_PRESET(X_CASE)
-#undef X_CASE
-    default: return env_post_step_kernel;
-    }
-}
 
 extern "C" {
 
@@ -112,7 +104,10 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
         const char *o = getenv("B200_DYN_ORDER");
         h->order_enabled = !(o && o[0] == '0');
     }
-    if (h->env_smem > 48 * 1024) CKH(cudaFuncSetAttribute(env_kernel_fn(h->env_preset), cudaFuncAttributeMaxDynamicSharedMemorySize, h->env_smem));
+    if (h->env_smem > 48 * 1024) {
+        CKH(cudaFuncSetAttribute(env_kernel_fn(h->env_preset), cudaFuncAttributeMaxDynamicSharedMemorySize, h->env_smem));
+        CKH(cudaFuncSetAttribute(env_kernel_dev_fn(h->env_preset), cudaFuncAttributeMaxDynamicSharedMemorySize, h->env_smem));
+    }
     CKH(cudaFuncSetAttribute(dynamics_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
     CKH(cudaFuncSetAttribute(dynamics_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->dyn_smem));
 #undef CKH
@@ -237,10 +232,12 @@ static EnvCall make_call(B200Handle *h, long long step, float lo, float span, lo
     call.inv_num_envs = 1.0f / (float)N;
     call.inv_teacher = h->task.i[TI_NUM_TEACHER] > 0 ? 1.0f / (float)max(n_teach, 1) : 0.f;
     call.inv_student = 1.0f / (float)max(N - n_teach, 1);
+    call.dstate = nullptr;
     return call;
 }
 
-static int launch_env(B200Handle *h, long long step, float lo, float span, long long hist_step, int mask, int force, void *stream) {
+static int launch_env(B200Handle *h, long long step, float lo, float span, long long hist_step, int mask, int force, void *stream,
+                      const int32_t *dstate = nullptr) {
     DeviceGuard guard(h);
     const int N = h->task.i[TI_NUM_ENVS];
     const int n_sums = h->task.i[TI_N_SUMS];
@@ -248,6 +245,7 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, long 
     if ((mask & PHASE_RESET) && !h->stats_zeroed) CK(cudaMemsetAsync(h->bufs.stats, 0, sizeof(float) * (n_sums + 4), s));
     h->stats_zeroed = false;
     EnvCall call = make_call(h, step, lo, span, hist_step, mask, force);
+    call.dstate = dstate;
     if (h->side_pending) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->side_pending = false; }      // join the side stream
     if (h->task.i[TI_R18] && (mask & PHASE_REWARD) && !force) {      // bug-compatible mode only: the "any env" bits row 0 follows (R18)
         B200_LAUNCH(r18_flags_kernel, dim3((N + R18_FLAGS_BLOCK - 1) / R18_FLAGS_BLOCK), R18_FLAGS_BLOCK, 0, s, h->task, h->bufs, call);
@@ -255,7 +253,7 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, long 
         CK(cudaGetLastError());
     }
     const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
-    B200_LAUNCH(env_kernel_fn(h->env_preset), grid, block, h->env_smem, s, h->task, h->bufs, h->terrain, call, h->stage);
+    B200_LAUNCH((dstate ? env_kernel_dev_fn(h->env_preset) : env_kernel_fn(h->env_preset)), grid, block, h->env_smem, s, h->task, h->bufs, h->terrain, call, h->stage);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -294,6 +292,23 @@ int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long
         if (host_time_out) CK(cudaMemcpyAsync(host_time_out, h->bufs.time_out_buf, (size_t)N, cudaMemcpyDeviceToHost, s));
     }
     return 0;
+}
+
+int b200_env_step_device(B200Handle *h, const float *actions, int32_t *ss, double sit_init_percent, void *stream) {
+    if (check_ready(h, "b200_env_step_device")) return 1;
+    if (!actions || !ss) return fail("b200_env_step_device: null argument");
+    if (h->task.i[TI_R18]) return fail("b200_env_step_device: the bug-compatible R18 mode needs host-stepped calls");
+    DeviceGuard guard(h);
+    // host: coin < p, coin = k * 2^-24  <=>  k < ceil(p * 2^24)
+    double thr = sit_init_percent > 0.0 ? sit_init_percent * 16777216.0 : 0.0;
+    uint32_t thr_q = (uint32_t)thr; if ((double)thr_q < thr) thr_q++;
+    if (thr_q > 16777216u) thr_q = 16777216u;
+    B200_LAUNCH(step_advance_kernel, 1, 32, 0, (cudaStream_t)stream, ss, (uint32_t)h->task.i[TI_SEED_LO], (uint32_t)h->task.i[TI_SEED_HI], thr_q,
+                h->task.i[TI_BEHAVIOR], (int)SITE_HOST);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (launch_dynamics(h, actions, stream, 0)) return 1;
+    return launch_env(h, 0, 0.f, 0.f, 0, PHASE_ALL, 0, stream, ss);
 }
 
 int b200_set_rollout_targets(B200Handle *h, const B200RolloutTargets *t) {
@@ -362,3 +377,8 @@ int b200_debug_dyn_timing(unsigned long long *out, int n_envs) {
 #endif
 
 }  // extern "C"
+
+#ifdef B200_WARP_EMU
+#include "env_kernels_host.cu"
+#include "env_kernels_dev.cu"
+#endif

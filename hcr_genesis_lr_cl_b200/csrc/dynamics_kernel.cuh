@@ -22,8 +22,7 @@
 //   * per-warp scratch (frames, M^-1 factors, J rows, A) is staged in shared memory, the robot model once per CTA.
 // The kernel is latency/issue bound, not HBM bound; tensor cores do not apply.
 #pragma once
-#include "cuda_compat.cuh"
-#include "../../include/b200_step.h"
+#include "task_dev.cuh"
 
 #ifndef DYN_WARPS_PER_BLOCK
 #define DYN_WARPS_PER_BLOCK 7
@@ -51,26 +50,6 @@
 #ifndef DYN_MIN_BLOCKS
 #define DYN_MIN_BLOCKS 4      // resident CTAs per SM the register allocator must allow: 4 x 7 warps = 28 envs per SM at 72 regs/thread
 #endif
-
-struct TaskDev {
-    float f[TF_COUNT];
-    int i[TI_COUNT];
-};
-
-struct ModelDev {          // device pointers to the packed robot model (see robot_model.py)
-    const float *body;     // [nb][20]
-    const float *link_off; // [nlinks][3]
-    const float *sph;      // [nspheres][4]
-    const int *link_body;  // [nlinks]
-    const int *sph_body;   // [nspheres]
-    const int *sph_link;   // [nspheres]
-};
-
-struct TerrainDev {
-    const int16_t *hf;     // [rows][cols] or nullptr (plane)
-    const float *origins;  // [levels][types][3]
-    int rows, cols, levels, types;
-};
 
 // ---- per-warp shared scratch (floats) ----
 // The frames / joint axes / body velocities / contact list / aux rows are consumed by the time the constraint rows are

@@ -22,7 +22,7 @@
 #pragma once
 #include "cuda_compat.cuh"
 #include "philox.cuh"
-#include "dynamics_kernel.cuh"   // TaskDev, TerrainDev
+#include "task_dev.cuh"          // TaskDev, TerrainDev
 #include "env_presets.inc"       // generated: the int descriptor of every built-in task preset as compile-time tables
 
 // The kernel is instantiated once per built-in preset with the structural ints of the task descriptor (widths, link
@@ -71,7 +71,34 @@ struct EnvCall {
     // extras["episode"] means: the last CTA to finish turns the per-step reductions into ring slot `stats_slot`
     int finalize, stats_slot;
     float inv_episode_length_s, inv_num_envs, inv_teacher, inv_student;
+    // Device-stepped launches (b200_env_step_device): the per-step scalars above -- step, hist_step, vx_lo / vx_span, beh[],
+    // sit_pose, gait_cb / gait_reset, stats_slot -- are NOT taken from this struct but from the device-resident step state
+    // (include/b200_step.h, B200_SS_*) that step_advance_kernel moved forward just before, so that a captured CUDA graph of
+    // the step can be replayed without any per-launch parameter from the host.  NULL for host-stepped launches.
+    const int32_t *dstate;
 };
+
+// The device-resident step state one policy step further (b200_env_step_device launches it ahead of the dynamics kernel):
+// the counters, and the scalars the host would have drawn for this step from the Philox stream of env id 0xFFFFFFFF
+// (host_rng.py: the sit-pose coin of tron1_pf_ee.py:204-210 and the two gait indices of go2_wtw.py:205-206), compared in
+// integers exactly like the host compares its doubles.
+#ifdef B200_ENV_DEFINE_KERNELS
+__global__ void step_advance_kernel(int32_t *ss, uint32_t k0, uint32_t k1, uint32_t sit_threshold_q24, int behavior, int site_host) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t step = (uint32_t)ss[B200_SS_STEP] + 1u;
+    ss[B200_SS_STEP] = (int32_t)step;
+    ss[B200_SS_HIST_STEP] = ss[B200_SS_HIST_STEP] + 1;
+    const Philox4 p = philox4x32_10(0xFFFFFFFFu, step, (uint32_t)site_host, 0u, k0, k1);
+    ss[B200_SS_SIT_POSE] = (sit_threshold_q24 != 0u && (p.w[0] >> 8) < sit_threshold_q24) ? 1 : 0;
+    if (behavior) {
+        const uint32_t ng = (uint32_t)max(ss[B200_SS_NUM_GAITS], 1);
+        ss[B200_SS_GAIT_CB] = (int32_t)min((uint32_t)(((uint64_t)(p.w[1] >> 8) * ng) >> 24), ng - 1u);
+        ss[B200_SS_GAIT_RESET] = (int32_t)min((uint32_t)(((uint64_t)(p.w[2] >> 8) * ng) >> 24), ng - 1u);
+    }
+}
+#else
+__global__ void step_advance_kernel(int32_t *ss, uint32_t k0, uint32_t k1, uint32_t sit_threshold_q24, int behavior, int site_host);
+#endif   // B200_ENV_DEFINE_KERNELS
 
 // shared memory per CTA: header (mbarrier, last-CTA flag, the CTA's every-env statistics) + per warp (scratch, staged input rows)
 #define ENV_HDR_WORDS 8             // [0,1] mbarrier  [2] last-CTA flag  [4] sum of terrain levels  [5] of the teacher envs  [6] sum of cstr_prob
@@ -1024,6 +1051,7 @@ __device__ __forceinline__ int env_post_step_warp(const TaskDev &T, const B200Bu
 #else
 #define R18_FLAGS_BLOCK 128
 #endif
+#ifdef B200_ENV_DEFINE_KERNELS
 __global__ void r18_flags_kernel(const TaskDev T, const B200Buffers B, const EnvCall call) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     int bits = 0;
@@ -1051,6 +1079,9 @@ __global__ void r18_flags_kernel(const TaskDev T, const B200Buffers B, const Env
         if ((threadIdx.x & 31) == 0) atomicOr(B.global_flags, bits << 8);
     }
 }
+#else
+__global__ void r18_flags_kernel(const TaskDev T, const B200Buffers B, const EnvCall call);
+#endif   // B200_ENV_DEFINE_KERNELS
 
 // extras["episode"] (legged_robot.py:127-141): means over the envs that reset this step, from the reductions the env
 // kernel left in stats[0..n_sums] (+ reset count, + sum of terrain levels); written to slot (step % ENV_STATS_RING) of
@@ -1067,6 +1098,7 @@ __device__ __forceinline__ void stats_finalize(float *stats, int n_sums, const E
     if (i == n_sums + 1) ring[i] = call.inv_teacher > 0.f ? __ldcg(stats + n_sums + 3) * call.inv_teacher     // go2_cts: teacher terrain level
                                                           : __ldcg(stats + n_sums + 2) * call.inv_num_envs;   // mean CaT termination probability
     if (i == n_sums + 2) ring[i] = (__ldcg(stats + n_sums + 1) - __ldcg(stats + n_sums + 3)) * call.inv_student;  // go2_cts: student terrain level
+    if (i == n_sums + 3) ring[i] = cnt;                                                   // envs that reset this step (0: the rew_* entries are carried over)
 }
 
 // A CTA that took its ticket early (env_post_step_warp): its first warp finalises if the ticket was the last one.  No CTA
@@ -1097,7 +1129,7 @@ __device__ __forceinline__ void env_finalize_cta(const B200Buffers &B, int n_sum
 }
 
 template <class S>
-__device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const EnvCall &call, const EnvStageTab &tab) {
+__device__ __forceinline__ void env_post_step_body_impl(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const EnvCall &call, const EnvStageTab &tab) {
     extern __shared__ float smem[];
     const TiView<S> ti{T.i};
     constexpr int nwarps = ENV_WARPS_PER_BLOCK;            // the launch geometry is fixed: slab offsets fold to constants
@@ -1141,18 +1173,48 @@ __device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200B
     if (call.finalize) env_finalize_cta(B, ti[TI_N_SUMS], call, (int *)(smem + 2));
 }
 
+// DEV: a device-stepped launch.  The per-step scalars come from the step state in device memory (EnvCall::dstate) -- four
+// uniform 16-byte loads per thread -- into a private copy of the call; the host-stepped instantiations read the kernel
+// parameter where it lies (constant bank operands, no registers), which is why the two are separate instantiations.
+template <class S, bool DEV>
+__device__ __forceinline__ void env_post_step_body(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const EnvCall &call_in, const EnvStageTab &tab) {
+    if constexpr (DEV) {
+        EnvCall call = call_in;
+        const int4 *ss = (const int4 *)call_in.dstate;
+        const int4 a = __ldg(ss), b = __ldg(ss + 1), c = __ldg(ss + 2), d = __ldg(ss + 3);
+        call.step = (uint32_t)a.x; call.hist_step = (uint32_t)a.y - 1u;     // [1] already counts this call's frame
+        call.vx_lo = __int_as_float(a.z); call.vx_span = __int_as_float(a.w);
+        call.beh[0] = __int_as_float(b.x); call.beh[1] = __int_as_float(b.y); call.beh[2] = __int_as_float(b.z); call.beh[3] = __int_as_float(b.w);
+        call.beh[4] = __int_as_float(c.x); call.beh[5] = __int_as_float(c.y); call.beh[6] = __int_as_float(c.z); call.beh[7] = __int_as_float(c.w);
+        call.sit_pose = d.x; call.gait_cb = d.y; call.gait_reset = d.z;
+        call.stats_slot = (int)(call.step % (uint32_t)ENV_STATS_RING);
+        env_post_step_body_impl<S>(T, B, tr, call, tab);
+    } else {
+        env_post_step_body_impl<S>(T, B, tr, call_in, tab);
+    }
+}
+
 // generic instantiation: every descriptor int is read at run time (any task configuration)
+template <bool DEV>
 __global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, ENV_MIN_BLOCKS)
 env_post_step_kernel(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call, const EnvStageTab tab) {
-    env_post_step_body<EnvSpecGeneric>(T, B, tr, call, tab);
+    env_post_step_body<EnvSpecGeneric, DEV>(T, B, tr, call, tab);
 }
 
 // one instantiation per built-in preset (env_presets.inc); selected by b200_create when the descriptor matches the table
-template <int P>
+template <int P, bool DEV>
 __global__ void B200_LAUNCH_BOUNDS(ENV_WARPS_PER_BLOCK * 32, ENV_MIN_BLOCKS)
 env_post_step_kernel_preset(const TaskDev T, const B200Buffers B, const TerrainDev tr, const EnvCall call, const EnvStageTab tab) {
-    env_post_step_body<EnvPresetSpec<P>>(T, B, tr, call, tab);
+    env_post_step_body<EnvPresetSpec<P>, DEV>(T, B, tr, call, tab);
 }
+
+typedef void (*EnvKernelFn)(const TaskDev, const B200Buffers, const TerrainDev, const EnvCall, const EnvStageTab);
+// The instantiations live in translation units of their own, compiled beside b200_step.cu and with -fmad=false: the env half
+// restates torch fp32 eager arithmetic, where every operation rounds on its own -- left to ptxas, which fuses FMUL + FADD
+// where its schedule likes it, two instantiations of the same source (preset / generic, host- / device-stepped) differ in the
+// last bit of a reward.  (fmaf() calls stay fused; the dynamics kernel keeps contraction.)
+EnvKernelFn env_kernel_fn(int preset);        // csrc/env_kernels_host.cu (+ r18_flags_kernel, step_advance_kernel)
+EnvKernelFn env_kernel_dev_fn(int preset);    // csrc/env_kernels_dev.cu
 
 // index of the preset whose compile-time ints all equal this descriptor's, or -1 (-> generic kernel)
 inline int env_match_preset(const int *ti) {

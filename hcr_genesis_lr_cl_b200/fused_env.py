@@ -223,6 +223,83 @@ class FusedLeggedEnv:
         self._fill_extras()
         return self._returns()
 
+    # ------------------------------------------------------------------ device-stepped mode (CUDA-graph capturable)
+    def sync_step_state(self) -> None:
+        """Host -> device copy of the step's host-owned scalars (step counter, command range, behaviour ranges, number of gaits):
+        call before the first `step_device` and whenever the host changed one of them (curricula)."""
+        beh = [self.gait_period_range, self.base_height_target_range, self.foot_clearance_target_range, self.pitch_target_range] \
+            if self.spec.behavior_enabled else None
+        self.simulator.write_step_state(self.common_step_counter, self.command_ranges["lin_vel_x"], beh,
+                                        self.num_gaits if self.spec.behavior_enabled else 1)
+        self._curriculum_done_to = self.common_step_counter      # curricula up to here were the host-stepped path's business
+
+    def step_device(self, actions: torch.Tensor):
+        """`step` with every per-step scalar taken from device memory (b200_env_step_device): the launches take no value from
+        the host that changes between steps, so T such steps -- with the policy's kernels in between -- can be captured into
+        ONE CUDA graph and replayed (rollout.GraphedRolloutCollector).  The host-drawn scalars of `_set_step_flags` are drawn
+        on the device from the same Philox stream; the command / behaviour curricula are NOT evaluated here (the caller
+        runs `device_steps_done` at its rollout boundaries)."""
+        if self.cat_global_allreduce and self._world_size() > 1:
+            raise RuntimeError("go2_cat with the job-wide stand-still flag needs a collective inside the step: host-stepped only")
+        self.common_step_counter += 1
+        self._set_output_targets()
+        self.simulator.fused_env_step_device(actions, self.spec.sit_init_percent)
+        self._fill_extras(curriculum=False)
+        return self._returns()
+
+    def device_steps_done(self, n_replayed: int = 0) -> None:
+        """Book-keeping after device-stepped steps: `n_replayed` steps ran on the device WITHOUT their python side (a graph
+        replay) -> move the host counters, the output ping-pong and the frame-stack position along; then apply the command /
+        behaviour curricula for every multiple of max_episode_length the window crossed (legged_robot.py:110-111, read from
+        the statistics ring: late by at most the window) and push changed ranges back to the device."""
+        if n_replayed:
+            self.common_step_counter += n_replayed
+            self.simulator._hist_count += n_replayed
+            if n_replayed % 2:
+                self._pp_i ^= 1
+            self._fill_extras(curriculum=False)
+        last = self.common_step_counter
+        L = int(self.max_episode_length)
+        done_to = getattr(self, "_curriculum_done_to", last)
+        if not (self.spec.cmd_curriculum and "tracking_lin_vel" in self.sum_names):
+            self._curriculum_done_to = last
+            return
+        changed = False
+        first = max(done_to + 1, last - self.stats_ring + 1, 1)      # older slots of the ring have been overwritten
+        for k in range((first + L - 1) // L * L, last + 1, L):
+            changed |= self._curriculum_from_ring(k)
+        self._curriculum_done_to = last
+        if changed:
+            self.sync_step_state()
+
+    def _curriculum_from_ring(self, step: int) -> bool:
+        """Command / behaviour curriculum of policy step `step` from its slot of the statistics ring (means over the envs that
+        reset in that step, and their count)."""
+        from ._cabi import STATS_RING, H
+        n = len(self.sum_names)
+        base, w = 2 * max(n, 1) + 4, n + H["B200_STATS_EXTRA"]
+        row = self._b["stats"][base + (step % STATS_RING) * w: base + (step % STATS_RING + 1) * w].clone()
+        import torch.distributed as dist
+        cnt = row[n + 3].clone()
+        sums = row[:n] * cnt                    # back to sums so that an env-sharded job can add its ranks up
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            pack = torch.cat([sums, cnt.view(1)])
+            dist.all_reduce(pack, op=dist.ReduceOp.SUM)
+            sums, cnt = pack[:n], pack[n]
+        if float(cnt) <= 0:
+            return False
+        # ring entries are sum / count / episode_length_s; the curricula compare sum / count / max_episode_length
+        means = sums / cnt * (self.max_episode_length_s / float(self.max_episode_length))
+        before = (list(self.command_ranges["lin_vel_x"]), self.num_gaits,
+                  [list(r) for r in (self.gait_period_range, self.base_height_target_range, self.foot_clearance_target_range, self.pitch_target_range)]
+                  if self.spec.behavior_enabled else None)
+        self._pending_curriculum = (means[self.sum_names.index("tracking_lin_vel")], cnt, means if self.spec.behavior_enabled else None)
+        self._apply_pending_curriculum()
+        after = (list(self.command_ranges["lin_vel_x"]), self.num_gaits,
+                 [list(r) for r in (self.gait_period_range, self.base_height_target_range, self.foot_clearance_target_range, self.pitch_target_range)]
+                 if self.spec.behavior_enabled else None)
+        return before != after
+
     def _set_step_flags(self):
         """Host scalars of the step: the sit-pose coin (one per reset batch, tron1_pf_ee.py:204-210)."""
         if self.spec.sit_init_percent > 0:
@@ -310,7 +387,7 @@ class FusedLeggedEnv:
     #: for more than `stats_ring` steps before reading (num_steps_per_env > stats_ring) must clone them at append time
     stats_ring = property(lambda self: int(self.simulator._lib.b200_stats_ring()))
 
-    def _fill_extras(self):
+    def _fill_extras(self, curriculum: bool = True):
         """extras["episode"]["rew_*"] = mean over resetting envs of episode_sums / episode_length_s
         (legged_robot.py:127-141): computed on the device by the env kernel's last CTA into slot step % 32."""
         from ._cabi import STATS_RING
@@ -328,7 +405,7 @@ class FusedLeggedEnv:
             self.extras["time_outs"] = self.time_out_buf
         # command curriculum (legged_robot.py:110-111,336-348): evaluated on the reductions of this step and applied
         # before the next one (one-step delay, DESIGN.md "deviations"); the only host read, once per max_episode_length.
-        if self.spec.cmd_curriculum and self.common_step_counter % int(self.max_episode_length) == 0 \
+        if curriculum and self.spec.cmd_curriculum and self.common_step_counter % int(self.max_episode_length) == 0 \
                 and "tracking_lin_vel" in self.sum_names:
             i = self.sum_names.index("tracking_lin_vel")
             tot = stats[:n + 1].clone()                       # episode sums of the envs that reset this step + their count

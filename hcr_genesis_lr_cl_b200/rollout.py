@@ -82,12 +82,19 @@ class FusedRolloutCollector:
             values=st.values[t].data_ptr() if self.bootstrap else None, gamma=float(self.alg.gamma),
             ep_return=self.ep_return.data_ptr(), ep_length=self.ep_length.data_ptr(), ep_stats=self.ep_stats.data_ptr())
 
+    def _env_step(self, actions):
+        self.env.step(actions)
+
     @torch.inference_mode()
     def collect(self):
         """One rollout of T policy steps into ``alg.storage``; returns the critic observation for ``alg.compute_returns``."""
-        env, alg, st, sim = self.env, self.alg, self.alg.storage, self.env.simulator
         if not self._primed:
             self.prime()
+        self._rollout()
+        return self.carry_priv if self.has_priv else self.carry_obs
+
+    def _rollout(self):
+        env, alg, st = self.env, self.alg, self.alg.storage
         st.observations[0].copy_(self.carry_obs)                     # one copy per ROLLOUT: the observation the last one ended on
         if self.has_priv:
             st.privileged_observations[0].copy_(self.carry_priv)
@@ -102,12 +109,11 @@ class FusedRolloutCollector:
             st.mu[t].copy_(tr.action_mean)
             st.sigma[t].copy_(tr.action_sigma)
             env.set_rollout_targets(self._targets(t))
-            env.step(actions)                                        # obs / priv / rewards / dones land in the slabs
+            self._env_step(actions)                                  # obs / priv / rewards / dones land in the slabs
             st.step += 1
             tr.clear()
             if alg.actor_critic.is_recurrent:
                 alg.actor_critic.reset(st.dones[t].view(-1))
-        return self.carry_priv if self.has_priv else self.carry_obs
 
     def episode_statistics(self, reset: bool = True):
         """(mean return, mean length, episodes) of the episodes that ended since the last call -- the one host read of the
@@ -117,3 +123,88 @@ class FusedRolloutCollector:
             self.ep_stats.zero_()
         n = max(s[2], 1.0)
         return s[0] / n, s[1] / n, int(s[2])
+
+
+class GraphedRolloutCollector(FusedRolloutCollector):
+    """The same rollout as ONE CUDA graph launch.
+
+    ``OnPolicyRunner.learn``'s collection loop is launch-bound in PyTorch eager mode: per policy step the actor / critic MLPs,
+    the Gaussian sampling and the storage copies are ~60 small kernels the host issues one by one, next to which the env step
+    (three launches, ~0.2 ms on the device) waits.  The env's device-stepped entry point (``FusedLeggedEnv.step_device`` ->
+    ``b200_env_step_device``) takes no per-step value from the host -- counters, the Philox step key, the frame-stack
+    position, the host-drawn gait / sit-pose scalars and the curriculum ranges live in device memory -- so the whole loop of
+    ``T`` x (``alg.act`` -> storage copies -> env step) is captured once with ``torch.cuda.graph`` and replayed per rollout.
+    Nothing but kernels is left in the replay: results are those of ``FusedRolloutCollector`` driven through ``step_device``
+    (bit-identical env side; the policy's sampling uses torch's graph-safe Philox offsets).
+
+    Restrictions: non-recurrent policies; an even ``T`` (the env's per-step rows and the dynamics kernel's scheduling buffers
+    alternate between two halves); ``alg.act`` must be capture-safe -- no host reads.  rsl_rl's own ``ActorCritic.act`` has
+    two: ``torch.distributions`` argument validation (switched off for the capture, as rsl_rl intends with its
+    ``Normal.set_default_validate_args``) and ``torch.normal(Tensor, Tensor)``'s ``std >= 0`` check behind ``Normal.sample``
+    (replaced for the capture by the arithmetic it performs, ``randn * std + mean`` on the same generator).
+    The command / behaviour curricula are applied at rollout boundaries (``FusedLeggedEnv.device_steps_done``).
+    """
+
+    def __init__(self, env: FusedLeggedEnv, alg, num_steps_per_env: Optional[int] = None, warmup_rollouts: int = 1):
+        super().__init__(env, alg, num_steps_per_env)
+        if self.T % 2:
+            raise ValueError("graphed collection needs an even number of steps per rollout")
+        if getattr(alg.actor_critic, "is_recurrent", False):
+            raise ValueError("graphed collection covers non-recurrent policies")
+        self._graph = None
+        self._warmup_left = int(warmup_rollouts)
+        self._synced = False
+
+    def _env_step(self, actions):
+        self.env.step_device(actions)
+
+    def _sync(self):
+        if not self._synced:
+            self.env.sync_step_state()
+            self._synced = True
+
+    @torch.inference_mode()
+    def collect(self):
+        env, st = self.env, self.alg.storage
+        if not self._primed:
+            self.prime()
+        self._sync()
+        if self._warmup_left > 0:
+            # eager, device-stepped: lets cuBLAS / the caching allocator / the library's side stream set themselves up outside a capture
+            self._warmup_left -= 1
+            self._rollout()
+            env.device_steps_done(0)
+        elif self._graph is None:
+            from torch.distributions import Distribution, Normal
+            prev, prev_sample = Distribution._validate_args, Normal.sample
+            Distribution.set_default_validate_args(False)
+
+            def sample(dist, sample_shape=torch.Size()):
+                # torch.normal(Tensor, Tensor) checks std >= 0 with a host read (not capturable); its arithmetic is
+                # randn * std + mean on the same generator, which is what gets captured instead
+                shape = dist._extended_shape(sample_shape)
+                with torch.no_grad():
+                    return torch.randn(shape, dtype=dist.loc.dtype, device=dist.loc.device).mul_(dist.scale.expand(shape)).add_(dist.loc.expand(shape))
+
+            Normal.sample = sample
+            try:
+                g = torch.cuda.CUDAGraph()
+                counters = (env.common_step_counter, env.simulator._hist_count, env._pp_i, st.step)
+                torch.cuda.synchronize(env.simulator._tdev)
+                with torch.cuda.graph(g):
+                    self._rollout()
+                # the capture ran the python side of T steps but no kernel: rewind the host's view and replay for real
+                env.common_step_counter, env.simulator._hist_count, env._pp_i, st.step = counters
+                self._graph = g
+            finally:
+                Distribution.set_default_validate_args(prev)
+                Normal.sample = prev_sample
+            self._replay()
+        else:
+            self._replay()
+        return self.carry_priv if self.has_priv else self.carry_obs
+
+    def _replay(self):
+        self._graph.replay()
+        self.alg.storage.step += self.T
+        self.env.device_steps_done(self.T)

@@ -357,6 +357,37 @@ class B200Simulator:
                                          host_time_out.data_ptr() if host_time_out is not None else None, self._stream()))
         self._hist_count += 1
 
+    # ---- device-stepped env.step (b200_env_step_device): per-step scalars live in device memory, the call is graph-capturable
+    @property
+    def step_state(self) -> torch.Tensor:
+        """The B200_STEP_STATE_WORDS int32 words of include/b200_step.h (B200_SS_*), on the env's device."""
+        if getattr(self, "_step_state", None) is None:
+            self._step_state = torch.zeros(H["B200_STEP_STATE_WORDS"], dtype=torch.int32, device=self._tdev)
+        return self._step_state
+
+    def write_step_state(self, step_counter: int, cmd_range_x: Sequence[float], beh_ranges=None, num_gaits: int = 1) -> None:
+        """Host -> device: the words the caller owns (counters, command range, behaviour ranges, number of gaits), with the
+        roundings b200_env_step / b200_set_behavior apply to the same values."""
+        w = np.zeros(H["B200_STEP_STATE_WORDS"], np.int32)
+        f = w.view(np.float32)
+        w[H["B200_SS_STEP"]] = np.array(int(step_counter) & 0xFFFFFFFF, np.uint32).view(np.int32)
+        w[H["B200_SS_HIST_STEP"]] = np.array(int(self._hist_count) & 0xFFFFFFFF, np.uint32).view(np.int32)
+        lo, hi = float(cmd_range_x[0]), float(cmd_range_x[1])
+        f[H["B200_SS_VX_LO"]], f[H["B200_SS_VX_SPAN"]] = np.float32(lo), np.float32(hi - lo)
+        if beh_ranges is not None:
+            for k, (a, b) in enumerate(beh_ranges):
+                f[H["B200_SS_BEH"] + 2 * k], f[H["B200_SS_BEH"] + 2 * k + 1] = np.float32(a), np.float32(float(b) - float(a))
+        w[H["B200_SS_NUM_GAITS"]] = int(num_gaits)
+        self.step_state.copy_(torch.from_numpy(w))
+
+    def fused_env_step_device(self, actions: torch.Tensor, sit_init_percent: float = 0.0) -> None:
+        """One whole env.step whose per-step scalars come from `step_state` (moved forward on the device by the call)."""
+        if not (self._on_device(actions) and actions.dtype == torch.float32 and actions.is_contiguous()):
+            raise ValueError("device-stepped env.step takes a contiguous float32 device tensor of actions")
+        self._ck(self._lib.b200_env_step_device(self._handle, actions.data_ptr(), self.step_state.data_ptr(), float(sit_init_percent),
+                                                self._stream()))
+        self._hist_count += 1
+
     def set_step_flags(self, sit_pose: bool) -> None:
         self._ck(self._lib.b200_set_step_flags(self._handle, int(bool(sit_pose))))
 

@@ -48,7 +48,7 @@ extern "C" {
 #define B200_RMAX 32       /* constraint rows = 3*KMAX + AUXMAX = one warp */
 #define B200_MAX_REWARDS 33
 #define B200_MAX_GAITS 4
-#define B200_STATS_EXTRA 3    /* per-step statistics beyond the episode sums: terrain level, cstr prob | teacher level, student level */
+#define B200_STATS_EXTRA 4    /* per-step statistics beyond the episode sums: terrain level, cstr prob | teacher level, student level, envs reset */
 #define B200_MAX_CTRL_DELAY 7 /* largest ctrl_delay_step_range[1] */
 #define B200_VM_MAX 56       /* most terms of the von Mises CDF series (kappa < 50, "smooth" gait indicator) */
 #define B200_GAIT_STATE 20   /* floats per env in gait_state */
@@ -240,11 +240,11 @@ typedef struct B200Buffers {
     uint8_t *reset_buf;         /* [N] uint8 (torch.bool storage) */
     uint8_t *time_out_buf;      /* [N] uint8 */
     int32_t *height_cells;      /* [N,P,2] int32 cell indices of the scan (diagnostic, may be NULL) */
-    float *stats;               /* [2*n_sums+4 + 32*(n_sums+1)] per-step reductions: [0,n_sums) sum over resetting envs of
+    float *stats;               /* [2*n_sums+4 + 32*(n_sums+B200_STATS_EXTRA)] per-step reductions: [0,n_sums) sum over resetting envs of
                                    episode_sums, [n_sums] count of resets, [n_sums+1] sum of terrain levels (all envs);
-                                   [n_sums+2] sum of cstr_prob (all envs); then a ring of 32 slots [n_sums+2]: the
-                                   extras["episode"] means of step % 32 (rew_* in episode-sum order, mean terrain level,
-                                   mean cstr_prob) */
+                                   [n_sums+2] sum of cstr_prob (all envs), [n_sums+3] sum of the teacher envs' terrain levels; then a
+                                   ring of 32 slots [n_sums+B200_STATS_EXTRA]: the extras["episode"] means of step % 32 (rew_* in
+                                   episode-sum order, mean terrain level, mean cstr_prob | teacher level, student level, envs reset) */
     float *gait_state;          /* [N,20] theta[4], gait_time, phi, gait_period, base_height_target, foot_clearance_target,
                                    pitch_target, clock_input[8] = sin[F], cos[F] (periodic-gait tasks) */
     float *cstr_prob;           /* [N] CaT termination probability (Go2CaT.cstr_prob); unused (but bound) for other tasks */
@@ -311,6 +311,33 @@ int b200_env_post_step(B200Handle *h, long long step_counter, float cmd_vx_lo, f
  * This is the call the rollout loop makes (on_policy_runner.py:118-139: env.step(actions) followed by host reads). */
 int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long long step_counter, float cmd_vx_lo, float cmd_vx_span,
                   long long hist_step, float *host_rew, uint8_t *host_reset, uint8_t *host_time_out, void *cuda_stream);
+
+/* Device-stepped env.step: the same step as b200_env_step with device-resident actions, but every per-step scalar the
+ * host passes there (step counter, frame-stack position, command range, go2_wtw behaviour ranges, the host-drawn sit-pose
+ * coin and gait indices) lives in `dev_step_state`, B200_STEP_STATE_WORDS int32 words of caller-owned DEVICE memory, and is
+ * moved forward by a one-thread kernel launched ahead of the dynamics kernel.  No launch parameter changes from one call to
+ * the next, so a stream capture of T such calls -- with the policy network's kernels in between -- is a CUDA graph that
+ * replays a whole rollout with one launch (on_policy_runner.py:118-139 is launch-bound in PyTorch eager mode).
+ * Layout (B200_SS_*): [0] LeggedRobot.common_step_counter (the call increments it first, like legged_robot.py:57), [1]
+ * observation frames appended so far (incremented too: the call runs with hist_step = the value it found), [2] cmd_vx_lo, [3] cmd_vx_span
+ * (fp32 bit patterns), [4..11] the eight behaviour floats as b200_set_behavior stores them (lower, span pairs), [12]
+ * sit-pose flag, [13] / [14] gait index of the callback / reset resampling (all three REdrawn by the call from the same
+ * Philox stream the host uses, hcr_genesis_lr_cl_b200/host_rng.py), [15] number of gaits to draw from.  The caller writes
+ * words 0..11 and 15 (and re-writes them when a curriculum moves a range); results are bit-identical to the host-stepped
+ * calls with the same values.  `sit_init_percent` is the reference's cfg.init_state.sit_init_percent (0: no sit-pose resets).
+ * The caller counts the steps itself (common_step_counter, hist_step) to keep its views of the frame-stack rings and of
+ * the statistics ring in step; the bug-compatible R18 mode is not available here. */
+#define B200_STEP_STATE_WORDS 16
+#define B200_SS_STEP 0
+#define B200_SS_HIST_STEP 1
+#define B200_SS_VX_LO 2
+#define B200_SS_VX_SPAN 3
+#define B200_SS_BEH 4
+#define B200_SS_SIT_POSE 12
+#define B200_SS_GAIT_CB 13
+#define B200_SS_GAIT_RESET 14
+#define B200_SS_NUM_GAITS 15
+int b200_env_step_device(B200Handle *h, const float *dev_actions, int32_t *dev_step_state, double sit_init_percent, void *cuda_stream);
 
 /* Rollout-side fusion: where the NEXT fused post step (b200_env_post_step with PHASE_ALL / b200_env_step)
  * additionally writes its results, so that the runner's per-step copies disappear:

@@ -410,8 +410,9 @@ def test_env_kernel_matches_numpy_oracle_seeded(task):
             _close(out[k], eo.st[k], what=f"step {t}: {k}")
         if o["episode_means"] is not None:                                   # extras["episode"] of this step (device ring)
             n = len(eo.sum_names)
-            base = 2 * n + 4 + (env.common_step_counter % 32) * (n + 3)
-            ring = out["stats"][base:base + n + 3]
+            we = n + H["B200_STATS_EXTRA"]
+            base = 2 * n + 4 + (env.common_step_counter % 32) * we
+            ring = out["stats"][base:base + we]
             for i, name in enumerate(eo.sum_names):
                 assert abs(ring[i] - o["episode_means"]["rew_" + name]) <= 1e-4 * abs(o["episode_means"]["rew_" + name]) + 1e-6, name
             if spec.terrain_curriculum:

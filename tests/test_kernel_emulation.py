@@ -5,6 +5,7 @@ library is built by nvcc and has no CPU path."""
 import numpy as np
 import pytest
 
+from hcr_genesis_lr_cl_b200 import _cabi
 from emu_util import EmuSim, oracle_params, oracle_policy_step
 from golden_util import load_golden, load_terrain, out_at, phys_at, spec_for
 from oracle.physics import PhysicsOracle
@@ -105,7 +106,9 @@ def _run_golden(name, steps, specialized=True, r18=False):
         assert B["stats"][n] == ref["reset_buf"].sum()            # reset counter of the per-step reductions
         # the last block finalised extras["episode"] into the ring slot of this step and re-armed the ticket counter
         assert B["global_flags"][1] == 0
-        ring = B["stats"][2 * n + 4 + (sim.step_counter % 32) * (n + 3):][:n + 3]
+        we = n + _cabi.H["B200_STATS_EXTRA"]
+        ring = B["stats"][2 * n + 4 + (sim.step_counter % 32) * we:][:we]
+        assert ring[n + 3] == ref["reset_buf"].sum()              # ... and again in the ring (device-stepped curricula read it there)
         cnt = max(float(ref["reset_buf"].sum()), 1.0)
         assert np.allclose(ring[:n], B["stats"][:n] / cnt / np.float32(spec.episode_length_s), rtol=1e-6, atol=0)
         if spec.terrain_curriculum:

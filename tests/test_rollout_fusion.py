@@ -100,3 +100,132 @@ def test_fused_collector_fills_the_reference_storage_emulated(task):
 def test_fused_collector_fills_the_reference_storage_gpu(task):
     from hcr_genesis_lr_cl_b200.fused_env import FusedLeggedEnv
     _compare(FusedLeggedEnv, task, 256, "cuda:0", T=24, rollouts=2)
+
+
+# ------------------------------------------------------------------ device-stepped env.step and the graphed collector
+def _twin_envs(env_cls, task, N, dev, **over):
+    from hcr_genesis_lr_cl_b200 import task_spec as TS
+    from hcr_genesis_lr_cl_b200.terrain_assets import terrain_for
+    spec = TS.PRESETS[task](**over)
+    envs = []
+    for _ in range(2):
+        e = env_cls(spec, N, dev, terrain=terrain_for(spec))
+        e.reset()
+        envs.append(e)
+    ep = envs[0].episode_length_buf
+    ep[0::3] = int(envs[0].max_episode_length) - 4 - (torch.arange(len(ep[0::3]), device=ep.device) % 5).to(ep.dtype)    # resets inside the window
+    envs[1].episode_length_buf = ep.clone()
+    return envs
+
+
+def _same_state(a, b, what):
+    sa, sb = a.simulator.get_state(), b.simulator.get_state()
+    for k in sa:
+        if k in ("dyn_cost", "dyn_order"):
+            continue
+        if k == "stats":            # float atomics over the envs of a step: the order of the additions is not fixed (logging only)
+            assert np.allclose(sa[k], sb[k], rtol=1e-5, atol=1e-6), f"{what}: buffer {k} differs"
+            continue
+        assert np.array_equal(sa[k], sb[k], equal_nan=True), f"{what}: buffer {k} differs"
+
+
+def _device_stepped_equals_host_stepped(env_cls, task, N, dev, steps):
+    """b200_env_step_device (per-step scalars in device memory, host draws re-drawn on the device) == b200_env_step."""
+    a, b = _twin_envs(env_cls, task, N, dev)
+    b.sync_step_state()
+    g = torch.Generator().manual_seed(5)
+    saw_reset = 0
+    for t in range(steps):
+        act = torch.randn(N, a.num_actions, generator=g).to(dev)
+        ra, rb = a.step(act), b.step_device(act.clone())
+        for i, (x, y) in enumerate(zip(ra[:-1], rb[:-1])):
+            if x is not None:
+                bad = (x != y).nonzero()
+                assert torch.equal(x, y), (f"{task}: returned tensor {i} differs at step {t}: {bad.shape[0]} entries, first {bad[0].tolist()}, "
+                                           f"{x[tuple(bad[0])].item()!r} vs {y[tuple(bad[0])].item()!r}")
+        _same_state(a, b, f"{task} step {t}")
+        saw_reset += int(a.reset_buf.sum())
+        for k, v in a.extras["episode"].items():
+            if torch.is_tensor(v):
+                assert torch.allclose(v, b.extras["episode"][k], rtol=1e-5, atol=1e-7), k
+    assert saw_reset > 0
+    b.device_steps_done(0)
+    assert a.common_step_counter == b.common_step_counter and a.simulator._hist_count == b.simulator._hist_count
+    st = b.simulator.step_state.cpu().numpy()
+    assert int(st[0]) == b.common_step_counter and int(st[1]) == b.simulator._hist_count
+
+
+@pytest.mark.parametrize("task", ["go2_ts", "tron1_pf_ee", "go2_wtw"])
+def test_device_stepped_step_equals_host_stepped_emulated(task):
+    from emu_backend import EmuFusedLeggedEnv
+    _device_stepped_equals_host_stepped(EmuFusedLeggedEnv, task, 8, "cpu", steps=6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["go2", "go2_ts", "go2_cat", "tron1_pf_ee", "go2_wtw", "go2_cts"])
+def test_device_stepped_step_equals_host_stepped_gpu(task):
+    from hcr_genesis_lr_cl_b200.fused_env import FusedLeggedEnv
+    _device_stepped_equals_host_stepped(FusedLeggedEnv, task, 256, "cuda:0", steps=40)
+
+
+class _Alg:
+    """ppo.py:91-103 shaped stand-in (capture-safe: no host read in act)."""
+
+    def __init__(self, no, npv, na, dev, T, N):
+        from types import SimpleNamespace
+        mk = lambda i, o: torch.nn.Sequential(torch.nn.Linear(i, 64), torch.nn.ELU(), torch.nn.Linear(64, o)).to(dev)
+        self.actor, self.critic, self.std, self.gamma = mk(no, na), mk(npv, 1), torch.ones(na, device=dev), 0.99
+        self.transition = SimpleNamespace(clear=lambda: None)
+        self.actor_critic = SimpleNamespace(is_recurrent=False)
+        z = lambda *s: torch.zeros(*s, device=dev)
+        self.storage = SimpleNamespace(observations=z(T, N, no), privileged_observations=z(T, N, npv), rewards=z(T, N, 1), actions=z(T, N, na),
+                                       dones=z(T, N, 1).byte(), actions_log_prob=z(T, N, 1), values=z(T, N, 1), mu=z(T, N, na), sigma=z(T, N, na),
+                                       num_transitions_per_env=T, step=0)
+
+    def act(self, obs, critic_obs):
+        tr = self.transition
+        mean = self.actor(obs)
+        dist = torch.distributions.Normal(mean, mean * 0. + self.std, validate_args=False)
+        tr.actions = dist.sample()
+        tr.values = self.critic(critic_obs)
+        tr.actions_log_prob = dist.log_prob(tr.actions).sum(dim=-1)
+        tr.action_mean, tr.action_sigma = mean, dist.stddev
+        return tr.actions
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["go2_ts", "go2_cat"])
+def test_graphed_collector_replays_the_rollout(task):
+    """GraphedRolloutCollector: T x (policy, storage copies, device-stepped env step) captured once, replayed per rollout.  The
+    env side of every replayed rollout must be what a host-stepped twin env makes of the SAME actions (read back from the
+    storage the graph filled): observations, rewards (with the time-out bootstrapping), dones, and the full env state."""
+    from hcr_genesis_lr_cl_b200.fused_env import FusedLeggedEnv
+    from hcr_genesis_lr_cl_b200.rollout import GraphedRolloutCollector
+    N, T, dev = 256, 8, "cuda:0"
+    a, b = _twin_envs(FusedLeggedEnv, task, N, dev)
+    torch.manual_seed(1)
+    alg = _Alg(b.num_obs, b.num_privileged_obs, b.num_actions, dev, T, N)
+    col = GraphedRolloutCollector(b, alg, warmup_rollouts=1)
+    st = alg.storage
+    launches0 = None
+    for r in range(5):                        # rollout 0: eager warm-up, 1: capture + replay, 2..: replays
+        col.collect()
+        torch.cuda.synchronize()
+        assert st.step == T
+        obs0 = a.obs_buf.clone()
+        assert torch.equal(st.observations[0], obs0), f"rollout {r}: slot 0 is not the observation the twin stands on"
+        for t in range(T):
+            a.step(st.actions[t].clone())
+            nxt = st.observations[t + 1] if t + 1 < T else col.carry_obs
+            assert torch.equal(nxt, a.obs_buf), f"rollout {r} step {t}: observations differ"
+            exp_rew = a.rew_buf + alg.gamma * st.values[t].view(-1) * a.time_out_buf
+            assert torch.equal(st.rewards[t].view(-1), torch.where(a.time_out_buf, exp_rew, a.rew_buf)), f"rollout {r} step {t}: rewards differ"
+            assert torch.equal(st.dones[t].view(-1).bool(), a.reset_buf)
+        _same_state(a, b, f"{task} rollout {r}")
+        assert a.common_step_counter == b.common_step_counter
+        if r >= 2:                            # a replay issues no launch through the library's host path
+            assert b.simulator._lib.b200_launch_count(b.simulator._handle) == launches0
+        launches0 = b.simulator._lib.b200_launch_count(b.simulator._handle)
+        st.step = 0
+    assert col._graph is not None
+    assert int(col.ep_stats[2]) > 0

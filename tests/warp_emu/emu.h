@@ -44,6 +44,7 @@ static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int m) { return emu
 static inline float __shfl_down_sync(unsigned, float v, int d) { return emu_float(emu_exchange(emu_bits(v), emu_cur_lane + d < 32 ? emu_cur_lane + d : emu_cur_lane)); }
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+struct int4 { int x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 static inline unsigned __ballot_sync(unsigned, bool p) { return emu_ballot(p); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_sync(); }

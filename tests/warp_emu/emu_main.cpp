@@ -4,6 +4,7 @@
 #include "emu.h"
 #include "../../hcr_genesis_lr_cl_b200/csrc/dynamics_kernel.cuh"
 #ifdef EMU_WITH_ENV
+#define B200_ENV_DEFINE_KERNELS
 #include "../../hcr_genesis_lr_cl_b200/csrc/env_kernel.cuh"
 #endif
 
@@ -40,10 +41,10 @@ static int g_env_preset = -1, g_env_specialized = 1;
 static void env_body(void *p) {
     EnvArgs *a = (EnvArgs *)p;
     switch (g_env_preset) {            // same selection as launch_env in csrc/b200_step.cu
-#define X_CASE(P) case P: env_post_step_kernel_preset<P>(a->T, a->B, a->tr, a->call, a->tab); break;
+#define X_CASE(P) case P: env_post_step_kernel_preset<P, false>(a->T, a->B, a->tr, a->call, a->tab); break;
         ENV_FOR_EACH_PRESET(X_CASE)
 #undef X_CASE
-    default: env_post_step_kernel(a->T, a->B, a->tr, a->call, a->tab);
+    default: env_post_step_kernel<false>(a->T, a->B, a->tr, a->call, a->tab);
     }
 }
 int emu_env_post_step(const float *tf, const int *ti, const int16_t *hf, int rows, int cols, const float *origins, int levels, int types,

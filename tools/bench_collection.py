@@ -8,7 +8,9 @@ Two loops over the same FusedLeggedEnv (`go2_ts`, 4096 envs) and the same rsl_rl
              process_env_step (rewards.clone, bootstrapping, 9 copy_ into the storage) -> per-step episode book-keeping with its
              two .cpu().numpy().tolist() host reads;
   fused      rollout.FusedRolloutCollector: the env kernel writes obs / privileged obs / rewards / dones into the storage slabs,
-             book-keeping stays on the device, no host read inside the loop.
+             book-keeping stays on the device, no host read inside the loop;
+  graphed    rollout.GraphedRolloutCollector: the fused loop with the device-stepped env step (b200_env_step_device), captured
+             once into a CUDA graph and replayed: one launch per rollout.
 
 The PPO / storage classes are small stand-ins with rsl_rl's attribute names (the reference tree does not travel to the GPU
 box for bench purposes); tests/test_rollout_fusion.py checks the collector against the reference's own classes.
@@ -28,7 +30,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hcr_genesis_lr_cl_b200 import build, task_spec as T  # noqa: E402
 from hcr_genesis_lr_cl_b200.fused_env import FusedLeggedEnv  # noqa: E402
-from hcr_genesis_lr_cl_b200.rollout import FusedRolloutCollector  # noqa: E402
+from hcr_genesis_lr_cl_b200.rollout import FusedRolloutCollector, GraphedRolloutCollector  # noqa: E402
 from hcr_genesis_lr_cl_b200.terrain_assets import terrain_for  # noqa: E402
 
 
@@ -71,7 +73,7 @@ class Alg:
     def act(self, obs, critic_obs):
         tr = self.transition
         mean = self.actor(obs)
-        dist = torch.distributions.Normal(mean, mean * 0. + self.std)
+        dist = torch.distributions.Normal(mean, mean * 0. + self.std, validate_args=False)
         tr.actions = dist.sample()
         tr.values = self.critic(critic_obs)
         tr.actions_log_prob = dist.log_prob(tr.actions).sum(dim=-1)
@@ -100,14 +102,14 @@ def main():
     spec = T.PRESETS[args.task]()
     N, H = args.envs, args.horizon
     out = {}
-    for mode in ("runner", "fused"):
+    for mode in ("runner", "fused", "graphed"):
         env = FusedLeggedEnv(spec, N, dev, terrain=terrain_for(spec))
         env.reset()
         torch.manual_seed(0)
         npv = env.num_privileged_obs or env.num_obs
         alg = Alg(mlp(env.num_obs, spec.num_actions).to(dev), mlp(npv, 1).to(dev), spec.num_actions, dev)
         alg.storage = Storage(H, N, env.num_obs, npv, spec.num_actions, dev)
-        col = FusedRolloutCollector(env, alg) if mode == "fused" else None
+        col = FusedRolloutCollector(env, alg) if mode == "fused" else (GraphedRolloutCollector(env, alg) if mode == "graphed" else None)
         rewbuffer, lenbuffer = deque(maxlen=100), deque(maxlen=100)
         cur_reward_sum, cur_episode_length = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
         for _ in range(300 // H + 1):                       # steady-state workload first
@@ -115,10 +117,10 @@ def main():
                 for _ in range(H):
                     env.step(torch.randn(N, spec.num_actions, device=dev))
         times = []
-        for it in range(args.iters + 2):
+        for it in range(args.iters + 3):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            if mode == "fused":
+            if col is not None:
                 col.collect()
                 col.episode_statistics()
             else:
@@ -139,14 +141,16 @@ def main():
                         cur_episode_length[new_ids] = 0
             alg.storage.clear()
             torch.cuda.synchronize()
-            if it >= 2:
+            if it >= 3:                      # graphed: warm-up rollout, capture, first replay
                 times.append(time.perf_counter() - t0)
         times.sort()
         med = times[len(times) // 2]
         out[mode] = {"ms_per_policy_step": 1e3 * med / H, "env_substeps_per_s": N * spec.decimation * H / med,
-                     "host_reads_per_policy_step": 0 if mode == "fused" else 2}
+                     "host_reads_per_policy_step": 2 if mode == "runner" else 0,
+                     "launches_per_rollout": 1 if mode == "graphed" else None}
         del env
     out["speedup"] = out["runner"]["ms_per_policy_step"] / out["fused"]["ms_per_policy_step"]
+    out["speedup_graphed"] = out["runner"]["ms_per_policy_step"] / out["graphed"]["ms_per_policy_step"]
     print(json.dumps({"task": args.task, "envs": N, "horizon": H, "policy": "MLP 512-256-128 actor + critic (PyTorch)", **out}))
 
 
