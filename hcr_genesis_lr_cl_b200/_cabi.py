@@ -180,6 +180,7 @@ def pack_task(spec: T.TaskSpec, model: RobotModel, num_envs: int, hf_shape=(0, 0
     si("TI_SINGLE_CRITIC", w["single_critic"]); si("TI_FRAME_STACK", spec.frame_stack); si("TI_C_FRAME_STACK", spec.c_frame_stack)
     si("TI_MAX_EPISODE_LENGTH", spec.max_episode_length); si("TI_RESAMPLE_INTERVAL", spec.resample_interval)
     si("TI_PUSH_INTERVAL", spec.push_interval)
+    si("TI_TRIMESH", spec.mesh_type == "trimesh")
     si("TI_HEIGHTFIELD", spec.heightfield); si("TI_MEASURE_HEIGHTS", spec.measure_heights and spec.heightfield)
     si("TI_FEET_INFO", spec.obtain_terrain_info_around_feet and spec.measure_heights and spec.heightfield)
     si("TI_TERRAIN_CURRICULUM", spec.terrain_curriculum and spec.heightfield); si("TI_HEADING_COMMAND", spec.heading_command)

@@ -142,8 +142,11 @@ __device__ __forceinline__ m33 axis_angle(f3 a, float th) {
     return R;
 }
 
-// terrain height and unit normal under world point (x, y): the triangle of the heightfield cell below it
-__device__ __forceinline__ void terrain_query(const TerrainDev &tr, float hs, float vs, float border, float x, float y, float &h, f3 &n) {
+// terrain height and unit normal under world point (x, y): the triangle of the heightfield cell below it.  `trimesh`
+// (terrain.mesh_type "trimesh"): the cell is cut along (i,j)-(i+1,j+1) like the mesh convert_heightfield_to_trimesh builds
+// (legged_gym/utils/terrain_utils.py:887-900: triangles (ind0, ind3, ind1) and (ind0, ind2, ind3)); heightfield: along
+// (i+1,j)-(i,j+1).  Warp-uniform.
+__device__ __forceinline__ void terrain_query(const TerrainDev &tr, float hs, float vs, float border, bool trimesh, float x, float y, float &h, f3 &n) {
     if (tr.hf == nullptr) { h = 0.f; n = mk3(0.f, 0.f, 1.f); return; }
     const float ihs = 1.f / hs;                    // grid coordinates by the reciprocal, like the oracle (same cell on both sides)
     const float gx = (x + border) * ihs, gy = (y + border) * ihs;
@@ -154,7 +157,10 @@ __device__ __forceinline__ void terrain_query(const TerrainDev &tr, float hs, fl
     const float h00 = (float)__ldg(p) * vs, h01 = (float)__ldg(p + 1) * vs;
     const float h10 = (float)__ldg(p + tr.cols) * vs, h11 = (float)__ldg(p + tr.cols + 1) * vs;
     float dhx, dhy;
-    if (u + w <= 1.f) { dhx = h10 - h00; dhy = h01 - h00; h = h00 + u * dhx + w * dhy; }
+    if (trimesh) {
+        if (u >= w) { dhx = h10 - h00; dhy = h11 - h10; } else { dhx = h11 - h01; dhy = h01 - h00; }
+        h = h00 + u * dhx + w * dhy;
+    } else if (u + w <= 1.f) { dhx = h10 - h00; dhy = h01 - h00; h = h00 + u * dhx + w * dhy; }
     else { dhx = h11 - h01; dhy = h11 - h10; h = h11 - (1.f - u) * dhx - (1.f - w) * dhy; }
     const f3 g = mk3(-dhx * ihs, -dhy * ihs, 1.f);
     n = g * rsqrtf(dot3(g, g));
@@ -570,7 +576,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                 for (int e = 0; e < 9; e++) Rb.m[e] = fr[e];
                 sx[t] = mk3(fr[9], fr[10], fr[11]) + mul(Rb, mk3(Sp[0], Sp[1], Sp[2]));
                 float hh;
-                terrain_query(tr, tf[TF_HSCALE], tf[TF_VSCALE], tf[TF_BORDER], p.x + sx[t].x, p.y + sx[t].y, hh, sn[t]);
+                terrain_query(tr, tf[TF_HSCALE], tf[TF_VSCALE], tf[TF_BORDER], T.i[TI_TRIMESH] != 0, p.x + sx[t].x, p.y + sx[t].y, hh, sn[t]);
                 sdist[t] = (p.z + sx[t].z - hh) * sn[t].z - Sp[3];
                 act[t] = sdist[t] < 0.f;
             }

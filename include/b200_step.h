@@ -134,6 +134,8 @@ enum B200TaskI {
                                                                     nonzero() of [N,1] masks makes env 0 follow "any env" for the gait-clock wrap and the swing /
                                                                     stance indicator (go2_wtw.py:258-263,443-466, tron1_pf_ee.py:27-35,397-420); default 0 = per env */
     TI_VM_TERMS,                                                 /* 0: "step" gait indicator; p > 0: "smooth" indicator, von Mises CDF series of p terms */
+    TI_TRIMESH,                                                  /* terrain.mesh_type "trimesh": collide with the triangles convert_heightfield_to_trimesh builds
+                                                                    (legged_gym/utils/terrain_utils.py:887-900: cell diagonal (i,j)-(i+1,j+1)); 0 = heightfield */
     TI_REWARD_IDS,                                               /* [B200_MAX_REWARDS] active term ids, evaluation order */
     TI_FEET_LINKS = TI_REWARD_IDS + B200_MAX_REWARDS,            /* [B200_MAX_FEET]  */
     TI_PEN_LINKS = TI_FEET_LINKS + B200_MAX_FEET,                /* [B200_MAX_LINKS] */

@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 P_DT, P_GRAV, P_TC, P_DAMPRATIO, P_D0, P_DMAX, P_WIDTH, P_MID, P_POWER, P_TERRAIN_MU, P_GEOM_MU, P_ITERS, \
-    P_HSCALE, P_VSCALE, P_BORDER, P_TOL = range(16)
+    P_HSCALE, P_VSCALE, P_BORDER, P_TOL, P_TRIMESH = range(17)
 
 
 def build(force: bool = False) -> None:
@@ -24,7 +24,7 @@ def build(force: bool = False) -> None:
             subprocess.check_call(["make", "-C", _HERE, name])
 
 
-def default_params(dt=0.005, iters=30, hscale=0.1, vscale=0.005, border=0.0, terrain_mu=1.0, geom_mu=1.0, tol=1e-4) -> np.ndarray:
+def default_params(dt=0.005, iters=30, hscale=0.1, vscale=0.005, border=0.0, terrain_mu=1.0, geom_mu=1.0, tol=1e-4, trimesh=False) -> np.ndarray:
     p = np.zeros(20, np.float32)
     p[P_DT], p[P_GRAV] = dt, 9.81
     p[P_TC], p[P_DAMPRATIO] = 2 * dt, 1.0
@@ -32,6 +32,7 @@ def default_params(dt=0.005, iters=30, hscale=0.1, vscale=0.005, border=0.0, ter
     p[P_TERRAIN_MU], p[P_GEOM_MU], p[P_ITERS] = terrain_mu, geom_mu, iters
     p[P_HSCALE], p[P_VSCALE], p[P_BORDER] = hscale, vscale, border
     p[P_TOL] = tol
+    p[P_TRIMESH] = 1.0 if trimesh else 0.0
     return p
 
 
@@ -86,10 +87,24 @@ class PhysicsOracle:
         return lp, lv
 
 
+def terrain_query(prm, hf, xy, lib=None):
+    """Height and unit normal of the oracle's collision surface under world points `xy` [n, 2] (float64)."""
+    build()
+    lib = lib or ctypes.CDLL(os.path.join(_HERE, "liboracle_f64.so"))
+    hf = np.ascontiguousarray(hf, np.int16)
+    xy = np.ascontiguousarray(xy, np.float64)
+    h, nrm = np.zeros(len(xy)), np.zeros((len(xy), 3))
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.oracle_terrain_query(vp(np.ascontiguousarray(prm, np.float32)), vp(hf), ctypes.c_int(hf.shape[0]), ctypes.c_int(hf.shape[1]),
+                             ctypes.c_int(len(xy)), vp(xy), vp(h), vp(nrm))
+    return h, nrm
+
+
 def oracle_params(spec, model=None, hf=None):
     return default_params(dt=spec.sim_dt, iters=spec.pgs_iterations, hscale=spec.horizontal_scale,
                                 vscale=spec.vertical_scale, border=spec.border_size if spec.heightfield else 0.0,
-                                terrain_mu=spec.static_friction, geom_mu=1.0, tol=spec.pgs_tolerance)
+                                terrain_mu=spec.static_friction, geom_mu=1.0, tol=spec.pgs_tolerance,
+                                trimesh=spec.mesh_type == "trimesh")
 
 
 def env_params(spec, st) -> np.ndarray:

@@ -61,7 +61,7 @@ typedef struct {
 
 /* physics parameters, float[16] */
 enum { P_DT, P_GRAV, P_TC, P_DAMPRATIO, P_D0, P_DMAX, P_WIDTH, P_MID, P_POWER,
-       P_TERRAIN_MU, P_GEOM_MU, P_ITERS, P_HSCALE, P_VSCALE, P_BORDER, P_TOL, P_NPARAM };
+       P_TERRAIN_MU, P_GEOM_MU, P_ITERS, P_HSCALE, P_VSCALE, P_BORDER, P_TOL, P_TRIMESH, P_NPARAM };
 
 static long long g_sweeps, g_substeps, g_rows, g_contacts;
 static long long g_hist[64];
@@ -136,7 +136,10 @@ static void terrain_query(const int16_t *hf, int rows, int cols, const float *pr
     real h00 = hf[i * cols + j] * vs, h10 = hf[(i + 1) * cols + j] * vs;
     real h01 = hf[i * cols + j + 1] * vs, h11 = hf[(i + 1) * cols + j + 1] * vs;
     real dhx, dhy;
-    if (u + w <= 1) { dhx = h10 - h00; dhy = h01 - h00; *h = h00 + u * dhx + w * dhy; }
+    if (prm[P_TRIMESH] != 0) {     /* mesh_type "trimesh": cell cut along (i,j)-(i+1,j+1), legged_gym/utils/terrain_utils.py:887-900 */
+        if (u >= w) { dhx = h10 - h00; dhy = h11 - h10; } else { dhx = h11 - h01; dhy = h01 - h00; }
+        *h = h00 + u * dhx + w * dhy;
+    } else if (u + w <= 1) { dhx = h10 - h00; dhy = h01 - h00; *h = h00 + u * dhx + w * dhy; }
     else { dhx = h11 - h01; dhy = h11 - h10; *h = h11 - (1 - u) * dhx - (1 - w) * dhy; }
     v3 g = V(-dhx * ihs, -dhy * ihs, 1);
     *n = scl(g, 1 / sqrt(dot(g, g)));
@@ -459,6 +462,15 @@ static Model mk_model(const int *mi, const float *mf) {
     M.link_body = mi + 8; M.sph_body = M.link_body + M.nlinks; M.sph_link = M.sph_body + M.nspheres;
     M.body = mf; M.link_off = M.body + M.nb * BODY_STRIDE; M.sph = M.link_off + 3 * M.nlinks;
     return M;
+}
+
+/* terrain height and unit normal under n world points (x, y): the collision surface the substep sees */
+void oracle_terrain_query(const float *prm, const int16_t *hf, int rows, int cols, int n, const double *xy, double *h_out, double *n_out) {
+    for (int k = 0; k < n; k++) {
+        real h; v3 nn;
+        terrain_query(hf, rows, cols, prm, (real)xy[2 * k], (real)xy[2 * k + 1], &h, &nn);
+        h_out[k] = h; n_out[3 * k] = nn.x; n_out[3 * k + 1] = nn.y; n_out[3 * k + 2] = nn.z;
+    }
 }
 
 /* All per-env arrays are row-major double [n_envs][k] regardless of REAL (converted on entry/exit). */

@@ -188,13 +188,16 @@ def _random_state(spec, N, terrain, seed):
     return st, model
 
 
-@pytest.mark.parametrize("task", ["go2_ts", "go2", "tron1_pf", "tron1_pf_ee", "go2_wtw"])
+@pytest.mark.parametrize("task", ["go2_ts", "go2", "tron1_pf", "tron1_pf_ee", "go2_wtw", "go2_ts:trimesh", "tron1_pf_ee:trimesh"])
 def test_dynamics_kernel_matches_oracle(task):
-    """One policy step (4 substeps) of the warp-per-env kernel vs the fp32 C oracle on seeded states."""
+    """One policy step (4 substeps) of the warp-per-env kernel vs the fp32 C oracle on seeded states.  ":trimesh" =
+    terrain.mesh_type "trimesh": the same height samples triangulated like convert_heightfield_to_trimesh does (the oracle's
+    surface for that mode is pinned against the reference's triangles in test_oracle_physics.py)."""
     from emu_util import oracle_params, oracle_policy_step
     from hcr_genesis_lr_cl_b200 import task_spec as T
     from oracle.physics import PhysicsOracle
-    spec = T.PRESETS[task]()
+    task, _, mesh = task.partition(":")
+    spec = T.PRESETS[task](**({"mesh_type": mesh} if mesh else {}))
     terrain = load_terrain(spec) if spec.heightfield else None
     N = 256
     st, model = _random_state(spec, N, terrain, seed=7)

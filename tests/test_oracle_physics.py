@@ -141,6 +141,33 @@ def test_heightfield_contact_normal_on_a_slope():
     assert np.abs(st[0, 7:9]).max() < 0.05
 
 
+def test_trimesh_surface_matches_the_reference_triangles():
+    """terrain.mesh_type "trimesh": the oracle's collision surface == the triangles the reference's own
+    convert_heightfield_to_trimesh builds (terrain_utils.py:835-902; golden from tools/make_golden_trimesh.py, which imports
+    it unchanged).  The heightfield mode cuts each cell along the other diagonal, so it must NOT match on twisted cells."""
+    import os
+    from oracle.physics import terrain_query
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trimesh_surface.npz"))
+    prm = default_params(hscale=float(g["hscale"]), vscale=float(g["vscale"]), border=0.0, trimesh=True)
+    h, n = terrain_query(prm, g["hf"], g["xy"])
+    assert np.abs(h - g["height"]).max() < 1e-6 and np.abs(n - g["normal"]).max() < 1e-6      # the reference stores float32 vertices
+    prm_hf = default_params(hscale=float(g["hscale"]), vscale=float(g["vscale"]), border=0.0, trimesh=False)
+    h2, _ = terrain_query(prm_hf, g["hf"], g["xy"])
+    assert np.abs(h2 - g["height"]).max() > 1e-3
+    # the same query restated from the committed triangles (no reference needed at test time)
+    v, t = g["vertices"].astype(np.float64), g["triangles"]
+    for k in range(0, len(g["xy"]), 37):
+        p = g["xy"][k]
+        best, zb = -1.0, None
+        for a, b, c in v[t]:
+            T = np.array([[b[0] - a[0], c[0] - a[0]], [b[1] - a[1], c[1] - a[1]]])
+            l1, l2 = np.linalg.solve(T, p - a[:2])
+            m = min(l1, l2, 1 - l1 - l2)
+            if m > best:
+                best, zb = m, a[2] * (1 - l1 - l2) + b[2] * l1 + c[2] * l2
+        assert abs(zb - h[k]) < 1e-6          # vertices are stored as float32 in the fixture
+
+
 @pytest.mark.parametrize("robot,names", [("go2", GO2_DOF_NAMES), ("tron1_pf", TRON1_PF_DOF_NAMES)])
 def test_work_energy_balance_with_joint_torques_and_gravity(robot, names):
     """dE/dt = tau . qd for the floating-base tree in flight (E = kinetic + potential from the independent numpy
