@@ -98,6 +98,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _config(args, spec, N, world):
+    """`config` of the JSON line: the workload both arms run (the reference arm steps the same env population on the host)."""
+    return {"workload": f"{args.task}: {WORKLOADS[args.task]}, {N} envs/GPU",
+            "envs_per_gpu": N, "decimation": spec.decimation, "pgs_iterations": spec.pgs_iterations,
+            "actions": "N(0,1) (policy at init)", "pre_roll_steps": args.pre_roll,
+            "timing": "median of K per-step CUDA-event times per rank, max over ranks",
+            "l2": "flushed between timed steps (256 MB write, then 256 MB read: no dirty lines left)",
+            "parallelism": f"env-sharded x{world}, no data-path collective"}
+
+
 def run_reference(args):
     """CPU arm: the oracle port on all host threads (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -116,10 +126,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.task}: {WORKLOADS[args.task]}, {args.envs} envs/GPU", "envs_per_gpu": args.envs,
-                   "decimation": spec.decimation, "pgs_iterations": spec.pgs_iterations, "actions": "N(0,1) (policy at init)",
-                   "cpu_sample": f"each step = {sample_envs} envs stepped once, {sample_envs // cores} per core on {cores} cores"},
-        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "config": _config(args, spec, args.envs, args.gpus),       # the b200 arm's config, key for key (timing / l2 describe that arm)
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                         "sample": res["sample"] + f"; each step = {sample_envs} envs stepped once, {sample_envs // cores} per core on {cores} cores, "
+                                                   "host wall clock, no pre-roll"},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -261,23 +271,19 @@ def run_gpu(args):
     step_bytes = env_bytes + dyn_bytes
     whole = step_bytes / (total_ms / K * 1e-3) / 1e9
     on_device = 4 * N * sum(env.widths[k] for k in ("obs", "priv", "hist", "critic"))     # observation tensors the policy reads in HBM
-    traffic = None                          # DRAM bytes per launch of the same kernels from the committed ncu capture
+    traffic, tj_all = None, {}              # DRAM bytes per launch of the same kernels from the committed ncu capture
     tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)
         if tj.get("workload") == f"{args.task}/{N}":
-            traffic = tj["env_post_step_kernel"]
+            traffic, tj_all = tj["env_post_step_kernel"], tj
     ki_env, ki_dyn = sim.kernel_info("env"), sim.kernel_info("dynamics")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.task}: {WORKLOADS[args.task]}, {N} envs/GPU",
-                   "envs_per_gpu": N, "decimation": spec.decimation, "pgs_iterations": spec.pgs_iterations,
-                   "actions": "N(0,1) (policy at init)", "pre_roll_steps": args.pre_roll,
-                   "timing": "median of K per-step CUDA-event times per rank, max over ranks", "l2": "flushed between timed steps (256 MB write, then 256 MB read: no dirty lines left)",
-                   "parallelism": f"env-sharded x{world}, no data-path collective"},
+        "config": _config(args, spec, N, world),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": N * spec.num_actions * 4 * world, "d2h_bytes_per_step": N * 6 * world,
                 "ms_per_step": e2e_ms / K, "result_on_device_bytes": on_device * world,
                 "note": "rewards / resets / time-outs come back to the host every step; the observation tensors stay in HBM, where the policy network reads them"},
@@ -285,18 +291,26 @@ def run_gpu(args):
         "workload_state": workload_state,
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "env_post_step_kernel (the fused post_physics_step)", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": env_bytes,
-                     "avg_launch_ms": t_env,
+        # the path's figure first (all kernels' algorithmic bytes over the step time: the recipe's number for the dominant part of
+        # the step), then each kernel on its own bytes and time
+        "roofline": {"kernel": "whole env.step: dynamics_step_kernel (86 % of the time) + env_post_step_kernel", "bound": "hbm",
+                     "achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
+                     "traffic": (tj_all.get("dynamics_step_kernel", 0) + tj_all.get("env_post_step_kernel", 0)) if traffic is not None else None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": step_bytes, "avg_launch_ms": total_ms / K,
                      "bytes_variant": "ring: frame stacks are double-written rings handed out as strided views, a step writes each new "
-                                      "frame twice and moves nothing (SURVEY 8d names this variant); re-writing the stacks every step, "
-                                      f"as round 1 did, would add {accounting.shifted_stack_bytes(spec, model) * N} B per launch",
-                     "whole_step": {"algorithmic_bytes": step_bytes, "ms": total_ms / K, "achieved": whole, "frac": whole / peak,
-                                    "note": "all three kernels' bytes over the step time; the dynamics kernel (most of the step) is "
-                                            "latency / issue bound by construction, SURVEY 8d"},
-                     "note": "at 4096 envs the kernel's whole working set (19 MB) is L2 resident and one warp per env leaves 28 warps "
-                             "per SM: it is bound by instruction latency, not by HBM -- time, not this fraction, is what to read"},
+                                      "frame twice and moves nothing (SURVEY 8d names this variant: 5.9 KB instead of 17.5 KB per env "
+                                      "and policy step for go2_ts)",
+                     "frac_with_round1_bytes": (step_bytes + accounting.shifted_stack_bytes(spec, model) * N) / (total_ms / K * 1e-3) / 1e9 / peak,
+                     "dynamics_step_kernel": {"algorithmic_bytes_per_launch": dyn_bytes, "avg_launch_ms": t_dyn,
+                                              "achieved": dyn_bytes / (t_dyn * 1e-3) / 1e9, "frac": dyn_bytes / (t_dyn * 1e-3) / 1e9 / peak,
+                                              "bound": "latency / issue (SURVEY 8d: 1.3 KB of HBM traffic per env against ~25 k "
+                                                       "dependent instructions): see profiles/*_kernels_ncu_summary.txt for issue-slot use"},
+                     "env_post_step_kernel": {"algorithmic_bytes_per_launch": env_bytes, "avg_launch_ms": t_env, "achieved": achieved,
+                                              "frac": achieved / peak, "traffic": traffic,
+                                              "bound": "instruction latency at 28 warps per SM: its working set (19 MB at 4096 envs) "
+                                                       "is L2 resident"},
+                     "note": "no kernel of this path is HBM-bound at 4096 envs per GPU (one wave of 28 one-env warps per SM): "
+                             "time per step, not this fraction, is what to read"},
         "kernels": {
             "step": {"avg_ms": t_step, "note": "one b200_env_step call: dynamics kernel (the env-ordering kernel on a side stream under it), env "
                      "kernel, stats finalize; the entries below are a second loop that times the kernels call by call"},
