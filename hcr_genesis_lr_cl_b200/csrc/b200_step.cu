@@ -45,7 +45,9 @@ struct B200Handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool side_enabled = true;
     int env_preset = -1;           // instantiation of the env kernel: index into env_presets.inc, -1 = generic
-    float *d_actions = nullptr;    // staging of b200_env_step's host actions
+    float *d_actions = nullptr;    // staging of b200_env_step's host actions (when they cannot be read in place)
+    bool zero_copy_actions = true; // pinned host actions are read by the dynamics kernel in place (B200_ZERO_COPY_ACTIONS=0: staged copy)
+    bool zero_copy_results = true; // the env kernel writes rew | reset | time_out into the caller's pinned slab (B200_ZERO_COPY_RESULTS=0: D2H copy)
     bool stats_zeroed = false;
     bool order_enabled = true;     // dynamics warps take envs sorted by solver cost (dynamics_order_kernel); B200_DYN_ORDER=0: slot w = env w
     long long dyn_launches = 0;    // parity of the cost / order buffers
@@ -103,6 +105,10 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
         CKH(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
         const char *o = getenv("B200_DYN_ORDER");
         h->order_enabled = !(o && o[0] == '0');
+        const char *z = getenv("B200_ZERO_COPY_ACTIONS");
+        h->zero_copy_actions = !(z && z[0] == '0');
+        const char *zr = getenv("B200_ZERO_COPY_RESULTS");
+        h->zero_copy_results = !(zr && zr[0] == '0');
     }
     if (h->env_smem > 48 * 1024) {
         CKH(cudaFuncSetAttribute(env_kernel_fn(h->env_preset), cudaFuncAttributeMaxDynamicSharedMemorySize, h->env_smem));
@@ -233,11 +239,12 @@ static EnvCall make_call(B200Handle *h, long long step, float lo, float span, lo
     call.inv_teacher = h->task.i[TI_NUM_TEACHER] > 0 ? 1.0f / (float)max(n_teach, 1) : 0.f;
     call.inv_student = 1.0f / (float)max(N - n_teach, 1);
     call.dstate = nullptr;
+    call.host_slab = nullptr; call.host_slab_vecs = 0;
     return call;
 }
 
 static int launch_env(B200Handle *h, long long step, float lo, float span, long long hist_step, int mask, int force, void *stream,
-                      const int32_t *dstate = nullptr) {
+                      const int32_t *dstate = nullptr, void *host_slab = nullptr) {
     DeviceGuard guard(h);
     const int N = h->task.i[TI_NUM_ENVS];
     const int n_sums = h->task.i[TI_N_SUMS];
@@ -246,6 +253,7 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, long 
     h->stats_zeroed = false;
     EnvCall call = make_call(h, step, lo, span, hist_step, mask, force);
     call.dstate = dstate;
+    if (host_slab && call.finalize) { call.host_slab = (uint4 *)host_slab; call.host_slab_vecs = (int)((6 * (size_t)N) / 16); }
     if (h->side_pending) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->side_pending = false; }      // join the side stream
     if (h->task.i[TI_R18] && (mask & PHASE_REWARD) && !force) {      // bug-compatible mode only: the "any env" bits row 0 follows (R18)
         B200_LAUNCH(r18_flags_kernel, dim3((N + R18_FLAGS_BLOCK - 1) / R18_FLAGS_BLOCK), R18_FLAGS_BLOCK, 0, s, h->task, h->bufs, call);
@@ -274,17 +282,40 @@ int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long
     cudaStream_t s = (cudaStream_t)stream;
     const float *dev_actions = actions;
     if (actions_on_host) {
-        if (!h->d_actions) CK(cudaMalloc(&h->d_actions, sizeof(float) * (size_t)N * A));
-        CK(cudaMemcpyAsync(h->d_actions, actions, sizeof(float) * (size_t)N * A, cudaMemcpyHostToDevice, s));
-        dev_actions = h->d_actions;
+        // Pinned (page-locked, mapped) host memory is addressable from the device: the dynamics kernel reads each env's A
+        // actions once, in its prologue, straight over PCIe -- no staging copy, no copy-engine operation in front of the
+        // launch (B200_ZERO_COPY_ACTIONS=0, or a buffer the driver does not report as mapped: staged copy as before).
+        const float *mapped = nullptr;
+        if (h->zero_copy_actions) {
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, actions) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+                mapped = (const float *)pa.devicePointer;
+            else (void)cudaGetLastError();
+        }
+        if (mapped) dev_actions = mapped;
+        else {
+            if (!h->d_actions) CK(cudaMalloc(&h->d_actions, sizeof(float) * (size_t)N * A));
+            CK(cudaMemcpyAsync(h->d_actions, actions, sizeof(float) * (size_t)N * A, cudaMemcpyHostToDevice, s));
+            dev_actions = h->d_actions;
+        }
     }
     if (b200_dynamics_step(h, dev_actions, stream)) return 1;
-    if (launch_env(h, step, lo, span, hist_step, PHASE_ALL, 0, stream)) return 1;
-    // rew | reset | time_out laid out back to back on both sides (B200Simulator allocates them so): one copy
+    // rew | reset | time_out laid out back to back on both sides (B200Simulator allocates them so): one copy ...
     const uint8_t *d_rew = (const uint8_t *)h->bufs.rew_buf;
     const bool packed = host_rew && host_reset && host_time_out && h->bufs.reset_buf == d_rew + 4 * (size_t)N &&
                         h->bufs.time_out_buf == d_rew + 5 * (size_t)N && host_reset == (uint8_t *)host_rew + 4 * (size_t)N &&
                         host_time_out == (uint8_t *)host_rew + 5 * (size_t)N;
+    // ... and none at all when the host slab is mapped into the device's address space: the env kernel's finalising CTA
+    // writes it over PCIe itself (EnvCall::host_slab; B200_ZERO_COPY_RESULTS=0: copy-engine transfer as before)
+    void *slab = nullptr;
+    if (packed && h->zero_copy_results && (6 * (size_t)N) % 16 == 0 && ((uintptr_t)d_rew & 15) == 0) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, host_rew) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
+            ((uintptr_t)pa.devicePointer & 15) == 0) slab = pa.devicePointer;
+        else (void)cudaGetLastError();
+    }
+    if (launch_env(h, step, lo, span, hist_step, PHASE_ALL, 0, stream, nullptr, slab)) return 1;
+    if (slab) return 0;
     if (packed) CK(cudaMemcpyAsync(host_rew, d_rew, 6 * (size_t)N, cudaMemcpyDeviceToHost, s));
     else {
         if (host_rew) CK(cudaMemcpyAsync(host_rew, h->bufs.rew_buf, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s));

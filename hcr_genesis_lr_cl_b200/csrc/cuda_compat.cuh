@@ -107,6 +107,18 @@ __device__ __forceinline__ void sts128(smaddr_t a, float x, float y, float z, fl
 }
 #endif
 
+// ---- 4-byte asynchronous global -> shared copy (LDGSTS): the loaded word never passes through a register, so a slow source
+// (pinned host memory read over PCIe) stalls nobody until cp_async_wait_all().  Emulator: a plain copy.
+#ifdef B200_WARP_EMU
+__device__ __forceinline__ void cp_async_f32(float *dst_smem, const float *src_gmem) { *dst_smem = *src_gmem; }
+__device__ __forceinline__ void cp_async_wait_all() {}
+#else
+__device__ __forceinline__ void cp_async_f32(float *dst_smem, const float *src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
+
 // ---- TMA (bulk async copy) + mbarrier helpers: 1-D cp.async.bulk between global and shared memory (sm_90+; SASS UBLKCP).
 // Sizes and both addresses must be multiples of 16 bytes.  Under the test emulator they degrade to memcpy.
 #ifdef B200_WARP_EMU

@@ -254,26 +254,13 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     }
 
     for (int e = lane; e < 48; e += 32) ws[WS_WARM + e] = B.contact_warm[env * 48 + e];
-    // ---------------- pre-step: action history, last_* (legged_robot.py:230-252, genesis_simulator.py:21-24) ----------------
-    float a_applied = 0.f;           // lane j < A: the action joint j is driven with (the clipped action, or a delayed one)
+    // ---------------- pre-step: last_* (genesis_simulator.py:21-24); the actions are only FETCHED here ----------------
+    // Each joint lane starts an asynchronous copy of its action into the (still unused) torque slot of its chain.  Nothing
+    // waits for it before the first substep's forward kinematics are done (see "actions arrive" below), so the latency of
+    // the read -- a PCIe round trip when b200_env_step hands over pinned HOST memory -- is off every warp's critical path.
     if (lane < A) {
         const int o = env * A + lane;
-        // sim_only (b200_simulator_step, plugin mode): LeggedRobot._pre_sim_step already clipped / delayed the actions and
-        // keeps the action history itself; only GenesisSimulator.step's part runs here
-        const float a = sim_only ? actions_in[o] : fminf(fmaxf(actions_in[o], -tf[TF_CLIP_ACTIONS]), tf[TF_CLIP_ACTIONS]);
-        if (!sim_only) {
-            B.llast_actions[o] = B.last_actions[o];
-            B.last_actions[o] = B.actions[o];
-            B.actions[o] = a;
-        }
-        a_applied = a;
-        if (T.i[TI_CTRL_DELAY] && !sim_only) {        // legged_robot.py:240-245: push the action into the env's queue, drive with slot action_delay
-            const int depth = T.i[TI_CTRL_DELAY_HI] + 1, dly = min(max(B.action_delay[env], 0), depth - 1);
-            float *qu = B.action_queue + (size_t)env * depth * A + lane;
-            for (int d = depth - 1; d > 0; d--) qu[d * A] = qu[(d - 1) * A];
-            qu[0] = a;
-            a_applied = qu[dly * A];
-        }
+        cp_async_f32(ws + WS_QS + 12 * (lane / 3) + 8 + lane % 3, actions_in + o);
         B.last_dof_vel[o] = B.dof_vel[o];
         if (lane < 3 * T.i[TI_F]) B.last_feet_vel[env * 3 * T.i[TI_F] + lane] = B.feet_vel[env * 3 * T.i[TI_F] + lane];
         if (lane < 3) { B.last_base_lin_vel[env * 3 + lane] = B.base_lin_vel[env * 3 + lane]; B.last_base_ang_vel[env * 3 + lane] = B.base_ang_vel[env * 3 + lane]; }
@@ -281,10 +268,8 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const int j = 3 * c + k, o = env * A + j;
-        const float a = __shfl_sync(B200_FULL_MASK, a_applied, j);
         const float arm_k = T.i[TI_RAND_ARMATURE] ? env_arm : ms[MS_BODY + (1 + j) * B200_BODY_STRIDE + 19];
         const float dmp_k = T.i[TI_RAND_JDAMPING] ? env_dmp : 0.f;
-        pd[k] = a * tf[TF_ACTION_SCALE] + tf[TF_DEFAULT_DOF_POS + j];
         pd[3 + k] = B.kp_scale[o] * tf[TF_KP]; pd[6 + k] = B.kd_scale[o] * tf[TF_KD];
         pd[9 + k] = arm_k + h * dmp_k; pd[12 + k] = dmp_k;
         if (k == 0) pd[15] = T.i[TI_RAND_JFRICTION] ? env_fls : 0.f;       // frictionloss bound: one value per env
@@ -293,7 +278,6 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         const int o = env * A + 3 * c;
         sts128(qs_a, B.dof_pos[o], B.dof_pos[o + 1], B.dof_pos[o + 2], 0.f);
         sts128(qs_a + 16u, B.dof_vel[o], B.dof_vel[o + 1], B.dof_vel[o + 2], 0.f);
-        sts128(qs_a + 32u, 0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
 
@@ -308,12 +292,6 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             const float4 a4 = lds128(st_a + 16u), b4 = lds128(st_a + 32u), c4 = lds128(st_a + 48u), q4 = lds128(qs_a), v4 = lds128(qs_a + 16u);
             Qw = a4.x; Qx = a4.y; Qy = a4.z; Qz = a4.w; vb = mk3(b4.x, b4.y, b4.z); wb = mk3(c4.x, c4.y, c4.z);
             q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; qd[0] = v4.x; qd[1] = v4.y; qd[2] = v4.z;
-        }
-        // ---------------- PD torque (genesis_simulator.py:630-642) ----------------
-        if (!last_pass) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) tau[k] = pd[3 + k] * (pd[k] - q[k]) - pd[6 + k] * qd[k];
-            if (leg) sts128(qs_a + 32u, tau[0], tau[1], tau[2], 0.f);      // the last substep's is the reported torque
         }
         // ---------------- forward kinematics, velocities, RNE, CRBA along this lane's chain ----------------
         const m33 R0 = quat_to_mat(Qw, Qx, Qy, Qz);
@@ -381,6 +359,43 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         }
         __syncwarp();
         if (last_pass) break;
+
+        if (sub == 0) {
+            // ---------------- actions arrive: clip, action history, delay queue (legged_robot.py:230-252) ----------------
+            cp_async_wait_all();
+            __syncwarp();
+            float a_applied = 0.f;           // lane j < A: the action joint j is driven with (the clipped action, or a delayed one)
+            if (lane < A) {
+                const int o = env * A + lane;
+                const float raw = ws[WS_QS + 12 * (lane / 3) + 8 + lane % 3];
+                // sim_only (b200_simulator_step, plugin mode): LeggedRobot._pre_sim_step already clipped / delayed the actions and
+                // keeps the action history itself; only GenesisSimulator.step's part runs here
+                const float a = sim_only ? raw : fminf(fmaxf(raw, -tf[TF_CLIP_ACTIONS]), tf[TF_CLIP_ACTIONS]);
+                if (!sim_only) {
+                    B.llast_actions[o] = B.last_actions[o];
+                    B.last_actions[o] = B.actions[o];
+                    B.actions[o] = a;
+                }
+                a_applied = a;
+                if (T.i[TI_CTRL_DELAY] && !sim_only) {        // legged_robot.py:240-245: push the action into the env's queue, drive with slot action_delay
+                    const int depth = T.i[TI_CTRL_DELAY_HI] + 1, dly = min(max(B.action_delay[env], 0), depth - 1);
+                    float *qu = B.action_queue + (size_t)env * depth * A + lane;
+                    for (int d = depth - 1; d > 0; d--) qu[d * A] = qu[(d - 1) * A];
+                    qu[0] = a;
+                    a_applied = qu[dly * A];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float a = __shfl_sync(B200_FULL_MASK, a_applied, 3 * c + k);
+                pd[k] = a * tf[TF_ACTION_SCALE] + tf[TF_DEFAULT_DOF_POS + 3 * c + k];
+            }
+            __syncwarp();                    // every lane has read its raw action before the torques replace them
+        }
+        // ---------------- PD torque (genesis_simulator.py:630-642) ----------------
+#pragma unroll
+        for (int k = 0; k < 3; k++) tau[k] = pd[3 + k] * (pd[k] - q[k]) - pd[6 + k] * qd[k];
+        if (leg) sts128(qs_a + 32u, tau[0], tau[1], tau[2], 0.f);      // the last substep's is the reported torque
 
         PHASE_SYNC_B();
         // backward pass along the chain: composite inertias, bias forces, CRBA columns
@@ -846,6 +861,30 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         for (; it < iters; it++) {
             const float fprev = f;
             const unsigned rd = 32u + 16u * (unsigned)(it & 1), wr = 48u - 16u * (unsigned)(it & 1);   // force copy read / written by this sweep
+#ifndef DYN_PGS_ROLLED
+            // unrolled over the (at most B200_KMAX) contacts: the shuffle sources and every shared-memory offset are
+            // immediates, no address / lane arithmetic and one predicate per contact instead of a counted loop
+            const smaddr_t bar_ = blk_a + rd, baw_ = blk_a + wr;
+#pragma unroll
+            for (int c2 = 0; c2 < B200_KMAX; c2++) {
+                if (c2 >= nc) break;
+                const float g = fmaf(Rr, f, wres);
+                const float g0 = __shfl_sync(B200_FULL_MASK, g, 3 * c2), g1 = __shfl_sync(B200_FULL_MASK, g, 3 * c2 + 1), g2 = __shfl_sync(B200_FULL_MASK, g, 3 * c2 + 2);
+                const float4 q0 = lds128(blk_a + 64u * c2), fc = lds128(bar_ + 64u * c2);
+                const float2 q1 = lds64(blk_a + 64u * c2 + 16u);
+                // the first shuffle to arrive feeds the innermost product of each chain
+                float n0 = fmaf(-q0.z, g2, fmaf(-q0.y, g1, fmaf(-q0.x, g0, fc.x)));
+                float n1 = fmaf(-q1.x, g2, fmaf(-q0.w, g1, fmaf(-q0.y, g0, fc.y)));
+                float n2 = fmaf(-q1.y, g2, fmaf(-q1.x, g1, fmaf(-q0.z, g0, fc.z)));
+                n0 = fmaxf(n0, 0.f);
+                const float lim = mu * n0, t2 = fmaf(n1, n1, n2 * n2);
+                if (t2 > lim * lim) { const float sc = lim * fast_rsqrtf(fmaxf(t2, 1e-30f)); n1 *= sc; n2 *= sc; }      // warp-uniform
+                wres = fmaf(lds32(arow_a + 396u * c2), n0 - fc.x, wres);
+                wres = fmaf(lds32(arow_a + 396u * c2 + 132u), n1 - fc.y, wres);
+                wres = fmaf(lds32(arow_a + 396u * c2 + 264u), n2 - fc.z, wres);
+                if (lane == 3 * c2) sts128(baw_ + 64u * c2, n0, n1, n2, 0.f);
+            }
+#else
             smaddr_t ba = blk_a, aa = arow_a;
             int src = 0;
             for (int c2 = 0; c2 < nc; c2++, ba += 64u, aa += 396u, src += 3) {
@@ -864,6 +903,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                 wres = fmaf(lds32(aa + 264u), n2 - fc.z, wres);
                 if (lane == src) sts128(ba + wr, n0, n1, n2, 0.f);
             }
+#endif
             __syncwarp();                                  // the forces written by the contacts' first lanes ...
             if (lane < 3 * nc) f = lds32(own_a + wr);      // ... are this sweep's result for the lanes that own those rows
             // joint-limit (f >= 0) and frictionloss (|f| <= bound) rows

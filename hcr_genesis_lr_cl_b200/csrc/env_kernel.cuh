@@ -76,6 +76,12 @@ struct EnvCall {
     // (include/b200_step.h, B200_SS_*) that step_advance_kernel moved forward just before, so that a captured CUDA graph of
     // the step can be replayed without any per-launch parameter from the host.  NULL for host-stepped launches.
     const int32_t *dstate;
+    // b200_env_step with pinned host result buffers: device-visible address of the caller's packed host slab
+    // (rew f32[N] | reset u8[N] | time_out u8[N], 16-byte aligned, 6 N a multiple of 16) -- the CTA that finalises the
+    // step's statistics also copies the slab from rew_buf into it with 16-byte stores over PCIe, so that no copy-engine
+    // operation follows the kernel.  NULL: nothing is written to the host by the kernel.
+    uint4 *host_slab;
+    int host_slab_vecs;
 };
 
 // The device-resident step state one policy step further (b200_env_step_device launches it ahead of the dynamics kernel):
@@ -1103,11 +1109,34 @@ __device__ __forceinline__ void stats_finalize(float *stats, int n_sums, const E
 
 // A CTA that took its ticket early (env_post_step_warp): its first warp finalises if the ticket was the last one.  No CTA
 // barrier, no fence unless last -- the other warps just leave.
-__device__ __forceinline__ void env_finalize_ticket(const B200Buffers &B, int n_sums, const EnvCall &call, int ticket) {
-    if (threadIdx.x >= 32) return;
-    const bool last = __shfl_sync(B200_FULL_MASK, ticket, 0) == (int)gridDim.x - 1;
-    if (!last) return;
-    __threadfence();
+// rew | reset | time_out of every env into the caller's pinned host slab (EnvCall::host_slab): run by the whole CTA that
+// took the last ticket -- every other CTA wrote its rows before its fence and ticket -- with all loads (L2, not this SM's
+// L1) in flight before the first store.
+static __device__ __noinline__ void env_host_slab_copy(const uint4 *src, uint4 *dst, int vecs) {    // out of line: run by one CTA per launch,
+    constexpr int BATCH = 6;                                                                    // must not shape the kernel's registers
+    for (int base = 0; base < vecs; base += BATCH * (int)blockDim.x) {
+        uint4 v[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; k++) v[k] = __ldcg(src + min(base + k * (int)blockDim.x + (int)threadIdx.x, vecs - 1));
+#pragma unroll
+        for (int k = 0; k < BATCH; k++) { const int i = base + k * (int)blockDim.x + (int)threadIdx.x; if (i < vecs) dst[i] = v[k]; }
+    }
+}
+
+__device__ __forceinline__ void env_finalize_ticket(const B200Buffers &B, int n_sums, const EnvCall &call, int ticket, int *last_w) {
+    if (call.host_slab) {                // uniform over the grid: one more CTA barrier, only on the host-buffer path
+        if (threadIdx.x == 0) *last_w = ticket == (int)gridDim.x - 1;
+        __syncthreads();
+        if (!*last_w) return;
+        __threadfence();
+        env_host_slab_copy((const uint4 *)B.rew_buf, call.host_slab, call.host_slab_vecs);
+        if (threadIdx.x >= 32) return;
+    } else {
+        if (threadIdx.x >= 32) return;
+        const bool last = __shfl_sync(B200_FULL_MASK, ticket, 0) == (int)gridDim.x - 1;
+        if (!last) return;
+        __threadfence();
+    }
     for (int i = (int)threadIdx.x; i < n_sums + B200_STATS_EXTRA; i += 32) stats_finalize(B.stats, n_sums, call, i);
     if (threadIdx.x == 0) B.global_flags[1] = 0;
 }
@@ -1123,6 +1152,7 @@ __device__ __forceinline__ void env_finalize_cta(const B200Buffers &B, int n_sum
     __syncthreads();
     if (*last) {
         __threadfence();
+        if (call.host_slab) env_host_slab_copy((const uint4 *)B.rew_buf, call.host_slab, call.host_slab_vecs);
         stats_finalize(B.stats, n_sums, call, (int)threadIdx.x);
         if (threadIdx.x == 0) B.global_flags[1] = 0;
     }
@@ -1158,7 +1188,7 @@ __device__ __forceinline__ void env_post_step_body_impl(const TaskDev &T, const 
 #undef X_VIEW
 #ifndef ENV_NO_SECTION_SYNC
         const int ticket = env_post_step_warp<S>(T, B, R, warp, tr, call, es + warp * ES_TOTAL, env, lane, true, true, bar, cta_acc);
-        if (call.finalize) env_finalize_ticket(B, ti[TI_N_SUMS], call, ticket);
+        if (call.finalize) env_finalize_ticket(B, ti[TI_N_SUMS], call, ticket, (int *)(smem + 2));
         return;
 #else
         env_post_step_warp<S>(T, B, R, warp, tr, call, es + warp * ES_TOTAL, env, lane, true, false, bar, cta_acc);

@@ -232,3 +232,36 @@ def test_emulated_nonfinite_state_is_contained_and_reset():
     assert not torch.equal(b["base_pos"][2], pose)                                          # re-placed by reset_idx
     env.step(a)
     assert torch.isfinite(b["obs_buf"]).all() and int(b["global_flags"][2]) == 1
+
+
+@pytest.mark.parametrize("zero_copy", ["1", "0"])
+def test_emulated_host_buffer_step_equals_the_device_step(monkeypatch, zero_copy):
+    """b200_env_step with HOST buffers -- actions read in place and the rew | reset | time_out slab written by the env kernel's
+    finalising CTA (zero copy, the default), or staged through copies (B200_ZERO_COPY_*=0) -- leaves the same state and the
+    same host results as the step with device-resident actions.  Ragged slab sizes (6 N not a multiple of 16) take the copy path."""
+    import numpy as np
+    import torch
+    from emu_backend import EmuFusedLeggedEnv
+    from hcr_genesis_lr_cl_b200 import task_spec as TS
+    from hcr_genesis_lr_cl_b200.terrain_assets import terrain_for
+    monkeypatch.setenv("B200_ZERO_COPY_ACTIONS", zero_copy)
+    monkeypatch.setenv("B200_ZERO_COPY_RESULTS", zero_copy)
+    spec = TS.PRESETS["go2_ts"]()
+    for N in (16, 13):
+        a_env = EmuFusedLeggedEnv(spec, N, torch.device("cpu"), terrain=terrain_for(spec))
+        b_env = EmuFusedLeggedEnv(spec, N, torch.device("cpu"), terrain=terrain_for(spec))
+        a_env.reset(); b_env.reset()
+        ep = a_env.episode_length_buf
+        ep[0::3] = int(a_env.max_episode_length) - 2          # time-outs (and resets) inside the window
+        b_env.episode_length_buf = ep.clone()
+        rew, rst, tmo = b_env.simulator.make_host_step_buffers()
+        rng = np.random.default_rng(5)
+        for t in range(4):
+            act = torch.from_numpy(rng.normal(size=(N, spec.num_actions)).astype(np.float32))
+            host_act = act.clone(); host_act._emu_host = True
+            out_a = a_env.step(act)
+            out_b = b_env.step_host(host_act, rew, rst, tmo)
+            for x, y in zip(out_a[:6], out_b[:6]):
+                assert torch.equal(x, y)
+            assert torch.equal(rew, a_env.rew_buf) and torch.equal(rst, a_env.reset_buf) and torch.equal(tmo, a_env.time_out_buf)
+        assert int(a_env.reset_buf.sum()) >= 0

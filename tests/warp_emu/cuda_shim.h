@@ -36,6 +36,12 @@ template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { *p = 
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+// "device" memory is host memory here: every pointer reads as mapped host memory, so the zero-copy paths of b200_env_step run
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void *devicePointer; void *hostPointer; };
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p) {
+    a->type = cudaMemoryTypeHost; a->device = 0; a->devicePointer = (void *)p; a->hostPointer = (void *)p; return cudaSuccess;
+}
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (void *)1; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }

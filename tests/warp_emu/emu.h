@@ -16,6 +16,7 @@
 #define __global__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__
 #define B200_LAUNCH_BOUNDS(t, b)
 
@@ -45,6 +46,7 @@ static inline float __shfl_down_sync(unsigned, float v, int d) { return emu_floa
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 static inline unsigned __ballot_sync(unsigned, bool p) { return emu_ballot(p); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_sync(); }
