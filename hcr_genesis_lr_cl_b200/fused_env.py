@@ -123,6 +123,12 @@ class FusedLeggedEnv:
             return self.obs_history
         if name == "privileged_obs_buf" and (self.__dict__.get("stacked") or self.__dict__["spec"].obs_kind == "go2_dreamwaq"):
             return self.critic_obs_buf
+        # sizes the reference's runners read off the env (ts_runner.py:56-67, ee_runner.py, dreamwaq_runner.py, cts_runner.py:
+        # num_latent_dims, num_explicit_dims, num_decoder_output, num_teacher, ...) live in cfg.env, like in the task classes
+        # (legged_robot_ts.py:92, legged_robot_dreamwaq.py:99-101, legged_robot_ee.py:88-89)
+        cfg = self.__dict__.get("cfg")
+        if name.startswith("num_") and cfg is not None and hasattr(getattr(cfg, "env", None), name):
+            return getattr(cfg.env, name)
         raise AttributeError(name)
 
     @property

@@ -1,0 +1,110 @@
+"""The reference's own training entry points, unchanged, on top of the backend (north_star: "LeggedRobot and every go2_* /
+tron1 task class ... and the rsl_rl OnPolicyRunner use it unchanged"): `task_registry.make_alg_runner` builds the runner
+class the task's train cfg names (OnPolicyRunner, TSRunner, EERunner, CTSRunner, DreamWaQRunner; task_registry.py:74-135)
+and `runner.learn` (on_policy_runner.py:100-160 and its subclasses) collects rollouts and updates the policy
+
+  * in PLUGIN mode: the env is the reference's task class over `B200Simulator` (task_registry.make_env through the import hook),
+  * in FUSED mode: the env is `FusedLeggedEnv` built from the same cfg (`TaskSpec.from_reference_cfg`).
+
+Checked: the iteration counter, finite losses, parameters that moved, a checkpoint on disk.  CPU variant: the warp emulator
+behind the same C ABI; GPU variant (`-m gpu`): libb200step.so on cuda:0, every fused task."""
+import math
+import os
+import tempfile
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from plugin_util import install_plugin, make_plugin_env, reference_root, uninstall_plugin
+
+needs_reference = pytest.mark.skipif(reference_root() is None, reason="no reference tree (/root/reference or baseline/_ref)")
+
+
+def _args(task, n, cpu):
+    return SimpleNamespace(task=task, headless=True, cpu=cpu, num_envs=n, debug=False, max_iterations=None, resume=False,
+                           sync_wandb=False, ckpt=-1, load_run=None, export_onnx=False, use_joystick=False, joystick_type=None,
+                           follow_robot=False, experiment_name=None, run_name=None, seed=None)
+
+
+def _edit(env_cfg, n, plugin=False):
+    if hasattr(env_cfg.env, "num_teacher"):          # go2_cts_config.py:8 derives it from the class-level 4096 envs
+        env_cfg.env.num_teacher = n // 4 * 3
+    # SURVEY R1 (a defect of the reference, independent of the backend): common_cfgs.py:101 names 5 patterns = 17 links while
+    # go2_ts_config.py:9,14 / go2_cts_config.py:10,15 size the networks for 12, so the reference's own env + runner do not fit
+    # together as shipped.  The reference env reports the cfg's widths, hence the documented 12-link list in plugin mode; the
+    # fused env reports the widths it really emits and trains with either list.
+    if plugin and hasattr(env_cfg.asset, "contact_state_link_names") and getattr(env_cfg.env, "num_privileged_obs", None) == 94:
+        env_cfg.asset.contact_state_link_names = ["thigh", "calf", "foot"]
+
+
+def _learn(env, task, train_cfg, n, cpu, iters, steps):
+    from legged_gym.utils.task_registry import task_registry
+    train_cfg.runner.num_steps_per_env = steps
+    train_cfg.runner.save_interval = 1000
+    with tempfile.TemporaryDirectory() as d:
+        runner, _ = task_registry.make_alg_runner(env=env, name=task, args=_args(task, n, cpu), train_cfg=train_cfg, log_root=d)
+        assert type(runner).__name__ == train_cfg.runner_class_name
+        ac = runner.alg.actor_critic
+        before = [p.detach().clone() for p in ac.parameters()]
+        runner.learn(num_learning_iterations=iters, init_at_random_ep_len=True)
+        assert runner.current_learning_iteration == iters
+        assert any(not torch.equal(a, b.detach()) for a, b in zip(before, ac.parameters())), "no parameter moved"
+        assert all(bool(torch.isfinite(p).all()) for p in ac.parameters())
+        saved = [f for _, _, fs in os.walk(d) for f in fs if f.endswith(".pt")]
+        assert saved, "runner.learn left no checkpoint"
+    assert runner.tot_timesteps == iters * steps * n and math.isfinite(runner.tot_time)
+
+
+def _plugin(task, impl, cpu, n, iters, steps):
+    try:
+        env, env_cfg, train_cfg = make_plugin_env(task, n, impl=impl, cpu=cpu, cfg_edit=lambda c: _edit(c, n, plugin=True))
+        _learn(env, task, train_cfg, n, cpu, iters, steps)
+    finally:
+        uninstall_plugin()
+
+
+def _fused(task, env_cls, cpu, n, iters, steps):
+    try:
+        install_plugin()
+        import legged_gym.envs  # noqa: F401
+        from legged_gym.utils.task_registry import task_registry
+        from hcr_genesis_lr_cl_b200.task_spec import TaskSpec
+        from hcr_genesis_lr_cl_b200.terrain_assets import terrain_for
+        env_cfg, train_cfg = task_registry.get_cfgs(name=task)
+        env_cfg.env.num_envs = n
+        _edit(env_cfg, n)
+        spec = TaskSpec.from_reference_cfg(env_cfg, task)
+        env = env_cls(spec, n, torch.device("cpu") if cpu else torch.device("cuda:0"), terrain=terrain_for(spec), cfg=env_cfg)
+        _learn(env, task, train_cfg, n, cpu, iters, steps)
+    finally:
+        uninstall_plugin()
+
+
+@needs_reference
+@pytest.mark.parametrize("task", ["go2", "go2_ts"])
+def test_reference_runner_trains_in_plugin_mode_emulated(task):
+    from emu_backend import EmuB200Simulator
+    _plugin(task, EmuB200Simulator, cpu=True, n=8, iters=1, steps=4)
+
+
+@needs_reference
+@pytest.mark.parametrize("task", ["go2", "go2_ts", "go2_cts", "tron1_pf_ee"])
+def test_reference_runner_trains_on_the_fused_env_emulated(task):
+    from emu_backend import EmuFusedLeggedEnv
+    _fused(task, EmuFusedLeggedEnv, cpu=True, n=8, iters=1, steps=4)
+
+
+@needs_reference
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["go2", "go2_ts", "go2_wtw", "tron1_pf_ee"])
+def test_reference_runner_trains_in_plugin_mode_gpu(task):
+    _plugin(task, None, cpu=False, n=256, iters=2, steps=8)
+
+
+@needs_reference
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["go2", "go2_ts", "go2_cat", "go2_wtw", "go2_cts", "go2_ee", "go2_dreamwaq", "tron1_pf", "tron1_pf_ee"])
+def test_reference_runner_trains_on_the_fused_env_gpu(task):
+    from hcr_genesis_lr_cl_b200.fused_env import FusedLeggedEnv
+    _fused(task, FusedLeggedEnv, cpu=False, n=256, iters=2, steps=8)
