@@ -57,8 +57,55 @@ def backend_class(impl=None):
     return B200Simulator
 
 
-def install(reference_root: Optional[str] = None, impl=None, fix_reference_defects: bool = True):
+_MAKE_ENV = None     # task_registry.make_env before install(fused=True)
+
+
+def _route_make_env_to_fused(env_class=None):
+    """`task_registry.make_env(name, args)` (task_registry.py:35-72, what scripts/train.py calls) hands out a `FusedLeggedEnv`
+    for every task whose cfg has a fused descriptor -- the reference's cfg handling (get_cfgs, update_cfg_from_args, set_seed)
+    and its terrain generator are used as they are; anything else (an unsupported task, reward term or asset) falls back to
+    the task class over the plugin backend with a warning."""
+    global _MAKE_ENV
+    import warnings
+    tr = importlib.import_module("legged_gym.utils.task_registry")
+    reg = tr.task_registry
+    if _MAKE_ENV is None:
+        _MAKE_ENV = reg.make_env
+
+    def make_env(name, args=None, env_cfg=None):
+        from .fused_env import FusedLeggedEnv
+        from .task_spec import TaskSpec
+        if args is None:
+            args = tr.get_args()
+        if name not in reg.task_classes:
+            raise ValueError(f"Task with name: {name} was not registered")
+        if env_cfg is None:
+            env_cfg, _ = reg.get_cfgs(name)
+        env_cfg, _ = tr.update_cfg_from_args(env_cfg, None, args)
+        try:
+            spec = TaskSpec.from_reference_cfg(env_cfg, name)
+        except (ValueError, KeyError, AttributeError) as e:
+            warnings.warn(f"B200 backend: task {name!r} has no fused descriptor ({e}); running the reference task class in plugin mode")
+            return _MAKE_ENV(name, args=args, env_cfg=env_cfg)
+        tr.set_seed(env_cfg.seed)
+        terrain = None
+        if spec.heightfield:
+            from legged_gym.utils.terrain import Terrain        # the reference generator, unchanged (genesis_simulator.py:267-269)
+            t = Terrain(env_cfg.terrain)
+            terrain = (t.heightsamples, t.env_origins)
+        cls = env_class or FusedLeggedEnv
+        env = cls(spec, int(env_cfg.env.num_envs), "cpu" if args.cpu else "cuda:0", terrain=terrain, cfg=env_cfg)
+        return env, env_cfg
+
+    reg.make_env = make_env
+
+
+def install(reference_root: Optional[str] = None, impl=None, fix_reference_defects: bool = True, fused: bool = False, fused_env_class=None):
     """Route the reference's backend dispatch to the B200 backend; returns the backend class.
+
+    ``fused=True``: additionally ``task_registry.make_env`` returns a ``FusedLeggedEnv`` (whole ``env.step`` = one C-ABI
+    call, same return tuples) for the tasks with a fused descriptor, so that ``scripts/train.py --task go2_ts`` runs fused
+    without any edit of the reference tree.
 
     ``fix_reference_defects``: also add the two harness-level aliases without which ``go2_wtw`` / ``tron1_pf_ee`` crash on
     any backend as shipped (``update_command_curriculum`` is called but only ``_update_command_curriculum``
@@ -88,6 +135,8 @@ def install(reference_root: Optional[str] = None, impl=None, fix_reference_defec
         if not hasattr(LeggedRobot, "update_command_curriculum"):
             LeggedRobot.update_command_curriculum = LeggedRobot._update_command_curriculum
     _BACKEND = cls
+    if fused:
+        _route_make_env_to_fused(fused_env_class)
     return cls
 
 
@@ -97,8 +146,10 @@ def installed():
 
 def uninstall() -> None:
     """Give BaseTask its original Genesis backend back (tests that run both harnesses in one process)."""
-    global _BACKEND, _ORIGINAL
+    global _BACKEND, _ORIGINAL, _MAKE_ENV
     if _ORIGINAL is not None:
         bt = importlib.import_module("legged_gym.envs.base.base_task")
         bt.GenesisSimulator = _ORIGINAL
-    _BACKEND = _ORIGINAL = None
+    if _MAKE_ENV is not None:
+        importlib.import_module("legged_gym.utils.task_registry").task_registry.__dict__.pop("make_env", None)
+    _BACKEND = _ORIGINAL = _MAKE_ENV = None

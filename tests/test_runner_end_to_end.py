@@ -95,6 +95,38 @@ def test_reference_runner_trains_on_the_fused_env_emulated(task):
     _fused(task, EmuFusedLeggedEnv, cpu=True, n=8, iters=1, steps=4)
 
 
+def _train_script_path(task, env_cls, cpu, n, iters, steps):
+    """What scripts/train.py does (train.py:14-22): make_env, make_alg_runner, learn -- after plugin.install(fused=True)."""
+    from hcr_genesis_lr_cl_b200 import plugin
+    from hcr_genesis_lr_cl_b200.fused_env import FusedLeggedEnv
+    try:
+        install_plugin()
+        plugin.install(fused=True, fused_env_class=env_cls)
+        from legged_gym.utils.task_registry import task_registry
+        env_cfg, train_cfg = task_registry.get_cfgs(name=task)
+        _edit(env_cfg, n)
+        env, env_cfg = task_registry.make_env(name=task, args=_args(task, n, cpu), env_cfg=env_cfg)
+        assert isinstance(env, FusedLeggedEnv) and env.num_envs == n
+        _learn(env, task, train_cfg, n, cpu, iters, steps)
+    finally:
+        uninstall_plugin()
+    from legged_gym.utils.task_registry import task_registry
+    assert "make_env" not in task_registry.__dict__            # uninstall gives the reference its own make_env back
+
+
+@needs_reference
+def test_train_script_path_gets_the_fused_env_emulated():
+    from emu_backend import EmuFusedLeggedEnv
+    _train_script_path("go2_ts", EmuFusedLeggedEnv, cpu=True, n=8, iters=1, steps=4)
+
+
+@needs_reference
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["go2_ts", "go2_wtw"])
+def test_train_script_path_gets_the_fused_env_gpu(task):
+    _train_script_path(task, None, cpu=False, n=256, iters=2, steps=8)
+
+
 @needs_reference
 @pytest.mark.gpu
 @pytest.mark.parametrize("task", ["go2", "go2_ts", "go2_wtw", "tron1_pf_ee"])
