@@ -46,7 +46,8 @@ struct B200Handle {
     bool side_enabled = true;
     int env_preset = -1;           // instantiation of the env kernel: index into env_presets.inc, -1 = generic
     float *d_actions = nullptr;    // staging of b200_env_step's host actions (when they cannot be read in place)
-    bool zero_copy_actions = true; // pinned host actions are read by the dynamics kernel in place (B200_ZERO_COPY_ACTIONS=0: staged copy)
+    int zero_copy_actions = 2;     // pinned host actions: 2 = staged by a copy kernel the dynamics kernel is the programmatic dependent of (default),
+                                   // 1 = read in place by the dynamics kernel, 0 = copy-engine transfer (B200_ZERO_COPY_ACTIONS)
     bool zero_copy_results = true; // the env kernel writes rew | reset | time_out into the caller's pinned slab (B200_ZERO_COPY_RESULTS=0: D2H copy)
     bool stats_zeroed = false;
     bool order_enabled = true;     // dynamics warps take envs sorted by solver cost (dynamics_order_kernel); B200_DYN_ORDER=0: slot w = env w
@@ -106,7 +107,7 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
         const char *o = getenv("B200_DYN_ORDER");
         h->order_enabled = !(o && o[0] == '0');
         const char *z = getenv("B200_ZERO_COPY_ACTIONS");
-        h->zero_copy_actions = !(z && z[0] == '0');
+        h->zero_copy_actions = (z && z[0] >= '0' && z[0] <= '2') ? z[0] - '0' : 2;
         const char *zr = getenv("B200_ZERO_COPY_RESULTS");
         h->zero_copy_results = !(zr && zr[0] == '0');
     }
@@ -162,7 +163,9 @@ static int check_ready(B200Handle *h, const char *who) {
     return 0;
 }
 
-static int launch_dynamics(B200Handle *h, const float *actions, void *stream, int sim_only) {
+// `host_actions` != NULL: device-visible address of pinned host actions; they are staged into h->d_actions by a copy kernel the
+// dynamics kernel is launched as the programmatic dependent of (fetch_actions_kernel), `actions` is ignored
+static int launch_dynamics(B200Handle *h, const float *actions, void *stream, int sim_only, const float *host_actions = nullptr) {
     DeviceGuard guard(h);
     const int N = h->task.i[TI_NUM_ENVS];
     const dim3 grid((N + DYN_WARPS_PER_BLOCK - 1) / DYN_WARPS_PER_BLOCK), block(DYN_WARPS_PER_BLOCK * 32);
@@ -181,8 +184,28 @@ static int launch_dynamics(B200Handle *h, const float *actions, void *stream, in
         CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     }
     const int par = ordered ? (int)(h->dyn_launches & 1) : -1;
-    if (h->task.i[TI_C] == 4) B200_LAUNCH(dynamics_step_kernel<4>, grid, block, h->dyn_smem, s, h->task, h->bufs, h->model, h->terrain, actions, par, sim_only);
-    else B200_LAUNCH(dynamics_step_kernel<2>, grid, block, h->dyn_smem, s, h->task, h->bufs, h->model, h->terrain, actions, par, sim_only);
+    int mode = sim_only ? DYN_MODE_SIM_ONLY : 0;
+#ifndef B200_WARP_EMU
+    if (host_actions) {
+        const int nvec = (int)(((size_t)N * h->task.i[TI_A] * sizeof(float)) / 16);
+        if (!h->d_actions) CK(cudaMalloc(&h->d_actions, sizeof(float) * (size_t)N * h->task.i[TI_A]));
+        fetch_actions_kernel<<<(nvec + 255) / 256, 256, 0, s>>>((const uint4 *)host_actions, (uint4 *)h->d_actions, nvec);
+        h->launches++;
+        CK(cudaGetLastError());
+        actions = h->d_actions;
+        mode |= DYN_MODE_LATE_ACTIONS;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = (size_t)h->dyn_smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (h->task.i[TI_C] == 4) CK(cudaLaunchKernelEx(&cfg, dynamics_step_kernel<4>, h->task, h->bufs, h->model, h->terrain, actions, par, mode));
+        else CK(cudaLaunchKernelEx(&cfg, dynamics_step_kernel<2>, h->task, h->bufs, h->model, h->terrain, actions, par, mode));
+    } else
+#endif
+    if (h->task.i[TI_C] == 4) B200_LAUNCH(dynamics_step_kernel<4>, grid, block, h->dyn_smem, s, h->task, h->bufs, h->model, h->terrain, actions, par, mode);
+    else B200_LAUNCH(dynamics_step_kernel<2>, grid, block, h->dyn_smem, s, h->task, h->bufs, h->model, h->terrain, actions, par, mode);
     h->dyn_launches++;
     h->launches++;
     h->stats_zeroed = true;
@@ -280,11 +303,13 @@ int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long
     DeviceGuard guard(h);
     const int N = h->task.i[TI_NUM_ENVS], A = h->task.i[TI_A];
     cudaStream_t s = (cudaStream_t)stream;
-    const float *dev_actions = actions;
+    const float *dev_actions = actions, *staged = nullptr;
     if (actions_on_host) {
-        // Pinned (page-locked, mapped) host memory is addressable from the device: the dynamics kernel reads each env's A
-        // actions once, in its prologue, straight over PCIe -- no staging copy, no copy-engine operation in front of the
-        // launch (B200_ZERO_COPY_ACTIONS=0, or a buffer the driver does not report as mapped: staged copy as before).
+        // Pinned (page-locked, mapped) host memory is addressable from the device, so no copy-engine operation has to sit in
+        // front of the launch.  Default (B200_ZERO_COPY_ACTIONS=2): a copy kernel stages the actions with 512-byte requests and
+        // the dynamics kernel, its programmatic dependent, waits for them only where the first torque needs them
+        // (fetch_actions_kernel).  =1: every env's warp reads its A actions in place (32-byte sectors over PCIe: ~6 us
+        // exposed at 4096 envs).  =0, or a buffer the driver does not report as mapped: cudaMemcpyAsync as before.
         const float *mapped = nullptr;
         if (h->zero_copy_actions) {
             cudaPointerAttributes pa;
@@ -292,14 +317,15 @@ int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long
                 mapped = (const float *)pa.devicePointer;
             else (void)cudaGetLastError();
         }
-        if (mapped) dev_actions = mapped;
+        if (mapped && h->zero_copy_actions == 2 && ((size_t)N * A * sizeof(float)) % 16 == 0 && ((uintptr_t)mapped & 15) == 0) staged = mapped;
+        else if (mapped) dev_actions = mapped;
         else {
             if (!h->d_actions) CK(cudaMalloc(&h->d_actions, sizeof(float) * (size_t)N * A));
             CK(cudaMemcpyAsync(h->d_actions, actions, sizeof(float) * (size_t)N * A, cudaMemcpyHostToDevice, s));
             dev_actions = h->d_actions;
         }
     }
-    if (b200_dynamics_step(h, dev_actions, stream)) return 1;
+    if (launch_dynamics(h, dev_actions, stream, 0, staged)) return 1;
     // rew | reset | time_out laid out back to back on both sides (B200Simulator allocates them so): one copy ...
     const uint8_t *d_rew = (const uint8_t *)h->bufs.rew_buf;
     const bool packed = host_rew && host_reset && host_time_out && h->bufs.reset_buf == d_rew + 4 * (size_t)N &&

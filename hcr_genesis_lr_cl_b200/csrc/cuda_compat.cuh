@@ -119,6 +119,14 @@ __device__ __forceinline__ void cp_async_f32(float *dst_smem, const float *src_g
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
+// ---- programmatic dependent launch: wait until the grid this one depends on has completed and its writes are visible
+// (a no-op for a launch without a programmatic dependency)
+__device__ __forceinline__ void grid_dependency_wait() {
+#ifndef B200_WARP_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 // ---- TMA (bulk async copy) + mbarrier helpers: 1-D cp.async.bulk between global and shared memory (sm_90+; SASS UBLKCP).
 // Sizes and both addresses must be multiples of 16 bytes.  Under the test emulator they degrade to memcpy.
 #ifdef B200_WARP_EMU

@@ -48,6 +48,8 @@
 #define PHASE_SYNC_D() do { if (DYN_SYNC_MASK & 8) PHASE_SYNC(); } while (0)
 #define PHASE_SYNC_E() do { if (DYN_SYNC_MASK & 16) PHASE_SYNC(); } while (0)
 #ifndef DYN_MIN_BLOCKS
+#define DYN_MODE_SIM_ONLY 1        // b200_simulator_step (plugin mode): no pre-step book-keeping
+#define DYN_MODE_LATE_ACTIONS 2    // the action buffer is filled by fetch_actions_kernel, this launch is its programmatic dependent
 #define DYN_MIN_BLOCKS 4      // resident CTAs per SM the register allocator must allow: 4 x 7 warps = 28 envs per SM at 72 regs/thread
 #endif
 
@@ -225,7 +227,9 @@ __device__ __forceinline__ void spd6_inverse(const float *S, float *Sinv) {
 // One env, `decimation` substeps.  C chains of 3 joints.  All 32 lanes execute every collective.
 template <int C>
 __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const TerrainDev &tr, const float *ms, float *ws,
-                              const float *actions_in, int env, int lane, int *cost_out, const int sim_only) {
+                              const float *actions_in, int env, int lane, int *cost_out, const int mode) {
+    const int sim_only = mode & DYN_MODE_SIM_ONLY;
+    const bool late_actions = (mode & DYN_MODE_LATE_ACTIONS) != 0;   // `actions_in` is being filled by fetch_actions_kernel (see there)
     const float *tf = T.f;
     const int A = 3 * C, L = T.i[TI_L], NS = T.i[TI_NSPHERES];
     const int *msi = (const int *)(ms + MS_INT);
@@ -260,7 +264,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
     // the read -- a PCIe round trip when b200_env_step hands over pinned HOST memory -- is off every warp's critical path.
     if (lane < A) {
         const int o = env * A + lane;
-        cp_async_f32(ws + WS_QS + 12 * (lane / 3) + 8 + lane % 3, actions_in + o);
+        if (!late_actions) cp_async_f32(ws + WS_QS + 12 * (lane / 3) + 8 + lane % 3, actions_in + o);
         B.last_dof_vel[o] = B.dof_vel[o];
         if (lane < 3 * T.i[TI_F]) B.last_feet_vel[env * 3 * T.i[TI_F] + lane] = B.feet_vel[env * 3 * T.i[TI_F] + lane];
         if (lane < 3) { B.last_base_lin_vel[env * 3 + lane] = B.base_lin_vel[env * 3 + lane]; B.last_base_ang_vel[env * 3 + lane] = B.base_ang_vel[env * 3 + lane]; }
@@ -362,12 +366,13 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 
         if (sub == 0) {
             // ---------------- actions arrive: clip, action history, delay queue (legged_robot.py:230-252) ----------------
-            cp_async_wait_all();
+            if (late_actions) grid_dependency_wait();       // the copy kernel launched ahead of this one has finished and is visible
+            else cp_async_wait_all();
             __syncwarp();
             float a_applied = 0.f;           // lane j < A: the action joint j is driven with (the clipped action, or a delayed one)
             if (lane < A) {
                 const int o = env * A + lane;
-                const float raw = ws[WS_QS + 12 * (lane / 3) + 8 + lane % 3];
+                const float raw = late_actions ? __ldcg(actions_in + o) : ws[WS_QS + 12 * (lane / 3) + 8 + lane % 3];
                 // sim_only (b200_simulator_step, plugin mode): LeggedRobot._pre_sim_step already clipped / delayed the actions and
                 // keeps the action history itself; only GenesisSimulator.step's part runs here
                 const float a = sim_only ? raw : fminf(fmaxf(raw, -tf[TF_CLIP_ACTIONS]), tf[TF_CLIP_ACTIONS]);
@@ -1121,10 +1126,24 @@ __global__ void dynamics_order_kernel(const int32_t *cost, int32_t *order_delta,
     }
 }
 
+// Host actions, staged: b200_env_step with pinned HOST actions launches this copy kernel right in front of the dynamics
+// kernel -- 16 bytes per thread, i.e. 512-byte requests over PCIe instead of the 32-byte sectors per-env reads would make
+// -- and the dynamics kernel as its PROGRAMMATIC DEPENDENT (cudaLaunchAttributeProgrammaticStreamSerialization): every copy
+// CTA releases the dependent launch first thing, so the dynamics CTAs load their state and run the first forward-kinematics
+// pass while the actions cross the bus, and only wait (griddepcontrol.wait = the copy grid has completed and is visible)
+// where the first torque needs them.
+__global__ void fetch_actions_kernel(const uint4 *__restrict__ src_host, uint4 *__restrict__ dst, int nvec) {
+#ifndef B200_WARP_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nvec) dst[i] = src_host[i];
+}
+
 template <int C>
 __global__ void B200_LAUNCH_BOUNDS(DYN_WARPS_PER_BLOCK * 32, DYN_MIN_BLOCKS)
 dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, const TerrainDev tr, const float *actions, const int parity,
-                     const int sim_only) {
+                     const int mode) {
     extern __shared__ float smem[];
     float *ms = smem;
     stage_model(M, T, ms);
@@ -1143,5 +1162,5 @@ dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, con
     const bool ordered = parity >= 0 && B.dyn_order != nullptr;
     const int env = ordered ? slot + B.dyn_order[(size_t)parity * N + slot] : slot;
     dynamics_warp<C>(T, B, tr, ms, smem + MS_TOTAL + warp * WS_TOTAL, actions, env, lane,
-                     (parity >= 0 && B.dyn_cost) ? B.dyn_cost + (size_t)parity * N + env : nullptr, sim_only);
+                     (parity >= 0 && B.dyn_cost) ? B.dyn_cost + (size_t)parity * N + env : nullptr, mode);
 }

@@ -306,9 +306,10 @@ int b200_env_post_step(B200Handle *h, long long step_counter, float cmd_vx_lo, f
                        int phase_mask, void *cuda_stream);
 
 /* One whole env.step (LeggedRobot.step, legged_robot.py:37-53) with HOST buffers, one call: takes `actions` ([N,A] fp32;
- * pinned host memory when `actions_on_host`, device memory otherwise) -- pinned memory is read in place by the dynamics
- * kernel (mapped host memory, no staging copy; the buffer must stay untouched until the stream has passed the call, as
- * with an asynchronous copy) --, then b200_dynamics_step and b200_env_post_step(PHASE_ALL), then copies rew_buf ([N] fp32),
+ * pinned host memory when `actions_on_host`, device memory otherwise) -- pinned memory is read by the kernels themselves
+ * (mapped host memory: a copy kernel overlapped with the dynamics kernel's first phase, no copy-engine operation; the buffer
+ * must stay untouched until the stream has passed the call, as with an asynchronous copy) --, then b200_dynamics_step and
+ * b200_env_post_step(PHASE_ALL), then hands back rew_buf ([N] fp32),
  * reset_buf and time_out_buf ([N] bool bytes) into the given pinned host buffers (each may be NULL).  Everything is
  * enqueued on `cuda_stream`; nothing is synchronised -- the caller waits on the stream before reading the host buffers.
  * This is the call the rollout loop makes (on_policy_runner.py:118-139: env.step(actions) followed by host reads). */

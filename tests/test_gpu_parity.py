@@ -506,13 +506,13 @@ def test_short_rollout_against_oracle(golden):
     assert worst < 5e-2, f"5-step rollout observation drift {worst:.3e}"
 
 
-@pytest.mark.parametrize("zero_copy", ["1", "0"])
+@pytest.mark.parametrize("zero_copy", ["2", "1", "0"])
 def test_one_call_host_step_equals_the_three_call_step(golden, monkeypatch, zero_copy):
     """b200_env_step (pinned host actions in, rew / reset / time_out out, ONE C-ABI call) is bit-identical to the step
     made call by call (b200_dynamics_step, b200_env_post_step) -- with the pinned buffers read / written in place by the
     kernels (zero copy, the default) and with copy-engine transfers (B200_ZERO_COPY_*=0)."""
     monkeypatch.setenv("B200_ZERO_COPY_ACTIONS", zero_copy)
-    monkeypatch.setenv("B200_ZERO_COPY_RESULTS", zero_copy)
+    monkeypatch.setenv("B200_ZERO_COPY_RESULTS", "0" if zero_copy == "0" else "1")
     g, s0, spec, terrain = golden
     N = 512
     rng = np.random.default_rng(2)

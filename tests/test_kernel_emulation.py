@@ -234,7 +234,7 @@ def test_emulated_nonfinite_state_is_contained_and_reset():
     assert torch.isfinite(b["obs_buf"]).all() and int(b["global_flags"][2]) == 1
 
 
-@pytest.mark.parametrize("zero_copy", ["1", "0"])
+@pytest.mark.parametrize("zero_copy", ["2", "1", "0"])
 def test_emulated_host_buffer_step_equals_the_device_step(monkeypatch, zero_copy):
     """b200_env_step with HOST buffers -- actions read in place and the rew | reset | time_out slab written by the env kernel's
     finalising CTA (zero copy, the default), or staged through copies (B200_ZERO_COPY_*=0) -- leaves the same state and the
@@ -245,7 +245,7 @@ def test_emulated_host_buffer_step_equals_the_device_step(monkeypatch, zero_copy
     from hcr_genesis_lr_cl_b200 import task_spec as TS
     from hcr_genesis_lr_cl_b200.terrain_assets import terrain_for
     monkeypatch.setenv("B200_ZERO_COPY_ACTIONS", zero_copy)
-    monkeypatch.setenv("B200_ZERO_COPY_RESULTS", zero_copy)
+    monkeypatch.setenv("B200_ZERO_COPY_RESULTS", "0" if zero_copy == "0" else "1")
     spec = TS.PRESETS["go2_ts"]()
     for N in (16, 13):
         a_env = EmuFusedLeggedEnv(spec, N, torch.device("cpu"), terrain=terrain_for(spec))
