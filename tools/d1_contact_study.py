@@ -135,10 +135,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=512)
     ap.add_argument("--samples", type=int, default=10)
+    ap.add_argument("--task", default="go2_ts", help="a fused preset: go2_ts (quadruped) or e.g. tron1_pf_ee (biped: the legs can cross)")
     args = ap.parse_args()
-    spec = T.go2_ts_spec()
+    spec = T.PRESETS[args.task]()
     terrain = terrain_for(spec)
-    mj = json.load(open(os.path.join(ROOT, "hcr_genesis_lr_cl_b200", "assets", "go2.json")))
+    A = spec.num_actions
+    mj = json.load(open(os.path.join(ROOT, "hcr_genesis_lr_cl_b200", "assets", ("tron1_pf" if args.task.startswith("tron1") else "go2") + ".json")))
     ter = Terrain(spec, terrain[0])
     links = [l["name"] for l in mj["links"]]
     for scale, label in ((1.0, "N(0,1) actions (bench workload)"), (0.3, "0.3 x N(0,1) actions")):
@@ -147,7 +149,7 @@ def main():
         pen_links = set(spec.link_groups(model)[1])
         rng = np.random.default_rng(0)
         for _ in range(150):
-            env.step(scale * rng.normal(size=(args.envs, 12)).astype(np.float32))
+            env.step(scale * rng.normal(size=(args.envs, A)).astype(np.float32))
         q0 = np.asarray(spec.default_dof_pos, np.float64)[None]
         Rn, on = body_frames(model, np.zeros((1, 3)), np.array([[1.0, 0, 0, 0]]), q0)
         neutral = self_collision_pairs(mj, model, Rn, on)[1][0]                   # pairs overlapping in the default pose: filtered
@@ -155,7 +157,7 @@ def main():
         bodies_hit = set()
         for _ in range(args.samples):
             for _ in range(10):
-                env.step(scale * rng.normal(size=(args.envs, 12)).astype(np.float32))
+                env.step(scale * rng.normal(size=(args.envs, A)).astype(np.float32))
             st = env.eo.st
             R, o = body_frames(model, st["base_pos"].astype(np.float64), st["base_quat_wxyz"].astype(np.float64), st["q"].astype(np.float64))
             ds = sphere_distances(mj, R, o, ter)
@@ -177,7 +179,7 @@ def main():
             acc["n_true"].append(n_true); acc["n_sph"].append(n_sph); acc["capped"].append(n_sph > 8)
             acc["pen_true"].append(pen_t); acc["pen_sph"].append(pen_s); acc["self"].append(sc); acc["basez"].append(st["base_pos"][:, 2] - st["env_origins"][:, 2])
         dt, dsp, ty = np.concatenate(acc["d_true"]), np.concatenate(acc["d_sph"]), np.concatenate(acc["type"])
-        print(f"=== go2_ts, {args.envs} envs x {args.samples} samples, {label}; base height above the env origin {np.concatenate(acc['basez']).mean():.3f} m")
+        print(f"=== {args.task}, {args.envs} envs x {args.samples} samples, {label}; base height above the env origin {np.concatenate(acc['basez']).mean():.3f} m")
         for t, name in enumerate(("sphere (feet, head)", "box (base, thighs)", "cylinder (hips, calves, head)")):
             m = ty == t
             both, miss, extra = (dt < 0) & (dsp < 0) & m, (dt < 0) & (dsp >= 0) & m, (dt >= 0) & (dsp < 0) & m
