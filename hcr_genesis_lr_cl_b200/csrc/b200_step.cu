@@ -48,6 +48,8 @@ struct B200Handle {
     float *d_actions = nullptr;    // staging of b200_env_step's host actions (when they cannot be read in place)
     int zero_copy_actions = 2;     // pinned host actions: 2 = staged by a copy kernel the dynamics kernel is the programmatic dependent of (default),
                                    // 1 = read in place by the dynamics kernel, 0 = copy-engine transfer (B200_ZERO_COPY_ACTIONS)
+    bool env_pdl = false;          // B200_ENV_PDL=1: env kernel launched as the programmatic dependent of the dynamics kernel (measured: see launch_env)
+    bool dyn_just_launched = false; // the last launch on the caller's stream was the dynamics kernel (set by b200_env_step only)
     bool zero_copy_results = true; // the env kernel writes rew | reset | time_out into the caller's pinned slab (B200_ZERO_COPY_RESULTS=0: D2H copy)
     bool stats_zeroed = false;
     bool order_enabled = true;     // dynamics warps take envs sorted by solver cost (dynamics_order_kernel); B200_DYN_ORDER=0: slot w = env w
@@ -108,6 +110,8 @@ int b200_create(const int32_t *mi, int n_mi, const float *mf, int n_mf, const in
         h->order_enabled = !(o && o[0] == '0');
         const char *z = getenv("B200_ZERO_COPY_ACTIONS");
         h->zero_copy_actions = (z && z[0] >= '0' && z[0] <= '2') ? z[0] - '0' : 2;
+        const char *ep = getenv("B200_ENV_PDL");
+        h->env_pdl = ep && ep[0] == '1';
         const char *zr = getenv("B200_ZERO_COPY_RESULTS");
         h->zero_copy_results = !(zr && zr[0] == '0');
     }
@@ -277,13 +281,32 @@ static int launch_env(B200Handle *h, long long step, float lo, float span, long 
     EnvCall call = make_call(h, step, lo, span, hist_step, mask, force);
     call.dstate = dstate;
     if (host_slab && call.finalize) { call.host_slab = (uint4 *)host_slab; call.host_slab_vecs = (int)((6 * (size_t)N) / 16); }
-    if (h->side_pending) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->side_pending = false; }      // join the side stream
+    // B200_ENV_PDL=1 (off by default): host-stepped whole steps launch the env kernel as the PROGRAMMATIC DEPENDENT of the
+    // dynamics kernel that precedes it on the stream -- its CTAs are placed and set up while the last dynamics CTAs drain, and
+    // wait (griddepcontrol.wait at the top of the kernel) for the dynamics grid to complete before they touch global memory.
+    // Nothing may sit between the two launches for that, so the side stream (whose ordering kernel only the NEXT dynamics
+    // launch reads) is then joined there instead of here.  Measured (go2_ts, 4096 envs, gpurun_out/r2ac_*): steps enqueued
+    // back to back 0.1885 -> 0.1875 ms, but an isolated step (cold L2, the bench's `value`) 0.1904 -> 0.1966 ms: not the default.
+    const bool pdl = h->env_pdl && h->dyn_just_launched && !dstate && !force && (mask & PHASE_ALL) == PHASE_ALL && !h->task.i[TI_R18];
+    h->dyn_just_launched = false;
+    if (h->side_pending && !pdl) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->side_pending = false; }      // join the side stream
     if (h->task.i[TI_R18] && (mask & PHASE_REWARD) && !force) {      // bug-compatible mode only: the "any env" bits row 0 follows (R18)
         B200_LAUNCH(r18_flags_kernel, dim3((N + R18_FLAGS_BLOCK - 1) / R18_FLAGS_BLOCK), R18_FLAGS_BLOCK, 0, s, h->task, h->bufs, call);
         h->launches++;
         CK(cudaGetLastError());
     }
     const dim3 grid((N + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK), block(ENV_WARPS_PER_BLOCK * 32);
+#ifndef B200_WARP_EMU
+    if (pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = (size_t)h->env_smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, env_kernel_fn(h->env_preset), h->task, h->bufs, h->terrain, call, h->stage));
+    } else
+#endif
     B200_LAUNCH((dstate ? env_kernel_dev_fn(h->env_preset) : env_kernel_fn(h->env_preset)), grid, block, h->env_smem, s, h->task, h->bufs, h->terrain, call, h->stage);
     h->launches++;
     CK(cudaGetLastError());
@@ -340,6 +363,7 @@ int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long
             ((uintptr_t)pa.devicePointer & 15) == 0) slab = pa.devicePointer;
         else (void)cudaGetLastError();
     }
+    h->dyn_just_launched = true;         // nothing was enqueued on `stream` since the dynamics launch above
     if (launch_env(h, step, lo, span, hist_step, PHASE_ALL, 0, stream, nullptr, slab)) return 1;
     if (slab) return 0;
     if (packed) CK(cudaMemcpyAsync(host_rew, d_rew, 6 * (size_t)N, cudaMemcpyDeviceToHost, s));

@@ -1146,6 +1146,11 @@ dynamics_step_kernel(const TaskDev T, const B200Buffers B, const ModelDev M, con
                      const int mode) {
     extern __shared__ float smem[];
     float *ms = smem;
+#ifndef B200_WARP_EMU
+    // a kernel launched as this one's programmatic dependent (the env kernel of a whole host-stepped step) may be placed as
+    // soon as every CTA of this grid has got here, i.e. is resident: its CTAs then take the slots this grid's CTAs free
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     stage_model(M, T, ms);
     // the per-step reduction area of the env kernel that follows (episode sums, reset count, level sums): zeroed here so
     // that the step needs no memset node between the kernels

@@ -1174,6 +1174,7 @@ __device__ __forceinline__ void env_post_step_body_impl(const TaskDev &T, const 
     if (staged) {
         if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_expect_tx(bar, tab.in_bytes); cta_acc[0] = 0.f; cta_acc[1] = 0.f; cta_acc[2] = 0.f; }
         __syncthreads();                                   // barrier armed before any copy can complete on it
+        grid_dependency_wait();                            // launched under the dynamics kernel (b200_env_step): its grid is complete from here on
         // thread t issues the bulk copy of table entry t
         for (int t = (int)threadIdx.x; t < tab.n; t += (int)blockDim.x)
             if (tab.off[t] != ENV_NOT_STAGED)
@@ -1193,12 +1194,15 @@ __device__ __forceinline__ void env_post_step_body_impl(const TaskDev &T, const 
 #else
         env_post_step_warp<S>(T, B, R, warp, tr, call, es + warp * ES_TOTAL, env, lane, true, false, bar, cta_acc);
 #endif
-    } else if (env < N) {
-        EnvInputs R;
+    } else {
+        grid_dependency_wait();                            // every thread, also the idle warps of a ragged last CTA
+        if (env < N) {
+            EnvInputs R;
 #define X_VIEW(field, type, k) R.field = B.field;
-        ENV_STAGED_INPUTS(X_VIEW, 0, 0, 0, 0)
+            ENV_STAGED_INPUTS(X_VIEW, 0, 0, 0, 0)
 #undef X_VIEW
-        env_post_step_warp<S>(T, B, R, env, tr, call, es + warp * ES_TOTAL, env, lane, false, false, bar, cta_acc);
+            env_post_step_warp<S>(T, B, R, env, tr, call, es + warp * ES_TOTAL, env, lane, false, false, bar, cta_acc);
+        }
     }
     if (call.finalize) env_finalize_cta(B, ti[TI_N_SUMS], call, (int *)(smem + 2));
 }
