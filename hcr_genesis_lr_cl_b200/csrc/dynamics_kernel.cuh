@@ -299,15 +299,15 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         }
         // ---------------- forward kinematics, velocities, RNE, CRBA along this lane's chain ----------------
         const m33 R0 = quat_to_mat(Qw, Qx, Qy, Qz);
-        f3 fn_last = mk3(0.f, 0.f, 0.f), ff_last = fn_last;
-        SIn si_last;
-        si_last.m = 0.f; si_last.h = fn_last;
-#pragma unroll
-        for (int e = 0; e < 6; e++) si_last.I[e] = 0.f;
-        // inertia and bias forces of the chain's first two bodies wait for the backward pass in a part of the A matrix's
-        // storage that nothing else touches before the constraint rows are built (this lane's slot: no barrier needed),
-        // not in 32 registers that the compiler would spill to local memory
-        float *park = ws + WS_AM + 640 + (leg ? lane : C) * 41;
+        // The chain walk below is serial in the body index and redundant over the lanes (lanes >= C shadow the last chain), so
+        // only what MUST follow the chain stays in it: frames, velocities and the velocity-product accelerations.  The body-local
+        // part of the RNE -- world inertia about the base origin (R I R^T, parallel axes), momenta, bias wrench: ~180
+        // instructions per body -- is done afterwards by ONE LANE PER BODY (lane j = body 1 + j), all bodies at once.
+        // Hand-over through the chain's parking slots in a part of the A matrix's storage that nothing else touches before
+        // the constraint rows are built: [k][16] per body (first aw, av from the chain lane; then m, h, I, fn, ff from the
+        // body lane), then the three moment arms.
+        constexpr int PARK = 57;
+        float *park = ws + WS_AM + 640 + c * PARK;       // lanes >= C read the last chain's slot (and write nothing)
         {
             m33 Rp = R0; f3 op = mk3(0.f, 0.f, 0.f), wp = wb, vp = vb;
             f3 awp = mk3(0.f, 0.f, 0.f), avp = cross3(vb, wb) + mk3(0.f, 0.f, tf[TF_GRAV]);
@@ -328,29 +328,14 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                     fr[9] = o.x; fr[10] = o.y; fr[11] = o.z;
                     float *axp = ws + WS_AX + (b - 1) * 3; axp[0] = a.x; axp[1] = a.y; axp[2] = a.z;
                     float *vl = ws + WS_VEL + b * 6; vl[0] = w.x; vl[1] = w.y; vl[2] = w.z; vl[3] = v.x; vl[4] = v.y; vl[5] = v.z;
+                    park[48 + 3 * k] = sv.x; park[49 + 3 * k] = sv.y; park[50 + 3 * k] = sv.z;
                 }
                 if (!last_pass) {
                     const f3 aw = awp + cross3(w, a) * qd[k];
                     const f3 av = avp + (cross3(w, sv) + cross3(v, a)) * qd[k];
-                    const f3 cm = o + mul(Rk, mk3(Bd[6], Bd[7], Bd[8]));
-                    const SIn sik = si_body(Bd[9], cm, Bd + 10, Rk);
-                    f3 LA, PA, LV, PV;
-                    si_apply(sik, aw, av, LA, PA);
-                    si_apply(sik, w, v, LV, PV);
-                    const f3 fnk = LA + cross3(w, LV) + cross3(v, PV);
-                    const f3 ffk = PA + cross3(w, PV);
-                    if (k < 2) {
-                        float *pk = park + 16 * k;
-                        pk[0] = sik.m; pk[1] = sik.h.x; pk[2] = sik.h.y; pk[3] = sik.h.z;
-#pragma unroll
-                        for (int e = 0; e < 6; e++) pk[4 + e] = sik.I[e];
-                        pk[10] = fnk.x; pk[11] = fnk.y; pk[12] = fnk.z; pk[13] = ffk.x; pk[14] = ffk.y; pk[15] = ffk.z;
-                    } else {
-                        si_last = sik; fn_last = fnk; ff_last = ffk;
-                    }
+                    if (leg) { float *pk = park + 16 * k; pk[0] = aw.x; pk[1] = aw.y; pk[2] = aw.z; pk[3] = av.x; pk[4] = av.y; pk[5] = av.z; }
                     awp = aw; avp = av;
                 }
-                park[32 + 3 * k] = sv.x; park[33 + 3 * k] = sv.y; park[34 + 3 * k] = sv.z;
                 Rp = Rk; op = o; wp = w; vp = v;
             }
         }
@@ -402,6 +387,30 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         for (int k = 0; k < 3; k++) tau[k] = pd[3 + k] * (pd[k] - q[k]) - pd[6 + k] * qd[k];
         if (leg) sts128(qs_a + 32u, tau[0], tau[1], tau[2], 0.f);      // the last substep's is the reported torque
 
+        // ---------------- body-local RNE: one lane per body ----------------
+        if (lane < A) {
+            const int b = 1 + lane;
+            const float *Bd = ms + MS_BODY + b * B200_BODY_STRIDE;
+            const float *fr = ws + WS_FR + b * 12, *vl = ws + WS_VEL + b * 6;
+            float *pk = ws + WS_AM + 640 + (lane / 3) * PARK + 16 * (lane % 3);
+            m33 Rk;
+#pragma unroll
+            for (int e = 0; e < 9; e++) Rk.m[e] = fr[e];
+            const f3 o = mk3(fr[9], fr[10], fr[11]), w = mk3(vl[0], vl[1], vl[2]), v = mk3(vl[3], vl[4], vl[5]);
+            const f3 aw = mk3(pk[0], pk[1], pk[2]), av = mk3(pk[3], pk[4], pk[5]);
+            const f3 cm = o + mul(Rk, mk3(Bd[6], Bd[7], Bd[8]));
+            const SIn sik = si_body(Bd[9], cm, Bd + 10, Rk);
+            f3 LA, PA, LV, PV;
+            si_apply(sik, aw, av, LA, PA);
+            si_apply(sik, w, v, LV, PV);
+            const f3 fnk = LA + cross3(w, LV) + cross3(v, PV);
+            const f3 ffk = PA + cross3(w, PV);
+            pk[0] = sik.m; pk[1] = sik.h.x; pk[2] = sik.h.y; pk[3] = sik.h.z;
+#pragma unroll
+            for (int e = 0; e < 6; e++) pk[4 + e] = sik.I[e];
+            pk[10] = fnk.x; pk[11] = fnk.y; pk[12] = fnk.z; pk[13] = ffk.x; pk[14] = ffk.y; pk[15] = ffk.z;
+        }
+        __syncwarp();
         PHASE_SYNC_B();
         // backward pass along the chain: composite inertias, bias forces, CRBA columns
         float Dm[6];           // chain block, lower tri (00,10,11,20,21,22)
@@ -412,10 +421,17 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         for (int k = 0; k < 3; k++) {
             const float *axp = ws + WS_AX + (3 * c + k) * 3;
             a_[k] = mk3(axp[0], axp[1], axp[2]);
-            sv_[k] = mk3(park[32 + 3 * k], park[33 + 3 * k], park[34 + 3 * k]);
+            sv_[k] = mk3(park[48 + 3 * k], park[49 + 3 * k], park[50 + 3 * k]);
         }
-        SIn comp = si_last;
-        f3 fns = fn_last, ffs = ff_last;
+        SIn comp;
+        f3 fns, ffs;
+        {
+            const float *pk = park + 32;
+            comp.m = pk[0]; comp.h = mk3(pk[1], pk[2], pk[3]);
+#pragma unroll
+            for (int e = 0; e < 6; e++) comp.I[e] = pk[4 + e];
+            fns = mk3(pk[10], pk[11], pk[12]); ffs = mk3(pk[13], pk[14], pk[15]);
+        }
 #pragma unroll
         for (int k = 2; k >= 0; k--) {
             if (k < 2) {
