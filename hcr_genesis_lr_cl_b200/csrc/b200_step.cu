@@ -357,7 +357,8 @@ int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long
     // ... and none at all when the host slab is mapped into the device's address space: the env kernel's finalising CTA
     // writes it over PCIe itself (EnvCall::host_slab; B200_ZERO_COPY_RESULTS=0: copy-engine transfer as before)
     void *slab = nullptr;
-    if (packed && h->zero_copy_results && (6 * (size_t)N) % 16 == 0 && ((uintptr_t)d_rew & 15) == 0) {
+    // (one CTA does that copy at the kernel's end: fine for the 24 KB of 4096 envs, slower than the copy engine beyond ~64 KB)
+    if (packed && h->zero_copy_results && (6 * (size_t)N) % 16 == 0 && 6 * (size_t)N <= 65536 && ((uintptr_t)d_rew & 15) == 0) {
         cudaPointerAttributes pa;
         if (cudaPointerGetAttributes(&pa, host_rew) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
             ((uintptr_t)pa.devicePointer & 15) == 0) slab = pa.devicePointer;
