@@ -13,10 +13,12 @@ GPU, no collective on the data path (weak scaling).  The line printed by rank 0 
                them), MEDIAN step time per rank, max over ranks (the mean is printed beside it: one host hiccup in a 4 ms
                window must not decide a scaling number); the workload is rolled to its steady state un-timed first
                (`config.pre_roll_steps`, `workload_state`)
-  e2e          the same metric through FusedLeggedEnv.step_host() = b200_env_step with HOST buffers: pinned actions H2D,
-               kernels, rewards + resets D2H inside the timed region, every step
-  roofline     the post_physics_step as its own kernel (env_post_step_kernel, timed call by call in a second loop) against
-               the measured HBM copy bandwidth (MEASURED_PEAKS.json); `whole_step` = all kernels' bytes over the step time
+  e2e          the same metric through FusedLeggedEnv.step_host() = b200_env_step with HOST buffers: the actions come out of
+               pinned host memory (a copy kernel reading the mapped buffer over PCIe, overlapped with the dynamics kernel's
+               first phase) and rewards / resets / time-outs go back into pinned host memory (written by the env kernel's
+               last CTA) inside the timed region, every step; K steps enqueued back to back, three blocks, median block
+  roofline     the whole step (all kernels' algorithmic bytes over the step time) against the measured HBM copy bandwidth
+               (MEASURED_PEAKS.json), then each kernel on its own bytes and time (timed call by call in a second loop)
   kernels      the step, and its kernels timed call by call: average duration, share of the step, static resources (the
                dynamics kernel is latency / issue bound)
   cpu_baseline the oracle port timed on host cores on a bounded sample (rank 0, N=1 only)
@@ -236,7 +238,8 @@ def run_gpu(args):
     t_env = statistics.median(e[1].elapsed_time(e[2]) for e in ev)
     # ---- end to end through the public API with host buffers
     rew_host, rst_host, tmo_host = sim.make_host_step_buffers()       # one pinned slab: rew f32[N] | reset u8[N] | time_out u8[N]
-    # FusedLeggedEnv.step_host = ONE C-ABI call (b200_env_step): H2D of the pinned actions, the kernels, one D2H of the slab
+    # FusedLeggedEnv.step_host = ONE C-ABI call (b200_env_step): pinned actions in (staged by a copy kernel), the kernels, the
+    # pinned rew | reset | time_out slab out (written by the env kernel)
     for i in range(W):
         env.step_host(host_pool[i % 16], rew_host, rst_host, tmo_host)
     barrier()
@@ -286,7 +289,7 @@ def run_gpu(args):
         "config": _config(args, spec, N, world),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": N * spec.num_actions * 4 * world, "d2h_bytes_per_step": N * 6 * world,
                 "ms_per_step": e2e_ms / K, "result_on_device_bytes": on_device * world,
-                "note": "rewards / resets / time-outs come back to the host every step; the observation tensors stay in HBM, where the policy network reads them"},
+                "note": "actions are read from pinned host memory and rewards / resets / time-outs written back into pinned host memory every step (by the kernels, no copy-engine operation); the observation tensors stay in HBM, where the policy network reads them"},
         "ms_per_step_mean": t_step_mean,
         "workload_state": workload_state,
         "gpu_launches": int(launches),
