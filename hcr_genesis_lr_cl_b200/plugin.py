@@ -60,6 +60,30 @@ def backend_class(impl=None):
 _MAKE_ENV = None     # task_registry.make_env before install(fused=True)
 
 
+def stub_missing_optional_imports() -> list:
+    """legged_gym imports trimesh (utils/terrain.py:32), matplotlib (utils/logger.py:4-5), pygame (the joystick script) and
+    xlsxwriter (utils/logger.py:6) at module level; none of them is called on the training path of a heightfield task.  Where
+    one is not installed, an empty placeholder module lets the import pass (returns the names it stood in for)."""
+    made = []
+    for name in ("trimesh", "matplotlib", "matplotlib.pyplot", "pygame", "xlsxwriter"):
+        try:
+            importlib.import_module(name)
+        except ImportError:
+            m = types.ModuleType(name)
+            m.__doc__ = "placeholder installed by hcr_genesis_lr_cl_b200.plugin.stub_missing_optional_imports"
+            if name == "matplotlib":
+                m.use = lambda *a, **k: None
+            if name == "matplotlib.pyplot":
+                m.rcParams = {}                      # legged_gym/utils/logger.py updates it at import time
+            if name == "trimesh":
+                m.Trimesh = type("Trimesh", (), {"__init__": lambda self, *a, **k: None})
+            sys.modules[name] = m
+            if "." in name:
+                setattr(sys.modules[name.split(".")[0]], name.split(".")[1], m)
+            made.append(name)
+    return made
+
+
 def _route_make_env_to_fused(env_class=None):
     """`task_registry.make_env(name, args)` (task_registry.py:35-72, what scripts/train.py calls) hands out a `FusedLeggedEnv`
     for every task whose cfg has a fused descriptor -- the reference's cfg handling (get_cfgs, update_cfg_from_args, set_seed)

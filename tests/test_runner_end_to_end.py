@@ -140,3 +140,53 @@ def test_reference_runner_trains_in_plugin_mode_gpu(task):
 def test_reference_runner_trains_on_the_fused_env_gpu(task):
     from hcr_genesis_lr_cl_b200.fused_env import FusedLeggedEnv
     _fused(task, FusedLeggedEnv, cpu=False, n=256, iters=2, steps=8)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's scripts/train.py itself, unmodified, through the launcher (python -m hcr_genesis_lr_cl_b200.launch)
+def _run_train_script(extra_env, launcher_args, script_args, driver=None):
+    import glob
+    import shutil
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "baseline", "_ref")          # a writable copy: train.py logs under <reference root>/logs
+    if not os.path.isdir(os.path.join(ref, "legged_gym")):
+        pytest.skip("no staged reference tree (baseline/_ref, tools/stage_reference.py)")
+    logs = os.path.join(ref, "logs")
+    shutil.rmtree(logs, ignore_errors=True)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([root, os.path.join(root, "tests")]), **extra_env)
+    env.pop("SIMULATOR", None)
+    cmd = [sys.executable] + (driver or ["-m", "hcr_genesis_lr_cl_b200.launch"]) + launcher_args + \
+          [os.path.join(ref, "legged_gym", "scripts", "train.py")] + script_args
+    try:
+        res = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=900)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+        saved = glob.glob(os.path.join(logs, "**", "model_*.pt"), recursive=True)
+        assert saved, "train.py left no checkpoint under " + logs
+        backups = glob.glob(os.path.join(logs, "**", "*_config.py"), recursive=True)
+        assert backups, "train.py did not back up the task's config (train.py:20-29)"
+        return res.stdout
+    finally:
+        shutil.rmtree(logs, ignore_errors=True)
+
+
+@needs_reference
+def test_reference_train_script_runs_through_the_launcher_emulated(tmp_path):
+    """CPU: a three-line driver hands the launcher the emulator-backed classes; everything else is the launcher's own path."""
+    driver = tmp_path / "launch_emu.py"
+    driver.write_text("from emu_backend import EmuB200Simulator, EmuFusedLeggedEnv\n"
+                      "from hcr_genesis_lr_cl_b200.launch import main\n"
+                      "main(impl=EmuB200Simulator, fused_env_class=EmuFusedLeggedEnv)\n")
+    out = _run_train_script({}, ["--b200-stub-missing-imports"], ["--task", "go2", "--headless", "--cpu", "--num_envs", "8", "--max_iterations", "1"],
+                            driver=[str(driver)])
+    assert "Learning iteration" in out or "Total timesteps" in out
+
+
+@needs_reference
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,task", [("fused", "go2_ts"), ("fused", "go2_wtw"), ("plugin", "go2")])
+def test_reference_train_script_runs_through_the_launcher_gpu(mode, task):
+    out = _run_train_script({}, ["--b200-mode", mode, "--b200-stub-missing-imports"],
+                            ["--task", task, "--headless", "--num_envs", "256", "--max_iterations", "2"])
+    assert "Total timesteps" in out

@@ -30,23 +30,6 @@ def reference_root():
     raise SystemExit("no reference tree (baseline/_ref or /root/reference)")
 
 
-def placeholders():
-    for name in ("trimesh", "matplotlib", "matplotlib.pyplot", "pygame", "xlsxwriter"):
-        try:
-            __import__(name)
-        except ImportError:
-            m = types.ModuleType(name)
-            sys.modules[name] = m
-            if name == "matplotlib":
-                m.use = lambda *a, **k: None
-            if name == "matplotlib.pyplot":
-                m.rcParams = {}                      # legged_gym/utils/logger.py updates it at import time
-            if name == "trimesh":
-                m.Trimesh = type("Trimesh", (), {"__init__": lambda self, *a, **k: None})
-            if "." in name:
-                setattr(sys.modules[name.split(".")[0]], name.split(".")[1], m)
-
-
 def timed(step, pool, K, reps=3):
     runs = []
     for _ in range(reps):
@@ -70,8 +53,8 @@ def main():
     args = ap.parse_args()
     torch.cuda.set_device(0)
     dev = torch.device("cuda:0")
-    placeholders()
     import hcr_genesis_lr_cl_b200.plugin as b200
+    b200.stub_missing_optional_imports()
     backend = b200.install(reference_root=reference_root())
     from legged_gym.utils.task_registry import task_registry
     ns = types.SimpleNamespace(task=args.task, headless=True, cpu=False, num_envs=args.envs, debug=False, max_iterations=None, resume=False,
