@@ -729,17 +729,23 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             kind = ax[3] < 0.f ? 3 : 4;
             wkey = (float)(8 * j + (kind == 3 ? (ax[1] > 0.f ? 7 : 6) : 4) + 1);
         }
-        // y = M^-1 J^T for this lane's row
-        float Yb[6], Yl[C][3];
+        // y = M^-1 J^T for this lane's row, in the arrowhead factorisation M = [D B; B^T M_bb]:
+        //   rb = Jb - G_c^T Jl   (c the row's chain, G = D^-1 B^T)      yb = S^-1 rb      yl_c' = [c' == c] D_c^-1 Jl - G_c' yb
+        // Only yb and ul = D_c^-1 Jl are formed.  The chain parts yl_c' of the other chains are never needed explicitly:
+        //   A[r][s] = J_r . y_s = rb_r . yb_s + [c_r == c_s] Jl_r . ul_s          (the rows stored for the others hold rb, not Jb)
+        //   sum_r yl_r,c' f_r = D_c'^-1 (sum_{r on c'} Jl_r f_r) - G_c' (sum_r yb_r f_r)      (after the solve, once per chain)
+        // which takes 4 x 18 multiply-adds, their loads of G and twelve registers that lived through the whole solve off
+        // every row.
+        float Yb[6], ul[3] = {0.f, 0.f, 0.f};
         float vel = 0.f, ja = 0.f;
         {
-            float tl[3] = {0.f, 0.f, 0.f}, rb[6];
+            float rb[6];
 #pragma unroll
             for (int e = 0; e < 6; e++) rb[e] = Jb[e];
             if (cl >= 0) {
                 const float *mi = ws + WS_MI + cl * 24;
 #pragma unroll
-                for (int a2 = 0; a2 < 3; a2++) tl[a2] = mi[tri(a2, 0)] * Jl[0] + mi[tri(a2, 1)] * Jl[1] + mi[tri(a2, 2)] * Jl[2];
+                for (int a2 = 0; a2 < 3; a2++) ul[a2] = mi[tri(a2, 0)] * Jl[0] + mi[tri(a2, 1)] * Jl[1] + mi[tri(a2, 2)] * Jl[2];
 #pragma unroll
                 for (int e = 0; e < 6; e++) rb[e] -= mi[6 + e] * Jl[0] + mi[12 + e] * Jl[1] + mi[18 + e] * Jl[2];
             }
@@ -753,28 +759,16 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                 for (int j2 = 0; j2 < 6; j2++) s += Sv[tri(i2, j2)] * rb[j2];
                 Yb[i2] = s;
             }
+            float *jr = ws + WS_JR + lane * 10;
 #pragma unroll
-            for (int l2 = 0; l2 < C; l2++) {
-                const float *mi = ws + WS_MI + l2 * 24;
-#pragma unroll
-                for (int a2 = 0; a2 < 3; a2++) {
-                    float s = (l2 == cl) ? tl[a2] : 0.f;
-                    const float2 *g2 = reinterpret_cast<const float2 *>(mi + 6 + a2 * 6);      // 8-byte aligned rows of G
-                    const float2 g01 = g2[0], g23 = g2[1], g45 = g2[2];
-                    s -= g01.x * Yb[0]; s -= g01.y * Yb[1]; s -= g23.x * Yb[2]; s -= g23.y * Yb[3]; s -= g45.x * Yb[4]; s -= g45.y * Yb[5];
-                    Yl[l2][a2] = s;
-                }
-            }
+            for (int e = 0; e < 6; e++) jr[e] = rb[e];
+            jr[6] = Jl[0]; jr[7] = Jl[1]; jr[8] = Jl[2]; jr[9] = __int_as_float(cl);
 #pragma unroll
             for (int e = 0; e < 6; e++) { vel += Jb[e] * ws[WS_NU + e]; ja += Jb[e] * ws[WS_AF + e]; }
             if (cl >= 0) {
 #pragma unroll
                 for (int k = 0; k < 3; k++) { vel += Jl[k] * ws[WS_NU + 6 + 3 * cl + k]; ja += Jl[k] * ws[WS_AF + 6 + 3 * cl + k]; }
             }
-            float *jr = ws + WS_JR + lane * 10;
-#pragma unroll
-            for (int e = 0; e < 6; e++) jr[e] = Jb[e];
-            jr[6] = Jl[0]; jr[7] = Jl[1]; jr[8] = Jl[2]; jr[9] = __int_as_float(cl);
         }
         __syncwarp();
         // this lane's column of A = J M^-1 J^T
@@ -782,11 +776,8 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         // contact rows: the three rows of a sphere sit on the same chain, whose Y columns are picked once per contact
         for (int c2 = 0; c2 < nc; c2++) {
             const float *jc = ws + WS_JR + 30 * c2;
-            const int clr = __float_as_int(jc[9]);
-            float y0 = 0.f, y1 = 0.f, y2 = 0.f;
-#pragma unroll
-            for (int l2 = 0; l2 < C; l2++)
-                if (clr == l2) { y0 = Yl[l2][0]; y1 = Yl[l2][1]; y2 = Yl[l2][2]; }
+            const bool same = __float_as_int(jc[9]) == cl;          // rows on this lane's chain also meet through D_c^-1
+            const float y0 = same ? ul[0] : 0.f, y1 = same ? ul[1] : 0.f, y2 = same ? ul[2] : 0.f;
 #pragma unroll
             for (int d = 0; d < 3; d++) {
                 // one row of J, the same for every lane: five 8-byte broadcast loads (rows are 40 bytes apart, WS_JR is 16-byte aligned)
@@ -804,10 +795,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             const float2 j01 = jr2[0], j23 = jr2[1], j45 = jr2[2], j67 = jr2[3], j89 = jr2[4];
             float a2 = 0.f;
             a2 += j01.x * Yb[0]; a2 += j01.y * Yb[1]; a2 += j23.x * Yb[2]; a2 += j23.y * Yb[3]; a2 += j45.x * Yb[4]; a2 += j45.y * Yb[5];
-            const int clr = __float_as_int(j89.y);
-#pragma unroll
-            for (int l2 = 0; l2 < C; l2++)
-                if (clr == l2) a2 += j67.x * Yl[l2][0] + j67.y * Yl[l2][1] + j89.x * Yl[l2][2];
+            if (__float_as_int(j89.y) == cl) a2 += j67.x * ul[0] + j67.y * ul[1] + j89.x * ul[2];
             ws[WS_AM + r * 33 + lane] = a2;
             if (r == lane) Arr = a2;
         }
@@ -956,9 +944,10 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         }
         PHASE_SYNC_E();
         // ---------------- total acceleration, contact forces, integration ----------------
-        // a += M^-1 J^T f = sum over the rows of Y_r f_r: every lane parks its 6 + 3C products in the (now dead) A matrix,
-        // lane e adds up column e over the R rows, the sums go back through shared memory -- 6 + 3C column sums for ~2R
-        // instructions instead of 6 + 3C butterfly reductions of 10
+        // a += M^-1 J^T f.  Base part: sum_r yb_r f_r.  Chain part: D_c^-1 tau_c - G_c (sum_r yb_r f_r) with the joint-space force
+        // tau_c = sum over the rows on chain c of Jl_r f_r (see the row assembly).  Every lane parks its 6 + 3C products in the
+        // (now dead) A matrix, lane e adds up column e over the R rows, the sums go back through shared memory -- 6 + 3C
+        // column sums for ~2R instructions instead of 6 + 3C butterfly reductions of 10
         float accb[6], accl[3];
         {
             constexpr int NV = 6 + 3 * C, LD = NV + 1;        // odd row stride: conflict-free column walks
@@ -970,18 +959,26 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 #pragma unroll
                 for (int l2 = 0; l2 < C; l2++)
 #pragma unroll
-                    for (int k = 0; k < 3; k++) yf[lane * LD + 6 + 3 * l2 + k] = Yl[l2][k] * f;
+                    for (int k = 0; k < 3; k++) yf[lane * LD + 6 + 3 * l2 + k] = (l2 == cl) ? Jl[k] * f : 0.f;
             }
             __syncwarp();
             float colsum = 0.f;
             if (lane < NV) for (int r = 0; r < R; r++) colsum += yf[r * LD + lane];
             __syncwarp();
-            if (lane < NV) yf[lane] = colsum + ws[WS_AF + lane];               // row 0 now holds the total accelerations
+            if (lane < NV) yf[lane] = colsum;                  // row 0: sum_r yb_r f_r (6), then tau_c (3 per chain)
             __syncwarp();
+            float sb[6];
 #pragma unroll
-            for (int e = 0; e < 6; e++) accb[e] = yf[e];
+            for (int e = 0; e < 6; e++) { sb[e] = yf[e]; accb[e] = sb[e] + ws[WS_AF + e]; }
+            const float t0 = yf[6 + 3 * c], t1 = yf[7 + 3 * c], t2 = yf[8 + 3 * c];
+            const float *mi = ws + WS_MI + c * 24;
 #pragma unroll
-            for (int k = 0; k < 3; k++) accl[k] = yf[6 + 3 * c + k];
+            for (int k = 0; k < 3; k++) {
+                float a = ws[WS_AF + 6 + 3 * c + k] + mi[tri(k, 0)] * t0 + mi[tri(k, 1)] * t1 + mi[tri(k, 2)] * t2;
+#pragma unroll
+                for (int e = 0; e < 6; e++) a -= mi[6 + k * 6 + e] * sb[e];
+                accl[k] = a;
+            }
         }
         {
             float *fv = ws + WS_FV + lane * 4;
