@@ -306,7 +306,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         // Hand-over through the chain's parking slots in a part of the A matrix's storage that nothing else touches before
         // the constraint rows are built: [k][16] per body (first aw, av from the chain lane; then m, h, I, fn, ff from the
         // body lane), then the three moment arms.
-        constexpr int PARK = 57;
+        constexpr int PARK = 60;         // 16-byte aligned slots: the body records move as 4 x 16 bytes
         float *park = ws + WS_AM + 640 + c * PARK;       // lanes >= C read the last chain's slot (and write nothing)
         {
             m33 Rp = R0; f3 op = mk3(0.f, 0.f, 0.f), wp = wb, vp = vb;
@@ -333,7 +333,7 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                 if (!last_pass) {
                     const f3 aw = awp + cross3(w, a) * qd[k];
                     const f3 av = avp + (cross3(w, sv) + cross3(v, a)) * qd[k];
-                    if (leg) { float *pk = park + 16 * k; pk[0] = aw.x; pk[1] = aw.y; pk[2] = aw.z; pk[3] = av.x; pk[4] = av.y; pk[5] = av.z; }
+                    if (leg) { const smaddr_t pa = sm_addr(park + 16 * k); sts128(pa, aw.x, aw.y, aw.z, av.x); sts128(pa + 16u, av.y, av.z, 0.f, 0.f); }
                     awp = aw; avp = av;
                 }
                 Rp = Rk; op = o; wp = w; vp = v;
@@ -391,13 +391,16 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         if (lane < A) {
             const int b = 1 + lane;
             const float *Bd = ms + MS_BODY + b * B200_BODY_STRIDE;
-            const float *fr = ws + WS_FR + b * 12, *vl = ws + WS_VEL + b * 6;
-            float *pk = ws + WS_AM + 640 + (lane / 3) * PARK + 16 * (lane % 3);
+            const smaddr_t fr_a = sm_addr(ws + WS_FR + b * 12), vl_a = sm_addr(ws + WS_VEL + b * 6);
+            const smaddr_t pk_a = sm_addr(ws + WS_AM + 640 + (lane / 3) * PARK + 16 * (lane % 3));
+            const float4 f0 = lds128(fr_a), f1 = lds128(fr_a + 16u), f2 = lds128(fr_a + 32u);       // R (9), o (3)
+            const float2 v0 = lds64(vl_a), v1 = lds64(vl_a + 8u), v2 = lds64(vl_a + 16u);           // w (3), v (3)
+            const float4 a0 = lds128(pk_a);                                                         // aw (3), av.x
+            const float2 a1 = lds64(pk_a + 16u);                                                    // av.y, av.z
             m33 Rk;
-#pragma unroll
-            for (int e = 0; e < 9; e++) Rk.m[e] = fr[e];
-            const f3 o = mk3(fr[9], fr[10], fr[11]), w = mk3(vl[0], vl[1], vl[2]), v = mk3(vl[3], vl[4], vl[5]);
-            const f3 aw = mk3(pk[0], pk[1], pk[2]), av = mk3(pk[3], pk[4], pk[5]);
+            Rk.m[0] = f0.x; Rk.m[1] = f0.y; Rk.m[2] = f0.z; Rk.m[3] = f0.w; Rk.m[4] = f1.x; Rk.m[5] = f1.y; Rk.m[6] = f1.z; Rk.m[7] = f1.w; Rk.m[8] = f2.x;
+            const f3 o = mk3(f2.y, f2.z, f2.w), w = mk3(v0.x, v0.y, v1.x), v = mk3(v1.y, v2.x, v2.y);
+            const f3 aw = mk3(a0.x, a0.y, a0.z), av = mk3(a0.w, a1.x, a1.y);
             const f3 cm = o + mul(Rk, mk3(Bd[6], Bd[7], Bd[8]));
             const SIn sik = si_body(Bd[9], cm, Bd + 10, Rk);
             f3 LA, PA, LV, PV;
@@ -405,10 +408,10 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
             si_apply(sik, w, v, LV, PV);
             const f3 fnk = LA + cross3(w, LV) + cross3(v, PV);
             const f3 ffk = PA + cross3(w, PV);
-            pk[0] = sik.m; pk[1] = sik.h.x; pk[2] = sik.h.y; pk[3] = sik.h.z;
-#pragma unroll
-            for (int e = 0; e < 6; e++) pk[4 + e] = sik.I[e];
-            pk[10] = fnk.x; pk[11] = fnk.y; pk[12] = fnk.z; pk[13] = ffk.x; pk[14] = ffk.y; pk[15] = ffk.z;
+            sts128(pk_a, sik.m, sik.h.x, sik.h.y, sik.h.z);
+            sts128(pk_a + 16u, sik.I[0], sik.I[1], sik.I[2], sik.I[3]);
+            sts128(pk_a + 32u, sik.I[4], sik.I[5], fnk.x, fnk.y);
+            sts128(pk_a + 48u, fnk.z, ffk.x, ffk.y, ffk.z);
         }
         __syncwarp();
         PHASE_SYNC_B();
@@ -425,22 +428,22 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
         }
         SIn comp;
         f3 fns, ffs;
+        const smaddr_t park_a = sm_addr(park);
         {
-            const float *pk = park + 32;
-            comp.m = pk[0]; comp.h = mk3(pk[1], pk[2], pk[3]);
-#pragma unroll
-            for (int e = 0; e < 6; e++) comp.I[e] = pk[4 + e];
-            fns = mk3(pk[10], pk[11], pk[12]); ffs = mk3(pk[13], pk[14], pk[15]);
+            const float4 r0 = lds128(park_a + 128u), r1 = lds128(park_a + 144u), r2 = lds128(park_a + 160u), r3 = lds128(park_a + 176u);
+            comp.m = r0.x; comp.h = mk3(r0.y, r0.z, r0.w);
+            comp.I[0] = r1.x; comp.I[1] = r1.y; comp.I[2] = r1.z; comp.I[3] = r1.w; comp.I[4] = r2.x; comp.I[5] = r2.y;
+            fns = mk3(r2.z, r2.w, r3.x); ffs = mk3(r3.y, r3.z, r3.w);
         }
 #pragma unroll
         for (int k = 2; k >= 0; k--) {
             if (k < 2) {
-                const float *pk = park + 16 * k;
+                const smaddr_t pa = park_a + 64u * k;
+                const float4 r0 = lds128(pa), r1 = lds128(pa + 16u), r2 = lds128(pa + 32u), r3 = lds128(pa + 48u);
                 SIn sik;
-                sik.m = pk[0]; sik.h = mk3(pk[1], pk[2], pk[3]);
-#pragma unroll
-                for (int e = 0; e < 6; e++) sik.I[e] = pk[4 + e];
-                si_acc(comp, sik); fns = fns + mk3(pk[10], pk[11], pk[12]); ffs = ffs + mk3(pk[13], pk[14], pk[15]);
+                sik.m = r0.x; sik.h = mk3(r0.y, r0.z, r0.w);
+                sik.I[0] = r1.x; sik.I[1] = r1.y; sik.I[2] = r1.z; sik.I[3] = r1.w; sik.I[4] = r2.x; sik.I[5] = r2.y;
+                si_acc(comp, sik); fns = fns + mk3(r2.z, r2.w, r3.x); ffs = ffs + mk3(r3.y, r3.z, r3.w);
             }
             biasl[k] = dot3(a_[k], fns) + dot3(sv_[k], ffs);
             f3 Lk, Pk; si_apply(comp, a_[k], sv_[k], Lk, Pk);
@@ -743,15 +746,21 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 #pragma unroll
             for (int e = 0; e < 6; e++) rb[e] = Jb[e];
             if (cl >= 0) {
-                const float *mi = ws + WS_MI + cl * 24;
+                float mi[24];                    // D^-1 (6) and G (18) of the row's chain: six 16-byte loads
+                const smaddr_t mi_a = sm_addr(ws + WS_MI + cl * 24);
+#pragma unroll
+                for (int e = 0; e < 6; e++) { const float4 v4 = lds128(mi_a + 16u * e); mi[4 * e] = v4.x; mi[4 * e + 1] = v4.y; mi[4 * e + 2] = v4.z; mi[4 * e + 3] = v4.w; }
 #pragma unroll
                 for (int a2 = 0; a2 < 3; a2++) ul[a2] = mi[tri(a2, 0)] * Jl[0] + mi[tri(a2, 1)] * Jl[1] + mi[tri(a2, 2)] * Jl[2];
 #pragma unroll
                 for (int e = 0; e < 6; e++) rb[e] -= mi[6 + e] * Jl[0] + mi[12 + e] * Jl[1] + mi[18 + e] * Jl[2];
             }
-            float Sv[21];                        // the Schur inverse back from shared memory (21 registers not carried through
-#pragma unroll                                   // the collision / aux-row phases)
-            for (int e = 0; e < 21; e++) Sv[e] = ws[WS_MI + 4 * 24 + e];
+            float Sv[24];                        // the Schur inverse back from shared memory (21 registers not carried through
+            {                                    // the collision / aux-row phases): six 16-byte broadcast loads
+                const smaddr_t sv_a = sm_addr(ws + WS_MI + 4 * 24);
+#pragma unroll
+                for (int e = 0; e < 6; e++) { const float4 v4 = lds128(sv_a + 16u * e); Sv[4 * e] = v4.x; Sv[4 * e + 1] = v4.y; Sv[4 * e + 2] = v4.z; Sv[4 * e + 3] = v4.w; }
+            }
 #pragma unroll
             for (int i2 = 0; i2 < 6; i2++) {
                 float s = 0.f;
@@ -971,7 +980,10 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
 #pragma unroll
             for (int e = 0; e < 6; e++) { sb[e] = yf[e]; accb[e] = sb[e] + ws[WS_AF + e]; }
             const float t0 = yf[6 + 3 * c], t1 = yf[7 + 3 * c], t2 = yf[8 + 3 * c];
-            const float *mi = ws + WS_MI + c * 24;
+            float mi[24];
+            const smaddr_t mi_a = sm_addr(ws + WS_MI + c * 24);
+#pragma unroll
+            for (int e = 0; e < 6; e++) { const float4 v4 = lds128(mi_a + 16u * e); mi[4 * e] = v4.x; mi[4 * e + 1] = v4.y; mi[4 * e + 2] = v4.z; mi[4 * e + 3] = v4.w; }
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 float a = ws[WS_AF + 6 + 3 * c + k] + mi[tri(k, 0)] * t0 + mi[tri(k, 1)] * t1 + mi[tri(k, 2)] * t2;
