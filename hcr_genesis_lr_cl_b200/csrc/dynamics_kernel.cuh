@@ -25,8 +25,10 @@
 #include "task_dev.cuh"
 
 #ifndef DYN_WARPS_PER_BLOCK
-#define DYN_WARPS_PER_BLOCK 7
-#endif
+#define DYN_WARPS_PER_BLOCK 14     // x DYN_MIN_BLOCKS = 2 CTAs per SM: 28 envs per SM, 4096 envs in one wave of 293 CTAs.  Round 1's kernel
+#endif                             // preferred 7 x 4; the current one measures 14 x 2 ahead at every env count (profiles/r2ak_sweep_dynamics_cta_shape.log:
+                                   // dynamics kernel 0.1454 / 0.1414 / 0.1474 ms for 7x4 / 14x2 / 28x1 at 4096 envs, 1.95 / 1.84 / 1.95 ms at 65 536,
+                                   // where CTAs in different phases compete for an SM's instruction cache)
 // The substep body is ~7k SASS instructions of mostly straight-line code (~110 KB), larger than the 32 KB L1.5
 // instruction cache: warps that drift apart each stream it from L2 and the kernel becomes instruction-fetch bound
 // (ncu: stall_no_instruction on top, profiles/r1b).  A CTA barrier at the top of a substep and after its
@@ -47,10 +49,10 @@
 #define PHASE_SYNC_C() do { if (DYN_SYNC_MASK & 4) PHASE_SYNC(); } while (0)
 #define PHASE_SYNC_D() do { if (DYN_SYNC_MASK & 8) PHASE_SYNC(); } while (0)
 #define PHASE_SYNC_E() do { if (DYN_SYNC_MASK & 16) PHASE_SYNC(); } while (0)
-#ifndef DYN_MIN_BLOCKS
 #define DYN_MODE_SIM_ONLY 1        // b200_simulator_step (plugin mode): no pre-step book-keeping
 #define DYN_MODE_LATE_ACTIONS 2    // the action buffer is filled by fetch_actions_kernel, this launch is its programmatic dependent
-#define DYN_MIN_BLOCKS 4      // resident CTAs per SM the register allocator must allow: 4 x 7 warps = 28 envs per SM at 72 regs/thread
+#ifndef DYN_MIN_BLOCKS
+#define DYN_MIN_BLOCKS 2      // resident CTAs per SM the register allocator must allow: 2 x 14 warps = 28 envs per SM at 72 regs/thread
 #endif
 
 // ---- per-warp shared scratch (floats) ----
