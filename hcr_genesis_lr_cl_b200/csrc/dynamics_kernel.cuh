@@ -40,9 +40,12 @@
 #define PHASE_SYNC()
 #endif
 #ifndef DYN_SYNC_MASK
-#define DYN_SYNC_MASK 17          // which of the five phase barriers are kept: A top of the substep, B after FK, C before collision, D before
-                                  // the rows, E after the PGS.  A + E do all the good (profiles/r1B_sweep_sync_mask.log: none 0.313, A 0.284,
-                                  // A+E 0.281, all five 0.284 ms per step)
+#define DYN_SYNC_MASK 16          // which of the five phase barriers are kept: A top of the substep, B after FK, C before collision, D before
+                                  // the rows, E after the solve.  Round 1: A + E did all the good (profiles/r1B_sweep_sync_mask.log: none 0.313,
+                                  // A 0.284, A+E 0.281, all five 0.284 ms per step); with the current kernel E alone is ahead
+                                  // (profiles/r2ao_sweep_sync_mask.log: dynamics kernel 0.1414 / 0.1393 / 0.1423 ms for A+E / E / all five at
+                                  // 4096 envs, 1.837 / 1.806 / 1.867 ms at 65 536): the integration between E and the next substep's top is short
+                                  // and uniform, so A re-aligns warps that E has just aligned
 #endif
 #define PHASE_SYNC_A() do { if (DYN_SYNC_MASK & 1) PHASE_SYNC(); } while (0)
 #define PHASE_SYNC_B() do { if (DYN_SYNC_MASK & 2) PHASE_SYNC(); } while (0)
