@@ -7,19 +7,24 @@
 //   scene.step() of the third-party engine legged_gym/simulator/genesis_simulator.py:29    (formulation: DESIGN.md)
 //   get_links_pos/vel/net_contact_force    legged_gym/simulator/genesis_simulator.py:49-51
 //
-// Mapping to the hardware.  A warp owns one env for all `decimation` substeps; state stays in registers between
-// substeps, HBM is touched once on entry and once on exit (~0.5 KB per env).  The robot is a star: a floating
-// base plus C serial chains of 3 revolute joints, so
-//   * lanes 0..C-1 each walk one chain (FK, RNE bias, CRBA) with all spatial quantities expressed about the
-//     base origin in world axes -- composite inertias and forces then add without any frame transforms;
+// Mapping to the hardware.  A warp owns one env for all `decimation` substeps; the env's state is parked in the warp's
+// shared-memory scratch between phases, HBM is touched once on entry and once on exit (~1.3 KB per env).  The robot is a
+// star: a floating base plus C serial chains of 3 revolute joints, so
+//   * the chains are walked body by body for what must follow the chain (frames, velocities, velocity-product
+//     accelerations; every lane walks one, lanes >= C shadow the last) with all spatial quantities expressed about the base
+//     origin in world axes -- composite inertias and forces then add without any frame transforms -- and the body-local
+//     half of the RNE (world inertia, momenta, bias wrench) is done by ONE LANE PER BODY, all bodies at once;
 //   * the mass matrix is an arrowhead [diag(D_c) B; B^T M_bb]: each chain lane inverts its own 3x3 block, the
-//     6x6 Schur complement is reduced with shuffles and factorised redundantly by every lane (no sync needed);
+//     6x6 Schur complement is summed through shared memory and factorised redundantly by every lane (no sync needed);
 //   * collision spheres are tested two per lane against the L2-resident int16 heightfield, the active set is
 //     compacted with ballots;
-//   * each of the <=32 constraint rows (3 per contact + joint limits + frictionloss) lives in one lane: the lane
-//     solves M y = J^T for its row, forms its column of A = J M^-1 J^T, and the projected Gauss-Seidel sweep
-//     broadcasts one delta per row with a shuffle (friction-cone projection per contact);
-//   * per-warp scratch (frames, M^-1 factors, J rows, A) is staged in shared memory, the robot model once per CTA.
+//   * each of the <=32 constraint rows (3 per contact + joint limits + frictionloss) lives in one lane: the lane forms
+//     rb = Jb - G^T Jl, yb = S^-1 rb and D^-1 Jl for its row (never the chain parts of M^-1 J^T for the other chains) and
+//     its column of A = J M^-1 J^T; the projected BLOCK Gauss-Seidel sweep solves a contact's three rows together from three
+//     shuffled residuals (friction-cone projection per contact), unrolled over the <= 8 contacts;
+//   * per-warp scratch (frames, M^-1 factors, J rows, A) is staged in shared memory, the robot model once per CTA;
+//     CTAs of 14 warps, two per SM: 28 envs per SM, 4096 envs in one wave.
+// Redundancy ACROSS lanes is free on a SIMT machine; what costs is repetition ALONG the instruction stream.
 // The kernel is latency/issue bound, not HBM bound; tensor cores do not apply.
 #pragma once
 #include "task_dev.cuh"
