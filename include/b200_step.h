@@ -310,7 +310,11 @@ int b200_env_post_step(B200Handle *h, long long step_counter, float cmd_vx_lo, f
  * (mapped host memory: a copy kernel overlapped with the dynamics kernel's first phase, no copy-engine operation; the buffer
  * must stay untouched until the stream has passed the call, as with an asynchronous copy) --, then b200_dynamics_step and
  * b200_env_post_step(PHASE_ALL), then hands back rew_buf ([N] fp32),
- * reset_buf and time_out_buf ([N] bool bytes) into the given pinned host buffers (each may be NULL).  Everything is
+ * reset_buf and time_out_buf ([N] bool bytes) into the given pinned host buffers (each may be NULL; when the three are one
+ * 16-byte aligned slab rew | reset | time_out of at most 64 KB, laid out like the device side, the env kernel's last CTA writes
+ * it into the mapped host memory itself, otherwise cudaMemcpyAsync does).  Environment switches, read at b200_create:
+ * B200_ZERO_COPY_ACTIONS = 2 (default: staging copy kernel + programmatic dependent launch) | 1 (every env's warp reads its
+ * actions in place) | 0 (copy engine); B200_ZERO_COPY_RESULTS = 1 (default) | 0 (copy engine).  Everything is
  * enqueued on `cuda_stream`; nothing is synchronised -- the caller waits on the stream before reading the host buffers.
  * This is the call the rollout loop makes (on_policy_runner.py:118-139: env.step(actions) followed by host reads). */
 int b200_env_step(B200Handle *h, const float *actions, int actions_on_host, long long step_counter, float cmd_vx_lo, float cmd_vx_span,
