@@ -1002,18 +1002,22 @@ __device__ void dynamics_warp(const TaskDev &T, const B200Buffers &B, const Terr
                 accl[k] = a;
             }
         }
-        {
-            float *fv = ws + WS_FV + lane * 4;
-            const float fz = lane < 3 * nc ? f : 0.f;
-            fv[0] = fz * dir.x; fv[1] = fz * dir.y; fv[2] = fz * dir.z; fv[3] = __int_as_float(lane < 3 * nc ? rlink : -1);
-        }
-        __syncwarp();
-        for (int e = lane; e < 3 * L; e += 32) ws[WS_LF + e] = 0.f;
-        __syncwarp();
-        if (lane < 3) {                        // contact order, one component per lane: deterministic accumulation per link
-            for (int c2 = 0; c2 < nc; c2++) {
-                const float *fv = ws + WS_FV + 12 * c2;
-                ws[WS_LF + 3 * __float_as_int(fv[3]) + lane] += fv[lane] + fv[4 + lane] + fv[8 + lane];
+        // net contact force per link: what get_links_net_contact_force returns after the decimation loop
+        // (genesis_simulator.py:51) is the LAST substep's, so only that one is assembled
+        if (sub == T.i[TI_DECIMATION] - 1) {
+            {
+                float *fv = ws + WS_FV + lane * 4;
+                const float fz = lane < 3 * nc ? f : 0.f;
+                fv[0] = fz * dir.x; fv[1] = fz * dir.y; fv[2] = fz * dir.z; fv[3] = __int_as_float(lane < 3 * nc ? rlink : -1);
+            }
+            __syncwarp();
+            for (int e = lane; e < 3 * L; e += 32) ws[WS_LF + e] = 0.f;
+            __syncwarp();
+            if (lane < 3) {                    // contact order, one component per lane: deterministic accumulation per link
+                for (int c2 = 0; c2 < nc; c2++) {
+                    const float *fv = ws + WS_FV + 12 * c2;
+                    ws[WS_LF + 3 * __float_as_int(fv[3]) + lane] += fv[lane] + fv[4 + lane] + fv[8 + lane];
+                }
             }
         }
         // semi-implicit Euler on the parked state: reload, advance, park again
