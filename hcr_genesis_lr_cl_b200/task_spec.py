@@ -395,6 +395,10 @@ class TaskSpec:
         def to_dict(o):
             return {k: getattr(o, k) for k in dir(o) if not k.startswith("_") and not callable(getattr(o, k))}
 
+        if getattr(getattr(cfg, "sensor", None), "add_depth", False):
+            # GenesisSimulator renders depth images when asked to (genesis_simulator.py:135-138, 316-317); this backend has no
+            # camera (north_star keeps legged_gym/warp out of the path): refuse instead of handing out a task without its sensor
+            raise ValueError("cfg.sensor.add_depth = True: depth sensors are outside the B200 backend")
         t, a, c, d, r, e = cfg.terrain, cfg.asset, cfg.commands, cfg.domain_rand, cfg.rewards, cfg.env
         n, ns = cfg.normalization, cfg.noise
         stiff, damp = cfg.control.stiffness, cfg.control.damping

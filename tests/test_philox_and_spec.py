@@ -114,3 +114,14 @@ def test_generated_env_presets_are_current():
     gen = importlib.util.module_from_spec(sp)
     sp.loader.exec_module(gen)
     assert open(gen.path()).read() == gen.render(), "run tools/gen_env_presets.py"
+
+
+def test_depth_sensor_configs_are_refused_loudly():
+    """A cfg that asks for depth images (sensor.add_depth, genesis_simulator.py:135-138) must not silently get a backend without
+    a camera."""
+    from types import SimpleNamespace
+    import pytest
+    from hcr_genesis_lr_cl_b200.task_spec import TaskSpec
+    cfg = SimpleNamespace(sensor=SimpleNamespace(add_depth=True))
+    with pytest.raises(ValueError, match="depth"):
+        TaskSpec.from_reference_cfg(cfg, "go2_ts")
