@@ -26,9 +26,9 @@ pool = [torch.randn(N, 12, generator=g).cuda() for _ in range(16)]
 lib = _cabi.load_library()
 lib.b200_debug_dyn_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
 buf = np.zeros((N, 4), np.uint64)
-for i in range(120):
+for i in range(420):
     env.step(pool[i % 16])
-    if i in (30, 60, 119):
+    if i in (419,):
         lib.b200_debug_dyn_timing(buf.ctypes.data_as(ctypes.c_void_p), N)
         t0 = buf[:, 0].min()
         start, end = (buf[:, 0] - t0).astype(np.float64) / 1e3, (buf[:, 1] - t0).astype(np.float64) / 1e3
@@ -57,5 +57,23 @@ for i in range(120):
         A = np.vstack([rows, np.ones(N)]).T
         k, b = np.linalg.lstsq(A, dur, rcond=None)[0]
         print(f"   duration ~ {b:.1f} us + {k * 1e3:.2f} ns x sweep-rows (corr {c:.2f})")
+        # how the block scheduler placed the CTAs (the cost-ordered slots assume: CTA i of a round on SM i, rounds of one CTA per SM)
+        ctas = np.unique(cta)
+        cta_sm = np.array([smid[cta == c][0] for c in ctas])
+        nsm = len(np.unique(smid))
+        first = cta_sm[:nsm]
+        print(f"   placement: CTAs 0..{nsm - 1} on {len(np.unique(first))} distinct SMs; second-round CTA {nsm}+k on the SM of CTA k for "
+              f"{int((cta_sm[nsm:2 * nsm] == first[:len(cta_sm[nsm:2 * nsm])]).sum())} of {len(cta_sm[nsm:2 * nsm])}; first 16 SM ids: {first[:16].tolist()}; "
+              f"SM ids of CTAs {nsm}..{nsm + 15}: {cta_sm[nsm:nsm + 16].tolist()}")
+        sm_ids = np.unique(smid)
+        order = np.argsort(sm_end)
+        print("   slowest SMs (sm, envs, sum sweep-rows, last end us, its CTAs): " +
+              "; ".join(f"{sm_ids[j]}, {sm_cnt[j]}, {sm_rows[j]:.0f}, {sm_end[j]:.0f}, {np.unique(cta[smid == sm_ids[j]]).tolist()}" for j in order[-4:]))
+        print("   fastest full SMs: " +
+              "; ".join(f"{sm_ids[j]}, {sm_cnt[j]}, {sm_rows[j]:.0f}, {sm_end[j]:.0f}, {np.unique(cta[smid == sm_ids[j]]).tolist()}" for j in [q for q in order if sm_cnt[q] == sm_cnt.max()][:4]))
+        pick = [0, 1, 2, 37, 74, 110, 146, 147, 148, 149, 185, 220, 256, 290, 291, 292]
+        print("   sweep-rows per CTA (index: sum over its envs, max env): " + "; ".join(f"{c}: {rows[cta == c].sum():.0f}, {rows[cta == c].max():.0f}" for c in pick if (cta == c).any()))
+        print(f"   per-SM sum of sweep-rows: min {sm_rows.min():.0f} p50 {np.median(sm_rows):.0f} max {sm_rows.max():.0f}; last end = "
+              f"{np.polyfit(sm_rows, sm_end, 1)[1]:.1f} us + {np.polyfit(sm_rows, sm_end, 1)[0] * 1e3:.2f} ns x (sum sweep-rows)")
 os.environ.pop("B200_NVCC_EXTRA")
 build.build(force=True)
