@@ -50,7 +50,7 @@
                                   // A 0.284, A+E 0.281, all five 0.284 ms per step); with the current kernel E alone is ahead
                                   // (profiles/r2ao_sweep_sync_mask.log: dynamics kernel 0.1414 / 0.1393 / 0.1423 ms for A+E / E / all five at
                                   // 4096 envs, 1.837 / 1.806 / 1.867 ms at 65 536): the integration between E and the next substep's top is short
-                                  // and uniform, so A re-aligns warps that E has just aligned
+                                  // and uniform, so A re-aligns warps that E has just aligned; no barrier at all 0.1617 ms, only C 0.1516, only D 0.1531
 #endif
 #define PHASE_SYNC_A() do { if (DYN_SYNC_MASK & 1) PHASE_SYNC(); } while (0)
 #define PHASE_SYNC_B() do { if (DYN_SYNC_MASK & 2) PHASE_SYNC(); } while (0)
