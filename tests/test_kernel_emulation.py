@@ -287,3 +287,29 @@ def test_emulated_dynamics_order_is_a_permutation(N):
             assert sorted(envs.tolist()) == list(range(N)), (N, t, envs)
     cost = env.simulator._buf["dyn_cost"].numpy()
     assert (cost >= 0).all()
+
+
+def test_emulated_host_buffer_step_with_misaligned_buffers_takes_the_copy_path():
+    """Host buffers that are not 16-byte aligned (views at an odd offset of a larger pinned allocation) cannot be read / written
+    with the 16-byte accesses of the zero-copy paths: b200_env_step must fall back to copies and still hand back the same values."""
+    import numpy as np
+    import torch
+    from emu_backend import EmuFusedLeggedEnv
+    from hcr_genesis_lr_cl_b200 import task_spec as TS
+    spec = TS.PRESETS["go2"]()
+    N = 16
+    a_env = EmuFusedLeggedEnv(spec, N, torch.device("cpu"))
+    b_env = EmuFusedLeggedEnv(spec, N, torch.device("cpu"))
+    a_env.reset(); b_env.reset()
+    slab = torch.zeros(6 * N + 4, dtype=torch.uint8)[4:]                 # 4 bytes into the allocation
+    rew, rst, tmo = slab[:4 * N].view(torch.float32), slab[4 * N:5 * N].view(torch.bool), slab[5 * N:].view(torch.bool)
+    big = torch.zeros(N * spec.num_actions + 1, dtype=torch.float32)
+    rng = np.random.default_rng(9)
+    for t in range(3):
+        act = torch.from_numpy(rng.normal(size=(N, spec.num_actions)).astype(np.float32))
+        host_act = big[1:].view(N, spec.num_actions)                     # 4 bytes into the allocation
+        host_act.copy_(act); host_act._emu_host = True
+        out_a = a_env.step(act)
+        out_b = b_env.step_host(host_act, rew, rst, tmo)
+        assert torch.equal(out_a[0], out_b[0])
+        assert torch.equal(rew, a_env.rew_buf) and torch.equal(rst, a_env.reset_buf) and torch.equal(tmo, a_env.time_out_buf)
